@@ -1,0 +1,150 @@
+/*
+ * vsgpu.h -- C ABI of libvsgpu, the B200-native (sm_100a) scoring path for VectorSearch.
+ *
+ * The reference (panghy/vectorsearch) has no plugin boundary for this path: the hot functions
+ * are public static Java methods.  This header is the boundary a Java maintainer binds through
+ * the FFM API (java.lang.foreign) or JNI; every entry point names the reference code it
+ * replaces (J/ = src/main/java/io/github/panghy/vectorsearch/).  See INTEGRATION.md for the
+ * Java-side stubs.
+ *
+ * Conventions
+ *   - every function returns an int32 status: VS_OK or a negative VS_E* code;
+ *     vs_last_error() returns a thread-local message for the last failure on this thread.
+ *     VS_EINVAL maps to IllegalArgumentException, VS_EEMPTY to IndexOutOfBoundsException,
+ *     everything else to IllegalStateException.
+ *   - pointer arguments are caller-owned HOST memory, read or written only during the call,
+ *     unless the function name ends in _dev (then they are DEVICE pointers and the work is
+ *     enqueued on the given CUDA stream without synchronising).
+ *   - device memory is owned by the library behind opaque uint64 handles.
+ *   - layouts are row-major and contiguous: vectors fp32 little-endian (bit-identical to
+ *     FloatPacker bytes, J/util/FloatPacker.java:21-39); codes uint8[n][M]; centroids
+ *     float[M][K][subDim] (the flattened Java float[][][], equal to the PQCodebook blobs
+ *     concatenated, J/tasks/SegmentBuildService.java:325-338); ids are int64 row indices
+ *     (segment id_base + local row); scores are IEEE doubles carrying the reference's
+ *     arithmetic (score = -l2 for L2, = similarity for COSINE, J/fdb/FdbVectorIndex.java:687-693).
+ *   - one process drives one GPU (vs_init(device)); multi-GPU runs use one process per GPU
+ *     and shard rows by range (see vectorsearch_b200/sharded.py).
+ *   - thread-safe and re-entrant: each calling thread gets its own stream and scratch.
+ *   - there is NO CPU fallback: every entry point fails with VS_ECUDA when no device is usable.
+ */
+#ifndef VSGPU_H
+#define VSGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VS_OK 0
+#define VS_EINVAL (-1)   /* bad argument (IllegalArgumentException) */
+#define VS_ENOMEM (-2)   /* host or device allocation failed */
+#define VS_ECUDA (-3)    /* CUDA runtime error / no usable device */
+#define VS_EHANDLE (-4)  /* unknown or freed handle */
+#define VS_ESTATE (-5)   /* operation needs something the segment does not have (e.g. PQ) */
+#define VS_EEMPTY (-6)   /* empty input where the reference throws IndexOutOfBounds */
+
+#define VS_METRIC_L2 0      /* J/config/VectorIndexConfig.Metric.L2 */
+#define VS_METRIC_COSINE 1  /* J/config/VectorIndexConfig.Metric.COSINE */
+
+/* ---- lifecycle ------------------------------------------------------------------------- */
+int32_t vs_version(void);
+const char* vs_last_error(void);
+/* Binds the calling process to one CUDA device.  Fails with VS_ECUDA if there is none. */
+int32_t vs_init(int32_t device);
+int32_t vs_shutdown(void);
+/* Lane count of the JVM's FloatVector.SPECIES_PREFERRED being reproduced (J/util/Distances.java:15):
+ * 16 (AVX-512, default), 8 (AVX2), 4 (NEON/SSE).  Affects only the low-order bits of scores. */
+int32_t vs_set_simd_lanes(int32_t lanes);
+int32_t vs_get_simd_lanes(void);
+/* SM count, and bytes of free / total device memory */
+int32_t vs_device_info(int32_t* sm_count, int64_t* free_bytes, int64_t* total_bytes);
+
+/* ---- pair operations: the DistanceAndPqBenchmark surface -------------------------------------
+ * Each call is one tiny kernel launch; they exist for API/known-answer parity, the throughput
+ * path is the segment API below. */
+int32_t vs_l2(const float* a, const float* b, int32_t len, double* out);          /* Distances.java:31-33 */
+int32_t vs_l2_squared(const float* a, const float* b, int32_t len, double* out);  /* :48-64, :77-94 */
+int32_t vs_dot(const float* a, const float* b, int32_t len, double* out);         /* :103-118 */
+int32_t vs_norm(const float* a, int32_t len, double* out);                        /* :126-140 */
+int32_t vs_cosine(const float* a, const float* b, int32_t len, double* out);      /* :149-153 */
+/* PqEncoder.encode, J/pq/PqEncoder.java:18-37 */
+int32_t vs_pq_encode(const float* centroids, int32_t M, int32_t K, int32_t subDim, const float* v,
+                     uint8_t* codes_out);
+/* pqLutDistance of the JMH suite (float LUT, float sum), B/DistanceAndPqBenchmark.java:116-123 */
+int32_t vs_pq_lut_distance(const float* lut, int32_t M, int32_t K, const uint8_t* codes, float* out);
+/* buildLut, J/fdb/FdbVectorIndex.java:1067-1079 -> double[M][K] */
+int32_t vs_build_lut(const float* centroids, int32_t M, int32_t K, int32_t subDim, const float* q,
+                     double* lut_out);
+/* pqApproxDistance over n code rows, J/fdb/FdbVectorIndex.java:1057-1065 */
+int32_t vs_pq_approx_distance(const double* lut, int32_t M, int32_t K, const uint8_t* codes,
+                              int64_t n, double* out);
+
+/* ---- segment residency ---------------------------------------------------------------------
+ * A segment is a row range of vectors resident in HBM (plus, once sealed, its PQ codebook and
+ * codes).  skip_mask (nullable, one byte per row, non-zero = skip) carries "deleted or gid
+ * missing" (J/fdb/FdbVectorIndex.java:681,696,1000,1022). */
+int32_t vs_segment_upload(const float* rows, int64_t n, int32_t d, const uint8_t* skip_mask,
+                          int64_t id_base, uint64_t* handle_out);
+/* Synthetic rows generated on the device: element (r, c) is draw (first_row + r) * d + c of
+ * new java.util.Random(seed), mapped as nextFloat()*2f-1f (B/DistanceAndPqBenchmark.java:127-133). */
+int32_t vs_segment_generate(int64_t seed, int64_t first_row, int64_t n, int32_t d, int64_t id_base,
+                            uint64_t* handle_out);
+int32_t vs_segment_set_skip(uint64_t h, const uint8_t* skip_mask /* nullable clears it */);
+int32_t vs_segment_info(uint64_t h, int64_t* n, int32_t* d, int32_t* M, int32_t* K, int64_t* id_base);
+int32_t vs_segment_download_rows(uint64_t h, int64_t first, int64_t count, float* rows_out);
+/* Attach a codebook and codes; codes == NULL encodes the resident rows on the device. */
+int32_t vs_segment_attach_pq(uint64_t h, const float* centroids, int32_t M, int32_t K,
+                             const uint8_t* codes);
+int32_t vs_segment_download_codes(uint64_t h, int64_t first, int64_t count, uint8_t* codes_out);
+int32_t vs_segment_free(uint64_t h);
+
+/* ---- query operations --------------------------------------------------------------------
+ * Outputs are [nq][k] (or [nq][n_cand]); counts_out[i] entries of row i are valid, the rest
+ * are id -1 / score NaN. */
+/* searchBruteForceSegment scoring + stable sort + subList(0,k), J/fdb/FdbVectorIndex.java:676-721 */
+int32_t vs_bruteforce_topk(uint64_t h, const float* q, int32_t nq, int32_t k, int32_t metric,
+                           int64_t* ids_out, double* scores_out, int32_t* counts_out);
+/* buildLut + full ADC scan + stable ascending sort + first n_cand, :741,:754-769,:820-822 */
+int32_t vs_adc_topk(uint64_t h, const float* q, int32_t nq, int32_t n_cand, int64_t* ids_out,
+                    double* approx_out, int32_t* counts_out);
+/* fetchExactAndScore: candidates scored in the given order, ties keep it, :997-1043 */
+int32_t vs_rerank_topk(uint64_t h, const float* q, const int64_t* cand_ids, int32_t n_cand, int32_t k,
+                       int32_t metric, int32_t normalize_on_read, int64_t* ids_out,
+                       double* scores_out, int32_t* count_out);
+/* ADC top n_cand followed by exact re-rank to k in one call (config C4) */
+int32_t vs_adc_rerank_topk(uint64_t h, const float* q, int32_t nq, int32_t n_cand, int32_t k,
+                           int32_t metric, int32_t normalize_on_read, int64_t* ids_out,
+                           double* scores_out, int32_t* counts_out);
+/* cross-segment merge: stable sort by score descending of lists concatenated in segment order,
+ * first k, J/fdb/FdbVectorIndex.java:432-437 */
+int32_t vs_merge_topk(const int64_t* ids, const double* scores, int64_t total, int32_t k,
+                      int64_t* ids_out, double* scores_out, int32_t* count_out);
+
+/* ---- build operations ----------------------------------------------------------------------
+ * Rows come from host memory (rows != NULL) or from a resident segment (rows == NULL, h != 0). */
+/* PqTrainer.train, J/pq/PqTrainer.java:28-91 (production call: iterations 5, seed 42,
+ * J/tasks/SegmentBuildService.java:180) */
+int32_t vs_pq_train(const float* rows, uint64_t h, int64_t n, int32_t d, int32_t M, int32_t K,
+                    int32_t iterations, int64_t seed, float* centroids_out);
+/* PqEncoder.encode over n rows, J/pq/PqEncoder.java:18-37, J/tasks/SegmentBuildService.java:301 */
+int32_t vs_pq_encode_batch(const float* centroids, int32_t M, int32_t K, int32_t subDim,
+                           const float* rows, uint64_t h, int64_t n, uint8_t* codes_out);
+
+/* ---- device-side (stream) variants -------------------------------------------------------------
+ * Same semantics; q / outputs are DEVICE pointers, work is enqueued on `stream` (a cudaStream_t)
+ * and NOT synchronised.  Used by the multi-GPU coordinator and for kernel-only timing. */
+int32_t vs_bruteforce_topk_dev(uint64_t h, const float* d_q, int32_t nq, int32_t k, int32_t metric,
+                               int64_t* d_ids, double* d_scores, int32_t* d_counts, void* stream);
+int32_t vs_adc_topk_dev(uint64_t h, const float* d_q, int32_t nq, int32_t n_cand, int64_t* d_ids,
+                        double* d_approx, int32_t* d_counts, void* stream);
+int32_t vs_adc_rerank_topk_dev(uint64_t h, const float* d_q, int32_t nq, int32_t n_cand, int32_t k,
+                               int32_t metric, int32_t normalize_on_read, int64_t* d_ids,
+                               double* d_scores, int32_t* d_counts, void* stream);
+/* number of kernels this library has launched so far in this process (for gpu_launches) */
+int64_t vs_kernel_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

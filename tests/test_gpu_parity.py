@@ -1,0 +1,324 @@
+"""GPU parity: libvsgpu (through its C ABI) against the CPU oracle on identical seeded inputs.
+
+Bar (BASELINE.json north_star): ids and PQ codes bit-exact; scores are doubles carrying the
+reference's own arithmetic, so they are compared bit-exactly too (tolerance 0).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def vs():
+    import vectorsearch_b200 as v
+
+    v.init(0)
+    yield v
+    v.set_simd_lanes(16)
+
+
+def _same(a, b):
+    """Bit-exact equality; NaN matches NaN (Java does not distinguish NaN payloads in ordering)."""
+    a, b = np.asarray(a), np.asarray(b)
+    if a.shape != b.shape:
+        return False
+    if a.dtype != np.float64:
+        return np.array_equal(a, b)
+    na, nb = np.isnan(a), np.isnan(b)
+    return np.array_equal(na, nb) and np.array_equal(a[~na].view(np.uint64), b[~nb].view(np.uint64))
+
+
+# ---- Distances: T/util/DistancesTest.java shapes, all lane models ---------------------------------------
+@pytest.mark.parametrize("lanes", [16, 8, 4])
+@pytest.mark.parametrize("dim", [1, 3, 7, 16, 17, 128, 768, 1000])
+def test_pair_ops_bit_exact(vs, oracle, dim, lanes):
+    vs.set_simd_lanes(lanes)
+    oracle.set_lanes(lanes)
+    try:
+        a = oracle.gen_floats(42 + dim, 0, dim)
+        b = oracle.gen_floats(42 + dim, dim, dim)
+        D = vs.Distances
+        assert D.l2_squared(a, b) == oracle.l2_squared(a, b)
+        assert D.l2(a, b) == oracle.l2(a, b)
+        assert D.dot(a, b) == oracle.dot(a, b)
+        assert D.norm(a) == oracle.norm(a)
+        assert D.cosine(a, b) == oracle.cosine(a, b)
+    finally:
+        vs.set_simd_lanes(16)
+        oracle.set_lanes(16)
+
+
+def test_known_answers(vs):
+    D = vs.Distances  # DistancesTest.java:36-47, :100-125
+    assert D.l2_squared([1, 2, 3], [4, 6, 3]) == 25.0
+    assert D.l2([1, 2, 3], [4, 6, 3]) == 5.0
+    assert D.cosine([0, 0, 0], [1, 2, 3]) == 0.0
+    assert D.dot([1, 0, 0, 0], [0, 1, 0, 0]) == 0.0
+    assert D.l2_squared([0, 1, 2, 3, 4], [9, 9, 2, 3, 9], 2, 2, 2) == 0.0  # offset overload :77-94
+    cent = np.array([[[0, 0], [1, 1]], [[0, 0], [2, 2]]], dtype=np.float32)  # PqEncoderTest.java:12-23
+    assert vs.PqEncoder.encode(cent, [0.1, 0.1, 1.9, 2.1]).tolist() == [0, 1]
+    with pytest.raises(ValueError):  # PqTrainerTest.java: dimension % m != 0
+        vs.PqTrainer.train(np.zeros((3, 3), np.float32), 3, 2, 2, 1, 1)
+    with pytest.raises(IndexError):
+        vs.PqTrainer.train(np.zeros((0, 4), np.float32), 4, 2, 2, 1, 1)
+
+
+def test_jmh_state_values(vs, oracle):
+    from tests.test_oracle_golden import jmh_pq_state
+
+    cent, vec, lut, codes = jmh_pq_state(oracle)
+    assert vs.PqEncoder.encode(cent, vec).tolist() == [81, 78, 7, 3, 2, 166, 155, 121, 147, 65, 197, 171,
+                                                      102, 180, 200, 175]
+    assert abs(vs.pq_lut_distance(lut, codes) - 90.38559) < 5e-5
+    assert _same(vs.build_lut(cent, vec), oracle.build_lut(cent, vec))
+
+
+def test_generator_matches_java_random(vs, oracle):
+    seg = vs.Segment.generate(42, 1000, 3001, 24)
+    try:
+        assert np.array_equal(seg.rows(), oracle.gen_rows(42, 1000, 3001, 24))
+    finally:
+        seg.free()
+
+
+# ---- brute force ----------------------------------------------------------------------------------------
+def _check_bruteforce(vs, oracle, rows, q, k, metric, skip=None, id_base=0):
+    seg = vs.Segment.upload(rows, skip=skip, id_base=id_base)
+    try:
+        ids, sc = seg.bruteforce_topk(q, k, metric)
+    finally:
+        seg.free()
+    oi, os_, _ = oracle.bruteforce_topk(rows, q, k, metric, skip=skip, threads=4)
+    assert np.array_equal(ids, oi + id_base), (ids[:10], oi[:10])
+    assert _same(sc, os_)
+
+
+@pytest.mark.parametrize("metric", [0, 1])
+@pytest.mark.parametrize("n,d,k", [(20000, 128, 10), (5000, 768, 50), (3000, 100, 10), (4000, 6, 7),
+                                   (1000, 16, 1000), (7, 128, 10), (33, 32, 1), (50000, 64, 100)])
+def test_bruteforce_matches_oracle(vs, oracle, n, d, k, metric):
+    rows = oracle.gen_rows(42, 0, n, d)
+    q = oracle.gen_floats(43, 0, d)
+    _check_bruteforce(vs, oracle, rows, q, k, metric)
+
+
+@pytest.mark.parametrize("lanes", [8, 4])
+@pytest.mark.parametrize("metric", [0, 1])
+def test_bruteforce_other_lane_models(vs, oracle, lanes, metric):
+    vs.set_simd_lanes(lanes)
+    oracle.set_lanes(lanes)
+    try:
+        rows = oracle.gen_rows(5, 0, 6000, 72)
+        q = oracle.gen_floats(6, 0, 72)
+        _check_bruteforce(vs, oracle, rows, q, 20, metric)
+    finally:
+        vs.set_simd_lanes(16)
+        oracle.set_lanes(16)
+
+
+@pytest.mark.parametrize("metric", [0, 1])
+def test_bruteforce_ties_nan_skip(vs, oracle, metric):
+    rows = oracle.gen_rows(11, 0, 4096, 32)
+    rows[100:400] = rows[7]          # 300 exact duplicates: ties resolve to the lowest row
+    rows[2000] = rows[7]
+    rows[50, 3] = np.nan             # NaN score sorts first (Double.compare)
+    rows[3000, 0] = np.nan
+    rows[9] = 0.0                    # zero norm: cosine 0.0
+    q = rows[7].copy()
+    _check_bruteforce(vs, oracle, rows, q, 40, metric)
+    skip = np.zeros(4096, np.uint8)
+    skip[[7, 50, 101, 102, 4095]] = 1  # deleted / gid missing
+    _check_bruteforce(vs, oracle, rows, q, 40, metric, skip=skip, id_base=1_000_000_007)
+    _check_bruteforce(vs, oracle, rows, np.zeros(32, np.float32), 5, metric)  # zero query
+
+
+def test_bruteforce_query_batch(vs, oracle):
+    rows = oracle.gen_rows(42, 0, 8000, 128)
+    qs = oracle.gen_rows(43, 0, 5, 128)
+    seg = vs.Segment.upload(rows)
+    try:
+        ids, sc, cn = seg.bruteforce_topk(qs, 10)
+        for i in range(5):
+            oi, os_, _ = oracle.bruteforce_topk(rows, qs[i], 10)
+            assert cn[i] == 10 and np.array_equal(ids[i], oi) and _same(sc[i], os_)
+        # VectorIndexTest.java:599-609 + query merge :432-437
+    finally:
+        seg.free()
+    seg = vs.Segment.upload(np.array([[1, 0, 0], [0, 1, 0], [0, 0, 1], [1, 1, 0]], np.float32))
+    try:
+        ids, sc = seg.bruteforce_topk([1, 0, 0], 4)
+        mi, ms = vs.merge_topk(ids, sc, 2)
+        assert mi.tolist() == [0, 3] and ms[0] == 0.0 and ms[1] == -1.0
+    finally:
+        seg.free()
+
+
+def test_empty_segment_and_bad_args(vs):
+    seg = vs.Segment.upload(np.zeros((0, 8), np.float32))
+    try:
+        ids, sc = seg.bruteforce_topk(np.zeros(8, np.float32), 5)
+        assert ids.size == 0
+        with pytest.raises(ValueError):
+            seg.bruteforce_topk(np.zeros(8, np.float32), 0)
+        with pytest.raises(vs.VsError):
+            seg.adc_topk(np.zeros(8, np.float32), 5)  # no PQ attached
+    finally:
+        seg.free()
+
+
+# ---- PQ encode / ADC / re-rank ----------------------------------------------------------------------------
+def _pq_fixture(oracle, n, d, M, K, seed=3):
+    rows = oracle.gen_rows(seed, 0, n, d)
+    sub = d // M
+    # centroids sampled from the data (as PqTrainer's init does) so codes are well spread
+    r = oracle.random(seed + 1)
+    cent = np.zeros((M, K, sub), np.float32)
+    for s in range(M):
+        for c in range(K):
+            cent[s, c] = rows[r.next_int(n), s * sub:(s + 1) * sub]
+    return rows, cent
+
+
+@pytest.mark.parametrize("n,d,M,K", [(20000, 128, 16, 256), (3000, 64, 8, 16), (2000, 768, 16, 256),
+                                     (1500, 96, 32, 100), (500, 20, 4, 7), (900, 24, 3, 300)])
+def test_pq_encode_matches_oracle(vs, oracle, n, d, M, K):
+    rows, cent = _pq_fixture(oracle, n, d, M, K)
+    want = oracle.pq_encode_batch(cent, rows, threads=8)
+    got = vs.PqEncoder.encode_batch(cent, rows)
+    assert np.array_equal(got, want)
+    seg = vs.Segment.upload(rows)
+    try:
+        seg.attach_pq(cent)  # codes == NULL: encoded on the device from the resident rows
+        assert np.array_equal(seg.codes(), want)
+        assert np.array_equal(vs.PqEncoder.encode_batch(cent, segment=seg), want)
+    finally:
+        seg.free()
+
+
+def test_pq_encode_duplicate_centroids_and_nan(vs, oracle):
+    rows, cent = _pq_fixture(oracle, 4000, 64, 8, 64)
+    cent[:, 40] = cent[:, 3]      # duplicates: strict '<' keeps the lower index
+    cent[:, 41] = cent[:, 3]
+    cent[2, 5, 1] = np.nan        # NaN never wins
+    rows[17, 9] = np.nan          # all distances NaN in that subspace -> code 0
+    rows[18] = 1e30               # fp32 estimate overflows -> all-exact path
+    want = oracle.pq_encode_batch(cent, rows, threads=8)
+    assert np.array_equal(vs.PqEncoder.encode_batch(cent, rows), want)
+
+
+@pytest.mark.parametrize("n,d,M,K,n_cand", [(30000, 128, 16, 256, 100), (5000, 64, 8, 16, 37),
+                                            (4000, 96, 32, 100, 1000), (600, 20, 5, 7, 50), (40, 128, 16, 256, 100)])
+def test_adc_scan_matches_oracle(vs, oracle, n, d, M, K, n_cand):
+    rows, cent = _pq_fixture(oracle, n, d, M, K)
+    codes = oracle.pq_encode_batch(cent, rows, threads=8)
+    q = oracle.gen_floats(77, 0, d)
+    lut = oracle.build_lut(cent, q)
+    assert _same(vs.build_lut(cent, q), lut)
+    oi, oa = oracle.adc_topn(lut, codes, n_cand, threads=4)
+    assert _same(vs.pq_approx_distance(lut, codes[:257]), np.array([oracle.pq_approx_distance(lut, c) for c in codes[:257]]))
+    seg = vs.Segment.upload(rows, id_base=5)
+    try:
+        seg.attach_pq(cent, codes)
+        ids, ap = seg.adc_topk(q, n_cand)
+        assert np.array_equal(ids, oi + 5) and _same(ap, oa)
+        # fused ADC -> exact re-rank (C4 shape: top-100 -> top-10)
+        k = min(10, n_cand)
+        for metric in (0, 1):
+            ri, rs, _ = oracle.rerank_topk(rows, q, oi, k, metric)
+            gi, gs = seg.adc_rerank_topk(q, n_cand, k, metric)
+            assert np.array_equal(gi, ri + 5) and _same(gs, rs)
+    finally:
+        seg.free()
+
+
+def test_adc_duplicate_codes_and_large_code_values(vs, oracle):
+    rows, cent = _pq_fixture(oracle, 6000, 64, 8, 50)
+    codes = oracle.pq_encode_batch(cent, rows, threads=8)
+    codes[1000:1500] = codes[3]       # massive ties -> lowest rows first
+    codes[20, 2] = 200                # >= K: skipped by pqApproxDistance (:1061)
+    codes[21] = 255
+    q = rows[3].copy()
+    lut = oracle.build_lut(cent, q)
+    oi, oa = oracle.adc_topn(lut, codes, 300, threads=3)
+    seg = vs.Segment.upload(rows)
+    try:
+        seg.attach_pq(cent, codes)
+        ids, ap = seg.adc_topk(q, 300)
+        assert np.array_equal(ids, oi) and _same(ap, oa)
+    finally:
+        seg.free()
+
+
+@pytest.mark.parametrize("metric", [0, 1])
+def test_rerank_matches_oracle(vs, oracle, metric):
+    rows = oracle.gen_rows(21, 0, 5000, 128)
+    rows[10] = rows[11]
+    q = oracle.gen_floats(22, 0, 128)
+    r = oracle.random(5)
+    cand = np.array([r.next_int(5000) for _ in range(300)] + [10, 11, 11, 10, -1, 5000, 99999], np.int64)
+    skip = np.zeros(5000, np.uint8)
+    skip[cand[5]] = 1
+    seg = vs.Segment.upload(rows, skip=skip)
+    try:
+        for k in (1, 10, 400):
+            oi, os_, _ = oracle.rerank_topk(rows, q, cand, k, metric, skip=skip)
+            gi, gs = seg.rerank_topk(q, cand, k, metric, normalize_on_read=bool(k % 2))
+            assert np.array_equal(gi, oi) and _same(gs, os_)
+    finally:
+        seg.free()
+
+
+def test_merge_matches_oracle(vs, oracle):
+    r = np.random.default_rng(0)
+    scores = -np.abs(r.standard_normal(3000)).round(2)  # many ties
+    scores[17] = np.nan
+    ids = r.integers(0, 1 << 40, 3000)
+    for k in (1, 10, 257):
+        oi, os_ = oracle.merge_topk(ids, scores, k)
+        gi, gs = vs.merge_topk(ids, scores, k)
+        assert np.array_equal(gi, oi) and _same(gs, os_)
+
+
+# ---- PQ training -------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,d,M,K,iters", [(6000, 32, 4, 16, 5), (3000, 128, 16, 256, 2), (300, 16, 2, 64, 5),
+                                           (50, 8, 2, 40, 3), (2000, 24, 3, 10, 0)])
+def test_pq_train_bit_exact(vs, oracle, n, d, M, K, iters):
+    rows = oracle.gen_rows(31, 0, n, d)
+    want = oracle.pq_train(rows, d, M, K, iters, 42)
+    got = vs.PqTrainer.train(rows, d, M, K, iters, 42)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    seg = vs.Segment.upload(rows)
+    try:
+        got2 = vs.PqTrainer.train(None, d, M, K, iters, 42, segment=seg)
+        assert np.array_equal(got2.view(np.uint32), want.view(np.uint32))
+    finally:
+        seg.free()
+
+
+def test_pq_train_with_duplicate_rows(vs, oracle):
+    rows = oracle.gen_rows(32, 0, 400, 16)
+    rows[100:300] = rows[5]  # distinct indices, identical sub-vectors: unpredicted empty clusters -> replay waves
+    want = oracle.pq_train(rows, 16, 4, 32, 5, 42)
+    got = vs.PqTrainer.train(rows, 16, 4, 32, 5, 42)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+# ---- full-size configurations (BASELINE.json configs) ----------------------------------------------------
+def test_c2_full_size_l2_top10(vs, oracle):
+    """C2: exact L2 top-10 over 1M x 128, rows generated on the device from the Java LCG stream."""
+    n, d = 1_000_000, 128
+    seg = vs.Segment.generate(42, 0, n, d)
+    try:
+        rows = oracle.gen_rows(42, 0, n, d)
+        assert np.array_equal(seg.rows(n - 1000, 1000), rows[-1000:])
+        for qi in range(3):
+            q = oracle.gen_floats(43, qi * d, d)
+            ids, sc = seg.bruteforce_topk(q, 10)
+            oi, os_, _ = oracle.bruteforce_topk(rows, q, 10, threads=8)
+            assert np.array_equal(ids, oi) and _same(sc, os_)
+        # size-independent properties: idempotence, sortedness, a row queries itself to distance 0
+        ids2, sc2 = seg.bruteforce_topk(rows[123456], 10)
+        assert ids2[0] == 123456 and sc2[0] == 0.0 and np.all(np.diff(sc2) <= 0)
+    finally:
+        seg.free()

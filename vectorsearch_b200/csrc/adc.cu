@@ -1,0 +1,253 @@
+// adc.cu -- K5/K6: ADC lookup-table build and the full-segment ADC scan over uint8 PQ codes.
+//
+// Replaces buildLut (J/fdb/FdbVectorIndex.java:1067-1079), pqApproxDistance (:1057-1065) and the
+// sealed-segment scan + sort (:754-769, first n_cand of the ascending stable sort :820-822).
+//
+// HBM-bound on paper (M bytes per distance evaluation), shared-memory-gather-bound in practice.
+//  * LUT entries are the reference's own doubles (Distances.l2Squared on sub-vectors; with
+//    subDim < SIMD lanes that is pure fp64).  The scan keeps an fp32 image of the LUT in shared
+//    memory and sums M fp32 lookups per row: an ESTIMATE whose relative error is bounded
+//    (entries are non-negative), used only to discard rows that cannot enter the top n_cand.
+//    Rows that survive the fp32 compare are re-summed in fp64 from the real LUT in subspace
+//    order, exactly like pqApproxDistance, and ranked by (approx, row) -- so ids and distances
+//    are the reference's, ties go to the lowest row.
+//  * one thread per code row, 128-bit streaming loads, U rows in flight per thread;
+//    grid = SMs x resident CTAs, last CTA merges (same epilogue as scan.cu).
+#include "kernels.h"
+#include "topk.cuh"
+
+namespace vs {
+
+// ---- LUT build: one thread per (query, subspace, centroid) ----------------------------------------
+__global__ void build_lut_kernel(const float* __restrict__ centroids, int M, int K, int subDim,
+                                 const float* __restrict__ Q, int nq, int lanes,
+                                 double* __restrict__ lut64) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t per_q = (int64_t)M * K;
+  if (t >= per_q * nq) return;
+  const int qi = (int)(t / per_q);
+  const int e = (int)(t % per_q);
+  const int s = e / K;
+  const float* q = Q + (size_t)qi * M * subDim + (size_t)s * subDim;
+  const float* c = centroids + (size_t)e * subDim;
+  lut64[t] = ref_sum_thread<REF_L2SQ>(q, c, subDim, lanes);
+}
+
+cudaError_t launch_build_lut(const float* centroids, int M, int K, int subDim, const float* q, int nq,
+                             int lanes, double* lut64, cudaStream_t st) {
+  const int64_t total = (int64_t)M * K * nq;
+  if (total <= 0) return cudaSuccess;
+  build_lut_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(centroids, M, K, subDim, q, nq, lanes, lut64);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// pqApproxDistance: fp64 adds in subspace order, codes >= K skipped (:1061)
+__device__ __forceinline__ double adc_exact(const double* __restrict__ lut, const uint8_t* __restrict__ cr,
+                                            int M, int K) {
+  double ad = 0.0;
+  for (int s = 0; s < M; s++) {
+    const int ci = cr[s];
+    if (ci >= K) continue;
+    ad = __dadd_rn(ad, lut[(size_t)s * K + ci]);
+  }
+  return ad;
+}
+
+__global__ void approx_distance_kernel(const double* __restrict__ lut, int M, int K,
+                                       const uint8_t* __restrict__ codes, int64_t n,
+                                       double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = adc_exact(lut, codes + (size_t)i * M, M, K);
+}
+
+cudaError_t launch_approx_distance(const double* lut, int M, int K, const uint8_t* codes, int64_t n,
+                                   double* out, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  approx_distance_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(lut, M, K, codes, n, out);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// fp32 estimate vs exact fp64 sum: each fp32 LUT entry is within 2^-24 relative of the double,
+// M-1 fp32 adds of non-negative terms add 2^-24 each -> (M+1) * 2^-24; doubled for slack.
+__device__ __forceinline__ float adc_filter_threshold(const Key& thr, int M) {
+  if (key_is_empty(thr)) return __int_as_float(0x7f800000);
+  const double val = dist_from_rank_hi(thr.hi);
+  if (val != val) return __int_as_float(0x7f800000);  // k-th is NaN: every non-NaN row beats it
+  const double m = val * (1.0 + (double)(M + 2) * (1.0 / 8388608.0)) + 1e-37;
+  const float f = __double2float_ru(m);
+  return (f == __int_as_float(0x7f800000)) ? f : f32_next_up(f);
+}
+
+constexpr int ADC_KS = 256;  // shared LUT row stride: codes are bytes, entries >= K read 0
+
+// MW = M/4 words per code row (M % 4 == 0), U rows in flight per thread.
+template <int MW, int U>
+__global__ void __launch_bounds__(SCAN_THREADS)
+adc_scan_kernel(const uint8_t* __restrict__ codes, int64_t n, int K, const double* __restrict__ LUT64,
+                int k, int kp, TopkOut out) {
+  extern __shared__ __align__(16) ulonglong2 smem[];
+  constexpr int M = MW * 4;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nw = blockDim.x >> 5;
+  const int stride_keys = kp + TOPK_BUF;
+  const double* __restrict__ lut64 = LUT64 + (size_t)blockIdx.y * M * K;
+
+  WarpTopK tk;
+  tk.init(smem + (size_t)warp * stride_keys, kp, k, lane);
+  float* lut = reinterpret_cast<float*>(smem + (size_t)nw * stride_keys);
+  for (int i = threadIdx.x; i < M * ADC_KS; i += blockDim.x) {
+    const int s = i / ADC_KS, c = i % ADC_KS;
+    lut[i] = c < K ? (float)lut64[(size_t)s * K + c] : 0.0f;
+  }
+  __syncthreads();
+
+  const int64_t rows_per_batch = 32 * U;
+  const int64_t nbatches = (n + rows_per_batch - 1) / rows_per_batch;
+  const int64_t total_warps = (int64_t)gridDim.x * nw;
+  float fthr = __int_as_float(0x7f800000);
+  uint64_t seen_hi = KEY_EMPTY64, seen_lo = KEY_EMPTY64;
+
+  for (int64_t b = (int64_t)blockIdx.x * nw + warp; b < nbatches; b += total_warps) {
+    const int64_t row0 = b * rows_per_batch + lane;
+    uint32_t w[U][MW];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      int64_t r = row0 + (int64_t)u * 32;
+      r = r < n ? r : n - 1;
+      const uint8_t* p = codes + (size_t)r * M;
+      if (MW % 4 == 0) {
+#pragma unroll
+        for (int j = 0; j < MW / 4; j++) {
+          uint4 v = ld_stream_u4(reinterpret_cast<const uint4*>(p) + j);
+          w[u][4 * j + 0] = v.x; w[u][4 * j + 1] = v.y; w[u][4 * j + 2] = v.z; w[u][4 * j + 3] = v.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < MW; j++) w[u][j] = __ldg(reinterpret_cast<const uint32_t*>(p) + j);
+      }
+    }
+    float est[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      float a = 0.0f;
+#pragma unroll
+      for (int j = 0; j < MW; j++) {
+        const uint32_t x = w[u][j];
+        a += lut[(4 * j + 0) * ADC_KS + (x & 0xffu)];
+        a += lut[(4 * j + 1) * ADC_KS + ((x >> 8) & 0xffu)];
+        a += lut[(4 * j + 2) * ADC_KS + ((x >> 16) & 0xffu)];
+        a += lut[(4 * j + 3) * ADC_KS + (x >> 24)];
+      }
+      est[u] = a;
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int64_t row = row0 + (int64_t)u * 32;
+      const bool cand = row < n && !(est[u] > fthr);
+      Key key = key_empty();
+      if (cand) key = Key{rank_hi_from_dist(adc_exact(lut64, codes + (size_t)row * M, M, K)), (uint64_t)row};
+      tk.push(key, cand, lane);
+    }
+    if (tk.thr.hi != seen_hi || tk.thr.lo != seen_lo) {
+      seen_hi = tk.thr.hi;
+      seen_lo = tk.thr.lo;
+      fthr = adc_filter_threshold(tk.thr, M);
+    }
+  }
+  topk_epilogue(tk, smem, kp, k, out);
+}
+
+// any M: byte loads, exact fp64 for every row (no estimate).  Correctness path for odd shapes.
+__global__ void __launch_bounds__(SCAN_THREADS)
+adc_scan_generic_kernel(const uint8_t* __restrict__ codes, int64_t n, int M, int K,
+                        const double* __restrict__ LUT64, int k, int kp, TopkOut out) {
+  extern __shared__ __align__(16) ulonglong2 smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nw = blockDim.x >> 5;
+  const int stride_keys = kp + TOPK_BUF;
+  const double* __restrict__ lut64 = LUT64 + (size_t)blockIdx.y * M * K;
+  WarpTopK tk;
+  tk.init(smem + (size_t)warp * stride_keys, kp, k, lane);
+  __syncthreads();
+  const int64_t nb = (n + 31) / 32;
+  for (int64_t b = (int64_t)blockIdx.x * nw + warp; b < nb; b += (int64_t)gridDim.x * nw) {
+    const int64_t row = b * 32 + lane;
+    Key key = key_empty();
+    if (row < n) key = Key{rank_hi_from_dist(adc_exact(lut64, codes + (size_t)row * M, M, K)), (uint64_t)row};
+    tk.push(key, row < n, lane);
+  }
+  topk_epilogue(tk, smem, kp, k, out);
+}
+
+template <typename KERN>
+static cudaError_t set_smem(KERN kern, size_t smem) {
+  if (smem > 48 * 1024)
+    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  return cudaSuccess;
+}
+
+static bool adc_is_streaming(int M, int K) { return K <= 256 && (M == 8 || M == 16 || M == 32 || M == 64); }
+
+size_t adc_scan_smem_bytes(int M, int K, int kp, int threads) {
+  size_t s = (size_t)(threads / 32) * topk_warp_smem(kp);
+  if (adc_is_streaming(M, K)) s += (size_t)M * ADC_KS * 4;
+  return s;
+}
+
+template <int MW, int U>
+static int adc_occ_t(int threads, size_t smem) {
+  auto kern = adc_scan_kernel<MW, U>;
+  if (set_smem(kern, smem) != cudaSuccess) return 0;
+  int nb = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, threads, smem) != cudaSuccess) nb = 0;
+  return nb;
+}
+
+int adc_scan_occupancy(int M, int K, int threads, size_t smem) {
+  if (!adc_is_streaming(M, K)) {
+    int nb = 0;
+    set_smem(adc_scan_generic_kernel, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, adc_scan_generic_kernel, threads, smem);
+    return nb;
+  }
+  switch (M) {
+    case 8: return adc_occ_t<2, 8>(threads, smem);
+    case 16: return adc_occ_t<4, 4>(threads, smem);
+    case 32: return adc_occ_t<8, 2>(threads, smem);
+    default: return adc_occ_t<16, 1>(threads, smem);
+  }
+}
+
+template <int MW, int U>
+static cudaError_t adc_launch_t(const AdcScanLaunch& L, const TopkOut& o, cudaStream_t st) {
+  auto kern = adc_scan_kernel<MW, U>;
+  cudaError_t e = set_smem(kern, L.smem_bytes);
+  if (e != cudaSuccess) return e;
+  kern<<<dim3(L.grid, L.nq), L.threads, L.smem_bytes, st>>>(L.codes, L.n, L.K, L.lut64, L.k, L.kp, o);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_adc_scan(const AdcScanLaunch& L, cudaStream_t st) {
+  TopkOut o{L.partial, L.ticket, L.ids_out, L.approx_out, L.counts_out, L.id_base, 1};
+  if (!adc_is_streaming(L.M, L.K)) {
+    cudaError_t e = set_smem(adc_scan_generic_kernel, L.smem_bytes);
+    if (e != cudaSuccess) return e;
+    adc_scan_generic_kernel<<<dim3(L.grid, L.nq), L.threads, L.smem_bytes, st>>>(L.codes, L.n, L.M, L.K,
+                                                                                 L.lut64, L.k, L.kp, o);
+    count_launch();
+    return cudaGetLastError();
+  }
+  switch (L.M) {
+    case 8: return adc_launch_t<2, 8>(L, o, st);
+    case 16: return adc_launch_t<4, 4>(L, o, st);
+    case 32: return adc_launch_t<8, 2>(L, o, st);
+    default: return adc_launch_t<16, 1>(L, o, st);
+  }
+}
+
+}  // namespace vs

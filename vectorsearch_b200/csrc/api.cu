@@ -1,0 +1,991 @@
+// api.cu -- the C ABI of libvsgpu (include/vsgpu.h): handle table, per-thread streams and
+// scratch, host<->device staging, launch configuration.  No torch types, no CPU fallback: every
+// compute entry point fails with VS_ECUDA when no device is bound.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/vsgpu.h"
+#include "host.h"
+#include "kernels.h"
+#include "topk.cuh"
+
+namespace vs {
+
+static std::atomic<int64_t> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+static std::atomic<int> g_device{-1};
+static std::atomic<int> g_lanes{16};
+static int g_sms = 0;
+static std::mutex g_mu;
+static std::unordered_map<uint64_t, Segment*> g_segments;
+static uint64_t g_next_handle = 1;
+
+static thread_local std::string t_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  t_err = buf;
+  return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  // leave the sticky error (if any) visible in the message; clear the non-sticky ones
+  cudaGetLastError();
+  return fail(e == cudaErrorMemoryAllocation ? VS_ENOMEM : VS_ECUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+int lanes() { return g_lanes.load(); }
+int sm_count() { return g_sms; }
+
+// ---- per-thread context ------------------------------------------------------------------------------
+struct ThreadCtx {
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  void* d_buf = nullptr;
+  size_t d_cap = 0;
+  void* h_buf = nullptr;  // pinned
+  size_t h_cap = 0;
+  unsigned int* d_ticket = nullptr;  // zero between launches
+  size_t ticket_cap = 0;
+  ~ThreadCtx() {
+    // process teardown: the context may already be gone; ignore errors
+    if (device >= 0 && g_device.load() == device) {
+      if (d_buf) cudaFree(d_buf);
+      if (h_buf) cudaFreeHost(h_buf);
+      if (d_ticket) cudaFree(d_ticket);
+      if (stream) cudaStreamDestroy(stream);
+    }
+  }
+};
+static thread_local ThreadCtx t_ctx;
+
+int ctx_bind(ThreadCtx** out) {
+  const int dev = g_device.load();
+  if (dev < 0) return fail(VS_ECUDA, "vs_init has not bound a CUDA device (there is no CPU fallback)");
+  ThreadCtx& c = t_ctx;
+  cudaError_t e = cudaSetDevice(dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+  if (c.device != dev) {
+    c = ThreadCtx{};
+    c.device = dev;
+    e = cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
+  }
+  *out = &c;
+  return VS_OK;
+}
+
+static int ctx_reserve_dev(ThreadCtx* c, size_t bytes) {
+  if (bytes <= c->d_cap) return VS_OK;
+  cudaStreamSynchronize(c->stream);
+  if (c->d_buf) cudaFree(c->d_buf);
+  c->d_buf = nullptr;
+  c->d_cap = 0;
+  size_t cap = bytes + bytes / 4 + 4096;
+  cudaError_t e = cudaMalloc(&c->d_buf, cap);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(scratch)");
+  c->d_cap = cap;
+  return VS_OK;
+}
+static int ctx_reserve_host(ThreadCtx* c, size_t bytes) {
+  if (bytes <= c->h_cap) return VS_OK;
+  cudaStreamSynchronize(c->stream);
+  if (c->h_buf) cudaFreeHost(c->h_buf);
+  c->h_buf = nullptr;
+  c->h_cap = 0;
+  size_t cap = bytes + bytes / 4 + 4096;
+  cudaError_t e = cudaMallocHost(&c->h_buf, cap);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMallocHost(staging)");
+  c->h_cap = cap;
+  return VS_OK;
+}
+static int ctx_reserve_ticket(ThreadCtx* c, size_t n) {
+  if (n <= c->ticket_cap) return VS_OK;
+  cudaStreamSynchronize(c->stream);
+  if (c->d_ticket) cudaFree(c->d_ticket);
+  c->d_ticket = nullptr;
+  c->ticket_cap = 0;
+  size_t cap = n < 1024 ? 1024 : n * 2;
+  cudaError_t e = cudaMalloc(&c->d_ticket, cap * sizeof(unsigned int));
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(ticket)");
+  e = cudaMemsetAsync(c->d_ticket, 0, cap * sizeof(unsigned int), c->stream);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMemset(ticket)");
+  c->ticket_cap = cap;
+  return VS_OK;
+}
+
+// bump allocator over the per-thread scratch
+struct Arena {
+  char* base;
+  size_t off = 0;
+  explicit Arena(void* b) : base(static_cast<char*>(b)) {}
+  template <typename T>
+  T* take(size_t count) {
+    off = (off + 255) & ~size_t(255);
+    T* p = reinterpret_cast<T*>(base + off);
+    off += count * sizeof(T);
+    return p;
+  }
+  static size_t need(std::initializer_list<size_t> sizes) {
+    size_t o = 0;
+    for (size_t s : sizes) o = ((o + 255) & ~size_t(255)) + s;
+    return o + 256;
+  }
+};
+
+// ---- segments -----------------------------------------------------------------------------------------
+Segment* seg_lookup(uint64_t h) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_segments.find(h);
+  return it == g_segments.end() ? nullptr : it->second;
+}
+static uint64_t seg_register(Segment* s) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  uint64_t h = g_next_handle++;
+  g_segments[h] = s;
+  return h;
+}
+static void seg_destroy(Segment* s) {
+  if (!s) return;
+  if (s->X) cudaFree(s->X);
+  if (s->skip) cudaFree(s->skip);
+  if (s->centroids) cudaFree(s->centroids);
+  if (s->codes) cudaFree(s->codes);
+  delete s;
+}
+
+#define CK(call, what)                                   \
+  do {                                                   \
+    cudaError_t _e = (call);                             \
+    if (_e != cudaSuccess) return cuda_fail(_e, what);   \
+  } while (0)
+#define RET(call)                 \
+  do {                            \
+    int _r = (call);              \
+    if (_r != VS_OK) return _r;   \
+  } while (0)
+
+// ---- launch configuration ------------------------------------------------------------------------------
+struct ScanPlan {
+  int grid, threads, kp;
+  size_t smem;
+};
+
+static int plan_scan(const Segment* s, int nq, int k, bool cosine, ScanPlan* p) {
+  p->kp = topk_pad(k);
+  p->threads = SCAN_THREADS;
+  p->smem = scan_smem_bytes(s->d, p->kp, p->threads);
+  while (p->smem > 200 * 1024 && p->threads > 64) {
+    p->threads /= 2;
+    p->smem = scan_smem_bytes(s->d, p->kp, p->threads);
+  }
+  int occ = scan_occupancy(s->d, lanes(), cosine, p->threads, p->smem);
+  if (occ < 1) return fail(VS_ECUDA, "scan kernel cannot be resident (smem %zu)", p->smem);
+  if (occ > 8) occ = 8;
+  int64_t grid = (int64_t)g_sms * (nq > 1 ? 1 : occ);
+  // never more CTAs than 16-row batches
+  int64_t cap = (s->n + 15) / 16;
+  if (cap < 1) cap = 1;
+  if (grid > cap) grid = cap;
+  p->grid = (int)grid;
+  return VS_OK;
+}
+
+static int plan_adc(const Segment* s, int nq, int k, ScanPlan* p) {
+  p->kp = topk_pad(k);
+  p->threads = SCAN_THREADS;
+  p->smem = adc_scan_smem_bytes(s->M, s->K, p->kp, p->threads);
+  while (p->smem > 200 * 1024 && p->threads > 64) {
+    p->threads /= 2;
+    p->smem = adc_scan_smem_bytes(s->M, s->K, p->kp, p->threads);
+  }
+  int occ = adc_scan_occupancy(s->M, s->K, p->threads, p->smem);
+  if (occ < 1) return fail(VS_ECUDA, "ADC scan kernel cannot be resident (smem %zu)", p->smem);
+  if (occ > 8) occ = 8;
+  int64_t grid = (int64_t)g_sms * (nq > 1 ? 1 : occ);
+  int64_t cap = (s->n + 127) / 128;
+  if (cap < 1) cap = 1;
+  if (grid > cap) grid = cap;
+  p->grid = (int)grid;
+  return VS_OK;
+}
+
+static void fill_empty(int64_t* ids, double* scores, int32_t* counts, int nq, int k) {
+  const double nan = __builtin_nan("");
+  for (int64_t i = 0; i < (int64_t)nq * k; i++) {
+    ids[i] = -1;
+    scores[i] = nan;
+  }
+  if (counts)
+    for (int i = 0; i < nq; i++) counts[i] = 0;
+}
+
+// ---- device-side bodies (everything on c->stream, no synchronisation) -------------------------------------
+static int bruteforce_dev(ThreadCtx* c, cudaStream_t st, const Segment* s, const float* d_q, int nq, int k,
+                          int metric, int64_t* d_ids, double* d_scores, int32_t* d_counts,
+                          ulonglong2* d_partial, unsigned int* d_ticket, const ScanPlan& p) {
+  (void)c;
+  ScanLaunch L{};
+  L.X = s->X; L.n = s->n; L.d = s->d; L.q = d_q; L.nq = nq; L.skip = s->skip; L.lanes = lanes();
+  L.cosine = metric == VS_METRIC_COSINE; L.k = k; L.kp = p.kp; L.partial = d_partial; L.ticket = d_ticket;
+  L.ids_out = d_ids; L.scores_out = d_scores; L.counts_out = d_counts; L.id_base = s->id_base;
+  L.grid = p.grid; L.threads = p.threads; L.smem_bytes = p.smem;
+  CK(launch_scan(L, st), "scan launch");
+  return VS_OK;
+}
+
+static int adc_dev(cudaStream_t st, const Segment* s, const float* d_q, int nq, int n_cand, double* d_lut,
+                   int64_t* d_ids, double* d_approx, int32_t* d_counts, ulonglong2* d_partial,
+                   unsigned int* d_ticket, const ScanPlan& p) {
+  CK(launch_build_lut(s->centroids, s->M, s->K, s->subDim, d_q, nq, lanes(), d_lut, st), "build_lut launch");
+  AdcScanLaunch L{};
+  L.codes = s->codes; L.n = s->n; L.M = s->M; L.K = s->K; L.lut64 = d_lut; L.nq = nq; L.k = n_cand; L.kp = p.kp;
+  L.partial = d_partial; L.ticket = d_ticket; L.ids_out = d_ids; L.approx_out = d_approx;
+  L.counts_out = d_counts; L.id_base = s->id_base; L.grid = p.grid; L.threads = p.threads; L.smem_bytes = p.smem;
+  CK(launch_adc_scan(L, st), "adc scan launch");
+  return VS_OK;
+}
+
+static int rerank_dev(cudaStream_t st, const Segment* s, const float* d_q, int nq, const int64_t* d_cand,
+                      int nc, int k, int metric, int64_t* d_ids, double* d_scores, int32_t* d_counts) {
+  RankLaunch L{};
+  L.X = s->X; L.n = s->n; L.d = s->d; L.skip = s->skip; L.lanes = lanes(); L.q = d_q; L.nq = nq;
+  L.cand_ids = d_cand; L.nc = nc; L.k = k; L.metric = metric; L.id_base = s->id_base;
+  L.ids_out = d_ids; L.scores_out = d_scores; L.counts_out = d_counts;
+  CK(launch_rank(L, st), "rank launch");
+  return VS_OK;
+}
+
+static int check_query_args(const Segment* s, const void* q, int nq, int k, int metric) {
+  if (!s) return fail(VS_EHANDLE, "unknown segment handle");
+  if (!q || nq <= 0) return fail(VS_EINVAL, "q must be non-null and nq positive");
+  if (k <= 0 || k > TOPK_MAX_K) return fail(VS_EINVAL, "k must be in 1..%d", TOPK_MAX_K);
+  if (metric != VS_METRIC_L2 && metric != VS_METRIC_COSINE) return fail(VS_EINVAL, "unknown metric %d", metric);
+  return VS_OK;
+}
+
+}  // namespace vs
+
+using namespace vs;
+
+// =================================================================================================
+// lifecycle
+// =================================================================================================
+extern "C" {
+
+int32_t vs_version(void) { return 100; }
+const char* vs_last_error(void) { return t_err.c_str(); }
+
+int32_t vs_init(int32_t device) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0) {
+    cudaGetLastError();
+    return fail(VS_ECUDA, "no usable CUDA device (%s); libvsgpu has no CPU fallback",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  }
+  if (device < 0 || device >= count) return fail(VS_EINVAL, "device %d out of range (0..%d)", device, count - 1);
+  CK(cudaSetDevice(device), "cudaSetDevice");
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties");
+  if (prop.major < 10) return fail(VS_ECUDA, "device %d is sm_%d%d; libvsgpu is built for sm_100a only", device, prop.major, prop.minor);
+  g_sms = prop.multiProcessorCount;
+  g_device.store(device);
+  return VS_OK;
+}
+
+int32_t vs_shutdown(void) {
+  std::vector<Segment*> segs;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (auto& kv : g_segments) segs.push_back(kv.second);
+    g_segments.clear();
+  }
+  if (g_device.load() >= 0) {
+    cudaSetDevice(g_device.load());
+    cudaDeviceSynchronize();
+    for (Segment* s : segs) seg_destroy(s);
+  }
+  return VS_OK;
+}
+
+int32_t vs_set_simd_lanes(int32_t lanes_) {
+  if (lanes_ != 16 && lanes_ != 8 && lanes_ != 4) return fail(VS_EINVAL, "lanes must be 16, 8 or 4");
+  g_lanes.store(lanes_);
+  return VS_OK;
+}
+int32_t vs_get_simd_lanes(void) { return g_lanes.load(); }
+
+int32_t vs_device_info(int32_t* sm_count_, int64_t* free_bytes, int64_t* total_bytes) {
+  ThreadCtx* c;
+  RET(ctx_bind(&c));
+  size_t f = 0, t = 0;
+  CK(cudaMemGetInfo(&f, &t), "cudaMemGetInfo");
+  if (sm_count_) *sm_count_ = g_sms;
+  if (free_bytes) *free_bytes = (int64_t)f;
+  if (total_bytes) *total_bytes = (int64_t)t;
+  return VS_OK;
+}
+
+int64_t vs_kernel_launch_count(void) { return g_launches.load(); }
+
+// =================================================================================================
+// pair operations
+// =================================================================================================
+static int32_t pair_op(int op, const float* a, const float* b, int32_t len, double* out) {
+  if (!a || (!b && op != PAIR_NORM) || !out || len < 0) return fail(VS_EINVAL, "null pointer or negative length");
+  ThreadCtx* c;
+  RET(ctx_bind(&c));
+  const size_t fb = (size_t)len * 4;
+  RET(ctx_reserve_dev(c, Arena::need({fb, fb, 8})));
+  RET(ctx_reserve_host(c, 8));
+  Arena A(c->d_buf);
+  float* da = A.take<float>(len);
+  float* db = A.take<float>(len);
+  double* dout = A.take<double>(1);
+  if (len > 0) {
+    CK(cudaMemcpyAsync(da, a, fb, cudaMemcpyHostToDevice, c->stream), "H2D a");
+    if (b) CK(cudaMemcpyAsync(db, b, fb, cudaMemcpyHostToDevice, c->stream), "H2D b");
+  }
+  CK(launch_pair(op, da, b ? db : da, len, lanes(), dout, c->stream), "pair launch");
+  CK(cudaMemcpyAsync(c->h_buf, dout, 8, cudaMemcpyDeviceToHost, c->stream), "D2H");
+  CK(cudaStreamSynchronize(c->stream), "sync");
+  *out = *static_cast<double*>(c->h_buf);
+  return VS_OK;
+}
+int32_t vs_l2(const float* a, const float* b, int32_t len, double* out) { return pair_op(PAIR_L2, a, b, len, out); }
+int32_t vs_l2_squared(const float* a, const float* b, int32_t len, double* out) { return pair_op(PAIR_L2SQ, a, b, len, out); }
+int32_t vs_dot(const float* a, const float* b, int32_t len, double* out) { return pair_op(PAIR_DOT, a, b, len, out); }
+int32_t vs_norm(const float* a, int32_t len, double* out) { return pair_op(PAIR_NORM, a, nullptr, len, out); }
+int32_t vs_cosine(const float* a, const float* b, int32_t len, double* out) { return pair_op(PAIR_COSINE, a, b, len, out); }
+
+static int check_pq_shape(int M, int K, int subDim) {
+  if (M <= 0 || K <= 0 || subDim <= 0) return fail(VS_EINVAL, "Invalid PQ params (m,k,dimension)");
+  return VS_OK;
+}
+
+int32_t vs_pq_encode(const float* centroids, int32_t M, int32_t K, int32_t subDim, const float* v,
+                     uint8_t* codes_out) {
+  return vs_pq_encode_batch(centroids, M, K, subDim, v, 0, 1, codes_out);
+}
+
+int32_t vs_pq_lut_distance(const float* lut, int32_t M, int32_t K, const uint8_t* codes, float* out) {
+  if (!lut || !codes || !out) return fail(VS_EINVAL, "null pointer");
+  if (M <= 0 || K <= 0) return fail(VS_EINVAL, "M and K must be positive");
+  for (int m = 0; m < M; m++)
+    if (codes[m] >= K) return fail(VS_EINVAL, "code %d of subspace %d is outside the LUT (K=%d)", (int)codes[m], m, K);
+  ThreadCtx* c;
+  RET(ctx_bind(&c));
+  const size_t lb = (size_t)M * K * 4;
+  RET(ctx_reserve_dev(c, Arena::need({lb, (size_t)M, 4})));
+  RET(ctx_reserve_host(c, 4));
+  Arena A(c->d_buf);
+  float* dl = A.take<float>((size_t)M * K);
+  uint8_t* dc = A.take<uint8_t>(M);
+  float* dout = A.take<float>(1);
+  CK(cudaMemcpyAsync(dl, lut, lb, cudaMemcpyHostToDevice, c->stream), "H2D lut");
+  CK(cudaMemcpyAsync(dc, codes, M, cudaMemcpyHostToDevice, c->stream), "H2D codes");
+  CK(launch_lut_distance_f32(dl, M, K, dc, dout, c->stream), "lut distance launch");
+  CK(cudaMemcpyAsync(c->h_buf, dout, 4, cudaMemcpyDeviceToHost, c->stream), "D2H");
+  CK(cudaStreamSynchronize(c->stream), "sync");
+  *out = *static_cast<float*>(c->h_buf);
+  return VS_OK;
+}
+
+int32_t vs_build_lut(const float* centroids, int32_t M, int32_t K, int32_t subDim, const float* q,
+                     double* lut_out) {
+  if (!centroids || !q || !lut_out) return fail(VS_EINVAL, "null pointer");
+  RET(check_pq_shape(M, K, subDim));
+  ThreadCtx* c;
+  RET(ctx_bind(&c));
+  const size_t cb = (size_t)M * K * subDim * 4, qb = (size_t)M * subDim * 4, lb = (size_t)M * K * 8;
+  RET(ctx_reserve_dev(c, Arena::need({cb, qb, lb})));
+  Arena A(c->d_buf);
+  float* dc = A.take<float>((size_t)M * K * subDim);
+  float* dq = A.take<float>((size_t)M * subDim);
+  double* dl = A.take<double>((size_t)M * K);
+  CK(cudaMemcpyAsync(dc, centroids, cb, cudaMemcpyHostToDevice, c->stream), "H2D centroids");
+  CK(cudaMemcpyAsync(dq, q, qb, cudaMemcpyHostToDevice, c->stream), "H2D q");
+  CK(launch_build_lut(dc, M, K, subDim, dq, 1, lanes(), dl, c->stream), "build_lut launch");
+  CK(cudaMemcpyAsync(lut_out, dl, lb, cudaMemcpyDeviceToHost, c->stream), "D2H lut");
+  CK(cudaStreamSynchronize(c->stream), "sync");
+  return VS_OK;
+}
+
+int32_t vs_pq_approx_distance(const double* lut, int32_t M, int32_t K, const uint8_t* codes, int64_t n,
+                              double* out) {
+  if (!lut || (!codes && n > 0) || (!out && n > 0) || n < 0) return fail(VS_EINVAL, "null pointer or negative n");
+  if (M <= 0 || K <= 0) return fail(VS_EINVAL, "M and K must be positive");
+  if (n == 0) return VS_OK;
+  ThreadCtx* c;
+  RET(ctx_bind(&c));
+  const size_t lb = (size_t)M * K * 8, cb = (size_t)n * M, ob = (size_t)n * 8;
+  RET(ctx_reserve_dev(c, Arena::need({lb, cb, ob})));
+  Arena A(c->d_buf);
+  double* dl = A.take<double>((size_t)M * K);
+  uint8_t* dc = A.take<uint8_t>(cb);
+  double* dout = A.take<double>(n);
+  CK(cudaMemcpyAsync(dl, lut, lb, cudaMemcpyHostToDevice, c->stream), "H2D lut");
+  CK(cudaMemcpyAsync(dc, codes, cb, cudaMemcpyHostToDevice, c->stream), "H2D codes");
+  CK(launch_approx_distance(dl, M, K, dc, n, dout, c->stream), "approx distance launch");
+  CK(cudaMemcpyAsync(out, dout, ob, cudaMemcpyDeviceToHost, c->stream), "D2H");
+  CK(cudaStreamSynchronize(c->stream), "sync");
+  return VS_OK;
+}
+
+// =================================================================================================
+// segment residency
+// =================================================================================================
+static int seg_new(int64_t n, int32_t d, int64_t id_base, Segment** out) {
+  if (n < 0 || d <= 0) return fail(VS_EINVAL, "n must be >= 0 and d positive");
+  Segment* s = new Segment();
+  s->n = n;
+  s->d = d;
+  s->id_base = id_base;
+  if (n > 0) {
+    cudaError_t e = cudaMalloc(&s->X, (size_t)n * d * 4);
+    if (e != cudaSuccess) {
+      delete s;
+      return cuda_fail(e, "cudaMalloc(rows)");
+    }
+  }
+  *out = s;
+  return VS_OK;
+}
+
+static int seg_set_skip(ThreadCtx* c, Segment* s, const uint8_t* skip_mask) {
+  if (!skip_mask) {
+    if (s->skip) {
+      CK(cudaStreamSynchronize(c->stream), "sync");
+      cudaFree(s->skip);
+      s->skip = nullptr;
+    }
+    return VS_OK;
+  }
+  if (s->n == 0) return VS_OK;
+  if (!s->skip) CK(cudaMalloc(&s->skip, (size_t)s->n), "cudaMalloc(skip)");
+  CK(cudaMemcpyAsync(s->skip, skip_mask, (size_t)s->n, cudaMemcpyHostToDevice, c->stream), "H2D skip");
+  CK(cudaStreamSynchronize(c->stream), "sync");
+  return VS_OK;
+}
+
+int32_t vs_segment_upload(const float* rows, int64_t n, int32_t d, const uint8_t* skip_mask,
+                          int64_t id_base, uint64_t* handle_out) {
+  if (!handle_out || (!rows && n > 0)) return fail(VS_EINVAL, "null pointer");
+  ThreadCtx* c;
+  RET(ctx_bind(&c));
+  Segment* s;
+  RET(seg_new(n, d, id_base, &s));
+  if (n > 0) {
+    cudaError_t e = cudaMemcpyAsync(s->X, rows, (size_t)n * d * 4, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) {
+      seg_destroy(s);
+      return cuda_fail(e, "H2D rows");
+    }
+  }
+  int r = seg_set_skip(c, s, skip_mask);
+  if (r != VS_OK) {
+    seg_destroy(s);
+    return r;
+  }
+  *handle_out = seg_register(s);
+  return VS_OK;
+}
+
+int32_t vs_segment_generate(int64_t seed, int64_t first_row, int64_t n, int32_t d, int64_t id_base,
+                            uint64_t* handle_out) {
+  if (!handle_out || first_row < 0) return fail(VS_EINVAL, "null pointer or negative first_row");
+  ThreadCtx* c;
+  RET(ctx_bind(&c));
+  Segment* s;
+  RET(seg_new(n, d, id_base, &s));
+  cudaError_t e = launch_generate(s->X, n * d, seed, first_row * d, 0, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  if (e != cudaSuccess) {
+    seg_destroy(s);
+    return cuda_fail(e, "generate");
+  }
+  *handle_out = seg_register(s);
+  return VS_OK;
+}
+
+int32_t vs_segment_set_skip(uint64_t h, const uint8_t* skip_mask) {
+  ThreadCtx* c;
+  RET(ctx_bind(&c));
+  Segment* s = seg_lookup(h);
+  if (!s) return fail(VS_EHANDLE, "unknown segment handle");
+  return seg_set_skip(c, s, skip_mask);
+}
+
+int32_t vs_segment_info(uint64_t h, int64_t* n, int32_t* d, int32_t* M, int32_t* K, int64_t* id_base) {
+  Segment* s = seg_lookup(h);
+  if (!s) return fail(VS_EHANDLE, "unknown segment handle");
+  if (n) *n = s->n;
+  if (d) *d = s->d;
+  if (M) *M = s->M;
+  if (K) *K = s->K;
+  if (id_base) *id_base = s->id_base;
+  return VS_OK;
+}
+
+int32_t vs_segment_download_rows(uint64_t h, int64_t first, int64_t count, float* rows_out) {
+  ThreadCtx* c;
+  RET(ctx_bind(&c));
+  Segment* s = seg_lookup(h);
+  if (!s) return fail(VS_EHANDLE, "unknown segment handle");
+  if (first < 0 || count < 0 || first + count > s->n || (!rows_out && count > 0)) return fail(VS_EINVAL, "row range out of bounds");
+  if (count == 0) return VS_OK;
+  CK(cudaMemcpyAsync(rows_out, s->X + (size_t)first * s->d, (size_t)count * s->d * 4, cudaMemcpyDeviceToHost, c->stream), "D2H rows");
+  CK(cudaStreamSynchronize(c->stream), "sync");
+  return VS_OK;
+}
+
+int32_t vs_segment_attach_pq(uint64_t h, const float* centroids, int32_t M, int32_t K, const uint8_t* codes) {
+  ThreadCtx* c;
+  RET(ctx_bind(&c));
+  Segment* s = seg_lookup(h);
+  if (!s) return fail(VS_EHANDLE, "unknown segment handle");
+  if (!centroids) return fail(VS_EINVAL, "null centroids");
+  if (M <= 0 || K <= 0 || s->d % M != 0) return fail(VS_EINVAL, "Invalid PQ params (m,k,dimension)");
+  const int subDim = s->d / M;
+  CK(cudaStreamSynchronize(c->stream), "sync");
+  if (s->centroids) cudaFree(s->centroids);
+  if (s->codes) cudaFree(s->codes);
+  s->centroids = nullptr;
+  s->codes = nullptr;
+  s->M = s->K = s->subDim = 0;
+  const size_t cb = (size_t)M * K * subDim * 4;
+  CK(cudaMalloc(&s->centroids, cb), "cudaMalloc(centroids)");
+  CK(cudaMemcpyAsync(s->centroids, centroids, cb, cudaMemcpyHostToDevice, c->stream), "H2D centroids");
+  if (s->n > 0) {
+    CK(cudaMalloc(&s->codes, (size_t)s->n * M), "cudaMalloc(codes)");
+    if (codes) {
+      CK(cudaMemcpyAsync(s->codes, codes, (size_t)s->n * M, cudaMemcpyHostToDevice, c->stream), "H2D codes");
+    } else {
+      PqAssignLaunch L{};
+      L.X = s->X; L.n = s->n; L.d = s->d; L.M = M; L.K = K; L.subDim = subDim; L.centroids = s->centroids;
+      L.lanes = lanes(); L.codes_u8 = s->codes; L.assign_i32 = nullptr; L.s_begin = 0; L.s_end = M;
+      CK(launch_pq_assign(L, c->stream), "pq assign launch");
+    }
+  }
+  CK(cudaStreamSynchronize(c->stream), "sync");
+  s->M = M;
+  s->K = K;
+  s->subDim = subDim;
+  return VS_OK;
+}
+
+int32_t vs_segment_download_codes(uint64_t h, int64_t first, int64_t count, uint8_t* codes_out) {
+  ThreadCtx* c;
+  RET(ctx_bind(&c));
+  Segment* s = seg_lookup(h);
+  if (!s) return fail(VS_EHANDLE, "unknown segment handle");
+  if (s->M == 0) return fail(VS_ESTATE, "segment has no PQ attached");
+  if (first < 0 || count < 0 || first + count > s->n || (!codes_out && count > 0)) return fail(VS_EINVAL, "row range out of bounds");
+  if (count == 0) return VS_OK;
+  CK(cudaMemcpyAsync(codes_out, s->codes + (size_t)first * s->M, (size_t)count * s->M, cudaMemcpyDeviceToHost, c->stream), "D2H codes");
+  CK(cudaStreamSynchronize(c->stream), "sync");
+  return VS_OK;
+}
+
+int32_t vs_segment_free(uint64_t h) {
+  Segment* s = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_segments.find(h);
+    if (it == g_segments.end()) return fail(VS_EHANDLE, "unknown segment handle");
+    s = it->second;
+    g_segments.erase(it);
+  }
+  if (g_device.load() >= 0) {
+    cudaSetDevice(g_device.load());
+    cudaDeviceSynchronize();
+  }
+  seg_destroy(s);
+  return VS_OK;
+}
+
+// =================================================================================================
+// query operations (host pointers; blocking)
+// =================================================================================================
+// queries are processed in groups so that the per-CTA partial lists stay within this budget
+static const size_t PARTIAL_BUDGET = size_t(192) << 20;
+
+int32_t vs_bruteforce_topk(uint64_t h, const float* q, int32_t nq, int32_t k, int32_t metric,
+                           int64_t* ids_out, double* scores_out, int32_t* counts_out) {
+  Segment* s = seg_lookup(h);
+  RET(check_query_args(s, q, nq, k, metric));
+  if (!ids_out || !scores_out) return fail(VS_EINVAL, "null output pointer");
+  ThreadCtx* c;
+  RET(ctx_bind(&c));
+  if (s->n == 0) {
+    fill_empty(ids_out, scores_out, counts_out, nq, k);
+    return VS_OK;
+  }
+  ScanPlan p;
+  RET(plan_scan(s, nq, k, metric == VS_METRIC_COSINE, &p));
+  const size_t per_q_partial = (size_t)p.grid * k * 16;
+  int group = (int)(PARTIAL_BUDGET / per_q_partial);
+  if (group < 1) group = 1;
+  if (group > nq) group = nq;
+  const size_t qb = (size_t)group * s->d * 4, ib = (size_t)group * k * 8, cb = (size_t)group * 4;
+  RET(ctx_reserve_dev(c, Arena::need({qb, ib, ib, cb, per_q_partial * group})));
+  RET(ctx_reserve_host(c, Arena::need({qb, ib, ib, cb})));
+  RET(ctx_reserve_ticket(c, group));
+  for (int q0 = 0; q0 < nq; q0 += group) {
+    const int g = (q0 + group <= nq) ? group : nq - q0;
+    Arena A(c->d_buf), H(c->h_buf);
+    float* dq = A.take<float>((size_t)group * s->d);
+    int64_t* dids = A.take<int64_t>((size_t)group * k);
+    double* dsc = A.take<double>((size_t)group * k);
+    int32_t* dcn = A.take<int32_t>(group);
+    ulonglong2* dpart = A.take<ulonglong2>((size_t)group * p.grid * k);
+    float* hq = H.take<float>((size_t)group * s->d);
+    int64_t* hids = H.take<int64_t>((size_t)group * k);
+    double* hsc = H.take<double>((size_t)group * k);
+    int32_t* hcn = H.take<int32_t>(group);
+    memcpy(hq, q + (size_t)q0 * s->d, (size_t)g * s->d * 4);
+    CK(cudaMemcpyAsync(dq, hq, (size_t)g * s->d * 4, cudaMemcpyHostToDevice, c->stream), "H2D q");
+    RET(bruteforce_dev(c, c->stream, s, dq, g, k, metric, dids, dsc, dcn, dpart, c->d_ticket, p));
+    CK(cudaMemcpyAsync(hids, dids, (size_t)g * k * 8, cudaMemcpyDeviceToHost, c->stream), "D2H ids");
+    CK(cudaMemcpyAsync(hsc, dsc, (size_t)g * k * 8, cudaMemcpyDeviceToHost, c->stream), "D2H scores");
+    CK(cudaMemcpyAsync(hcn, dcn, (size_t)g * 4, cudaMemcpyDeviceToHost, c->stream), "D2H counts");
+    CK(cudaStreamSynchronize(c->stream), "sync");
+    memcpy(ids_out + (size_t)q0 * k, hids, (size_t)g * k * 8);
+    memcpy(scores_out + (size_t)q0 * k, hsc, (size_t)g * k * 8);
+    if (counts_out) memcpy(counts_out + q0, hcn, (size_t)g * 4);
+  }
+  return VS_OK;
+}
+
+static int adc_common(uint64_t h, const float* q, int32_t nq, int32_t n_cand, bool rerank, int32_t k,
+                      int32_t metric, int64_t* ids_out, double* scores_out, int32_t* counts_out) {
+  Segment* s = seg_lookup(h);
+  RET(check_query_args(s, q, nq, n_cand, rerank ? metric : VS_METRIC_L2));
+  if (rerank && (k <= 0 || k > TOPK_MAX_K)) return fail(VS_EINVAL, "k must be in 1..%d", TOPK_MAX_K);
+  if (!ids_out || !scores_out) return fail(VS_EINVAL, "null output pointer");
+  if (s->M == 0) return fail(VS_ESTATE, "segment has no PQ attached");
+  ThreadCtx* c;
+  RET(ctx_bind(&c));
+  const int kout = rerank ? k : n_cand;
+  if (s->n == 0) {
+    fill_empty(ids_out, scores_out, counts_out, nq, kout);
+    return VS_OK;
+  }
+  ScanPlan p;
+  RET(plan_adc(s, nq, n_cand, &p));
+  const size_t per_q_partial = (size_t)p.grid * n_cand * 16;
+  int group = (int)(PARTIAL_BUDGET / per_q_partial);
+  if (group < 1) group = 1;
+  if (group > nq) group = nq;
+  const size_t qb = (size_t)group * s->d * 4, cib = (size_t)group * n_cand * 8, ccb = (size_t)group * 4;
+  const size_t ob = (size_t)group * kout * 8, lb = (size_t)group * s->M * s->K * 8;
+  RET(ctx_reserve_dev(c, Arena::need({qb, cib, cib, ccb, ob, ob, ccb, lb, per_q_partial * group})));
+  RET(ctx_reserve_host(c, Arena::need({qb, ob, ob, ccb})));
+  RET(ctx_reserve_ticket(c, group));
+  for (int q0 = 0; q0 < nq; q0 += group) {
+    const int g = (q0 + group <= nq) ? group : nq - q0;
+    Arena A(c->d_buf), H(c->h_buf);
+    float* dq = A.take<float>((size_t)group * s->d);
+    int64_t* dcid = A.take<int64_t>((size_t)group * n_cand);
+    double* dcap = A.take<double>((size_t)group * n_cand);
+    int32_t* dccn = A.take<int32_t>(group);
+    int64_t* dids = A.take<int64_t>((size_t)group * kout);
+    double* dsc = A.take<double>((size_t)group * kout);
+    int32_t* dcn = A.take<int32_t>(group);
+    double* dlut = A.take<double>((size_t)group * s->M * s->K);
+    ulonglong2* dpart = A.take<ulonglong2>((size_t)group * p.grid * n_cand);
+    float* hq = H.take<float>((size_t)group * s->d);
+    int64_t* hids = H.take<int64_t>((size_t)group * kout);
+    double* hsc = H.take<double>((size_t)group * kout);
+    int32_t* hcn = H.take<int32_t>(group);
+    memcpy(hq, q + (size_t)q0 * s->d, (size_t)g * s->d * 4);
+    CK(cudaMemcpyAsync(dq, hq, (size_t)g * s->d * 4, cudaMemcpyHostToDevice, c->stream), "H2D q");
+    RET(adc_dev(c->stream, s, dq, g, n_cand, dlut, dcid, dcap, dccn, dpart, c->d_ticket, p));
+    const int64_t* src_ids = dcid;
+    const double* src_sc = dcap;
+    const int32_t* src_cn = dccn;
+    if (rerank) {
+      RET(rerank_dev(c->stream, s, dq, g, dcid, n_cand, k, metric, dids, dsc, dcn));
+      src_ids = dids;
+      src_sc = dsc;
+      src_cn = dcn;
+    }
+    CK(cudaMemcpyAsync(hids, src_ids, (size_t)g * kout * 8, cudaMemcpyDeviceToHost, c->stream), "D2H ids");
+    CK(cudaMemcpyAsync(hsc, src_sc, (size_t)g * kout * 8, cudaMemcpyDeviceToHost, c->stream), "D2H scores");
+    CK(cudaMemcpyAsync(hcn, src_cn, (size_t)g * 4, cudaMemcpyDeviceToHost, c->stream), "D2H counts");
+    CK(cudaStreamSynchronize(c->stream), "sync");
+    memcpy(ids_out + (size_t)q0 * kout, hids, (size_t)g * kout * 8);
+    memcpy(scores_out + (size_t)q0 * kout, hsc, (size_t)g * kout * 8);
+    if (counts_out) memcpy(counts_out + q0, hcn, (size_t)g * 4);
+  }
+  return VS_OK;
+}
+
+int32_t vs_adc_topk(uint64_t h, const float* q, int32_t nq, int32_t n_cand, int64_t* ids_out,
+                    double* approx_out, int32_t* counts_out) {
+  return adc_common(h, q, nq, n_cand, false, 0, VS_METRIC_L2, ids_out, approx_out, counts_out);
+}
+
+int32_t vs_adc_rerank_topk(uint64_t h, const float* q, int32_t nq, int32_t n_cand, int32_t k, int32_t metric,
+                           int32_t normalize_on_read, int64_t* ids_out, double* scores_out,
+                           int32_t* counts_out) {
+  (void)normalize_on_read;  // same arithmetic either way (J/fdb/FdbVectorIndex.java:1006-1012)
+  return adc_common(h, q, nq, n_cand, true, k, metric, ids_out, scores_out, counts_out);
+}
+
+int32_t vs_rerank_topk(uint64_t h, const float* q, const int64_t* cand_ids, int32_t n_cand, int32_t k,
+                       int32_t metric, int32_t normalize_on_read, int64_t* ids_out, double* scores_out,
+                       int32_t* count_out) {
+  (void)normalize_on_read;
+  Segment* s = seg_lookup(h);
+  if (!s) return fail(VS_EHANDLE, "unknown segment handle");
+  if (!q || !ids_out || !scores_out || (!cand_ids && n_cand > 0)) return fail(VS_EINVAL, "null pointer");
+  if (n_cand < 0 || n_cand > 8192) return fail(VS_EINVAL, "n_cand must be in 0..8192");
+  if (k <= 0 || k > TOPK_MAX_K) return fail(VS_EINVAL, "k must be in 1..%d", TOPK_MAX_K);
+  if (metric != VS_METRIC_L2 && metric != VS_METRIC_COSINE) return fail(VS_EINVAL, "unknown metric %d", metric);
+  ThreadCtx* c;
+  RET(ctx_bind(&c));
+  if (n_cand == 0 || s->n == 0) {
+    fill_empty(ids_out, scores_out, count_out, 1, k);
+    return VS_OK;
+  }
+  const size_t qb = (size_t)s->d * 4, cb = (size_t)n_cand * 8, ob = (size_t)k * 8;
+  RET(ctx_reserve_dev(c, Arena::need({qb, cb, ob, ob, 4})));
+  RET(ctx_reserve_host(c, Arena::need({qb, cb, ob, ob, 4})));
+  Arena A(c->d_buf), H(c->h_buf);
+  float* dq = A.take<float>(s->d);
+  int64_t* dcand = A.take<int64_t>(n_cand);
+  int64_t* dids = A.take<int64_t>(k);
+  double* dsc = A.take<double>(k);
+  int32_t* dcn = A.take<int32_t>(1);
+  float* hq = H.take<float>(s->d);
+  int64_t* hcand = H.take<int64_t>(n_cand);
+  int64_t* hids = H.take<int64_t>(k);
+  double* hsc = H.take<double>(k);
+  int32_t* hcn = H.take<int32_t>(1);
+  memcpy(hq, q, qb);
+  memcpy(hcand, cand_ids, cb);
+  CK(cudaMemcpyAsync(dq, hq, qb, cudaMemcpyHostToDevice, c->stream), "H2D q");
+  CK(cudaMemcpyAsync(dcand, hcand, cb, cudaMemcpyHostToDevice, c->stream), "H2D cand");
+  RET(rerank_dev(c->stream, s, dq, 1, dcand, n_cand, k, metric, dids, dsc, dcn));
+  CK(cudaMemcpyAsync(hids, dids, ob, cudaMemcpyDeviceToHost, c->stream), "D2H ids");
+  CK(cudaMemcpyAsync(hsc, dsc, ob, cudaMemcpyDeviceToHost, c->stream), "D2H scores");
+  CK(cudaMemcpyAsync(hcn, dcn, 4, cudaMemcpyDeviceToHost, c->stream), "D2H count");
+  CK(cudaStreamSynchronize(c->stream), "sync");
+  memcpy(ids_out, hids, ob);
+  memcpy(scores_out, hsc, ob);
+  if (count_out) *count_out = *hcn;
+  return VS_OK;
+}
+
+int32_t vs_merge_topk(const int64_t* ids, const double* scores, int64_t total, int32_t k, int64_t* ids_out,
+                      double* scores_out, int32_t* count_out) {
+  if ((!ids || !scores) && total > 0) return fail(VS_EINVAL, "null pointer");
+  if (!ids_out || !scores_out || total < 0) return fail(VS_EINVAL, "null output pointer or negative total");
+  if (k <= 0 || k > TOPK_MAX_K) return fail(VS_EINVAL, "k must be in 1..%d", TOPK_MAX_K);
+  ThreadCtx* c;
+  RET(ctx_bind(&c));
+  if (total == 0) {
+    fill_empty(ids_out, scores_out, count_out, 1, k);
+    return VS_OK;
+  }
+  const size_t tb = (size_t)total * 8, ob = (size_t)k * 8;
+  RET(ctx_reserve_dev(c, Arena::need({tb, tb, ob, ob, 4})));
+  RET(ctx_reserve_host(c, Arena::need({ob, ob, 4})));
+  Arena A(c->d_buf), H(c->h_buf);
+  int64_t* din = A.take<int64_t>(total);
+  double* dsin = A.take<double>(total);
+  int64_t* dids = A.take<int64_t>(k);
+  double* dsc = A.take<double>(k);
+  int32_t* dcn = A.take<int32_t>(1);
+  int64_t* hids = H.take<int64_t>(k);
+  double* hsc = H.take<double>(k);
+  int32_t* hcn = H.take<int32_t>(1);
+  CK(cudaMemcpyAsync(din, ids, tb, cudaMemcpyHostToDevice, c->stream), "H2D ids");
+  CK(cudaMemcpyAsync(dsin, scores, tb, cudaMemcpyHostToDevice, c->stream), "H2D scores");
+  CK(launch_merge(din, dsin, total, k, dids, dsc, dcn, c->stream), "merge launch");
+  CK(cudaMemcpyAsync(hids, dids, ob, cudaMemcpyDeviceToHost, c->stream), "D2H ids");
+  CK(cudaMemcpyAsync(hsc, dsc, ob, cudaMemcpyDeviceToHost, c->stream), "D2H scores");
+  CK(cudaMemcpyAsync(hcn, dcn, 4, cudaMemcpyDeviceToHost, c->stream), "D2H count");
+  CK(cudaStreamSynchronize(c->stream), "sync");
+  memcpy(ids_out, hids, ob);
+  memcpy(scores_out, hsc, ob);
+  if (count_out) *count_out = *hcn;
+  return VS_OK;
+}
+
+// =================================================================================================
+// build operations
+// =================================================================================================
+int32_t vs_pq_encode_batch(const float* centroids, int32_t M, int32_t K, int32_t subDim, const float* rows,
+                           uint64_t h, int64_t n, uint8_t* codes_out) {
+  if (!centroids || (!codes_out && n > 0) || n < 0) return fail(VS_EINVAL, "null pointer or negative n");
+  RET(check_pq_shape(M, K, subDim));
+  ThreadCtx* c;
+  RET(ctx_bind(&c));
+  if (n == 0) return VS_OK;
+  const int d = M * subDim;
+  const float* dX = nullptr;
+  Segment* s = nullptr;
+  if (!rows) {
+    s = seg_lookup(h);
+    if (!s) return fail(VS_EHANDLE, "rows == NULL needs a valid segment handle");
+    if (s->d != d) return fail(VS_EINVAL, "segment dimension %d != M*subDim %d", s->d, d);
+    if (n > s->n) return fail(VS_EINVAL, "n exceeds the segment's row count");
+    dX = s->X;
+  }
+  const size_t cb = (size_t)M * K * subDim * 4;
+  // host rows are streamed through the scratch in slabs
+  const int64_t slab = rows ? std::min<int64_t>(n, (int64_t)((size_t(256) << 20) / ((size_t)d * 4)) + 1) : n;
+  const size_t xb = rows ? (size_t)slab * d * 4 : 0, ob = (size_t)slab * M;
+  RET(ctx_reserve_dev(c, Arena::need({cb, xb, ob})));
+  Arena A(c->d_buf);
+  float* dc = A.take<float>((size_t)M * K * subDim);
+  float* dx = A.take<float>(rows ? (size_t)slab * d : 0);
+  uint8_t* dcodes = A.take<uint8_t>(ob);
+  CK(cudaMemcpyAsync(dc, centroids, cb, cudaMemcpyHostToDevice, c->stream), "H2D centroids");
+  for (int64_t r0 = 0; r0 < n; r0 += slab) {
+    const int64_t cnt = std::min<int64_t>(slab, n - r0);
+    const float* src = dX ? dX + (size_t)r0 * d : dx;
+    if (rows) CK(cudaMemcpyAsync(dx, rows + (size_t)r0 * d, (size_t)cnt * d * 4, cudaMemcpyHostToDevice, c->stream), "H2D rows");
+    PqAssignLaunch L{};
+    L.X = src; L.n = cnt; L.d = d; L.M = M; L.K = K; L.subDim = subDim; L.centroids = dc; L.lanes = lanes();
+    L.codes_u8 = dcodes; L.assign_i32 = nullptr; L.s_begin = 0; L.s_end = M;
+    CK(launch_pq_assign(L, c->stream), "pq assign launch");
+    CK(cudaMemcpyAsync(codes_out + (size_t)r0 * M, dcodes, (size_t)cnt * M, cudaMemcpyDeviceToHost, c->stream), "D2H codes");
+    CK(cudaStreamSynchronize(c->stream), "sync");
+  }
+  return VS_OK;
+}
+
+int32_t vs_pq_train(const float* rows, uint64_t h, int64_t n, int32_t d, int32_t M, int32_t K,
+                    int32_t iterations, int64_t seed, float* centroids_out) {
+  // PqTrainer.java:29-34
+  if (M <= 0 || K <= 0 || d <= 0) return fail(VS_EINVAL, "Invalid PQ params (m,k,dimension)");
+  if (d % M != 0) return fail(VS_EINVAL, "dimension must be divisible by m");
+  if (!centroids_out) return fail(VS_EINVAL, "null output pointer");
+  if (n <= 0) return fail(VS_EEMPTY, "empty training set (the reference throws IndexOutOfBoundsException)");
+  if (n > 0x7fffffffLL) return fail(VS_EINVAL, "a Java List cannot hold more than 2^31-1 vectors");
+  ThreadCtx* c;
+  RET(ctx_bind(&c));
+  const float* dX = nullptr;
+  float* owned = nullptr;
+  if (rows) {
+    CK(cudaMalloc(&owned, (size_t)n * d * 4), "cudaMalloc(train rows)");
+    cudaError_t e = cudaMemcpyAsync(owned, rows, (size_t)n * d * 4, cudaMemcpyHostToDevice, c->stream);
+    if (e != cudaSuccess) {
+      cudaFree(owned);
+      return cuda_fail(e, "H2D rows");
+    }
+    dX = owned;
+  } else {
+    Segment* s = seg_lookup(h);
+    if (!s) return fail(VS_EHANDLE, "rows == NULL needs a valid segment handle");
+    if (s->d != d) return fail(VS_EINVAL, "segment dimension %d != d %d", s->d, d);
+    if (n > s->n) return fail(VS_EINVAL, "n exceeds the segment's row count");
+    dX = s->X;
+  }
+  int r = pq_train_device(c->stream, dX, n, d, M, K, iterations, seed, lanes(), centroids_out);
+  if (owned) {
+    cudaStreamSynchronize(c->stream);
+    cudaFree(owned);
+  }
+  return r;
+}
+
+// =================================================================================================
+// device-pointer (stream) variants
+// =================================================================================================
+// Scratch for these comes from the calling thread's context and is only valid until that thread's
+// next libvsgpu call; the caller orders work on `stream` (the multi-GPU coordinator uses one
+// thread and one stream per process).
+int32_t vs_bruteforce_topk_dev(uint64_t h, const float* d_q, int32_t nq, int32_t k, int32_t metric,
+                               int64_t* d_ids, double* d_scores, int32_t* d_counts, void* stream) {
+  Segment* s = seg_lookup(h);
+  RET(check_query_args(s, d_q, nq, k, metric));
+  if (!d_ids || !d_scores || !d_counts) return fail(VS_EINVAL, "null output pointer");
+  ThreadCtx* c;
+  RET(ctx_bind(&c));
+  if (s->n == 0) return fail(VS_EINVAL, "empty segment: use the host variant");
+  ScanPlan p;
+  RET(plan_scan(s, nq, k, metric == VS_METRIC_COSINE, &p));
+  const size_t pb = (size_t)nq * p.grid * k * 16;
+  if (pb > (size_t(1) << 31)) return fail(VS_EINVAL, "query batch too large for the stream variant");
+  RET(ctx_reserve_dev(c, Arena::need({pb})));
+  RET(ctx_reserve_ticket(c, nq));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // ticket memset (if any) ran on c->stream: order it before the caller's stream
+  CK(cudaStreamSynchronize(c->stream), "sync");
+  Arena A(c->d_buf);
+  ulonglong2* dpart = A.take<ulonglong2>((size_t)nq * p.grid * k);
+  return bruteforce_dev(c, st, s, d_q, nq, k, metric, d_ids, d_scores, d_counts, dpart, c->d_ticket, p);
+}
+
+int32_t vs_adc_topk_dev(uint64_t h, const float* d_q, int32_t nq, int32_t n_cand, int64_t* d_ids,
+                        double* d_approx, int32_t* d_counts, void* stream) {
+  Segment* s = seg_lookup(h);
+  RET(check_query_args(s, d_q, nq, n_cand, VS_METRIC_L2));
+  if (!d_ids || !d_approx || !d_counts) return fail(VS_EINVAL, "null output pointer");
+  if (s->M == 0) return fail(VS_ESTATE, "segment has no PQ attached");
+  ThreadCtx* c;
+  RET(ctx_bind(&c));
+  if (s->n == 0) return fail(VS_EINVAL, "empty segment: use the host variant");
+  ScanPlan p;
+  RET(plan_adc(s, nq, n_cand, &p));
+  const size_t pb = (size_t)nq * p.grid * n_cand * 16, lb = (size_t)nq * s->M * s->K * 8;
+  if (pb > (size_t(1) << 31)) return fail(VS_EINVAL, "query batch too large for the stream variant");
+  RET(ctx_reserve_dev(c, Arena::need({pb, lb})));
+  RET(ctx_reserve_ticket(c, nq));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CK(cudaStreamSynchronize(c->stream), "sync");
+  Arena A(c->d_buf);
+  ulonglong2* dpart = A.take<ulonglong2>((size_t)nq * p.grid * n_cand);
+  double* dlut = A.take<double>((size_t)nq * s->M * s->K);
+  return adc_dev(st, s, d_q, nq, n_cand, dlut, d_ids, d_approx, d_counts, dpart, c->d_ticket, p);
+}
+
+int32_t vs_adc_rerank_topk_dev(uint64_t h, const float* d_q, int32_t nq, int32_t n_cand, int32_t k,
+                               int32_t metric, int32_t normalize_on_read, int64_t* d_ids, double* d_scores,
+                               int32_t* d_counts, void* stream) {
+  (void)normalize_on_read;
+  Segment* s = seg_lookup(h);
+  RET(check_query_args(s, d_q, nq, n_cand, metric));
+  if (k <= 0 || k > TOPK_MAX_K) return fail(VS_EINVAL, "k must be in 1..%d", TOPK_MAX_K);
+  if (!d_ids || !d_scores || !d_counts) return fail(VS_EINVAL, "null output pointer");
+  if (s->M == 0) return fail(VS_ESTATE, "segment has no PQ attached");
+  ThreadCtx* c;
+  RET(ctx_bind(&c));
+  if (s->n == 0) return fail(VS_EINVAL, "empty segment: use the host variant");
+  ScanPlan p;
+  RET(plan_adc(s, nq, n_cand, &p));
+  const size_t pb = (size_t)nq * p.grid * n_cand * 16, lb = (size_t)nq * s->M * s->K * 8;
+  const size_t cib = (size_t)nq * n_cand * 8, ccb = (size_t)nq * 4;
+  if (pb > (size_t(1) << 31)) return fail(VS_EINVAL, "query batch too large for the stream variant");
+  RET(ctx_reserve_dev(c, Arena::need({pb, lb, cib, cib, ccb})));
+  RET(ctx_reserve_ticket(c, nq));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CK(cudaStreamSynchronize(c->stream), "sync");
+  Arena A(c->d_buf);
+  ulonglong2* dpart = A.take<ulonglong2>((size_t)nq * p.grid * n_cand);
+  double* dlut = A.take<double>((size_t)nq * s->M * s->K);
+  int64_t* dcid = A.take<int64_t>((size_t)nq * n_cand);
+  double* dcap = A.take<double>((size_t)nq * n_cand);
+  int32_t* dccn = A.take<int32_t>(nq);
+  RET(adc_dev(st, s, d_q, nq, n_cand, dlut, dcid, dcap, dccn, dpart, c->d_ticket, p));
+  return rerank_dev(st, s, d_q, nq, dcid, n_cand, k, metric, d_ids, d_scores, d_counts);
+}
+
+}  // extern "C"

@@ -1,0 +1,31 @@
+// host.h -- host-side declarations shared by the translation units of libvsgpu.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vs {
+
+// A row range of vectors resident in HBM (+ PQ codebook and codes once sealed).
+struct Segment {
+  float* X = nullptr;        // [n][d] fp32, row-major (bit-identical to FloatPacker bytes)
+  uint8_t* skip = nullptr;   // nullable [n]: deleted or gid missing
+  int64_t n = 0;
+  int d = 0;
+  int64_t id_base = 0;
+  float* centroids = nullptr;  // [M][K][subDim]
+  uint8_t* codes = nullptr;    // [n][M]
+  int M = 0, K = 0, subDim = 0;
+};
+
+int fail(int code, const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+int lanes();
+int sm_count();
+Segment* seg_lookup(uint64_t h);
+
+// PqTrainer.train on device-resident rows; centroids_out is HOST memory [M][K][d/M]  (pqtrain.cu)
+int pq_train_device(cudaStream_t st, const float* dX, int64_t n, int d, int M, int K, int iterations,
+                    int64_t seed, int lanes, float* centroids_out);
+
+}  // namespace vs

@@ -1,0 +1,114 @@
+// kernels.h -- host-side launch interface between api.cu and the kernel translation units.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace vs {
+
+constexpr int SCAN_THREADS = 256;
+
+void count_launch();  // bumps the process-wide kernel launch counter (api.cu)
+
+// ---- scan.cu: exact brute-force scan + top-k, one launch --------------------------------------
+struct ScanLaunch {
+  const float* X;        // [n][d] resident rows
+  int64_t n;
+  int d;
+  const float* q;        // [nq][d] device
+  int nq;
+  const uint8_t* skip;   // nullable [n]
+  int lanes;             // modelled SIMD lane count (16 / 8 / 4)
+  bool cosine;
+  int k, kp;             // kp = topk_pad(k)
+  ulonglong2* partial;   // scratch [nq][grid][k]
+  unsigned int* ticket;  // scratch [nq], zero between launches
+  int64_t* ids_out;      // [nq][k]
+  double* scores_out;    // [nq][k]
+  int32_t* counts_out;   // [nq]
+  int64_t id_base;
+  int grid, threads;
+  size_t smem_bytes;
+};
+bool scan_is_streaming(int d, int lanes, bool cosine);
+size_t scan_smem_bytes(int d, int kp, int threads);
+int scan_occupancy(int d, int lanes, bool cosine, int threads, size_t smem);
+cudaError_t launch_scan(const ScanLaunch& L, cudaStream_t st);
+
+// ---- rank.cu: exact scoring + ordering of caller-supplied candidates (re-rank), merge ----------
+struct RankLaunch {
+  const float* X;
+  int64_t n;
+  int d;
+  const uint8_t* skip;
+  int lanes;
+  const float* q;           // [nq][d]
+  int nq;
+  const int64_t* cand_ids;  // [nq][nc] global ids (id_base + row), anything else = missing record
+  int nc;
+  int k;
+  int metric;               // VS_METRIC_*
+  int64_t id_base;
+  int64_t* ids_out;         // [nq][k]
+  double* scores_out;
+  int32_t* counts_out;
+};
+cudaError_t launch_rank(const RankLaunch& L, cudaStream_t st);
+// stable sort by score descending of `total` (id, score) pairs, first k
+cudaError_t launch_merge(const int64_t* ids, const double* scores, int64_t total, int k,
+                         int64_t* ids_out, double* scores_out, int32_t* count_out, cudaStream_t st);
+
+// ---- misc.cu ----------------------------------------------------------------------------------
+// element e of the output = draw (first + e) of new java.util.Random(seed); kind 0: nextFloat()*2f-1f,
+// 1: nextFloat(), 2: nextFloat()*10f  (B/DistanceAndPqBenchmark.java:66-85,127-133)
+cudaError_t launch_generate(float* out, int64_t count, int64_t seed, int64_t first, int kind,
+                            cudaStream_t st);
+enum PairOp { PAIR_L2 = 0, PAIR_L2SQ = 1, PAIR_DOT = 2, PAIR_NORM = 3, PAIR_COSINE = 4 };
+cudaError_t launch_pair(int op, const float* a, const float* b, int len, int lanes, double* out,
+                        cudaStream_t st);
+cudaError_t launch_lut_distance_f32(const float* lut, int M, int K, const uint8_t* codes, float* out,
+                                    cudaStream_t st);
+
+// ---- adc.cu -----------------------------------------------------------------------------------
+// lut64[nq][M][K] in reference arithmetic (buildLut, J/fdb/FdbVectorIndex.java:1067-1079)
+cudaError_t launch_build_lut(const float* centroids, int M, int K, int subDim, const float* q, int nq,
+                             int lanes, double* lut64, cudaStream_t st);
+cudaError_t launch_approx_distance(const double* lut, int M, int K, const uint8_t* codes, int64_t n,
+                                   double* out, cudaStream_t st);
+struct AdcScanLaunch {
+  const uint8_t* codes;  // [n][M]
+  int64_t n;
+  int M, K;
+  const double* lut64;   // [nq][M][K]
+  int nq;
+  int k, kp;
+  ulonglong2* partial;
+  unsigned int* ticket;
+  int64_t* ids_out;
+  double* approx_out;
+  int32_t* counts_out;
+  int64_t id_base;
+  int grid, threads;
+  size_t smem_bytes;
+};
+size_t adc_scan_smem_bytes(int M, int K, int kp, int threads);
+int adc_scan_occupancy(int M, int K, int threads, size_t smem);
+cudaError_t launch_adc_scan(const AdcScanLaunch& L, cudaStream_t st);
+
+// ---- pq.cu ------------------------------------------------------------------------------------
+// PqEncoder.encode / the PqTrainer assignment step over n rows (J/pq/PqEncoder.java:18-37,
+// J/pq/PqTrainer.java:56-68): strict-< argmin over K centroids per subspace, reference arithmetic.
+struct PqAssignLaunch {
+  const float* X;          // [n][d]
+  int64_t n;
+  int d, M, K, subDim;
+  const float* centroids;  // [M][K][subDim]
+  int lanes;
+  uint8_t* codes_u8;       // nullable: [n][M] (best & 0xFF)
+  int32_t* assign_i32;     // nullable: [M][n]
+  int s_begin, s_end;      // subspaces to process
+};
+cudaError_t launch_pq_assign(const PqAssignLaunch& L, cudaStream_t st);
+
+}  // namespace vs

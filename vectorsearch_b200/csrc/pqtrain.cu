@@ -1,0 +1,337 @@
+// pqtrain.cu -- K4: PqTrainer.train (J/pq/PqTrainer.java:28-91) on device-resident rows.
+//
+// Per subspace the reference runs Lloyd's k-means: K initial centroids drawn WITH replacement by
+// rnd.nextInt(n) (:47-50), then `iterations` x { assign (strict-< argmin, :56-68); update:
+// float sums `newC[a][d] += x[d]` IN ROW ORDER plus int counts (:70-77); an empty cluster becomes
+// a copy of data.get(rnd.nextInt(n)) (:79-82), the others are divided by their count in fp32
+// (:84) }.  One java.util.Random(seed) is shared by all subspaces in sequence (:37).
+//
+// What is parallel here and what is not:
+//  * assignment: pq.cu, all subspaces of a wave in one pass over the rows;
+//  * update: fp32 addition is not associative, so a tree/atomic reduction would not reproduce the
+//    reference's sums.  Rows are therefore stably partitioned by cluster (per-warp-block
+//    histograms -> exclusive scan -> in-order scatter) and every (subspace, cluster, component)
+//    chain is summed sequentially in row order by its own thread: M*K*subDim independent chains
+//    (32 768 for the production shape) keep the GPU busy while each chain's order is the
+//    reference's.  Centroids are bit-identical to the JVM's.
+//  * the shared Random couples the subspaces only through the NUMBER of draws each one consumes
+//    (K for the init + one per empty cluster).  All remaining subspaces run together with their
+//    stream positions predicted (duplicate init draws produce exactly one empty cluster each in
+//    iteration 1); the prediction is verified afterwards and the subspaces behind the first
+//    mismatch are replayed with the corrected position.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "../../include/vsgpu.h"
+#include "common.cuh"
+#include "host.h"
+#include "kernels.h"
+
+namespace vs {
+
+namespace {
+
+// ---- java.util.Random on the host (JDK core, fully specified) -----------------------------------------
+struct JRandom {
+  uint64_t s;
+  static constexpr uint64_t MULT = 0x5DEECE66DULL, ADD = 0xBULL, MASK = (1ULL << 48) - 1;
+  explicit JRandom(int64_t seed) : s(((uint64_t)seed ^ MULT) & MASK) {}
+  int32_t next(int bits) {
+    s = (s * MULT + ADD) & MASK;
+    return (int32_t)(uint32_t)(s >> (48 - bits));
+  }
+  int32_t nextInt(int32_t bound) {  // bound > 0
+    int32_t r = next(31);
+    const int32_t m = bound - 1;
+    if ((bound & m) == 0) return (int32_t)(((int64_t)bound * (int64_t)r) >> 31);
+    for (int32_t u = r;;) {
+      r = u % bound;
+      if ((int32_t)((uint32_t)u - (uint32_t)r + (uint32_t)m) >= 0) return r;
+      u = next(31);
+    }
+  }
+};
+
+constexpr int RB = 2048;  // rows per warp-block of the stable partition
+
+// centroids[s][ci] <- sub-vector s of row rows[(s - s_begin) * K + ci]   (rows < 0: leave as is)
+__global__ void gather_subvectors_kernel(const float* __restrict__ X, int d, int K, int sd,
+                                         const int64_t* __restrict__ rows, float* __restrict__ centroids,
+                                         int s_begin, int s_end) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)(s_end - s_begin) * K * sd;
+  if (t >= total) return;
+  const int comp = (int)(t % sd);
+  const int64_t e = t / sd;
+  const int ci = (int)(e % K);
+  const int s = s_begin + (int)(e / K);
+  const int64_t row = rows[e];
+  if (row < 0) return;
+  centroids[((size_t)s * K + ci) * sd + comp] = X[(size_t)row * d + (size_t)s * sd + comp];
+}
+
+// one warp per (row block, subspace): histogram of assignments
+__global__ void __launch_bounds__(32)
+hist_kernel(const int32_t* __restrict__ assign, int64_t n, int K, int nb, int s_begin,
+            int32_t* __restrict__ blockhist) {
+  extern __shared__ int32_t h[];
+  const int b = blockIdx.x;
+  const int sl = blockIdx.y;
+  const int lane = threadIdx.x;
+  for (int i = lane; i < K; i += 32) h[i] = 0;
+  __syncwarp();
+  const int32_t* a = assign + (size_t)(s_begin + sl) * n;
+  const int64_t r0 = (int64_t)b * RB;
+  const int64_t r1 = r0 + RB < n ? r0 + RB : n;
+  for (int64_t r = r0 + lane; r < r1; r += 32) atomicAdd(&h[a[r]], 1);
+  __syncwarp();
+  int32_t* out = blockhist + ((size_t)sl * nb + b) * K;
+  for (int i = lane; i < K; i += 32) out[i] = h[i];
+}
+
+// thread per (subspace, cluster): exclusive prefix over row blocks, in place; totals -> counts
+__global__ void scan_blocks_kernel(int32_t* __restrict__ blockhist, int K, int nb, int ns,
+                                   int32_t* __restrict__ counts /* [ns][K] */) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ns * K) return;
+  const int sl = t / K, ci = t % K;
+  int32_t run = 0;
+  int32_t* p = blockhist + (size_t)sl * nb * K + ci;
+  for (int b = 0; b < nb; b++) {
+    const int32_t v = p[(size_t)b * K];
+    p[(size_t)b * K] = run;
+    run += v;
+  }
+  counts[t] = run;
+}
+
+// one thread per subspace: offsets[sl][0..K] = exclusive scan of counts
+__global__ void scan_clusters_kernel(const int32_t* __restrict__ counts, int K, int ns,
+                                     int32_t* __restrict__ offsets /* [ns][K+1] */) {
+  const int sl = blockIdx.x * blockDim.x + threadIdx.x;
+  if (sl >= ns) return;
+  int32_t run = 0;
+  for (int ci = 0; ci < K; ci++) {
+    offsets[(size_t)sl * (K + 1) + ci] = run;
+    run += counts[(size_t)sl * K + ci];
+  }
+  offsets[(size_t)sl * (K + 1) + K] = run;
+}
+
+// one warp per (row block, subspace): rows visited in ascending order, each written to its
+// cluster's next free slot -> order[sl][...] lists every cluster's members in row order
+__global__ void __launch_bounds__(32)
+scatter_kernel(const int32_t* __restrict__ assign, int64_t n, int K, int nb, int s_begin,
+               const int32_t* __restrict__ blockprefix, const int32_t* __restrict__ offsets,
+               int32_t* __restrict__ order) {
+  extern __shared__ int32_t pos[];
+  const int b = blockIdx.x;
+  const int sl = blockIdx.y;
+  const int lane = threadIdx.x;
+  const int32_t* bp = blockprefix + ((size_t)sl * nb + b) * K;
+  const int32_t* off = offsets + (size_t)sl * (K + 1);
+  for (int i = lane; i < K; i += 32) pos[i] = off[i] + bp[i];
+  __syncwarp();
+  const int32_t* a = assign + (size_t)(s_begin + sl) * n;
+  int32_t* ord = order + (size_t)sl * n;
+  const int64_t r0 = (int64_t)b * RB;
+  const int64_t r1 = r0 + RB < n ? r0 + RB : n;
+  for (int64_t rb = r0; rb < r1; rb += 32) {
+    const int64_t r = rb + lane;
+    const bool live = r < r1;
+    const int32_t ci = live ? a[r] : -1 - lane;  // dead lanes get unique keys
+    const unsigned peers = __match_any_sync(FULL_MASK, ci);
+    const int rank = __popc(peers & ((1u << lane) - 1u));
+    int32_t base = 0;
+    if (live) base = pos[ci];
+    __syncwarp();
+    if (live) {
+      ord[base + rank] = (int32_t)r;
+      if (rank == 0) pos[ci] = base + __popc(peers);
+    }
+    __syncwarp();
+  }
+}
+
+// thread per (subspace, cluster, component): sequential fp32 sum over the cluster's rows in row order
+__global__ void __launch_bounds__(256)
+chain_sum_kernel(const float* __restrict__ X, int64_t n, int d, int K, int sd, int s_begin, int ns,
+                 const int32_t* __restrict__ order, const int32_t* __restrict__ offsets,
+                 float* __restrict__ sums /* [ns][K][sd] */) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)ns * K * sd) return;
+  const int comp = (int)(t % sd);
+  const int64_t e = t / sd;
+  const int ci = (int)(e % K);
+  const int sl = (int)(e / K);
+  const int32_t* ord = order + (size_t)sl * n;
+  const int32_t j0 = offsets[(size_t)sl * (K + 1) + ci];
+  const int32_t j1 = offsets[(size_t)sl * (K + 1) + ci + 1];
+  const float* col = X + (size_t)(s_begin + sl) * sd + comp;
+  float acc = 0.0f;
+  int32_t j = j0;
+  for (; j + 8 <= j1; j += 8) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) v[u] = __ldg(col + (size_t)ord[j + u] * d);
+#pragma unroll
+    for (int u = 0; u < 8; u++) acc = __fadd_rn(acc, v[u]);
+  }
+  for (; j < j1; j++) acc = __fadd_rn(acc, __ldg(col + (size_t)ord[j] * d));
+  sums[t] = acc;
+}
+
+// centroid = count ? sum / (float)count : sub-vector of the re-init row   (PqTrainer.java:78-87)
+__global__ void finalize_kernel(const float* __restrict__ X, int d, int K, int sd, int s_begin, int ns,
+                                const float* __restrict__ sums, const int32_t* __restrict__ counts,
+                                const int64_t* __restrict__ reinit, float* __restrict__ centroids) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)ns * K * sd) return;
+  const int comp = (int)(t % sd);
+  const int64_t e = t / sd;
+  const int ci = (int)(e % K);
+  const int sl = (int)(e / K);
+  const int s = s_begin + sl;
+  const int32_t c = counts[e];
+  float v;
+  if (c == 0)
+    v = X[(size_t)reinit[e] * d + (size_t)s * sd + comp];
+  else
+    v = __fdiv_rn(sums[t], (float)c);
+  centroids[((size_t)s * K + ci) * sd + comp] = v;
+}
+
+struct DevBuf {
+  void* p = nullptr;
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+  template <typename T>
+  T* as() { return static_cast<T*>(p); }
+};
+
+#define TCK(call, what)                                 \
+  do {                                                  \
+    cudaError_t _e = (call);                            \
+    if (_e != cudaSuccess) return cuda_fail(_e, what);  \
+  } while (0)
+
+}  // namespace
+
+int pq_train_device(cudaStream_t st, const float* dX, int64_t n, int d, int M, int K, int iterations,
+                    int64_t seed, int lanes_, float* centroids_out) {
+  const int sd = d / M;
+  if ((size_t)K * 4 > 96 * 1024) return fail(VS_EINVAL, "K too large for the device trainer (max 24576)");
+  const int nb = (int)((n + RB - 1) / RB);
+  DevBuf b_cent, b_assign, b_order, b_hist, b_counts, b_offsets, b_sums, b_rows;
+  TCK(b_cent.alloc((size_t)M * K * sd * 4), "cudaMalloc(centroids)");
+  TCK(b_assign.alloc((size_t)M * n * 4), "cudaMalloc(assign)");
+  TCK(b_order.alloc((size_t)M * n * 4), "cudaMalloc(order)");
+  TCK(b_hist.alloc((size_t)M * nb * K * 4), "cudaMalloc(blockhist)");
+  TCK(b_counts.alloc((size_t)M * K * 4), "cudaMalloc(counts)");
+  TCK(b_offsets.alloc((size_t)M * (K + 1) * 4), "cudaMalloc(offsets)");
+  TCK(b_sums.alloc((size_t)M * K * sd * 4), "cudaMalloc(sums)");
+  TCK(b_rows.alloc((size_t)M * K * 8), "cudaMalloc(rows)");
+  float* d_cent = b_cent.as<float>();
+  int32_t* d_assign = b_assign.as<int32_t>();
+  int32_t* d_order = b_order.as<int32_t>();
+  int32_t* d_hist = b_hist.as<int32_t>();
+  int32_t* d_counts = b_counts.as<int32_t>();
+  int32_t* d_offsets = b_offsets.as<int32_t>();
+  float* d_sums = b_sums.as<float>();
+  int64_t* d_rows = b_rows.as<int64_t>();
+
+  const size_t ksmem = (size_t)K * 4;
+  if (ksmem > 48 * 1024) {
+    TCK(cudaFuncSetAttribute(hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ksmem), "smem attr");
+    TCK(cudaFuncSetAttribute(scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ksmem), "smem attr");
+  }
+
+  JRandom rnd(seed);
+  std::vector<int64_t> h_rows((size_t)M * K);
+  std::vector<int32_t> h_counts((size_t)M * K);
+  std::vector<JRandom> cur(M, JRandom(0));
+  std::vector<int> predicted(M), actual(M);
+
+  int s0 = 0;
+  while (s0 < M) {
+    const int ns = M - s0;
+    // ---- plan the wave: init draws at predicted stream positions --------------------------------
+    JRandom r = rnd;
+    for (int s = s0; s < M; s++) {
+      int64_t* rows = h_rows.data() + (size_t)(s - s0) * K;
+      for (int ci = 0; ci < K; ci++) rows[ci] = r.nextInt((int32_t)n);  // PqTrainer.java:48
+      cur[s] = r;
+      int dups = 0;
+      if (iterations > 0) {
+        std::vector<int64_t> sorted(rows, rows + K);
+        std::sort(sorted.begin(), sorted.end());
+        for (int i = 1; i < K; i++) dups += sorted[i] == sorted[i - 1];
+      }
+      predicted[s] = dups;
+      actual[s] = 0;
+      for (int e = 0; e < dups; e++) r.nextInt((int32_t)n);
+    }
+    TCK(cudaMemcpyAsync(d_rows, h_rows.data(), (size_t)ns * K * 8, cudaMemcpyHostToDevice, st), "H2D init rows");
+    {
+      const int64_t total = (int64_t)ns * K * sd;
+      gather_subvectors_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dX, d, K, sd, d_rows, d_cent, s0, M);
+      count_launch();
+      TCK(cudaGetLastError(), "gather launch");
+    }
+    TCK(cudaStreamSynchronize(st), "sync");  // h_rows is reused below
+
+    for (int it = 0; it < iterations; it++) {
+      PqAssignLaunch L{};
+      L.X = dX; L.n = n; L.d = d; L.M = M; L.K = K; L.subDim = sd; L.centroids = d_cent; L.lanes = lanes_;
+      L.codes_u8 = nullptr; L.assign_i32 = d_assign; L.s_begin = s0; L.s_end = M;
+      TCK(launch_pq_assign(L, st), "pq assign launch");
+      hist_kernel<<<dim3(nb, ns), 32, ksmem, st>>>(d_assign, n, K, nb, s0, d_hist);
+      count_launch();
+      TCK(cudaGetLastError(), "hist launch");
+      scan_blocks_kernel<<<(ns * K + 127) / 128, 128, 0, st>>>(d_hist, K, nb, ns, d_counts);
+      count_launch();
+      scan_clusters_kernel<<<(ns + 31) / 32, 32, 0, st>>>(d_counts, K, ns, d_offsets);
+      count_launch();
+      scatter_kernel<<<dim3(nb, ns), 32, ksmem, st>>>(d_assign, n, K, nb, s0, d_hist, d_offsets, d_order);
+      count_launch();
+      TCK(cudaGetLastError(), "scatter launch");
+      const int64_t total = (int64_t)ns * K * sd;
+      chain_sum_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dX, n, d, K, sd, s0, ns, d_order, d_offsets, d_sums);
+      count_launch();
+      TCK(cudaGetLastError(), "chain launch");
+      TCK(cudaMemcpyAsync(h_counts.data(), d_counts, (size_t)ns * K * 4, cudaMemcpyDeviceToHost, st), "D2H counts");
+      TCK(cudaStreamSynchronize(st), "sync");
+      for (int s = s0; s < M; s++) {
+        for (int ci = 0; ci < K; ci++) {
+          const size_t e = (size_t)(s - s0) * K + ci;
+          if (h_counts[e] == 0) {
+            h_rows[e] = cur[s].nextInt((int32_t)n);  // PqTrainer.java:81
+            actual[s]++;
+          } else {
+            h_rows[e] = -1;
+          }
+        }
+      }
+      TCK(cudaMemcpyAsync(d_rows, h_rows.data(), (size_t)ns * K * 8, cudaMemcpyHostToDevice, st), "H2D reinit rows");
+      finalize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dX, d, K, sd, s0, ns, d_sums, d_counts, d_rows, d_cent);
+      count_launch();
+      TCK(cudaGetLastError(), "finalize launch");
+      TCK(cudaStreamSynchronize(st), "sync");
+    }
+    // ---- verify the predicted stream positions -------------------------------------------------------
+    int s = s0;
+    for (; s < M; s++)
+      if (actual[s] != predicted[s]) break;
+    if (s >= M) break;   // every subspace of the wave started where the reference would have
+    rnd = cur[s];        // subspace s itself is right; everything behind it is replayed
+    s0 = s + 1;
+  }
+  TCK(cudaMemcpyAsync(centroids_out, d_cent, (size_t)M * K * sd * 4, cudaMemcpyDeviceToHost, st), "D2H centroids");
+  TCK(cudaStreamSynchronize(st), "sync");
+  return VS_OK;
+}
+
+}  // namespace vs

@@ -1,0 +1,151 @@
+// rank.cu -- exact scoring + final ordering of a short candidate list, and the cross-segment merge.
+//
+// Re-rank = fetchExactAndScore (J/fdb/FdbVectorIndex.java:997-1043): candidates are scored IN THE
+// GIVEN ORDER with Distances.l2 / cosine (normalizeOnRead evaluates the same expression with
+// norm(q) hoisted, :1006-1010), missing / deleted / gid-less records are dropped (:1000,:1022),
+// the list is stably sorted by score descending (:1031) and cut to k (:1042): ties keep candidate
+// order.  Merge = query() :432-437: concatenated per-segment lists, stable sort by score
+// descending, first k.
+//
+// One CTA per query.  A half-warp scores one candidate with the reference's lane arithmetic
+// (thread l of the half-warp is SIMD lane l), the block sorts (score image, position) keys.
+#include "kernels.h"
+#include "topk.cuh"
+
+namespace vs {
+
+constexpr int RANK_THREADS = 256;
+constexpr int RANK_MAX_CAND = 8192;
+
+__device__ __forceinline__ void block_bitonic_sort_keys(ulonglong2* a, int n) {
+  for (int size = 2; size <= n; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = threadIdx.x; t < (n >> 1); t += blockDim.x) {
+        int i = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));
+        cswap(a, i, i | stride, (i & size) == 0);
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(RANK_THREADS)
+rank_kernel(const float* __restrict__ X, int64_t n, int d, const uint8_t* __restrict__ skip, int lanes,
+            const float* __restrict__ Q, const int64_t* __restrict__ cand_ids, int nc, int np, int k,
+            int cosine, int64_t id_base, int64_t* __restrict__ ids_out, double* __restrict__ scores_out,
+            int32_t* __restrict__ counts_out) {
+  extern __shared__ __align__(16) ulonglong2 skey[];  // [np]
+  const int qi = blockIdx.x;
+  const float* q = Q + (size_t)qi * d;
+  const int64_t* cand = cand_ids + (size_t)qi * nc;
+  const int lane = threadIdx.x & 31;
+  const int hl = lane & 15;
+  const int hw = threadIdx.x >> 4;
+  const int nhw = blockDim.x >> 4;
+  const unsigned hmask = (lane < 16) ? 0x0000ffffu : 0xffff0000u;
+  const int base_lane = lane & 16;
+
+  for (int i = threadIdx.x; i < np; i += blockDim.x) st_key(skey + i, key_empty());
+  __syncthreads();
+  double qq = 0.0;
+  if (cosine) qq = ref_sum_halfwarp<REF_DOT>(q, q, d, lanes, hl, hmask, base_lane);
+  for (int c = hw; c < nc; c += nhw) {
+    const int64_t g = cand[c];
+    const int64_t row = g - id_base;
+    bool ok = g >= 0 && row >= 0 && row < n;      // rec == null otherwise
+    if (ok && skip != nullptr && skip[row]) ok = false;  // deleted / gid missing
+    if (!ok) continue;                             // uniform across the half-warp
+    const float* x = X + (size_t)row * d;
+    double score;
+    if (cosine) {
+      const double dot = ref_sum_halfwarp<REF_DOT>(q, x, d, lanes, hl, hmask, base_lane);
+      const double xx = ref_sum_halfwarp<REF_DOT>(x, x, d, lanes, hl, hmask, base_lane);
+      score = ref_cosine_from_sums(dot, qq, xx);
+    } else {
+      score = -__dsqrt_rn(ref_sum_halfwarp<REF_L2SQ>(q, x, d, lanes, hl, hmask, base_lane));
+    }
+    if (hl == 0) st_key(skey + c, Key{rank_hi_from_score(score), (uint64_t)c});
+  }
+  __syncthreads();
+  block_bitonic_sort_keys(skey, np);
+  __shared__ int s_found;
+  if (threadIdx.x == 0) s_found = 0;
+  __syncthreads();
+  int found = 0;
+  for (int i = threadIdx.x; i < k; i += blockDim.x) {
+    Key e = i < np ? ld_key(skey + i) : key_empty();
+    const bool ok = !key_is_empty(e);
+    ids_out[(size_t)qi * k + i] = ok ? cand[e.lo] : -1;
+    scores_out[(size_t)qi * k + i] = ok ? score_from_rank_hi(e.hi) : __longlong_as_double(0x7ff8000000000000ll);
+    found += ok ? 1 : 0;
+  }
+  if (found) atomicAdd(&s_found, found);
+  __syncthreads();
+  if (threadIdx.x == 0) counts_out[qi] = s_found;
+}
+
+__global__ void __launch_bounds__(RANK_THREADS)
+merge_kernel(const int64_t* __restrict__ ids, const double* __restrict__ scores, int64_t total, int k,
+             int kp, int64_t* __restrict__ ids_out, double* __restrict__ scores_out,
+             int32_t* __restrict__ count_out) {
+  extern __shared__ __align__(16) ulonglong2 smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nw = blockDim.x >> 5;
+  const int stride_keys = kp + TOPK_BUF;
+  WarpTopK tk;
+  tk.init(smem + (size_t)warp * stride_keys, kp, k, lane);
+  for (int64_t i0 = (int64_t)warp * 32; i0 < total; i0 += (int64_t)nw * 32) {
+    const int64_t i = i0 + lane;
+    Key key = key_empty();
+    if (i < total) key = Key{rank_hi_from_score(scores[i]), (uint64_t)i};
+    tk.push(key, i < total, lane);
+  }
+  tk.flush(lane);
+  block_combine_lists(smem, stride_keys, nw, kp, warp, lane);
+  __shared__ int s_found;
+  if (threadIdx.x == 0) s_found = 0;
+  __syncthreads();
+  int found = 0;
+  for (int i = threadIdx.x; i < k; i += blockDim.x) {
+    Key e = ld_key(smem + i);
+    const bool ok = !key_is_empty(e);
+    ids_out[i] = ok ? ids[e.lo] : -1;
+    scores_out[i] = ok ? score_from_rank_hi(e.hi) : __longlong_as_double(0x7ff8000000000000ll);
+    found += ok ? 1 : 0;
+  }
+  if (found) atomicAdd(&s_found, found);
+  __syncthreads();
+  if (threadIdx.x == 0) *count_out = s_found;
+}
+
+cudaError_t launch_rank(const RankLaunch& L, cudaStream_t st) {
+  if (L.nc > RANK_MAX_CAND) return cudaErrorInvalidValue;
+  int np = 2;
+  while (np < L.nc) np <<= 1;
+  const size_t smem = (size_t)np * 16;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  rank_kernel<<<L.nq, RANK_THREADS, smem, st>>>(L.X, L.n, L.d, L.skip, L.lanes, L.q, L.cand_ids, L.nc, np,
+                                               L.k, L.metric == 1, L.id_base, L.ids_out, L.scores_out,
+                                               L.counts_out);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_merge(const int64_t* ids, const double* scores, int64_t total, int k,
+                         int64_t* ids_out, double* scores_out, int32_t* count_out, cudaStream_t st) {
+  const int kp = topk_pad(k);
+  const size_t smem = (size_t)(RANK_THREADS / 32) * topk_warp_smem(kp);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  merge_kernel<<<1, RANK_THREADS, smem, st>>>(ids, scores, total, k, kp, ids_out, scores_out, count_out);
+  count_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace vs
