@@ -141,6 +141,17 @@ int32_t vs_adc_topk_dev(uint64_t h, const float* d_q, int32_t nq, int32_t n_cand
 int32_t vs_adc_rerank_topk_dev(uint64_t h, const float* d_q, int32_t nq, int32_t n_cand, int32_t k,
                                int32_t metric, int32_t normalize_on_read, int64_t* d_ids,
                                double* d_scores, int32_t* d_counts, void* stream);
+/* Packed variants for the multi-GPU merge (one collective per query batch): d_pack is [nq][2k]
+ * int64 -- k ids (id_base + row, -1 = empty slot) followed by the k score bit patterns. */
+int32_t vs_bruteforce_topk_packed_dev(uint64_t h, const float* d_q, int32_t nq, int32_t k, int32_t metric,
+                                      int64_t* d_pack, int32_t* d_counts, void* stream);
+/* d_gath is the all-gathered [world][nq][2k] buffer: per query, lists concatenated in rank order,
+ * stable sort by score descending (descending != 0) or distance ascending, first k
+ * (J/fdb/FdbVectorIndex.java:432-437 with shards in the role of segments). */
+int32_t vs_merge_packed_dev(const int64_t* d_gath, int32_t world, int32_t nq, int32_t k, int32_t descending,
+                            int64_t* d_ids_out, double* d_scores_out, int32_t* d_counts_out, void* stream);
+int32_t vs_merge_topk_dev(const int64_t* d_ids, const double* d_scores, int64_t total, int32_t k,
+                          int64_t* d_ids_out, double* d_scores_out, int32_t* d_count_out, void* stream);
 /* number of kernels this library has launched so far in this process (for gpu_launches) */
 int64_t vs_kernel_launch_count(void);
 

@@ -26,10 +26,10 @@ _u8p = C.POINTER(C.c_uint8)
 _i64p = C.POINTER(C.c_int64)
 
 
-def build(native: bool = False) -> Path:
+def build(native: bool = False, force: bool = False) -> Path:
     """Compile the oracle with the Makefile beside it (gcc only, no reference build system)."""
     target = "libvsoracle_native.so" if native else "libvsoracle.so"
-    subprocess.run(["make", "-C", str(_HERE), target], check=True, capture_output=True)
+    subprocess.run(["make", "-C", str(_HERE)] + (["-B"] if force else []) + [target], check=True, capture_output=True)
     return _HERE / target
 
 

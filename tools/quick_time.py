@@ -48,6 +48,9 @@ for _ in range(200):
     seg.bruteforce_topk(qh, 10)
 print(f"host e2e: {(time.perf_counter()-t0)/200*1e6:.1f} us/query")
 
+import os
+if os.environ.get('BF_ONLY'):
+    seg.free(); sys.exit(0)
 # ADC
 M, K = 16, 256
 t0 = time.perf_counter()

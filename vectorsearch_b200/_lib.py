@@ -60,6 +60,9 @@ SIGNATURES = {
     "vs_bruteforce_topk_dev": (i32, [u64, vp, i32, i32, i32, vp, vp, vp, vp]),
     "vs_adc_topk_dev": (i32, [u64, vp, i32, i32, vp, vp, vp, vp]),
     "vs_adc_rerank_topk_dev": (i32, [u64, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp]),
+    "vs_bruteforce_topk_packed_dev": (i32, [u64, vp, i32, i32, i32, vp, vp, vp]),
+    "vs_merge_packed_dev": (i32, [vp, i32, i32, i32, i32, vp, vp, vp, vp]),
+    "vs_merge_topk_dev": (i32, [vp, vp, i64, i32, vp, vp, vp, vp]),
     "vs_kernel_launch_count": (i64, []),
 }
 

@@ -72,7 +72,7 @@ cudaError_t launch_approx_distance(const double* lut, int M, int K, const uint8_
 // fp32 estimate vs exact fp64 sum: each fp32 LUT entry is within 2^-24 relative of the double,
 // M-1 fp32 adds of non-negative terms add 2^-24 each -> (M+1) * 2^-24; doubled for slack.
 __device__ __forceinline__ float adc_filter_threshold(const Key& thr, int M) {
-  if (key_is_empty(thr)) return __int_as_float(0x7f800000);
+  if (thr.hi == KEY_EMPTY64) return __int_as_float(0x7f800000);
   const double val = dist_from_rank_hi(thr.hi);
   if (val != val) return __int_as_float(0x7f800000);  // k-th is NaN: every non-NaN row beats it
   const double m = val * (1.0 + (double)(M + 2) * (1.0 / 8388608.0)) + 1e-37;
@@ -83,11 +83,11 @@ __device__ __forceinline__ float adc_filter_threshold(const Key& thr, int M) {
 constexpr int ADC_KS = 256;  // shared LUT row stride: codes are bytes, entries >= K read 0
 
 // MW = M/4 words per code row (M % 4 == 0), U rows in flight per thread.
-template <int MW, int U>
+template <int MW, int U, class TK>
 __global__ void __launch_bounds__(SCAN_THREADS)
 adc_scan_kernel(const uint8_t* __restrict__ codes, int64_t n, int K, const double* __restrict__ LUT64,
                 int k, int kp, TopkOut out) {
-  extern __shared__ __align__(16) ulonglong2 smem[];
+  extern __shared__ __align__(128) ulonglong2 smem[];
   constexpr int M = MW * 4;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -95,9 +95,9 @@ adc_scan_kernel(const uint8_t* __restrict__ codes, int64_t n, int K, const doubl
   const int stride_keys = kp + TOPK_BUF;
   const double* __restrict__ lut64 = LUT64 + (size_t)blockIdx.y * M * K;
 
-  WarpTopK tk;
+  TK tk;
   tk.init(smem + (size_t)warp * stride_keys, kp, k, lane);
-  float* lut = reinterpret_cast<float*>(smem + (size_t)nw * stride_keys);
+  float* lut = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(smem) + ((topk_block_smem(k, kp, nw) + 15) / 16) * 16);
   for (int i = threadIdx.x; i < M * ADC_KS; i += blockDim.x) {
     const int s = i / ADC_KS, c = i % ADC_KS;
     lut[i] = c < K ? (float)lut64[(size_t)s * K + c] : 0.0f;
@@ -161,16 +161,17 @@ adc_scan_kernel(const uint8_t* __restrict__ codes, int64_t n, int K, const doubl
 }
 
 // any M: byte loads, exact fp64 for every row (no estimate).  Correctness path for odd shapes.
+template <class TK>
 __global__ void __launch_bounds__(SCAN_THREADS)
 adc_scan_generic_kernel(const uint8_t* __restrict__ codes, int64_t n, int M, int K,
                         const double* __restrict__ LUT64, int k, int kp, TopkOut out) {
-  extern __shared__ __align__(16) ulonglong2 smem[];
+  extern __shared__ __align__(128) ulonglong2 smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int nw = blockDim.x >> 5;
   const int stride_keys = kp + TOPK_BUF;
   const double* __restrict__ lut64 = LUT64 + (size_t)blockIdx.y * M * K;
-  WarpTopK tk;
+  TK tk;
   tk.init(smem + (size_t)warp * stride_keys, kp, k, lane);
   __syncthreads();
   const int64_t nb = (n + 31) / 32;
@@ -192,62 +193,64 @@ static cudaError_t set_smem(KERN kern, size_t smem) {
 
 static bool adc_is_streaming(int M, int K) { return K <= 256 && (M == 8 || M == 16 || M == 32 || M == 64); }
 
-size_t adc_scan_smem_bytes(int M, int K, int kp, int threads) {
-  size_t s = (size_t)(threads / 32) * topk_warp_smem(kp);
-  if (adc_is_streaming(M, K)) s += (size_t)M * ADC_KS * 4;
-  return s;
-}
-
-template <int MW, int U>
-static int adc_occ_t(int threads, size_t smem) {
-  auto kern = adc_scan_kernel<MW, U>;
-  if (set_smem(kern, smem) != cudaSuccess) return 0;
-  int nb = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, threads, smem) != cudaSuccess) nb = 0;
-  return nb;
-}
-
-int adc_scan_occupancy(int M, int K, int threads, size_t smem) {
-  if (!adc_is_streaming(M, K)) {
-    int nb = 0;
-    set_smem(adc_scan_generic_kernel, smem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, adc_scan_generic_kernel, threads, smem);
-    return nb;
-  }
+typedef void (*AdcKern)(const uint8_t*, int64_t, int, const double*, int, int, TopkOut);
+typedef void (*AdcGenKern)(const uint8_t*, int64_t, int, int, const double*, int, int, TopkOut);
+template <class TK>
+static AdcKern adc_kernel(int M) {
   switch (M) {
-    case 8: return adc_occ_t<2, 8>(threads, smem);
-    case 16: return adc_occ_t<4, 4>(threads, smem);
-    case 32: return adc_occ_t<8, 2>(threads, smem);
-    default: return adc_occ_t<16, 1>(threads, smem);
+    case 8: return adc_scan_kernel<2, 8, TK>;
+    case 16: return adc_scan_kernel<4, 4, TK>;
+    case 32: return adc_scan_kernel<8, 2, TK>;
+    default: return adc_scan_kernel<16, 1, TK>;
   }
 }
+static AdcKern pick_adc(int M, int k) { return k <= TOPK_REG_MAX_K ? adc_kernel<WarpTopKReg>(M) : adc_kernel<WarpTopK>(M); }
+static AdcGenKern pick_adc_generic(int k) {
+  return k <= TOPK_REG_MAX_K ? adc_scan_generic_kernel<WarpTopKReg> : adc_scan_generic_kernel<WarpTopK>;
+}
 
-template <int MW, int U>
-static cudaError_t adc_launch_t(const AdcScanLaunch& L, const TopkOut& o, cudaStream_t st) {
-  auto kern = adc_scan_kernel<MW, U>;
-  cudaError_t e = set_smem(kern, L.smem_bytes);
-  if (e != cudaSuccess) return e;
-  kern<<<dim3(L.grid, L.nq), L.threads, L.smem_bytes, st>>>(L.codes, L.n, L.K, L.lut64, L.k, L.kp, o);
-  count_launch();
-  return cudaGetLastError();
+bool adc_configure(AdcScanLaunch& L, int sms) {
+  L.kp = topk_pad(L.k);
+  L.threads = SCAN_THREADS;
+  const bool streaming = adc_is_streaming(L.M, L.K);
+  const size_t lut = streaming ? (size_t)L.M * ADC_KS * 4 : 0;
+  while (((topk_block_smem(L.k, L.kp, L.threads / 32) + 15) / 16) * 16 + lut > 200 * 1024 && L.threads > 32) L.threads /= 2;
+  L.smem_bytes = ((topk_block_smem(L.k, L.kp, L.threads / 32) + 15) / 16) * 16 + lut;
+  int occ = 0;
+  if (streaming) {
+    AdcKern kern = pick_adc(L.M, L.k);
+    if (set_smem(kern, L.smem_bytes) != cudaSuccess) return false;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, L.threads, L.smem_bytes);
+  } else {
+    AdcGenKern kern = pick_adc_generic(L.k);
+    if (set_smem(kern, L.smem_bytes) != cudaSuccess) return false;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, L.threads, L.smem_bytes);
+  }
+  if (occ < 1) return false;
+  if (occ > 8) occ = 8;
+  int64_t grid = (int64_t)sms * (L.nq > 1 ? 1 : occ);
+  if (L.k <= TOPK_REG_MAX_K && grid > TOPK_MAX_LISTS) grid = TOPK_MAX_LISTS;
+  const int64_t cap = (L.n + 127) / 128;
+  if (grid > cap) grid = cap;
+  L.grid = (int)(grid < 1 ? 1 : grid);
+  L.partial_keys = topk_partial_keys(L.k, L.grid, L.threads / 32);
+  return true;
 }
 
 cudaError_t launch_adc_scan(const AdcScanLaunch& L, cudaStream_t st) {
-  TopkOut o{L.partial, L.ticket, L.ids_out, L.approx_out, L.counts_out, L.id_base, 1};
+  TopkOut o{L.partial, L.ctrl, L.partial_keys, L.ids_out, L.approx_out, L.counts_out, L.id_base, 1, L.out_stride > 0 ? L.out_stride : L.k};
+  count_launch();
+  cudaError_t e;
   if (!adc_is_streaming(L.M, L.K)) {
-    cudaError_t e = set_smem(adc_scan_generic_kernel, L.smem_bytes);
-    if (e != cudaSuccess) return e;
-    adc_scan_generic_kernel<<<dim3(L.grid, L.nq), L.threads, L.smem_bytes, st>>>(L.codes, L.n, L.M, L.K,
-                                                                                 L.lut64, L.k, L.kp, o);
-    count_launch();
-    return cudaGetLastError();
+    AdcGenKern kern = pick_adc_generic(L.k);
+    if ((e = set_smem(kern, L.smem_bytes)) != cudaSuccess) return e;
+    kern<<<dim3(L.grid, L.nq), L.threads, L.smem_bytes, st>>>(L.codes, L.n, L.M, L.K, L.lut64, L.k, L.kp, o);
+  } else {
+    AdcKern kern = pick_adc(L.M, L.k);
+    if ((e = set_smem(kern, L.smem_bytes)) != cudaSuccess) return e;
+    kern<<<dim3(L.grid, L.nq), L.threads, L.smem_bytes, st>>>(L.codes, L.n, L.K, L.lut64, L.k, L.kp, o);
   }
-  switch (L.M) {
-    case 8: return adc_launch_t<2, 8>(L, o, st);
-    case 16: return adc_launch_t<4, 4>(L, o, st);
-    case 32: return adc_launch_t<8, 2>(L, o, st);
-    default: return adc_launch_t<16, 1>(L, o, st);
-  }
+  return cudaGetLastError();
 }
 
 }  // namespace vs

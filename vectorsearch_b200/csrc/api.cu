@@ -56,7 +56,7 @@ struct ThreadCtx {
   size_t d_cap = 0;
   void* h_buf = nullptr;  // pinned
   size_t h_cap = 0;
-  unsigned int* d_ticket = nullptr;  // zero between launches
+  unsigned long long* d_ticket = nullptr;  // [queries][4] control words, zero between launches
   size_t ticket_cap = 0;
   ~ThreadCtx() {
     // process teardown: the context may already be gone; ignore errors
@@ -117,9 +117,9 @@ static int ctx_reserve_ticket(ThreadCtx* c, size_t n) {
   c->d_ticket = nullptr;
   c->ticket_cap = 0;
   size_t cap = n < 1024 ? 1024 : n * 2;
-  cudaError_t e = cudaMalloc(&c->d_ticket, cap * sizeof(unsigned int));
+  cudaError_t e = cudaMalloc(&c->d_ticket, cap * 4 * sizeof(unsigned long long));
   if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(ticket)");
-  e = cudaMemsetAsync(c->d_ticket, 0, cap * sizeof(unsigned int), c->stream);
+  e = cudaMemsetAsync(c->d_ticket, 0, cap * 4 * sizeof(unsigned long long), c->stream);
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemset(ticket)");
   c->ticket_cap = cap;
   return VS_OK;
@@ -182,42 +182,71 @@ struct ScanPlan {
   size_t smem;
 };
 
-static int plan_scan(const Segment* s, int nq, int k, bool cosine, ScanPlan* p) {
-  p->kp = topk_pad(k);
-  p->threads = SCAN_THREADS;
-  p->smem = scan_smem_bytes(s->d, p->kp, p->threads);
-  while (p->smem > 200 * 1024 && p->threads > 64) {
-    p->threads /= 2;
-    p->smem = scan_smem_bytes(s->d, p->kp, p->threads);
+// occupancy queries (and the smem attribute they set) are cached per kernel configuration
+static std::mutex g_occ_mu;
+static std::unordered_map<uint64_t, int> g_occ_cache;
+template <typename F>
+static int cached_occ(uint64_t key, F compute) {
+  {
+    std::lock_guard<std::mutex> lk(g_occ_mu);
+    auto it = g_occ_cache.find(key);
+    if (it != g_occ_cache.end()) return it->second;
   }
-  int occ = scan_occupancy(s->d, lanes(), cosine, p->threads, p->smem);
-  if (occ < 1) return fail(VS_ECUDA, "scan kernel cannot be resident (smem %zu)", p->smem);
-  if (occ > 8) occ = 8;
-  int64_t grid = (int64_t)g_sms * (nq > 1 ? 1 : occ);
-  // never more CTAs than 16-row batches
-  int64_t cap = (s->n + 15) / 16;
-  if (cap < 1) cap = 1;
-  if (grid > cap) grid = cap;
-  p->grid = (int)grid;
+  const int occ = compute();
+  std::lock_guard<std::mutex> lk(g_occ_mu);
+  g_occ_cache[key] = occ;
+  return occ;
+}
+static uint64_t occ_key(int kind, int a, int b, int c, int threads, size_t smem) {
+  uint64_t h = 1469598103934665603ull;
+  for (uint64_t v : {(uint64_t)kind, (uint64_t)a, (uint64_t)b, (uint64_t)c, (uint64_t)threads, (uint64_t)smem}) {
+    h ^= v;
+    h *= 1099511628211ull;
+  }
+  return h;
+}
+
+// scan launch shapes are cached per (n, d, nq > 1, k, metric, lanes)
+static std::mutex g_scan_mu;
+static std::unordered_map<uint64_t, ScanLaunch> g_scan_cache;
+static std::unordered_map<uint64_t, AdcScanLaunch> g_adc_cache;
+
+static int plan_scan(const Segment* s, int nq, int k, bool cosine, ScanLaunch* out) {
+  const int ln = lanes();
+  uint64_t key = occ_key(cosine ? 11 : 10, s->d, ln, k, nq > 1 ? 2 : 1, (size_t)s->n);
+  {
+    std::lock_guard<std::mutex> lk(g_scan_mu);
+    auto it = g_scan_cache.find(key);
+    if (it != g_scan_cache.end()) {
+      *out = it->second;
+      return VS_OK;
+    }
+  }
+  ScanLaunch L{};
+  L.n = s->n; L.d = s->d; L.nq = nq; L.lanes = ln; L.cosine = cosine; L.k = k;
+  if (!scan_configure(L, g_sms)) return fail(VS_ECUDA, "scan kernel cannot be resident for d=%d k=%d", s->d, k);
+  std::lock_guard<std::mutex> lk(g_scan_mu);
+  g_scan_cache[key] = L;
+  *out = L;
   return VS_OK;
 }
 
-static int plan_adc(const Segment* s, int nq, int k, ScanPlan* p) {
-  p->kp = topk_pad(k);
-  p->threads = SCAN_THREADS;
-  p->smem = adc_scan_smem_bytes(s->M, s->K, p->kp, p->threads);
-  while (p->smem > 200 * 1024 && p->threads > 64) {
-    p->threads /= 2;
-    p->smem = adc_scan_smem_bytes(s->M, s->K, p->kp, p->threads);
+static int plan_adc(const Segment* s, int nq, int k, AdcScanLaunch* out) {
+  uint64_t key = occ_key(20, s->M, s->K, k, nq > 1 ? 2 : 1, (size_t)s->n);
+  {
+    std::lock_guard<std::mutex> lk(g_scan_mu);
+    auto it = g_adc_cache.find(key);
+    if (it != g_adc_cache.end()) {
+      *out = it->second;
+      return VS_OK;
+    }
   }
-  int occ = adc_scan_occupancy(s->M, s->K, p->threads, p->smem);
-  if (occ < 1) return fail(VS_ECUDA, "ADC scan kernel cannot be resident (smem %zu)", p->smem);
-  if (occ > 8) occ = 8;
-  int64_t grid = (int64_t)g_sms * (nq > 1 ? 1 : occ);
-  int64_t cap = (s->n + 127) / 128;
-  if (cap < 1) cap = 1;
-  if (grid > cap) grid = cap;
-  p->grid = (int)grid;
+  AdcScanLaunch L{};
+  L.n = s->n; L.M = s->M; L.K = s->K; L.nq = nq; L.k = k;
+  if (!adc_configure(L, g_sms)) return fail(VS_ECUDA, "ADC scan kernel cannot be resident for M=%d k=%d", s->M, k);
+  std::lock_guard<std::mutex> lk(g_scan_mu);
+  g_adc_cache[key] = L;
+  *out = L;
   return VS_OK;
 }
 
@@ -234,25 +263,29 @@ static void fill_empty(int64_t* ids, double* scores, int32_t* counts, int nq, in
 // ---- device-side bodies (everything on c->stream, no synchronisation) -------------------------------------
 static int bruteforce_dev(ThreadCtx* c, cudaStream_t st, const Segment* s, const float* d_q, int nq, int k,
                           int metric, int64_t* d_ids, double* d_scores, int32_t* d_counts,
-                          ulonglong2* d_partial, unsigned int* d_ticket, const ScanPlan& p) {
+                          ulonglong2* d_partial, unsigned long long* d_ticket, const ScanLaunch& p,
+                          int64_t out_stride = 0) {
   (void)c;
-  ScanLaunch L{};
-  L.X = s->X; L.n = s->n; L.d = s->d; L.q = d_q; L.nq = nq; L.skip = s->skip; L.lanes = lanes();
-  L.cosine = metric == VS_METRIC_COSINE; L.k = k; L.kp = p.kp; L.partial = d_partial; L.ticket = d_ticket;
+  (void)k;
+  (void)metric;
+  ScanLaunch L = p;
+  L.X = s->X; L.q = d_q; L.nq = nq; L.skip = s->skip;
+  L.partial = d_partial; L.ctrl = d_ticket;
   L.ids_out = d_ids; L.scores_out = d_scores; L.counts_out = d_counts; L.id_base = s->id_base;
-  L.grid = p.grid; L.threads = p.threads; L.smem_bytes = p.smem;
+  L.out_stride = out_stride;
   CK(launch_scan(L, st), "scan launch");
   return VS_OK;
 }
 
 static int adc_dev(cudaStream_t st, const Segment* s, const float* d_q, int nq, int n_cand, double* d_lut,
                    int64_t* d_ids, double* d_approx, int32_t* d_counts, ulonglong2* d_partial,
-                   unsigned int* d_ticket, const ScanPlan& p) {
+                   unsigned long long* d_ticket, const AdcScanLaunch& p) {
+  (void)n_cand;
   CK(launch_build_lut(s->centroids, s->M, s->K, s->subDim, d_q, nq, lanes(), d_lut, st), "build_lut launch");
-  AdcScanLaunch L{};
-  L.codes = s->codes; L.n = s->n; L.M = s->M; L.K = s->K; L.lut64 = d_lut; L.nq = nq; L.k = n_cand; L.kp = p.kp;
-  L.partial = d_partial; L.ticket = d_ticket; L.ids_out = d_ids; L.approx_out = d_approx;
-  L.counts_out = d_counts; L.id_base = s->id_base; L.grid = p.grid; L.threads = p.threads; L.smem_bytes = p.smem;
+  AdcScanLaunch L = p;
+  L.codes = s->codes; L.lut64 = d_lut; L.nq = nq;
+  L.partial = d_partial; L.ctrl = d_ticket; L.ids_out = d_ids; L.approx_out = d_approx;
+  L.counts_out = d_counts; L.id_base = s->id_base;
   CK(launch_adc_scan(L, st), "adc scan launch");
   return VS_OK;
 }
@@ -339,6 +372,9 @@ int32_t vs_device_info(int32_t* sm_count_, int64_t* free_bytes, int64_t* total_b
 }
 
 int64_t vs_kernel_launch_count(void) { return g_launches.load(); }
+#ifdef VS_PHASE_STAMPS
+int32_t vs_debug_read_stamps(void* dst, int64_t bytes) { return vs::debug_read_stamps(dst, (size_t)bytes); }
+#endif
 
 // =================================================================================================
 // pair operations
@@ -634,9 +670,9 @@ int32_t vs_bruteforce_topk(uint64_t h, const float* q, int32_t nq, int32_t k, in
     fill_empty(ids_out, scores_out, counts_out, nq, k);
     return VS_OK;
   }
-  ScanPlan p;
+  ScanLaunch p;
   RET(plan_scan(s, nq, k, metric == VS_METRIC_COSINE, &p));
-  const size_t per_q_partial = (size_t)p.grid * k * 16;
+  const size_t per_q_partial = (size_t)p.partial_keys * 16;
   int group = (int)(PARTIAL_BUDGET / per_q_partial);
   if (group < 1) group = 1;
   if (group > nq) group = nq;
@@ -651,7 +687,7 @@ int32_t vs_bruteforce_topk(uint64_t h, const float* q, int32_t nq, int32_t k, in
     int64_t* dids = A.take<int64_t>((size_t)group * k);
     double* dsc = A.take<double>((size_t)group * k);
     int32_t* dcn = A.take<int32_t>(group);
-    ulonglong2* dpart = A.take<ulonglong2>((size_t)group * p.grid * k);
+    ulonglong2* dpart = A.take<ulonglong2>((size_t)group * p.partial_keys);
     float* hq = H.take<float>((size_t)group * s->d);
     int64_t* hids = H.take<int64_t>((size_t)group * k);
     double* hsc = H.take<double>((size_t)group * k);
@@ -684,9 +720,9 @@ static int adc_common(uint64_t h, const float* q, int32_t nq, int32_t n_cand, bo
     fill_empty(ids_out, scores_out, counts_out, nq, kout);
     return VS_OK;
   }
-  ScanPlan p;
+  AdcScanLaunch p;
   RET(plan_adc(s, nq, n_cand, &p));
-  const size_t per_q_partial = (size_t)p.grid * n_cand * 16;
+  const size_t per_q_partial = (size_t)p.partial_keys * 16;
   int group = (int)(PARTIAL_BUDGET / per_q_partial);
   if (group < 1) group = 1;
   if (group > nq) group = nq;
@@ -706,7 +742,7 @@ static int adc_common(uint64_t h, const float* q, int32_t nq, int32_t n_cand, bo
     double* dsc = A.take<double>((size_t)group * kout);
     int32_t* dcn = A.take<int32_t>(group);
     double* dlut = A.take<double>((size_t)group * s->M * s->K);
-    ulonglong2* dpart = A.take<ulonglong2>((size_t)group * p.grid * n_cand);
+    ulonglong2* dpart = A.take<ulonglong2>((size_t)group * p.partial_keys);
     float* hq = H.take<float>((size_t)group * s->d);
     int64_t* hids = H.take<int64_t>((size_t)group * kout);
     double* hsc = H.take<double>((size_t)group * kout);
@@ -920,18 +956,63 @@ int32_t vs_bruteforce_topk_dev(uint64_t h, const float* d_q, int32_t nq, int32_t
   ThreadCtx* c;
   RET(ctx_bind(&c));
   if (s->n == 0) return fail(VS_EINVAL, "empty segment: use the host variant");
-  ScanPlan p;
+  ScanLaunch p;
   RET(plan_scan(s, nq, k, metric == VS_METRIC_COSINE, &p));
-  const size_t pb = (size_t)nq * p.grid * k * 16;
+  const size_t pb = (size_t)nq * p.partial_keys * 16;
   if (pb > (size_t(1) << 31)) return fail(VS_EINVAL, "query batch too large for the stream variant");
+  const bool grow = Arena::need({pb}) > c->d_cap || (size_t)nq > c->ticket_cap;
   RET(ctx_reserve_dev(c, Arena::need({pb})));
   RET(ctx_reserve_ticket(c, nq));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // ticket memset (if any) ran on c->stream: order it before the caller's stream
-  CK(cudaStreamSynchronize(c->stream), "sync");
+  if (grow) CK(cudaStreamSynchronize(c->stream), "sync");
   Arena A(c->d_buf);
-  ulonglong2* dpart = A.take<ulonglong2>((size_t)nq * p.grid * k);
+  ulonglong2* dpart = A.take<ulonglong2>((size_t)nq * p.partial_keys);
   return bruteforce_dev(c, st, s, d_q, nq, k, metric, d_ids, d_scores, d_counts, dpart, c->d_ticket, p);
+}
+
+int32_t vs_bruteforce_topk_packed_dev(uint64_t h, const float* d_q, int32_t nq, int32_t k, int32_t metric,
+                                      int64_t* d_pack, int32_t* d_counts, void* stream) {
+  Segment* s = seg_lookup(h);
+  RET(check_query_args(s, d_q, nq, k, metric));
+  if (!d_pack || !d_counts) return fail(VS_EINVAL, "null output pointer");
+  ThreadCtx* c;
+  RET(ctx_bind(&c));
+  if (s->n == 0) return fail(VS_EINVAL, "empty segment: use the host variant");
+  ScanLaunch p;
+  RET(plan_scan(s, nq, k, metric == VS_METRIC_COSINE, &p));
+  const size_t pb = (size_t)nq * p.partial_keys * 16;
+  if (pb > (size_t(1) << 31)) return fail(VS_EINVAL, "query batch too large for the stream variant");
+  const bool grow = Arena::need({pb}) > c->d_cap || (size_t)nq > c->ticket_cap;
+  RET(ctx_reserve_dev(c, Arena::need({pb})));
+  RET(ctx_reserve_ticket(c, nq));
+  if (grow) CK(cudaStreamSynchronize(c->stream), "sync");
+  Arena A(c->d_buf);
+  ulonglong2* dpart = A.take<ulonglong2>((size_t)nq * p.partial_keys);
+  return bruteforce_dev(c, static_cast<cudaStream_t>(stream), s, d_q, nq, k, metric, d_pack,
+                        reinterpret_cast<double*>(d_pack + k), d_counts, dpart, c->d_ticket, p, 2 * (int64_t)k);
+}
+
+int32_t vs_merge_packed_dev(const int64_t* d_gath, int32_t world, int32_t nq, int32_t k, int32_t descending,
+                            int64_t* d_ids_out, double* d_scores_out, int32_t* d_counts_out, void* stream) {
+  if (!d_gath || !d_ids_out || !d_scores_out || !d_counts_out) return fail(VS_EINVAL, "null pointer");
+  if (world <= 0 || nq <= 0) return fail(VS_EINVAL, "world and nq must be positive");
+  if (k <= 0 || k > TOPK_MAX_K) return fail(VS_EINVAL, "k must be in 1..%d", TOPK_MAX_K);
+  ThreadCtx* c;
+  RET(ctx_bind(&c));
+  CK(launch_merge_packed(d_gath, world, nq, k, descending != 0, d_ids_out, d_scores_out, d_counts_out,
+                         static_cast<cudaStream_t>(stream)), "merge launch");
+  return VS_OK;
+}
+
+int32_t vs_merge_topk_dev(const int64_t* d_ids, const double* d_scores, int64_t total, int32_t k,
+                          int64_t* d_ids_out, double* d_scores_out, int32_t* d_count_out, void* stream) {
+  if (!d_ids || !d_scores || !d_ids_out || !d_scores_out || !d_count_out || total <= 0) return fail(VS_EINVAL, "null pointer or empty input");
+  if (k <= 0 || k > TOPK_MAX_K) return fail(VS_EINVAL, "k must be in 1..%d", TOPK_MAX_K);
+  ThreadCtx* c;
+  RET(ctx_bind(&c));
+  CK(launch_merge(d_ids, d_scores, total, k, d_ids_out, d_scores_out, d_count_out, static_cast<cudaStream_t>(stream)), "merge launch");
+  return VS_OK;
 }
 
 int32_t vs_adc_topk_dev(uint64_t h, const float* d_q, int32_t nq, int32_t n_cand, int64_t* d_ids,
@@ -943,16 +1024,16 @@ int32_t vs_adc_topk_dev(uint64_t h, const float* d_q, int32_t nq, int32_t n_cand
   ThreadCtx* c;
   RET(ctx_bind(&c));
   if (s->n == 0) return fail(VS_EINVAL, "empty segment: use the host variant");
-  ScanPlan p;
+  AdcScanLaunch p;
   RET(plan_adc(s, nq, n_cand, &p));
-  const size_t pb = (size_t)nq * p.grid * n_cand * 16, lb = (size_t)nq * s->M * s->K * 8;
+  const size_t pb = (size_t)nq * p.partial_keys * 16, lb = (size_t)nq * s->M * s->K * 8;
   if (pb > (size_t(1) << 31)) return fail(VS_EINVAL, "query batch too large for the stream variant");
   RET(ctx_reserve_dev(c, Arena::need({pb, lb})));
   RET(ctx_reserve_ticket(c, nq));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CK(cudaStreamSynchronize(c->stream), "sync");
   Arena A(c->d_buf);
-  ulonglong2* dpart = A.take<ulonglong2>((size_t)nq * p.grid * n_cand);
+  ulonglong2* dpart = A.take<ulonglong2>((size_t)nq * p.partial_keys);
   double* dlut = A.take<double>((size_t)nq * s->M * s->K);
   return adc_dev(st, s, d_q, nq, n_cand, dlut, d_ids, d_approx, d_counts, dpart, c->d_ticket, p);
 }
@@ -969,9 +1050,9 @@ int32_t vs_adc_rerank_topk_dev(uint64_t h, const float* d_q, int32_t nq, int32_t
   ThreadCtx* c;
   RET(ctx_bind(&c));
   if (s->n == 0) return fail(VS_EINVAL, "empty segment: use the host variant");
-  ScanPlan p;
+  AdcScanLaunch p;
   RET(plan_adc(s, nq, n_cand, &p));
-  const size_t pb = (size_t)nq * p.grid * n_cand * 16, lb = (size_t)nq * s->M * s->K * 8;
+  const size_t pb = (size_t)nq * p.partial_keys * 16, lb = (size_t)nq * s->M * s->K * 8;
   const size_t cib = (size_t)nq * n_cand * 8, ccb = (size_t)nq * 4;
   if (pb > (size_t(1) << 31)) return fail(VS_EINVAL, "query batch too large for the stream variant");
   RET(ctx_reserve_dev(c, Arena::need({pb, lb, cib, cib, ccb})));
@@ -979,7 +1060,7 @@ int32_t vs_adc_rerank_topk_dev(uint64_t h, const float* d_q, int32_t nq, int32_t
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CK(cudaStreamSynchronize(c->stream), "sync");
   Arena A(c->d_buf);
-  ulonglong2* dpart = A.take<ulonglong2>((size_t)nq * p.grid * n_cand);
+  ulonglong2* dpart = A.take<ulonglong2>((size_t)nq * p.partial_keys);
   double* dlut = A.take<double>((size_t)nq * s->M * s->K);
   int64_t* dcid = A.take<int64_t>((size_t)nq * n_cand);
   double* dcap = A.take<double>((size_t)nq * n_cand);

@@ -17,6 +17,20 @@ namespace vs {
 
 constexpr unsigned FULL_MASK = 0xffffffffu;
 
+// development-only phase timestamps (build with -DVS_PHASE_STAMPS; tools/phase_stamps.py)
+#ifdef VS_PHASE_STAMPS
+static __device__ unsigned long long g_phase_stamps[8 * 1024];
+__device__ __forceinline__ void phase_stamp(int ph) {
+  if (threadIdx.x == 0 && blockIdx.y == 0 && blockIdx.x < 1024) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    g_phase_stamps[blockIdx.x * 8 + ph] = t;
+  }
+}
+#else
+__device__ __forceinline__ void phase_stamp(int) {}
+#endif
+
 // ----------------------------------------------------------------------------------------------
 // sortable keys
 // ----------------------------------------------------------------------------------------------
@@ -27,8 +41,9 @@ struct Key {
 };
 constexpr uint64_t KEY_EMPTY64 = ~0ull;
 __device__ __forceinline__ Key key_empty() { return Key{KEY_EMPTY64, KEY_EMPTY64}; }
+// branch-free on purpose: short-circuit evaluation turns every compare into a divergent branch
 __device__ __forceinline__ bool key_lt(const Key& a, const Key& b) {
-  return a.hi < b.hi || (a.hi == b.hi && a.lo < b.lo);
+  return (a.hi < b.hi) | ((a.hi == b.hi) & (a.lo < b.lo));
 }
 __device__ __forceinline__ bool key_is_empty(const Key& a) { return a.lo == KEY_EMPTY64; }
 __device__ __forceinline__ Key ld_key(const ulonglong2* p) {
@@ -121,6 +136,7 @@ __device__ __forceinline__ double ref_sum_thread(const float* __restrict__ a,
 template <int OP>
 __device__ __forceinline__ double ref_add_tail(double sum, const float* __restrict__ a,
                                                const float* __restrict__ b, int ub, int len) {
+#pragma unroll 1
   for (int i = ub; i < len; i++) {
     if (OP == REF_L2SQ) {
       double d = __dsub_rn((double)a[i], (double)b[i]);

@@ -28,4 +28,8 @@ Segment* seg_lookup(uint64_t h);
 int pq_train_device(cudaStream_t st, const float* dX, int64_t n, int d, int M, int K, int iterations,
                     int64_t seed, int lanes, float* centroids_out);
 
+#ifdef VS_PHASE_STAMPS
+int debug_read_stamps(void* dst, size_t bytes);  // development only (scan.cu)
+#endif
+
 }  // namespace vs

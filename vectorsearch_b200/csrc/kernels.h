@@ -23,17 +23,23 @@ struct ScanLaunch {
   bool cosine;
   int k, kp;             // kp = topk_pad(k)
   ulonglong2* partial;   // scratch [nq][grid][k]
-  unsigned int* ticket;  // scratch [nq], zero between launches
+  unsigned long long* ctrl;  // scratch [nq][4], zero between launches
+  int64_t partial_keys;      // keys of `partial` per query (filled by scan_configure)
   int64_t* ids_out;      // [nq][k]
   double* scores_out;    // [nq][k]
   int32_t* counts_out;   // [nq]
   int64_t id_base;
+  int64_t out_stride;    // elements between queries in ids_out / scores_out (0 = k)
+  // filled by scan_configure:
+  int variant;           // ScanVariant
   int grid, threads;
   size_t smem_bytes;
+  int TR, NS;            // TMA ring: rows per stage, stages per warp
 };
+enum ScanVariant { SCAN_TMA = 0, SCAN_LDG = 1, SCAN_ROWTHREAD = 2 };
 bool scan_is_streaming(int d, int lanes, bool cosine);
-size_t scan_smem_bytes(int d, int kp, int threads);
-int scan_occupancy(int d, int lanes, bool cosine, int threads, size_t smem);
+// chooses the kernel variant and launch shape from (n, d, nq, lanes, cosine, k); false = not launchable
+bool scan_configure(ScanLaunch& L, int sms);
 cudaError_t launch_scan(const ScanLaunch& L, cudaStream_t st);
 
 // ---- rank.cu: exact scoring + ordering of caller-supplied candidates (re-rank), merge ----------
@@ -58,6 +64,10 @@ cudaError_t launch_rank(const RankLaunch& L, cudaStream_t st);
 // stable sort by score descending of `total` (id, score) pairs, first k
 cudaError_t launch_merge(const int64_t* ids, const double* scores, int64_t total, int k,
                          int64_t* ids_out, double* scores_out, int32_t* count_out, cudaStream_t st);
+// gathered [w][nq][2k] packed lists (k ids then k score bit patterns; id < 0 = empty slot):
+// per query, concatenate in rank order, stable sort (descending scores or ascending distances), first k
+cudaError_t launch_merge_packed(const int64_t* gath, int w, int nq, int k, bool descending,
+                                int64_t* ids_out, double* scores_out, int32_t* counts_out, cudaStream_t st);
 
 // ---- misc.cu ----------------------------------------------------------------------------------
 // element e of the output = draw (first + e) of new java.util.Random(seed); kind 0: nextFloat()*2f-1f,
@@ -84,16 +94,18 @@ struct AdcScanLaunch {
   int nq;
   int k, kp;
   ulonglong2* partial;
-  unsigned int* ticket;
+  unsigned long long* ctrl;
+  int64_t partial_keys;
   int64_t* ids_out;
   double* approx_out;
   int32_t* counts_out;
   int64_t id_base;
+  int64_t out_stride;
   int grid, threads;
   size_t smem_bytes;
 };
-size_t adc_scan_smem_bytes(int M, int K, int kp, int threads);
-int adc_scan_occupancy(int M, int K, int threads, size_t smem);
+// fills kp / threads / grid / smem_bytes from (n, M, K, nq, k); false = not launchable
+bool adc_configure(AdcScanLaunch& L, int sms);
 cudaError_t launch_adc_scan(const AdcScanLaunch& L, cudaStream_t st);
 
 // ---- pq.cu ------------------------------------------------------------------------------------

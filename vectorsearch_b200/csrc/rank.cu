@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(RANK_THREADS)
 merge_kernel(const int64_t* __restrict__ ids, const double* __restrict__ scores, int64_t total, int k,
              int kp, int64_t* __restrict__ ids_out, double* __restrict__ scores_out,
              int32_t* __restrict__ count_out) {
-  extern __shared__ __align__(16) ulonglong2 smem[];
+  extern __shared__ __align__(128) ulonglong2 smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int nw = blockDim.x >> 5;
@@ -117,6 +117,74 @@ merge_kernel(const int64_t* __restrict__ ids, const double* __restrict__ scores,
   if (found) atomicAdd(&s_found, found);
   __syncthreads();
   if (threadIdx.x == 0) *count_out = s_found;
+}
+
+__global__ void __launch_bounds__(RANK_THREADS)
+merge_packed_kernel(const int64_t* __restrict__ gath, int w, int nq, int k, int kp, int descending,
+                    int64_t* __restrict__ ids_out, double* __restrict__ scores_out,
+                    int32_t* __restrict__ counts_out) {
+  extern __shared__ __align__(128) ulonglong2 smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nw = blockDim.x >> 5;
+  const int stride_keys = kp + TOPK_BUF;
+  const int qi = blockIdx.x;
+  const int total = w * k;
+  WarpTopK tk;
+  tk.init(smem + (size_t)warp * stride_keys, kp, k, lane);
+  for (int i0 = warp * 32; i0 < total; i0 += nw * 32) {
+    const int i = i0 + lane;
+    Key key = key_empty();
+    bool ok = false;
+    if (i < total) {
+      const int r = i / k, j = i % k;
+      const int64_t* row = gath + ((size_t)r * nq + qi) * 2 * k;
+      const int64_t id = row[j];
+      if (id >= 0) {
+        const double sc = __longlong_as_double(row[k + j]);
+        key = Key{descending ? rank_hi_from_score(sc) : rank_hi_from_dist(sc), (uint64_t)i};
+        ok = true;
+      }
+    }
+    tk.push(key, ok, lane);
+  }
+  tk.flush(lane);
+  block_combine_lists(smem, stride_keys, nw, kp, warp, lane);
+  __shared__ int s_found;
+  if (threadIdx.x == 0) s_found = 0;
+  __syncthreads();
+  int found = 0;
+  for (int i = threadIdx.x; i < k; i += blockDim.x) {
+    Key e = ld_key(smem + i);
+    const bool ok = !key_is_empty(e);
+    int64_t id = -1;
+    double sc = __longlong_as_double(0x7ff8000000000000ll);
+    if (ok) {
+      const int r = (int)(e.lo / k), j = (int)(e.lo % k);
+      const int64_t* row = gath + ((size_t)r * nq + qi) * 2 * k;
+      id = row[j];
+      sc = __longlong_as_double(row[k + j]);
+    }
+    ids_out[(size_t)qi * k + i] = id;
+    scores_out[(size_t)qi * k + i] = sc;
+    found += ok ? 1 : 0;
+  }
+  if (found) atomicAdd(&s_found, found);
+  __syncthreads();
+  if (threadIdx.x == 0) counts_out[qi] = s_found;
+}
+
+cudaError_t launch_merge_packed(const int64_t* gath, int w, int nq, int k, bool descending,
+                                int64_t* ids_out, double* scores_out, int32_t* counts_out, cudaStream_t st) {
+  const int kp = topk_pad(k);
+  const size_t smem = (size_t)(RANK_THREADS / 32) * topk_warp_smem(kp);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(merge_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  merge_packed_kernel<<<nq, RANK_THREADS, smem, st>>>(gath, w, nq, k, kp, descending ? 1 : 0, ids_out, scores_out, counts_out);
+  count_launch();
+  return cudaGetLastError();
 }
 
 cudaError_t launch_rank(const RankLaunch& L, cudaStream_t st) {

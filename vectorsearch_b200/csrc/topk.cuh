@@ -151,19 +151,115 @@ __device__ __forceinline__ void block_collect_keys(const ulonglong2* __restrict_
   block_combine_lists(smem, stride_keys, nw, kp, warp, lane);
 }
 
-// ---- shared epilogue of the streaming kernels ---------------------------------------------------
+
 struct TopkOut {
   ulonglong2* partial;   // [nq][grid][k]
-  unsigned int* ticket;  // [nq] zero-initialised, reset by the last CTA
+  unsigned long long* ctrl;  // [nq][4] zero between launches: ticket, append count, ~global bound, tile counter
+  int64_t partial_keys;      // keys of `partial` reserved per query
   int64_t* ids;          // [nq][k]
   double* scores;        // [nq][k]
   int32_t* counts;       // [nq]
   int64_t id_base;
   int score_kind;        // 0: hi is a descending-score image, 1: hi is an ascending-distance image
+  int64_t out_stride;    // elements between consecutive queries in ids / scores (>= k)
 };
 
+// ---- register-resident collector for k <= 32 ------------------------------------------------------
+// One key per lane, sorted ascending across the warp.  An insertion is a ballot (position), one
+// shuffle-up and a broadcast of the new k-th key: the threshold tightens after EVERY accepted
+// row, so few rows survive the fp32 pre-filter and nothing is ever sorted.
+constexpr int TOPK_REG_MAX_K = 32;
+constexpr int TOPK_MAX_LISTS = 320;  // per-query CTA lists the fast final merge can take
+
+struct WarpTopKReg {
+  uint64_t my_hi, my_lo;
+  Key thr;
+  int k;
+
+  __device__ __forceinline__ void init(ulonglong2*, int, int k_, int) {
+    my_hi = KEY_EMPTY64;
+    my_lo = KEY_EMPTY64;
+    thr = key_empty();
+    k = k_;
+  }
+  __device__ __forceinline__ void flush(int) {}
+  __device__ __forceinline__ void push(const Key& key, bool pred, int lane) {
+    pred = pred && key_lt(key, thr);
+    unsigned m = __ballot_sync(FULL_MASK, pred);
+    while (m) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      const Key c{__shfl_sync(FULL_MASK, key.hi, src), __shfl_sync(FULL_MASK, key.lo, src)};
+      if (!key_lt(c, thr)) continue;  // the threshold may have tightened since the ballot
+      const bool lt = key_lt(Key{my_hi, my_lo}, c);
+      const int pos = __popc(__ballot_sync(FULL_MASK, lt));  // sorted: the smaller keys are a prefix
+      const uint64_t uh = __shfl_up_sync(FULL_MASK, my_hi, 1), ul = __shfl_up_sync(FULL_MASK, my_lo, 1);
+      if (lane > pos) {
+        my_hi = uh;
+        my_lo = ul;
+      } else if (lane == pos) {
+        my_hi = c.hi;
+        my_lo = c.lo;
+      }
+      thr = Key{__shfl_sync(FULL_MASK, my_hi, k - 1), __shfl_sync(FULL_MASK, my_lo, k - 1)};
+    }
+  }
+};
+
+// shared memory (bytes) the block-level top-k machinery needs, for either collector
+__host__ __device__ inline size_t topk_block_smem(int k, int kp, int nw) {
+  if (k <= TOPK_REG_MAX_K) {
+    const int surv = k * k > TOPK_MAX_LISTS ? k * k : TOPK_MAX_LISTS;
+    return (size_t)(nw * k + k + surv) * 16;
+  }
+  return (size_t)nw * topk_warp_smem(kp);
+}
+// keys of `partial` scratch one query needs
+__host__ __device__ inline int64_t topk_partial_keys(int k, int grid, int nw) {
+  (void)nw;
+  return (int64_t)grid * k;
+}
+
+// rank of every key among `total` keys in shared memory; keys with rank < k land in outk[rank]
+__device__ __forceinline__ void block_rank_select(const ulonglong2* keys, int total, int k, ulonglong2* outk) {
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const Key me = ld_key(keys + i);
+    if (key_is_empty(me)) continue;
+    int rank = 0;
+#pragma unroll 4
+    for (int j = 0; j < total; j++) rank += key_lt(ld_key(keys + j), me) ? 1 : 0;
+    if (rank < k) st_key(outk + rank, me);
+  }
+}
+
+__device__ __forceinline__ void topk_write_out(const ulonglong2* outk, int k, const TopkOut& o, int qi) {
+  __shared__ int s_found;
+  if (threadIdx.x == 0) s_found = 0;
+  __syncthreads();
+  int found = 0;
+  for (int i = threadIdx.x; i < k; i += blockDim.x) {
+    Key e = ld_key(outk + i);
+    const bool ok = !key_is_empty(e);
+    o.ids[(size_t)qi * o.out_stride + i] = ok ? o.id_base + (int64_t)e.lo : -1;
+    o.scores[(size_t)qi * o.out_stride + i] = ok ? (o.score_kind == 0 ? score_from_rank_hi(e.hi) : dist_from_rank_hi(e.hi))
+                                                 : __longlong_as_double(0x7ff8000000000000ll);
+    found += ok ? 1 : 0;
+  }
+  if (found) atomicAdd(&s_found, found);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    o.counts[qi] = s_found;
+    o.ctrl[4 * qi + 0] = 0ull;  // ready for the next launch on this scratch
+    o.ctrl[4 * qi + 1] = 0ull;
+    o.ctrl[4 * qi + 2] = 0ull;
+    o.ctrl[4 * qi + 3] = 0ull;
+  }
+}
+
+// ---- shared epilogue of the streaming kernels ---------------------------------------------------
+
 // flush + block combine + publish + (last CTA) final merge.  smem holds nw collectors.
-__device__ __forceinline__ void topk_epilogue(WarpTopK& tk, ulonglong2* smem, int kp, int k,
+static __device__ __noinline__ void topk_epilogue(WarpTopK& tk, ulonglong2* smem, int kp, int k,
                                               const TopkOut& o) {
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -172,13 +268,13 @@ __device__ __forceinline__ void topk_epilogue(WarpTopK& tk, ulonglong2* smem, in
   const int qi = blockIdx.y;
   tk.flush(lane);
   block_combine_lists(smem, stride_keys, nw, kp, warp, lane);
-  ulonglong2* mine = o.partial + ((size_t)qi * gridDim.x + blockIdx.x) * k;
+  ulonglong2* mine = o.partial + (size_t)qi * o.partial_keys + (size_t)blockIdx.x * k;
   for (int i = threadIdx.x; i < k; i += blockDim.x) __stcg(mine + i, smem[i]);
   __threadfence();
   __syncthreads();
   __shared__ unsigned int s_last;
   if (threadIdx.x == 0) {
-    unsigned int t = atomicAdd(o.ticket + qi, 1u);
+    unsigned long long t = atomicAdd(o.ctrl + 4 * qi, 1ull);
     s_last = (t == gridDim.x - 1) ? 1u : 0u;
   }
   __syncthreads();
@@ -186,7 +282,7 @@ __device__ __forceinline__ void topk_epilogue(WarpTopK& tk, ulonglong2* smem, in
   __threadfence();
   // final merge by the last CTA of this query
   {
-    const ulonglong2* all = o.partial + (size_t)qi * gridDim.x * k;
+    const ulonglong2* all = o.partial + (size_t)qi * o.partial_keys;
     const int64_t total = (int64_t)gridDim.x * k;
     WarpTopK fk;
     fk.init(smem + (size_t)warp * stride_keys, kp, k, lane);
@@ -209,8 +305,8 @@ __device__ __forceinline__ void topk_epilogue(WarpTopK& tk, ulonglong2* smem, in
   for (int i = threadIdx.x; i < k; i += blockDim.x) {
     Key e = ld_key(smem + i);
     const bool ok = !key_is_empty(e);
-    o.ids[(size_t)qi * k + i] = ok ? o.id_base + (int64_t)e.lo : -1;
-    o.scores[(size_t)qi * k + i] = ok ? (o.score_kind == 0 ? score_from_rank_hi(e.hi) : dist_from_rank_hi(e.hi))
+    o.ids[(size_t)qi * o.out_stride + i] = ok ? o.id_base + (int64_t)e.lo : -1;
+    o.scores[(size_t)qi * o.out_stride + i] = ok ? (o.score_kind == 0 ? score_from_rank_hi(e.hi) : dist_from_rank_hi(e.hi))
                                       : __longlong_as_double(0x7ff8000000000000ll);
     found += ok ? 1 : 0;
   }
@@ -218,8 +314,80 @@ __device__ __forceinline__ void topk_epilogue(WarpTopK& tk, ulonglong2* smem, in
   __syncthreads();
   if (threadIdx.x == 0) {
     o.counts[qi] = s_found;
-    o.ticket[qi] = 0u;  // ready for the next launch on this scratch
+    o.ctrl[4 * qi] = 0ull;  // ready for the next launch on this scratch
   }
+}
+
+// Epilogue of the register collector: block combine by rank selection, publish the CTA's k keys,
+// and (last CTA of the query) the final merge.  The k-th smallest list head bounds the launch-wide
+// k-th key, so only keys at or below that bound -- at most k lists x k keys -- are gathered and
+// rank-selected; nothing is sorted and nothing scales with grid x k beyond two coalesced reads.
+static __device__ __noinline__ void topk_epilogue(WarpTopKReg& tk, ulonglong2* smem, int kp, int k,
+                                              const TopkOut& o) {
+  (void)kp;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nw = blockDim.x >> 5;
+  const int qi = blockIdx.y;
+  unsigned long long* ctrl = o.ctrl + 4 * qi;
+  ulonglong2* keys = smem;            // [nw * k]
+  ulonglong2* outk = smem + nw * k;   // [k]
+  ulonglong2* surv = outk + k;        // [max(k*k, TOPK_MAX_LISTS)]
+  if (lane < k) st_key(keys + warp * k + lane, Key{tk.my_hi, tk.my_lo});
+  if (threadIdx.x < k) st_key(outk + threadIdx.x, key_empty());
+  __syncthreads();
+  block_rank_select(keys, nw * k, k, outk);
+  __syncthreads();
+  phase_stamp(5);
+  ulonglong2* all = o.partial + (size_t)qi * o.partial_keys;
+  for (int i = threadIdx.x; i < k; i += blockDim.x) __stcg(all + (size_t)blockIdx.x * k + i, outk[i]);
+  __threadfence();
+  __syncthreads();
+  __shared__ unsigned int s_last;
+  __shared__ int s_cnt;
+  __shared__ ulonglong2 s_bound;
+  if (threadIdx.x == 0) {
+    unsigned long long t = atomicAdd(ctrl, 1ull);
+    s_last = (t == gridDim.x - 1) ? 1u : 0u;
+    s_cnt = 0;
+    st_key(&s_bound, key_empty());
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  phase_stamp(6);
+  const int nl = gridDim.x;  // <= TOPK_MAX_LISTS (host guarantees)
+  for (int i = threadIdx.x; i < nl; i += blockDim.x) surv[i] = __ldcg(all + (size_t)i * k);
+  if (threadIdx.x < k) st_key(outk + threadIdx.x, key_empty());
+  __syncthreads();
+  phase_stamp(1);
+  for (int i = threadIdx.x; i < nl; i += blockDim.x) {
+    const Key h = ld_key(surv + i);
+    if (key_is_empty(h)) continue;
+    int rank = 0;
+#pragma unroll 4
+    for (int j = 0; j < nl; j++) rank += key_lt(ld_key(surv + j), h) ? 1 : 0;
+    if (rank == k - 1) st_key(&s_bound, h);
+  }
+  __syncthreads();
+  const Key B = ld_key(&s_bound);
+  phase_stamp(2);
+  __syncthreads();  // heads are dead from here on: surv is reused for the survivors
+  const int total = nl * k;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const ulonglong2 v = __ldcg(all + i);
+    const Key x{v.x, v.y};
+    if (!key_is_empty(x) && !key_lt(B, x)) {
+      const int slot = atomicAdd(&s_cnt, 1);
+      st_key(surv + slot, x);  // at most k lists reach below the bound: slot < k*k
+    }
+  }
+  __syncthreads();
+  phase_stamp(3);
+  block_rank_select(surv, s_cnt, k, outk);
+  __syncthreads();
+  phase_stamp(7);
+  topk_write_out(outk, k, o, qi);
 }
 
 }  // namespace vs

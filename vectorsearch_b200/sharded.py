@@ -1,0 +1,108 @@
+"""Row-range sharding of one corpus over the GPUs of a box: one process per GPU, torch.distributed
+for the plumbing (NCCL over NVLink on GPUs, gloo in the CPU tests of the host logic).
+
+The reference scales by SEGMENTS searched independently and merged (J/fdb/FdbVectorIndex.java:
+418-437): per-segment lists are concatenated in ascending segment order, stably sorted by score
+descending and cut to k.  Shards are ascending row ranges, so gathering the per-rank top-k lists
+in rank order and running the same stable merge (vs_merge_topk) reproduces that result exactly:
+ties go to the lower rank = the lower global row.
+
+Everything numeric runs in libvsgpu; torch only carries device buffers, streams and collectives.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib as L
+from ._lib import METRIC_L2, check
+
+
+def shard_range(n_total: int, rank: int, world: int) -> tuple[int, int]:
+    """Rows [lo, hi) owned by `rank`: contiguous, ascending, sizes differ by at most one."""
+    base, rem = divmod(n_total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def merge_gathered_host(ids: np.ndarray, scores: np.ndarray, counts: np.ndarray, k: int, desc: bool = True):
+    """Host restatement of the cross-shard merge used by the gloo tests: lists [world][k] with
+    `counts` valid entries each, concatenated in rank order, stable sort, first k.
+    desc=True sorts scores descending (brute force / re-rank), False ascending (ADC distances).
+    NaN handling follows Double.compare: NaN is the largest value."""
+    cat_i, cat_s = [], []
+    for r in range(ids.shape[0]):
+        c = int(counts[r])
+        cat_i.append(ids[r, :c])
+        cat_s.append(scores[r, :c])
+    cat_i = np.concatenate(cat_i) if cat_i else np.zeros(0, np.int64)
+    cat_s = np.concatenate(cat_s) if cat_s else np.zeros(0, np.float64)
+    key = cat_s.copy()
+    nan = np.isnan(key)
+    key[nan] = np.inf
+    # Double.compare orders -0.0 before +0.0 and NaN after +inf; lexsort is stable
+    sign = np.signbit(cat_s) & (cat_s == 0)
+    tie = np.where(nan, 2, np.where(sign, 0, 1))
+    if desc:
+        order = np.lexsort((np.arange(key.size), -tie, -key))
+    else:
+        order = np.lexsort((np.arange(key.size), tie, key))
+    order = order[:k]
+    return cat_i[order], cat_s[order]
+
+
+class ShardedSegment:
+    """One rank's row range of a corpus + the collective merge (torch.distributed)."""
+
+    def __init__(self, segment, rank: int, world: int, group=None):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist = torch, dist
+        self.seg, self.rank, self.world, self.group = segment, rank, world, group
+        self.lib = L.load()
+        self.dev = torch.device("cuda", torch.cuda.current_device())
+        self._bufs = {}
+
+    def _buffers(self, nq: int, k: int):
+        key = (nq, k)
+        if key not in self._bufs:
+            t, dev, w = self.torch, self.dev, self.world
+            self._bufs[key] = dict(
+                pack=t.empty((nq, 2 * k), dtype=t.int64, device=dev),
+                cn=t.empty((nq,), dtype=t.int32, device=dev),
+                gath=t.empty((w, nq, 2 * k), dtype=t.int64, device=dev),
+                out_i=t.empty((nq, k), dtype=t.int64, device=dev), out_s=t.empty((nq, k), dtype=t.float64, device=dev),
+                out_c=t.empty((nq,), dtype=t.int32, device=dev))
+        return self._bufs[key]
+
+    def bruteforce_topk_dev(self, d_q, nq: int, k: int, metric: int = METRIC_L2):
+        """Device-resident query batch [nq][d] -> (ids [nq][k], scores [nq][k], counts [nq]) tensors,
+        identical on every rank.  Three launches per batch on torch's current stream -- local scan
+        (writes ids and score bit patterns straight into the packed send buffer), ONE all-gather,
+        one merge of the rank-ordered lists -- and nothing synchronises."""
+        t = self.torch
+        b = self._buffers(nq, k)
+        st = t.cuda.current_stream().cuda_stream
+        check(self.lib.vs_bruteforce_topk_packed_dev(self.seg.handle, d_q.data_ptr(), nq, k, metric,
+                                                     b["pack"].data_ptr(), b["cn"].data_ptr(), st))
+        if self.world == 1:
+            gath = b["pack"]
+        else:
+            self.dist.all_gather_into_tensor(b["gath"].view(-1), b["pack"].view(-1), group=self.group)
+            gath = b["gath"]
+        check(self.lib.vs_merge_packed_dev(gath.data_ptr(), self.world, nq, k, 1, b["out_i"].data_ptr(),
+                                           b["out_s"].data_ptr(), b["out_c"].data_ptr(), st))
+        return b["out_i"], b["out_s"], b["out_c"]
+
+    def bruteforce_topk(self, q, k: int, metric: int = METRIC_L2):
+        """Host query [d] or [nq][d] (numpy) -> numpy results; H2D and D2H inside (the e2e path)."""
+        t = self.torch
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        single = q.ndim == 1
+        q2 = q.reshape(1, -1) if single else q
+        d_q = t.from_numpy(q2).to(self.dev, non_blocking=True)
+        ids, sc, cn = self.bruteforce_topk_dev(d_q, q2.shape[0], k, metric)
+        ids, sc, cn = ids.cpu().numpy(), sc.cpu().numpy(), cn.cpu().numpy()
+        if single:
+            return ids[0, :cn[0]], sc[0, :cn[0]]
+        return ids, sc, cn
