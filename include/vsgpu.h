@@ -154,6 +154,11 @@ int32_t vs_merge_topk_dev(const int64_t* d_ids, const double* d_scores, int64_t 
                           int64_t* d_ids_out, double* d_scores_out, int32_t* d_count_out, void* stream);
 /* number of kernels this library has launched so far in this process (for gpu_launches) */
 int64_t vs_kernel_launch_count(void);
+/* Tuning knobs (process-wide).  "adc_fast_min_rows": segments with fewer code rows use the generic
+ * ADC kernel (default 16384); "adc_fast_cap": candidate-list entries per scan CTA of the fast ADC
+ * scan (default 4096; on overflow the query is evaluated exactly over every row).  Results never depend
+ * on either. */
+int32_t vs_set_option(const char* name, int64_t value);
 
 #ifdef __cplusplus
 }

@@ -250,6 +250,78 @@ def test_adc_duplicate_codes_and_large_code_values(vs, oracle):
         seg.free()
 
 
+@pytest.fixture
+def force_adc_fast(vs):
+    """Route every M in {8, 16}, K <= 256 segment through the byte-LUT fast scan regardless of size."""
+    vs.set_option("adc_fast_min_rows", 0)
+    yield
+    vs.set_option("adc_fast_min_rows", 16384)
+    vs.set_option("adc_fast_cap", 4096)
+
+
+@pytest.mark.parametrize("n,d,M,K,n_cand", [(70000, 128, 16, 256, 100), (9000, 64, 8, 16, 37), (5000, 128, 16, 256, 10),
+                                            (3000, 32, 8, 256, 1000), (40, 128, 16, 256, 100), (1, 64, 8, 5, 3)])
+def test_adc_fast_scan_matches_oracle(vs, oracle, force_adc_fast, n, d, M, K, n_cand):
+    rows, cent = _pq_fixture(oracle, n, d, M, K)
+    codes = oracle.pq_encode_batch(cent, rows, threads=8)
+    seg = vs.Segment.upload(rows, id_base=11)
+    try:
+        seg.attach_pq(cent, codes)
+        qs = np.stack([oracle.gen_floats(78 + i, 0, d) for i in range(3)])
+        for q in qs:
+            oi, oa = oracle.adc_topn(oracle.build_lut(cent, q), codes, n_cand, threads=4)
+            ids, ap = seg.adc_topk(q, n_cand)
+            assert np.array_equal(ids, oi + 11) and _same(ap, oa)
+        # a query batch through the same launch (one histogram / candidate list per query)
+        bi, ba, bc = seg.adc_topk(qs, n_cand)
+        for j, q in enumerate(qs):
+            oi, oa = oracle.adc_topn(oracle.build_lut(cent, q), codes, n_cand, threads=4)
+            assert bc[j] == len(oi) and np.array_equal(bi[j, :bc[j]], oi + 11) and _same(ba[j, :bc[j]], oa)
+    finally:
+        seg.free()
+
+
+def test_adc_fast_scan_fallbacks(vs, oracle, force_adc_fast):
+    rows, cent = _pq_fixture(oracle, 20000, 64, 8, 40)
+    codes = oracle.pq_encode_batch(cent, rows, threads=8)
+    codes[1000:9000] = codes[3]       # 8000 exact ties inside the top: lowest rows first
+    codes[20, 2] = 200                # >= K: contributes 0 (:1061)
+    codes[21] = 255
+    q = rows[3].copy()
+    seg = vs.Segment.upload(rows)
+    try:
+        seg.attach_pq(cent, codes)
+        oi, oa = oracle.adc_topn(oracle.build_lut(cent, q), codes, 300, threads=3)
+        ids, ap = seg.adc_topk(q, 300)
+        assert np.array_equal(ids, oi) and _same(ap, oa)
+        # candidate list far too small: the query is evaluated exactly over every row instead
+        vs.set_option("adc_fast_cap", 8)
+        ids, ap = seg.adc_topk(q, 300)
+        assert np.array_equal(ids, oi) and _same(ap, oa)
+        ids, ap = seg.adc_topk(q, 300)    # the scratch was left clean by the fallback
+        assert np.array_equal(ids, oi) and _same(ap, oa)
+        vs.set_option("adc_fast_cap", 4096)
+        # NaN query: every LUT entry is NaN, every distance NaN, ties -> rows 0..k-1
+        qn = q.copy()
+        qn[:] = np.nan
+        oi, oa = oracle.adc_topn(oracle.build_lut(cent, qn), codes, 20, threads=3)
+        ids, ap = seg.adc_topk(qn, 20)
+        assert np.array_equal(ids, oi) and _same(ap, oa)
+        # constant table (all centroids equal): zero range, all rows tie
+        flat = np.zeros_like(cent)
+        seg.attach_pq(flat, codes)
+        oi, oa = oracle.adc_topn(oracle.build_lut(flat, q), codes, 50, threads=3)
+        ids, ap = seg.adc_topk(q, 50)
+        assert np.array_equal(ids, oi) and _same(ap, oa)
+        # and a healthy query right after the degenerate ones
+        seg.attach_pq(cent, codes)
+        oi, oa = oracle.adc_topn(oracle.build_lut(cent, q), codes, 300, threads=3)
+        ids, ap = seg.adc_topk(q, 300)
+        assert np.array_equal(ids, oi) and _same(ap, oa)
+    finally:
+        seg.free()
+
+
 @pytest.mark.parametrize("metric", [0, 1])
 def test_rerank_matches_oracle(vs, oracle, metric):
     rows = oracle.gen_rows(21, 0, 5000, 128)

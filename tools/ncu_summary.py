@@ -1,0 +1,65 @@
+"""Summarise ncu outputs brought back in gpurun_out/ into small text files under profiles/.
+
+    python tools/ncu_summary.py launches gpurun_out/launches_r1.csv profiles/r1_c2_launches.txt
+    python tools/ncu_summary.py full gpurun_out/prof_scan_r1.ncu-rep profiles/r1_c2_scan_full.txt
+"""
+import collections
+import csv
+import subprocess
+import sys
+
+FULL_METRICS = [
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__bytes_read.sum.per_second",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size",
+    "launch__block_size", "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_shared_mem",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+    "smsp__inst_executed.sum", "sm__inst_executed_pipe_lsu.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_tensor.sum", "lts__t_bytes.sum", "lts__t_sector_hit_rate.pct",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active",
+]
+
+
+def launches(src, dst):
+    rows = [r for r in csv.reader(open(src)) if len(r) > 5]
+    hdr = rows[0]
+    ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
+    agg = collections.defaultdict(list)
+    for r in rows[1:]:
+        try:
+            agg[r[ki]].append(float(r[vi].replace(",", "")))
+        except ValueError:
+            pass
+    tot = sum(sum(v) for v in agg.values())
+    with open(dst, "w") as f:
+        f.write(f"# {src}: ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised launches)\n")
+        f.write(f"# {sum(len(v) for v in agg.values())} launches, {tot / 1e3:.1f} us in total\n")
+        for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
+            f.write(f"{len(v):5d} x {sum(v) / len(v) / 1e3:10.1f} us  share {sum(v) / tot * 100:5.1f}%  {k[:150]}\n")
+    print(open(dst).read())
+
+
+def full(src, dst):
+    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    rows = [r for r in rows if len(r) > 10]
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    with open(dst, "w") as f:
+        f.write(f"# {src}: ncu --set full --clock-control none --import-source on (values per launch)\n")
+        ki = hdr.index("Kernel Name")
+        for r in data:
+            f.write(f"kernel: {r[ki][:200]}\n")
+        for m in FULL_METRICS:
+            if m in hdr:
+                i = hdr.index(m)
+                f.write(f"{m} [{units[i]}]: {', '.join(r[i] for r in data)}\n")
+    print(open(dst).read())
+
+
+if __name__ == "__main__":
+    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])

@@ -40,7 +40,7 @@ def bf():
     L.check(lib.vs_bruteforce_topk_dev(seg.handle, q.data_ptr(), 1, 10, 0, ids.data_ptr(), sc.data_ptr(), cn.data_ptr(), st))
 
 
-us = timeit(bf)
+us = timeit(bf) if not __import__("os").environ.get('ADC_ONLY') else 1.0
 print(f"bruteforce L2 top-10 n={n} d={d}: {us:.1f} us  {n*d*4/us/1e3:.1f} GB/s  {n/us*1e6:.3e} evals/s")
 qh = q.cpu().numpy()[0]
 t0 = time.perf_counter()
@@ -54,7 +54,12 @@ if os.environ.get('BF_ONLY'):
 # ADC
 M, K = 16, 256
 t0 = time.perf_counter()
-cent = vs.PqTrainer.train(None, d, M, K, 5, 42, segment=seg)
+if os.environ.get('ADC_ONLY'):
+    tr = vs.Segment.generate(42, 0, min(n, 1000000), d)
+    cent = vs.PqTrainer.train(None, d, M, K, 5, 42, segment=tr)
+    tr.free()
+else:
+    cent = vs.PqTrainer.train(None, d, M, K, 5, 42, segment=seg)
 print(f"pq_train 5 iters n={n}: {time.perf_counter()-t0:.3f} s")
 t0 = time.perf_counter()
 seg.attach_pq(cent)
@@ -68,6 +73,10 @@ def adc():
 
 
 us = timeit(adc)
+st8 = (C.c_uint32 * 8)()
+lib.vs_debug_adc_stats.argtypes = [C.POINTER(C.c_uint32)]
+lib.vs_debug_adc_stats(st8)
+print("adc stats (55 launches): candidates", st8[0], "T_final", st8[1], "survivors", st8[2], "fallbacks", st8[3])
 print(f"ADC top-100 n={n} M={M}: {us:.1f} us  {n*M/us/1e3:.1f} GB/s  {n/us*1e6:.3e} evals/s")
 
 

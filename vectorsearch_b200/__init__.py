@@ -8,4 +8,4 @@ J/fdb/FdbVectorIndex.java:676-721 (brute force), :754-769 (ADC) and :997-1043 (r
 from ._lib import METRIC_COSINE, METRIC_L2, VsError, load  # noqa: F401
 from .ops import (Distances, PqEncoder, PqTrainer, Segment, build_lut, device_info, init,  # noqa: F401
                   kernel_launch_count, merge_topk, pq_approx_distance, pq_lut_distance,
-                  set_simd_lanes, shutdown)
+                  set_option, set_simd_lanes, shutdown)

@@ -64,6 +64,7 @@ SIGNATURES = {
     "vs_merge_packed_dev": (i32, [vp, i32, i32, i32, i32, vp, vp, vp, vp]),
     "vs_merge_topk_dev": (i32, [vp, vp, i64, i32, vp, vp, vp, vp]),
     "vs_kernel_launch_count": (i64, []),
+    "vs_set_option": (i32, [C.c_char_p, i64]),
 }
 
 

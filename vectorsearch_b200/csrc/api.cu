@@ -22,6 +22,8 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 static std::atomic<int> g_device{-1};
 static std::atomic<int> g_lanes{16};
+static std::atomic<int64_t> g_adc_fast_min_rows{16384};   // below this the generic ADC kernel runs
+static std::atomic<int64_t> g_adc_fast_cap{4096};         // candidate-list entries per scan CTA
 static int g_sms = 0;
 static std::mutex g_mu;
 static std::unordered_map<uint64_t, Segment*> g_segments;
@@ -58,12 +60,15 @@ struct ThreadCtx {
   size_t h_cap = 0;
   unsigned long long* d_ticket = nullptr;  // [queries][4] control words, zero between launches
   size_t ticket_cap = 0;
+  unsigned int* d_fs = nullptr;  // [queries][FS_WORDS] ADC fast-scan histogram + control, zero between launches
+  size_t fs_cap = 0;
   ~ThreadCtx() {
     // process teardown: the context may already be gone; ignore errors
     if (device >= 0 && g_device.load() == device) {
       if (d_buf) cudaFree(d_buf);
       if (h_buf) cudaFreeHost(h_buf);
       if (d_ticket) cudaFree(d_ticket);
+      if (d_fs) cudaFree(d_fs);
       if (stream) cudaStreamDestroy(stream);
     }
   }
@@ -122,6 +127,23 @@ static int ctx_reserve_ticket(ThreadCtx* c, size_t n) {
   e = cudaMemsetAsync(c->d_ticket, 0, cap * 4 * sizeof(unsigned long long), c->stream);
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemset(ticket)");
   c->ticket_cap = cap;
+  return VS_OK;
+}
+
+static int ctx_reserve_fs(ThreadCtx* c, size_t n) {
+  if (n <= c->fs_cap) return VS_OK;
+  cudaStreamSynchronize(c->stream);
+  if (c->d_fs) cudaFree(c->d_fs);
+  c->d_fs = nullptr;
+  c->fs_cap = 0;
+  size_t cap = n < 4 ? 4 : n * 2;
+  cudaError_t e = cudaMalloc(&c->d_fs, cap * FS_WORDS * sizeof(unsigned int));
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(fast-scan scratch)");
+  e = cudaMemsetAsync(c->d_fs, 0, cap * FS_WORDS * sizeof(unsigned int), c->stream);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMemset(fast-scan scratch)");
+  e = cudaStreamSynchronize(c->stream);
+  if (e != cudaSuccess) return cuda_fail(e, "sync");
+  c->fs_cap = cap;
   return VS_OK;
 }
 
@@ -209,7 +231,15 @@ static uint64_t occ_key(int kind, int a, int b, int c, int threads, size_t smem)
 // scan launch shapes are cached per (n, d, nq > 1, k, metric, lanes)
 static std::mutex g_scan_mu;
 static std::unordered_map<uint64_t, ScanLaunch> g_scan_cache;
-static std::unordered_map<uint64_t, AdcScanLaunch> g_adc_cache;
+struct AdcPlan {
+  bool fast;
+  AdcScanLaunch slow;
+  AdcFastLaunch fastL;
+  int64_t partial_keys;     // keys of per-CTA list scratch per query
+  size_t cand_entries;      // candidate-list entries per query (fast path)
+  size_t extra_words;       // 8-byte units per query that follow the lists (byte table + header)
+};
+static std::unordered_map<uint64_t, AdcPlan> g_adc_cache;
 
 static int plan_scan(const Segment* s, int nq, int k, bool cosine, ScanLaunch* out) {
   const int ln = lanes();
@@ -231,8 +261,10 @@ static int plan_scan(const Segment* s, int nq, int k, bool cosine, ScanLaunch* o
   return VS_OK;
 }
 
-static int plan_adc(const Segment* s, int nq, int k, AdcScanLaunch* out) {
-  uint64_t key = occ_key(20, s->M, s->K, k, nq > 1 ? 2 : 1, (size_t)s->n);
+static int plan_adc(const Segment* s, int nq, int k, AdcPlan* out) {
+  const int64_t min_rows = g_adc_fast_min_rows.load(), cap_opt = g_adc_fast_cap.load();
+  uint64_t key = occ_key(20, s->M, s->K, k, nq > 1 ? 2 : 1, (size_t)s->n) ^ ((uint64_t)min_rows * 0x9e3779b97f4a7c15ull) ^
+                 ((uint64_t)cap_opt << 17);
   {
     std::lock_guard<std::mutex> lk(g_scan_mu);
     auto it = g_adc_cache.find(key);
@@ -241,12 +273,26 @@ static int plan_adc(const Segment* s, int nq, int k, AdcScanLaunch* out) {
       return VS_OK;
     }
   }
-  AdcScanLaunch L{};
-  L.n = s->n; L.M = s->M; L.K = s->K; L.nq = nq; L.k = k;
-  if (!adc_configure(L, g_sms)) return fail(VS_ECUDA, "ADC scan kernel cannot be resident for M=%d k=%d", s->M, k);
+  AdcPlan P{};
+  P.fast = adc_fast_supported(s->M, s->K) && s->n >= min_rows && s->n < (int64_t(1) << 47);
+  if (P.fast) {
+    AdcFastLaunch& L = P.fastL;
+    L.n = s->n; L.M = s->M; L.K = s->K; L.nq = nq; L.k = k;
+    if (!adc_fast_configure(L, g_sms)) return fail(VS_ECUDA, "ADC fast-scan kernel cannot be resident for M=%d k=%d", s->M, k);
+    L.cap = (unsigned int)(cap_opt < 1 ? 1 : cap_opt);
+    P.partial_keys = L.partial_keys;
+    P.cand_entries = (size_t)L.cap * L.grid;
+    P.extra_words = ((size_t)s->M * 256 + 8 + 7) / 8;  // byte table + header, in 8-byte units
+  } else {
+    AdcScanLaunch& L = P.slow;
+    L.n = s->n; L.M = s->M; L.K = s->K; L.nq = nq; L.k = k;
+    if (!adc_configure(L, g_sms)) return fail(VS_ECUDA, "ADC scan kernel cannot be resident for M=%d k=%d", s->M, k);
+    P.partial_keys = L.partial_keys;
+    P.cand_entries = 0;
+  }
   std::lock_guard<std::mutex> lk(g_scan_mu);
-  g_adc_cache[key] = L;
-  *out = L;
+  g_adc_cache[key] = P;
+  *out = P;
   return VS_OK;
 }
 
@@ -279,10 +325,23 @@ static int bruteforce_dev(ThreadCtx* c, cudaStream_t st, const Segment* s, const
 
 static int adc_dev(cudaStream_t st, const Segment* s, const float* d_q, int nq, int n_cand, double* d_lut,
                    int64_t* d_ids, double* d_approx, int32_t* d_counts, ulonglong2* d_partial,
-                   unsigned long long* d_ticket, const AdcScanLaunch& p) {
+                   unsigned long long* d_ticket, unsigned int* d_fs, unsigned long long* d_cand, const AdcPlan& p) {
   (void)n_cand;
+  if (p.fast) {
+    // the candidate scratch also carries the byte tables: [nq * cand_entries][nq * M*256 bytes][nq headers]
+    unsigned char* d_qtab = reinterpret_cast<unsigned char*>(d_cand + (size_t)nq * p.cand_entries);
+    unsigned int* d_qhdr = reinterpret_cast<unsigned int*>(d_qtab + (size_t)nq * s->M * 256);
+    CK(launch_build_lut_q(s->centroids, s->M, s->K, s->subDim, d_q, nq, lanes(), d_lut, d_qtab, d_qhdr, st), "build_lut launch");
+    AdcFastLaunch L = p.fastL;
+    L.codes = s->codes; L.lut64 = d_lut; L.qtab = d_qtab; L.qhdr = d_qhdr; L.nq = nq; L.fs = d_fs; L.cand = d_cand;
+    L.partial = d_partial; L.ctrl = d_ticket; L.ids_out = d_ids; L.approx_out = d_approx;
+    L.counts_out = d_counts; L.id_base = s->id_base;
+    CK(launch_adc_fast(L, st), "adc fast-scan launch");
+    CK(launch_adc_fallback(L, st), "adc fallback launch");
+    return VS_OK;
+  }
   CK(launch_build_lut(s->centroids, s->M, s->K, s->subDim, d_q, nq, lanes(), d_lut, st), "build_lut launch");
-  AdcScanLaunch L = p;
+  AdcScanLaunch L = p.slow;
   L.codes = s->codes; L.lut64 = d_lut; L.nq = nq;
   L.partial = d_partial; L.ctrl = d_ticket; L.ids_out = d_ids; L.approx_out = d_approx;
   L.counts_out = d_counts; L.id_base = s->id_base;
@@ -372,8 +431,26 @@ int32_t vs_device_info(int32_t* sm_count_, int64_t* free_bytes, int64_t* total_b
 }
 
 int64_t vs_kernel_launch_count(void) { return g_launches.load(); }
+
+int32_t vs_debug_adc_stats(uint32_t* out8) { return vs::debug_adc_stats(out8) == 0 ? VS_OK : VS_ECUDA; }
+
+int32_t vs_set_option(const char* name, int64_t value) {
+  if (!name) return fail(VS_EINVAL, "null option name");
+  if (!strcmp(name, "adc_fast_min_rows")) {
+    if (value < 0) return fail(VS_EINVAL, "adc_fast_min_rows must be >= 0");
+    g_adc_fast_min_rows.store(value);
+    return VS_OK;
+  }
+  if (!strcmp(name, "adc_fast_cap")) {
+    if (value < 1 || value > (int64_t(1) << 24)) return fail(VS_EINVAL, "adc_fast_cap must be in 1..2^24");
+    g_adc_fast_cap.store(value);
+    return VS_OK;
+  }
+  return fail(VS_EINVAL, "unknown option %s", name);
+}
 #ifdef VS_PHASE_STAMPS
 int32_t vs_debug_read_stamps(void* dst, int64_t bytes) { return vs::debug_read_stamps(dst, (size_t)bytes); }
+int32_t vs_debug_read_stamps_adc(void* dst, int64_t bytes) { return vs::debug_read_stamps_adc(dst, (size_t)bytes); }
 #endif
 
 // =================================================================================================
@@ -720,17 +797,18 @@ static int adc_common(uint64_t h, const float* q, int32_t nq, int32_t n_cand, bo
     fill_empty(ids_out, scores_out, counts_out, nq, kout);
     return VS_OK;
   }
-  AdcScanLaunch p;
+  AdcPlan p;
   RET(plan_adc(s, nq, n_cand, &p));
-  const size_t per_q_partial = (size_t)p.partial_keys * 16;
-  int group = (int)(PARTIAL_BUDGET / per_q_partial);
+  const size_t per_q_partial = (size_t)p.partial_keys * 16, per_q_cand = (p.cand_entries + p.extra_words) * 8;
+  int group = (int)(PARTIAL_BUDGET / (per_q_partial + per_q_cand));
   if (group < 1) group = 1;
   if (group > nq) group = nq;
   const size_t qb = (size_t)group * s->d * 4, cib = (size_t)group * n_cand * 8, ccb = (size_t)group * 4;
   const size_t ob = (size_t)group * kout * 8, lb = (size_t)group * s->M * s->K * 8;
-  RET(ctx_reserve_dev(c, Arena::need({qb, cib, cib, ccb, ob, ob, ccb, lb, per_q_partial * group})));
+  RET(ctx_reserve_dev(c, Arena::need({qb, cib, cib, ccb, ob, ob, ccb, lb, per_q_partial * group, per_q_cand * group})));
   RET(ctx_reserve_host(c, Arena::need({qb, ob, ob, ccb})));
   RET(ctx_reserve_ticket(c, group));
+  if (p.fast) RET(ctx_reserve_fs(c, group));
   for (int q0 = 0; q0 < nq; q0 += group) {
     const int g = (q0 + group <= nq) ? group : nq - q0;
     Arena A(c->d_buf), H(c->h_buf);
@@ -743,13 +821,14 @@ static int adc_common(uint64_t h, const float* q, int32_t nq, int32_t n_cand, bo
     int32_t* dcn = A.take<int32_t>(group);
     double* dlut = A.take<double>((size_t)group * s->M * s->K);
     ulonglong2* dpart = A.take<ulonglong2>((size_t)group * p.partial_keys);
+    unsigned long long* dcand = A.take<unsigned long long>((size_t)group * (p.cand_entries + p.extra_words));
     float* hq = H.take<float>((size_t)group * s->d);
     int64_t* hids = H.take<int64_t>((size_t)group * kout);
     double* hsc = H.take<double>((size_t)group * kout);
     int32_t* hcn = H.take<int32_t>(group);
     memcpy(hq, q + (size_t)q0 * s->d, (size_t)g * s->d * 4);
     CK(cudaMemcpyAsync(dq, hq, (size_t)g * s->d * 4, cudaMemcpyHostToDevice, c->stream), "H2D q");
-    RET(adc_dev(c->stream, s, dq, g, n_cand, dlut, dcid, dcap, dccn, dpart, c->d_ticket, p));
+    RET(adc_dev(c->stream, s, dq, g, n_cand, dlut, dcid, dcap, dccn, dpart, c->d_ticket, c->d_fs, dcand, p));
     const int64_t* src_ids = dcid;
     const double* src_sc = dcap;
     const int32_t* src_cn = dccn;
@@ -1024,18 +1103,22 @@ int32_t vs_adc_topk_dev(uint64_t h, const float* d_q, int32_t nq, int32_t n_cand
   ThreadCtx* c;
   RET(ctx_bind(&c));
   if (s->n == 0) return fail(VS_EINVAL, "empty segment: use the host variant");
-  AdcScanLaunch p;
+  AdcPlan p;
   RET(plan_adc(s, nq, n_cand, &p));
   const size_t pb = (size_t)nq * p.partial_keys * 16, lb = (size_t)nq * s->M * s->K * 8;
-  if (pb > (size_t(1) << 31)) return fail(VS_EINVAL, "query batch too large for the stream variant");
-  RET(ctx_reserve_dev(c, Arena::need({pb, lb})));
+  const size_t cdb = (size_t)nq * (p.cand_entries + p.extra_words) * 8;
+  if (pb + cdb > (size_t(1) << 31)) return fail(VS_EINVAL, "query batch too large for the stream variant");
+  const bool grow = Arena::need({pb, lb, cdb}) > c->d_cap || (size_t)nq > c->ticket_cap || (p.fast && (size_t)nq > c->fs_cap);
+  RET(ctx_reserve_dev(c, Arena::need({pb, lb, cdb})));
   RET(ctx_reserve_ticket(c, nq));
+  if (p.fast) RET(ctx_reserve_fs(c, nq));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  CK(cudaStreamSynchronize(c->stream), "sync");
+  if (grow) CK(cudaStreamSynchronize(c->stream), "sync");
   Arena A(c->d_buf);
   ulonglong2* dpart = A.take<ulonglong2>((size_t)nq * p.partial_keys);
   double* dlut = A.take<double>((size_t)nq * s->M * s->K);
-  return adc_dev(st, s, d_q, nq, n_cand, dlut, d_ids, d_approx, d_counts, dpart, c->d_ticket, p);
+  unsigned long long* dcand = A.take<unsigned long long>((size_t)nq * (p.cand_entries + p.extra_words));
+  return adc_dev(st, s, d_q, nq, n_cand, dlut, d_ids, d_approx, d_counts, dpart, c->d_ticket, c->d_fs, dcand, p);
 }
 
 int32_t vs_adc_rerank_topk_dev(uint64_t h, const float* d_q, int32_t nq, int32_t n_cand, int32_t k,
@@ -1050,22 +1133,26 @@ int32_t vs_adc_rerank_topk_dev(uint64_t h, const float* d_q, int32_t nq, int32_t
   ThreadCtx* c;
   RET(ctx_bind(&c));
   if (s->n == 0) return fail(VS_EINVAL, "empty segment: use the host variant");
-  AdcScanLaunch p;
+  AdcPlan p;
   RET(plan_adc(s, nq, n_cand, &p));
   const size_t pb = (size_t)nq * p.partial_keys * 16, lb = (size_t)nq * s->M * s->K * 8;
-  const size_t cib = (size_t)nq * n_cand * 8, ccb = (size_t)nq * 4;
-  if (pb > (size_t(1) << 31)) return fail(VS_EINVAL, "query batch too large for the stream variant");
-  RET(ctx_reserve_dev(c, Arena::need({pb, lb, cib, cib, ccb})));
+  const size_t cib = (size_t)nq * n_cand * 8, ccb = (size_t)nq * 4, cdb = (size_t)nq * (p.cand_entries + p.extra_words) * 8;
+  if (pb + cdb > (size_t(1) << 31)) return fail(VS_EINVAL, "query batch too large for the stream variant");
+  const bool grow = Arena::need({pb, lb, cib, cib, ccb, cdb}) > c->d_cap || (size_t)nq > c->ticket_cap ||
+                    (p.fast && (size_t)nq > c->fs_cap);
+  RET(ctx_reserve_dev(c, Arena::need({pb, lb, cib, cib, ccb, cdb})));
   RET(ctx_reserve_ticket(c, nq));
+  if (p.fast) RET(ctx_reserve_fs(c, nq));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  CK(cudaStreamSynchronize(c->stream), "sync");
+  if (grow) CK(cudaStreamSynchronize(c->stream), "sync");
   Arena A(c->d_buf);
   ulonglong2* dpart = A.take<ulonglong2>((size_t)nq * p.partial_keys);
   double* dlut = A.take<double>((size_t)nq * s->M * s->K);
   int64_t* dcid = A.take<int64_t>((size_t)nq * n_cand);
   double* dcap = A.take<double>((size_t)nq * n_cand);
   int32_t* dccn = A.take<int32_t>(nq);
-  RET(adc_dev(st, s, d_q, nq, n_cand, dlut, dcid, dcap, dccn, dpart, c->d_ticket, p));
+  unsigned long long* dcand = A.take<unsigned long long>((size_t)nq * (p.cand_entries + p.extra_words));
+  RET(adc_dev(st, s, d_q, nq, n_cand, dlut, dcid, dcap, dccn, dpart, c->d_ticket, c->d_fs, dcand, p));
   return rerank_dev(st, s, d_q, nq, dcid, n_cand, k, metric, d_ids, d_scores, d_counts);
 }
 

@@ -30,6 +30,7 @@ int pq_train_device(cudaStream_t st, const float* dX, int64_t n, int d, int M, i
 
 #ifdef VS_PHASE_STAMPS
 int debug_read_stamps(void* dst, size_t bytes);  // development only (scan.cu)
+int debug_read_stamps_adc(void* dst, size_t bytes);  // development only (adc_fast.cu)
 #endif
 
 }  // namespace vs

@@ -108,6 +108,51 @@ struct AdcScanLaunch {
 bool adc_configure(AdcScanLaunch& L, int sms);
 cudaError_t launch_adc_scan(const AdcScanLaunch& L, cudaStream_t st);
 
+// ---- adc_fast.cu: conflict-free byte-LUT scan + exact candidate ranking (M = 8 or 16, K <= 256) ----
+constexpr int FS_THREADS = 1024;
+constexpr int FS_U = 8;                     // rows in flight per thread (128 KB per SM: the HBM latency x bandwidth product)
+constexpr int FS_WU = 4;                    // rows per thread of the warm-up sample
+constexpr int FS_PF = 3;                     // batches requested into L2 ahead of the loads
+constexpr int FS_BINS = 4096;               // histogram bins of the integer row sum (<= 255 * 16)
+constexpr int FS_CTRL = 8;                  // control words: ticket, ~T, fallback flag
+constexpr int FS_TICKET = 0, FS_TINV = 1, FS_FLAG = 2, FS_NEXT = 3;  // FS_NEXT: dynamic batch counter
+constexpr int FS_MAX_GRID = 256;            // scan CTAs per query (one candidate list each)
+constexpr int FS_WORDS = FS_BINS + FS_CTRL + FS_MAX_GRID;  // per-query persistent scratch (uint32)
+constexpr unsigned int FS_T_INF = 0xfffffffeu;  // "no threshold yet"; 0xffffffff marks rows that do not exist
+struct AdcFastLaunch {
+  const uint8_t* codes;
+  int64_t n;
+  int M, K;
+  const double* lut64;       // [nq][M][K]
+  const unsigned char* qtab; // [nq][M][256] byte image of the LUT (build_lut_q)
+  const unsigned int* qhdr;  // [nq] 1 = no usable byte image
+  int nq;
+  int k, kp;
+  unsigned int* fs;          // [nq][FS_WORDS], zero between launches
+  unsigned long long* cand;  // [nq][grid][cap] per-CTA candidate lists (S << 48 | row)
+  unsigned int cap;          // entries per CTA list
+  ulonglong2* partial;       // final kernel: per-CTA lists
+  unsigned long long* ctrl;
+  int64_t partial_keys;
+  int64_t* ids_out;
+  double* approx_out;
+  int32_t* counts_out;
+  int64_t id_base;
+  int64_t out_stride;
+  int grid;                  // scan CTAs per query
+  size_t smem_bytes;
+  int final_grid, final_threads;
+  size_t final_smem;
+};
+bool adc_fast_supported(int M, int K);
+bool adc_fast_configure(AdcFastLaunch& L, int sms);
+// buildLut for nq queries plus the byte image the fast scan needs (one CTA per query, M <= 16)
+cudaError_t launch_build_lut_q(const float* centroids, int M, int K, int subDim, const float* q, int nq, int lanes,
+                               double* lut64, unsigned char* qtab, unsigned int* qhdr, cudaStream_t st);
+cudaError_t launch_adc_fast(const AdcFastLaunch& L, cudaStream_t st);
+cudaError_t launch_adc_fallback(const AdcFastLaunch& L, cudaStream_t st);
+int debug_adc_stats(unsigned int* out8);  // development: {candidates, T_final, full-scan flag} of the last query 0
+
 // ---- pq.cu ------------------------------------------------------------------------------------
 // PqEncoder.encode / the PqTrainer assignment step over n rows (J/pq/PqEncoder.java:18-37,
 // J/pq/PqTrainer.java:56-68): strict-< argmin over K centroids per subspace, reference arithmetic.

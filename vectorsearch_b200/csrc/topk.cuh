@@ -259,7 +259,8 @@ __device__ __forceinline__ void topk_write_out(const ulonglong2* outk, int k, co
 // ---- shared epilogue of the streaming kernels ---------------------------------------------------
 
 // flush + block combine + publish + (last CTA) final merge.  smem holds nw collectors.
-static __device__ __noinline__ void topk_epilogue(WarpTopK& tk, ulonglong2* smem, int kp, int k,
+// Both overloads return true in the CTA that ran the final merge (the last one of its query).
+static __device__ __noinline__ bool topk_epilogue(WarpTopK& tk, ulonglong2* smem, int kp, int k,
                                               const TopkOut& o) {
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -278,7 +279,7 @@ static __device__ __noinline__ void topk_epilogue(WarpTopK& tk, ulonglong2* smem
     s_last = (t == gridDim.x - 1) ? 1u : 0u;
   }
   __syncthreads();
-  if (!s_last) return;
+  if (!s_last) return false;
   __threadfence();
   // final merge by the last CTA of this query
   {
@@ -316,13 +317,14 @@ static __device__ __noinline__ void topk_epilogue(WarpTopK& tk, ulonglong2* smem
     o.counts[qi] = s_found;
     o.ctrl[4 * qi] = 0ull;  // ready for the next launch on this scratch
   }
+  return true;
 }
 
 // Epilogue of the register collector: block combine by rank selection, publish the CTA's k keys,
 // and (last CTA of the query) the final merge.  The k-th smallest list head bounds the launch-wide
 // k-th key, so only keys at or below that bound -- at most k lists x k keys -- are gathered and
 // rank-selected; nothing is sorted and nothing scales with grid x k beyond two coalesced reads.
-static __device__ __noinline__ void topk_epilogue(WarpTopKReg& tk, ulonglong2* smem, int kp, int k,
+static __device__ __noinline__ bool topk_epilogue(WarpTopKReg& tk, ulonglong2* smem, int kp, int k,
                                               const TopkOut& o) {
   (void)kp;
   const int lane = threadIdx.x & 31;
@@ -353,7 +355,7 @@ static __device__ __noinline__ void topk_epilogue(WarpTopKReg& tk, ulonglong2* s
     st_key(&s_bound, key_empty());
   }
   __syncthreads();
-  if (!s_last) return;
+  if (!s_last) return false;
   __threadfence();
   phase_stamp(6);
   const int nl = gridDim.x;  // <= TOPK_MAX_LISTS (host guarantees)
@@ -388,6 +390,7 @@ static __device__ __noinline__ void topk_epilogue(WarpTopKReg& tk, ulonglong2* s
   __syncthreads();
   phase_stamp(7);
   topk_write_out(outk, k, o, qi);
+  return true;
 }
 
 }  // namespace vs

@@ -42,6 +42,11 @@ def set_simd_lanes(lanes: int) -> None:
     check(L.load().vs_set_simd_lanes(lanes))
 
 
+def set_option(name: str, value: int) -> None:
+    """Tuning knobs of libvsgpu (vs_set_option); results never depend on them."""
+    check(L.load().vs_set_option(name.encode(), int(value)))
+
+
 def kernel_launch_count() -> int:
     return int(L.load().vs_kernel_launch_count())
 
