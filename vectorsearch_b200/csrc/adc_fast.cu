@@ -7,7 +7,7 @@
 // Why not the obvious kernel (adc.cu): M random 4-byte shared-memory lookups per row serialise on
 // bank conflicts (~3.5-way for 32 random addresses) and every survivor of a per-warp threshold
 // walks a divergent fp64 path; measured 390 GB/s of code bytes (6% of HBM).  This kernel:
-//  * quantises the query's LUT (the reference's doubles, buildLut :1067-1079; build_lut_q_kernel)
+//  * quantises the query's LUT (the reference's doubles, buildLut :1067-1079; build_lut_mm_kernel)
 //    to ONE BYTE per entry, q = floor((lut[s][c] - min_s) / delta), with one global step delta, so that
 //        sum_s min_s + delta * S  <=  pqApproxDistance  <=  sum_s min_s + delta * (S + M),
 //    S = sum_s q[s][code_s] an integer <= 255*M;
@@ -126,79 +126,46 @@ __device__ __forceinline__ unsigned int fs_word_sum(unsigned int w, unsigned int
 // high address byte = bits 2..6 of c, low address byte = bit 7 and bits 0..1 of c
 __host__ __device__ inline unsigned int fs_entry_offset(unsigned int c) { return ((c >> 2) & 31u) * 256u + (c & 0x83u); }
 
-// ---- LUT build + byte quantisation: one CTA per query ------------------------------------------------
+// ---- LUT build: one CTA per (subspace, query) ----------------------------------------------------------
 // lut64[q][s][c] = Distances.l2Squared(query, s*subDim, centroids[s][c], 0, subDim) (buildLut,
-// J/fdb/FdbVectorIndex.java:1067-1079) in reference arithmetic; qtab[q][s][c] = its byte image
-// floor((v - min_s) / delta), entries c >= K standing for the 0 that pqApproxDistance adds for
-// them (:1061); qhdr[q] = 1 when the table has no usable byte image.
-__global__ void __launch_bounds__(FS_THREADS)
-build_lut_q_kernel(const float* __restrict__ centroids, int M, int K, int subDim, const float* __restrict__ Q,
-                   int lanes, double* __restrict__ LUT64, unsigned char* __restrict__ QTAB,
-                   unsigned int* __restrict__ QHDR) {
-  const int tid = threadIdx.x;
-  const int lane = tid & 31;
-  const int qi = blockIdx.x;
-  const int NE = M * 256;
-  const float* q = Q + (size_t)qi * M * subDim;
-  double* lut64 = LUT64 + (size_t)qi * M * K;
-  unsigned char* qtab = QTAB + (size_t)qi * NE;
-  __shared__ unsigned long long s_mn[16], s_mx[16];
-  __shared__ unsigned long long s_amax;
-  __shared__ int s_bad;
-  if (tid < 16) {
-    s_mn[tid] = ~0ull;
-    s_mx[tid] = 0ull;
-  }
-  if (tid == 0) {
-    s_bad = 0;
-    s_amax = 0ull;
+// J/fdb/FdbVectorIndex.java:1067-1079) in reference arithmetic, plus what the scan needs to derive
+// the byte image: mm[q][s] = {min, max} of the subspace's entries as order-preserving uint64 images
+// (max = ~0 when an entry is NaN or infinite).
+__global__ void __launch_bounds__(256)
+build_lut_mm_kernel(const float* __restrict__ centroids, int M, int K, int subDim, const float* __restrict__ Q,
+                    int lanes, double* __restrict__ LUT64, unsigned long long* __restrict__ MM) {
+  const int s = blockIdx.x, qi = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const float* q = Q + (size_t)qi * M * subDim + (size_t)s * subDim;
+  __shared__ unsigned long long s_mn, s_mx;
+  if (threadIdx.x == 0) {
+    s_mn = ~0ull;
+    s_mx = 0ull;
   }
   __syncthreads();
-  double v[4];  // M <= 16: at most 4 entries per thread
+  for (int c0 = 0; c0 < K; c0 += blockDim.x) {
+    const int c = c0 + threadIdx.x;
+    unsigned long long lo = ~0ull, hi = 0ull;
+    if (c < K) {
+      const double v = ref_sum_thread<REF_L2SQ>(q, centroids + ((size_t)s * K + c) * subDim, subDim, lanes);
+      LUT64[((size_t)qi * M + s) * K + c] = v;
+      lo = hi = f64_ordered(v);
+      if (!(fabs(v) <= 1.7976931348623157e308)) hi = ~0ull;
+    }
 #pragma unroll
-  for (int i = 0; i < 4; i++) {
-    const int e = tid + i * FS_THREADS;  // a warp stays inside one subspace
-    v[i] = 0.0;
-    if (e < NE) {
-      const int s = e >> 8, c = e & 255;
-      if (c < K) {
-        v[i] = ref_sum_thread<REF_L2SQ>(q + (size_t)s * subDim, centroids + ((size_t)s * K + c) * subDim, subDim, lanes);
-        lut64[(size_t)s * K + c] = v[i];
-      }
-      const bool bad = !(fabs(v[i]) <= 1.7976931348623157e308);
-      unsigned long long lo = f64_ordered(v[i]), hi = lo, am = (unsigned long long)__double_as_longlong(fabs(v[i]));
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        lo = min(lo, __shfl_xor_sync(FULL_MASK, lo, o));
-        hi = max(hi, __shfl_xor_sync(FULL_MASK, hi, o));
-        am = max(am, __shfl_xor_sync(FULL_MASK, am, o));
-      }
-      const unsigned anybad = __ballot_sync(FULL_MASK, bad);
-      if (lane == 0) {
-        atomicMin(&s_mn[s], lo);
-        atomicMax(&s_mx[s], hi);
-        atomicMax(&s_amax, am);
-        if (anybad) s_bad = 1;
-      }
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = min(lo, __shfl_xor_sync(FULL_MASK, lo, o));
+      hi = max(hi, __shfl_xor_sync(FULL_MASK, hi, o));
+    }
+    if (lane == 0) {
+      atomicMin(&s_mn, lo);
+      atomicMax(&s_mx, hi);
     }
   }
   __syncthreads();
-  double range = 0.0;
-  for (int s = 0; s < M; s++) range = fmax(range, f64_from_ordered(s_mx[s]) - f64_from_ordered(s_mn[s]));
-  const double delta = range / 255.0;
-  const double amax = __longlong_as_double((long long)s_amax);
-  const bool degenerate = s_bad || !(delta > 0.0) || !(delta > amax * 1e-9);
-  if (tid == 0) QHDR[qi] = degenerate ? 1u : 0u;
-  if (degenerate) return;
-  const double inv_delta = 1.0 / delta;
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    const int e = tid + i * FS_THREADS;
-    if (e < NE) {
-      int qv = (int)((v[i] - f64_from_ordered(s_mn[e >> 8])) * inv_delta);
-      qv = qv < 0 ? 0 : (qv > 255 ? 255 : qv);
-      qtab[e] = (unsigned char)qv;
-    }
+  if (threadIdx.x == 0) {
+    MM[((size_t)qi * M + s) * 2 + 0] = s_mn;
+    MM[((size_t)qi * M + s) * 2 + 1] = s_mx;
   }
 }
 
@@ -206,8 +173,7 @@ build_lut_q_kernel(const float* __restrict__ centroids, int M, int K, int subDim
 template <int MW>
 __global__ void __launch_bounds__(FS_THREADS, 1)
 adc_fastscan_kernel(const uint8_t* __restrict__ codes, int64_t n, int K, const double* __restrict__ LUT64,
-                    const unsigned char* __restrict__ QTAB, const unsigned int* __restrict__ QHDR,
-                    unsigned int k, unsigned int* __restrict__ fs, unsigned long long* __restrict__ cand_all,
+                    const unsigned long long* __restrict__ MM, unsigned int k, unsigned int* __restrict__ fs, unsigned long long* __restrict__ cand_all,
                     unsigned int cap, int64_t* __restrict__ ids_out, double* __restrict__ approx_out,
                     int32_t* __restrict__ counts_out, int64_t id_base, int64_t out_stride) {
   extern __shared__ __align__(128) unsigned char fsm[];
@@ -231,7 +197,30 @@ adc_fastscan_kernel(const uint8_t* __restrict__ codes, int64_t n, int K, const d
   __shared__ long long s_next[2];
   phase_stamp(0);
 
-  if (QHDR[qi] != 0u) {
+  // ---- byte image of the LUT: q = floor((v - min_s) / delta), delta = largest subspace range / 255 ------
+  // (entries c >= K stand for the 0 that pqApproxDistance adds for codes outside the codebook, :1061)
+  __shared__ double s_mn[16];
+  __shared__ double s_delta;
+  if (tid == 0) {
+    double range = 0.0, amax = 0.0;
+    bool bad = false;
+    for (int s = 0; s < M; s++) {
+      const unsigned long long lo = MM[((size_t)qi * M + s) * 2], hi = MM[((size_t)qi * M + s) * 2 + 1];
+      bad |= hi == ~0ull;
+      double mn = f64_from_ordered(lo), mx = f64_from_ordered(hi);
+      if (K < 256) {
+        mn = fmin(mn, 0.0);
+        mx = fmax(mx, 0.0);
+      }
+      s_mn[s] = mn;
+      range = fmax(range, mx - mn);
+      amax = fmax(amax, fmax(fabs(mn), fabs(mx)));
+    }
+    const double delta = range / 255.0;
+    s_delta = (bad || !(delta > 0.0) || !(delta > amax * 1e-9)) ? 0.0 : delta;
+  }
+  __syncthreads();
+  if (!(s_delta > 0.0)) {
     // no usable byte image of this table: adc_fallback_kernel evaluates every row exactly
     if (blockIdx.x == 0 && tid == 0) atomicExch(ctrl + FS_FLAG, 1u);
     return;
@@ -240,10 +229,24 @@ adc_fastscan_kernel(const uint8_t* __restrict__ codes, int64_t n, int K, const d
   {
     // word (s, hbit, line) of the byte table holds the four codes c = hbit*128 + line*4 + {0..3}; it goes
     // to s*8192 + line*256 + hbit*128 + l*4 for every lane l (fs_entry_offset)
-    unsigned int* q32 = s_hist;  // staging; the histogram is zeroed below
-    const unsigned int* qsrc = reinterpret_cast<const unsigned int*>(QTAB + (size_t)qi * M * 256);
-    for (int i = tid; i < M * 64; i += FS_THREADS) q32[i] = qsrc[i];
+    unsigned char* qtab = reinterpret_cast<unsigned char*>(s_hist);  // staging; the histogram is zeroed below
+    const double inv_delta = 1.0 / s_delta;
+    double v[(M * 256 + FS_THREADS - 1) / FS_THREADS];
+#pragma unroll
+    for (int i = 0; i < (M * 256 + FS_THREADS - 1) / FS_THREADS; i++) {
+      const int e = tid + i * FS_THREADS, s = e >> 8, c = e & 255;
+      v[i] = (e < M * 256 && c < K) ? lut64[(size_t)s * K + c] : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < (M * 256 + FS_THREADS - 1) / FS_THREADS; i++) {
+      const int e = tid + i * FS_THREADS;
+      if (e < M * 256) {
+        int qv = (int)((v[i] - s_mn[e >> 8]) * inv_delta);
+        qtab[e] = (unsigned char)(qv < 0 ? 0 : (qv > 255 ? 255 : qv));
+      }
+    }
     __syncthreads();
+    const unsigned int* q32 = reinterpret_cast<const unsigned int*>(qtab);
     unsigned int* t32 = reinterpret_cast<unsigned int*>(table);
     for (int wi = tid; wi < M * 2048; wi += FS_THREADS) {
       const int l = wi & 31, rest = wi >> 5, s = rest >> 6, hbit = (rest >> 5) & 1, line = rest & 31;
@@ -652,9 +655,9 @@ bool adc_fast_configure(AdcFastLaunch& L, int sms) {
   return true;
 }
 
-cudaError_t launch_build_lut_q(const float* centroids, int M, int K, int subDim, const float* q, int nq, int lanes,
-                               double* lut64, unsigned char* qtab, unsigned int* qhdr, cudaStream_t st) {
-  build_lut_q_kernel<<<nq, FS_THREADS, 0, st>>>(centroids, M, K, subDim, q, lanes, lut64, qtab, qhdr);
+cudaError_t launch_build_lut_mm(const float* centroids, int M, int K, int subDim, const float* q, int nq, int lanes,
+                                double* lut64, unsigned long long* mm, cudaStream_t st) {
+  build_lut_mm_kernel<<<dim3(M, nq), 256, 0, st>>>(centroids, M, K, subDim, q, lanes, lut64, mm);
   count_launch();
   return cudaGetLastError();
 }
@@ -663,11 +666,11 @@ cudaError_t launch_adc_fast(const AdcFastLaunch& L, cudaStream_t st) {
   const dim3 grid(L.grid, L.nq);
   const int64_t stride = L.out_stride > 0 ? L.out_stride : L.k;
   if (L.M == 16)
-    adc_fastscan_kernel<4><<<grid, FS_THREADS, L.smem_bytes, st>>>(L.codes, L.n, L.K, L.lut64, L.qtab, L.qhdr,
+    adc_fastscan_kernel<4><<<grid, FS_THREADS, L.smem_bytes, st>>>(L.codes, L.n, L.K, L.lut64, L.mm,
                                                                    (unsigned int)L.k, L.fs, L.cand, L.cap, L.ids_out, L.approx_out,
                                                                    L.counts_out, L.id_base, stride);
   else
-    adc_fastscan_kernel<2><<<grid, FS_THREADS, L.smem_bytes, st>>>(L.codes, L.n, L.K, L.lut64, L.qtab, L.qhdr,
+    adc_fastscan_kernel<2><<<grid, FS_THREADS, L.smem_bytes, st>>>(L.codes, L.n, L.K, L.lut64, L.mm,
                                                                    (unsigned int)L.k, L.fs, L.cand, L.cap, L.ids_out, L.approx_out,
                                                                    L.counts_out, L.id_base, stride);
   count_launch();

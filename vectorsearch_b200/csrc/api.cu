@@ -237,7 +237,7 @@ struct AdcPlan {
   AdcFastLaunch fastL;
   int64_t partial_keys;     // keys of per-CTA list scratch per query
   size_t cand_entries;      // candidate-list entries per query (fast path)
-  size_t extra_words;       // 8-byte units per query that follow the lists (byte table + header)
+  size_t extra_words;       // 8-byte units per query that follow the lists (LUT extremes)
 };
 static std::unordered_map<uint64_t, AdcPlan> g_adc_cache;
 
@@ -282,7 +282,7 @@ static int plan_adc(const Segment* s, int nq, int k, AdcPlan* out) {
     L.cap = (unsigned int)(cap_opt < 1 ? 1 : cap_opt);
     P.partial_keys = L.partial_keys;
     P.cand_entries = (size_t)L.cap * L.grid;
-    P.extra_words = ((size_t)s->M * 256 + 8 + 7) / 8;  // byte table + header, in 8-byte units
+    P.extra_words = (size_t)s->M * 2;  // per-subspace {min, max} of the LUT
   } else {
     AdcScanLaunch& L = P.slow;
     L.n = s->n; L.M = s->M; L.K = s->K; L.nq = nq; L.k = k;
@@ -328,12 +328,11 @@ static int adc_dev(cudaStream_t st, const Segment* s, const float* d_q, int nq, 
                    unsigned long long* d_ticket, unsigned int* d_fs, unsigned long long* d_cand, const AdcPlan& p) {
   (void)n_cand;
   if (p.fast) {
-    // the candidate scratch also carries the byte tables: [nq * cand_entries][nq * M*256 bytes][nq headers]
-    unsigned char* d_qtab = reinterpret_cast<unsigned char*>(d_cand + (size_t)nq * p.cand_entries);
-    unsigned int* d_qhdr = reinterpret_cast<unsigned int*>(d_qtab + (size_t)nq * s->M * 256);
-    CK(launch_build_lut_q(s->centroids, s->M, s->K, s->subDim, d_q, nq, lanes(), d_lut, d_qtab, d_qhdr, st), "build_lut launch");
+    // the candidate scratch also carries the per-subspace LUT extremes: [nq * cand_entries][nq * M * 2]
+    unsigned long long* d_mm = d_cand + (size_t)nq * p.cand_entries;
+    CK(launch_build_lut_mm(s->centroids, s->M, s->K, s->subDim, d_q, nq, lanes(), d_lut, d_mm, st), "build_lut launch");
     AdcFastLaunch L = p.fastL;
-    L.codes = s->codes; L.lut64 = d_lut; L.qtab = d_qtab; L.qhdr = d_qhdr; L.nq = nq; L.fs = d_fs; L.cand = d_cand;
+    L.codes = s->codes; L.lut64 = d_lut; L.mm = d_mm; L.nq = nq; L.fs = d_fs; L.cand = d_cand;
     L.partial = d_partial; L.ctrl = d_ticket; L.ids_out = d_ids; L.approx_out = d_approx;
     L.counts_out = d_counts; L.id_base = s->id_base;
     CK(launch_adc_fast(L, st), "adc fast-scan launch");

@@ -157,6 +157,7 @@ __device__ __forceinline__ double ref_sum_halfwarp(const float* __restrict__ a,
   const int ub = len - (len % lanes);
   float acc = 0.0f;
   if (hl < lanes) {
+#pragma unroll 8
     for (int i = hl; i < ub; i += lanes) {
       if (OP == REF_L2SQ) {
         float diff = __fsub_rn(a[i], b[i]);

@@ -124,8 +124,7 @@ struct AdcFastLaunch {
   int64_t n;
   int M, K;
   const double* lut64;       // [nq][M][K]
-  const unsigned char* qtab; // [nq][M][256] byte image of the LUT (build_lut_q)
-  const unsigned int* qhdr;  // [nq] 1 = no usable byte image
+  const unsigned long long* mm;  // [nq][M][2] per-subspace {min, max} images of the LUT (build_lut_mm)
   int nq;
   int k, kp;
   unsigned int* fs;          // [nq][FS_WORDS], zero between launches
@@ -146,9 +145,9 @@ struct AdcFastLaunch {
 };
 bool adc_fast_supported(int M, int K);
 bool adc_fast_configure(AdcFastLaunch& L, int sms);
-// buildLut for nq queries plus the byte image the fast scan needs (one CTA per query, M <= 16)
-cudaError_t launch_build_lut_q(const float* centroids, int M, int K, int subDim, const float* q, int nq, int lanes,
-                               double* lut64, unsigned char* qtab, unsigned int* qhdr, cudaStream_t st);
+// buildLut for nq queries plus the per-subspace extremes the fast scan quantises with (M <= 16)
+cudaError_t launch_build_lut_mm(const float* centroids, int M, int K, int subDim, const float* q, int nq, int lanes,
+                                double* lut64, unsigned long long* mm, cudaStream_t st);
 cudaError_t launch_adc_fast(const AdcFastLaunch& L, cudaStream_t st);
 cudaError_t launch_adc_fallback(const AdcFastLaunch& L, cudaStream_t st);
 int debug_adc_stats(unsigned int* out8);  // development: {candidates, T_final, full-scan flag} of the last query 0

@@ -29,7 +29,7 @@ __device__ __forceinline__ void block_bitonic_sort_keys(ulonglong2* a, int n) {
   }
 }
 
-__global__ void __launch_bounds__(RANK_THREADS)
+__global__ void __launch_bounds__(1024)
 rank_kernel(const float* __restrict__ X, int64_t n, int d, const uint8_t* __restrict__ skip, int lanes,
             const float* __restrict__ Q, const int64_t* __restrict__ cand_ids, int nc, int np, int k,
             int cosine, int64_t id_base, int64_t* __restrict__ ids_out, double* __restrict__ scores_out,
@@ -196,7 +196,11 @@ cudaError_t launch_rank(const RankLaunch& L, cudaStream_t st) {
     cudaError_t e = cudaFuncSetAttribute(rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  rank_kernel<<<L.nq, RANK_THREADS, smem, st>>>(L.X, L.n, L.d, L.skip, L.lanes, L.q, L.cand_ids, L.nc, np,
+  // a half-warp per candidate: as many half-warps as candidates (up to 64) so that the gather of the
+  // candidate rows is one or two latency-bound rounds
+  int threads = RANK_THREADS;
+  while (threads < 1024 && threads < 16 * L.nc) threads <<= 1;
+  rank_kernel<<<L.nq, threads, smem, st>>>(L.X, L.n, L.d, L.skip, L.lanes, L.q, L.cand_ids, L.nc, np,
                                                L.k, L.metric == 1, L.id_base, L.ids_out, L.scores_out,
                                                L.counts_out);
   count_launch();
