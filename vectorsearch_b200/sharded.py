@@ -50,6 +50,24 @@ def merge_gathered_host(ids: np.ndarray, scores: np.ndarray, counts: np.ndarray,
     return cat_i[order], cat_s[order]
 
 
+def gather_and_merge_host(ids: np.ndarray, scores: np.ndarray, count: int, k: int, desc: bool = True, group=None):
+    """One rank's list (ids [k], scores [k], `count` valid) -> the merged top-k, identical on every
+    rank.  Same plumbing as the device path (one all-gather of the fixed-size packed lists, then the
+    rank-ordered stable merge) on host tensors: used with the gloo backend by the CPU tests."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    pack = torch.zeros(2 * k + 1, dtype=torch.int64)
+    pack[:k] = torch.from_numpy(np.ascontiguousarray(ids, dtype=np.int64))
+    pack[k:2 * k] = torch.from_numpy(np.ascontiguousarray(scores, dtype=np.float64).view(np.int64))
+    pack[2 * k] = int(count)
+    gath = [torch.zeros_like(pack) for _ in range(world)]
+    dist.all_gather(gath, pack, group=group)
+    g = torch.stack(gath).numpy()
+    return merge_gathered_host(g[:, :k], g[:, k:2 * k].copy().view(np.float64), g[:, 2 * k], k, desc)
+
+
 class ShardedSegment:
     """One rank's row range of a corpus + the collective merge (torch.distributed)."""
 
