@@ -42,6 +42,25 @@ def host_threads() -> int:
     return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
 
 
+def profiled_traffic(name: str) -> float | None:
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full`
+    summary profiles/<name> (made by tools/ncu_summary.py), or None."""
+    p = ROOT / "profiles" / name
+    if not p.exists():
+        return None
+    tot, seen = 0.0, 0
+    for line in p.read_text().splitlines():
+        for key in ("dram__bytes_read.sum [", "dram__bytes_write.sum ["):
+            if line.startswith(key):
+                unit = line[len(key):line.index("]")]
+                scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit)
+                vals = [float(v) for v in line.split(":", 1)[1].split(",")]
+                if scale and vals:
+                    tot += scale * sum(vals) / len(vals)
+                    seen += 1
+    return tot if seen == 2 else None
+
+
 def measured_peaks() -> tuple[float, str]:
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -271,8 +290,8 @@ def run_ours(args) -> None:
                "ms_per_query": cms}
 
     extra = {}
-    if args.workload == "c4" and world == 1:
-        extra["c4"] = bench_c4(vs, L, lib, torch, dev, K, W, hbm_peak)
+    if args.workload in ("c4", "all") and world == 1:
+        extra["c4"] = bench_c4(vs, L, lib, torch, dev, min(K, 50), W, hbm_peak)
 
     if rank == 0:
         line = {
@@ -286,8 +305,10 @@ def run_ours(args) -> None:
                        "l2_policy": "input 512 MB per step > 126 MB L2 (no flush needed)"},
             "qps": 1e3 / ms_per_step,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
-                         "kernel": "scan_kernel<TPR=4,U=2,L2> (K1)", "kernel_ms": kern_ms,
+                         "frac": achieved / hbm_peak, "traffic": profiled_traffic("r1_c2_scan_full.txt"),
+                         "traffic_source": "profiles/r1_c2_scan_full.txt (ncu --set full, dram read+write per launch)",
+                         "peak_source": peak_src,
+                         "kernel": "scan_tma_kernel<TPR=4,U=2,L2,WarpTopKReg> (K1)", "kernel_ms": kern_ms,
                          "kernel_ms_median": durs[len(durs) // 2], "algorithmic_bytes_per_launch": alg_bytes},
             "e2e": {"value": e2e_value, "unit": "distance-evals/s", "h2d_bytes_per_step": DIM * 4,
                     "d2h_bytes_per_step": TOPK * 16 + 4, "ms_per_step": e2e_s / K * 1e3, "qps": K / e2e_s},
@@ -340,9 +361,22 @@ def bench_c4(vs, L, lib, torch, dev, K, W, hbm_peak):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / K
-    out = {"workload": f"C4: ADC top-{C4_NCAND} + exact re-rank top-{TOPK} over {n}x{DIM} (M={C4_M} uint8 codes)",
+    # the ADC scan alone (LUT build + fast scan + conditional fallback launch), for its roofline
+    ids100 = torch.empty((1, C4_NCAND), dtype=torch.int64, device=dev)
+    ap100 = torch.empty((1, C4_NCAND), dtype=torch.float64, device=dev)
+    e0.record()
+    for i in range(K):
+        L.check(lib.vs_adc_topk_dev(seg.handle, q_dev[W + i].data_ptr(), 1, C4_NCAND, ids100.data_ptr(),
+                                    ap100.data_ptr(), cn.data_ptr(), st))
+    e1.record()
+    torch.cuda.synchronize()
+    ms_adc = e0.elapsed_time(e1) / K
+    gbs = n * C4_M / (ms_adc * 1e-3) / 1e9
+    out = {"workload": f"C4: ADC top-{C4_NCAND} + exact re-rank top-{TOPK} over {n}x{DIM} (M={C4_M} uint8 codes), 1 GPU",
            "ms_per_query": ms, "adc_evals_per_s": n / (ms * 1e-3), "qps": 1e3 / ms,
-           "hbm_gbs_algorithmic": n * C4_M / (ms * 1e-3) / 1e9, "roofline_frac": n * C4_M / (ms * 1e-3) / 1e9 / hbm_peak,
+           "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                        "kernel": "build_lut_mm + adc_fastscan_kernel<4> (K5+K6)", "ms_per_launch_group": ms_adc,
+                        "algorithmic_bytes_per_launch": n * C4_M, "traffic": None},
            "generate_s": t_gen, "train_1M_5iters_s": t_train, "encode_s": t_enc,
            "encode_vectors_per_s": n / t_enc}
     seg.free()
@@ -355,7 +389,8 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c4"])
+    ap.add_argument("--workload", default="all", choices=["c2", "c4", "all"],
+                    help="c2 = the headline line only; c4/all also time C4 (ADC + re-rank, 100M rows) into `extra`")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.warmup < 3:
