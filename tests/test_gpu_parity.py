@@ -154,6 +154,123 @@ def test_bruteforce_query_batch(vs, oracle):
         seg.free()
 
 
+# ---- batched queries: tensor-core nomination + exact re-score (batch.cu) ----------------------------------
+@pytest.fixture
+def force_batch(vs):
+    """Route every query batch of >= 2 queries through batch.cu, whatever the segment size."""
+    vs.set_option("batch_min_queries", 2)
+    vs.set_option("batch_min_rows", 1)
+    yield
+    vs.set_option("batch_min_queries", 3)
+    vs.set_option("batch_min_rows", 16384)
+
+
+def _check_batch(vs, oracle, rows, qs, k, metric, skip=None, id_base=0, threads=4):
+    seg = vs.Segment.upload(rows, skip=skip, id_base=id_base)
+    try:
+        ids, sc, cn = seg.bruteforce_topk(qs, k, metric)
+        for i in range(qs.shape[0]):
+            oi, os_, _ = oracle.bruteforce_topk(rows, qs[i], k, metric, skip=skip, threads=threads)
+            c = len(oi)
+            assert cn[i] == c, (i, cn[i], c)
+            assert np.array_equal(ids[i, :c], oi + id_base), f"query {i}: ids differ: {ids[i, :8]} vs {oi[:8] + id_base}"
+            assert _same(sc[i, :c], os_), f"query {i}: scores differ"
+    finally:
+        seg.free()
+
+
+@pytest.mark.parametrize("metric", [0, 1])
+@pytest.mark.parametrize("n,d,k,nq", [(40000, 128, 10, 37), (20000, 768, 50, 130), (9000, 72, 10, 5), (6000, 100, 100, 3),
+                                      (300, 32, 1, 2), (7, 128, 10, 4), (70000, 64, 33, 260), (1000, 128, 1000, 3)])
+def test_batch_bruteforce_matches_oracle(vs, oracle, force_batch, n, d, k, nq, metric):
+    rows = oracle.gen_rows(42, 0, n, d)
+    qs = oracle.gen_rows(43, 0, nq, d)
+    _check_batch(vs, oracle, rows, qs, k, metric)
+
+
+@pytest.mark.parametrize("lanes", [8, 4])
+@pytest.mark.parametrize("metric", [0, 1])
+def test_batch_other_lane_models(vs, oracle, force_batch, lanes, metric):
+    vs.set_simd_lanes(lanes)
+    oracle.set_lanes(lanes)
+    try:
+        rows = oracle.gen_rows(5, 0, 12000, 72)
+        qs = oracle.gen_rows(6, 0, 9, 72)
+        _check_batch(vs, oracle, rows, qs, 20, metric)
+    finally:
+        vs.set_simd_lanes(16)
+        oracle.set_lanes(16)
+
+
+@pytest.mark.parametrize("metric", [0, 1])
+def test_batch_ties_skip_and_fallbacks(vs, oracle, force_batch, metric):
+    n, d = 30000, 64
+    rows = oracle.gen_rows(11, 0, n, d)
+    rows[100:400] = rows[7]           # 300 exact duplicates: ties resolve to the lowest row
+    rows[20000] = rows[7]
+    rows[9] = 0.0                     # zero norm: cosine 0.0
+    rows[5000:5004] *= 3.0            # same direction, larger norm
+    qs = oracle.gen_rows(12, 0, 6, d)
+    qs[0] = rows[7]
+    qs[1] = 0.0                       # zero query: every cosine is 0.0, L2 = |x|
+    skip = np.zeros(n, np.uint8)
+    skip[[7, 101, 102, n - 1]] = 1
+    _check_batch(vs, oracle, rows, qs, 40, metric)
+    _check_batch(vs, oracle, rows, qs, 40, metric, skip=skip, id_base=1_000_000_007)
+    # candidate-list overflow: 20000 duplicates of the best row -> that query falls back to the exact scan
+    rows2 = rows.copy()
+    rows2[2000:22000] = rows2[7]
+    _check_batch(vs, oracle, rows2, qs, 10, metric)
+    # non-finite query -> exact scan for that query only; NaN row -> the whole segment stays per-query
+    qs2 = qs.copy()
+    qs2[3, 5] = np.nan
+    qs2[4, 0] = np.inf
+    _check_batch(vs, oracle, rows, qs2, 10, metric)
+    rows3 = rows.copy()
+    rows3[50, 3] = np.nan
+    rows3[3000, 0] = np.inf
+    _check_batch(vs, oracle, rows3, qs, 10, metric)
+
+
+def test_batch_skip_update_invalidates_coefficients(vs, oracle, force_batch):
+    rows = oracle.gen_rows(21, 0, 5000, 32)
+    qs = oracle.gen_rows(22, 0, 4, 32)
+    seg = vs.Segment.upload(rows)
+    try:
+        ids0, _, _ = seg.bruteforce_topk(qs, 5)
+        skip = np.zeros(5000, np.uint8)
+        skip[ids0[:, 0]] = 1
+        seg.set_skip(skip)
+        ids1, sc1, _ = seg.bruteforce_topk(qs, 5)
+        for i in range(4):
+            oi, os_, _ = oracle.bruteforce_topk(rows, qs[i], 5, 0, skip=skip)
+            assert np.array_equal(ids1[i], oi) and _same(sc1[i], os_)
+        seg.set_skip(None)
+        ids2, _, _ = seg.bruteforce_topk(qs, 5)
+        assert np.array_equal(ids2, ids0)
+    finally:
+        seg.free()
+
+
+def test_c2_full_size_batch_1024(vs, oracle):
+    """C2, query batch 1024: batched results equal the per-query kernel's (all 1024) and the oracle's (a sample)."""
+    n, d, nq = 1_000_000, 128, 1024
+    seg = vs.Segment.generate(42, 0, n, d)
+    try:
+        qs = oracle.gen_rows(43, 0, nq, d)
+        ids, sc, cn = seg.bruteforce_topk(qs, 10)
+        assert np.all(cn == 10) and np.all(np.diff(sc, axis=1) <= 0)
+        for i in range(0, nq, 16):
+            si, ss = seg.bruteforce_topk(qs[i], 10)     # single query: scan.cu
+            assert np.array_equal(ids[i], si) and _same(sc[i], ss)
+        rows = oracle.gen_rows(42, 0, n, d)
+        for i in (0, 511, 1023):
+            oi, os_, _ = oracle.bruteforce_topk(rows, qs[i], 10, threads=8)
+            assert np.array_equal(ids[i], oi) and _same(sc[i], os_)
+    finally:
+        seg.free()
+
+
 def test_empty_segment_and_bad_args(vs):
     seg = vs.Segment.upload(np.zeros((0, 8), np.float32))
     try:

@@ -24,6 +24,9 @@ static std::atomic<int> g_device{-1};
 static std::atomic<int> g_lanes{16};
 static std::atomic<int64_t> g_adc_fast_min_rows{16384};   // below this the generic ADC kernel runs
 static std::atomic<int64_t> g_adc_fast_cap{4096};         // candidate-list entries per scan CTA
+static std::atomic<int64_t> g_batch_min_queries{3};        // query batches at least this large use batch.cu
+static std::atomic<int64_t> g_batch_min_rows{16384};       // ... on segments at least this long
+static std::atomic<int64_t> g_batch_gm_bytes{int64_t(1) << 30};  // group-minima scratch per query chunk
 static int g_sms = 0;
 static std::mutex g_mu;
 static std::unordered_map<uint64_t, Segment*> g_segments;
@@ -184,6 +187,10 @@ static void seg_destroy(Segment* s) {
   if (s->skip) cudaFree(s->skip);
   if (s->centroids) cudaFree(s->centroids);
   if (s->codes) cudaFree(s->codes);
+  for (int m = 0; m < 2; m++) {
+    if (s->ab[m]) cudaFree(s->ab[m]);
+    if (s->stats[m]) cudaFree(s->stats[m]);
+  }
   delete s;
 }
 
@@ -358,6 +365,114 @@ static int rerank_dev(cudaStream_t st, const Segment* s, const float* d_q, int n
   return VS_OK;
 }
 
+// ---- batched-query brute force (batch.cu) ---------------------------------------------------------------
+static std::unordered_map<uint64_t, BatchLaunch> g_batch_cache;
+
+static bool batch_wanted(const Segment* s, int nq, bool cosine) {
+  return nq >= g_batch_min_queries.load() && s->n >= g_batch_min_rows.load() &&
+         batch_supported(s->d, lanes(), cosine, s->n);
+}
+
+static int plan_batch(const Segment* s, int k, bool cosine, BatchLaunch* out) {
+  const int ln = lanes();
+  const uint64_t key = occ_key(cosine ? 31 : 30, s->d, ln, k, 0, (size_t)s->n);
+  {
+    std::lock_guard<std::mutex> lk(g_scan_mu);
+    auto it = g_batch_cache.find(key);
+    if (it != g_batch_cache.end()) {
+      *out = it->second;
+      return VS_OK;
+    }
+  }
+  BatchLaunch L{};
+  L.n = s->n; L.d = s->d; L.lanes = ln; L.cosine = cosine; L.k = k;
+  if (!batch_configure(L, g_sms)) return fail(VS_ECUDA, "batched scan cannot be resident for d=%d k=%d", s->d, k);
+  std::lock_guard<std::mutex> lk(g_scan_mu);
+  g_batch_cache[key] = L;
+  *out = L;
+  return VS_OK;
+}
+
+static void batch_invalidate(Segment* s) {  // caller holds s->mu and has synchronised the device work
+  for (int m = 0; m < 2; m++) {
+    if (s->ab[m]) cudaFree(s->ab[m]);
+    if (s->stats[m]) cudaFree(s->stats[m]);
+    s->ab[m] = nullptr;
+    s->stats[m] = nullptr;
+    s->nonfinite[m] = 0;
+  }
+}
+
+// Builds (once per segment and metric) the nomination coefficients and the tensor map.  *ok = false when
+// the segment must stay on the per-query scan (non-finite rows, tensor map not encodable).
+static int batch_prepare(cudaStream_t st, Segment* s, bool cosine, bool* ok) {
+  const int m = cosine ? 1 : 0;
+  std::lock_guard<std::mutex> lk(s->mu);
+  *ok = false;
+  if (!s->tm_ok) {
+    if (!batch_encode_segment_map(s->tmX, s->X, s->n, s->d)) return VS_OK;
+    s->tm_ok = true;
+  }
+  if (!s->ab[m]) {
+    void *ab = nullptr, *stv = nullptr;
+    CK(cudaMalloc(&ab, (size_t)s->n * sizeof(float2)), "cudaMalloc(row coefficients)");
+    cudaError_t e = cudaMalloc(&stv, sizeof(SegStats));
+    SegStats hs{};
+    if (e == cudaSuccess) e = launch_row_prep(s->X, s->n, s->d, s->skip, cosine, static_cast<float2*>(ab), static_cast<SegStats*>(stv), g_sms, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&hs, stv, sizeof(SegStats), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+      cudaFree(ab);
+      if (stv) cudaFree(stv);
+      return cuda_fail(e, "row_prep");
+    }
+    s->ab[m] = ab;
+    s->stats[m] = stv;
+    s->nonfinite[m] = hs.nonfinite;
+  }
+  *ok = s->nonfinite[m] == 0;
+  return VS_OK;
+}
+
+// queries per chunk: the group-minima scratch stays within its budget (at least one 128-query block)
+static int batch_chunk(const BatchLaunch& p, int nq) {
+  const int64_t per_q = p.gm_stride * 4;
+  int64_t c = g_batch_gm_bytes.load() / (per_q > 0 ? per_q : 1);
+  c = (c / 128) * 128;
+  if (c < 128) c = 128;
+  return (int)(c < nq ? c : nq);
+}
+static size_t batch_scratch_need(const BatchLaunch& p, int nq) {
+  const int c = batch_chunk(p, nq);
+  const size_t gm = (size_t)((c + 127) / 128 * 128) * p.gm_stride * 4;
+  return Arena::need({gm, (size_t)(1 + 2 * (size_t)c) * 4, (size_t)c * batch_partial_keys(p, c) * 16});
+}
+
+// everything on `st`, no synchronisation; scratch = batch_scratch_need bytes, tickets for one chunk reserved
+static int batch_run_dev(cudaStream_t st, const Segment* s, const BatchLaunch& p, bool cosine, const float* d_q, int nq,
+                         int64_t* d_ids, double* d_scores, int32_t* d_counts, int64_t out_stride, void* scratch,
+                         unsigned long long* d_ticket) {
+  const int m = cosine ? 1 : 0;
+  const int chunk = batch_chunk(p, nq);
+  const int64_t os = out_stride > 0 ? out_stride : p.k;
+  for (int q0 = 0; q0 < nq; q0 += chunk) {
+    const int c = q0 + chunk <= nq ? chunk : nq - q0;
+    Arena A(scratch);
+    BatchLaunch L = p;
+    L.X = s->X; L.skip = s->skip; L.q = d_q + (size_t)q0 * s->d; L.nq = c;
+    L.tmX = s->tmX; L.ab = static_cast<const float2*>(s->ab[m]); L.stats = static_cast<const SegStats*>(s->stats[m]);
+    L.gm = A.take<float>((size_t)((chunk + 127) / 128 * 128) * p.gm_stride);
+    L.fb = A.take<int32_t>(1 + 2 * (size_t)chunk);
+    L.partial_keys = batch_partial_keys(p, c);
+    L.partial = A.take<ulonglong2>((size_t)chunk * batch_partial_keys(p, chunk));
+    L.ctrl = d_ticket;
+    L.ids_out = d_ids + (size_t)q0 * os; L.scores_out = d_scores + (size_t)q0 * os; L.counts_out = d_counts + q0;
+    L.id_base = s->id_base; L.out_stride = os;
+    CK(launch_batch(L, st), "batched scan launch");
+  }
+  return VS_OK;
+}
+
 static int check_query_args(const Segment* s, const void* q, int nq, int k, int metric) {
   if (!s) return fail(VS_EHANDLE, "unknown segment handle");
   if (!q || nq <= 0) return fail(VS_EINVAL, "q must be non-null and nq positive");
@@ -435,6 +550,11 @@ int32_t vs_debug_adc_stats(uint32_t* out8) { return vs::debug_adc_stats(out8) ==
 
 int32_t vs_set_option(const char* name, int64_t value) {
   if (!name) return fail(VS_EINVAL, "null option name");
+  if (!strcmp(name, "batch_min_queries") || !strcmp(name, "batch_min_rows") || !strcmp(name, "batch_gm_bytes")) {
+    if (value < 1) return fail(VS_EINVAL, "%s must be >= 1", name);
+    (name[6] == 'm' && name[10] == 'q' ? g_batch_min_queries : (name[6] == 'm' ? g_batch_min_rows : g_batch_gm_bytes)).store(value);
+    return VS_OK;
+  }
   if (!strcmp(name, "adc_fast_min_rows")) {
     if (value < 0) return fail(VS_EINVAL, "adc_fast_min_rows must be >= 0");
     g_adc_fast_min_rows.store(value);
@@ -577,6 +697,13 @@ static int seg_new(int64_t n, int32_t d, int64_t id_base, Segment** out) {
 }
 
 static int seg_set_skip(ThreadCtx* c, Segment* s, const uint8_t* skip_mask) {
+  {  // the skip mask is folded into the batched path's row coefficients: rebuild them at next use
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (s->ab[0] || s->ab[1]) {
+      CK(cudaDeviceSynchronize(), "sync");
+      batch_invalidate(s);
+    }
+  }
   if (!skip_mask) {
     if (s->skip) {
       CK(cudaStreamSynchronize(c->stream), "sync");
@@ -746,8 +873,50 @@ int32_t vs_bruteforce_topk(uint64_t h, const float* q, int32_t nq, int32_t k, in
     fill_empty(ids_out, scores_out, counts_out, nq, k);
     return VS_OK;
   }
+  const bool cosine = metric == VS_METRIC_COSINE;
+  if (batch_wanted(s, nq, cosine)) {  // tensor-core nomination + exact re-score (batch.cu)
+    bool ok = false;
+    RET(batch_prepare(c->stream, s, cosine, &ok));
+    if (ok) {
+      BatchLaunch bp;
+      RET(plan_batch(s, k, cosine, &bp));
+      int64_t hg = (int64_t(32) << 20) / ((int64_t)s->d * 4);  // queries per host staging group
+      if (hg < 128) hg = 128;
+      if (hg > nq) hg = nq;
+      const int group = (int)hg;
+      const size_t qb = (size_t)group * s->d * 4, ib = (size_t)group * k * 8, cb = (size_t)group * 4;
+      const size_t sb = batch_scratch_need(bp, group);
+      RET(ctx_reserve_dev(c, Arena::need({qb, ib, ib, cb, sb})));
+      RET(ctx_reserve_host(c, Arena::need({qb, ib, ib, cb})));
+      RET(ctx_reserve_ticket(c, batch_chunk(bp, group)));
+      for (int q0 = 0; q0 < nq; q0 += group) {
+        const int g = (q0 + group <= nq) ? group : nq - q0;
+        Arena A(c->d_buf), H(c->h_buf);
+        float* dq = A.take<float>((size_t)group * s->d);
+        int64_t* dids = A.take<int64_t>((size_t)group * k);
+        double* dsc = A.take<double>((size_t)group * k);
+        int32_t* dcn = A.take<int32_t>(group);
+        char* scratch = A.take<char>(sb);
+        float* hq = H.take<float>((size_t)group * s->d);
+        int64_t* hids = H.take<int64_t>((size_t)group * k);
+        double* hsc = H.take<double>((size_t)group * k);
+        int32_t* hcn = H.take<int32_t>(group);
+        memcpy(hq, q + (size_t)q0 * s->d, (size_t)g * s->d * 4);
+        CK(cudaMemcpyAsync(dq, hq, (size_t)g * s->d * 4, cudaMemcpyHostToDevice, c->stream), "H2D q");
+        RET(batch_run_dev(c->stream, s, bp, cosine, dq, g, dids, dsc, dcn, 0, scratch, c->d_ticket));
+        CK(cudaMemcpyAsync(hids, dids, (size_t)g * k * 8, cudaMemcpyDeviceToHost, c->stream), "D2H ids");
+        CK(cudaMemcpyAsync(hsc, dsc, (size_t)g * k * 8, cudaMemcpyDeviceToHost, c->stream), "D2H scores");
+        CK(cudaMemcpyAsync(hcn, dcn, (size_t)g * 4, cudaMemcpyDeviceToHost, c->stream), "D2H counts");
+        CK(cudaStreamSynchronize(c->stream), "sync");
+        memcpy(ids_out + (size_t)q0 * k, hids, (size_t)g * k * 8);
+        memcpy(scores_out + (size_t)q0 * k, hsc, (size_t)g * k * 8);
+        if (counts_out) memcpy(counts_out + q0, hcn, (size_t)g * 4);
+      }
+      return VS_OK;
+    }
+  }
   ScanLaunch p;
-  RET(plan_scan(s, nq, k, metric == VS_METRIC_COSINE, &p));
+  RET(plan_scan(s, nq, k, cosine, &p));
   const size_t per_q_partial = (size_t)p.partial_keys * 16;
   int group = (int)(PARTIAL_BUDGET / per_q_partial);
   if (group < 1) group = 1;
@@ -1026,6 +1195,29 @@ int32_t vs_pq_train(const float* rows, uint64_t h, int64_t n, int32_t d, int32_t
 // Scratch for these comes from the calling thread's context and is only valid until that thread's
 // next libvsgpu call; the caller orders work on `stream` (the multi-GPU coordinator uses one
 // thread and one stream per process).
+// the stream variants' batched route: *done = true when the work was enqueued here
+static int batch_try_dev(ThreadCtx* c, cudaStream_t st, Segment* s, const float* d_q, int nq, int k, int metric,
+                         int64_t* d_ids, double* d_scores, int32_t* d_counts, int64_t out_stride, bool* done) {
+  *done = false;
+  const bool cosine = metric == VS_METRIC_COSINE;
+  if (!batch_wanted(s, nq, cosine)) return VS_OK;
+  bool ok = false;
+  RET(batch_prepare(st, s, cosine, &ok));
+  if (!ok) return VS_OK;
+  BatchLaunch bp;
+  RET(plan_batch(s, k, cosine, &bp));
+  const size_t sb = batch_scratch_need(bp, nq);
+  const int chunk = batch_chunk(bp, nq);
+  const bool grow = Arena::need({sb}) > c->d_cap || (size_t)chunk > c->ticket_cap;
+  RET(ctx_reserve_dev(c, Arena::need({sb})));
+  RET(ctx_reserve_ticket(c, chunk));
+  if (grow) CK(cudaStreamSynchronize(c->stream), "sync");  // ticket memset ran on c->stream
+  Arena A(c->d_buf);
+  RET(batch_run_dev(st, s, bp, cosine, d_q, nq, d_ids, d_scores, d_counts, out_stride, A.take<char>(sb), c->d_ticket));
+  *done = true;
+  return VS_OK;
+}
+
 int32_t vs_bruteforce_topk_dev(uint64_t h, const float* d_q, int32_t nq, int32_t k, int32_t metric,
                                int64_t* d_ids, double* d_scores, int32_t* d_counts, void* stream) {
   Segment* s = seg_lookup(h);
@@ -1034,6 +1226,10 @@ int32_t vs_bruteforce_topk_dev(uint64_t h, const float* d_q, int32_t nq, int32_t
   ThreadCtx* c;
   RET(ctx_bind(&c));
   if (s->n == 0) return fail(VS_EINVAL, "empty segment: use the host variant");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  bool done = false;
+  RET(batch_try_dev(c, st, s, d_q, nq, k, metric, d_ids, d_scores, d_counts, 0, &done));
+  if (done) return VS_OK;
   ScanLaunch p;
   RET(plan_scan(s, nq, k, metric == VS_METRIC_COSINE, &p));
   const size_t pb = (size_t)nq * p.partial_keys * 16;
@@ -1041,7 +1237,6 @@ int32_t vs_bruteforce_topk_dev(uint64_t h, const float* d_q, int32_t nq, int32_t
   const bool grow = Arena::need({pb}) > c->d_cap || (size_t)nq > c->ticket_cap;
   RET(ctx_reserve_dev(c, Arena::need({pb})));
   RET(ctx_reserve_ticket(c, nq));
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   // ticket memset (if any) ran on c->stream: order it before the caller's stream
   if (grow) CK(cudaStreamSynchronize(c->stream), "sync");
   Arena A(c->d_buf);
@@ -1057,6 +1252,10 @@ int32_t vs_bruteforce_topk_packed_dev(uint64_t h, const float* d_q, int32_t nq, 
   ThreadCtx* c;
   RET(ctx_bind(&c));
   if (s->n == 0) return fail(VS_EINVAL, "empty segment: use the host variant");
+  bool done = false;
+  RET(batch_try_dev(c, static_cast<cudaStream_t>(stream), s, d_q, nq, k, metric, d_pack, reinterpret_cast<double*>(d_pack + k),
+                    d_counts, 2 * (int64_t)k, &done));
+  if (done) return VS_OK;
   ScanLaunch p;
   RET(plan_scan(s, nq, k, metric == VS_METRIC_COSINE, &p));
   const size_t pb = (size_t)nq * p.partial_keys * 16;

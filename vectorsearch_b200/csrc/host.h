@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
+
 namespace vs {
 
 // A row range of vectors resident in HBM (+ PQ codebook and codes once sealed).
@@ -16,6 +18,13 @@ struct Segment {
   float* centroids = nullptr;  // [M][K][subDim]
   uint8_t* codes = nullptr;    // [n][M]
   int M = 0, K = 0, subDim = 0;
+  // batched-query nomination state (batch.cu), built at first use per metric under `mu`
+  std::mutex mu;
+  void* ab[2] = {nullptr, nullptr};     // float2[n] per metric
+  void* stats[2] = {nullptr, nullptr};  // SegStats per metric (device)
+  int nonfinite[2] = {0, 0};            // host copy of SegStats::nonfinite
+  bool tm_ok = false;
+  alignas(64) unsigned char tmX[128];   // CUtensorMap over X
 };
 
 int fail(int code, const char* fmt, ...);

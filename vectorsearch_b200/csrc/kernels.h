@@ -42,6 +42,48 @@ bool scan_is_streaming(int d, int lanes, bool cosine);
 bool scan_configure(ScanLaunch& L, int sms);
 cudaError_t launch_scan(const ScanLaunch& L, cudaStream_t st);
 
+// ---- batch.cu: batched-query brute force -- tensor-core nomination + exact re-score ----------------
+struct SegStats {
+  unsigned int xmax2_bits;  // bit pattern of max |x|^2 over live rows
+  int nonfinite;            // a live row has a non-finite (or absurdly large) norm
+};
+// per-row nomination coefficients (alpha, beta) for one metric + SegStats; one pass over the segment
+cudaError_t launch_row_prep(const float* X, int64_t n, int d, const uint8_t* skip, bool cosine, float2* ab,
+                            SegStats* stats, int sms, cudaStream_t st);
+struct BatchLaunch {
+  const float* X;
+  int64_t n;
+  int d;
+  const uint8_t* skip;
+  int lanes;
+  bool cosine;
+  const float* q;        // [nq][d] device
+  int nq;
+  int k, kp;
+  const void* tmX;       // host copy of the segment's CUtensorMap (128 bytes)
+  const float2* ab;      // [n]
+  const SegStats* stats; // device
+  float* gm;             // [round_up(nq, 128)][gm_stride] group minima
+  int32_t* fb;           // [1 + 2 nq]: fallback count, fallback query list, per-query "listed" flags
+  ulonglong2* partial;   // [nq][partial_keys]
+  int64_t partial_keys;
+  unsigned long long* ctrl;  // [nq][4], zero between launches
+  int64_t* ids_out;
+  double* scores_out;
+  int32_t* counts_out;
+  int64_t id_base;
+  int64_t out_stride;
+  // filled by batch_configure:
+  int64_t tiles, ngroups, gm_stride;
+  int cap, sms, fb_gx, fb_threads;
+  size_t gemm_smem, select_smem, fb_smem;
+};
+bool batch_supported(int d, int lanes, bool cosine, int64_t n);
+bool batch_encode_segment_map(void* tm128, const float* X, int64_t n, int d);
+bool batch_configure(BatchLaunch& L, int sms);          // from (n, d, lanes, cosine, k)
+int64_t batch_partial_keys(const BatchLaunch& L, int nq);  // keys of `partial` per query for a chunk of nq
+cudaError_t launch_batch(const BatchLaunch& L, cudaStream_t st);  // one chunk of L.nq queries
+
 // ---- rank.cu: exact scoring + ordering of caller-supplied candidates (re-rank), merge ----------
 struct RankLaunch {
   const float* X;

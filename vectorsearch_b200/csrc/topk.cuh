@@ -261,12 +261,12 @@ __device__ __forceinline__ void topk_write_out(const ulonglong2* outk, int k, co
 // flush + block combine + publish + (last CTA) final merge.  smem holds nw collectors.
 // Both overloads return true in the CTA that ran the final merge (the last one of its query).
 static __device__ __noinline__ bool topk_epilogue(WarpTopK& tk, ulonglong2* smem, int kp, int k,
-                                              const TopkOut& o) {
+                                              const TopkOut& o, int qi_or_neg = -1) {
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int nw = blockDim.x >> 5;
   const int stride_keys = kp + TOPK_BUF;
-  const int qi = blockIdx.y;
+  const int qi = qi_or_neg >= 0 ? qi_or_neg : (int)blockIdx.y;  // query slot of ids / scores / partial / ctrl
   tk.flush(lane);
   block_combine_lists(smem, stride_keys, nw, kp, warp, lane);
   ulonglong2* mine = o.partial + (size_t)qi * o.partial_keys + (size_t)blockIdx.x * k;
@@ -325,12 +325,12 @@ static __device__ __noinline__ bool topk_epilogue(WarpTopK& tk, ulonglong2* smem
 // k-th key, so only keys at or below that bound -- at most k lists x k keys -- are gathered and
 // rank-selected; nothing is sorted and nothing scales with grid x k beyond two coalesced reads.
 static __device__ __noinline__ bool topk_epilogue(WarpTopKReg& tk, ulonglong2* smem, int kp, int k,
-                                              const TopkOut& o) {
+                                              const TopkOut& o, int qi_or_neg = -1) {
   (void)kp;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int nw = blockDim.x >> 5;
-  const int qi = blockIdx.y;
+  const int qi = qi_or_neg >= 0 ? qi_or_neg : (int)blockIdx.y;  // query slot of ids / scores / partial / ctrl
   unsigned long long* ctrl = o.ctrl + 4 * qi;
   ulonglong2* keys = smem;            // [nw * k]
   ulonglong2* outk = smem + nw * k;   // [k]
