@@ -155,14 +155,17 @@ def test_bruteforce_query_batch(vs, oracle):
 
 
 # ---- batched queries: tensor-core nomination + exact re-score (batch.cu) ----------------------------------
-@pytest.fixture
-def force_batch(vs):
-    """Route every query batch of >= 2 queries through batch.cu, whatever the segment size."""
+@pytest.fixture(params=["fp16", "tf32"])
+def force_batch(vs, request):
+    """Route every query batch of >= 2 queries through batch.cu, whatever the segment size, nominating
+    on the fp16 operand copies (default) or on the fp32 rows read as tf32."""
     vs.set_option("batch_min_queries", 2)
     vs.set_option("batch_min_rows", 1)
+    vs.set_option("batch_fp16", 1 if request.param == "fp16" else 0)
     yield
     vs.set_option("batch_min_queries", 3)
     vs.set_option("batch_min_rows", 16384)
+    vs.set_option("batch_fp16", 1)
 
 
 def _check_batch(vs, oracle, rows, qs, k, metric, skip=None, id_base=0, threads=4):

@@ -10,6 +10,9 @@ from vectorsearch_b200 import _lib as L
 
 vs.init(0)
 lib = vs.load()
+import os
+if os.environ.get("VS_TF32"):
+    vs.set_option("batch_fp16", 0)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
 d = int(sys.argv[2]) if len(sys.argv) > 2 else 128
 k = int(sys.argv[3]) if len(sys.argv) > 3 else 10

@@ -27,6 +27,7 @@ static std::atomic<int64_t> g_adc_fast_cap{4096};         // candidate-list entr
 static std::atomic<int64_t> g_batch_min_queries{3};        // query batches at least this large use batch.cu
 static std::atomic<int64_t> g_batch_min_rows{16384};       // ... on segments at least this long
 static std::atomic<int64_t> g_batch_gm_bytes{int64_t(1) << 30};  // group-minima scratch per query chunk
+static std::atomic<int64_t> g_batch_fp16{1};                // nominate on fp16 operand copies (0: the fp32 rows as tf32)
 static int g_sms = 0;
 static std::mutex g_mu;
 static std::unordered_map<uint64_t, Segment*> g_segments;
@@ -191,6 +192,7 @@ static void seg_destroy(Segment* s) {
     if (s->ab[m]) cudaFree(s->ab[m]);
     if (s->stats[m]) cudaFree(s->stats[m]);
   }
+  if (s->Xh) cudaFree(s->Xh);
   delete s;
 }
 
@@ -373,9 +375,9 @@ static bool batch_wanted(const Segment* s, int nq, bool cosine) {
          batch_supported(s->d, lanes(), cosine, s->n);
 }
 
-static int plan_batch(const Segment* s, int k, bool cosine, BatchLaunch* out) {
+static int plan_batch(const Segment* s, int k, bool cosine, bool half, BatchLaunch* out) {
   const int ln = lanes();
-  const uint64_t key = occ_key(cosine ? 31 : 30, s->d, ln, k, 0, (size_t)s->n);
+  const uint64_t key = occ_key(cosine ? 31 : 30, s->d, ln, k, half ? 1 : 0, (size_t)s->n);
   {
     std::lock_guard<std::mutex> lk(g_scan_mu);
     auto it = g_batch_cache.find(key);
@@ -385,7 +387,7 @@ static int plan_batch(const Segment* s, int k, bool cosine, BatchLaunch* out) {
     }
   }
   BatchLaunch L{};
-  L.n = s->n; L.d = s->d; L.lanes = ln; L.cosine = cosine; L.k = k;
+  L.n = s->n; L.d = s->d; L.lanes = ln; L.cosine = cosine; L.k = k; L.half = half; L.dp = (s->d + 7) & ~7;
   if (!batch_configure(L, g_sms)) return fail(VS_ECUDA, "batched scan cannot be resident for d=%d k=%d", s->d, k);
   std::lock_guard<std::mutex> lk(g_scan_mu);
   g_batch_cache[key] = L;
@@ -394,6 +396,7 @@ static int plan_batch(const Segment* s, int k, bool cosine, BatchLaunch* out) {
 }
 
 static void batch_invalidate(Segment* s) {  // caller holds s->mu and has synchronised the device work
+  // (the fp16 copy does not depend on the skip mask and stays)
   for (int m = 0; m < 2; m++) {
     if (s->ab[m]) cudaFree(s->ab[m]);
     if (s->stats[m]) cudaFree(s->stats[m]);
@@ -405,20 +408,21 @@ static void batch_invalidate(Segment* s) {  // caller holds s->mu and has synchr
 
 // Builds (once per segment and metric) the nomination coefficients and the tensor map.  *ok = false when
 // the segment must stay on the per-query scan (non-finite rows, tensor map not encodable).
-static int batch_prepare(cudaStream_t st, Segment* s, bool cosine, bool* ok) {
+static int batch_prepare(cudaStream_t st, Segment* s, bool cosine, bool* ok, bool* half) {
   const int m = cosine ? 1 : 0;
   std::lock_guard<std::mutex> lk(s->mu);
   *ok = false;
+  *half = false;
   if (!s->tm_ok) {
-    if (!batch_encode_segment_map(s->tmX, s->X, s->n, s->d)) return VS_OK;
+    if (!batch_encode_segment_map(s->tmX, s->X, s->n, s->d, s->d, false)) return VS_OK;
     s->tm_ok = true;
   }
   if (!s->ab[m]) {
     void *ab = nullptr, *stv = nullptr;
-    CK(cudaMalloc(&ab, (size_t)s->n * sizeof(float2)), "cudaMalloc(row coefficients)");
+    CK(cudaMalloc(&ab, (size_t)s->n * sizeof(float)), "cudaMalloc(row coefficients)");
     cudaError_t e = cudaMalloc(&stv, sizeof(SegStats));
     SegStats hs{};
-    if (e == cudaSuccess) e = launch_row_prep(s->X, s->n, s->d, s->skip, cosine, static_cast<float2*>(ab), static_cast<SegStats*>(stv), g_sms, st);
+    if (e == cudaSuccess) e = launch_row_prep(s->X, s->n, s->d, s->skip, cosine, static_cast<float*>(ab), static_cast<SegStats*>(stv), g_sms, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(&hs, stv, sizeof(SegStats), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) {
@@ -429,8 +433,35 @@ static int batch_prepare(cudaStream_t st, Segment* s, bool cosine, bool* ok) {
     s->ab[m] = ab;
     s->stats[m] = stv;
     s->nonfinite[m] = hs.nonfinite;
+    s->xmax2 = hs.xmax2_bits;
   }
   *ok = s->nonfinite[m] == 0;
+  if (*ok && !s->xh_tried && g_batch_fp16.load() != 0) {
+    // optional fp16 operand copy (n * dp * 2 bytes): twice the tensor rate at half the L2 traffic
+    s->xh_tried = true;
+    float xmax2;
+    memcpy(&xmax2, &s->xmax2, 4);
+    int e2 = 0;
+    if (xmax2 > 0.0f) frexpf(sqrtf(xmax2) * 1.0001f, &e2);  // max |x| < 2^e2
+    const float sx = xmax2 > 0.0f ? ldexpf(1.0f, 14 - e2) : 1.0f;
+    const int dp = (s->d + 7) & ~7;
+    void* xh = nullptr;
+    if (cudaMalloc(&xh, (size_t)s->n * dp * 2) != cudaSuccess) {
+      cudaGetLastError();  // not enough memory for the copy: stay on tf32 operands
+    } else {
+      cudaError_t e = launch_row_convert(s->X, s->n, s->d, dp, sx, xh, g_sms, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess || !batch_encode_segment_map(s->tmXh, xh, s->n, s->d, dp, true)) {
+        cudaFree(xh);
+        if (e != cudaSuccess) return cuda_fail(e, "row_convert");
+      } else {
+        s->Xh = xh;
+        s->dp = dp;
+        s->x_scale = sx;
+      }
+    }
+  }
+  *half = s->Xh != nullptr && g_batch_fp16.load() != 0;
   return VS_OK;
 }
 
@@ -444,8 +475,10 @@ static int batch_chunk(const BatchLaunch& p, int nq) {
 }
 static size_t batch_scratch_need(const BatchLaunch& p, int nq) {
   const int c = batch_chunk(p, nq);
-  const size_t gm = (size_t)((c + 127) / 128 * 128) * p.gm_stride * 4;
-  return Arena::need({gm, (size_t)(1 + 2 * (size_t)c) * 4, (size_t)c * batch_partial_keys(p, c) * 16});
+  const size_t cp = (size_t)((c + 127) / 128 * 128);
+  const size_t gm = cp * p.gm_stride * 4;
+  return Arena::need({gm, (size_t)(1 + 2 * (size_t)c) * 4, (size_t)c * batch_partial_keys(p, c) * 16,
+                      p.half ? (size_t)c * p.dp * 2 : 0, p.half ? cp * 4 : 0});
 }
 
 // everything on `st`, no synchronisation; scratch = batch_scratch_need bytes, tickets for one chunk reserved
@@ -460,11 +493,14 @@ static int batch_run_dev(cudaStream_t st, const Segment* s, const BatchLaunch& p
     Arena A(scratch);
     BatchLaunch L = p;
     L.X = s->X; L.skip = s->skip; L.q = d_q + (size_t)q0 * s->d; L.nq = c;
-    L.tmX = s->tmX; L.ab = static_cast<const float2*>(s->ab[m]); L.stats = static_cast<const SegStats*>(s->stats[m]);
+    L.tmX = p.half ? s->tmXh : s->tmX; L.x_scale = s->x_scale;
+    L.coef = static_cast<const float*>(s->ab[m]); L.stats = static_cast<const SegStats*>(s->stats[m]);
     L.gm = A.take<float>((size_t)((chunk + 127) / 128 * 128) * p.gm_stride);
     L.fb = A.take<int32_t>(1 + 2 * (size_t)chunk);
     L.partial_keys = batch_partial_keys(p, c);
     L.partial = A.take<ulonglong2>((size_t)chunk * batch_partial_keys(p, chunk));
+    L.qh = p.half ? A.take<char>((size_t)chunk * p.dp * 2) : nullptr;
+    L.qinv = p.half ? A.take<float>((size_t)((chunk + 127) / 128 * 128)) : nullptr;
     L.ctrl = d_ticket;
     L.ids_out = d_ids + (size_t)q0 * os; L.scores_out = d_scores + (size_t)q0 * os; L.counts_out = d_counts + q0;
     L.id_base = s->id_base; L.out_stride = os;
@@ -550,6 +586,10 @@ int32_t vs_debug_adc_stats(uint32_t* out8) { return vs::debug_adc_stats(out8) ==
 
 int32_t vs_set_option(const char* name, int64_t value) {
   if (!name) return fail(VS_EINVAL, "null option name");
+  if (!strcmp(name, "batch_fp16")) {  // applies to segments that have not been queried in batches yet
+    g_batch_fp16.store(value != 0);
+    return VS_OK;
+  }
   if (!strcmp(name, "batch_min_queries") || !strcmp(name, "batch_min_rows") || !strcmp(name, "batch_gm_bytes")) {
     if (value < 1) return fail(VS_EINVAL, "%s must be >= 1", name);
     (name[6] == 'm' && name[10] == 'q' ? g_batch_min_queries : (name[6] == 'm' ? g_batch_min_rows : g_batch_gm_bytes)).store(value);
@@ -875,11 +915,11 @@ int32_t vs_bruteforce_topk(uint64_t h, const float* q, int32_t nq, int32_t k, in
   }
   const bool cosine = metric == VS_METRIC_COSINE;
   if (batch_wanted(s, nq, cosine)) {  // tensor-core nomination + exact re-score (batch.cu)
-    bool ok = false;
-    RET(batch_prepare(c->stream, s, cosine, &ok));
+    bool ok = false, half = false;
+    RET(batch_prepare(c->stream, s, cosine, &ok, &half));
     if (ok) {
       BatchLaunch bp;
-      RET(plan_batch(s, k, cosine, &bp));
+      RET(plan_batch(s, k, cosine, half, &bp));
       int64_t hg = (int64_t(32) << 20) / ((int64_t)s->d * 4);  // queries per host staging group
       if (hg < 128) hg = 128;
       if (hg > nq) hg = nq;
@@ -1201,11 +1241,11 @@ static int batch_try_dev(ThreadCtx* c, cudaStream_t st, Segment* s, const float*
   *done = false;
   const bool cosine = metric == VS_METRIC_COSINE;
   if (!batch_wanted(s, nq, cosine)) return VS_OK;
-  bool ok = false;
-  RET(batch_prepare(st, s, cosine, &ok));
+  bool ok = false, half = false;
+  RET(batch_prepare(st, s, cosine, &ok, &half));
   if (!ok) return VS_OK;
   BatchLaunch bp;
-  RET(plan_batch(s, k, cosine, &bp));
+  RET(plan_batch(s, k, cosine, half, &bp));
   const size_t sb = batch_scratch_need(bp, nq);
   const int chunk = batch_chunk(bp, nq);
   const bool grow = Arena::need({sb}) > c->d_cap || (size_t)chunk > c->ticket_cap;

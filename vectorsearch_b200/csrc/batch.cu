@@ -6,9 +6,9 @@
 // queries would stream it nq times, so here the segment is read once per 128 queries and the
 // dense part -- the nq x n inner products -- runs on the 5th-generation tensor cores:
 //
-//   (1) row_prep_kernel   one pass at first use: per row (alpha, beta) so that
-//                         a(q, x) = alpha + beta * <q, x>  orders rows like the metric does
-//                         (L2: |x|^2 - 2<q,x>;  cosine: -<q,x>/|x|), plus max |x|^2.
+//   (1) row_prep_kernel   one pass at first use: one coefficient c per row so that a(q, x) orders rows like
+//                         the metric does (L2: c = |x|^2, a = c - 2<q,x>;  cosine: c = -1/|x|, a = c<q,x>),
+//                         plus max |x|^2; row_convert_kernel makes the optional fp16 operand copy.
 //   (2) batch_gemm_kernel persistent, warp-specialised tcgen05 kernel: TMA (128-byte swizzle) stages
 //                         a 128-query x 32-float block of Q and a 256-row x 32-float block of X per
 //                         pipeline stage, one thread issues tcgen05.mma.kind::tf32 (fp32 bits read
@@ -27,6 +27,7 @@
 //                         Segments holding non-finite rows never enter this path (api.cu).
 // Tensor cores only nominate; they never produce a returned value.
 #include <cuda.h>  // CUtensorMap and enums only; the encoder is resolved through the runtime (no libcuda link)
+#include <cuda_fp16.h>
 
 #include <mutex>
 
@@ -37,16 +38,16 @@ namespace vs {
 
 constexpr int BQ_M = 128;       // queries per tile = TMEM lanes
 constexpr int BQ_N = 256;       // rows per tile = TMEM columns of one accumulator
-constexpr int BQ_KB = 32;       // floats per k-block: one 128-byte swizzle atom
-constexpr int BQ_STAGES = 4;
-constexpr int BQ_THREADS = 256;
+constexpr int BQ_THREADS = 384;     // warp 0 TMA, warp 1 MMA, warp 2 TMEM allocator, warps 4..11 epilogue
+constexpr int BQ_EPI_WARPS = 8;
 constexpr uint32_t BQ_A_BYTES = BQ_M * 128;
 constexpr uint32_t BQ_B_BYTES = BQ_N * 128;
 constexpr uint32_t BQ_STAGE_BYTES = BQ_A_BYTES + BQ_B_BYTES;
-constexpr uint32_t BQ_AB_BYTES = 4 * 2 * BQ_N * 8;  // (alpha, beta) of the tile's rows: per epilogue warp, per accumulator
-constexpr size_t BQ_GEMM_SMEM = 1024 + (size_t)BQ_STAGES * BQ_STAGE_BYTES + BQ_AB_BYTES + 256;
+constexpr uint32_t BQ_AB_BYTES = BQ_EPI_WARPS * 2 * (BQ_N / 2) * 4;  // row coefficients of the warp's 128 columns, per accumulator
+constexpr size_t BQ_GEMM_SMEM_BUDGET = 224 * 1024;  // dynamic shared memory of the nomination kernel
 constexpr int BQ_SELECT_THREADS = 256;
 constexpr int BQ_FB_SLOTS = 8;  // grid.y of the fallback scan
+constexpr int BQ_TMIN_MAX_K = 64;  // up to this k the select threshold comes from per-thread minima
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -67,6 +68,12 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uin
   asm volatile(
       "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
 // 32 lanes x 32 consecutive columns: thread t of the warp receives lane (base + t), columns c..c+31
@@ -102,14 +109,15 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   d |= (uint64_t)2 << 61;            // SWIZZLE_128B
   return d;
 }
-// instruction descriptor: D fp32, A and B tf32, both K-major, N = 256, M = 128
-constexpr uint32_t BQ_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BQ_N >> 3) << 17) | ((uint32_t)(BQ_M >> 4) << 24);
+// instruction descriptors: D fp32, both operands K-major, N = 256, M = 128; A/B format 2 = tf32, 0 = fp16
+constexpr uint32_t BQ_IDESC_TF32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BQ_N >> 3) << 17) | ((uint32_t)(BQ_M >> 4) << 24);
+constexpr uint32_t BQ_IDESC_F16 = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BQ_N >> 3) << 17) | ((uint32_t)(BQ_M >> 4) << 24);
 
 // ---- (1) per-row nomination coefficients --------------------------------------------------------------------
 template <bool COSINE>
 __global__ void __launch_bounds__(256)
 row_prep_kernel(const float* __restrict__ X, int64_t n, int d, const uint8_t* __restrict__ skip,
-                float2* __restrict__ ab, SegStats* __restrict__ stats) {
+                float* __restrict__ coef, SegStats* __restrict__ stats) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -130,16 +138,18 @@ row_prep_kernel(const float* __restrict__ X, int64_t n, int d, const uint8_t* __
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(FULL_MASK, ss, o);
     if (lane == 0) {
       const float inf = __int_as_float(0x7f800000);
-      float2 v;
+      float v;
+      // the maximum covers skipped rows too: it also fixes the scale of the fp16 operand copy, which outlives
+      // a change of the skip mask
+      if (ss < 1e30f) vmax = max(vmax, __float_as_uint(ss));
       if (skip != nullptr && skip[r]) {
-        v = make_float2(inf, 0.0f);  // never nominated
+        v = COSINE ? __int_as_float(0x7fc00000) : inf;  // never nominated (fminf drops NaN)
       } else {
         if (!(ss < 1e30f)) bad = 1;  // NaN, inf or out of the range the slack bound was derived for
-        else vmax = max(vmax, __float_as_uint(ss));
-        if (COSINE) v = make_float2(0.0f, ss > 0.0f ? -(1.0f / sqrtf(ss)) : 0.0f);
-        else v = make_float2(ss, -2.0f);
+        if (COSINE) v = ss > 0.0f ? -(1.0f / sqrtf(ss)) : 0.0f;
+        else v = ss;
       }
-      ab[r] = v;
+      coef[r] = v;
     }
   }
   if (lane == 0) {
@@ -148,35 +158,102 @@ row_prep_kernel(const float* __restrict__ X, int64_t n, int d, const uint8_t* __
   }
 }
 
-cudaError_t launch_row_prep(const float* X, int64_t n, int d, const uint8_t* skip, bool cosine, float2* ab,
+cudaError_t launch_row_prep(const float* X, int64_t n, int d, const uint8_t* skip, bool cosine, float* coef,
                             SegStats* stats, int sms, cudaStream_t st) {
   cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(SegStats), st);
   if (e != cudaSuccess) return e;
   int64_t grid = (n + 7) / 8;
   if (grid > (int64_t)sms * 8) grid = (int64_t)sms * 8;
   count_launch();
-  if (cosine) row_prep_kernel<true><<<(int)grid, 256, 0, st>>>(X, n, d, skip, ab, stats);
-  else row_prep_kernel<false><<<(int)grid, 256, 0, st>>>(X, n, d, skip, ab, stats);
+  if (cosine) row_prep_kernel<true><<<(int)grid, 256, 0, st>>>(X, n, d, skip, coef, stats);
+  else row_prep_kernel<false><<<(int)grid, 256, 0, st>>>(X, n, d, skip, coef, stats);
   return cudaGetLastError();
+}
+
+// fp16 operand copy of the rows: Xh[r][c] = half(x[r][c] * sx), sx a power of two chosen so that no element
+// overflows (|x| * sx <= 2^14); row pitch dp = d rounded up to 8, padding zero.  Nomination only.
+__global__ void __launch_bounds__(256)
+row_convert_kernel(const float* __restrict__ X, int64_t n, int d, int dp, float sx, __half* __restrict__ Xh) {
+  const int cpr = dp >> 2;  // 4-element chunks per row
+  const int64_t total = n * cpr;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cpr;
+    const int c = (int)(i - r * cpr) * 4;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < d) x = ld_stream_f4(reinterpret_cast<const float4*>(X + (size_t)r * d + c));
+    const __half2 lo = __floats2half2_rn(x.x * sx, x.y * sx), hi = __floats2half2_rn(x.z * sx, x.w * sx);
+    uint2 o;
+    o.x = *reinterpret_cast<const unsigned int*>(&lo);
+    o.y = *reinterpret_cast<const unsigned int*>(&hi);
+    *reinterpret_cast<uint2*>(Xh + (size_t)r * dp + c) = o;
+  }
+}
+cudaError_t launch_row_convert(const float* X, int64_t n, int d, int dp, float sx, void* Xh, int sms, cudaStream_t st) {
+  int64_t grid = (n * (dp >> 2) + 255) / 256;
+  if (grid > (int64_t)sms * 16) grid = (int64_t)sms * 16;
+  count_launch();
+  row_convert_kernel<<<(int)(grid < 1 ? 1 : grid), 256, 0, st>>>(X, n, d, dp, sx, static_cast<__half*>(Xh));
+  return cudaGetLastError();
+}
+
+// Queries: Qh[q][c] = half(q[c] * sq) with a per-query power of two sq (|q| * sq <= 2^14), and
+// qinv[q] = 1 / (sx * sq), the factor that brings the accumulator back to <q, x>.  One warp per query.
+__global__ void __launch_bounds__(256)
+query_convert_kernel(const float* __restrict__ Q, int nq, int nq_pad, int d, int dp, float sx, __half* __restrict__ Qh,
+                     float* __restrict__ qinv) {
+  const int lane = threadIdx.x & 31;
+  const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (qi >= nq_pad) return;
+  if (qi >= nq) {
+    if (lane == 0) qinv[qi] = 0.0f;
+    return;
+  }
+  const float* q = Q + (size_t)qi * d;
+  float ss = 0.0f;
+  for (int i = lane; i < d; i += 32) ss = fmaf(q[i], q[i], ss);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(FULL_MASK, ss, o);
+  float sq = 1.0f;
+  if (ss > 0.0f && ss < 1e30f) {
+    int e;
+    frexpf(sqrtf(ss) * 1.0001f, &e);  // |q| < 2^e
+    sq = ldexpf(1.0f, 14 - e);
+  }
+  for (int i = lane; i < dp; i += 32) Qh[(size_t)qi * dp + i] = __float2half_rn(i < d ? q[i] * sq : 0.0f);
+  if (lane == 0) qinv[qi] = 1.0f / (sx * sq);
 }
 
 // ---- (2) tensor-core nomination ---------------------------------------------------------------------------------
 // grid.x = nqb * nsplit; CTA (qb, split) owns query block qb and row tiles split, split + nsplit, ...
 // (CTAs of the same split run side by side, so a row tile is fetched from HBM once and re-read from L2).
+// STAT: the CTA's 128-query block (num_kb k-blocks of 16 KB) is loaded once and stays in shared memory, the
+// pipeline stages carry row blocks only -- a third less L2 -> SM traffic, which is what bounds this kernel
+// at d = 128.  Otherwise (long vectors) every stage carries the k-block of both operands.
+constexpr int BQ_MAX_STAGES = 8;
+// HALF: operands are the fp16 copies (k-block = 64 halfs, kind::f16, twice the tensor rate and half the bytes);
+// qinv[query] undoes the power-of-two scaling of both copies.  Otherwise the fp32 data itself, read as tf32.
+template <bool STAT, bool HALF, bool COSINE>
 __global__ void __launch_bounds__(BQ_THREADS, 1)
 batch_gemm_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmX,
-                  const float2* __restrict__ ab, int64_t n, int num_kb, int nqb, int64_t tiles,
-                  float* __restrict__ gm, int64_t gm_stride) {
-  extern __shared__ uint8_t bq_smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(bq_smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* stages = base;
-  float2* sm_ab = reinterpret_cast<float2*>(base + (size_t)BQ_STAGES * BQ_STAGE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sm_ab) + BQ_AB_BYTES);
-  uint64_t* full = bars;                      // [BQ_STAGES] TMA -> MMA
-  uint64_t* empty = bars + BQ_STAGES;         // [BQ_STAGES] MMA -> TMA
-  uint64_t* tfull = bars + 2 * BQ_STAGES;     // [2] MMA -> epilogue
-  uint64_t* tempty = bars + 2 * BQ_STAGES + 2;  // [2] epilogue -> MMA
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * BQ_STAGES + 4);
+                  const float* __restrict__ coef, const float* __restrict__ qinv, int64_t n, int num_kb, int nstages,
+                  int nqb, int64_t tiles, float* __restrict__ gm, int64_t gm_stride) {
+  // the swizzled operand tiles need 1024-byte alignment; no integer round-trip on the pointer, so every access
+  // below stays a shared-memory instruction (LDS / STS) instead of a generic one
+  extern __shared__ __align__(1024) uint8_t bq_smem[];
+  uint8_t* base = bq_smem;
+  if ((smem_u32(base) & 1023u) != 0) __trap();
+  constexpr uint32_t STAGE_BYTES = STAT ? BQ_B_BYTES : BQ_STAGE_BYTES;
+  constexpr int KB_ELEMS = HALF ? 64 : 32;  // elements per 128-byte k-block
+  uint8_t* aq = base;                                                    // STAT: [num_kb][16 KB] query block
+  uint8_t* stages = base + (STAT ? (size_t)num_kb * BQ_A_BYTES : 0);
+  float* sm_coef = reinterpret_cast<float*>(stages + (size_t)nstages * STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sm_coef) + BQ_AB_BYTES);
+  uint64_t* full = bars;                          // [BQ_MAX_STAGES] TMA -> MMA
+  uint64_t* empty = bars + BQ_MAX_STAGES;         // [BQ_MAX_STAGES] MMA -> TMA
+  uint64_t* tfull = bars + 2 * BQ_MAX_STAGES;     // [2] MMA -> epilogue
+  uint64_t* tempty = bars + 2 * BQ_MAX_STAGES + 2;  // [2] epilogue -> MMA
+  uint64_t* afull = bars + 2 * BQ_MAX_STAGES + 4;   // [1] resident query block has landed
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * BQ_MAX_STAGES + 5);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -187,14 +264,15 @@ batch_gemm_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmQ)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmX)) : "memory");
-    for (int s = 0; s < BQ_STAGES; s++) {
+    for (int s = 0; s < nstages; s++) {
       mbar_init(full + s, 1);
       mbar_init(empty + s, 1);
     }
     for (int a = 0; a < 2; a++) {
       mbar_init(tfull + a, 1);
-      mbar_init(tempty + a, 4);
+      mbar_init(tempty + a, BQ_EPI_WARPS);
     }
+    mbar_init(afull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -208,16 +286,20 @@ batch_gemm_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 
   if (warp == 0) {
     if (lane == 0) {  // ===== TMA producer =====
+      if (STAT) {
+        mbar_expect_tx(afull, (uint32_t)num_kb * BQ_A_BYTES);
+        for (int kb = 0; kb < num_kb; kb++) tma_load_2d(aq + (size_t)kb * BQ_A_BYTES, &tmQ, kb * KB_ELEMS, qb * BQ_M, afull);
+      }
       int s = 0;
       uint32_t ph = 0;
       for (int64_t tile = split; tile < tiles; tile += nsplit) {
         for (int kb = 0; kb < num_kb; kb++) {
           mbar_wait(empty + s, ph ^ 1);
-          mbar_expect_tx(full + s, BQ_STAGE_BYTES);
-          uint8_t* st = stages + (size_t)s * BQ_STAGE_BYTES;
-          tma_load_2d(st, &tmQ, kb * BQ_KB, qb * BQ_M, full + s);
-          tma_load_2d(st + BQ_A_BYTES, &tmX, kb * BQ_KB, (int)(tile * BQ_N), full + s);
-          if (++s == BQ_STAGES) {
+          mbar_expect_tx(full + s, STAGE_BYTES);
+          uint8_t* st = stages + (size_t)s * STAGE_BYTES;
+          if (!STAT) tma_load_2d(st, &tmQ, kb * KB_ELEMS, qb * BQ_M, full + s);
+          tma_load_2d(st + (STAT ? 0 : BQ_A_BYTES), &tmX, kb * KB_ELEMS, (int)(tile * BQ_N), full + s);
+          if (++s == nstages) {
             s = 0;
             ph ^= 1;
           }
@@ -228,6 +310,7 @@ batch_gemm_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     if (lane == 0) {  // ===== MMA issuer =====
       int s = 0, it = 0;
       uint32_t ph = 0;
+      if (STAT) mbar_wait(afull, 0);
       for (int64_t tile = split; tile < tiles; tile += nsplit, it++) {
         const int a = it & 1;
         mbar_wait(tempty + a, ((it >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
@@ -236,13 +319,16 @@ batch_gemm_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         for (int kb = 0; kb < num_kb; kb++) {
           mbar_wait(full + s, ph);
           tc_fence_after();
-          const uint32_t sa = smem_u32(stages + (size_t)s * BQ_STAGE_BYTES);
-          const uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sa + BQ_A_BYTES);
+          const uint32_t sb = smem_u32(stages + (size_t)s * STAGE_BYTES) + (STAT ? 0u : BQ_A_BYTES);
+          const uint32_t sa = STAT ? smem_u32(aq + (size_t)kb * BQ_A_BYTES) : smem_u32(stages + (size_t)s * STAGE_BYTES);
+          const uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sb);
 #pragma unroll
-          for (int kk = 0; kk < BQ_KB / 8; kk++)  // 8 tf32 = 32 bytes per instruction: +2 in descriptor units
-            tc_mma_tf32(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, BQ_IDESC, (kb | kk) != 0 ? 1u : 0u);
+          for (int kk = 0; kk < 4; kk++) {  // 8 tf32 / 16 fp16 = 32 bytes per instruction: +2 in descriptor units
+            if (HALF) tc_mma_f16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, BQ_IDESC_F16, (kb | kk) != 0 ? 1u : 0u);
+            else tc_mma_tf32(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, BQ_IDESC_TF32, (kb | kk) != 0 ? 1u : 0u);
+          }
           tc_commit(empty + s);  // frees the stage once these MMAs have read it
-          if (++s == BQ_STAGES) {
+          if (++s == nstages) {
             s = 0;
             ph ^= 1;
           }
@@ -251,44 +337,72 @@ batch_gemm_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       }
     }
   } else if (warp >= 4) {  // ===== epilogue: TMEM -> per-group minima =====
-    const int ew = warp - 4;  // TMEM lane quarter this warp may read
+    const int ew = warp - 4;
+    const int lq = ew & 3;    // TMEM lane quarter this warp may read (= warp % 4)
+    const int ch = ew >> 2;   // which 128 of the tile's 256 columns
     const float inf = __int_as_float(0x7f800000);
+    const float qs = HALF ? qinv[qb * BQ_M + lq * 32 + lane] : 1.0f;  // exact power of two, > 0
+    const float m2 = -2.0f * qs;
+    const float dead = COSINE ? __int_as_float(0x7fc00000) : inf;
+    // the warp's 128 coefficients of the NEXT tile travel in registers while this tile is reduced
+    float cnext[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int64_t r = (int64_t)split * BQ_N + ch * (BQ_N / 2) + i * 32 + lane;
+      cnext[i] = (split < tiles && r < n) ? __ldg(coef + r) : dead;
+    }
     int it = 0;
     for (int64_t tile = split; tile < tiles; tile += nsplit, it++) {
       const int a = it & 1;
-      float2* myab = sm_ab + (size_t)(ew * 2 + a) * BQ_N;
-      for (int i = lane; i < BQ_N; i += 32) {
-        const int64_t r = tile * BQ_N + i;
-        myab[i] = r < n ? __ldg(ab + r) : make_float2(inf, 0.0f);
-      }
+      float* myc = sm_coef + (size_t)(ew * 2 + a) * (BQ_N / 2);
+#pragma unroll
+      for (int i = 0; i < 4; i++) myc[i * 32 + lane] = cnext[i];
       __syncwarp();
+      {
+        const int64_t nt = tile + nsplit;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const int64_t r = nt * BQ_N + ch * (BQ_N / 2) + i * 32 + lane;
+          cnext[i] = (nt < tiles && r < n) ? __ldg(coef + r) : dead;
+        }
+      }
       mbar_wait(tfull + a, (it >> 1) & 1);
       tc_fence_after();
-      float mins[4];
+      float mins[2];
 #pragma unroll
-      for (int g = 0; g < 4; g++) {
-        uint32_t v[64];
-        const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(a * BQ_N + g * 64);
-        tc_ld32(taddr, v);
-        tc_ld32(taddr + 32, v + 32);
-        tc_wait_ld();
-        tc_pin32(v);
-        tc_pin32(v + 32);
-        const float4* p4 = reinterpret_cast<const float4*>(myab + g * 64);
+      for (int g = 0; g < 2; g++) {
         float m0 = inf, m1 = inf;
 #pragma unroll
-        for (int j = 0; j < 32; j++) {
-          const float4 p = p4[j];  // (alpha, beta) of two rows; same address in every lane: broadcast
-          m0 = fminf(m0, fmaf(__uint_as_float(v[2 * j]), p.y, p.x));
-          m1 = fminf(m1, fmaf(__uint_as_float(v[2 * j + 1]), p.w, p.z));
+        for (int h = 0; h < 2; h++) {
+          uint32_t v[32];
+          tc_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(a * BQ_N + ch * (BQ_N / 2) + g * 64 + h * 32), v);
+          tc_wait_ld();
+          tc_pin32(v);
+          const float4* p4 = reinterpret_cast<const float4*>(myc + g * 64 + h * 32);
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            const float4 p = p4[j];  // coefficients of four rows; same address in every lane: broadcast
+            if (COSINE) {            // a = c <q,x>; the per-query scale is applied after the minimum
+              m0 = fminf(m0, __uint_as_float(v[4 * j]) * p.x);
+              m1 = fminf(m1, __uint_as_float(v[4 * j + 1]) * p.y);
+              m0 = fminf(m0, __uint_as_float(v[4 * j + 2]) * p.z);
+              m1 = fminf(m1, __uint_as_float(v[4 * j + 3]) * p.w);
+            } else {                 // a = c - 2 <q,x>
+              m0 = fminf(m0, fmaf(__uint_as_float(v[4 * j]), m2, p.x));
+              m1 = fminf(m1, fmaf(__uint_as_float(v[4 * j + 1]), m2, p.y));
+              m0 = fminf(m0, fmaf(__uint_as_float(v[4 * j + 2]), m2, p.z));
+              m1 = fminf(m1, fmaf(__uint_as_float(v[4 * j + 3]), m2, p.w));
+            }
+          }
         }
         mins[g] = fminf(m0, m1);
+        if (COSINE) mins[g] *= qs;
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty + a);
-      float4* dst = reinterpret_cast<float4*>(gm + (size_t)(qb * BQ_M + ew * 32 + lane) * gm_stride + tile * 4);
-      *dst = make_float4(mins[0], mins[1], mins[2], mins[3]);
+      float2* dst = reinterpret_cast<float2*>(gm + (size_t)(qb * BQ_M + lq * 32 + lane) * gm_stride + tile * 4 + ch * 2);
+      *dst = make_float2(mins[0], mins[1]);
     }
   }
   tc_fence_before();
@@ -300,8 +414,12 @@ batch_gemm_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 }
 
 // ---- (3) threshold, candidate groups, exact ranking --------------------------------------------------------------
-__device__ __forceinline__ double batch_slack(bool cosine, int d, double xmax, double qn) {
-  const double c1 = (1.0 / 512.0) * 1.02 + (double)d * (1.0 / 1048576.0);  // tf32 operand truncation + accumulation
+// |a(q, x) - exact| <= slack.  Operand rounding: tf32 truncates both operands (2^-10 each), the fp16 copies are
+// rounded to nearest (2^-11 each, plus a subnormal floor that the power-of-two scaling keeps below 2^-37 relative);
+// d * 2^-20 covers the tensor core's fp32 accumulation whatever its internal alignment.
+__host__ __device__ __forceinline__ double batch_slack(bool cosine, bool half, int d, double xmax, double qn) {
+  const double c1 = (half ? (1.0 / 1024.0) * 1.01 + sqrt((double)d) * (1.0 / 68719476736.0) : (1.0 / 512.0) * 1.02) +
+                    (double)d * (1.0 / 1048576.0);
   const double c2 = (double)(d + 64) * (1.0 / 8388608.0);                  // fp32 rounding of alpha, of a, of the reference sums
   if (cosine) return (c1 + c2) * qn;
   return 2.0 * c1 * xmax * qn + c2 * (xmax + qn) * (xmax + qn);
@@ -317,7 +435,7 @@ template <int TPR, int U, bool COSINE, class TK>
 __global__ void __launch_bounds__(BQ_SELECT_THREADS)
 batch_select_kernel(const float* __restrict__ X, int64_t n, int d, const float* __restrict__ Q,
                     const uint8_t* __restrict__ skip, const float* __restrict__ gm, int64_t gm_stride,
-                    int64_t ngroups, const SegStats* __restrict__ stats, int k, int kp, int cap,
+                    int64_t ngroups, const SegStats* __restrict__ stats, int half, int k, int kp, int cap,
                     int32_t* __restrict__ fb, int nq_total, TopkOut out) {
   extern __shared__ __align__(128) ulonglong2 smem[];
   constexpr int L = TPR * 4;
@@ -362,11 +480,48 @@ batch_select_kernel(const float* __restrict__ X, int64_t n, int d, const float* 
   }
   const double qq = COSINE ? s_qq : 0.0;
   const float qn = COSINE ? (float)sqrt(qq) : 0.0f;
-  const double slack = batch_slack(COSINE, d, sqrt((double)__uint_as_float(stats->xmax2_bits)), sqrt((double)q2));
+  const double slack = batch_slack(COSINE, half != 0, d, sqrt((double)__uint_as_float(stats->xmax2_bits)), sqrt((double)q2));
 
-  // phase 1: k-th smallest group minimum of this slice
+  // phase 1: T = an upper bound of the k-th smallest group minimum of this slice
   const int64_t g0 = ngroups * blockIdx.x / gridDim.x, g1 = ngroups * (blockIdx.x + 1) / gridDim.x;
-  {
+  float tau = __int_as_float(0x7f800000);
+  if (k <= BQ_TMIN_MAX_K) {
+    // small k: the k-th smallest of the per-thread minima.  The minima belong to distinct groups, so k of
+    // them lie at or below it -- a valid bound, and nearly the exact one because the few best groups
+    // rarely share a thread.  One strided pass, one 256-way rank count.
+    float* tmin = reinterpret_cast<float*>(smem);
+    float tm = __int_as_float(0x7f800000);
+    {
+      const float4* gm4 = reinterpret_cast<const float4*>(gmq);
+      const int64_t c0 = g0 >> 2, c1 = (g1 + 3) >> 2;
+#pragma unroll 4
+      for (int64_t c = c0 + threadIdx.x; c < c1; c += blockDim.x) {
+        const float4 v = gm4[c];
+        const int64_t g = c << 2;
+        if (g >= g0 && g < g1) tm = fminf(tm, v.x);
+        if (g + 1 >= g0 && g + 1 < g1) tm = fminf(tm, v.y);
+        if (g + 2 >= g0 && g + 2 < g1) tm = fminf(tm, v.z);
+        if (g + 3 >= g0 && g + 3 < g1) tm = fminf(tm, v.w);
+      }
+    }
+    tmin[threadIdx.x] = tm;
+    __shared__ float s_T;
+    if (threadIdx.x == 0) s_T = __int_as_float(0x7f800000);
+    __syncthreads();
+    int rank = 0;
+    for (int j = 0; j < (int)blockDim.x; j++) {
+      const float o = tmin[j];
+      rank += (o < tm) | ((o == tm) & (j < (int)threadIdx.x));
+    }
+    if (rank == k - 1) s_T = tm;
+    __syncthreads();
+    const float T = s_T;
+    if (T < __int_as_float(0x7f800000)) {
+      tau = f32_next_up(__double2float_ru((double)T + 2.0 * slack + 1e-37));
+      if (!(tau == tau)) tau = __int_as_float(0x7f800000);
+    }
+    __syncthreads();  // tmin aliases the collectors
+  } else {
     WarpTopK c1;
     c1.init(smem + (size_t)warp * stride1, kp, k, lane);
     for (int64_t gb = g0 + (int64_t)warp * 32; gb < g1; gb += (int64_t)nw * 32) {
@@ -377,20 +532,30 @@ batch_select_kernel(const float* __restrict__ X, int64_t n, int d, const float* 
     }
     c1.flush(lane);
     block_combine_lists(smem, stride1, nw, kp, warp, lane);
-  }
-  const Key kth = ld_key(smem + (k - 1));
-  __syncthreads();  // everyone has read the k-th key: the collectors may be reused
-  float tau = __int_as_float(0x7f800000);
-  if (!key_is_empty(kth)) {
-    const double T = f64_from_ordered(kth.hi);
-    tau = f32_next_up(__double2float_ru(T + 2.0 * slack + 1e-37));
-    if (!(tau == tau)) tau = __int_as_float(0x7f800000);
+    const Key kth = ld_key(smem + (k - 1));
+    __syncthreads();  // everyone has read the k-th key: the collectors may be reused
+    if (!key_is_empty(kth)) {
+      const double T = f64_from_ordered(kth.hi);
+      tau = f32_next_up(__double2float_ru(T + 2.0 * slack + 1e-37));
+      if (!(tau == tau)) tau = __int_as_float(0x7f800000);
+    }
   }
   // phase 2: groups that can hold a top-k row
-  for (int64_t g = g0 + threadIdx.x; g < g1; g += blockDim.x) {
-    if (gmq[g] <= tau) {
-      const int idx = atomicAdd(&s_cnt, 1);
-      if (idx < cap) list[idx] = (int)g;
+  {
+    const float4* gm4 = reinterpret_cast<const float4*>(gmq);
+    const int64_t c0 = g0 >> 2, c1 = (g1 + 3) >> 2;
+#pragma unroll 4
+    for (int64_t c = c0 + threadIdx.x; c < c1; c += blockDim.x) {
+      const float4 v = gm4[c];
+      const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int64_t g = (c << 2) + j;
+        if (g >= g0 && g < g1 && e[j] <= tau) {
+          const int idx = atomicAdd(&s_cnt, 1);
+          if (idx < cap) list[idx] = (int)g;
+        }
+      }
     }
   }
   __syncthreads();
@@ -399,7 +564,17 @@ batch_select_kernel(const float* __restrict__ X, int64_t n, int d, const float* 
     if (threadIdx.x == 0) batch_list_fallback(fb, nq_total, qi);
     cnt = cap;      // keep the ticket protocol of the epilogue intact; the fallback overwrites the result
   }
-  // phase 3: exact scores of the candidate groups' rows, ranked like scan.cu
+  // phase 3: exact scores of the candidate groups' rows, ranked like scan.cu.  All their lines are requested
+  // into L2 first, so the scoring rounds below do not each wait on HBM.
+  {
+    const int lpg = d >> 1;  // 128-byte lines per 64-row group
+    const char* xb = reinterpret_cast<const char*>(X);
+    const int64_t xbytes = n * (int64_t)d * 4;
+    for (int i = threadIdx.x; i < cnt * lpg; i += blockDim.x) {
+      const int64_t off = (int64_t)list[i / lpg] * 64 * d * 4 + (int64_t)(i % lpg) * 128;
+      if (off < xbytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(xb + off));
+    }
+  }
   TK tk;
   tk.init(smem + (size_t)warp * stride1, kp, k, lane);
   const int ub = d - (d % L);
@@ -482,27 +657,29 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// row-major fp32 matrix [rows][d] -> tensor map with a (32 floats x box_rows) box, 128-byte swizzle, zero fill
-static bool encode_rows_map(CUtensorMap* tm, const float* base, int64_t rows, int d, int box_rows) {
+// row-major matrix [rows][pitch elements] -> tensor map with a (128 bytes x box_rows) box, 128-byte swizzle, zero fill
+static bool encode_rows_map(CUtensorMap* tm, const void* base, int64_t rows, int d, int64_t pitch, bool half, int box_rows) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
+  const int esz = half ? 2 : 4;
   const cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)rows};
-  const cuuint64_t strides[1] = {(cuuint64_t)d * 4};
-  const cuuint32_t box[2] = {(cuuint32_t)BQ_KB, (cuuint32_t)box_rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)pitch * esz};
+  const cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
-  return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  return fn(tm, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims,
+            strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-bool batch_encode_segment_map(void* tm128, const float* X, int64_t n, int d) {
+// tensor map over the segment's rows: the fp32 rows themselves (half = false) or their fp16 copy with pitch dp
+bool batch_encode_segment_map(void* tm128, const void* X, int64_t n, int d, int64_t pitch, bool half) {
   static_assert(sizeof(CUtensorMap) == 128, "tensor map size");
-  return encode_rows_map(reinterpret_cast<CUtensorMap*>(tm128), X, n, d, BQ_N);
+  return encode_rows_map(reinterpret_cast<CUtensorMap*>(tm128), X, n, d, pitch, half, BQ_N);
 }
 
 bool batch_supported(int d, int lanes, bool cosine, int64_t n) {
   if (!scan_is_streaming(d, lanes, cosine)) return false;  // the re-score uses the streaming row scorer
-  if (d < BQ_KB || d > 65536) return false;
+  if (d < 32 || d > 65536) return false;
   if (n < 1 || n > (int64_t(1) << 31) - 2 * BQ_N) return false;  // 32-bit TMA coordinates, int group ids
   return encode_fn() != nullptr;
 }
@@ -514,7 +691,7 @@ static cudaError_t set_smem_attr(K kern, size_t smem) {
 }
 
 typedef void (*SelectKern)(const float*, int64_t, int, const float*, const uint8_t*, const float*, int64_t, int64_t,
-                           const SegStats*, int, int, int, int32_t*, int, TopkOut);
+                           const SegStats*, int, int, int, int, int32_t*, int, TopkOut);
 typedef void (*FallbackKern)(const float*, int64_t, int, const float*, const uint8_t*, int, int, const int32_t*, TopkOut);
 
 template <class TK>
@@ -534,12 +711,35 @@ static FallbackKern pick_fallback(int TPR, bool cosine, int k) {
   return k <= TOPK_REG_MAX_K ? fallback_kernel<WarpTopKReg>(TPR, cosine) : fallback_kernel<WarpTopK>(TPR, cosine);
 }
 
+typedef void (*GemmKern)(const CUtensorMap, const CUtensorMap, const float*, const float*, int64_t, int, int, int, int64_t,
+                         float*, int64_t);
+static GemmKern pick_gemm(bool stat, bool half, bool cosine) {
+  if (stat) {
+    if (half) return cosine ? batch_gemm_kernel<true, true, true> : batch_gemm_kernel<true, true, false>;
+    return cosine ? batch_gemm_kernel<true, false, true> : batch_gemm_kernel<true, false, false>;
+  }
+  if (half) return cosine ? batch_gemm_kernel<false, true, true> : batch_gemm_kernel<false, true, false>;
+  return cosine ? batch_gemm_kernel<false, false, true> : batch_gemm_kernel<false, false, false>;
+}
+
 bool batch_configure(BatchLaunch& L, int sms) {
   L.kp = topk_pad(L.k);
   L.tiles = (L.n + BQ_N - 1) / BQ_N;
   L.ngroups = (L.n + 63) / 64;
   L.gm_stride = L.tiles * 4;
-  L.gemm_smem = BQ_GEMM_SMEM;
+  // resident query block when it leaves room for at least 3 row-block stages, else both operands stream
+  {
+    const int kbe = L.half ? 64 : 32;
+    const int num_kb = (L.d + kbe - 1) / kbe;
+    const size_t fixed = 1024 + BQ_AB_BYTES + 256;
+    const size_t a_res = (size_t)num_kb * BQ_A_BYTES;
+    L.gemm_stat = fixed + a_res + 3 * (size_t)BQ_B_BYTES <= BQ_GEMM_SMEM_BUDGET;
+    const size_t per = L.gemm_stat ? BQ_B_BYTES : BQ_STAGE_BYTES;
+    int ns = (int)((BQ_GEMM_SMEM_BUDGET - fixed - (L.gemm_stat ? a_res : 0)) / per);
+    if (ns > BQ_MAX_STAGES) ns = BQ_MAX_STAGES;
+    L.gemm_stages = ns;
+    L.gemm_smem = fixed + (L.gemm_stat ? a_res : 0) + (size_t)ns * per;
+  }
   // candidate groups per select CTA: the k-th smallest group minimum admits about k groups, the slack a few more
   L.cap = 4 * L.k + 256;
   const int nw = BQ_SELECT_THREADS / 32;
@@ -559,7 +759,11 @@ bool batch_configure(BatchLaunch& L, int sms) {
   L.fb_gx = sms > TOPK_MAX_LISTS ? TOPK_MAX_LISTS : sms;
   L.sms = sms;
   const int TPR = L.lanes / 4;
-  if (set_smem_attr(batch_gemm_kernel, L.gemm_smem) != cudaSuccess) return false;
+  {
+    cudaError_t e;
+    e = set_smem_attr(pick_gemm(L.gemm_stat, L.half, L.cosine), L.gemm_smem);
+    if (e != cudaSuccess) return false;
+  }
   if (set_smem_attr(pick_select(TPR, L.cosine, L.k), L.select_smem) != cudaSuccess) return false;
   if (set_smem_attr(pick_fallback(TPR, L.cosine, L.k), L.fb_smem) != cudaSuccess) return false;
   return true;
@@ -583,16 +787,26 @@ int64_t batch_partial_keys(const BatchLaunch& L, int nq) {
 cudaError_t launch_batch(const BatchLaunch& L, cudaStream_t st) {
   cudaError_t e;
   CUtensorMap tmQ;
-  if (!encode_rows_map(&tmQ, L.q, L.nq, L.d, BQ_M)) return cudaErrorInvalidValue;
-  const CUtensorMap tmX = *reinterpret_cast<const CUtensorMap*>(L.tmX);
   const int nqb = (L.nq + BQ_M - 1) / BQ_M;
+  const int kbe = L.half ? 64 : 32;
+  const int num_kb = (L.d + kbe - 1) / kbe;
+  if (L.half) {
+    count_launch();
+    query_convert_kernel<<<(nqb * BQ_M + 7) / 8, 256, 0, st>>>(L.q, L.nq, nqb * BQ_M, L.d, L.dp, L.x_scale, static_cast<__half*>(L.qh), L.qinv);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (!encode_rows_map(&tmQ, L.qh, L.nq, L.d, L.dp, true, BQ_M)) return cudaErrorInvalidValue;
+  } else {
+    if (!encode_rows_map(&tmQ, L.q, L.nq, L.d, L.d, false, BQ_M)) return cudaErrorInvalidValue;
+  }
+  const CUtensorMap tmX = *reinterpret_cast<const CUtensorMap*>(L.tmX);
   int nsplit = L.sms / nqb;
   if (nsplit < 1) nsplit = 1;
   if (nsplit > L.tiles) nsplit = (int)L.tiles;
   if ((e = cudaMemsetAsync(L.fb, 0, sizeof(int32_t) * (1 + 2 * (size_t)L.nq), st)) != cudaSuccess) return e;
   count_launch();
-  batch_gemm_kernel<<<nqb * nsplit, BQ_THREADS, L.gemm_smem, st>>>(tmQ, tmX, L.ab, L.n, (L.d + BQ_KB - 1) / BQ_KB, nqb,
-                                                                   L.tiles, L.gm, L.gm_stride);
+  const int grid = nqb * nsplit;
+  pick_gemm(L.gemm_stat, L.half, L.cosine)<<<grid, BQ_THREADS, L.gemm_smem, st>>>(tmQ, tmX, L.coef, L.qinv, L.n, num_kb,
+                                                                                 L.gemm_stages, nqb, L.tiles, L.gm, L.gm_stride);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   const int TPR = L.lanes / 4;
   const int P = batch_select_ctas(L, L.nq);
@@ -600,7 +814,7 @@ cudaError_t launch_batch(const BatchLaunch& L, cudaStream_t st) {
             L.out_stride > 0 ? L.out_stride : L.k};
   count_launch();
   pick_select(TPR, L.cosine, L.k)<<<dim3(P, L.nq), BQ_SELECT_THREADS, L.select_smem, st>>>(
-      L.X, L.n, L.d, L.q, L.skip, L.gm, L.gm_stride, L.ngroups, L.stats, L.k, L.kp, L.cap, L.fb, L.nq, o);
+      L.X, L.n, L.d, L.q, L.skip, L.gm, L.gm_stride, L.ngroups, L.stats, L.half ? 1 : 0, L.k, L.kp, L.cap, L.fb, L.nq, o);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   count_launch();
   const int gy = L.nq < BQ_FB_SLOTS ? L.nq : BQ_FB_SLOTS;

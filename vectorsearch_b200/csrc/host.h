@@ -20,11 +20,17 @@ struct Segment {
   int M = 0, K = 0, subDim = 0;
   // batched-query nomination state (batch.cu), built at first use per metric under `mu`
   std::mutex mu;
-  void* ab[2] = {nullptr, nullptr};     // float2[n] per metric
+  void* ab[2] = {nullptr, nullptr};     // float[n] nomination coefficients per metric
   void* stats[2] = {nullptr, nullptr};  // SegStats per metric (device)
   int nonfinite[2] = {0, 0};            // host copy of SegStats::nonfinite
+  unsigned int xmax2 = 0;               // host copy of SegStats::xmax2_bits (same for both metrics)
   bool tm_ok = false;
-  alignas(64) unsigned char tmX[128];   // CUtensorMap over X
+  alignas(64) unsigned char tmX[128];   // CUtensorMap over X (fp32 rows, consumed as tf32)
+  void* Xh = nullptr;                   // fp16 operand copy [n][dp], scaled by x_scale (a power of two)
+  int dp = 0;
+  float x_scale = 1.0f;
+  bool xh_tried = false;                // the copy was attempted (it is optional: tf32 operands otherwise)
+  alignas(64) unsigned char tmXh[128];  // CUtensorMap over Xh
 };
 
 int fail(int code, const char* fmt, ...);

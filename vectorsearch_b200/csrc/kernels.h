@@ -47,8 +47,8 @@ struct SegStats {
   unsigned int xmax2_bits;  // bit pattern of max |x|^2 over live rows
   int nonfinite;            // a live row has a non-finite (or absurdly large) norm
 };
-// per-row nomination coefficients (alpha, beta) for one metric + SegStats; one pass over the segment
-cudaError_t launch_row_prep(const float* X, int64_t n, int d, const uint8_t* skip, bool cosine, float2* ab,
+// per-row nomination coefficient for one metric + SegStats; one pass over the segment
+cudaError_t launch_row_prep(const float* X, int64_t n, int d, const uint8_t* skip, bool cosine, float* coef,
                             SegStats* stats, int sms, cudaStream_t st);
 struct BatchLaunch {
   const float* X;
@@ -60,8 +60,13 @@ struct BatchLaunch {
   const float* q;        // [nq][d] device
   int nq;
   int k, kp;
-  const void* tmX;       // host copy of the segment's CUtensorMap (128 bytes)
-  const float2* ab;      // [n]
+  const void* tmX;       // host copy of the CUtensorMap (128 bytes) over the operand rows (fp32 rows or their fp16 copy)
+  bool half;             // operands are fp16 copies (kind::f16) instead of the fp32 data read as tf32
+  int dp;                // fp16 row pitch in elements (d rounded up to 8)
+  float x_scale;         // power of two the fp16 row copy was scaled by
+  void* qh;              // [nq][dp] fp16 scratch for the scaled queries (half only)
+  float* qinv;           // [round_up(nq, 128)] 1 / (x_scale * query scale) (half only)
+  const float* coef;     // [n] per-row nomination coefficient of this metric
   const SegStats* stats; // device
   float* gm;             // [round_up(nq, 128)][gm_stride] group minima
   int32_t* fb;           // [1 + 2 nq]: fallback count, fallback query list, per-query "listed" flags
@@ -77,10 +82,13 @@ struct BatchLaunch {
   int64_t tiles, ngroups, gm_stride;
   int cap, sms, fb_gx, fb_threads;
   size_t gemm_smem, select_smem, fb_smem;
+  bool gemm_stat;        // query block resident in shared memory (short vectors)
+  int gemm_stages;
 };
 bool batch_supported(int d, int lanes, bool cosine, int64_t n);
-bool batch_encode_segment_map(void* tm128, const float* X, int64_t n, int d);
-bool batch_configure(BatchLaunch& L, int sms);          // from (n, d, lanes, cosine, k)
+bool batch_encode_segment_map(void* tm128, const void* rows, int64_t n, int d, int64_t pitch, bool half);
+cudaError_t launch_row_convert(const float* X, int64_t n, int d, int dp, float sx, void* Xh, int sms, cudaStream_t st);
+bool batch_configure(BatchLaunch& L, int sms);          // from (n, d, lanes, cosine, k, half)
 int64_t batch_partial_keys(const BatchLaunch& L, int nq);  // keys of `partial` per query for a chunk of nq
 cudaError_t launch_batch(const BatchLaunch& L, cudaStream_t st);  // one chunk of L.nq queries
 
