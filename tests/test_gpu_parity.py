@@ -155,17 +155,20 @@ def test_bruteforce_query_batch(vs, oracle):
 
 
 # ---- batched queries: tensor-core nomination + exact re-score (batch.cu) ----------------------------------
-@pytest.fixture(params=["fp16", "tf32"])
+@pytest.fixture(params=["fp16", "tf32", "fp16-warpselect"])
 def force_batch(vs, request):
     """Route every query batch of >= 2 queries through batch.cu, whatever the segment size, nominating
-    on the fp16 operand copies (default) or on the fp32 rows read as tf32."""
+    on the fp16 operand copies (default) or on the fp32 rows read as tf32; "warpselect" also forces the
+    one-warp-per-query selection kernel that large batches use."""
     vs.set_option("batch_min_queries", 2)
     vs.set_option("batch_min_rows", 1)
-    vs.set_option("batch_fp16", 1 if request.param == "fp16" else 0)
+    vs.set_option("batch_fp16", 0 if request.param == "tf32" else 1)
+    vs.set_option("batch_warp_min_queries", 2 if "warpselect" in request.param else 512)
     yield
     vs.set_option("batch_min_queries", 3)
     vs.set_option("batch_min_rows", 16384)
     vs.set_option("batch_fp16", 1)
+    vs.set_option("batch_warp_min_queries", 512)
 
 
 def _check_batch(vs, oracle, rows, qs, k, metric, skip=None, id_base=0, threads=4):

@@ -647,10 +647,11 @@ bool adc_fast_configure(AdcFastLaunch& L, int sms) {
   L.final_grid = sms < TOPK_MAX_LISTS ? sms : TOPK_MAX_LISTS;
   L.final_smem = topk_block_smem(L.k, L.kp, L.final_threads / 32);
   FallbackKern fk = L.k <= TOPK_REG_MAX_K ? adc_fallback_kernel<WarpTopKReg> : adc_fallback_kernel<WarpTopK>;
-  if (L.final_smem > 48 * 1024) {
-    e = cudaFuncSetAttribute(fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.final_smem);
-    if (e != cudaSuccess) return false;
-  }
+  // the attribute is per kernel and plans are cached: opt in to the largest size any plan can ask for
+  // (k = TOPK_MAX_K), so that a later plan with a smaller k cannot lower it under an earlier one
+  e = cudaFuncSetAttribute(fk, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)topk_block_smem(TOPK_MAX_K, topk_pad(TOPK_MAX_K), L.final_threads / 32));
+  if (e != cudaSuccess) return false;
   L.partial_keys = topk_partial_keys(L.k, L.final_grid, L.final_threads / 32);
   return true;
 }

@@ -27,6 +27,7 @@ static std::atomic<int64_t> g_adc_fast_cap{4096};         // candidate-list entr
 static std::atomic<int64_t> g_batch_min_queries{3};        // query batches at least this large use batch.cu
 static std::atomic<int64_t> g_batch_min_rows{16384};       // ... on segments at least this long
 static std::atomic<int64_t> g_batch_gm_bytes{int64_t(1) << 30};  // group-minima scratch per query chunk
+static std::atomic<int64_t> g_batch_warp_min_q{512};       // batches this large select with one warp per query
 static std::atomic<int64_t> g_batch_fp16{1};                // nominate on fp16 operand copies (0: the fp32 rows as tf32)
 static int g_sms = 0;
 static std::mutex g_mu;
@@ -503,7 +504,7 @@ static int batch_run_dev(cudaStream_t st, const Segment* s, const BatchLaunch& p
     L.qinv = p.half ? A.take<float>((size_t)((chunk + 127) / 128 * 128)) : nullptr;
     L.ctrl = d_ticket;
     L.ids_out = d_ids + (size_t)q0 * os; L.scores_out = d_scores + (size_t)q0 * os; L.counts_out = d_counts + q0;
-    L.id_base = s->id_base; L.out_stride = os;
+    L.id_base = s->id_base; L.out_stride = os; L.warp_min_q = (int)g_batch_warp_min_q.load();
     CK(launch_batch(L, st), "batched scan launch");
   }
   return VS_OK;
@@ -586,6 +587,11 @@ int32_t vs_debug_adc_stats(uint32_t* out8) { return vs::debug_adc_stats(out8) ==
 
 int32_t vs_set_option(const char* name, int64_t value) {
   if (!name) return fail(VS_EINVAL, "null option name");
+  if (!strcmp(name, "batch_warp_min_queries")) {
+    if (value < 1) return fail(VS_EINVAL, "batch_warp_min_queries must be >= 1");
+    g_batch_warp_min_q.store(value);
+    return VS_OK;
+  }
   if (!strcmp(name, "batch_fp16")) {  // applies to segments that have not been queried in batches yet
     g_batch_fp16.store(value != 0);
     return VS_OK;

@@ -595,6 +595,134 @@ batch_select_kernel(const float* __restrict__ X, int64_t n, int d, const float* 
   topk_epilogue(tk, smem, kp, k, out);
 }
 
+// Large batches, k <= 32: one WARP per query.  Every step of the selection is latency-bound (a pass over the
+// query's group minima, then a dozen 32 KB row groups fetched from HBM), so what matters is how many queries
+// an SM works on at once: 16 here against 2 CTAs of the kernel above, with no block-wide barrier anywhere.
+template <int TPR, int U, bool COSINE>
+__global__ void __launch_bounds__(BQ_SELECT_THREADS)
+batch_select_warp_kernel(const float* __restrict__ X, int64_t n, int d, const float* __restrict__ Q,
+                         const uint8_t* __restrict__ skip, const float* __restrict__ gm, int64_t gm_stride,
+                         int64_t ngroups, const SegStats* __restrict__ stats, int half, int k, int cap,
+                         int32_t* __restrict__ fb, int nq, int64_t* __restrict__ ids, double* __restrict__ scores,
+                         int32_t* __restrict__ counts, int64_t id_base, int64_t out_stride) {
+  extern __shared__ __align__(128) ulonglong2 smem[];
+  constexpr int L = TPR * 4;
+  constexpr int RPB = (32 / TPR) * U;
+  constexpr int BPG = 64 / RPB;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int qi = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (qi >= nq) return;
+  const int qpad = (d + 3) & ~3;
+  int* list = reinterpret_cast<int*>(smem) + (size_t)warp * (cap + qpad);
+  float* qs = reinterpret_cast<float*>(list + cap);
+  const float* __restrict__ q = Q + (size_t)qi * d;
+  const float* __restrict__ gmq = gm + (size_t)qi * gm_stride;
+  const float inf = __int_as_float(0x7f800000);
+
+  float ss = 0.0f;
+  for (int i = lane; i < d; i += 32) {
+    const float v = q[i];
+    qs[i] = v;
+    ss = fmaf(v, v, ss);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(FULL_MASK, ss, o);
+  if (!(ss < 1e30f)) {  // non-finite query: exact scan instead
+    if (lane == 0) batch_list_fallback(fb, nq, qi);
+    return;
+  }
+  double qq = 0.0;
+  if (COSINE) {
+    if (lane == 0) qq = ref_sum_thread_L<L, REF_DOT>(q, q, d);
+    qq = __shfl_sync(FULL_MASK, qq, 0);
+  }
+  const float qn = COSINE ? (float)sqrt(qq) : 0.0f;
+  const double slack = batch_slack(COSINE, half != 0, d, sqrt((double)__uint_as_float(stats->xmax2_bits)), sqrt((double)ss));
+  __syncwarp();
+
+  // T = k-th smallest of the 32 per-lane minima (distinct groups, so k of them lie at or below it)
+  const float4* gm4 = reinterpret_cast<const float4*>(gmq);
+  const int64_t nch = (ngroups + 3) >> 2;  // the tile padding beyond ngroups holds +inf
+  float tm = inf;
+#pragma unroll 8
+  for (int64_t c = lane; c < nch; c += 32) {
+    const float4 v = gm4[c];
+    tm = fminf(fminf(tm, v.x), fminf(v.y, fminf(v.z, v.w)));
+  }
+  int rank = 0;
+#pragma unroll
+  for (int j = 0; j < 32; j++) {
+    const float o = __shfl_sync(FULL_MASK, tm, j);
+    rank += (o < tm) | ((o == tm) & (j < lane));
+  }
+  const unsigned who = __ballot_sync(FULL_MASK, rank == k - 1);
+  const float T = __shfl_sync(FULL_MASK, tm, __ffs(who) - 1);
+  float tau = inf;
+  if (T < inf) {
+    tau = f32_next_up(__double2float_ru((double)T + 2.0 * slack + 1e-37));
+    if (!(tau == tau)) tau = inf;
+  }
+  // groups that can hold a top-k row, compacted with ballots
+  int cnt = 0;
+  for (int64_t c0 = 0; c0 < nch; c0 += 32) {
+    const int64_t c = c0 + lane;
+    float4 v = make_float4(inf, inf, inf, inf);
+    if (c < nch) v = gm4[c];
+    const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int64_t g = (c << 2) + j;
+      const bool p = c < nch && g < ngroups && e[j] <= tau;
+      const unsigned m = __ballot_sync(FULL_MASK, p);
+      if (p) {
+        const int pos = cnt + __popc(m & ((1u << lane) - 1u));
+        if (pos < cap) list[pos] = (int)g;
+      }
+      cnt += __popc(m);
+    }
+  }
+  if (cnt > cap) {  // adversarial data: full exact scan for this query (its result below is overwritten)
+    if (lane == 0) batch_list_fallback(fb, nq, qi);
+    cnt = cap;
+  }
+  __syncwarp();
+  {
+    const int lpg = d >> 1;  // 128-byte lines per 64-row group
+    const char* xb = reinterpret_cast<const char*>(X);
+    const int64_t xbytes = n * (int64_t)d * 4;
+    for (int i = lane; i < cnt * lpg; i += 32) {
+      const int64_t off = (int64_t)list[i / lpg] * 64 * d * 4 + (int64_t)(i % lpg) * 128;
+      if (off < xbytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(xb + off));
+    }
+  }
+  WarpTopKReg tk;
+  tk.init(nullptr, 32, k, lane);
+  const int ub = d - (d % L);
+  const int nv = ub / L;
+  float fthr = inf;
+  uint64_t seen_hi = KEY_EMPTY64, seen_lo = KEY_EMPTY64;
+  const int total = cnt * BPG;
+  for (int b = 0; b < total; b++) {
+    const int64_t row_base = (int64_t)list[b / BPG] * 64 + (int64_t)(b % BPG) * RPB;
+    if (row_base >= n) continue;
+    scan_batch_ldg<TPR, U, COSINE, WarpTopKReg>(X, n, d, q, qs, skip, row_base, nv, ub, qq, qn, fthr, tk, lane);
+    if (tk.thr.hi != seen_hi || tk.thr.lo != seen_lo) {
+      seen_hi = tk.thr.hi;
+      seen_lo = tk.thr.lo;
+      fthr = scan_filter_threshold<COSINE>(tk.thr);
+    }
+  }
+  // lane i holds the i-th best key
+  const bool ok = lane < k && tk.my_lo != KEY_EMPTY64;
+  if (lane < k) {
+    ids[(size_t)qi * out_stride + lane] = ok ? id_base + (int64_t)tk.my_lo : -1;
+    scores[(size_t)qi * out_stride + lane] = ok ? score_from_rank_hi(tk.my_hi) : __longlong_as_double(0x7ff8000000000000ll);
+  }
+  const unsigned okm = __ballot_sync(FULL_MASK, ok);
+  if (lane == 0) counts[qi] = __popc(okm);
+}
+
 // ---- (4) exact scan of the queries listed in fb (count, then query indices) ----------------------------------------
 template <int TPR, int U, bool COSINE, class TK>
 __global__ void __launch_bounds__(SCAN_THREADS)
@@ -684,14 +812,22 @@ bool batch_supported(int d, int lanes, bool cosine, int64_t n) {
   return encode_fn() != nullptr;
 }
 
+// The attribute is per kernel, not per launch shape: plans are cached, so every kernel is opted in to the
+// largest dynamic shared memory any plan may ask for (a smaller, later request must not lower it).
 template <typename K>
-static cudaError_t set_smem_attr(K kern, size_t smem) {
-  if (smem > 48 * 1024) return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  return cudaSuccess;
+static cudaError_t set_smem_attr(K kern, size_t smem_max) {
+  return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
 }
+constexpr size_t BQ_SELECT_SMEM_MAX = 220 * 1024, BQ_SELW_SMEM_MAX = 96 * 1024;
 
 typedef void (*SelectKern)(const float*, int64_t, int, const float*, const uint8_t*, const float*, int64_t, int64_t,
                            const SegStats*, int, int, int, int, int32_t*, int, TopkOut);
+typedef void (*SelectWarpKern)(const float*, int64_t, int, const float*, const uint8_t*, const float*, int64_t, int64_t,
+                               const SegStats*, int, int, int, int32_t*, int, int64_t*, double*, int32_t*, int64_t, int64_t);
+static SelectWarpKern pick_select_warp(int TPR, bool cosine) {
+  if (cosine) return TPR == 4 ? batch_select_warp_kernel<4, 1, true> : (TPR == 2 ? batch_select_warp_kernel<2, 1, true> : batch_select_warp_kernel<1, 1, true>);
+  return TPR == 4 ? batch_select_warp_kernel<4, 2, false> : (TPR == 2 ? batch_select_warp_kernel<2, 2, false> : batch_select_warp_kernel<1, 2, false>);
+}
 typedef void (*FallbackKern)(const float*, int64_t, int, const float*, const uint8_t*, int, int, const int32_t*, TopkOut);
 
 template <class TK>
@@ -752,20 +888,26 @@ bool batch_configure(BatchLaunch& L, int sms) {
     if (L.select_smem <= 200 * 1024 || L.cap <= L.k + 64) break;
     L.cap = L.cap / 2 > L.k + 64 ? L.cap / 2 : L.k + 64;
   }
-  if (L.select_smem > 220 * 1024) return false;
+  if (L.select_smem > BQ_SELECT_SMEM_MAX) return false;
+  L.selw_smem = (size_t)(BQ_SELECT_THREADS / 32) * (size_t)(L.cap + ((L.d + 3) & ~3)) * 4;
+  if (L.k <= TOPK_REG_MAX_K && L.selw_smem <= BQ_SELW_SMEM_MAX) {
+    if (set_smem_attr(pick_select_warp(L.lanes / 4, L.cosine), BQ_SELW_SMEM_MAX) != cudaSuccess) return false;
+  } else {
+    L.selw_smem = 0;  // warp-per-query selection not available for this shape
+  }
   L.fb_threads = SCAN_THREADS;
   L.fb_smem = ((topk_block_smem(L.k, L.kp, L.fb_threads / 32) + 15) & ~size_t(15)) + (((size_t)L.d * 4 + 15) & ~size_t(15));
-  if (L.fb_smem > 220 * 1024) return false;
+  if (L.fb_smem > BQ_SELECT_SMEM_MAX) return false;
   L.fb_gx = sms > TOPK_MAX_LISTS ? TOPK_MAX_LISTS : sms;
   L.sms = sms;
   const int TPR = L.lanes / 4;
   {
     cudaError_t e;
-    e = set_smem_attr(pick_gemm(L.gemm_stat, L.half, L.cosine), L.gemm_smem);
+    e = set_smem_attr(pick_gemm(L.gemm_stat, L.half, L.cosine), BQ_GEMM_SMEM_BUDGET);
     if (e != cudaSuccess) return false;
   }
-  if (set_smem_attr(pick_select(TPR, L.cosine, L.k), L.select_smem) != cudaSuccess) return false;
-  if (set_smem_attr(pick_fallback(TPR, L.cosine, L.k), L.fb_smem) != cudaSuccess) return false;
+  if (set_smem_attr(pick_select(TPR, L.cosine, L.k), BQ_SELECT_SMEM_MAX) != cudaSuccess) return false;
+  if (set_smem_attr(pick_fallback(TPR, L.cosine, L.k), BQ_SELECT_SMEM_MAX) != cudaSuccess) return false;
   return true;
 }
 
@@ -813,6 +955,12 @@ cudaError_t launch_batch(const BatchLaunch& L, cudaStream_t st) {
   TopkOut o{L.partial, L.ctrl, L.partial_keys, L.ids_out, L.scores_out, L.counts_out, L.id_base, 0,
             L.out_stride > 0 ? L.out_stride : L.k};
   count_launch();
+  if (L.selw_smem != 0 && L.nq >= L.warp_min_q) {
+    const int wpb = BQ_SELECT_THREADS / 32;
+    pick_select_warp(TPR, L.cosine)<<<(L.nq + wpb - 1) / wpb, BQ_SELECT_THREADS, L.selw_smem, st>>>(
+        L.X, L.n, L.d, L.q, L.skip, L.gm, L.gm_stride, L.ngroups, L.stats, L.half ? 1 : 0, L.k, L.cap, L.fb, L.nq,
+        L.ids_out, L.scores_out, L.counts_out, L.id_base, L.out_stride > 0 ? L.out_stride : L.k);
+  } else
   pick_select(TPR, L.cosine, L.k)<<<dim3(P, L.nq), BQ_SELECT_THREADS, L.select_smem, st>>>(
       L.X, L.n, L.d, L.q, L.skip, L.gm, L.gm_stride, L.ngroups, L.stats, L.half ? 1 : 0, L.k, L.kp, L.cap, L.fb, L.nq, o);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;

@@ -78,10 +78,11 @@ struct BatchLaunch {
   int32_t* counts_out;
   int64_t id_base;
   int64_t out_stride;
+  int warp_min_q;        // chunks of at least this many queries select with one warp per query (k <= 32)
   // filled by batch_configure:
   int64_t tiles, ngroups, gm_stride;
   int cap, sms, fb_gx, fb_threads;
-  size_t gemm_smem, select_smem, fb_smem;
+  size_t gemm_smem, select_smem, selw_smem, fb_smem;
   bool gemm_stat;        // query block resident in shared memory (short vectors)
   int gemm_stages;
 };
