@@ -71,6 +71,17 @@ def measured_peaks() -> tuple[float, str]:
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def measured_tensor_peak() -> tuple[float, str]:
+    """Dense 16-bit tensor TFLOP/s (the fp16 nomination GEMM runs at the bf16 rate): burst figure, the kernel is timed alone."""
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["bf16_tflops"]), "measured (MEASURED_PEAKS.json bf16_tflops, burst)"
+        except Exception:
+            pass
+    return 1670.0, "fallback (B200_PROFILING.md dense bf16)"
+
+
 # ---------------------------------------------------------------------------------------------------
 # clocks: sampled DURING the timed regions with NVML
 # ---------------------------------------------------------------------------------------------------
@@ -290,6 +301,8 @@ def run_ours(args) -> None:
                "ms_per_query": cms}
 
     extra = {}
+    if world == 1:
+        extra["c2_b1024"] = bench_c2_batch(vs, L, lib, torch, dev, seg, min(K, 50), W)
     if args.workload in ("c4", "all") and world == 1:
         extra["c4"] = bench_c4(vs, L, lib, torch, dev, min(K, 50), W, hbm_peak)
 
@@ -325,6 +338,59 @@ def run_ours(args) -> None:
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def bench_c2_batch(vs, L, lib, torch, dev, seg, K, W, nq=1024):
+    """C2, query batch 1024: one step = 1024 queries against the resident 1M x 128 segment (batch.cu:
+    tcgen05 fp16 nomination GEMM + exact re-score).  Tensor-bound: 2 * N * D * B flop per batch."""
+    import numpy as np
+
+    tpeak, tsrc = measured_tensor_peak()
+    g = torch.Generator(device="cpu").manual_seed(QUERY_SEED + 1)
+    q_host = (torch.rand((nq, DIM), generator=g, dtype=torch.float32) * 2 - 1).pin_memory()
+    q_dev = q_host.to(dev)
+    ids = torch.empty((nq, TOPK), dtype=torch.int64, device=dev)
+    sc = torch.empty((nq, TOPK), dtype=torch.float64, device=dev)
+    cn = torch.empty((nq,), dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream()
+    st = stream.cuda_stream
+
+    def step():
+        L.check(lib.vs_bruteforce_topk_dev(seg.handle, q_dev.data_ptr(), nq, TOPK, 0, ids.data_ptr(), sc.data_ptr(), cn.data_ptr(), st))
+
+    for _ in range(max(W, 3)):
+        step()
+    torch.cuda.synchronize()
+    l0 = vs.kernel_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(K):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / K
+    launches = vs.kernel_launch_count() - l0
+    qn = q_host.numpy()
+    for _ in range(3):
+        seg.bruteforce_topk(qn, TOPK)
+    t0 = time.perf_counter()
+    for _ in range(K):
+        r = seg.bruteforce_topk(qn, TOPK)
+    e2e_ms = (time.perf_counter() - t0) / K * 1e3
+    flops = 2.0 * N_ROWS * DIM * nq
+    tf = flops / (ms * 1e-3) / 1e12
+    # the same 1024 queries one at a time through the streaming scan must give the same lists (spot check)
+    same = all(np.array_equal(seg.bruteforce_topk(qn[i], TOPK)[0], r[0][i]) for i in (0, 511, 1023))
+    return {"workload": f"C2: exact L2 brute-force top-{TOPK} over {N_ROWS}x{DIM} fp32, query batch {nq}, 1 GPU",
+            "ms_per_batch": ms, "qps": nq / (ms * 1e-3), "distance_evals_per_s": N_ROWS * nq / (ms * 1e-3),
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak,
+                         "peak_source": tsrc, "algorithmic_flops_per_batch": flops,
+                         "kernel": "batch_gemm_kernel<STAT,HALF,L2,G64> (K2, tcgen05 kind::f16) + batch_select + fallback; "
+                                   "achieved is over the WHOLE batch, the GEMM alone is the share profiles/r1_c2_b1024_launches.txt shows",
+                         "traffic": None},
+            "e2e": {"ms_per_batch": e2e_ms, "qps": nq / (e2e_ms * 1e-3), "distance_evals_per_s": N_ROWS * nq / (e2e_ms * 1e-3),
+                    "h2d_bytes_per_step": nq * DIM * 4, "d2h_bytes_per_step": nq * (TOPK * 16 + 4)},
+            "gpu_launches": int(launches), "matches_per_query_scan": bool(same)}
 
 
 def bench_c4(vs, L, lib, torch, dev, K, W, hbm_peak):

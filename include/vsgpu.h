@@ -156,9 +156,23 @@ int32_t vs_merge_topk_dev(const int64_t* d_ids, const double* d_scores, int64_t 
 int64_t vs_kernel_launch_count(void);
 /* Tuning knobs (process-wide).  "adc_fast_min_rows": segments with fewer code rows use the generic
  * ADC kernel (default 16384); "adc_fast_cap": candidate-list entries per scan CTA of the fast ADC
- * scan (default 4096; on overflow the query is evaluated exactly over every row).  Results never depend
- * on either. */
+ * scan (default 4096; on overflow the query is evaluated exactly over every row).
+ * Batched brute force (query batches are nominated on the tensor cores and re-scored exactly, batch.cu):
+ * "batch_min_queries" (default 3) and "batch_min_rows" (default 16384): smaller batches / segments use
+ * the per-query scan; "batch_fp16" (default 1): nominate on an fp16 operand copy of the rows (n * d * 2
+ * bytes of HBM, made at the first batched query) instead of the fp32 rows read as tf32; "batch_group"
+ * (0 = automatic, 16 / 32 / 64): rows per nomination group; "batch_gm_bytes": scratch per query chunk;
+ * "batch_warp_min_queries" (0 = automatic).  Results never depend on any of them. */
 int32_t vs_set_option(const char* name, int64_t value);
+
+/* ---- diagnostics -----------------------------------------------------------------------------------
+ * The batched path nominates rows with a(q, x) computed on the tensor cores (L2: |x|^2 - 2<q,x>,
+ * COSINE: -<q,x>/|x|) and keeps every row whose value can be within `slack` of the exact one.  This
+ * returns what the tensor-core stage produced -- per query the minimum of a over each group of
+ * *group_out consecutive rows, gm_out[nq][*ngroups_out] -- and the slack per query, so that a test can
+ * check |tensor-core value - exact value| <= slack.  gm_out == NULL only reports the two sizes. */
+int32_t vs_debug_batch_groupmins(uint64_t h, const float* q, int32_t nq, int32_t metric, float* gm_out,
+                                 int64_t gm_capacity, int64_t* ngroups_out, int32_t* group_out, double* slack_out);
 
 #ifdef __cplusplus
 }

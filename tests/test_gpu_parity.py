@@ -155,7 +155,7 @@ def test_bruteforce_query_batch(vs, oracle):
 
 
 # ---- batched queries: tensor-core nomination + exact re-score (batch.cu) ----------------------------------
-@pytest.fixture(params=["fp16", "tf32", "fp16-warpselect"])
+@pytest.fixture(params=["fp16", "tf32", "fp16-warpselect", "fp16-g16", "tf32-g32", "fp16-g64"])
 def force_batch(vs, request):
     """Route every query batch of >= 2 queries through batch.cu, whatever the segment size, nominating
     on the fp16 operand copies (default) or on the fp32 rows read as tf32; "warpselect" also forces the
@@ -163,12 +163,14 @@ def force_batch(vs, request):
     vs.set_option("batch_min_queries", 2)
     vs.set_option("batch_min_rows", 1)
     vs.set_option("batch_fp16", 0 if request.param == "tf32" else 1)
-    vs.set_option("batch_warp_min_queries", 2 if "warpselect" in request.param else 512)
+    vs.set_option("batch_warp_min_queries", 2 if "warpselect" in request.param else 0)
+    vs.set_option("batch_group", int(request.param.split("-g")[1]) if "-g" in request.param else 0)  # rows per group
     yield
+    vs.set_option("batch_group", 0)
     vs.set_option("batch_min_queries", 3)
     vs.set_option("batch_min_rows", 16384)
     vs.set_option("batch_fp16", 1)
-    vs.set_option("batch_warp_min_queries", 512)
+    vs.set_option("batch_warp_min_queries", 0)
 
 
 def _check_batch(vs, oracle, rows, qs, k, metric, skip=None, id_base=0, threads=4):
@@ -275,6 +277,48 @@ def test_c2_full_size_batch_1024(vs, oracle):
             assert np.array_equal(ids[i], oi) and _same(sc[i], os_)
     finally:
         seg.free()
+
+
+@pytest.mark.parametrize("mode", ["fp16", "tf32"])
+@pytest.mark.parametrize("metric", [0, 1])
+@pytest.mark.parametrize("n,d,scale", [(20000, 128, 1.0), (6000, 768, 1.0), (8000, 96, 300.0), (8000, 64, 1e-4)])
+def test_batch_nomination_bound(vs, oracle, mode, metric, n, d, scale):
+    """The tensor-core stage may deviate from the exact a(q, x) by at most the slack the selection adds
+    (that is what makes the nominated set a superset of the true top-k).  Measured here against float64."""
+    import ctypes as C
+
+    from vectorsearch_b200 import _lib as L
+
+    vs.set_option("batch_fp16", 1 if mode == "fp16" else 0)
+    try:
+        rows = (oracle.gen_rows(7, 0, n, d) * np.float32(scale)).astype(np.float32)
+        rows[::7] *= np.float32(0.25)                       # mixed norms
+        qs = (oracle.gen_rows(8, 0, 16, d) * np.float32(scale)).astype(np.float32)
+        qs[3] *= np.float32(1e-3)                           # a query much smaller than the rows
+        seg = vs.Segment.upload(rows)
+        try:
+            lib = vs.load()
+            ng, g = C.c_int64(), C.c_int32()
+            L.check(lib.vs_debug_batch_groupmins(seg.handle, qs.ctypes.data_as(L.f32p), 16, metric, None, 0, C.byref(ng), C.byref(g), None))
+            gm = np.zeros((16, ng.value), np.float32)
+            slack = np.zeros(16, np.float64)
+            L.check(lib.vs_debug_batch_groupmins(seg.handle, qs.ctypes.data_as(L.f32p), 16, metric, gm.ctypes.data_as(L.f32p),
+                                                 gm.size, C.byref(ng), C.byref(g), slack.ctypes.data_as(L.f64p)))
+        finally:
+            seg.free()
+        X, Q = rows.astype(np.float64), qs.astype(np.float64)
+        dots = Q @ X.T
+        xx = (X * X).sum(1)
+        a = (xx[None, :] - 2 * dots) if metric == 0 else -dots / np.sqrt(xx)[None, :]
+        pad = (-n) % g.value
+        a = np.pad(a, ((0, 0), (0, pad)), constant_values=np.inf).reshape(16, -1, g.value).min(2)
+        err = np.abs(gm.astype(np.float64) - a)
+        worst = float((err / slack[:, None]).max())
+        assert worst <= 1.0, f"nomination error exceeds the slack: {worst:.3f} of the bound"
+        assert worst >= 1e-4 or d < 64, "suspiciously exact: is the tensor-core stage running?"
+        print(f"nomination error / slack: max {worst:.4f} ({mode}, metric {metric}, n={n}, d={d}, scale={scale})")
+    finally:
+        vs.set_option("batch_fp16", 1)
 
 
 def test_empty_segment_and_bad_args(vs):

@@ -21,7 +21,7 @@ for (n, d, k, nq) in shapes:
         vs.set_option("batch_min_queries", 2)
         vs.set_option("batch_min_rows", 1)
         vs.set_option("batch_fp16", 0 if mode == "tf32" else 1)
-        vs.set_option("batch_warp_min_queries", 2 if "warp" in mode else 512)
+        vs.set_option("batch_warp_min_queries", 2 if "warp" in mode else 0)
         fails = 0
         for trial in range(40):
             seg = vs.Segment.upload(rows)

@@ -13,6 +13,8 @@ lib = vs.load()
 import os
 if os.environ.get("VS_TF32"):
     vs.set_option("batch_fp16", 0)
+if os.environ.get("VS_GROUP"):
+    vs.set_option("batch_group", int(os.environ["VS_GROUP"]))
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
 d = int(sys.argv[2]) if len(sys.argv) > 2 else 128
 k = int(sys.argv[3]) if len(sys.argv) > 3 else 10

@@ -65,6 +65,7 @@ SIGNATURES = {
     "vs_merge_topk_dev": (i32, [vp, vp, i64, i32, vp, vp, vp, vp]),
     "vs_kernel_launch_count": (i64, []),
     "vs_set_option": (i32, [C.c_char_p, i64]),
+    "vs_debug_batch_groupmins": (i32, [u64, f32p, i32, i32, f32p, i64, i64p, i32p, f64p]),
 }
 
 

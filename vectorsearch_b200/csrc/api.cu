@@ -27,7 +27,8 @@ static std::atomic<int64_t> g_adc_fast_cap{4096};         // candidate-list entr
 static std::atomic<int64_t> g_batch_min_queries{3};        // query batches at least this large use batch.cu
 static std::atomic<int64_t> g_batch_min_rows{16384};       // ... on segments at least this long
 static std::atomic<int64_t> g_batch_gm_bytes{int64_t(1) << 30};  // group-minima scratch per query chunk
-static std::atomic<int64_t> g_batch_warp_min_q{512};       // batches this large select with one warp per query
+static std::atomic<int64_t> g_batch_warp_min_q{0};         // > 0: batches this large always select with one warp per query (tests)
+static std::atomic<int64_t> g_batch_group{0};               // 0 = automatic rows per nomination group, else 16 / 32 / 64
 static std::atomic<int64_t> g_batch_fp16{1};                // nominate on fp16 operand copies (0: the fp32 rows as tf32)
 static int g_sms = 0;
 static std::mutex g_mu;
@@ -378,7 +379,8 @@ static bool batch_wanted(const Segment* s, int nq, bool cosine) {
 
 static int plan_batch(const Segment* s, int k, bool cosine, bool half, BatchLaunch* out) {
   const int ln = lanes();
-  const uint64_t key = occ_key(cosine ? 31 : 30, s->d, ln, k, half ? 1 : 0, (size_t)s->n);
+  const int go = (int)g_batch_group.load();
+  const uint64_t key = occ_key(cosine ? 31 : 30, s->d, ln, k, (half ? 1 : 0) + 2 * go, (size_t)s->n);
   {
     std::lock_guard<std::mutex> lk(g_scan_mu);
     auto it = g_batch_cache.find(key);
@@ -388,7 +390,7 @@ static int plan_batch(const Segment* s, int k, bool cosine, bool half, BatchLaun
     }
   }
   BatchLaunch L{};
-  L.n = s->n; L.d = s->d; L.lanes = ln; L.cosine = cosine; L.k = k; L.half = half; L.dp = (s->d + 7) & ~7;
+  L.n = s->n; L.d = s->d; L.lanes = ln; L.cosine = cosine; L.k = k; L.half = half; L.dp = (s->d + 7) & ~7; L.group_override = go;
   if (!batch_configure(L, g_sms)) return fail(VS_ECUDA, "batched scan cannot be resident for d=%d k=%d", s->d, k);
   std::lock_guard<std::mutex> lk(g_scan_mu);
   g_batch_cache[key] = L;
@@ -587,8 +589,13 @@ int32_t vs_debug_adc_stats(uint32_t* out8) { return vs::debug_adc_stats(out8) ==
 
 int32_t vs_set_option(const char* name, int64_t value) {
   if (!name) return fail(VS_EINVAL, "null option name");
+  if (!strcmp(name, "batch_group")) {
+    if (value != 0 && value != 16 && value != 32 && value != 64) return fail(VS_EINVAL, "batch_group must be 0, 16, 32 or 64");
+    g_batch_group.store(value);
+    return VS_OK;
+  }
   if (!strcmp(name, "batch_warp_min_queries")) {
-    if (value < 1) return fail(VS_EINVAL, "batch_warp_min_queries must be >= 1");
+    if (value < 0) return fail(VS_EINVAL, "batch_warp_min_queries must be >= 0");
     g_batch_warp_min_q.store(value);
     return VS_OK;
   }
@@ -1261,6 +1268,61 @@ static int batch_try_dev(ThreadCtx* c, cudaStream_t st, Segment* s, const float*
   Arena A(c->d_buf);
   RET(batch_run_dev(st, s, bp, cosine, d_q, nq, d_ids, d_scores, d_counts, out_stride, A.take<char>(sb), c->d_ticket));
   *done = true;
+  return VS_OK;
+}
+
+// Diagnostics for the batched path's nomination bound: runs the tensor-core stage only and returns, per query,
+// the group minima of a(q, x) (L2: |x|^2 - 2<q,x>; COSINE: -<q,x>/|x|) and the slack the selection adds.
+int32_t vs_debug_batch_groupmins(uint64_t h, const float* q, int32_t nq, int32_t metric, float* gm_out,
+                                 int64_t gm_capacity, int64_t* ngroups_out, int32_t* group_out, double* slack_out) {
+  Segment* s = seg_lookup(h);
+  RET(check_query_args(s, q, nq, 1, metric));
+  if (!ngroups_out || !group_out) return fail(VS_EINVAL, "null output pointer");
+  ThreadCtx* c;
+  RET(ctx_bind(&c));
+  const bool cosine = metric == VS_METRIC_COSINE;
+  if (s->n == 0 || !batch_supported(s->d, lanes(), cosine, s->n)) return fail(VS_ESTATE, "segment shape not eligible for the batched path");
+  bool ok = false, half = false;
+  RET(batch_prepare(c->stream, s, cosine, &ok, &half));
+  if (!ok) return fail(VS_ESTATE, "segment holds non-finite rows: the batched path is off");
+  BatchLaunch bp;
+  RET(plan_batch(s, 1, cosine, half, &bp));
+  *ngroups_out = bp.ngroups;
+  *group_out = bp.group;
+  if (!gm_out) return VS_OK;
+  if (nq > batch_chunk(bp, nq)) return fail(VS_EINVAL, "too many queries for one chunk");
+  if (gm_capacity < (int64_t)nq * bp.ngroups) return fail(VS_EINVAL, "gm_out too small");
+  const size_t qb = (size_t)nq * s->d * 4, sb = batch_scratch_need(bp, nq);
+  RET(ctx_reserve_dev(c, Arena::need({qb, sb})));
+  Arena A(c->d_buf);
+  float* dq = A.take<float>((size_t)nq * s->d);
+  char* scratch = A.take<char>(sb);
+  CK(cudaMemcpyAsync(dq, q, qb, cudaMemcpyHostToDevice, c->stream), "H2D q");
+  Arena B(scratch);
+  BatchLaunch L = bp;
+  const int m = cosine ? 1 : 0;
+  L.X = s->X; L.skip = s->skip; L.q = dq; L.nq = nq; L.tmX = half ? s->tmXh : s->tmX; L.x_scale = s->x_scale;
+  L.coef = static_cast<const float*>(s->ab[m]); L.stats = static_cast<const SegStats*>(s->stats[m]);
+  const int chunk = batch_chunk(bp, nq);
+  L.gm = B.take<float>((size_t)((chunk + 127) / 128 * 128) * bp.gm_stride);
+  L.fb = B.take<int32_t>(1 + 2 * (size_t)chunk);
+  L.partial = B.take<ulonglong2>((size_t)chunk * batch_partial_keys(bp, chunk));
+  L.qh = half ? B.take<char>((size_t)chunk * bp.dp * 2) : nullptr;
+  L.qinv = half ? B.take<float>((size_t)((chunk + 127) / 128 * 128)) : nullptr;
+  L.gemm_only = true;
+  CK(launch_batch(L, c->stream), "batched scan launch");
+  CK(cudaMemcpy2DAsync(gm_out, (size_t)bp.ngroups * 4, L.gm, (size_t)bp.gm_stride * 4, (size_t)bp.ngroups * 4, nq,
+                       cudaMemcpyDeviceToHost, c->stream), "D2H group minima");
+  CK(cudaStreamSynchronize(c->stream), "sync");
+  if (slack_out) {
+    float xmax2;
+    memcpy(&xmax2, &s->xmax2, 4);
+    for (int i = 0; i < nq; i++) {
+      double qq = 0.0;
+      for (int j = 0; j < s->d; j++) qq += (double)q[(size_t)i * s->d + j] * q[(size_t)i * s->d + j];
+      slack_out[i] = batch_slack_host(cosine, half, s->d, sqrt((double)xmax2), sqrt(qq));
+    }
+  }
   return VS_OK;
 }
 

@@ -232,7 +232,7 @@ query_convert_kernel(const float* __restrict__ Q, int nq, int nq_pad, int d, int
 constexpr int BQ_MAX_STAGES = 8;
 // HALF: operands are the fp16 copies (k-block = 64 halfs, kind::f16, twice the tensor rate and half the bytes);
 // qinv[query] undoes the power-of-two scaling of both copies.  Otherwise the fp32 data itself, read as tf32.
-template <bool STAT, bool HALF, bool COSINE>
+template <bool STAT, bool HALF, bool COSINE, int GROUP>
 __global__ void __launch_bounds__(BQ_THREADS, 1)
 batch_gemm_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmX,
                   const float* __restrict__ coef, const float* __restrict__ qinv, int64_t n, int num_kb, int nstages,
@@ -368,41 +368,62 @@ batch_gemm_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       }
       mbar_wait(tfull + a, (it >> 1) & 1);
       tc_fence_after();
-      float mins[2];
+      constexpr int NM = (BQ_N / 2) / GROUP;  // minima this thread produces per tile (GROUP = 16 / 32 / 64 rows)
+      float mins[NM];
 #pragma unroll
-      for (int g = 0; g < 2; g++) {
-        float m0 = inf, m1 = inf;
+      for (int i = 0; i < NM; i++) mins[i] = inf;
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
-          uint32_t v[32];
-          tc_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(a * BQ_N + ch * (BQ_N / 2) + g * 64 + h * 32), v);
-          tc_wait_ld();
-          tc_pin32(v);
-          const float4* p4 = reinterpret_cast<const float4*>(myc + g * 64 + h * 32);
+      for (int h = 0; h < 4; h++) {  // 32 columns per TMEM load
+        uint32_t v[32];
+        tc_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(a * BQ_N + ch * (BQ_N / 2) + h * 32), v);
+        tc_wait_ld();
+        tc_pin32(v);
+        const float4* p4 = reinterpret_cast<const float4*>(myc + h * 32);
+        float pm[2];  // columns 0..15 and 16..31 of this load
 #pragma unroll
-          for (int j = 0; j < 8; j++) {
-            const float4 p = p4[j];  // coefficients of four rows; same address in every lane: broadcast
-            if (COSINE) {            // a = c <q,x>; the per-query scale is applied after the minimum
-              m0 = fminf(m0, __uint_as_float(v[4 * j]) * p.x);
-              m1 = fminf(m1, __uint_as_float(v[4 * j + 1]) * p.y);
-              m0 = fminf(m0, __uint_as_float(v[4 * j + 2]) * p.z);
-              m1 = fminf(m1, __uint_as_float(v[4 * j + 3]) * p.w);
-            } else {                 // a = c - 2 <q,x>
-              m0 = fminf(m0, fmaf(__uint_as_float(v[4 * j]), m2, p.x));
-              m1 = fminf(m1, fmaf(__uint_as_float(v[4 * j + 1]), m2, p.y));
-              m0 = fminf(m0, fmaf(__uint_as_float(v[4 * j + 2]), m2, p.z));
-              m1 = fminf(m1, fmaf(__uint_as_float(v[4 * j + 3]), m2, p.w));
+        for (int hh = 0; hh < 2; hh++) {
+          float m0 = inf, m1 = inf;
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const float4 p = p4[hh * 4 + j];  // coefficients of four rows; same address in every lane: broadcast
+            const int c = hh * 16 + 4 * j;
+            if (COSINE) {  // a = c <q,x>; the per-query scale is applied after the minimum
+              m0 = fminf(m0, __uint_as_float(v[c]) * p.x);
+              m1 = fminf(m1, __uint_as_float(v[c + 1]) * p.y);
+              m0 = fminf(m0, __uint_as_float(v[c + 2]) * p.z);
+              m1 = fminf(m1, __uint_as_float(v[c + 3]) * p.w);
+            } else {       // a = c - 2 <q,x>
+              m0 = fminf(m0, fmaf(__uint_as_float(v[c]), m2, p.x));
+              m1 = fminf(m1, fmaf(__uint_as_float(v[c + 1]), m2, p.y));
+              m0 = fminf(m0, fmaf(__uint_as_float(v[c + 2]), m2, p.z));
+              m1 = fminf(m1, fmaf(__uint_as_float(v[c + 3]), m2, p.w));
             }
           }
+          pm[hh] = fminf(m0, m1);
         }
-        mins[g] = fminf(m0, m1);
-        if (COSINE) mins[g] *= qs;
+        if (GROUP == 16) {
+          mins[(2 * h) % NM] = pm[0];
+          mins[(2 * h + 1) % NM] = pm[1];
+        } else if (GROUP == 32) {
+          mins[h % NM] = fminf(pm[0], pm[1]);
+        } else {
+          mins[(h / 2) % NM] = fminf(mins[(h / 2) % NM], fminf(pm[0], pm[1]));
+        }
+      }
+      if (COSINE) {
+#pragma unroll
+        for (int i = 0; i < NM; i++) mins[i] *= qs;
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty + a);
-      float2* dst = reinterpret_cast<float2*>(gm + (size_t)(qb * BQ_M + lq * 32 + lane) * gm_stride + tile * 4 + ch * 2);
-      *dst = make_float2(mins[0], mins[1]);
+      float* dst = gm + (size_t)(qb * BQ_M + lq * 32 + lane) * gm_stride + tile * (BQ_N / GROUP) + ch * NM;
+      if (NM == 2) {
+        *reinterpret_cast<float2*>(dst) = make_float2(mins[0], mins[1]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < NM; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(mins[i], mins[(i + 1) % NM], mins[(i + 2) % NM], mins[(i + 3) % NM]);
+      }
     }
   }
   tc_fence_before();
@@ -416,10 +437,12 @@ batch_gemm_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 // ---- (3) threshold, candidate groups, exact ranking --------------------------------------------------------------
 // |a(q, x) - exact| <= slack.  Operand rounding: tf32 truncates both operands (2^-10 each), the fp16 copies are
 // rounded to nearest (2^-11 each, plus a subnormal floor that the power-of-two scaling keeps below 2^-37 relative);
-// d * 2^-20 covers the tensor core's fp32 accumulation whatever its internal alignment.
+// d * 2^-22 covers the tensor core's fp32 accumulation: twice the worst case of one truncation (round toward zero,
+// 2^-23 relative to the running sum) per accumulated product.  tests/test_gpu_parity.py::test_batch_nomination_bound
+// measures the actual deviation against this bound through vs_debug_batch_groupmins.
 __host__ __device__ __forceinline__ double batch_slack(bool cosine, bool half, int d, double xmax, double qn) {
   const double c1 = (half ? (1.0 / 1024.0) * 1.01 + sqrt((double)d) * (1.0 / 68719476736.0) : (1.0 / 512.0) * 1.02) +
-                    (double)d * (1.0 / 1048576.0);
+                    (double)d * (1.0 / 4194304.0);
   const double c2 = (double)(d + 64) * (1.0 / 8388608.0);                  // fp32 rounding of alpha, of a, of the reference sums
   if (cosine) return (c1 + c2) * qn;
   return 2.0 * c1 * xmax * qn + c2 * (xmax + qn) * (xmax + qn);
@@ -430,17 +453,17 @@ __device__ __forceinline__ void batch_list_fallback(int32_t* fb, int nq_total, i
   if (atomicExch(fb + 1 + nq_total + qi, 1) == 0) fb[1 + atomicAdd(fb, 1)] = qi;
 }
 
-// grid (P, nq): CTA (p, qi) owns the p-th slice of the 64-row groups of query qi.
+// grid (P, nq): CTA (p, qi) owns the p-th slice of the row groups (gsz rows each) of query qi.
 template <int TPR, int U, bool COSINE, class TK>
 __global__ void __launch_bounds__(BQ_SELECT_THREADS)
 batch_select_kernel(const float* __restrict__ X, int64_t n, int d, const float* __restrict__ Q,
                     const uint8_t* __restrict__ skip, const float* __restrict__ gm, int64_t gm_stride,
-                    int64_t ngroups, const SegStats* __restrict__ stats, int half, int k, int kp, int cap,
+                    int64_t ngroups, int gsz, const SegStats* __restrict__ stats, int half, int k, int kp, int cap,
                     int32_t* __restrict__ fb, int nq_total, TopkOut out) {
   extern __shared__ __align__(128) ulonglong2 smem[];
   constexpr int L = TPR * 4;
   constexpr int RPB = (32 / TPR) * U;  // rows per scoring batch
-  constexpr int BPG = 64 / RPB;        // batches per group
+  const int BPG = gsz / RPB;           // scoring batches per group (the host keeps gsz >= RPB)
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int nw = blockDim.x >> 5;
@@ -485,7 +508,7 @@ batch_select_kernel(const float* __restrict__ X, int64_t n, int d, const float* 
   // phase 1: T = an upper bound of the k-th smallest group minimum of this slice
   const int64_t g0 = ngroups * blockIdx.x / gridDim.x, g1 = ngroups * (blockIdx.x + 1) / gridDim.x;
   float tau = __int_as_float(0x7f800000);
-  if (k <= BQ_TMIN_MAX_K) {
+  if (k <= BQ_TMIN_MAX_K && k <= (int)blockDim.x) {
     // small k: the k-th smallest of the per-thread minima.  The minima belong to distinct groups, so k of
     // them lie at or below it -- a valid bound, and nearly the exact one because the few best groups
     // rarely share a thread.  One strided pass, one 256-way rank count.
@@ -567,11 +590,11 @@ batch_select_kernel(const float* __restrict__ X, int64_t n, int d, const float* 
   // phase 3: exact scores of the candidate groups' rows, ranked like scan.cu.  All their lines are requested
   // into L2 first, so the scoring rounds below do not each wait on HBM.
   {
-    const int lpg = d >> 1;  // 128-byte lines per 64-row group
+    const int lpg = (gsz * d) >> 5;  // 128-byte lines per group
     const char* xb = reinterpret_cast<const char*>(X);
     const int64_t xbytes = n * (int64_t)d * 4;
     for (int i = threadIdx.x; i < cnt * lpg; i += blockDim.x) {
-      const int64_t off = (int64_t)list[i / lpg] * 64 * d * 4 + (int64_t)(i % lpg) * 128;
+      const int64_t off = (int64_t)list[i / lpg] * gsz * d * 4 + (int64_t)(i % lpg) * 128;
       if (off < xbytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(xb + off));
     }
   }
@@ -583,7 +606,7 @@ batch_select_kernel(const float* __restrict__ X, int64_t n, int d, const float* 
   uint64_t seen_hi = KEY_EMPTY64, seen_lo = KEY_EMPTY64;
   const int total = cnt * BPG;
   for (int b = warp; b < total; b += nw) {
-    const int64_t row_base = (int64_t)list[b / BPG] * 64 + (int64_t)(b % BPG) * RPB;
+    const int64_t row_base = (int64_t)list[b / BPG] * gsz + (int64_t)(b % BPG) * RPB;
     if (row_base >= n) continue;
     scan_batch_ldg<TPR, U, COSINE, TK>(X, n, d, q, qs, skip, row_base, nv, ub, qq, qn, fthr, tk, lane);
     if (tk.thr.hi != seen_hi || tk.thr.lo != seen_lo) {
@@ -602,13 +625,13 @@ template <int TPR, int U, bool COSINE>
 __global__ void __launch_bounds__(BQ_SELECT_THREADS)
 batch_select_warp_kernel(const float* __restrict__ X, int64_t n, int d, const float* __restrict__ Q,
                          const uint8_t* __restrict__ skip, const float* __restrict__ gm, int64_t gm_stride,
-                         int64_t ngroups, const SegStats* __restrict__ stats, int half, int k, int cap,
+                         int64_t ngroups, int gsz, const SegStats* __restrict__ stats, int half, int k, int cap,
                          int32_t* __restrict__ fb, int nq, int64_t* __restrict__ ids, double* __restrict__ scores,
                          int32_t* __restrict__ counts, int64_t id_base, int64_t out_stride) {
   extern __shared__ __align__(128) ulonglong2 smem[];
   constexpr int L = TPR * 4;
   constexpr int RPB = (32 / TPR) * U;
-  constexpr int BPG = 64 / RPB;
+  const int BPG = gsz / RPB;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int qi = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -688,11 +711,11 @@ batch_select_warp_kernel(const float* __restrict__ X, int64_t n, int d, const fl
   }
   __syncwarp();
   {
-    const int lpg = d >> 1;  // 128-byte lines per 64-row group
+    const int lpg = (gsz * d) >> 5;  // 128-byte lines per group
     const char* xb = reinterpret_cast<const char*>(X);
     const int64_t xbytes = n * (int64_t)d * 4;
     for (int i = lane; i < cnt * lpg; i += 32) {
-      const int64_t off = (int64_t)list[i / lpg] * 64 * d * 4 + (int64_t)(i % lpg) * 128;
+      const int64_t off = (int64_t)list[i / lpg] * gsz * d * 4 + (int64_t)(i % lpg) * 128;
       if (off < xbytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(xb + off));
     }
   }
@@ -704,7 +727,7 @@ batch_select_warp_kernel(const float* __restrict__ X, int64_t n, int d, const fl
   uint64_t seen_hi = KEY_EMPTY64, seen_lo = KEY_EMPTY64;
   const int total = cnt * BPG;
   for (int b = 0; b < total; b++) {
-    const int64_t row_base = (int64_t)list[b / BPG] * 64 + (int64_t)(b % BPG) * RPB;
+    const int64_t row_base = (int64_t)list[b / BPG] * gsz + (int64_t)(b % BPG) * RPB;
     if (row_base >= n) continue;
     scan_batch_ldg<TPR, U, COSINE, WarpTopKReg>(X, n, d, q, qs, skip, row_base, nv, ub, qq, qn, fthr, tk, lane);
     if (tk.thr.hi != seen_hi || tk.thr.lo != seen_lo) {
@@ -805,6 +828,9 @@ bool batch_encode_segment_map(void* tm128, const void* X, int64_t n, int d, int6
   return encode_rows_map(reinterpret_cast<CUtensorMap*>(tm128), X, n, d, pitch, half, BQ_N);
 }
 
+// host copy of the device-side bound, for diagnostics
+double batch_slack_host(bool cosine, bool half, int d, double xmax, double qn) { return batch_slack(cosine, half, d, xmax, qn); }
+
 bool batch_supported(int d, int lanes, bool cosine, int64_t n) {
   if (!scan_is_streaming(d, lanes, cosine)) return false;  // the re-score uses the streaming row scorer
   if (d < 32 || d > 65536) return false;
@@ -820,9 +846,9 @@ static cudaError_t set_smem_attr(K kern, size_t smem_max) {
 }
 constexpr size_t BQ_SELECT_SMEM_MAX = 220 * 1024, BQ_SELW_SMEM_MAX = 96 * 1024;
 
-typedef void (*SelectKern)(const float*, int64_t, int, const float*, const uint8_t*, const float*, int64_t, int64_t,
+typedef void (*SelectKern)(const float*, int64_t, int, const float*, const uint8_t*, const float*, int64_t, int64_t, int,
                            const SegStats*, int, int, int, int, int32_t*, int, TopkOut);
-typedef void (*SelectWarpKern)(const float*, int64_t, int, const float*, const uint8_t*, const float*, int64_t, int64_t,
+typedef void (*SelectWarpKern)(const float*, int64_t, int, const float*, const uint8_t*, const float*, int64_t, int64_t, int,
                                const SegStats*, int, int, int, int32_t*, int, int64_t*, double*, int32_t*, int64_t, int64_t);
 static SelectWarpKern pick_select_warp(int TPR, bool cosine) {
   if (cosine) return TPR == 4 ? batch_select_warp_kernel<4, 1, true> : (TPR == 2 ? batch_select_warp_kernel<2, 1, true> : batch_select_warp_kernel<1, 1, true>);
@@ -849,20 +875,45 @@ static FallbackKern pick_fallback(int TPR, bool cosine, int k) {
 
 typedef void (*GemmKern)(const CUtensorMap, const CUtensorMap, const float*, const float*, int64_t, int, int, int, int64_t,
                          float*, int64_t);
-static GemmKern pick_gemm(bool stat, bool half, bool cosine) {
+template <int GROUP>
+static GemmKern pick_gemm_g(bool stat, bool half, bool cosine) {
   if (stat) {
-    if (half) return cosine ? batch_gemm_kernel<true, true, true> : batch_gemm_kernel<true, true, false>;
-    return cosine ? batch_gemm_kernel<true, false, true> : batch_gemm_kernel<true, false, false>;
+    if (half) return cosine ? batch_gemm_kernel<true, true, true, GROUP> : batch_gemm_kernel<true, true, false, GROUP>;
+    return cosine ? batch_gemm_kernel<true, false, true, GROUP> : batch_gemm_kernel<true, false, false, GROUP>;
   }
-  if (half) return cosine ? batch_gemm_kernel<false, true, true> : batch_gemm_kernel<false, true, false>;
-  return cosine ? batch_gemm_kernel<false, false, true> : batch_gemm_kernel<false, false, false>;
+  if (half) return cosine ? batch_gemm_kernel<false, true, true, GROUP> : batch_gemm_kernel<false, true, false, GROUP>;
+  return cosine ? batch_gemm_kernel<false, false, true, GROUP> : batch_gemm_kernel<false, false, false, GROUP>;
+}
+static GemmKern pick_gemm(bool stat, bool half, bool cosine, int group) {
+  return group == 16 ? pick_gemm_g<16>(stat, half, cosine) : (group == 32 ? pick_gemm_g<32>(stat, half, cosine) : pick_gemm_g<64>(stat, half, cosine));
+}
+
+// dynamic shared memory of batch_select_kernel with nw warps: collectors, group list, query
+static size_t batch_select_smem(const BatchLaunch& L, int nw) {
+  size_t coll = (size_t)nw * topk_warp_smem(L.kp);
+  const size_t b3 = topk_block_smem(L.k, L.kp, nw);
+  if (b3 > coll) coll = b3;
+  coll = (coll + 15) & ~size_t(15);
+  return coll + (size_t)((L.cap + 3) & ~3) * 4 + (((size_t)L.d * 4 + 15) & ~size_t(15));
 }
 
 bool batch_configure(BatchLaunch& L, int sms) {
   L.kp = topk_pad(L.k);
   L.tiles = (L.n + BQ_N - 1) / BQ_N;
-  L.ngroups = (L.n + 63) / 64;
-  L.gm_stride = L.tiles * 4;
+  // Rows per nomination group: small groups cost group-minima traffic (2 * 4 n / G bytes per query, written then
+  // read), large ones cost re-score traffic (about 1.3 k + 3 candidate groups of G * d * 4 bytes per query).
+  {
+    const double kc = 1.3 * L.k + 3.0;
+    // (measured: the minima cost about 1.5x their bytes -- short scattered stores in the epilogue)
+    const double gopt = 1.5 * sqrt(2.0 * (double)L.n / (kc * (double)L.d));
+    int g = gopt < 23.0 ? 16 : (gopt < 46.0 ? 32 : 64);
+    const int rpb = (32 / (L.lanes / 4)) * (L.cosine ? 1 : 2);  // rows per scoring batch of the re-score
+    if (g < rpb) g = rpb;
+    if (L.group_override == 16 || L.group_override == 32 || L.group_override == 64) g = L.group_override < rpb ? rpb : L.group_override;
+    L.group = g;
+  }
+  L.ngroups = (L.n + L.group - 1) / L.group;
+  L.gm_stride = L.tiles * (BQ_N / L.group);
   // resident query block when it leaves room for at least 3 row-block stages, else both operands stream
   {
     const int kbe = L.half ? 64 : 32;
@@ -878,13 +929,8 @@ bool batch_configure(BatchLaunch& L, int sms) {
   }
   // candidate groups per select CTA: the k-th smallest group minimum admits about k groups, the slack a few more
   L.cap = 4 * L.k + 256;
-  const int nw = BQ_SELECT_THREADS / 32;
-  size_t coll = (size_t)nw * topk_warp_smem(L.kp);
-  const size_t b3 = topk_block_smem(L.k, L.kp, nw);
-  if (b3 > coll) coll = b3;
-  coll = (coll + 15) & ~size_t(15);
   for (;;) {
-    L.select_smem = coll + (size_t)((L.cap + 3) & ~3) * 4 + (((size_t)L.d * 4 + 15) & ~size_t(15));
+    L.select_smem = batch_select_smem(L, BQ_SELECT_THREADS / 32);
     if (L.select_smem <= 200 * 1024 || L.cap <= L.k + 64) break;
     L.cap = L.cap / 2 > L.k + 64 ? L.cap / 2 : L.k + 64;
   }
@@ -903,7 +949,7 @@ bool batch_configure(BatchLaunch& L, int sms) {
   const int TPR = L.lanes / 4;
   {
     cudaError_t e;
-    e = set_smem_attr(pick_gemm(L.gemm_stat, L.half, L.cosine), BQ_GEMM_SMEM_BUDGET);
+    e = set_smem_attr(pick_gemm(L.gemm_stat, L.half, L.cosine, L.group), BQ_GEMM_SMEM_BUDGET);
     if (e != cudaSuccess) return false;
   }
   if (set_smem_attr(pick_select(TPR, L.cosine, L.k), BQ_SELECT_SMEM_MAX) != cudaSuccess) return false;
@@ -947,22 +993,30 @@ cudaError_t launch_batch(const BatchLaunch& L, cudaStream_t st) {
   if ((e = cudaMemsetAsync(L.fb, 0, sizeof(int32_t) * (1 + 2 * (size_t)L.nq), st)) != cudaSuccess) return e;
   count_launch();
   const int grid = nqb * nsplit;
-  pick_gemm(L.gemm_stat, L.half, L.cosine)<<<grid, BQ_THREADS, L.gemm_smem, st>>>(tmQ, tmX, L.coef, L.qinv, L.n, num_kb,
+  pick_gemm(L.gemm_stat, L.half, L.cosine, L.group)<<<grid, BQ_THREADS, L.gemm_smem, st>>>(tmQ, tmX, L.coef, L.qinv, L.n, num_kb,
                                                                                  L.gemm_stages, nqb, L.tiles, L.gm, L.gm_stride);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  if (L.gemm_only) return cudaSuccess;  // diagnostics: group minima only
   const int TPR = L.lanes / 4;
   const int P = batch_select_ctas(L, L.nq);
   TopkOut o{L.partial, L.ctrl, L.partial_keys, L.ids_out, L.scores_out, L.counts_out, L.id_base, 0,
             L.out_stride > 0 ? L.out_stride : L.k};
   count_launch();
-  if (L.selw_smem != 0 && L.nq >= L.warp_min_q) {
+  // Selection is latency-bound per query, so the batch decides how many warps a query gets: about 16 resident
+  // warps per SM in total -- 8 per query for small batches (and P CTAs per query), down to one warp per query.
+  int W = 8;
+  while (W > 1 && (int64_t)L.nq * W > 16 * (int64_t)L.sms) W >>= 1;
+  const bool force_warp = L.warp_min_q > 0 && L.nq >= L.warp_min_q;
+  if (L.selw_smem != 0 && (W == 1 || force_warp)) {
     const int wpb = BQ_SELECT_THREADS / 32;
     pick_select_warp(TPR, L.cosine)<<<(L.nq + wpb - 1) / wpb, BQ_SELECT_THREADS, L.selw_smem, st>>>(
-        L.X, L.n, L.d, L.q, L.skip, L.gm, L.gm_stride, L.ngroups, L.stats, L.half ? 1 : 0, L.k, L.cap, L.fb, L.nq,
+        L.X, L.n, L.d, L.q, L.skip, L.gm, L.gm_stride, L.ngroups, L.group, L.stats, L.half ? 1 : 0, L.k, L.cap, L.fb, L.nq,
         L.ids_out, L.scores_out, L.counts_out, L.id_base, L.out_stride > 0 ? L.out_stride : L.k);
-  } else
-  pick_select(TPR, L.cosine, L.k)<<<dim3(P, L.nq), BQ_SELECT_THREADS, L.select_smem, st>>>(
-      L.X, L.n, L.d, L.q, L.skip, L.gm, L.gm_stride, L.ngroups, L.stats, L.half ? 1 : 0, L.k, L.kp, L.cap, L.fb, L.nq, o);
+  } else {
+    if (W < 2) W = 2;
+    pick_select(TPR, L.cosine, L.k)<<<dim3(P, L.nq), 32 * W, batch_select_smem(L, W), st>>>(
+        L.X, L.n, L.d, L.q, L.skip, L.gm, L.gm_stride, L.ngroups, L.group, L.stats, L.half ? 1 : 0, L.k, L.kp, L.cap, L.fb, L.nq, o);
+  }
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   count_launch();
   const int gy = L.nq < BQ_FB_SLOTS ? L.nq : BQ_FB_SLOTS;

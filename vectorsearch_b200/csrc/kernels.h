@@ -78,15 +78,19 @@ struct BatchLaunch {
   int32_t* counts_out;
   int64_t id_base;
   int64_t out_stride;
+  int group_override;    // 0 = choose the rows per nomination group (16 / 32 / 64) from the shape
+  bool gemm_only;        // diagnostics: stop after the group minima
   int warp_min_q;        // chunks of at least this many queries select with one warp per query (k <= 32)
   // filled by batch_configure:
   int64_t tiles, ngroups, gm_stride;
+  int group;             // rows per nomination group
   int cap, sms, fb_gx, fb_threads;
   size_t gemm_smem, select_smem, selw_smem, fb_smem;
   bool gemm_stat;        // query block resident in shared memory (short vectors)
   int gemm_stages;
 };
 bool batch_supported(int d, int lanes, bool cosine, int64_t n);
+double batch_slack_host(bool cosine, bool half, int d, double xmax, double qn);
 bool batch_encode_segment_map(void* tm128, const void* rows, int64_t n, int d, int64_t pitch, bool half);
 cudaError_t launch_row_convert(const float* X, int64_t n, int d, int dp, float sx, void* Xh, int sms, cudaStream_t st);
 bool batch_configure(BatchLaunch& L, int sms);          // from (n, d, lanes, cosine, k, half)
