@@ -321,6 +321,37 @@ def test_batch_nomination_bound(vs, oracle, mode, metric, n, d, scale):
         vs.set_option("batch_fp16", 1)
 
 
+def test_sharded_coordinator_pipelined_streams(vs, oracle):
+    """The multi-GPU coordinator alternates independent queries between two streams (one libvsgpu scratch set
+    per stream); with one rank the collective drops out and the rest is testable here.  Results must equal
+    the oracle's for every query, whatever overlapped."""
+    import torch
+
+    from vectorsearch_b200.sharded import ShardedSegment
+
+    n, d, nq = 300_000, 128, 24
+    rows = oracle.gen_rows(42, 0, n, d)
+    qs = oracle.gen_rows(43, 0, nq, d)
+    seg = vs.Segment.upload(rows, id_base=5_000_000)
+    try:
+        sh = ShardedSegment(seg, 0, 1)
+        q_dev = torch.from_numpy(qs).cuda()
+        torch.cuda.synchronize()
+        kept = []
+        for i in range(nq):
+            ids, sc, cn, stream = sh.bruteforce_topk_pipelined(q_dev[i:i + 1], 1, 10)
+            with torch.cuda.stream(stream):
+                kept.append((ids.clone(), sc.clone(), cn.clone()))
+        sh.drain()
+        torch.cuda.synchronize()
+        for i in range(nq):
+            oi, os_, _ = oracle.bruteforce_topk(rows, qs[i], 10, threads=4)
+            assert kept[i][2].item() == 10
+            assert np.array_equal(kept[i][0].cpu().numpy()[0], oi + 5_000_000) and _same(kept[i][1].cpu().numpy()[0], os_)
+    finally:
+        seg.free()
+
+
 def test_empty_segment_and_bad_args(vs):
     seg = vs.Segment.upload(np.zeros((0, 8), np.float32))
     try:

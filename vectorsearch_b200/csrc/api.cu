@@ -68,18 +68,71 @@ struct ThreadCtx {
   size_t ticket_cap = 0;
   unsigned int* d_fs = nullptr;  // [queries][FS_WORDS] ADC fast-scan histogram + control, zero between launches
   size_t fs_cap = 0;
+  // The device scratch above is the ACTIVE set.  Work enqueued on different caller streams (the *_dev entry
+  // points) may overlap on the GPU, so every stream gets its own set: ctx_use_stream parks the active set in
+  // its slot and activates the one of the requested stream.
+  struct DevScratch {
+    void* key = nullptr;  // the stream this set belongs to
+    bool used = false;
+    void* d_buf = nullptr;
+    size_t d_cap = 0;
+    unsigned long long* d_ticket = nullptr;
+    size_t ticket_cap = 0;
+    unsigned int* d_fs = nullptr;
+    size_t fs_cap = 0;
+  };
+  static constexpr int MAX_SLOTS = 4;
+  DevScratch slots[MAX_SLOTS];
+  int active = -1;
+  void park() {
+    if (active < 0) return;
+    DevScratch& a = slots[active];
+    a.d_buf = d_buf; a.d_cap = d_cap; a.d_ticket = d_ticket; a.ticket_cap = ticket_cap; a.d_fs = d_fs; a.fs_cap = fs_cap;
+  }
+  void activate(int i) {
+    const DevScratch& a = slots[i];
+    d_buf = a.d_buf; d_cap = a.d_cap; d_ticket = a.d_ticket; ticket_cap = a.ticket_cap; d_fs = a.d_fs; fs_cap = a.fs_cap;
+    active = i;
+  }
   ~ThreadCtx() {
     // process teardown: the context may already be gone; ignore errors
     if (device >= 0 && g_device.load() == device) {
-      if (d_buf) cudaFree(d_buf);
+      park();
+      for (DevScratch& a : slots) {
+        if (a.d_buf) cudaFree(a.d_buf);
+        if (a.d_ticket) cudaFree(a.d_ticket);
+        if (a.d_fs) cudaFree(a.d_fs);
+      }
       if (h_buf) cudaFreeHost(h_buf);
-      if (d_ticket) cudaFree(d_ticket);
-      if (d_fs) cudaFree(d_fs);
       if (stream) cudaStreamDestroy(stream);
     }
   }
 };
 static thread_local ThreadCtx t_ctx;
+
+// Makes the device scratch of `stream` the active one (at most MAX_SLOTS streams per host thread; beyond that
+// the least recently bound caller stream is drained and its set is handed over).
+static int ctx_use_stream(ThreadCtx* c, void* stream) {
+  if (c->active >= 0 && c->slots[c->active].key == stream) return VS_OK;
+  c->park();
+  int free_slot = -1;
+  for (int i = 0; i < ThreadCtx::MAX_SLOTS; i++) {
+    if (c->slots[i].used && c->slots[i].key == stream) {
+      c->activate(i);
+      return VS_OK;
+    }
+    if (!c->slots[i].used && free_slot < 0) free_slot = i;
+  }
+  if (free_slot < 0) {  // recycle a caller-stream slot (never slot 0, the thread's own stream)
+    free_slot = 1 + (c->active >= 1 ? c->active % (ThreadCtx::MAX_SLOTS - 1) : 0);
+    cudaError_t e = cudaStreamSynchronize(static_cast<cudaStream_t>(c->slots[free_slot].key));
+    if (e != cudaSuccess) return cuda_fail(e, "sync (scratch hand-over)");
+  }
+  c->slots[free_slot].used = true;
+  c->slots[free_slot].key = stream;
+  c->activate(free_slot);
+  return VS_OK;
+}
 
 int ctx_bind(ThreadCtx** out) {
   const int dev = g_device.load();
@@ -94,7 +147,7 @@ int ctx_bind(ThreadCtx** out) {
     if (e != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
   }
   *out = &c;
-  return VS_OK;
+  return ctx_use_stream(&c, c.stream);
 }
 
 static int ctx_reserve_dev(ThreadCtx* c, size_t bytes) {
@@ -1333,6 +1386,7 @@ int32_t vs_bruteforce_topk_dev(uint64_t h, const float* d_q, int32_t nq, int32_t
   if (!d_ids || !d_scores || !d_counts) return fail(VS_EINVAL, "null output pointer");
   ThreadCtx* c;
   RET(ctx_bind(&c));
+  RET(ctx_use_stream(c, stream));
   if (s->n == 0) return fail(VS_EINVAL, "empty segment: use the host variant");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   bool done = false;
@@ -1359,6 +1413,7 @@ int32_t vs_bruteforce_topk_packed_dev(uint64_t h, const float* d_q, int32_t nq, 
   if (!d_pack || !d_counts) return fail(VS_EINVAL, "null output pointer");
   ThreadCtx* c;
   RET(ctx_bind(&c));
+  RET(ctx_use_stream(c, stream));
   if (s->n == 0) return fail(VS_EINVAL, "empty segment: use the host variant");
   bool done = false;
   RET(batch_try_dev(c, static_cast<cudaStream_t>(stream), s, d_q, nq, k, metric, d_pack, reinterpret_cast<double*>(d_pack + k),
@@ -1408,6 +1463,7 @@ int32_t vs_adc_topk_dev(uint64_t h, const float* d_q, int32_t nq, int32_t n_cand
   if (s->M == 0) return fail(VS_ESTATE, "segment has no PQ attached");
   ThreadCtx* c;
   RET(ctx_bind(&c));
+  RET(ctx_use_stream(c, stream));
   if (s->n == 0) return fail(VS_EINVAL, "empty segment: use the host variant");
   AdcPlan p;
   RET(plan_adc(s, nq, n_cand, &p));
@@ -1438,6 +1494,7 @@ int32_t vs_adc_rerank_topk_dev(uint64_t h, const float* d_q, int32_t nq, int32_t
   if (s->M == 0) return fail(VS_ESTATE, "segment has no PQ attached");
   ThreadCtx* c;
   RET(ctx_bind(&c));
+  RET(ctx_use_stream(c, stream));
   if (s->n == 0) return fail(VS_EINVAL, "empty segment: use the host variant");
   AdcPlan p;
   RET(plan_adc(s, nq, n_cand, &p));

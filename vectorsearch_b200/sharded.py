@@ -71,7 +71,7 @@ def gather_and_merge_host(ids: np.ndarray, scores: np.ndarray, count: int, k: in
 class ShardedSegment:
     """One rank's row range of a corpus + the collective merge (torch.distributed)."""
 
-    def __init__(self, segment, rank: int, world: int, group=None):
+    def __init__(self, segment, rank: int, world: int, group=None, slots: int = 2):
         import torch
         import torch.distributed as dist
 
@@ -80,9 +80,14 @@ class ShardedSegment:
         self.lib = L.load()
         self.dev = torch.device("cuda", torch.cuda.current_device())
         self._bufs = {}
+        # query batches are independent: consecutive ones alternate between `slots` streams (each with its
+        # own buffers; libvsgpu keeps one scratch set per stream), so the latency of one batch's all-gather
+        # and merge hides behind the next batch's scan
+        self._streams = [torch.cuda.Stream(device=self.dev) for _ in range(max(1, slots))]
+        self._next = 0
 
-    def _buffers(self, nq: int, k: int):
-        key = (nq, k)
+    def _buffers(self, nq: int, k: int, slot: int = -1):
+        key = (nq, k, slot)
         if key not in self._bufs:
             t, dev, w = self.torch, self.dev, self.world
             self._bufs[key] = dict(
@@ -93,13 +98,30 @@ class ShardedSegment:
                 out_c=t.empty((nq,), dtype=t.int32, device=dev))
         return self._bufs[key]
 
-    def bruteforce_topk_dev(self, d_q, nq: int, k: int, metric: int = METRIC_L2):
+    def bruteforce_topk_pipelined(self, d_q, nq: int, k: int, metric: int = METRIC_L2):
+        """Same as bruteforce_topk_dev, enqueued on the next of the coordinator's streams.  Returns
+        (ids, scores, counts, stream); the tensors are valid once `stream` has been waited on (drain())
+        and until the same slot comes round again.  d_q must already be complete on the device."""
+        t = self.torch
+        slot = self._next
+        self._next = (self._next + 1) % len(self._streams)
+        with t.cuda.stream(self._streams[slot]):
+            ids, sc, cn = self.bruteforce_topk_dev(d_q, nq, k, metric, slot)
+        return ids, sc, cn, self._streams[slot]
+
+    def drain(self):
+        """Make torch's current stream wait for everything enqueued through bruteforce_topk_pipelined."""
+        cur = self.torch.cuda.current_stream()
+        for s in self._streams:
+            cur.wait_stream(s)
+
+    def bruteforce_topk_dev(self, d_q, nq: int, k: int, metric: int = METRIC_L2, slot: int = -1):
         """Device-resident query batch [nq][d] -> (ids [nq][k], scores [nq][k], counts [nq]) tensors,
         identical on every rank.  Three launches per batch on torch's current stream -- local scan
         (writes ids and score bit patterns straight into the packed send buffer), ONE all-gather,
         one merge of the rank-ordered lists -- and nothing synchronises."""
         t = self.torch
-        b = self._buffers(nq, k)
+        b = self._buffers(nq, k, slot)
         st = t.cuda.current_stream().cuda_stream
         check(self.lib.vs_bruteforce_topk_packed_dev(self.seg.handle, d_q.data_ptr(), nq, k, metric,
                                                      b["pack"].data_ptr(), b["cn"].data_ptr(), st))
