@@ -150,6 +150,17 @@ int32_t vs_bruteforce_topk_packed_dev(uint64_t h, const float* d_q, int32_t nq, 
  * (J/fdb/FdbVectorIndex.java:432-437 with shards in the role of segments). */
 int32_t vs_merge_packed_dev(const int64_t* d_gath, int32_t world, int32_t nq, int32_t k, int32_t descending,
                             int64_t* d_ids_out, double* d_scores_out, int32_t* d_counts_out, void* stream);
+/* Cross-shard ADC + re-rank (config C4 on several GPUs).  The reference re-ranks the GLOBAL first n_cand rows
+ * by approximate distance (J/fdb/FdbVectorIndex.java:769,820-828), so a shard ships its own n_cand candidates
+ * WITH their exact scores: d_pack is [nq][4][n_cand] int64 = ids | approximate distance bits | exact score
+ * bits | state (1 scored, 0 dropped by the re-rank: deleted or gid missing, -1 empty slot). */
+int32_t vs_adc_rerank_packed_dev(uint64_t h, const float* d_q, int32_t nq, int32_t n_cand, int32_t metric,
+                                 int32_t normalize_on_read, int64_t* d_pack, void* stream);
+/* d_gath is the all-gathered [world][nq][4][n_cand] buffer.  Per query: the global first n_cand by
+ * (approximate distance, rank, position) -- shards are ascending row ranges, so that is the reference's
+ * stable order -- and of those the scored ones by exact score descending, ties in approximate order; first k. */
+int32_t vs_merge_adc_rerank_packed_dev(const int64_t* d_gath, int32_t world, int32_t nq, int32_t n_cand, int32_t k,
+                                       int64_t* d_ids_out, double* d_scores_out, int32_t* d_counts_out, void* stream);
 int32_t vs_merge_topk_dev(const int64_t* d_ids, const double* d_scores, int64_t total, int32_t k,
                           int64_t* d_ids_out, double* d_scores_out, int32_t* d_count_out, void* stream);
 /* number of kernels this library has launched so far in this process (for gpu_launches) */

@@ -150,3 +150,70 @@ def test_two_rank_gloo_merge_equals_single_segment(oracle, metric):
 
 def _q(oracle, d):
     return oracle.gen_floats(10, 0, d)
+
+
+def _adc_worker(rank, world, port, n, d, M, K, n_cand, k, q, qv):
+    """One rank of the cross-shard ADC + re-rank: the oracle stands in for the device kernels of the shard,
+    the exchange is the same single all-gather of the packed candidates, the merge is the host restatement
+    of vs_merge_adc_rerank_packed_dev."""
+    import torch
+    import torch.distributed as dist
+
+    from oracle import pyoracle
+    from vectorsearch_b200.sharded import merge_adc_rerank_host, shard_range
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        orc = pyoracle.get()
+        full = orc.gen_rows(9, 0, n, d)
+        full[n // 2:n // 2 + 20] = full[3]            # duplicates that straddle nothing but tie in both distances
+        full[5:25] = full[3]
+        cent = orc.pq_train(full[:2000], d, M, K, 2, 42)
+        lo, hi = shard_range(n, rank, world)
+        rows = full[lo:hi]
+        codes = orc.pq_encode_batch(cent, rows)
+        ci, ca = orc.adc_topn(orc.build_lut(cent, qv), codes, n_cand)
+        pack = np.zeros((4, n_cand), np.int64)
+        pack[3] = -1
+        c = len(ci)
+        pack[0, :c] = ci + lo
+        pack[1, :c] = np.asarray(ca, np.float64).view(np.int64)
+        for j in range(c):                             # exact score of every candidate, in candidate order
+            _, sc, _ = orc.rerank_topk(rows, qv, ci[j:j + 1], 1, 0)
+            pack[2, j] = np.asarray(sc[:1], np.float64).view(np.int64)[0]
+            pack[3, j] = 1
+        tp = torch.from_numpy(pack.reshape(-1))
+        gath = [torch.zeros_like(tp) for _ in range(world)]
+        dist.all_gather(gath, tp)
+        g = torch.stack(gath).numpy().reshape(world, 4, n_cand)
+        gi, gs = merge_adc_rerank_host(g, k)
+        q.put((rank, gi.tolist(), gs.view(np.uint64).tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_adc_rerank_equals_single_segment(oracle):
+    import torch.multiprocessing as mp
+
+    world, n, d, M, K, n_cand, k = 2, 3001, 16, 4, 16, 40, 7
+    ctx = mp.get_context("spawn")
+    queue = ctx.Queue()
+    port = _free_port()
+    qv = oracle.gen_floats(10, 0, d)
+    procs = [ctx.Process(target=_adc_worker, args=(r, world, port, n, d, M, K, n_cand, k, queue, qv)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted(queue.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    full = oracle.gen_rows(9, 0, n, d)
+    full[n // 2:n // 2 + 20] = full[3]
+    full[5:25] = full[3]
+    cent = oracle.pq_train(full[:2000], d, M, K, 2, 42)
+    codes = oracle.pq_encode_batch(cent, full)
+    ci, _ = oracle.adc_topn(oracle.build_lut(cent, qv), codes, n_cand)
+    ri, rs, _ = oracle.rerank_topk(full, qv, ci, k, 0)
+    for rank, gi, gs in got:
+        assert gi == ri.tolist() and gs == rs.view(np.uint64).tolist(), f"rank {rank}"

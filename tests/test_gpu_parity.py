@@ -352,6 +352,61 @@ def test_sharded_coordinator_pipelined_streams(vs, oracle):
         seg.free()
 
 
+@pytest.mark.parametrize("metric", [0, 1])
+@pytest.mark.parametrize("shards", [1, 2, 3])
+def test_adc_rerank_across_shards(vs, oracle, shards, metric):
+    """C4 on several GPUs, emulated with row-range shards resident on this one: every shard packs its ADC
+    candidates with their exact scores, the packs are concatenated in rank order (what the all-gather
+    produces) and merged.  Must equal the reference's single-segment result: global first n_cand by
+    approximate distance, re-ranked exactly (FdbVectorIndex.java:769,820-828,997-1043)."""
+    import torch
+
+    from vectorsearch_b200 import _lib as L
+    from vectorsearch_b200.sharded import merge_adc_rerank_host, shard_range
+
+    n, d, M, K, n_cand, k, nq = 60000, 64, 8, 64, 100, 10, 3
+    rows = oracle.gen_rows(42, 0, n, d)
+    rows[1000:1040] = rows[17]                      # duplicate rows: equal approximate AND exact distances
+    rows[40000:40030] = rows[17]
+    qs = oracle.gen_rows(43, 0, nq, d)
+    qs[0] = rows[17]
+    skip = np.zeros(n, np.uint8)
+    skip[[17, 1001, 40001, 59999]] = 1              # deleted rows keep their candidate slot, are not scored
+    cent = oracle.pq_train(rows[:5000], d, M, K, 3, 42)
+    codes = oracle.pq_encode_batch(cent, rows, threads=4)
+    lib = vs.load()
+    st = torch.cuda.current_stream().cuda_stream
+    segs, packs = [], []
+    try:
+        q_dev = torch.from_numpy(qs).cuda()
+        for r in range(shards):
+            lo, hi = shard_range(n, r, shards)
+            seg = vs.Segment.upload(rows[lo:hi], skip=skip[lo:hi], id_base=lo)
+            seg.attach_pq(cent, codes[lo:hi])
+            segs.append(seg)
+            pack = torch.empty((nq, 4, n_cand), dtype=torch.int64, device="cuda")
+            L.check(lib.vs_adc_rerank_packed_dev(seg.handle, q_dev.data_ptr(), nq, n_cand, metric, 0, pack.data_ptr(), st))
+            packs.append(pack)
+        gath = torch.stack(packs).contiguous()
+        ids = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+        sc = torch.empty((nq, k), dtype=torch.float64, device="cuda")
+        cn = torch.empty((nq,), dtype=torch.int32, device="cuda")
+        L.check(lib.vs_merge_adc_rerank_packed_dev(gath.data_ptr(), shards, nq, n_cand, k, ids.data_ptr(), sc.data_ptr(), cn.data_ptr(), st))
+        torch.cuda.synchronize()
+        ids, sc, cn, gath = ids.cpu().numpy(), sc.cpu().numpy(), cn.cpu().numpy(), gath.cpu().numpy()
+        for i in range(nq):
+            ci, _ = oracle.adc_topn(oracle.build_lut(cent, qs[i]), codes, n_cand)
+            ri, rs, _ = oracle.rerank_topk(rows, qs[i], ci, k, metric, skip=skip)
+            c = len(ri)
+            assert cn[i] == c
+            assert np.array_equal(ids[i, :c], ri) and _same(sc[i, :c], rs), (i, ids[i], ri)
+            hi_, hs_ = merge_adc_rerank_host(gath[:, i], k)   # the host restatement the gloo test uses
+            assert np.array_equal(hi_, ri) and _same(hs_, rs)
+    finally:
+        for seg in segs:
+            seg.free()
+
+
 def test_empty_segment_and_bad_args(vs):
     seg = vs.Segment.upload(np.zeros((0, 8), np.float32))
     try:

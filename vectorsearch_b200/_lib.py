@@ -63,6 +63,8 @@ SIGNATURES = {
     "vs_bruteforce_topk_packed_dev": (i32, [u64, vp, i32, i32, i32, vp, vp, vp]),
     "vs_merge_packed_dev": (i32, [vp, i32, i32, i32, i32, vp, vp, vp, vp]),
     "vs_merge_topk_dev": (i32, [vp, vp, i64, i32, vp, vp, vp, vp]),
+    "vs_adc_rerank_packed_dev": (i32, [u64, vp, i32, i32, i32, i32, vp, vp]),
+    "vs_merge_adc_rerank_packed_dev": (i32, [vp, i32, i32, i32, i32, vp, vp, vp, vp]),
     "vs_kernel_launch_count": (i64, []),
     "vs_set_option": (i32, [C.c_char_p, i64]),
     "vs_debug_batch_groupmins": (i32, [u64, f32p, i32, i32, f32p, i64, i64p, i32p, f64p]),

@@ -1445,6 +1445,58 @@ int32_t vs_merge_packed_dev(const int64_t* d_gath, int32_t world, int32_t nq, in
   return VS_OK;
 }
 
+// ADC top n_cand of this shard with the exact score of every candidate, packed for the cross-shard merge
+int32_t vs_adc_rerank_packed_dev(uint64_t h, const float* d_q, int32_t nq, int32_t n_cand, int32_t metric,
+                                 int32_t normalize_on_read, int64_t* d_pack, void* stream) {
+  (void)normalize_on_read;  // same expression with norm(q) hoisted (J/fdb/FdbVectorIndex.java:1006-1010)
+  Segment* s = seg_lookup(h);
+  RET(check_query_args(s, d_q, nq, n_cand, metric));
+  if (!d_pack) return fail(VS_EINVAL, "null output pointer");
+  if (s->M == 0) return fail(VS_ESTATE, "segment has no PQ attached");
+  ThreadCtx* c;
+  RET(ctx_bind(&c));
+  RET(ctx_use_stream(c, stream));
+  if (s->n == 0) return fail(VS_EINVAL, "empty segment: use the host variant");
+  AdcPlan p;
+  RET(plan_adc(s, nq, n_cand, &p));
+  const size_t pb = (size_t)nq * p.partial_keys * 16, lb = (size_t)nq * s->M * s->K * 8;
+  const size_t cib = (size_t)nq * n_cand * 8, ccb = (size_t)nq * 4, cdb = (size_t)nq * (p.cand_entries + p.extra_words) * 8;
+  if (pb + cdb > (size_t(1) << 31)) return fail(VS_EINVAL, "query batch too large for the stream variant");
+  const bool grow = Arena::need({pb, lb, cib, cib, ccb, cdb}) > c->d_cap || (size_t)nq > c->ticket_cap ||
+                    (p.fast && (size_t)nq > c->fs_cap);
+  RET(ctx_reserve_dev(c, Arena::need({pb, lb, cib, cib, ccb, cdb})));
+  RET(ctx_reserve_ticket(c, nq));
+  if (p.fast) RET(ctx_reserve_fs(c, nq));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (grow) CK(cudaStreamSynchronize(c->stream), "sync");
+  Arena A(c->d_buf);
+  ulonglong2* dpart = A.take<ulonglong2>((size_t)nq * p.partial_keys);
+  double* dlut = A.take<double>((size_t)nq * s->M * s->K);
+  int64_t* dcid = A.take<int64_t>((size_t)nq * n_cand);
+  double* dcap = A.take<double>((size_t)nq * n_cand);
+  int32_t* dccn = A.take<int32_t>(nq);
+  unsigned long long* dcand = A.take<unsigned long long>((size_t)nq * (p.cand_entries + p.extra_words));
+  RET(adc_dev(st, s, d_q, nq, n_cand, dlut, dcid, dcap, dccn, dpart, c->d_ticket, c->d_fs, dcand, p));
+  RankLaunch L{};
+  L.X = s->X; L.n = s->n; L.d = s->d; L.skip = s->skip; L.lanes = lanes(); L.q = d_q; L.nq = nq;
+  L.cand_ids = dcid; L.nc = n_cand; L.k = n_cand; L.metric = metric; L.id_base = s->id_base;
+  CK(launch_score_pack(L, dcap, dccn, d_pack, st), "score_pack launch");
+  return VS_OK;
+}
+
+int32_t vs_merge_adc_rerank_packed_dev(const int64_t* d_gath, int32_t world, int32_t nq, int32_t n_cand, int32_t k,
+                                       int64_t* d_ids_out, double* d_scores_out, int32_t* d_counts_out, void* stream) {
+  if (!d_gath || !d_ids_out || !d_scores_out || !d_counts_out) return fail(VS_EINVAL, "null pointer");
+  if (world <= 0 || nq <= 0 || n_cand <= 0) return fail(VS_EINVAL, "world, nq and n_cand must be positive");
+  if (k <= 0 || k > TOPK_MAX_K) return fail(VS_EINVAL, "k must be in 1..%d", TOPK_MAX_K);
+  if ((int64_t)world * n_cand > 8192) return fail(VS_EINVAL, "world * n_cand must be <= 8192");
+  ThreadCtx* c;
+  RET(ctx_bind(&c));
+  CK(launch_merge_adc_rerank(d_gath, world, nq, n_cand, k, d_ids_out, d_scores_out, d_counts_out,
+                             static_cast<cudaStream_t>(stream)), "merge launch");
+  return VS_OK;
+}
+
 int32_t vs_merge_topk_dev(const int64_t* d_ids, const double* d_scores, int64_t total, int32_t k,
                           int64_t* d_ids_out, double* d_scores_out, int32_t* d_count_out, void* stream) {
   if (!d_ids || !d_scores || !d_ids_out || !d_scores_out || !d_count_out || total <= 0) return fail(VS_EINVAL, "null pointer or empty input");

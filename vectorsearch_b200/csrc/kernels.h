@@ -116,6 +116,11 @@ struct RankLaunch {
   int32_t* counts_out;
 };
 cudaError_t launch_rank(const RankLaunch& L, cudaStream_t st);
+// cross-shard ADC + re-rank: per query int64[4][nc] = ids | approx bits | exact score bits | state
+cudaError_t launch_score_pack(const RankLaunch& L, const double* cand_approx, const int32_t* cand_counts, int64_t* pack,
+                              cudaStream_t st);
+cudaError_t launch_merge_adc_rerank(const int64_t* gath, int w, int nq, int nc, int k, int64_t* ids_out,
+                                    double* scores_out, int32_t* counts_out, cudaStream_t st);
 // stable sort by score descending of `total` (id, score) pairs, first k
 cudaError_t launch_merge(const int64_t* ids, const double* scores, int64_t total, int k,
                          int64_t* ids_out, double* scores_out, int32_t* count_out, cudaStream_t st);

@@ -174,6 +174,137 @@ merge_packed_kernel(const int64_t* __restrict__ gath, int w, int nq, int k, int 
   if (threadIdx.x == 0) counts_out[qi] = s_found;
 }
 
+// ---- cross-shard ADC + re-rank (one collective per query batch) -------------------------------------------
+// The reference re-ranks the GLOBAL first n_cand rows by approximate distance (searchSealedSegment,
+// J/fdb/FdbVectorIndex.java:769,820-828); re-ranking each shard's own candidates and merging the winners
+// would look at world x n_cand rows and can return different results.  So every shard ships its ADC
+// candidates together with their exact scores, packed per query as int64[4][nc]:
+//   ids | approximate distance bits | exact score bits | state (1 scored, 0 dropped at re-rank, -1 empty slot)
+// and after the all-gather every rank selects the global first nc by (approx, rank, position) and ranks
+// those that were scored by (exact score descending, approximate order).
+__global__ void __launch_bounds__(1024)
+score_pack_kernel(const float* __restrict__ X, int64_t n, int d, const uint8_t* __restrict__ skip, int lanes,
+                  const float* __restrict__ Q, const int64_t* __restrict__ cand_ids, const double* __restrict__ cand_approx,
+                  const int32_t* __restrict__ cand_counts, int nc, int cosine, int64_t id_base, int64_t* __restrict__ pack) {
+  const int qi = blockIdx.x;
+  const float* q = Q + (size_t)qi * d;
+  const int64_t* cand = cand_ids + (size_t)qi * nc;
+  const double* appr = cand_approx + (size_t)qi * nc;
+  int64_t* out = pack + (size_t)qi * 4 * nc;
+  const int cnt = cand_counts[qi];
+  const int lane = threadIdx.x & 31;
+  const int hl = lane & 15;
+  const int hw = threadIdx.x >> 4;
+  const int nhw = blockDim.x >> 4;
+  const unsigned hmask = (lane < 16) ? 0x0000ffffu : 0xffff0000u;
+  const int base_lane = lane & 16;
+  double qq = 0.0;
+  if (cosine) qq = ref_sum_halfwarp<REF_DOT>(q, q, d, lanes, hl, hmask, base_lane);
+  for (int c = hw; c < nc; c += nhw) {
+    const int64_t g = c < cnt ? cand[c] : -1;
+    const int64_t row = g - id_base;
+    int64_t state = g < 0 ? -1 : 0;
+    double score = 0.0;
+    bool ok = g >= 0 && row >= 0 && row < n;
+    if (ok && skip != nullptr && skip[row]) ok = false;  // deleted / gid missing: takes a slot, is not scored
+    if (ok) {                                            // uniform across the half-warp
+      const float* x = X + (size_t)row * d;
+      if (cosine) {
+        const double dot = ref_sum_halfwarp<REF_DOT>(q, x, d, lanes, hl, hmask, base_lane);
+        const double xx = ref_sum_halfwarp<REF_DOT>(x, x, d, lanes, hl, hmask, base_lane);
+        score = ref_cosine_from_sums(dot, qq, xx);
+      } else {
+        score = -__dsqrt_rn(ref_sum_halfwarp<REF_L2SQ>(q, x, d, lanes, hl, hmask, base_lane));
+      }
+      state = 1;
+    }
+    if (hl == 0) {
+      out[c] = g;
+      out[nc + c] = g >= 0 ? __double_as_longlong(appr[c]) : 0;
+      out[2 * nc + c] = __double_as_longlong(score);
+      out[3 * nc + c] = state;
+    }
+  }
+}
+
+cudaError_t launch_score_pack(const RankLaunch& L, const double* cand_approx, const int32_t* cand_counts, int64_t* pack,
+                              cudaStream_t st) {
+  int threads = RANK_THREADS;
+  while (threads < 1024 && threads < 16 * L.nc) threads <<= 1;
+  score_pack_kernel<<<L.nq, threads, 0, st>>>(L.X, L.n, L.d, L.skip, L.lanes, L.q, L.cand_ids, cand_approx, cand_counts,
+                                               L.nc, L.metric == 1, L.id_base, pack);
+  count_launch();
+  return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(1024)
+merge_adc_rerank_kernel(const int64_t* __restrict__ gath, int w, int nq, int nc, int np, int np2, int k,
+                        int64_t* __restrict__ ids_out, double* __restrict__ scores_out, int32_t* __restrict__ counts_out) {
+  extern __shared__ __align__(16) ulonglong2 skey[];  // [np] approximate order, then [np2] exact order
+  ulonglong2* skey2 = skey + np;
+  const int qi = blockIdx.x;
+  const int total = w * nc;
+  auto entry = [&](int p) { return gath + ((size_t)(p / nc) * nq + qi) * 4 * nc + (p % nc); };
+  for (int p = threadIdx.x; p < np; p += blockDim.x) {
+    Key key = key_empty();
+    if (p < total) {
+      const int64_t* e = entry(p);
+      if (e[3 * nc] >= 0) key = Key{rank_hi_from_dist(__longlong_as_double(e[nc])), (uint64_t)p};
+    }
+    st_key(skey + p, key);
+  }
+  __syncthreads();
+  block_bitonic_sort_keys(skey, np);  // stable: ties in approx fall back to (rank, position) = ascending global row
+  for (int c = threadIdx.x; c < np2; c += blockDim.x) {
+    Key key = key_empty();
+    if (c < nc) {
+      const Key a = ld_key(skey + c);
+      if (!key_is_empty(a)) {
+        const int64_t* e = entry((int)a.lo);
+        if (e[3 * nc] == 1) key = Key{rank_hi_from_score(__longlong_as_double(e[2 * nc])), (uint64_t)c};
+      }
+    }
+    st_key(skey2 + c, key);
+  }
+  __syncthreads();
+  block_bitonic_sort_keys(skey2, np2);
+  __shared__ int s_found;
+  if (threadIdx.x == 0) s_found = 0;
+  __syncthreads();
+  int found = 0;
+  for (int i = threadIdx.x; i < k; i += blockDim.x) {
+    const Key e2 = i < np2 ? ld_key(skey2 + i) : key_empty();
+    const bool ok = !key_is_empty(e2);
+    int64_t id = -1;
+    if (ok) id = entry((int)ld_key(skey + e2.lo).lo)[0];
+    ids_out[(size_t)qi * k + i] = id;
+    scores_out[(size_t)qi * k + i] = ok ? score_from_rank_hi(e2.hi) : __longlong_as_double(0x7ff8000000000000ll);
+    found += ok ? 1 : 0;
+  }
+  if (found) atomicAdd(&s_found, found);
+  __syncthreads();
+  if (threadIdx.x == 0) counts_out[qi] = s_found;
+}
+
+cudaError_t launch_merge_adc_rerank(const int64_t* gath, int w, int nq, int nc, int k, int64_t* ids_out,
+                                    double* scores_out, int32_t* counts_out, cudaStream_t st) {
+  if ((int64_t)w * nc > RANK_MAX_CAND) return cudaErrorInvalidValue;
+  int np = 2, np2 = 2;
+  while (np < w * nc) np <<= 1;
+  while (np2 < nc) np2 <<= 1;
+  const size_t smem = (size_t)(np + np2) * 16;
+  // largest case: RANK_MAX_CAND gathered entries plus their first TOPK_MAX_K by approximate distance
+  cudaError_t e = cudaFuncSetAttribute(merge_adc_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)((size_t)(RANK_MAX_CAND + TOPK_MAX_K) * 16));
+  if (e != cudaSuccess) return e;
+  if (smem > (size_t)(RANK_MAX_CAND + TOPK_MAX_K) * 16) return cudaErrorInvalidValue;
+  int threads = RANK_THREADS;
+  while (threads < 1024 && threads < np / 2) threads <<= 1;
+  merge_adc_rerank_kernel<<<nq, threads, smem, st>>>(gath, w, nq, nc, np, np2, k, ids_out, scores_out, counts_out);
+  count_launch();
+  return cudaGetLastError();
+}
+
 cudaError_t launch_merge_packed(const int64_t* gath, int w, int nq, int k, bool descending,
                                 int64_t* ids_out, double* scores_out, int32_t* counts_out, cudaStream_t st) {
   const int kp = topk_pad(k);

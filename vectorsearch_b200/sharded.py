@@ -68,6 +68,36 @@ def gather_and_merge_host(ids: np.ndarray, scores: np.ndarray, count: int, k: in
     return merge_gathered_host(g[:, :k], g[:, k:2 * k].copy().view(np.float64), g[:, 2 * k], k, desc)
 
 
+def merge_adc_rerank_host(packs: np.ndarray, k: int):
+    """Host restatement of vs_merge_adc_rerank_packed_dev for ONE query: packs is [world][4][n_cand] int64
+    (ids | approx bits | exact score bits | state).  Global first n_cand by (approx, rank, position), then
+    the scored ones by exact score descending (Double.compare), ties in approximate order; first k."""
+    world, _, nc = packs.shape
+    ent = []
+    for r in range(world):
+        ap = packs[r, 1].copy().view(np.float64)
+        sc = packs[r, 2].copy().view(np.float64)
+        for i in range(nc):
+            if packs[r, 3, i] >= 0:
+                ent.append((float(ap[i]), r * nc + i, int(packs[r, 0, i]), float(sc[i]), int(packs[r, 3, i])))
+
+    def akey(e):  # ascending distance, NaN last (Double.compare)
+        return (1, 0.0, e[1]) if e[0] != e[0] else (0, e[0], e[1])
+
+    first = sorted(ent, key=akey)[:nc]
+    scored = [(c, e) for c, e in enumerate(first) if e[4] == 1]
+
+    def skey(ce):  # descending score, NaN first, -0.0 after +0.0
+        c, e = ce
+        sc = e[3]
+        if sc != sc:
+            return (0, 0.0, 0, c)
+        return (1, -sc, 1 if (sc == 0 and np.signbit(sc)) else 0, c)
+
+    top = sorted(scored, key=skey)[:k]
+    return (np.array([e[2] for _, e in top], np.int64), np.array([e[3] for _, e in top], np.float64))
+
+
 class ShardedSegment:
     """One rank's row range of a corpus + the collective merge (torch.distributed)."""
 
@@ -132,6 +162,32 @@ class ShardedSegment:
             gath = b["gath"]
         check(self.lib.vs_merge_packed_dev(gath.data_ptr(), self.world, nq, k, 1, b["out_i"].data_ptr(),
                                            b["out_s"].data_ptr(), b["out_c"].data_ptr(), st))
+        return b["out_i"], b["out_s"], b["out_c"]
+
+    def adc_rerank_topk_dev(self, d_q, nq: int, n_cand: int, k: int, metric: int = METRIC_L2):
+        """Config C4 across shards: local ADC top n_cand + their exact scores (packed), ONE all-gather,
+        one merge that re-ranks the GLOBAL first n_cand by approximate distance -- the reference's
+        candidate set (J/fdb/FdbVectorIndex.java:820-828), not the union of per-shard winners."""
+        t = self.torch
+        key = ("adc", nq, n_cand, k)
+        if key not in self._bufs:
+            dev, w = self.dev, self.world
+            self._bufs[key] = dict(
+                pack=t.empty((nq, 4, n_cand), dtype=t.int64, device=dev),
+                gath=t.empty((w, nq, 4, n_cand), dtype=t.int64, device=dev),
+                out_i=t.empty((nq, k), dtype=t.int64, device=dev), out_s=t.empty((nq, k), dtype=t.float64, device=dev),
+                out_c=t.empty((nq,), dtype=t.int32, device=dev))
+        b = self._bufs[key]
+        st = t.cuda.current_stream().cuda_stream
+        check(self.lib.vs_adc_rerank_packed_dev(self.seg.handle, d_q.data_ptr(), nq, n_cand, metric, 0,
+                                                b["pack"].data_ptr(), st))
+        if self.world == 1:
+            gath = b["pack"]
+        else:
+            self.dist.all_gather_into_tensor(b["gath"].view(-1), b["pack"].view(-1), group=self.group)
+            gath = b["gath"]
+        check(self.lib.vs_merge_adc_rerank_packed_dev(gath.data_ptr(), self.world, nq, n_cand, k, b["out_i"].data_ptr(),
+                                                      b["out_s"].data_ptr(), b["out_c"].data_ptr(), st))
         return b["out_i"], b["out_s"], b["out_c"]
 
     def bruteforce_topk(self, q, k: int, metric: int = METRIC_L2):
