@@ -407,6 +407,76 @@ def test_adc_rerank_across_shards(vs, oracle, shards, metric):
             seg.free()
 
 
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_pq_train_sharded_ranks_emulated_with_threads(vs, oracle, world):
+    """C3 on several GPUs, emulated here: `world` host threads, each owning a row-range shard resident on
+    this GPU, call vs_pq_train_sharded concurrently; the collective hook is a thread barrier that sums the
+    ranks' buffers.  One rank must be bit-identical to the reference; several re-associate the fp32 sums
+    across shards, so centroids agree to rounding and the codes agree except at near-ties."""
+    import threading
+
+    import torch
+
+    from vectorsearch_b200.sharded import ShardedSegment, shard_range
+
+    n, d, M, K, iters = 9000, 32, 4, 16, 5
+    rows = oracle.gen_rows(42, 0, n, d)
+    rows[100:160] = rows[3]          # duplicates: duplicate initial draws / empty clusters get re-initialised
+    want = oracle.pq_train(rows, d, M, K, iters, 42)
+    segs = []
+    try:
+        for r in range(world):
+            lo, hi = shard_range(n, r, world)
+            segs.append((vs.Segment.upload(rows[lo:hi]), lo))
+        barrier = threading.Barrier(world)
+        pending, lock = [], threading.Lock()
+
+        def allreduce(buf):
+            with lock:
+                pending.append(buf)
+            barrier.wait()
+            if barrier.wait() == 0:            # one thread sums, everybody waits for it
+                total = torch.stack(pending).sum(0) if buf.dtype != torch.float32 else None
+                if total is None:              # fp32: add in rank order, like a ring would not -- any order is legal
+                    total = pending[0].clone()
+                    for b in pending[1:]:
+                        total += b
+                for b in pending:
+                    b.copy_(total)
+                torch.cuda.synchronize()
+                pending.clear()
+            barrier.wait()
+
+        out, errs = [None] * world, []
+
+        def run(r):
+            try:
+                torch.cuda.set_device(0)
+                sh = ShardedSegment(segs[r][0], r, world)
+                out[r] = sh.pq_train(n, segs[r][1], M, K, iters, 42, allreduce=allreduce if world > 1 else None)
+            except Exception as e:
+                errs.append(e)
+                barrier.abort()
+
+        threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+        for th in threads:
+            th.start()
+        for th in threads:
+            th.join(timeout=120)
+        assert not errs, errs
+        for r in range(1, world):
+            assert np.array_equal(out[r].view(np.uint32), out[0].view(np.uint32)), "ranks disagree"
+        if world == 1:
+            assert np.array_equal(out[0].view(np.uint32), want.view(np.uint32))
+        else:
+            assert np.allclose(out[0], want, rtol=2e-5, atol=1e-6)
+            codes, ref = oracle.pq_encode_batch(out[0], rows), oracle.pq_encode_batch(want, rows)
+            assert (codes != ref).mean() < 1e-3
+    finally:
+        for seg, _ in segs:
+            seg.free()
+
+
 def test_empty_segment_and_bad_args(vs):
     seg = vs.Segment.upload(np.zeros((0, 8), np.float32))
     try:

@@ -1219,6 +1219,27 @@ int32_t vs_merge_topk(const int64_t* ids, const double* scores, int64_t total, i
 // =================================================================================================
 // build operations
 // =================================================================================================
+// PqTrainer.train over a corpus sharded by ascending row range: this process holds rows
+// [row_lo, row_lo + segment rows) of n_total.  See include/vsgpu.h.
+int32_t vs_pq_train_sharded(uint64_t h, int64_t n_total, int64_t row_lo, int32_t M, int32_t K, int32_t iterations,
+                            int64_t seed, float* d_comm_f32, int32_t* d_comm_i32, vs_allreduce_fn allreduce, void* user,
+                            float* centroids_out) {
+  Segment* s = seg_lookup(h);
+  if (!s) return fail(VS_EHANDLE, "unknown segment handle");
+  const int d = s->d;
+  if (M <= 0 || K <= 0) return fail(VS_EINVAL, "Invalid PQ params (m,k,dimension)");
+  if (d % M != 0) return fail(VS_EINVAL, "dimension must be divisible by m");
+  if (!centroids_out || !d_comm_f32 || !d_comm_i32 || !allreduce) return fail(VS_EINVAL, "null pointer");
+  if (n_total <= 0) return fail(VS_EEMPTY, "empty training set (the reference throws IndexOutOfBoundsException)");
+  if (n_total > 0x7fffffffLL) return fail(VS_EINVAL, "a Java List cannot hold more than 2^31-1 vectors");
+  if (row_lo < 0 || row_lo + s->n > n_total) return fail(VS_EINVAL, "row range outside the corpus");
+  if (s->n == 0) return fail(VS_EINVAL, "a rank must own at least one row");
+  ThreadCtx* c;
+  RET(ctx_bind(&c));
+  TrainComm comm{row_lo, n_total, user, allreduce, d_comm_f32, d_comm_i32};
+  return pq_train_device(c->stream, s->X, s->n, d, M, K, iterations, seed, lanes(), centroids_out, &comm);
+}
+
 int32_t vs_pq_encode_batch(const float* centroids, int32_t M, int32_t K, int32_t subDim, const float* rows,
                            uint64_t h, int64_t n, uint8_t* codes_out) {
   if (!centroids || (!codes_out && n > 0) || n < 0) return fail(VS_EINVAL, "null pointer or negative n");

@@ -39,9 +39,17 @@ int lanes();
 int sm_count();
 Segment* seg_lookup(uint64_t h);
 
+// Row-sharded training: the caller's collective hook and the device buffers it reduces (sum, in place)
+struct TrainComm {
+  int64_t row_lo, n_total;
+  void* user;
+  int32_t (*allreduce)(void* user, int32_t kind, int64_t count);  // kind 0: d_f32[0..count), 1: d_i32[0..count)
+  float* d_f32;    // >= M * K * subDim floats
+  int32_t* d_i32;  // >= M * K ints
+};
 // PqTrainer.train on device-resident rows; centroids_out is HOST memory [M][K][d/M]  (pqtrain.cu)
 int pq_train_device(cudaStream_t st, const float* dX, int64_t n, int d, int M, int K, int iterations,
-                    int64_t seed, int lanes, float* centroids_out);
+                    int64_t seed, int lanes, float* centroids_out, const TrainComm* comm = nullptr);
 
 #ifdef VS_PHASE_STAMPS
 int debug_read_stamps(void* dst, size_t bytes);  // development only (scan.cu)

@@ -71,6 +71,20 @@ __global__ void gather_subvectors_kernel(const float* __restrict__ X, int d, int
   centroids[((size_t)s * K + ci) * sd + comp] = X[(size_t)row * d + (size_t)s * sd + comp];
 }
 
+// Sharded training: out[sl][ci][comp] <- sub-vector of GLOBAL row rows[sl * K + ci] if this rank owns it
+// (row_lo <= row < row_lo + n), else untouched (the buffer is zeroed first and summed across ranks)
+__global__ void gather_owned_kernel(const float* __restrict__ X, int64_t n, int d, int K, int sd, int64_t row_lo,
+                                    const int64_t* __restrict__ rows, float* __restrict__ out, int s_begin, int ns) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)ns * K * sd) return;
+  const int comp = (int)(t % sd);
+  const int64_t e = t / sd;
+  const int s = s_begin + (int)(e / K);
+  const int64_t row = rows[e] - row_lo;
+  if (rows[e] < 0 || row < 0 || row >= n) return;
+  out[t] = X[(size_t)row * d + (size_t)s * sd + comp];
+}
+
 // one warp per (row block, subspace): histogram of assignments
 __global__ void __launch_bounds__(32)
 hist_kernel(const int32_t* __restrict__ assign, int64_t n, int K, int nb, int s_begin,
@@ -185,7 +199,8 @@ chain_sum_kernel(const float* __restrict__ X, int64_t n, int d, int K, int sd, i
 // centroid = count ? sum / (float)count : sub-vector of the re-init row   (PqTrainer.java:78-87)
 __global__ void finalize_kernel(const float* __restrict__ X, int d, int K, int sd, int s_begin, int ns,
                                 const float* __restrict__ sums, const int32_t* __restrict__ counts,
-                                const int64_t* __restrict__ reinit, float* __restrict__ centroids) {
+                                const int64_t* __restrict__ reinit, const float* __restrict__ reinit_vals,
+                                float* __restrict__ centroids) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (int64_t)ns * K * sd) return;
   const int comp = (int)(t % sd);
@@ -195,8 +210,8 @@ __global__ void finalize_kernel(const float* __restrict__ X, int d, int K, int s
   const int s = s_begin + sl;
   const int32_t c = counts[e];
   float v;
-  if (c == 0)
-    v = X[(size_t)reinit[e] * d + (size_t)s * sd + comp];
+  if (c == 0)  // reinit_vals: the sub-vector was fetched from the rank that owns the row (sharded training)
+    v = reinit_vals != nullptr ? reinit_vals[t] : X[(size_t)reinit[e] * d + (size_t)s * sd + comp];
   else
     v = __fdiv_rn(sums[t], (float)c);
   centroids[((size_t)s * K + ci) * sd + comp] = v;
@@ -220,9 +235,21 @@ struct DevBuf {
 
 }  // namespace
 
+// comm == nullptr: one process owns all n rows (bit-identical to the reference).  Otherwise this process owns
+// rows [comm->row_lo, comm->row_lo + n) of comm->n_total: per-cluster sums and counts are all-reduced across
+// the ranks every iteration (fp32 addition re-associated across shards: centroids agree with the reference to
+// rounding, not bit for bit), and rows another rank owns (initial centroids, re-initialised empty clusters)
+// arrive through a zero-padded sum.  Every rank takes the same decisions: counts and random draws are global.
 int pq_train_device(cudaStream_t st, const float* dX, int64_t n, int d, int M, int K, int iterations,
-                    int64_t seed, int lanes_, float* centroids_out) {
+                    int64_t seed, int lanes_, float* centroids_out, const TrainComm* comm) {
   const int sd = d / M;
+  const int64_t n_draw = comm ? comm->n_total : n;  // bound of rnd.nextInt(n)
+  auto reduce = [&](int kind, int64_t count) -> int {
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return cuda_fail(e, "sync before all-reduce");
+    if (comm->allreduce(comm->user, kind, count) != 0) return fail(VS_ESTATE, "all-reduce callback failed");
+    return VS_OK;
+  };
   if ((size_t)K * 4 > 96 * 1024) return fail(VS_EINVAL, "K too large for the device trainer (max 24576)");
   const int nb = (int)((n + RB - 1) / RB);
   DevBuf b_cent, b_assign, b_order, b_hist, b_counts, b_offsets, b_sums, b_rows;
@@ -262,7 +289,7 @@ int pq_train_device(cudaStream_t st, const float* dX, int64_t n, int d, int M, i
     JRandom r = rnd;
     for (int s = s0; s < M; s++) {
       int64_t* rows = h_rows.data() + (size_t)(s - s0) * K;
-      for (int ci = 0; ci < K; ci++) rows[ci] = r.nextInt((int32_t)n);  // PqTrainer.java:48
+      for (int ci = 0; ci < K; ci++) rows[ci] = r.nextInt((int32_t)n_draw);  // PqTrainer.java:48
       cur[s] = r;
       int dups = 0;
       if (iterations > 0) {
@@ -272,14 +299,23 @@ int pq_train_device(cudaStream_t st, const float* dX, int64_t n, int d, int M, i
       }
       predicted[s] = dups;
       actual[s] = 0;
-      for (int e = 0; e < dups; e++) r.nextInt((int32_t)n);
+      for (int e = 0; e < dups; e++) r.nextInt((int32_t)n_draw);
     }
     TCK(cudaMemcpyAsync(d_rows, h_rows.data(), (size_t)ns * K * 8, cudaMemcpyHostToDevice, st), "H2D init rows");
     {
       const int64_t total = (int64_t)ns * K * sd;
-      gather_subvectors_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dX, d, K, sd, d_rows, d_cent, s0, M);
-      count_launch();
-      TCK(cudaGetLastError(), "gather launch");
+      if (comm) {
+        TCK(cudaMemsetAsync(comm->d_f32, 0, (size_t)total * 4, st), "memset");
+        gather_owned_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dX, n, d, K, sd, comm->row_lo, d_rows, comm->d_f32, s0, ns);
+        count_launch();
+        TCK(cudaGetLastError(), "gather launch");
+        { int r_ = reduce(0, total); if (r_ != VS_OK) return r_; }
+        TCK(cudaMemcpyAsync(d_cent + (size_t)s0 * K * sd, comm->d_f32, (size_t)total * 4, cudaMemcpyDeviceToDevice, st), "D2D centroids");
+      } else {
+        gather_subvectors_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dX, d, K, sd, d_rows, d_cent, s0, M);
+        count_launch();
+        TCK(cudaGetLastError(), "gather launch");
+      }
     }
     TCK(cudaStreamSynchronize(st), "sync");  // h_rows is reused below
 
@@ -302,13 +338,23 @@ int pq_train_device(cudaStream_t st, const float* dX, int64_t n, int d, int M, i
       chain_sum_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dX, n, d, K, sd, s0, ns, d_order, d_offsets, d_sums);
       count_launch();
       TCK(cudaGetLastError(), "chain launch");
+      if (comm) {  // per-cluster sums and counts of all shards
+        TCK(cudaMemcpyAsync(comm->d_f32, d_sums, (size_t)total * 4, cudaMemcpyDeviceToDevice, st), "D2D sums");
+        TCK(cudaMemcpyAsync(comm->d_i32, d_counts, (size_t)ns * K * 4, cudaMemcpyDeviceToDevice, st), "D2D counts");
+        { int r_ = reduce(0, total); if (r_ != VS_OK) return r_; }
+        { int r_ = reduce(1, (int64_t)ns * K); if (r_ != VS_OK) return r_; }
+        TCK(cudaMemcpyAsync(d_sums, comm->d_f32, (size_t)total * 4, cudaMemcpyDeviceToDevice, st), "D2D sums");
+        TCK(cudaMemcpyAsync(d_counts, comm->d_i32, (size_t)ns * K * 4, cudaMemcpyDeviceToDevice, st), "D2D counts");
+      }
       TCK(cudaMemcpyAsync(h_counts.data(), d_counts, (size_t)ns * K * 4, cudaMemcpyDeviceToHost, st), "D2H counts");
       TCK(cudaStreamSynchronize(st), "sync");
+      bool any_empty = false;
       for (int s = s0; s < M; s++) {
         for (int ci = 0; ci < K; ci++) {
           const size_t e = (size_t)(s - s0) * K + ci;
           if (h_counts[e] == 0) {
-            h_rows[e] = cur[s].nextInt((int32_t)n);  // PqTrainer.java:81
+            h_rows[e] = cur[s].nextInt((int32_t)n_draw);  // PqTrainer.java:81
+            any_empty = true;
             actual[s]++;
           } else {
             h_rows[e] = -1;
@@ -316,7 +362,18 @@ int pq_train_device(cudaStream_t st, const float* dX, int64_t n, int d, int M, i
         }
       }
       TCK(cudaMemcpyAsync(d_rows, h_rows.data(), (size_t)ns * K * 8, cudaMemcpyHostToDevice, st), "H2D reinit rows");
-      finalize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dX, d, K, sd, s0, ns, d_sums, d_counts, d_rows, d_cent);
+      const float* reinit_vals = nullptr;
+      if (comm && any_empty) {  // the re-init rows may live on other ranks (every rank sees the same empties)
+        TCK(cudaMemsetAsync(comm->d_f32, 0, (size_t)total * 4, st), "memset");
+        gather_owned_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dX, n, d, K, sd, comm->row_lo, d_rows, comm->d_f32, s0, ns);
+        count_launch();
+        TCK(cudaGetLastError(), "gather launch");
+        { int r_ = reduce(0, total); if (r_ != VS_OK) return r_; }
+        reinit_vals = comm->d_f32;
+      } else if (comm) {
+        reinit_vals = comm->d_f32;  // unused: no cluster is empty
+      }
+      finalize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dX, d, K, sd, s0, ns, d_sums, d_counts, d_rows, reinit_vals, d_cent);
       count_launch();
       TCK(cudaGetLastError(), "finalize launch");
       TCK(cudaStreamSynchronize(st), "sync");

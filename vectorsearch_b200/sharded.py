@@ -190,6 +190,42 @@ class ShardedSegment:
                                                       b["out_s"].data_ptr(), b["out_c"].data_ptr(), st))
         return b["out_i"], b["out_s"], b["out_c"]
 
+    def pq_train(self, n_total: int, row_lo: int, m: int, k: int, iterations: int, seed: int, allreduce=None):
+        """PqTrainer.train over the sharded corpus (config C3): local assignment and per-cluster sums on
+        this rank's rows, an all-reduce of the sums and counts per iteration (NCCL over NVLink through
+        torch.distributed), identical centroids on every rank.  `allreduce(tensor)` overrides the
+        collective (the single-GPU emulation in the tests passes a thread barrier)."""
+        import ctypes as C
+
+        t = self.torch
+        d = self.seg.d
+        f32 = t.zeros(m * k * (d // m), dtype=t.float32, device=self.dev)
+        i32 = t.zeros(m * k, dtype=t.int32, device=self.dev)
+        t.cuda.synchronize()
+        err = []
+
+        def hook(_user, kind, count):
+            try:
+                buf = (f32 if kind == 0 else i32)[:count]
+                if allreduce is not None:
+                    allreduce(buf)
+                elif self.world > 1:
+                    self.dist.all_reduce(buf, group=self.group)
+                t.cuda.current_stream().synchronize()
+                return 0
+            except Exception as e:  # never unwind through the C frame
+                err.append(e)
+                return 1
+
+        cb = L.ALLREDUCE_FN(hook)
+        cent = np.empty((m, k, d // m), dtype=np.float32)
+        rc = self.lib.vs_pq_train_sharded(self.seg.handle, n_total, row_lo, m, k, iterations, seed, f32.data_ptr(),
+                                          i32.data_ptr(), cb, None, cent.ctypes.data_as(L.f32p))
+        if err:
+            raise err[0]
+        check(rc)
+        return cent
+
     def bruteforce_topk(self, q, k: int, metric: int = METRIC_L2):
         """Host query [d] or [nq][d] (numpy) -> numpy results; H2D and D2H inside (the e2e path)."""
         t = self.torch
