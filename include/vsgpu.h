@@ -127,20 +127,23 @@ int32_t vs_merge_topk(const int64_t* ids, const double* scores, int64_t total, i
  * J/tasks/SegmentBuildService.java:180) */
 int32_t vs_pq_train(const float* rows, uint64_t h, int64_t n, int32_t d, int32_t M, int32_t K,
                     int32_t iterations, int64_t seed, float* centroids_out);
-/* PqTrainer.train over a corpus sharded by ascending row range over several processes (one per GPU): the
- * segment h holds rows [row_lo, row_lo + its row count) of n_total.  Every Lloyd iteration the per-cluster
- * fp32 sums and int counts of all shards are summed through the caller's collective: the library fills the
- * caller-owned DEVICE buffers d_comm_f32 (>= M*K*d/M floats) / d_comm_i32 (>= M*K ints), synchronises its
- * stream and calls allreduce(user, kind, count) -- kind 0: sum d_comm_f32[0..count) over all ranks in place,
- * kind 1: the same for d_comm_i32 -- which must return 0 once the reduced values are visible to other
- * streams.  Rows another rank owns (initial centroids, re-initialised empty clusters) travel through the same
- * hook as zero-padded sums.  Every rank returns the same centroids.  With one rank the result is bit-identical
- * to vs_pq_train; with several, fp32 sums are re-associated across shards, so centroids match the reference
- * to rounding (north_star: centroid sums are combined with an all-reduce). */
+/* PqTrainer.train over a corpus sharded by ascending row range over `world` processes (one per GPU): the
+ * segment h holds rows [row_lo, row_lo + its row count) of n_total and this process is `rank`.  Every Lloyd
+ * iteration the per-cluster fp32 sums and int counts of all shards are combined through the caller's
+ * collective: the library fills the caller-owned DEVICE buffers d_comm_f32 (>= M*K*d/M floats) / d_comm_i32
+ * (>= M*K ints), synchronises its stream and calls allreduce(user, kind, count) -- kind 0: sum
+ * d_comm_f32[0..count) over all ranks in place, kind 1: the same for d_comm_i32 -- which must return 0 once
+ * the reduced values are visible to other streams.  Rows another rank owns (initial centroids, re-initialised
+ * empty clusters) travel through the same hook as zero-padded sums.  Every rank returns the same centroids.
+ *   exact_order != 0: the sums continue rank after rank in ascending row order (world reductions per
+ *     iteration, one contributing rank each): centroids are bit-identical to the reference / vs_pq_train.
+ *   exact_order == 0: ONE all-reduce of the sums per iteration (north_star's scheme).  fp32 additions are
+ *     re-associated across shards; k-means amplifies that last-bit difference as soon as one row changes
+ *     cluster, so this is a different but statistically equivalent Lloyd trajectory, not the reference's. */
 typedef int32_t (*vs_allreduce_fn)(void* user, int32_t kind, int64_t count);
-int32_t vs_pq_train_sharded(uint64_t h, int64_t n_total, int64_t row_lo, int32_t M, int32_t K, int32_t iterations,
-                            int64_t seed, float* d_comm_f32, int32_t* d_comm_i32, vs_allreduce_fn allreduce, void* user,
-                            float* centroids_out);
+int32_t vs_pq_train_sharded(uint64_t h, int64_t n_total, int64_t row_lo, int32_t rank, int32_t world, int32_t exact_order,
+                            int32_t M, int32_t K, int32_t iterations, int64_t seed, float* d_comm_f32, int32_t* d_comm_i32,
+                            vs_allreduce_fn allreduce, void* user, float* centroids_out);
 /* PqEncoder.encode over n rows, J/pq/PqEncoder.java:18-37, J/tasks/SegmentBuildService.java:301 */
 int32_t vs_pq_encode_batch(const float* centroids, int32_t M, int32_t K, int32_t subDim,
                            const float* rows, uint64_t h, int64_t n, uint8_t* codes_out);

@@ -407,19 +407,28 @@ def test_adc_rerank_across_shards(vs, oracle, shards, metric):
             seg.free()
 
 
+def _quantisation_error(oracle, cent, rows):
+    codes = oracle.pq_encode_batch(cent, rows)
+    M, K, sd = cent.shape
+    rec = np.concatenate([cent[s][codes[:, s]] for s in range(M)], axis=1)
+    return float(((rows - rec) ** 2).sum(1).mean())
+
+
+@pytest.mark.parametrize("exact", [True, False])
 @pytest.mark.parametrize("world", [1, 2, 3])
-def test_pq_train_sharded_ranks_emulated_with_threads(vs, oracle, world):
+def test_pq_train_sharded_ranks_emulated_with_threads(vs, oracle, world, exact):
     """C3 on several GPUs, emulated here: `world` host threads, each owning a row-range shard resident on
     this GPU, call vs_pq_train_sharded concurrently; the collective hook is a thread barrier that sums the
-    ranks' buffers.  One rank must be bit-identical to the reference; several re-associate the fp32 sums
-    across shards, so centroids agree to rounding and the codes agree except at near-ties."""
+    ranks' buffers.  exact_order: bit-identical to the reference on any number of ranks.  One all-reduce per
+    iteration: identical on all ranks, and as good a codebook (quantisation error within 2 % of the
+    reference's) -- but a different Lloyd trajectory as soon as one row changes cluster."""
     import threading
 
     import torch
 
     from vectorsearch_b200.sharded import ShardedSegment, shard_range
 
-    n, d, M, K, iters = 9000, 32, 4, 16, 5
+    n, d, M, K, iters = 30000, 32, 4, 64, 5
     rows = oracle.gen_rows(42, 0, n, d)
     rows[100:160] = rows[3]          # duplicates: duplicate initial draws / empty clusters get re-initialised
     want = oracle.pq_train(rows, d, M, K, iters, 42)
@@ -453,7 +462,7 @@ def test_pq_train_sharded_ranks_emulated_with_threads(vs, oracle, world):
             try:
                 torch.cuda.set_device(0)
                 sh = ShardedSegment(segs[r][0], r, world)
-                out[r] = sh.pq_train(n, segs[r][1], M, K, iters, 42, allreduce=allreduce if world > 1 else None)
+                out[r] = sh.pq_train(n, segs[r][1], M, K, iters, 42, allreduce=allreduce if world > 1 else None, exact_order=exact)
             except Exception as e:
                 errs.append(e)
                 barrier.abort()
@@ -466,12 +475,11 @@ def test_pq_train_sharded_ranks_emulated_with_threads(vs, oracle, world):
         assert not errs, errs
         for r in range(1, world):
             assert np.array_equal(out[r].view(np.uint32), out[0].view(np.uint32)), "ranks disagree"
-        if world == 1:
+        if world == 1 or exact:
             assert np.array_equal(out[0].view(np.uint32), want.view(np.uint32))
         else:
-            assert np.allclose(out[0], want, rtol=2e-5, atol=1e-6)
-            codes, ref = oracle.pq_encode_batch(out[0], rows), oracle.pq_encode_batch(want, rows)
-            assert (codes != ref).mean() < 1e-3
+            e_got, e_ref = _quantisation_error(oracle, out[0], rows), _quantisation_error(oracle, want, rows)
+            assert abs(e_got - e_ref) <= 0.02 * e_ref, (e_got, e_ref)
     finally:
         for seg, _ in segs:
             seg.free()

@@ -56,7 +56,7 @@ SIGNATURES = {
     "vs_adc_rerank_topk": (i32, [u64, f32p, i32, i32, i32, i32, i32, i64p, f64p, i32p]),
     "vs_merge_topk": (i32, [i64p, f64p, i64, i32, i64p, f64p, i32p]),
     "vs_pq_train": (i32, [f32p, u64, i64, i32, i32, i32, i32, i64, f32p]),
-    "vs_pq_train_sharded": (i32, [u64, i64, i64, i32, i32, i32, i64, vp, vp, vp, vp, f32p]),
+    "vs_pq_train_sharded": (i32, [u64, i64, i64, i32, i32, i32, i32, i32, i32, i64, vp, vp, vp, vp, f32p]),
     "vs_pq_encode_batch": (i32, [f32p, i32, i32, i32, f32p, u64, i64, u8p]),
     "vs_bruteforce_topk_dev": (i32, [u64, vp, i32, i32, i32, vp, vp, vp, vp]),
     "vs_adc_topk_dev": (i32, [u64, vp, i32, i32, vp, vp, vp, vp]),

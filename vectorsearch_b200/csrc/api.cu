@@ -1221,9 +1221,9 @@ int32_t vs_merge_topk(const int64_t* ids, const double* scores, int64_t total, i
 // =================================================================================================
 // PqTrainer.train over a corpus sharded by ascending row range: this process holds rows
 // [row_lo, row_lo + segment rows) of n_total.  See include/vsgpu.h.
-int32_t vs_pq_train_sharded(uint64_t h, int64_t n_total, int64_t row_lo, int32_t M, int32_t K, int32_t iterations,
-                            int64_t seed, float* d_comm_f32, int32_t* d_comm_i32, vs_allreduce_fn allreduce, void* user,
-                            float* centroids_out) {
+int32_t vs_pq_train_sharded(uint64_t h, int64_t n_total, int64_t row_lo, int32_t rank, int32_t world, int32_t exact_order,
+                            int32_t M, int32_t K, int32_t iterations, int64_t seed, float* d_comm_f32, int32_t* d_comm_i32,
+                            vs_allreduce_fn allreduce, void* user, float* centroids_out) {
   Segment* s = seg_lookup(h);
   if (!s) return fail(VS_EHANDLE, "unknown segment handle");
   const int d = s->d;
@@ -1234,9 +1234,10 @@ int32_t vs_pq_train_sharded(uint64_t h, int64_t n_total, int64_t row_lo, int32_t
   if (n_total > 0x7fffffffLL) return fail(VS_EINVAL, "a Java List cannot hold more than 2^31-1 vectors");
   if (row_lo < 0 || row_lo + s->n > n_total) return fail(VS_EINVAL, "row range outside the corpus");
   if (s->n == 0) return fail(VS_EINVAL, "a rank must own at least one row");
+  if (world <= 0 || rank < 0 || rank >= world) return fail(VS_EINVAL, "rank must be in [0, world)");
   ThreadCtx* c;
   RET(ctx_bind(&c));
-  TrainComm comm{row_lo, n_total, user, allreduce, d_comm_f32, d_comm_i32};
+  TrainComm comm{row_lo, n_total, rank, world, exact_order != 0 ? 1 : 0, user, allreduce, d_comm_f32, d_comm_i32};
   return pq_train_device(c->stream, s->X, s->n, d, M, K, iterations, seed, lanes(), centroids_out, &comm);
 }
 

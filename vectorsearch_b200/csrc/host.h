@@ -42,6 +42,8 @@ Segment* seg_lookup(uint64_t h);
 // Row-sharded training: the caller's collective hook and the device buffers it reduces (sum, in place)
 struct TrainComm {
   int64_t row_lo, n_total;
+  int rank, world;
+  int exact_order;  // 1: sums continue rank after rank in row order (bit-exact); 0: one all-reduce per iteration
   void* user;
   int32_t (*allreduce)(void* user, int32_t kind, int64_t count);  // kind 0: d_f32[0..count), 1: d_i32[0..count)
   float* d_f32;    // >= M * K * subDim floats

@@ -172,6 +172,7 @@ scatter_kernel(const int32_t* __restrict__ assign, int64_t n, int K, int nb, int
 __global__ void __launch_bounds__(256)
 chain_sum_kernel(const float* __restrict__ X, int64_t n, int d, int K, int sd, int s_begin, int ns,
                  const int32_t* __restrict__ order, const int32_t* __restrict__ offsets,
+                 const float* __restrict__ carry /* nullable: running sums of the lower row ranges */,
                  float* __restrict__ sums /* [ns][K][sd] */) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (int64_t)ns * K * sd) return;
@@ -183,7 +184,7 @@ chain_sum_kernel(const float* __restrict__ X, int64_t n, int d, int K, int sd, i
   const int32_t j0 = offsets[(size_t)sl * (K + 1) + ci];
   const int32_t j1 = offsets[(size_t)sl * (K + 1) + ci + 1];
   const float* col = X + (size_t)(s_begin + sl) * sd + comp;
-  float acc = 0.0f;
+  float acc = carry != nullptr ? carry[t] : 0.0f;
   int32_t j = j0;
   for (; j + 8 <= j1; j += 8) {
     float v[8];
@@ -236,10 +237,13 @@ struct DevBuf {
 }  // namespace
 
 // comm == nullptr: one process owns all n rows (bit-identical to the reference).  Otherwise this process owns
-// rows [comm->row_lo, comm->row_lo + n) of comm->n_total: per-cluster sums and counts are all-reduced across
-// the ranks every iteration (fp32 addition re-associated across shards: centroids agree with the reference to
-// rounding, not bit for bit), and rows another rank owns (initial centroids, re-initialised empty clusters)
-// arrive through a zero-padded sum.  Every rank takes the same decisions: counts and random draws are global.
+// rows [comm->row_lo, comm->row_lo + n) of comm->n_total and the per-cluster sums and counts are combined
+// across the ranks every iteration through comm->allreduce: in row order, rank after rank (exact_order:
+// centroids bit-identical to the reference on any number of ranks), or with ONE all-reduce (fp32 additions
+// re-associated across shards: a different, statistically equivalent Lloyd trajectory -- k-means amplifies
+// the last-bit difference as soon as one row changes cluster).  Rows another rank owns (initial centroids,
+// re-initialised empty clusters) arrive through a zero-padded sum.  Every rank takes the same decisions:
+// counts and random draws are global.
 int pq_train_device(cudaStream_t st, const float* dX, int64_t n, int d, int M, int K, int iterations,
                     int64_t seed, int lanes_, float* centroids_out, const TrainComm* comm) {
   const int sd = d / M;
@@ -335,16 +339,38 @@ int pq_train_device(cudaStream_t st, const float* dX, int64_t n, int d, int M, i
       count_launch();
       TCK(cudaGetLastError(), "scatter launch");
       const int64_t total = (int64_t)ns * K * sd;
-      chain_sum_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dX, n, d, K, sd, s0, ns, d_order, d_offsets, d_sums);
+      if (comm && comm->exact_order) {
+        // The reference adds the rows of a cluster in ascending row order.  Shards are ascending row ranges, so
+        // rank r continues the running sums of ranks 0..r-1: world rounds, in each of which exactly one rank
+        // contributes (the others add zeros, x + 0.0f == x) -- the sums, hence the centroids, are the reference's bit for bit.
+        for (int r = 0; r < comm->world; r++) {
+          if (r == comm->rank) {
+            chain_sum_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dX, n, d, K, sd, s0, ns, d_order, d_offsets,
+                                                                              r == 0 ? nullptr : comm->d_f32, d_sums);
+            count_launch();
+            TCK(cudaGetLastError(), "chain launch");
+            TCK(cudaMemcpyAsync(comm->d_f32, d_sums, (size_t)total * 4, cudaMemcpyDeviceToDevice, st), "D2D sums");
+          } else {
+            TCK(cudaMemsetAsync(comm->d_f32, 0, (size_t)total * 4, st), "memset");
+          }
+          { int r_ = reduce(0, total); if (r_ != VS_OK) return r_; }
+        }
+        TCK(cudaMemcpyAsync(d_sums, comm->d_f32, (size_t)total * 4, cudaMemcpyDeviceToDevice, st), "D2D sums");
+        TCK(cudaMemcpyAsync(comm->d_i32, d_counts, (size_t)ns * K * 4, cudaMemcpyDeviceToDevice, st), "D2D counts");
+        { int r_ = reduce(1, (int64_t)ns * K); if (r_ != VS_OK) return r_; }
+        TCK(cudaMemcpyAsync(d_counts, comm->d_i32, (size_t)ns * K * 4, cudaMemcpyDeviceToDevice, st), "D2D counts");
+      } else {
+      chain_sum_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dX, n, d, K, sd, s0, ns, d_order, d_offsets, nullptr, d_sums);
       count_launch();
       TCK(cudaGetLastError(), "chain launch");
-      if (comm) {  // per-cluster sums and counts of all shards
+      if (comm) {  // per-cluster sums and counts of all shards, one all-reduce each (sums re-associated across shards)
         TCK(cudaMemcpyAsync(comm->d_f32, d_sums, (size_t)total * 4, cudaMemcpyDeviceToDevice, st), "D2D sums");
         TCK(cudaMemcpyAsync(comm->d_i32, d_counts, (size_t)ns * K * 4, cudaMemcpyDeviceToDevice, st), "D2D counts");
         { int r_ = reduce(0, total); if (r_ != VS_OK) return r_; }
         { int r_ = reduce(1, (int64_t)ns * K); if (r_ != VS_OK) return r_; }
         TCK(cudaMemcpyAsync(d_sums, comm->d_f32, (size_t)total * 4, cudaMemcpyDeviceToDevice, st), "D2D sums");
         TCK(cudaMemcpyAsync(d_counts, comm->d_i32, (size_t)ns * K * 4, cudaMemcpyDeviceToDevice, st), "D2D counts");
+      }
       }
       TCK(cudaMemcpyAsync(h_counts.data(), d_counts, (size_t)ns * K * 4, cudaMemcpyDeviceToHost, st), "D2H counts");
       TCK(cudaStreamSynchronize(st), "sync");

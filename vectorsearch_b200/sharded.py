@@ -190,11 +190,15 @@ class ShardedSegment:
                                                       b["out_s"].data_ptr(), b["out_c"].data_ptr(), st))
         return b["out_i"], b["out_s"], b["out_c"]
 
-    def pq_train(self, n_total: int, row_lo: int, m: int, k: int, iterations: int, seed: int, allreduce=None):
+    def pq_train(self, n_total: int, row_lo: int, m: int, k: int, iterations: int, seed: int, allreduce=None,
+                 exact_order: bool = True):
         """PqTrainer.train over the sharded corpus (config C3): local assignment and per-cluster sums on
         this rank's rows, an all-reduce of the sums and counts per iteration (NCCL over NVLink through
-        torch.distributed), identical centroids on every rank.  `allreduce(tensor)` overrides the
-        collective (the single-GPU emulation in the tests passes a thread barrier)."""
+        torch.distributed), identical centroids on every rank.  exact_order=True continues the sums rank
+        after rank in row order (bit-identical to the reference, `world` reductions per iteration);
+        False is one all-reduce per iteration (faster, a statistically equivalent Lloyd trajectory).
+        `allreduce(tensor)` overrides the collective (the single-GPU emulation in the tests passes a
+        thread barrier)."""
         import ctypes as C
 
         t = self.torch
@@ -219,7 +223,8 @@ class ShardedSegment:
 
         cb = L.ALLREDUCE_FN(hook)
         cent = np.empty((m, k, d // m), dtype=np.float32)
-        rc = self.lib.vs_pq_train_sharded(self.seg.handle, n_total, row_lo, m, k, iterations, seed, f32.data_ptr(),
+        rc = self.lib.vs_pq_train_sharded(self.seg.handle, n_total, row_lo, self.rank, self.world, 1 if exact_order else 0,
+                                          m, k, iterations, seed, f32.data_ptr(),
                                           i32.data_ptr(), cb, None, cent.ctypes.data_as(L.f32p))
         if err:
             raise err[0]
