@@ -28,6 +28,7 @@ static std::atomic<int64_t> g_batch_min_queries{3};        // query batches at l
 static std::atomic<int64_t> g_batch_min_rows{16384};       // ... on segments at least this long
 static std::atomic<int64_t> g_batch_gm_bytes{int64_t(1) << 30};  // group-minima scratch per query chunk
 static std::atomic<int64_t> g_batch_warp_min_q{0};         // > 0: batches this large always select with one warp per query (tests)
+static std::atomic<int64_t> g_scan_reserve_sms{0};          // SMs the one-query scan leaves free (for a collective's CTAs)
 static std::atomic<int64_t> g_batch_group{0};               // 0 = automatic rows per nomination group, else 16 / 32 / 64
 static std::atomic<int64_t> g_batch_fp16{1};                // nominate on fp16 operand copies (0: the fp32 rows as tf32)
 static int g_sms = 0;
@@ -307,7 +308,9 @@ static std::unordered_map<uint64_t, AdcPlan> g_adc_cache;
 
 static int plan_scan(const Segment* s, int nq, int k, bool cosine, ScanLaunch* out) {
   const int ln = lanes();
-  uint64_t key = occ_key(cosine ? 11 : 10, s->d, ln, k, nq > 1 ? 2 : 1, (size_t)s->n);
+  int sms = g_sms - (int)g_scan_reserve_sms.load();
+  if (sms < 1) sms = 1;
+  uint64_t key = occ_key(cosine ? 11 : 10, s->d, ln, k, (nq > 1 ? 2 : 1) + 4 * sms, (size_t)s->n);
   {
     std::lock_guard<std::mutex> lk(g_scan_mu);
     auto it = g_scan_cache.find(key);
@@ -318,7 +321,7 @@ static int plan_scan(const Segment* s, int nq, int k, bool cosine, ScanLaunch* o
   }
   ScanLaunch L{};
   L.n = s->n; L.d = s->d; L.nq = nq; L.lanes = ln; L.cosine = cosine; L.k = k;
-  if (!scan_configure(L, g_sms)) return fail(VS_ECUDA, "scan kernel cannot be resident for d=%d k=%d", s->d, k);
+  if (!scan_configure(L, sms)) return fail(VS_ECUDA, "scan kernel cannot be resident for d=%d k=%d", s->d, k);
   std::lock_guard<std::mutex> lk(g_scan_mu);
   g_scan_cache[key] = L;
   *out = L;
@@ -642,6 +645,11 @@ int32_t vs_debug_adc_stats(uint32_t* out8) { return vs::debug_adc_stats(out8) ==
 
 int32_t vs_set_option(const char* name, int64_t value) {
   if (!name) return fail(VS_EINVAL, "null option name");
+  if (!strcmp(name, "scan_reserve_sms")) {
+    if (value < 0 || value >= 128) return fail(VS_EINVAL, "scan_reserve_sms must be in 0..127");
+    g_scan_reserve_sms.store(value);
+    return VS_OK;
+  }
   if (!strcmp(name, "batch_group")) {
     if (value != 0 && value != 16 && value != 32 && value != 64) return fail(VS_EINVAL, "batch_group must be 0, 16, 32 or 64");
     g_batch_group.store(value);
