@@ -527,6 +527,35 @@ def test_pq_encode_matches_oracle(vs, oracle, n, d, M, K):
         seg.free()
 
 
+@pytest.mark.parametrize("tensor_cores", [1, 0])
+@pytest.mark.parametrize("n,d,M,K", [(20001, 128, 16, 256), (5000, 64, 8, 200), (777, 32, 4, 3), (63, 8, 1, 256),
+                                     (9000, 40, 5, 33)])
+def test_pq_encode_subdim8_tensor_core_and_ffma_nomination(vs, oracle, tensor_cores, n, d, M, K):
+    """subDim 8 (the production shape) nominates with mma.sync 3xTF32 or with the FFMA kernel; both decide
+    near-ties in the reference arithmetic, so both are bit-identical to the oracle -- near-duplicate centroids,
+    centroids trained on the data (rows AT a centroid) and ragged K / n included."""
+    vs.set_option("pq_tensor_cores", tensor_cores)
+    try:
+        rows = oracle.gen_rows(42, 0, n, d)
+        cent = oracle.pq_train(rows[:min(n, 3000)], d, M, K, 3, 42)
+        if K > 8:
+            cent[:, 5] = cent[:, 2]                                      # exact duplicates
+            cent[:, 6] = cent[:, 2] * np.float32(1 + 2e-7)               # one ulp away: inside every band
+            cent[0, 7] = np.nextafter(cent[0, 2], np.float32(10), dtype=np.float32)
+        rows[10, :8] = cent[0, min(2, K - 1)]                            # a row exactly at a centroid
+        rows[11] = 0.0
+        want = oracle.pq_encode_batch(cent, rows, threads=8)
+        assert np.array_equal(vs.PqEncoder.encode_batch(cent, rows), want)
+        rows[20, 3] = np.nan
+        rows[21] = 3e30
+        rows[22] = -1e19
+        cent[0, 0, 1] = np.nan
+        want = oracle.pq_encode_batch(cent, rows, threads=8)
+        assert np.array_equal(vs.PqEncoder.encode_batch(cent, rows), want)
+    finally:
+        vs.set_option("pq_tensor_cores", 0)
+
+
 def test_pq_encode_duplicate_centroids_and_nan(vs, oracle):
     rows, cent = _pq_fixture(oracle, 4000, 64, 8, 64)
     cent[:, 40] = cent[:, 3]      # duplicates: strict '<' keeps the lower index

@@ -645,6 +645,10 @@ int32_t vs_debug_adc_stats(uint32_t* out8) { return vs::debug_adc_stats(out8) ==
 
 int32_t vs_set_option(const char* name, int64_t value) {
   if (!name) return fail(VS_EINVAL, "null option name");
+  if (!strcmp(name, "pq_tensor_cores")) {
+    pq_set_tensor_cores(value != 0);
+    return VS_OK;
+  }
   if (!strcmp(name, "scan_reserve_sms")) {
     if (value < 0 || value >= 128) return fail(VS_EINVAL, "scan_reserve_sms must be in 0..127");
     g_scan_reserve_sms.store(value);

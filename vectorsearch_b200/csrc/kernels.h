@@ -225,6 +225,7 @@ struct PqAssignLaunch {
   int32_t* assign_i32;     // nullable: [M][n]
   int s_begin, s_end;      // subspaces to process
 };
+void pq_set_tensor_cores(int on);  // subDim 8: mma.sync 3xTF32 nomination (default) or the FFMA kernel
 cudaError_t launch_pq_assign(const PqAssignLaunch& L, cudaStream_t st);
 
 }  // namespace vs
