@@ -291,6 +291,8 @@ def run_ours(args) -> None:
     value = world * N_ROWS * K / (ms_total * 1e-3)
 
     # ---- per-launch duration of the scan kernel (roofline), events around every launch ------------------
+    # (launched alone it has the whole GPU: all SMs; the reserve only pays off when queries overlap)
+    vs.set_option("scan_reserve_sms", 0)
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     with clocks:
         for i in range(K):

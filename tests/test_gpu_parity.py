@@ -189,7 +189,8 @@ def _check_batch(vs, oracle, rows, qs, k, metric, skip=None, id_base=0, threads=
 
 @pytest.mark.parametrize("metric", [0, 1])
 @pytest.mark.parametrize("n,d,k,nq", [(40000, 128, 10, 37), (20000, 768, 50, 130), (9000, 72, 10, 5), (6000, 100, 100, 3),
-                                      (300, 32, 1, 2), (7, 128, 10, 4), (70000, 64, 33, 260), (1000, 128, 1000, 3)])
+                                      (300, 32, 1, 2), (7, 128, 10, 4), (70000, 64, 33, 260), (1000, 128, 1000, 3),
+                                      (33000, 128, 10, 300), (500, 96, 5, 129)])
 def test_batch_bruteforce_matches_oracle(vs, oracle, force_batch, n, d, k, nq, metric):
     rows = oracle.gen_rows(42, 0, n, d)
     qs = oracle.gen_rows(43, 0, nq, d)
