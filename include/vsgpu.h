@@ -190,7 +190,8 @@ int64_t vs_kernel_launch_count(void);
  * the per-query scan; "batch_fp16" (default 1): nominate on an fp16 operand copy of the rows (n * d * 2
  * bytes of HBM, made at the first batched query) instead of the fp32 rows read as tf32; "batch_group"
  * (0 = automatic, 16 / 32 / 64): rows per nomination group; "batch_gm_bytes": scratch per query chunk;
- * "batch_warp_min_queries" (0 = automatic).  "scan_reserve_sms": SMs the one-query scan leaves free so that
+ * "batch_warp_min_queries" (0 = automatic); "batch_pairs" (default 0): batches of more than 128 queries
+ * nominate on CTA pairs (tcgen05 cta_group::2).  "scan_reserve_sms": SMs the one-query scan leaves free so that
  * work of another stream (the next query's prologue, a collective's CTAs) runs beside it (default 0).
  * "pq_tensor_cores" (default 0): subDim-8 PQ assignment nominates with mma.sync 3xTF32 instead of FFMA
  * (slower on B200, kept as a measured reference point).  Results never depend on any of them. */

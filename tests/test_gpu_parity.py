@@ -155,7 +155,7 @@ def test_bruteforce_query_batch(vs, oracle):
 
 
 # ---- batched queries: tensor-core nomination + exact re-score (batch.cu) ----------------------------------
-@pytest.fixture(params=["fp16", "tf32", "fp16-warpselect", "fp16-g16", "tf32-g32", "fp16-g64"])
+@pytest.fixture(params=["fp16", "tf32", "fp16-warpselect", "fp16-g16", "tf32-g32", "fp16-g64", "fp16-pairs", "tf32-pairs"])
 def force_batch(vs, request):
     """Route every query batch of >= 2 queries through batch.cu, whatever the segment size, nominating
     on the fp16 operand copies (default) or on the fp32 rows read as tf32; "warpselect" also forces the
@@ -165,8 +165,10 @@ def force_batch(vs, request):
     vs.set_option("batch_fp16", 0 if request.param == "tf32" else 1)
     vs.set_option("batch_warp_min_queries", 2 if "warpselect" in request.param else 0)
     vs.set_option("batch_group", int(request.param.split("-g")[1]) if "-g" in request.param else 0)  # rows per group
+    vs.set_option("batch_pairs", 1 if "pairs" in request.param else 0)  # cta_group::2 nomination kernel
     yield
     vs.set_option("batch_group", 0)
+    vs.set_option("batch_pairs", 0)
     vs.set_option("batch_min_queries", 3)
     vs.set_option("batch_min_rows", 16384)
     vs.set_option("batch_fp16", 1)

@@ -13,6 +13,8 @@ lib = vs.load()
 import os
 if os.environ.get("VS_TF32"):
     vs.set_option("batch_fp16", 0)
+if os.environ.get("VS_PAIRS"):
+    vs.set_option("batch_pairs", int(os.environ["VS_PAIRS"]))
 if os.environ.get("VS_GROUP"):
     vs.set_option("batch_group", int(os.environ["VS_GROUP"]))
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000

@@ -29,6 +29,7 @@ static std::atomic<int64_t> g_batch_min_rows{16384};       // ... on segments at
 static std::atomic<int64_t> g_batch_gm_bytes{int64_t(1) << 30};  // group-minima scratch per query chunk
 static std::atomic<int64_t> g_batch_warp_min_q{0};         // > 0: batches this large always select with one warp per query (tests)
 static std::atomic<int64_t> g_scan_reserve_sms{0};          // SMs the one-query scan leaves free (for a collective's CTAs)
+static std::atomic<int64_t> g_batch_pairs{0};               // 1: cta_group::2 nomination kernel for batches > 128 queries (measured equal)
 static std::atomic<int64_t> g_batch_group{0};               // 0 = automatic rows per nomination group, else 16 / 32 / 64
 static std::atomic<int64_t> g_batch_fp16{1};                // nominate on fp16 operand copies (0: the fp32 rows as tf32)
 static int g_sms = 0;
@@ -473,7 +474,9 @@ static int batch_prepare(cudaStream_t st, Segment* s, bool cosine, bool* ok, boo
   *ok = false;
   *half = false;
   if (!s->tm_ok) {
-    if (!batch_encode_segment_map(s->tmX, s->X, s->n, s->d, s->d, false)) return VS_OK;
+    if (!batch_encode_segment_map(s->tmX, s->X, s->n, s->d, s->d, false, 256) ||
+        !batch_encode_segment_map(s->tmX_b128, s->X, s->n, s->d, s->d, false, 128))
+      return VS_OK;
     s->tm_ok = true;
   }
   if (!s->ab[m]) {
@@ -510,7 +513,8 @@ static int batch_prepare(cudaStream_t st, Segment* s, bool cosine, bool* ok, boo
     } else {
       cudaError_t e = launch_row_convert(s->X, s->n, s->d, dp, sx, xh, g_sms, st);
       if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-      if (e != cudaSuccess || !batch_encode_segment_map(s->tmXh, xh, s->n, s->d, dp, true)) {
+      if (e != cudaSuccess || !batch_encode_segment_map(s->tmXh, xh, s->n, s->d, dp, true, 256) ||
+          !batch_encode_segment_map(s->tmXh_b128, xh, s->n, s->d, dp, true, 128)) {
         cudaFree(xh);
         if (e != cudaSuccess) return cuda_fail(e, "row_convert");
       } else {
@@ -534,7 +538,7 @@ static int batch_chunk(const BatchLaunch& p, int nq) {
 }
 static size_t batch_scratch_need(const BatchLaunch& p, int nq) {
   const int c = batch_chunk(p, nq);
-  const size_t cp = (size_t)((c + 127) / 128 * 128);
+  const size_t cp = (size_t)((c + 255) / 256 * 256);
   const size_t gm = cp * p.gm_stride * 4;
   return Arena::need({gm, (size_t)(1 + 2 * (size_t)c) * 4, (size_t)c * batch_partial_keys(p, c) * 16,
                       p.half ? (size_t)c * p.dp * 2 : 0, p.half ? cp * 4 : 0});
@@ -552,14 +556,15 @@ static int batch_run_dev(cudaStream_t st, const Segment* s, const BatchLaunch& p
     Arena A(scratch);
     BatchLaunch L = p;
     L.X = s->X; L.skip = s->skip; L.q = d_q + (size_t)q0 * s->d; L.nq = c;
-    L.tmX = p.half ? s->tmXh : s->tmX; L.x_scale = s->x_scale;
+    L.tmX = p.half ? s->tmXh : s->tmX; L.tmX128 = p.half ? s->tmXh_b128 : s->tmX_b128; L.x_scale = s->x_scale;
+    L.pairs = g_batch_pairs.load() != 0;
     L.coef = static_cast<const float*>(s->ab[m]); L.stats = static_cast<const SegStats*>(s->stats[m]);
-    L.gm = A.take<float>((size_t)((chunk + 127) / 128 * 128) * p.gm_stride);
+    L.gm = A.take<float>((size_t)((chunk + 255) / 256 * 256) * p.gm_stride);
     L.fb = A.take<int32_t>(1 + 2 * (size_t)chunk);
     L.partial_keys = batch_partial_keys(p, c);
     L.partial = A.take<ulonglong2>((size_t)chunk * batch_partial_keys(p, chunk));
     L.qh = p.half ? A.take<char>((size_t)chunk * p.dp * 2) : nullptr;
-    L.qinv = p.half ? A.take<float>((size_t)((chunk + 127) / 128 * 128)) : nullptr;
+    L.qinv = p.half ? A.take<float>((size_t)((chunk + 255) / 256 * 256)) : nullptr;
     L.ctrl = d_ticket;
     L.ids_out = d_ids + (size_t)q0 * os; L.scores_out = d_scores + (size_t)q0 * os; L.counts_out = d_counts + q0;
     L.id_base = s->id_base; L.out_stride = os; L.warp_min_q = (int)g_batch_warp_min_q.load();
@@ -652,6 +657,10 @@ int32_t vs_set_option(const char* name, int64_t value) {
   if (!strcmp(name, "scan_reserve_sms")) {
     if (value < 0 || value >= 128) return fail(VS_EINVAL, "scan_reserve_sms must be in 0..127");
     g_scan_reserve_sms.store(value);
+    return VS_OK;
+  }
+  if (!strcmp(name, "batch_pairs")) {
+    g_batch_pairs.store(value != 0);
     return VS_OK;
   }
   if (!strcmp(name, "batch_group")) {
@@ -1389,13 +1398,14 @@ int32_t vs_debug_batch_groupmins(uint64_t h, const float* q, int32_t nq, int32_t
   BatchLaunch L = bp;
   const int m = cosine ? 1 : 0;
   L.X = s->X; L.skip = s->skip; L.q = dq; L.nq = nq; L.tmX = half ? s->tmXh : s->tmX; L.x_scale = s->x_scale;
+  L.tmX128 = half ? s->tmXh_b128 : s->tmX_b128; L.pairs = g_batch_pairs.load() != 0;
   L.coef = static_cast<const float*>(s->ab[m]); L.stats = static_cast<const SegStats*>(s->stats[m]);
   const int chunk = batch_chunk(bp, nq);
-  L.gm = B.take<float>((size_t)((chunk + 127) / 128 * 128) * bp.gm_stride);
+  L.gm = B.take<float>((size_t)((chunk + 255) / 256 * 256) * bp.gm_stride);
   L.fb = B.take<int32_t>(1 + 2 * (size_t)chunk);
   L.partial = B.take<ulonglong2>((size_t)chunk * batch_partial_keys(bp, chunk));
   L.qh = half ? B.take<char>((size_t)chunk * bp.dp * 2) : nullptr;
-  L.qinv = half ? B.take<float>((size_t)((chunk + 127) / 128 * 128)) : nullptr;
+  L.qinv = half ? B.take<float>((size_t)((chunk + 255) / 256 * 256)) : nullptr;
   L.gemm_only = true;
   CK(launch_batch(L, c->stream), "batched scan launch");
   CK(cudaMemcpy2DAsync(gm_out, (size_t)bp.ngroups * 4, L.gm, (size_t)bp.gm_stride * 4, (size_t)bp.ngroups * 4, nq,

@@ -223,6 +223,61 @@ query_convert_kernel(const float* __restrict__ Q, int nq, int nq_pad, int d, int
   if (lane == 0) qinv[qi] = 1.0f / (sx * sq);
 }
 
+// Epilogue core shared by the nomination kernels: reduce this thread's 128 accumulator columns (TMEM address
+// taddr, columns taddr .. taddr + 127 of its lane) to (BQ_N / 2) / GROUP minima of a(q, x).  The four 32-column
+// TMEM loads are software-pipelined: load h + 1 is in flight while load h is reduced.
+template <bool COSINE, int GROUP>
+__device__ __forceinline__ void bq_reduce_columns(uint32_t taddr, const float* __restrict__ myc, float m2, float qs,
+                                                  float (&mins)[(BQ_N / 2) / GROUP]) {
+  constexpr int NM = (BQ_N / 2) / GROUP;
+  const float inf = __int_as_float(0x7f800000);
+#pragma unroll
+  for (int i = 0; i < NM; i++) mins[i] = inf;
+  uint32_t v[2][32];
+  tc_ld32(taddr, v[0]);
+#pragma unroll
+  for (int h = 0; h < 4; h++) {
+    tc_wait_ld();
+    tc_pin32(v[h & 1]);
+    if (h < 3) tc_ld32(taddr + (uint32_t)(h + 1) * 32, v[(h + 1) & 1]);
+    const float4* p4 = reinterpret_cast<const float4*>(myc + h * 32);
+    float pm[2];  // columns 0..15 and 16..31 of this load
+#pragma unroll
+    for (int hh = 0; hh < 2; hh++) {
+      float m0 = inf, m1 = inf;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const float4 p = p4[hh * 4 + j];  // coefficients of four rows; same address in every lane: broadcast
+        const int c = hh * 16 + 4 * j;
+        if (COSINE) {  // a = c <q,x>; the per-query scale is applied after the minimum
+          m0 = fminf(m0, __uint_as_float(v[h & 1][c]) * p.x);
+          m1 = fminf(m1, __uint_as_float(v[h & 1][c + 1]) * p.y);
+          m0 = fminf(m0, __uint_as_float(v[h & 1][c + 2]) * p.z);
+          m1 = fminf(m1, __uint_as_float(v[h & 1][c + 3]) * p.w);
+        } else {       // a = c - 2 <q,x>
+          m0 = fminf(m0, fmaf(__uint_as_float(v[h & 1][c]), m2, p.x));
+          m1 = fminf(m1, fmaf(__uint_as_float(v[h & 1][c + 1]), m2, p.y));
+          m0 = fminf(m0, fmaf(__uint_as_float(v[h & 1][c + 2]), m2, p.z));
+          m1 = fminf(m1, fmaf(__uint_as_float(v[h & 1][c + 3]), m2, p.w));
+        }
+      }
+      pm[hh] = fminf(m0, m1);
+    }
+    if (GROUP == 16) {
+      mins[(2 * h) % NM] = pm[0];
+      mins[(2 * h + 1) % NM] = pm[1];
+    } else if (GROUP == 32) {
+      mins[h % NM] = fminf(pm[0], pm[1]);
+    } else {
+      mins[(h / 2) % NM] = fminf(mins[(h / 2) % NM], fminf(pm[0], pm[1]));
+    }
+  }
+  if (COSINE) {
+#pragma unroll
+    for (int i = 0; i < NM; i++) mins[i] *= qs;
+  }
+}
+
 // ---- (2) tensor-core nomination ---------------------------------------------------------------------------------
 // grid.x = nqb * nsplit; CTA (qb, split) owns query block qb and row tiles split, split + nsplit, ...
 // (CTAs of the same split run side by side, so a row tile is fetched from HBM once and re-read from L2).
@@ -370,50 +425,7 @@ batch_gemm_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       tc_fence_after();
       constexpr int NM = (BQ_N / 2) / GROUP;  // minima this thread produces per tile (GROUP = 16 / 32 / 64 rows)
       float mins[NM];
-#pragma unroll
-      for (int i = 0; i < NM; i++) mins[i] = inf;
-#pragma unroll
-      for (int h = 0; h < 4; h++) {  // 32 columns per TMEM load
-        uint32_t v[32];
-        tc_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(a * BQ_N + ch * (BQ_N / 2) + h * 32), v);
-        tc_wait_ld();
-        tc_pin32(v);
-        const float4* p4 = reinterpret_cast<const float4*>(myc + h * 32);
-        float pm[2];  // columns 0..15 and 16..31 of this load
-#pragma unroll
-        for (int hh = 0; hh < 2; hh++) {
-          float m0 = inf, m1 = inf;
-#pragma unroll
-          for (int j = 0; j < 4; j++) {
-            const float4 p = p4[hh * 4 + j];  // coefficients of four rows; same address in every lane: broadcast
-            const int c = hh * 16 + 4 * j;
-            if (COSINE) {  // a = c <q,x>; the per-query scale is applied after the minimum
-              m0 = fminf(m0, __uint_as_float(v[c]) * p.x);
-              m1 = fminf(m1, __uint_as_float(v[c + 1]) * p.y);
-              m0 = fminf(m0, __uint_as_float(v[c + 2]) * p.z);
-              m1 = fminf(m1, __uint_as_float(v[c + 3]) * p.w);
-            } else {       // a = c - 2 <q,x>
-              m0 = fminf(m0, fmaf(__uint_as_float(v[c]), m2, p.x));
-              m1 = fminf(m1, fmaf(__uint_as_float(v[c + 1]), m2, p.y));
-              m0 = fminf(m0, fmaf(__uint_as_float(v[c + 2]), m2, p.z));
-              m1 = fminf(m1, fmaf(__uint_as_float(v[c + 3]), m2, p.w));
-            }
-          }
-          pm[hh] = fminf(m0, m1);
-        }
-        if (GROUP == 16) {
-          mins[(2 * h) % NM] = pm[0];
-          mins[(2 * h + 1) % NM] = pm[1];
-        } else if (GROUP == 32) {
-          mins[h % NM] = fminf(pm[0], pm[1]);
-        } else {
-          mins[(h / 2) % NM] = fminf(mins[(h / 2) % NM], fminf(pm[0], pm[1]));
-        }
-      }
-      if (COSINE) {
-#pragma unroll
-        for (int i = 0; i < NM; i++) mins[i] *= qs;
-      }
+      bq_reduce_columns<COSINE, GROUP>(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(a * BQ_N + ch * (BQ_N / 2)), myc, m2, qs, mins);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty + a);
@@ -431,6 +443,208 @@ batch_gemm_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ---- (2b) the same nomination on CTA PAIRS (tcgen05 cta_group::2) ---------------------------------------------------
+// Batches of more than 128 queries over short vectors.  Two CTAs on the SMs of one TPC form a cluster: each keeps
+// its own 128-query block resident and loads HALF of every 256-row tile; one thread of the leader CTA issues
+// tcgen05.mma.cta_group::2 (M = 256: both query blocks, N = 256), which reads A and its half of B from each
+// CTA's shared memory and writes each CTA's 128 accumulator lanes into that CTA's TMEM.  Per flop that halves
+// the L2 -> SM traffic of the row tiles and cuts the operand reads from shared memory by a third -- the two
+// things suspected of bounding batch_gemm_kernel at d = 128 (tensor pipe 59 % active).  Measured (r1, 1M x 128,
+// 1024 queries): 258 us against 250 us for the single-CTA kernel, and both drop to the same 212 us with the epilogue
+// reduction stubbed out -- so neither operand path is the limiter at this shape.  Off by default ("batch_pairs"),
+// parity-tested, kept as the starting point for deeper MMA/epilogue decoupling.
+//   full[s] / afull live in the leader: both CTAs' TMA loads complete_tx on the leader's barrier (peer bit masked);
+//   empty[s], tfull[a]: tcgen05.commit multicasts the arrival to both CTAs; tempty[a]: the epilogue warps of both
+//   CTAs arrive on the leader's barrier (mapa + remote arrive).
+constexpr int BQ_PAIR_MAX_STAGES = 12;
+constexpr uint32_t BQ_BH_BYTES = (BQ_N / 2) * 128;  // one k-block of this CTA's half of the row tile
+constexpr uint32_t BQ_IDESC_TF32_M256 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BQ_N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+constexpr uint32_t BQ_IDESC_F16_M256 = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BQ_N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// 2-SM TMA load: the bytes are credited to the LEADER CTA's barrier at the same shared-memory offset
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {  // arrives on this barrier in BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+// arrive on the leader CTA's copy of `bar` (plain arrive: a cluster-scope release would add MEMBAR.ALL.GPU per tile;
+// the TMEM reads it orders are fenced by tcgen05.fence::before_thread_sync)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("{\n.reg .b32 ra;\nmapa.shared::cluster.u32 ra, %0, %1;\nmbarrier.arrive.shared::cluster.b64 _, [ra];\n}"
+               ::"r"(smem_u32(bar)), "r"(0) : "memory");
+}
+__device__ __forceinline__ void tc_mma_pair(bool half, uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  if (half)
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+  else
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+
+template <bool HALF, bool COSINE, int GROUP>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BQ_THREADS, 1)
+batch_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmX /* 128-row box */,
+                       const float* __restrict__ coef, const float* __restrict__ qinv, int64_t n, int num_kb, int nstages,
+                       int nqp /* pairs of query blocks */, int64_t tiles, float* __restrict__ gm, int64_t gm_stride) {
+  extern __shared__ __align__(1024) uint8_t bq_smem[];
+  uint8_t* base = bq_smem;
+  if ((smem_u32(base) & 1023u) != 0) __trap();
+  constexpr int KB_ELEMS = HALF ? 64 : 32;
+  uint8_t* aq = base;                                   // [num_kb][16 KB] this CTA's query block
+  uint8_t* stages = base + (size_t)num_kb * BQ_A_BYTES;  // [nstages][16 KB] this CTA's half of the row tile
+  float* sm_coef = reinterpret_cast<float*>(stages + (size_t)nstages * BQ_BH_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sm_coef) + BQ_AB_BYTES);
+  uint64_t* full = bars;                                  // leader's copy is the live one
+  uint64_t* empty = bars + BQ_PAIR_MAX_STAGES;            // one per CTA
+  uint64_t* tfull = bars + 2 * BQ_PAIR_MAX_STAGES;        // one per CTA
+  uint64_t* tempty = bars + 2 * BQ_PAIR_MAX_STAGES + 2;   // leader's copy is the live one
+  uint64_t* afull = bars + 2 * BQ_PAIR_MAX_STAGES + 4;    // leader's copy is the live one
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * BQ_PAIR_MAX_STAGES + 5);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();
+  const int pair = blockIdx.x >> 1;
+  const int qp = pair % nqp;
+  const int split = pair / nqp;
+  const int nsplit = (gridDim.x >> 1) / nqp;
+  const int qb = 2 * qp + rank;
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmQ)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmX)) : "memory");
+    for (int s = 0; s < nstages; s++) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, 1);
+    }
+    for (int a = 0; a < 2; a++) {
+      mbar_init(tfull + a, 1);
+      mbar_init(tempty + a, 2 * BQ_EPI_WARPS);
+    }
+    mbar_init(afull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();  // both CTAs' barriers are initialised before anything signals them
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(s_tmem);
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer (both CTAs) =====
+      if (rank == 0) mbar_expect_tx(afull, 2u * (uint32_t)num_kb * BQ_A_BYTES);
+      for (int kb = 0; kb < num_kb; kb++) tma_load_2d_pair(aq + (size_t)kb * BQ_A_BYTES, &tmQ, kb * KB_ELEMS, qb * BQ_M, afull);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int64_t tile = split; tile < tiles; tile += nsplit) {
+        for (int kb = 0; kb < num_kb; kb++) {
+          mbar_wait(empty + s, ph ^ 1);
+          if (rank == 0) mbar_expect_tx(full + s, 2u * BQ_BH_BYTES);
+          tma_load_2d_pair(stages + (size_t)s * BQ_BH_BYTES, &tmX, kb * KB_ELEMS, (int)(tile * BQ_N + rank * (BQ_N / 2)), full + s);
+          if (++s == nstages) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {  // ===== MMA issuer (leader CTA only) =====
+      int s = 0, it = 0;
+      uint32_t ph = 0;
+      mbar_wait(afull, 0);
+      for (int64_t tile = split; tile < tiles; tile += nsplit, it++) {
+        const int a = it & 1;
+        mbar_wait(tempty + a, ((it >> 1) & 1) ^ 1);  // both CTAs' epilogues have drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)a * BQ_N;
+        for (int kb = 0; kb < num_kb; kb++) {
+          mbar_wait(full + s, ph);
+          tc_fence_after();
+          const uint64_t adesc = umma_desc_sw128(smem_u32(aq + (size_t)kb * BQ_A_BYTES));
+          const uint64_t bdesc = umma_desc_sw128(smem_u32(stages + (size_t)s * BQ_BH_BYTES));
+#pragma unroll
+          for (int kk = 0; kk < 4; kk++)
+            tc_mma_pair(HALF, d_tmem, adesc + 2 * kk, bdesc + 2 * kk, HALF ? BQ_IDESC_F16_M256 : BQ_IDESC_TF32_M256, (kb | kk) != 0 ? 1u : 0u);
+          tc_commit_pair(empty + s);
+          if (++s == nstages) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+        tc_commit_pair(tfull + a);
+      }
+    }
+  } else if (warp >= 4) {  // ===== epilogue (both CTAs, each on its own 128 accumulator lanes) =====
+    const int ew = warp - 4;
+    const int lq = ew & 3;
+    const int ch = ew >> 2;
+    const float inf = __int_as_float(0x7f800000);
+    const float qs = HALF ? qinv[qb * BQ_M + lq * 32 + lane] : 1.0f;
+    const float m2 = -2.0f * qs;
+    const float dead = COSINE ? __int_as_float(0x7fc00000) : inf;
+    float cnext[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int64_t r = (int64_t)split * BQ_N + ch * (BQ_N / 2) + i * 32 + lane;
+      cnext[i] = (split < tiles && r < n) ? __ldg(coef + r) : dead;
+    }
+    int it = 0;
+    for (int64_t tile = split; tile < tiles; tile += nsplit, it++) {
+      const int a = it & 1;
+      float* myc = sm_coef + (size_t)(ew * 2 + a) * (BQ_N / 2);
+#pragma unroll
+      for (int i = 0; i < 4; i++) myc[i * 32 + lane] = cnext[i];
+      __syncwarp();
+      {
+        const int64_t nt = tile + nsplit;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const int64_t r = nt * BQ_N + ch * (BQ_N / 2) + i * 32 + lane;
+          cnext[i] = (nt < tiles && r < n) ? __ldg(coef + r) : dead;
+        }
+      }
+      mbar_wait(tfull + a, (it >> 1) & 1);
+      tc_fence_after();
+      constexpr int NM = (BQ_N / 2) / GROUP;  // minima this thread produces per tile (GROUP = 16 / 32 / 64 rows)
+      float mins[NM];
+      bq_reduce_columns<COSINE, GROUP>(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(a * BQ_N + ch * (BQ_N / 2)), myc, m2, qs, mins);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(tempty + a);
+      float* dst = gm + (size_t)(qb * BQ_M + lq * 32 + lane) * gm_stride + tile * (BQ_N / GROUP) + ch * NM;
+      if (NM == 2) {
+        *reinterpret_cast<float2*>(dst) = make_float2(mins[0], mins[1]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < NM; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(mins[i], mins[(i + 1) % NM], mins[(i + 2) % NM], mins[(i + 3) % NM]);
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();  // nobody leaves (or frees TMEM) while the peer may still signal or read
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 
@@ -823,9 +1037,9 @@ static bool encode_rows_map(CUtensorMap* tm, const void* base, int64_t rows, int
 }
 
 // tensor map over the segment's rows: the fp32 rows themselves (half = false) or their fp16 copy with pitch dp
-bool batch_encode_segment_map(void* tm128, const void* X, int64_t n, int d, int64_t pitch, bool half) {
+bool batch_encode_segment_map(void* tm128, const void* X, int64_t n, int d, int64_t pitch, bool half, int box_rows) {
   static_assert(sizeof(CUtensorMap) == 128, "tensor map size");
-  return encode_rows_map(reinterpret_cast<CUtensorMap*>(tm128), X, n, d, pitch, half, BQ_N);
+  return encode_rows_map(reinterpret_cast<CUtensorMap*>(tm128), X, n, d, pitch, half, box_rows);
 }
 
 // host copy of the device-side bound, for diagnostics
@@ -888,6 +1102,15 @@ static GemmKern pick_gemm(bool stat, bool half, bool cosine, int group) {
   return group == 16 ? pick_gemm_g<16>(stat, half, cosine) : (group == 32 ? pick_gemm_g<32>(stat, half, cosine) : pick_gemm_g<64>(stat, half, cosine));
 }
 
+template <int GROUP>
+static GemmKern pick_gemm_pair_g(bool half, bool cosine) {
+  if (half) return cosine ? batch_gemm_pair_kernel<true, true, GROUP> : batch_gemm_pair_kernel<true, false, GROUP>;
+  return cosine ? batch_gemm_pair_kernel<false, true, GROUP> : batch_gemm_pair_kernel<false, false, GROUP>;
+}
+static GemmKern pick_gemm_pair(bool half, bool cosine, int group) {
+  return group == 16 ? pick_gemm_pair_g<16>(half, cosine) : (group == 32 ? pick_gemm_pair_g<32>(half, cosine) : pick_gemm_pair_g<64>(half, cosine));
+}
+
 // dynamic shared memory of batch_select_kernel with nw warps: collectors, group list, query
 static size_t batch_select_smem(const BatchLaunch& L, int nw) {
   size_t coll = (size_t)nw * topk_warp_smem(L.kp);
@@ -926,6 +1149,14 @@ bool batch_configure(BatchLaunch& L, int sms) {
     if (ns > BQ_MAX_STAGES) ns = BQ_MAX_STAGES;
     L.gemm_stages = ns;
     L.gemm_smem = fixed + (L.gemm_stat ? a_res : 0) + (size_t)ns * per;
+    // CTA pairs (batches > 128 queries): resident query block + at least 4 stages of half a row tile
+    L.pair_stages = 0;
+    if (fixed + a_res + 4 * (size_t)BQ_BH_BYTES + 128 <= BQ_GEMM_SMEM_BUDGET) {
+      int ns2 = (int)((BQ_GEMM_SMEM_BUDGET - fixed - a_res - 128) / BQ_BH_BYTES);
+      if (ns2 > BQ_PAIR_MAX_STAGES) ns2 = BQ_PAIR_MAX_STAGES;
+      L.pair_stages = ns2;
+      L.pair_smem = fixed + a_res + 128 + (size_t)ns2 * BQ_BH_BYTES;
+    }
   }
   // candidate groups per select CTA: the k-th smallest group minimum admits about k groups, the slack a few more
   L.cap = 4 * L.k + 256;
@@ -951,6 +1182,7 @@ bool batch_configure(BatchLaunch& L, int sms) {
     cudaError_t e;
     e = set_smem_attr(pick_gemm(L.gemm_stat, L.half, L.cosine, L.group), BQ_GEMM_SMEM_BUDGET);
     if (e != cudaSuccess) return false;
+    if (L.pair_stages > 0 && set_smem_attr(pick_gemm_pair(L.half, L.cosine, L.group), BQ_GEMM_SMEM_BUDGET) != cudaSuccess) return false;
   }
   if (set_smem_attr(pick_select(TPR, L.cosine, L.k), BQ_SELECT_SMEM_MAX) != cudaSuccess) return false;
   if (set_smem_attr(pick_fallback(TPR, L.cosine, L.k), BQ_SELECT_SMEM_MAX) != cudaSuccess) return false;
@@ -980,21 +1212,31 @@ cudaError_t launch_batch(const BatchLaunch& L, cudaStream_t st) {
   const int num_kb = (L.d + kbe - 1) / kbe;
   if (L.half) {
     count_launch();
-    query_convert_kernel<<<(nqb * BQ_M + 7) / 8, 256, 0, st>>>(L.q, L.nq, nqb * BQ_M, L.d, L.dp, L.x_scale, static_cast<__half*>(L.qh), L.qinv);
+    const int nq_pad = (L.nq + 2 * BQ_M - 1) / (2 * BQ_M) * (2 * BQ_M);  // whole pairs of query blocks
+    query_convert_kernel<<<(nq_pad + 7) / 8, 256, 0, st>>>(L.q, L.nq, nq_pad, L.d, L.dp, L.x_scale, static_cast<__half*>(L.qh), L.qinv);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if (!encode_rows_map(&tmQ, L.qh, L.nq, L.d, L.dp, true, BQ_M)) return cudaErrorInvalidValue;
   } else {
     if (!encode_rows_map(&tmQ, L.q, L.nq, L.d, L.d, false, BQ_M)) return cudaErrorInvalidValue;
   }
-  const CUtensorMap tmX = *reinterpret_cast<const CUtensorMap*>(L.tmX);
-  int nsplit = L.sms / nqb;
-  if (nsplit < 1) nsplit = 1;
-  if (nsplit > L.tiles) nsplit = (int)L.tiles;
   if ((e = cudaMemsetAsync(L.fb, 0, sizeof(int32_t) * (1 + 2 * (size_t)L.nq), st)) != cudaSuccess) return e;
   count_launch();
-  const int grid = nqb * nsplit;
-  pick_gemm(L.gemm_stat, L.half, L.cosine, L.group)<<<grid, BQ_THREADS, L.gemm_smem, st>>>(tmQ, tmX, L.coef, L.qinv, L.n, num_kb,
-                                                                                 L.gemm_stages, nqb, L.tiles, L.gm, L.gm_stride);
+  if (L.pair_stages > 0 && L.pairs && L.nq > BQ_M && L.tmX128 != nullptr && L.sms >= 2) {
+    const CUtensorMap tmX = *reinterpret_cast<const CUtensorMap*>(L.tmX128);
+    const int nqp = (nqb + 1) / 2;
+    int nsplit = (L.sms / 2) / nqp;
+    if (nsplit < 1) nsplit = 1;
+    if (nsplit > L.tiles) nsplit = (int)L.tiles;
+    pick_gemm_pair(L.half, L.cosine, L.group)<<<2 * nqp * nsplit, BQ_THREADS, L.pair_smem, st>>>(
+        tmQ, tmX, L.coef, L.qinv, L.n, num_kb, L.pair_stages, nqp, L.tiles, L.gm, L.gm_stride);
+  } else {
+    const CUtensorMap tmX = *reinterpret_cast<const CUtensorMap*>(L.tmX);
+    int nsplit = L.sms / nqb;
+    if (nsplit < 1) nsplit = 1;
+    if (nsplit > L.tiles) nsplit = (int)L.tiles;
+    pick_gemm(L.gemm_stat, L.half, L.cosine, L.group)<<<nqb * nsplit, BQ_THREADS, L.gemm_smem, st>>>(
+        tmQ, tmX, L.coef, L.qinv, L.n, num_kb, L.gemm_stages, nqb, L.tiles, L.gm, L.gm_stride);
+  }
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   if (L.gemm_only) return cudaSuccess;  // diagnostics: group minima only
   const int TPR = L.lanes / 4;

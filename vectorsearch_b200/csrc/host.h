@@ -31,6 +31,7 @@ struct Segment {
   float x_scale = 1.0f;
   bool xh_tried = false;                // the copy was attempted (it is optional: tf32 operands otherwise)
   alignas(64) unsigned char tmXh[128];  // CUtensorMap over Xh
+  alignas(64) unsigned char tmX_b128[128], tmXh_b128[128];  // the same two with 128-row boxes (CTA pairs)
 };
 
 int fail(int code, const char* fmt, ...);

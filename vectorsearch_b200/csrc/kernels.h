@@ -61,14 +61,16 @@ struct BatchLaunch {
   int nq;
   int k, kp;
   const void* tmX;       // host copy of the CUtensorMap (128 bytes) over the operand rows (fp32 rows or their fp16 copy)
+  const void* tmX128;    // the same with a 128-row box (CTA pairs load half a row tile each), nullable
+  bool pairs;            // allow the cta_group::2 kernel for batches of more than 128 queries
   bool half;             // operands are fp16 copies (kind::f16) instead of the fp32 data read as tf32
   int dp;                // fp16 row pitch in elements (d rounded up to 8)
   float x_scale;         // power of two the fp16 row copy was scaled by
   void* qh;              // [nq][dp] fp16 scratch for the scaled queries (half only)
-  float* qinv;           // [round_up(nq, 128)] 1 / (x_scale * query scale) (half only)
+  float* qinv;           // [round_up(nq, 256)] 1 / (x_scale * query scale) (half only)
   const float* coef;     // [n] per-row nomination coefficient of this metric
   const SegStats* stats; // device
-  float* gm;             // [round_up(nq, 128)][gm_stride] group minima
+  float* gm;             // [round_up(nq, 256)][gm_stride] group minima
   int32_t* fb;           // [1 + 2 nq]: fallback count, fallback query list, per-query "listed" flags
   ulonglong2* partial;   // [nq][partial_keys]
   int64_t partial_keys;
@@ -88,10 +90,12 @@ struct BatchLaunch {
   size_t gemm_smem, select_smem, selw_smem, fb_smem;
   bool gemm_stat;        // query block resident in shared memory (short vectors)
   int gemm_stages;
+  int pair_stages;       // > 0: the cta_group::2 kernel fits (resident query block per CTA)
+  size_t pair_smem;
 };
 bool batch_supported(int d, int lanes, bool cosine, int64_t n);
 double batch_slack_host(bool cosine, bool half, int d, double xmax, double qn);
-bool batch_encode_segment_map(void* tm128, const void* rows, int64_t n, int d, int64_t pitch, bool half);
+bool batch_encode_segment_map(void* tm128, const void* rows, int64_t n, int d, int64_t pitch, bool half, int box_rows);
 cudaError_t launch_row_convert(const float* X, int64_t n, int d, int dp, float sx, void* Xh, int sms, cudaStream_t st);
 bool batch_configure(BatchLaunch& L, int sms);          // from (n, d, lanes, cosine, k, half)
 int64_t batch_partial_keys(const BatchLaunch& L, int nq);  // keys of `partial` per query for a chunk of nq
