@@ -1,0 +1,28 @@
+"""Development helper: phase timestamps of batch_select_kernel per query (build libvsgpu with -DVS_BQ_STAMPS)."""
+import ctypes as C, sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import vectorsearch_b200 as vs
+from vectorsearch_b200 import _lib as L
+vs.init(0); lib = vs.load()
+n, d, nq, k = 1_000_000, 128, int(sys.argv[1]) if len(sys.argv) > 1 else 1024, 10
+seg = vs.Segment.generate(42, 0, n, d)
+dev = torch.device("cuda:0")
+q = torch.rand(nq, d, device=dev) * 2 - 1
+ids = torch.zeros(nq, k, dtype=torch.int64, device=dev); sc = torch.zeros(nq, k, dtype=torch.float64, device=dev); cn = torch.zeros(nq, dtype=torch.int32, device=dev)
+st = torch.cuda.current_stream().cuda_stream
+for it in range(4):
+    L.check(lib.vs_bruteforce_topk_dev(seg.handle, q.data_ptr(), nq, k, 0, ids.data_ptr(), sc.data_ptr(), cn.data_ptr(), st))
+torch.cuda.synchronize()
+buf = np.zeros(8 * 1024, dtype=np.uint64)
+lib.vs_debug_read_stamps_batch.argtypes = [C.c_void_p, C.c_int64]
+lib.vs_debug_read_stamps_batch(buf.ctypes.data_as(C.c_void_p), buf.nbytes)
+s = buf.reshape(1024, 8)[:min(nq, 1024), :7].astype(np.int64)
+t0 = s[:, 0].min()
+names = ["start", "setup(q, slack)", "phase1 (T)", "phase2 (list)", "prefetch issued", "phase3 (exact)", "epilogue"]
+print("kernel span: %.1f us; CTA start spread: %.1f us" % ((s[:, 6].max() - t0) / 1e3, (s[:, 0].max() - t0) / 1e3))
+for i in range(1, 7):
+    dt = (s[:, i] - s[:, i - 1]) / 1e3
+    print(f"{names[i]:18s} median {np.median(dt):7.2f}  p90 {np.percentile(dt, 90):7.2f}  max {dt.max():7.2f} us")
+dt = (s[:, 6] - s[:, 0]) / 1e3
+print(f"{'whole CTA':18s} median {np.median(dt):7.2f}  p90 {np.percentile(dt, 90):7.2f}  max {dt.max():7.2f} us")

@@ -694,6 +694,9 @@ int32_t vs_set_option(const char* name, int64_t value) {
   }
   return fail(VS_EINVAL, "unknown option %s", name);
 }
+#ifdef VS_BQ_STAMPS
+int32_t vs_debug_read_stamps_batch(void* dst, int64_t bytes) { return vs::debug_read_stamps_batch(dst, (size_t)bytes); }
+#endif
 #ifdef VS_PHASE_STAMPS
 int32_t vs_debug_read_stamps(void* dst, int64_t bytes) { return vs::debug_read_stamps(dst, (size_t)bytes); }
 int32_t vs_debug_read_stamps_adc(void* dst, int64_t bytes) { return vs::debug_read_stamps_adc(dst, (size_t)bytes); }

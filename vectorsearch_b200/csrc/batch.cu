@@ -47,6 +47,7 @@ constexpr uint32_t BQ_AB_BYTES = BQ_EPI_WARPS * 2 * (BQ_N / 2) * 4;  // row coef
 constexpr size_t BQ_GEMM_SMEM_BUDGET = 224 * 1024;  // dynamic shared memory of the nomination kernel
 constexpr int BQ_SELECT_THREADS = 256;
 constexpr int BQ_FB_SLOTS = 8;  // grid.y of the fallback scan
+constexpr int BQ_SEL_MLP = 8;     // float4 loads of group minima in flight per thread of the selection passes
 constexpr int BQ_TMIN_MAX_K = 64;  // up to this k the select threshold comes from per-thread minima
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------------
@@ -648,6 +649,24 @@ batch_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   }
 }
 
+// development-only phase timestamps of the selection kernel (build with -DVS_BQ_STAMPS; tools/select_stamps.py)
+#ifdef VS_BQ_STAMPS
+static __device__ unsigned long long g_bq_stamps[8 * 1024];
+__device__ __forceinline__ void bq_stamp(int ph) {
+  if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y < 1024) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    g_bq_stamps[blockIdx.y * 8 + ph] = t;
+  }
+}
+int debug_read_stamps_batch(void* dst, size_t bytes) {
+  cudaDeviceSynchronize();
+  return (int)cudaMemcpyFromSymbol(dst, g_bq_stamps, bytes);
+}
+#else
+__device__ __forceinline__ void bq_stamp(int) {}
+#endif
+
 // ---- (3) threshold, candidate groups, exact ranking --------------------------------------------------------------
 // |a(q, x) - exact| <= slack.  Operand rounding: tf32 truncates both operands (2^-10 each), the fp16 copies are
 // rounded to nearest (2^-11 each, plus a subnormal floor that the power-of-two scaling keeps below 2^-37 relative);
@@ -697,6 +716,7 @@ batch_select_kernel(const float* __restrict__ X, int64_t n, int d, const float* 
   __shared__ double s_qq;
   __shared__ float s_q2;
   __shared__ int s_cnt;
+  bq_stamp(0);
   for (int i = threadIdx.x; i < d; i += blockDim.x) qs[i] = q[i];
   if (COSINE && threadIdx.x == 32) s_qq = ref_sum_thread_L<L, REF_DOT>(q, q, d);
   if (warp == 0) {
@@ -719,6 +739,7 @@ batch_select_kernel(const float* __restrict__ X, int64_t n, int d, const float* 
   const float qn = COSINE ? (float)sqrt(qq) : 0.0f;
   const double slack = batch_slack(COSINE, half != 0, d, sqrt((double)__uint_as_float(stats->xmax2_bits)), sqrt((double)q2));
 
+  bq_stamp(1);
   // phase 1: T = an upper bound of the k-th smallest group minimum of this slice
   const int64_t g0 = ngroups * blockIdx.x / gridDim.x, g1 = ngroups * (blockIdx.x + 1) / gridDim.x;
   float tau = __int_as_float(0x7f800000);
@@ -731,14 +752,26 @@ batch_select_kernel(const float* __restrict__ X, int64_t n, int d, const float* 
     {
       const float4* gm4 = reinterpret_cast<const float4*>(gmq);
       const int64_t c0 = g0 >> 2, c1 = (g1 + 3) >> 2;
-#pragma unroll 4
-      for (int64_t c = c0 + threadIdx.x; c < c1; c += blockDim.x) {
-        const float4 v = gm4[c];
-        const int64_t g = c << 2;
-        if (g >= g0 && g < g1) tm = fminf(tm, v.x);
-        if (g + 1 >= g0 && g + 1 < g1) tm = fminf(tm, v.y);
-        if (g + 2 >= g0 && g + 2 < g1) tm = fminf(tm, v.z);
-        if (g + 3 >= g0 && g + 3 < g1) tm = fminf(tm, v.w);
+      const float4 inf4 = make_float4(tm, tm, tm, tm);
+      for (int64_t cb = c0 + threadIdx.x; cb < c1; cb += (int64_t)BQ_SEL_MLP * blockDim.x) {
+        float4 v[BQ_SEL_MLP];  // BQ_SEL_MLP independent loads in flight per thread: this pass is pure latency
+#pragma unroll
+        for (int j = 0; j < BQ_SEL_MLP; j++) {
+          const int64_t c = cb + (int64_t)j * blockDim.x;
+          v[j] = c < c1 ? __ldg(gm4 + c) : inf4;
+        }
+#pragma unroll
+        for (int j = 0; j < BQ_SEL_MLP; j++) {
+          const int64_t g = (cb + (int64_t)j * blockDim.x) << 2;
+          if (g >= g0 && g + 3 < g1) {
+            tm = fminf(fminf(tm, v[j].x), fminf(v[j].y, fminf(v[j].z, v[j].w)));
+          } else {  // slice boundaries
+            if (g >= g0 && g < g1) tm = fminf(tm, v[j].x);
+            if (g + 1 >= g0 && g + 1 < g1) tm = fminf(tm, v[j].y);
+            if (g + 2 >= g0 && g + 2 < g1) tm = fminf(tm, v[j].z);
+            if (g + 3 >= g0 && g + 3 < g1) tm = fminf(tm, v[j].w);
+          }
+        }
       }
     }
     tmin[threadIdx.x] = tm;
@@ -777,20 +810,32 @@ batch_select_kernel(const float* __restrict__ X, int64_t n, int d, const float* 
       if (!(tau == tau)) tau = __int_as_float(0x7f800000);
     }
   }
+  bq_stamp(2);
   // phase 2: groups that can hold a top-k row
   {
     const float4* gm4 = reinterpret_cast<const float4*>(gmq);
     const int64_t c0 = g0 >> 2, c1 = (g1 + 3) >> 2;
-#pragma unroll 4
-    for (int64_t c = c0 + threadIdx.x; c < c1; c += blockDim.x) {
-      const float4 v = gm4[c];
-      const float e[4] = {v.x, v.y, v.z, v.w};
+    const float inf = __int_as_float(0x7f800000);
+    const float4 inf4 = make_float4(inf, inf, inf, inf);
+    for (int64_t cb = c0 + threadIdx.x; cb < c1; cb += (int64_t)BQ_SEL_MLP * blockDim.x) {
+      float4 v[BQ_SEL_MLP];
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const int64_t g = (c << 2) + j;
-        if (g >= g0 && g < g1 && e[j] <= tau) {
-          const int idx = atomicAdd(&s_cnt, 1);
-          if (idx < cap) list[idx] = (int)g;
+      for (int j = 0; j < BQ_SEL_MLP; j++) {
+        const int64_t c = cb + (int64_t)j * blockDim.x;
+        v[j] = c < c1 ? __ldg(gm4 + c) : inf4;
+      }
+#pragma unroll
+      for (int j = 0; j < BQ_SEL_MLP; j++) {
+        const float m4 = fminf(fminf(v[j].x, v[j].y), fminf(v[j].z, v[j].w));
+        if (!(m4 <= tau)) continue;  // almost always: nothing of this chunk qualifies
+        const float e[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const int64_t g = ((cb + (int64_t)j * blockDim.x) << 2) + i;
+          if (g >= g0 && g < g1 && e[i] <= tau) {
+            const int idx = atomicAdd(&s_cnt, 1);
+            if (idx < cap) list[idx] = (int)g;
+          }
         }
       }
     }
@@ -801,17 +846,20 @@ batch_select_kernel(const float* __restrict__ X, int64_t n, int d, const float* 
     if (threadIdx.x == 0) batch_list_fallback(fb, nq_total, qi);
     cnt = cap;      // keep the ticket protocol of the epilogue intact; the fallback overwrites the result
   }
+  bq_stamp(3);
   // phase 3: exact scores of the candidate groups' rows, ranked like scan.cu.  All their lines are requested
   // into L2 first, so the scoring rounds below do not each wait on HBM.
   {
-    const int lpg = (gsz * d) >> 5;  // 128-byte lines per group
+    // one bulk L2 prefetch per candidate group (its rows are contiguous: gsz * d * 4 bytes)
     const char* xb = reinterpret_cast<const char*>(X);
-    const int64_t xbytes = n * (int64_t)d * 4;
-    for (int i = threadIdx.x; i < cnt * lpg; i += blockDim.x) {
-      const int64_t off = (int64_t)list[i / lpg] * gsz * d * 4 + (int64_t)(i % lpg) * 128;
-      if (off < xbytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(xb + off));
+    const int64_t xbytes = n * (int64_t)d * 4, gbytes = (int64_t)gsz * d * 4;
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+      const int64_t off = (int64_t)list[i] * gbytes;
+      const int64_t len = off + gbytes <= xbytes ? gbytes : xbytes - off;
+      if (len > 0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(xb + off), "r"((uint32_t)len) : "memory");
     }
   }
+  bq_stamp(4);
   TK tk;
   tk.init(smem + (size_t)warp * stride1, kp, k, lane);
   const int ub = d - (d % L);
@@ -829,7 +877,9 @@ batch_select_kernel(const float* __restrict__ X, int64_t n, int d, const float* 
       fthr = scan_filter_threshold<COSINE>(tk.thr);
     }
   }
+  bq_stamp(5);
   topk_epilogue(tk, smem, kp, k, out);
+  bq_stamp(6);
 }
 
 // Large batches, k <= 32: one WARP per query.  Every step of the selection is latency-bound (a pass over the
@@ -925,12 +975,12 @@ batch_select_warp_kernel(const float* __restrict__ X, int64_t n, int d, const fl
   }
   __syncwarp();
   {
-    const int lpg = (gsz * d) >> 5;  // 128-byte lines per group
     const char* xb = reinterpret_cast<const char*>(X);
-    const int64_t xbytes = n * (int64_t)d * 4;
-    for (int i = lane; i < cnt * lpg; i += 32) {
-      const int64_t off = (int64_t)list[i / lpg] * gsz * d * 4 + (int64_t)(i % lpg) * 128;
-      if (off < xbytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(xb + off));
+    const int64_t xbytes = n * (int64_t)d * 4, gbytes = (int64_t)gsz * d * 4;
+    for (int i = lane; i < cnt; i += 32) {
+      const int64_t off = (int64_t)list[i] * gbytes;
+      const int64_t len = off + gbytes <= xbytes ? gbytes : xbytes - off;
+      if (len > 0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(xb + off), "r"((uint32_t)len) : "memory");
     }
   }
   WarpTopKReg tk;

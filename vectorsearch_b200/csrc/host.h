@@ -54,6 +54,9 @@ struct TrainComm {
 int pq_train_device(cudaStream_t st, const float* dX, int64_t n, int d, int M, int K, int iterations,
                     int64_t seed, int lanes, float* centroids_out, const TrainComm* comm = nullptr);
 
+#ifdef VS_BQ_STAMPS
+int debug_read_stamps_batch(void* dst, size_t bytes);  // development only (batch.cu)
+#endif
 #ifdef VS_PHASE_STAMPS
 int debug_read_stamps(void* dst, size_t bytes);  // development only (scan.cu)
 int debug_read_stamps_adc(void* dst, size_t bytes);  // development only (adc_fast.cu)
