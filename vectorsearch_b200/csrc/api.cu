@@ -30,6 +30,7 @@ static std::atomic<int64_t> g_batch_gm_bytes{int64_t(1) << 30};  // group-minima
 static std::atomic<int64_t> g_batch_warp_min_q{0};         // > 0: batches this large always select with one warp per query (tests)
 static std::atomic<int64_t> g_scan_reserve_sms{0};          // SMs the one-query scan leaves free (for a collective's CTAs)
 static std::atomic<int64_t> g_batch_pairs{0};               // 1: cta_group::2 nomination kernel for batches > 128 queries (measured equal)
+static std::atomic<int64_t> g_batch_prefilter{1};           // candidate groups are pre-filtered on the fp16 copy before exact scoring
 static std::atomic<int64_t> g_batch_group{0};               // 0 = automatic rows per nomination group, else 16 / 32 / 64
 static std::atomic<int64_t> g_batch_fp16{1};                // nominate on fp16 operand copies (0: the fp32 rows as tf32)
 static int g_sms = 0;
@@ -558,6 +559,7 @@ static int batch_run_dev(cudaStream_t st, const Segment* s, const BatchLaunch& p
     L.X = s->X; L.skip = s->skip; L.q = d_q + (size_t)q0 * s->d; L.nq = c;
     L.tmX = p.half ? s->tmXh : s->tmX; L.tmX128 = p.half ? s->tmXh_b128 : s->tmX_b128; L.x_scale = s->x_scale;
     L.pairs = g_batch_pairs.load() != 0;
+    L.xh = s->Xh; L.prefilter = g_batch_prefilter.load() != 0;
     L.coef = static_cast<const float*>(s->ab[m]); L.stats = static_cast<const SegStats*>(s->stats[m]);
     L.gm = A.take<float>((size_t)((chunk + 255) / 256 * 256) * p.gm_stride);
     L.fb = A.take<int32_t>(1 + 2 * (size_t)chunk);
@@ -657,6 +659,10 @@ int32_t vs_set_option(const char* name, int64_t value) {
   if (!strcmp(name, "scan_reserve_sms")) {
     if (value < 0 || value >= 128) return fail(VS_EINVAL, "scan_reserve_sms must be in 0..127");
     g_scan_reserve_sms.store(value);
+    return VS_OK;
+  }
+  if (!strcmp(name, "batch_prefilter")) {
+    g_batch_prefilter.store(value != 0);
     return VS_OK;
   }
   if (!strcmp(name, "batch_pairs")) {

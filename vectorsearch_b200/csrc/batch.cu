@@ -667,6 +667,93 @@ int debug_read_stamps_batch(void* dst, size_t bytes) {
 __device__ __forceinline__ void bq_stamp(int) {}
 #endif
 
+// ---- candidate groups: fp16 pre-filter, then exact scores ------------------------------------------------------------
+// A candidate group holds gsz rows of which one or two matter.  With the fp16 operand copy at hand the warp first
+// recomputes a(q, x) for the group's rows from that copy (half the bytes of the fp32 rows; exact products, fp32
+// sums: the same slack covers it) and only the rows with a <= tau -- the condition every row of the true top-k
+// satisfies -- are fetched in fp32 and scored with the reference arithmetic, one row per half-warp.
+struct HalfOperands {
+  const __half* Xh;    // [n][dp] scaled fp16 rows, nullptr: no copy (tf32 operands), whole groups are scored exactly
+  const __half* Qh;    // [nq][dp] scaled fp16 queries
+  const float* qinv;   // [nq] 1 / (row scale * query scale)
+  const float* coef;   // [n] row coefficients of the metric
+  int dp;
+};
+
+template <bool COSINE, class TK>
+__device__ __forceinline__ void bq_group_prefilter_exact(const HalfOperands& H, const float* __restrict__ X, int64_t n, int d,
+                                                         const float* __restrict__ q, const float* __restrict__ qf /* smem [dp] */,
+                                                         float qi_scale, const uint8_t* __restrict__ skip, int lanes, double qq,
+                                                         float tau, int64_t row0, int gsz, int* __restrict__ plist /* warp smem [gsz] */,
+                                                         TK& tk, int lane) {
+  const int t = lane & 3, g = lane >> 2;
+  const int chunks = H.dp >> 3;  // 16-byte chunks (8 halfs) per row
+  int pcnt = 0;
+  for (int r0 = 0; r0 < gsz; r0 += 8) {
+    const int64_t row = row0 + r0 + g;
+    const bool live = row < n && r0 + g < gsz;
+    float dot = 0.0f;
+    if (live) {
+      const uint4* xr = reinterpret_cast<const uint4*>(H.Xh + (size_t)row * H.dp);
+      float d0 = 0.0f, d1 = 0.0f;
+      for (int c = t; c < chunks; c += 4) {
+        const uint4 v = __ldg(xr + c);
+        const float4 qa = *reinterpret_cast<const float4*>(qf + c * 8), qb = *reinterpret_cast<const float4*>(qf + c * 8 + 4);
+        const float2 x0 = __half22float2(*reinterpret_cast<const __half2*>(&v.x)), x1 = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+        const float2 x2 = __half22float2(*reinterpret_cast<const __half2*>(&v.z)), x3 = __half22float2(*reinterpret_cast<const __half2*>(&v.w));
+        d0 = fmaf(x0.x, qa.x, d0);
+        d1 = fmaf(x0.y, qa.y, d1);
+        d0 = fmaf(x1.x, qa.z, d0);
+        d1 = fmaf(x1.y, qa.w, d1);
+        d0 = fmaf(x2.x, qb.x, d0);
+        d1 = fmaf(x2.y, qb.y, d1);
+        d0 = fmaf(x3.x, qb.z, d0);
+        d1 = fmaf(x3.y, qb.w, d1);
+      }
+      dot = d0 + d1;
+    }
+    dot += __shfl_xor_sync(FULL_MASK, dot, 1);
+    dot += __shfl_xor_sync(FULL_MASK, dot, 2);
+    bool pass = false;
+    if (live && t == 0) {
+      const float c = __ldg(H.coef + row);
+      const float a = COSINE ? (c * dot) * qi_scale : fmaf(dot, -2.0f * qi_scale, c);
+      pass = a <= tau;  // dead rows carry +inf / NaN coefficients and never pass
+    }
+    const unsigned m = __ballot_sync(FULL_MASK, pass);
+    if (pass) plist[pcnt + __popc(m & ((1u << lane) - 1u))] = r0 + g;
+    pcnt += __popc(m);
+  }
+  __syncwarp();
+  // exact scores of the survivors: one row per half-warp, lane hl is SIMD lane hl of the modelled JVM
+  const int hl = lane & 15, hw = lane >> 4;
+  const unsigned hmask = (lane < 16) ? 0x0000ffffu : 0xffff0000u;
+  const int base_lane = lane & 16;
+  for (int i = 0; i < pcnt; i += 2) {
+    const bool have = i + hw < pcnt;
+    Key key = key_empty();
+    bool ok = false;
+    if (have) {  // uniform across the half-warp
+      const int64_t row = row0 + plist[i + hw];
+      ok = !(skip != nullptr && skip[row]);
+      if (ok) {
+        const float* x = X + (size_t)row * d;
+        double score;
+        if (COSINE) {
+          const double dotx = ref_sum_halfwarp<REF_DOT>(q, x, d, lanes, hl, hmask, base_lane);
+          const double xx = ref_sum_halfwarp<REF_DOT>(x, x, d, lanes, hl, hmask, base_lane);
+          score = ref_cosine_from_sums(dotx, qq, xx);
+        } else {
+          score = -__dsqrt_rn(ref_sum_halfwarp<REF_L2SQ>(q, x, d, lanes, hl, hmask, base_lane));
+        }
+        key = Key{rank_hi_from_score(score), (uint64_t)row};
+      }
+    }
+    tk.push(key, ok && hl == 0, lane);
+  }
+  __syncwarp();
+}
+
 // ---- (3) threshold, candidate groups, exact ranking --------------------------------------------------------------
 // |a(q, x) - exact| <= slack.  Operand rounding: tf32 truncates both operands (2^-10 each), the fp16 copies are
 // rounded to nearest (2^-11 each, plus a subnormal floor that the power-of-two scaling keeps below 2^-37 relative);
@@ -691,8 +778,8 @@ template <int TPR, int U, bool COSINE, class TK>
 __global__ void __launch_bounds__(BQ_SELECT_THREADS)
 batch_select_kernel(const float* __restrict__ X, int64_t n, int d, const float* __restrict__ Q,
                     const uint8_t* __restrict__ skip, const float* __restrict__ gm, int64_t gm_stride,
-                    int64_t ngroups, int gsz, const SegStats* __restrict__ stats, int half, int k, int kp, int cap,
-                    int32_t* __restrict__ fb, int nq_total, TopkOut out) {
+                    int64_t ngroups, int gsz, const SegStats* __restrict__ stats, int half, HalfOperands H, int k, int kp,
+                    int cap, int32_t* __restrict__ fb, int nq_total, TopkOut out) {
   extern __shared__ __align__(128) ulonglong2 smem[];
   constexpr int L = TPR * 4;
   constexpr int RPB = (32 / TPR) * U;  // rows per scoring batch
@@ -717,7 +804,11 @@ batch_select_kernel(const float* __restrict__ X, int64_t n, int d, const float* 
   __shared__ float s_q2;
   __shared__ int s_cnt;
   bq_stamp(0);
-  for (int i = threadIdx.x; i < d; i += blockDim.x) qs[i] = q[i];
+  if (H.Xh != nullptr) {
+    for (int i = threadIdx.x; i < H.dp; i += blockDim.x) qs[i] = __half2float(H.Qh[(size_t)qi * H.dp + i]);
+  } else {
+    for (int i = threadIdx.x; i < d; i += blockDim.x) qs[i] = q[i];
+  }
   if (COSINE && threadIdx.x == 32) s_qq = ref_sum_thread_L<L, REF_DOT>(q, q, d);
   if (warp == 0) {
     float ss = 0.0f;
@@ -850,9 +941,12 @@ batch_select_kernel(const float* __restrict__ X, int64_t n, int d, const float* 
   // phase 3: exact scores of the candidate groups' rows, ranked like scan.cu.  All their lines are requested
   // into L2 first, so the scoring rounds below do not each wait on HBM.
   {
-    // one bulk L2 prefetch per candidate group (its rows are contiguous: gsz * d * 4 bytes)
-    const char* xb = reinterpret_cast<const char*>(X);
-    const int64_t xbytes = n * (int64_t)d * 4, gbytes = (int64_t)gsz * d * 4;
+    // one bulk L2 prefetch per candidate group (its rows are contiguous): the fp16 rows the pre-filter reads, or
+    // the fp32 rows when whole groups are scored exactly
+    const bool hp = H.Xh != nullptr;
+    const char* xb = hp ? reinterpret_cast<const char*>(H.Xh) : reinterpret_cast<const char*>(X);
+    const int64_t rbytes = hp ? (int64_t)H.dp * 2 : (int64_t)d * 4;
+    const int64_t xbytes = n * rbytes, gbytes = (int64_t)gsz * rbytes;
     for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
       const int64_t off = (int64_t)list[i] * gbytes;
       const int64_t len = off + gbytes <= xbytes ? gbytes : xbytes - off;
@@ -866,6 +960,12 @@ batch_select_kernel(const float* __restrict__ X, int64_t n, int d, const float* 
   const int nv = ub / L;
   float fthr = __int_as_float(0x7f800000);
   uint64_t seen_hi = KEY_EMPTY64, seen_lo = KEY_EMPTY64;
+  if (H.Xh != nullptr) {
+    // fp16 pre-filter per group, exact scores for the rows that pass (qs holds the scaled fp16 query as floats)
+    int* plist = reinterpret_cast<int*>(qs + ((H.dp + 3) & ~3)) + warp * 64;
+    for (int gi = warp; gi < cnt; gi += nw)
+      bq_group_prefilter_exact<COSINE, TK>(H, X, n, d, q, qs, H.qinv[qi], skip, L, qq, tau, (int64_t)list[gi] * gsz, gsz, plist, tk, lane);
+  } else {
   const int total = cnt * BPG;
   for (int b = warp; b < total; b += nw) {
     const int64_t row_base = (int64_t)list[b / BPG] * gsz + (int64_t)(b % BPG) * RPB;
@@ -876,6 +976,7 @@ batch_select_kernel(const float* __restrict__ X, int64_t n, int d, const float* 
       seen_lo = tk.thr.lo;
       fthr = scan_filter_threshold<COSINE>(tk.thr);
     }
+  }
   }
   bq_stamp(5);
   topk_epilogue(tk, smem, kp, k, out);
@@ -889,7 +990,7 @@ template <int TPR, int U, bool COSINE>
 __global__ void __launch_bounds__(BQ_SELECT_THREADS)
 batch_select_warp_kernel(const float* __restrict__ X, int64_t n, int d, const float* __restrict__ Q,
                          const uint8_t* __restrict__ skip, const float* __restrict__ gm, int64_t gm_stride,
-                         int64_t ngroups, int gsz, const SegStats* __restrict__ stats, int half, int k, int cap,
+                         int64_t ngroups, int gsz, const SegStats* __restrict__ stats, int half, HalfOperands H, int k, int cap,
                          int32_t* __restrict__ fb, int nq, int64_t* __restrict__ ids, double* __restrict__ scores,
                          int32_t* __restrict__ counts, int64_t id_base, int64_t out_stride) {
   extern __shared__ __align__(128) ulonglong2 smem[];
@@ -900,9 +1001,10 @@ batch_select_warp_kernel(const float* __restrict__ X, int64_t n, int d, const fl
   const int warp = threadIdx.x >> 5;
   const int qi = blockIdx.x * (blockDim.x >> 5) + warp;
   if (qi >= nq) return;
-  const int qpad = (d + 3) & ~3;
+  const int qpad = (((H.Xh != nullptr ? H.dp : d) + 3) & ~3) + 64;  // query floats + the pre-filter's survivor list
   int* list = reinterpret_cast<int*>(smem) + (size_t)warp * (cap + qpad);
   float* qs = reinterpret_cast<float*>(list + cap);
+  int* plist = reinterpret_cast<int*>(qs + qpad - 64);
   const float* __restrict__ q = Q + (size_t)qi * d;
   const float* __restrict__ gmq = gm + (size_t)qi * gm_stride;
   const float inf = __int_as_float(0x7f800000);
@@ -910,9 +1012,11 @@ batch_select_warp_kernel(const float* __restrict__ X, int64_t n, int d, const fl
   float ss = 0.0f;
   for (int i = lane; i < d; i += 32) {
     const float v = q[i];
-    qs[i] = v;
+    if (H.Xh == nullptr) qs[i] = v;
     ss = fmaf(v, v, ss);
   }
+  if (H.Xh != nullptr)  // the pre-filter multiplies the fp16 operand copies: stage the scaled fp16 query as floats
+    for (int i = lane; i < H.dp; i += 32) qs[i] = __half2float(H.Qh[(size_t)qi * H.dp + i]);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(FULL_MASK, ss, o);
   if (!(ss < 1e30f)) {  // non-finite query: exact scan instead
@@ -975,8 +1079,10 @@ batch_select_warp_kernel(const float* __restrict__ X, int64_t n, int d, const fl
   }
   __syncwarp();
   {
-    const char* xb = reinterpret_cast<const char*>(X);
-    const int64_t xbytes = n * (int64_t)d * 4, gbytes = (int64_t)gsz * d * 4;
+    const bool hp = H.Xh != nullptr;
+    const char* xb = hp ? reinterpret_cast<const char*>(H.Xh) : reinterpret_cast<const char*>(X);
+    const int64_t rbytes = hp ? (int64_t)H.dp * 2 : (int64_t)d * 4;
+    const int64_t xbytes = n * rbytes, gbytes = (int64_t)gsz * rbytes;
     for (int i = lane; i < cnt; i += 32) {
       const int64_t off = (int64_t)list[i] * gbytes;
       const int64_t len = off + gbytes <= xbytes ? gbytes : xbytes - off;
@@ -989,6 +1095,10 @@ batch_select_warp_kernel(const float* __restrict__ X, int64_t n, int d, const fl
   const int nv = ub / L;
   float fthr = inf;
   uint64_t seen_hi = KEY_EMPTY64, seen_lo = KEY_EMPTY64;
+  if (H.Xh != nullptr) {
+    for (int gi = 0; gi < cnt; gi++)
+      bq_group_prefilter_exact<COSINE, WarpTopKReg>(H, X, n, d, q, qs, H.qinv[qi], skip, L, qq, tau, (int64_t)list[gi] * gsz, gsz, plist, tk, lane);
+  } else {
   const int total = cnt * BPG;
   for (int b = 0; b < total; b++) {
     const int64_t row_base = (int64_t)list[b / BPG] * gsz + (int64_t)(b % BPG) * RPB;
@@ -999,6 +1109,7 @@ batch_select_warp_kernel(const float* __restrict__ X, int64_t n, int d, const fl
       seen_lo = tk.thr.lo;
       fthr = scan_filter_threshold<COSINE>(tk.thr);
     }
+  }
   }
   // lane i holds the i-th best key
   const bool ok = lane < k && tk.my_lo != KEY_EMPTY64;
@@ -1111,9 +1222,9 @@ static cudaError_t set_smem_attr(K kern, size_t smem_max) {
 constexpr size_t BQ_SELECT_SMEM_MAX = 220 * 1024, BQ_SELW_SMEM_MAX = 96 * 1024;
 
 typedef void (*SelectKern)(const float*, int64_t, int, const float*, const uint8_t*, const float*, int64_t, int64_t, int,
-                           const SegStats*, int, int, int, int, int32_t*, int, TopkOut);
+                           const SegStats*, int, HalfOperands, int, int, int, int32_t*, int, TopkOut);
 typedef void (*SelectWarpKern)(const float*, int64_t, int, const float*, const uint8_t*, const float*, int64_t, int64_t, int,
-                               const SegStats*, int, int, int, int32_t*, int, int64_t*, double*, int32_t*, int64_t, int64_t);
+                               const SegStats*, int, HalfOperands, int, int, int32_t*, int, int64_t*, double*, int32_t*, int64_t, int64_t);
 static SelectWarpKern pick_select_warp(int TPR, bool cosine) {
   if (cosine) return TPR == 4 ? batch_select_warp_kernel<4, 1, true> : (TPR == 2 ? batch_select_warp_kernel<2, 1, true> : batch_select_warp_kernel<1, 1, true>);
   return TPR == 4 ? batch_select_warp_kernel<4, 2, false> : (TPR == 2 ? batch_select_warp_kernel<2, 2, false> : batch_select_warp_kernel<1, 2, false>);
@@ -1167,7 +1278,8 @@ static size_t batch_select_smem(const BatchLaunch& L, int nw) {
   const size_t b3 = topk_block_smem(L.k, L.kp, nw);
   if (b3 > coll) coll = b3;
   coll = (coll + 15) & ~size_t(15);
-  return coll + (size_t)((L.cap + 3) & ~3) * 4 + (((size_t)L.d * 4 + 15) & ~size_t(15));
+  // collectors, group list, query (d floats, or the dp floats of the scaled fp16 query), survivor lists of the pre-filter
+  return coll + (size_t)((L.cap + 3) & ~3) * 4 + (size_t)((L.dp + 3) & ~3) * 4 + (size_t)nw * 64 * 4;
 }
 
 bool batch_configure(BatchLaunch& L, int sms) {
@@ -1216,7 +1328,7 @@ bool batch_configure(BatchLaunch& L, int sms) {
     L.cap = L.cap / 2 > L.k + 64 ? L.cap / 2 : L.k + 64;
   }
   if (L.select_smem > BQ_SELECT_SMEM_MAX) return false;
-  L.selw_smem = (size_t)(BQ_SELECT_THREADS / 32) * (size_t)(L.cap + ((L.d + 3) & ~3)) * 4;
+  L.selw_smem = (size_t)(BQ_SELECT_THREADS / 32) * (size_t)(L.cap + ((L.dp + 3) & ~3) + 64) * 4;
   if (L.k <= TOPK_REG_MAX_K && L.selw_smem <= BQ_SELW_SMEM_MAX) {
     if (set_smem_attr(pick_select_warp(L.lanes / 4, L.cosine), BQ_SELW_SMEM_MAX) != cudaSuccess) return false;
   } else {
@@ -1299,15 +1411,17 @@ cudaError_t launch_batch(const BatchLaunch& L, cudaStream_t st) {
   int W = 8;
   while (W > 1 && (int64_t)L.nq * W > 16 * (int64_t)L.sms) W >>= 1;
   const bool force_warp = L.warp_min_q > 0 && L.nq >= L.warp_min_q;
+  HalfOperands H{};
+  if (L.half && L.prefilter) H = HalfOperands{static_cast<const __half*>(L.xh), static_cast<const __half*>(L.qh), L.qinv, L.coef, L.dp};
   if (L.selw_smem != 0 && (W == 1 || force_warp)) {
     const int wpb = BQ_SELECT_THREADS / 32;
     pick_select_warp(TPR, L.cosine)<<<(L.nq + wpb - 1) / wpb, BQ_SELECT_THREADS, L.selw_smem, st>>>(
-        L.X, L.n, L.d, L.q, L.skip, L.gm, L.gm_stride, L.ngroups, L.group, L.stats, L.half ? 1 : 0, L.k, L.cap, L.fb, L.nq,
+        L.X, L.n, L.d, L.q, L.skip, L.gm, L.gm_stride, L.ngroups, L.group, L.stats, L.half ? 1 : 0, H, L.k, L.cap, L.fb, L.nq,
         L.ids_out, L.scores_out, L.counts_out, L.id_base, L.out_stride > 0 ? L.out_stride : L.k);
   } else {
     if (W < 2) W = 2;
     pick_select(TPR, L.cosine, L.k)<<<dim3(P, L.nq), 32 * W, batch_select_smem(L, W), st>>>(
-        L.X, L.n, L.d, L.q, L.skip, L.gm, L.gm_stride, L.ngroups, L.group, L.stats, L.half ? 1 : 0, L.k, L.kp, L.cap, L.fb, L.nq, o);
+        L.X, L.n, L.d, L.q, L.skip, L.gm, L.gm_stride, L.ngroups, L.group, L.stats, L.half ? 1 : 0, H, L.k, L.kp, L.cap, L.fb, L.nq, o);
   }
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   count_launch();

@@ -66,6 +66,8 @@ struct BatchLaunch {
   bool half;             // operands are fp16 copies (kind::f16) instead of the fp32 data read as tf32
   int dp;                // fp16 row pitch in elements (d rounded up to 8)
   float x_scale;         // power of two the fp16 row copy was scaled by
+  const void* xh;        // [n][dp] the fp16 operand copy itself (half only)
+  bool prefilter;        // candidate groups: fp16 pre-filter before the exact scores (half only)
   void* qh;              // [nq][dp] fp16 scratch for the scaled queries (half only)
   float* qinv;           // [round_up(nq, 256)] 1 / (x_scale * query scale) (half only)
   const float* coef;     // [n] per-row nomination coefficient of this metric
