@@ -473,8 +473,18 @@ def bench_c4(vs, L, lib, torch, dev, K, W, hbm_peak):
     torch.cuda.synchronize()
     ms_adc = e0.elapsed_time(e1) / K
     gbs = n * C4_M / (ms_adc * 1e-3) / 1e9
+    # end to end through the host API: query from host memory in, ids + scores out, every query
+    qh = q_dev.cpu().numpy()
+    for i in range(3):
+        seg.adc_rerank_topk(qh[i], C4_NCAND, TOPK)
+    t0 = time.perf_counter()
+    for i in range(K):
+        seg.adc_rerank_topk(qh[W + i], C4_NCAND, TOPK)
+    e2e_ms = (time.perf_counter() - t0) / K * 1e3
     out = {"workload": f"C4: ADC top-{C4_NCAND} + exact re-rank top-{TOPK} over {n}x{DIM} (M={C4_M} uint8 codes), 1 GPU",
            "ms_per_query": ms, "adc_evals_per_s": n / (ms * 1e-3), "qps": 1e3 / ms,
+           "e2e": {"ms_per_query": e2e_ms, "adc_evals_per_s": n / (e2e_ms * 1e-3), "h2d_bytes_per_step": DIM * 4,
+                   "d2h_bytes_per_step": TOPK * 16 + 4},
            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
                         "kernel": "build_lut_mm + adc_fastscan_kernel<4> (K5+K6)", "ms_per_launch_group": ms_adc,
                         "algorithmic_bytes_per_launch": n * C4_M, "traffic": None},

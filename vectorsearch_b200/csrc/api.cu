@@ -1142,15 +1142,20 @@ static int adc_common(uint64_t h, const float* q, int32_t nq, int32_t n_cand, bo
     const int64_t* src_ids = dcid;
     const double* src_sc = dcap;
     const int32_t* src_cn = dccn;
+    bool direct = false;
     if (rerank) {
-      RET(rerank_dev(c->stream, s, dq, g, dcid, n_cand, k, metric, dids, dsc, dcn));
+      // short lists: the re-rank kernel writes straight into the pinned staging buffer (device-visible under UVA)
+      direct = (size_t)g * kout <= 4096;
+      RET(rerank_dev(c->stream, s, dq, g, dcid, n_cand, k, metric, direct ? hids : dids, direct ? hsc : dsc, direct ? hcn : dcn));
       src_ids = dids;
       src_sc = dsc;
       src_cn = dcn;
     }
-    CK(cudaMemcpyAsync(hids, src_ids, (size_t)g * kout * 8, cudaMemcpyDeviceToHost, c->stream), "D2H ids");
-    CK(cudaMemcpyAsync(hsc, src_sc, (size_t)g * kout * 8, cudaMemcpyDeviceToHost, c->stream), "D2H scores");
-    CK(cudaMemcpyAsync(hcn, src_cn, (size_t)g * 4, cudaMemcpyDeviceToHost, c->stream), "D2H counts");
+    if (!direct) {
+      CK(cudaMemcpyAsync(hids, src_ids, (size_t)g * kout * 8, cudaMemcpyDeviceToHost, c->stream), "D2H ids");
+      CK(cudaMemcpyAsync(hsc, src_sc, (size_t)g * kout * 8, cudaMemcpyDeviceToHost, c->stream), "D2H scores");
+      CK(cudaMemcpyAsync(hcn, src_cn, (size_t)g * 4, cudaMemcpyDeviceToHost, c->stream), "D2H counts");
+    }
     CK(cudaStreamSynchronize(c->stream), "sync");
     memcpy(ids_out + (size_t)q0 * kout, hids, (size_t)g * kout * 8);
     memcpy(scores_out + (size_t)q0 * kout, hsc, (size_t)g * kout * 8);
