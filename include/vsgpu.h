@@ -193,6 +193,8 @@ int64_t vs_kernel_launch_count(void);
  * "batch_warp_min_queries" (0 = automatic); "batch_pairs" (default 0): batches of more than 128 queries
  * nominate on CTA pairs (tcgen05 cta_group::2).  "scan_reserve_sms": SMs the one-query scan leaves free so that
  * work of another stream (the next query's prologue, a collective's CTAs) runs beside it (default 0).
+ * "pdl" (default 1): the kernels of one call are chained with programmatic dependent launch (the next
+ * kernel is set up while its predecessor runs and waits, in the kernel, for its results).
  * "pq_tensor_cores" (default 0): subDim-8 PQ assignment nominates with mma.sync 3xTF32 instead of FFMA
  * (slower on B200, kept as a measured reference point).  Results never depend on any of them. */
 int32_t vs_set_option(const char* name, int64_t value);

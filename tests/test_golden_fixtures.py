@@ -69,6 +69,34 @@ def test_gpu_bruteforce_matches_golden(vs, oracle, gold):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("operands", ["fp16", "tf32"])
+def test_gpu_batched_bruteforce_matches_golden(vs, oracle, gold, operands):
+    """The tensor-core batched path (batch.cu) must return the golden lists for every query of a batch --
+    here the golden query repeated next to unrelated ones -- without the oracle in the loop."""
+    inp = mg.inputs(oracle)
+    vs.set_option("batch_min_queries", 2)
+    vs.set_option("batch_min_rows", 1)
+    vs.set_option("batch_fp16", 1 if operands == "fp16" else 0)
+    try:
+        seg = vs.Segment.upload(inp["bf_rows"], skip=inp["bf_skip"])
+        try:
+            q = np.asarray(inp["bf_q"], np.float32)
+            qs = np.stack([q, -q, q, q * np.float32(0.5) + np.float32(0.1), q])
+            for metric, name in ((0, "l2"), (1, "cos")):
+                ids, sc, cn = seg.bruteforce_topk(qs, mg.BF["k"], metric)
+                for i in (0, 2, 4):
+                    c = len(gold[f"bf_{name}_ids"])
+                    assert cn[i] == c and np.array_equal(ids[i, :c], gold[f"bf_{name}_ids"])
+                    assert np.array_equal(_bits(sc[i, :c]), _bits(gold[f"bf_{name}_scores"]))
+        finally:
+            seg.free()
+    finally:
+        vs.set_option("batch_min_queries", 3)
+        vs.set_option("batch_min_rows", 16384)
+        vs.set_option("batch_fp16", 1)
+
+
+@pytest.mark.gpu
 def test_gpu_pq_path_matches_golden(vs, oracle, gold):
     inp = mg.inputs(oracle)
     P = mg.PQ

@@ -134,6 +134,7 @@ __host__ __device__ inline unsigned int fs_entry_offset(unsigned int c) { return
 __global__ void __launch_bounds__(256)
 build_lut_mm_kernel(const float* __restrict__ centroids, int M, int K, int subDim, const float* __restrict__ Q,
                     int lanes, double* __restrict__ LUT64, unsigned long long* __restrict__ MM) {
+  pdl_trigger();  // the scan's CTAs may be placed (they wait for this grid before reading the table)
   const int s = blockIdx.x, qi = blockIdx.y;
   const int lane = threadIdx.x & 31;
   const float* q = Q + (size_t)qi * M * subDim + (size_t)s * subDim;
@@ -172,18 +173,21 @@ build_lut_mm_kernel(const float* __restrict__ centroids, int M, int K, int subDi
 // MW = M/4 words of codes per row (M = 8 or 16).
 template <int MW>
 __global__ void __launch_bounds__(FS_THREADS, 1)
-adc_fastscan_kernel(const uint8_t* __restrict__ codes, int64_t n, int K, const double* __restrict__ LUT64,
-                    const unsigned long long* __restrict__ MM, unsigned int k, unsigned int* __restrict__ fs, unsigned long long* __restrict__ cand_all,
+adc_fastscan_kernel(const uint8_t* __restrict__ codes, int64_t n, int K,
+                    const double* LUT64 /* written by the LUT kernel this one may overlap (launch_pdl): no __restrict__ */,
+                    const unsigned long long* MM, unsigned int k, unsigned int* __restrict__ fs, unsigned long long* __restrict__ cand_all,
                     unsigned int cap, int64_t* __restrict__ ids_out, double* __restrict__ approx_out,
                     int32_t* __restrict__ counts_out, int64_t id_base, int64_t out_stride) {
   extern __shared__ __align__(128) unsigned char fsm[];
+  pdl_trigger();  // the fallback check may be set up and placed while this kernel runs
+  pdl_wait();     // the LUT kernel's output
   constexpr int M = MW * 4;
   constexpr int BPT = FS_BINS / FS_THREADS;  // histogram bins owned by a thread
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
   const int qi = blockIdx.y;
-  const double* __restrict__ lut64 = LUT64 + (size_t)qi * M * K;
+  const double* lut64 = LUT64 + (size_t)qi * M * K;
   unsigned int* hist_g = fs + (size_t)qi * FS_WORDS;
   unsigned int* ctrl = hist_g + FS_BINS;
   unsigned int* counts_g = ctrl + FS_CTRL;
@@ -588,6 +592,10 @@ adc_fallback_kernel(const uint8_t* __restrict__ codes, int64_t n, int M, int K, 
   extern __shared__ __align__(128) ulonglong2 smem[];
   const int qi = blockIdx.y;
   unsigned int* ctrl = fs + (size_t)qi * FS_WORDS + FS_BINS;
+  // launched with programmatic stream serialisation: the launch itself overlaps the scan kernel's tail, this
+  // waits for the scan (and its flag) to be complete and visible
+  pdl_trigger();  // the re-rank kernel may be placed
+  pdl_wait();
   if (ld_cg_u32(ctrl + FS_FLAG) == 0u) return;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -666,26 +674,20 @@ cudaError_t launch_build_lut_mm(const float* centroids, int M, int K, int subDim
 cudaError_t launch_adc_fast(const AdcFastLaunch& L, cudaStream_t st) {
   const dim3 grid(L.grid, L.nq);
   const int64_t stride = L.out_stride > 0 ? L.out_stride : L.k;
-  if (L.M == 16)
-    adc_fastscan_kernel<4><<<grid, FS_THREADS, L.smem_bytes, st>>>(L.codes, L.n, L.K, L.lut64, L.mm,
-                                                                   (unsigned int)L.k, L.fs, L.cand, L.cap, L.ids_out, L.approx_out,
-                                                                   L.counts_out, L.id_base, stride);
-  else
-    adc_fastscan_kernel<2><<<grid, FS_THREADS, L.smem_bytes, st>>>(L.codes, L.n, L.K, L.lut64, L.mm,
-                                                                   (unsigned int)L.k, L.fs, L.cand, L.cap, L.ids_out, L.approx_out,
-                                                                   L.counts_out, L.id_base, stride);
   count_launch();
-  return cudaGetLastError();
+  if (L.M == 16)
+    return launch_pdl(adc_fastscan_kernel<4>, grid, dim3(FS_THREADS), L.smem_bytes, st, L.codes, L.n, L.K, L.lut64, L.mm,
+                      (unsigned int)L.k, L.fs, L.cand, L.cap, L.ids_out, L.approx_out, L.counts_out, L.id_base, stride);
+  return launch_pdl(adc_fastscan_kernel<2>, grid, dim3(FS_THREADS), L.smem_bytes, st, L.codes, L.n, L.K, L.lut64, L.mm,
+                    (unsigned int)L.k, L.fs, L.cand, L.cap, L.ids_out, L.approx_out, L.counts_out, L.id_base, stride);
 }
-
-// the conditional exact pass: a no-op launch unless the fast scan flagged the query
 cudaError_t launch_adc_fallback(const AdcFastLaunch& L, cudaStream_t st) {
   TopkOut o{L.partial, L.ctrl, L.partial_keys, L.ids_out, L.approx_out, L.counts_out, L.id_base, 1,
             L.out_stride > 0 ? L.out_stride : L.k};
   FallbackKern fk = L.k <= TOPK_REG_MAX_K ? adc_fallback_kernel<WarpTopKReg> : adc_fallback_kernel<WarpTopK>;
-  fk<<<dim3(L.final_grid, L.nq), L.final_threads, L.final_smem, st>>>(L.codes, L.n, L.M, L.K, L.lut64, L.fs, L.k, L.kp, o);
   count_launch();
-  return cudaGetLastError();
+  return launch_pdl(fk, dim3(L.final_grid, L.nq), dim3(L.final_threads), L.final_smem, st, L.codes, L.n, L.M, L.K, L.lut64,
+                    L.fs, L.k, L.kp, o);
 }
 
 }  // namespace vs

@@ -31,6 +31,7 @@ static std::atomic<int64_t> g_batch_warp_min_q{0};         // > 0: batches this 
 static std::atomic<int64_t> g_scan_reserve_sms{0};          // SMs the one-query scan leaves free (for a collective's CTAs)
 static std::atomic<int64_t> g_batch_pairs{0};               // 1: cta_group::2 nomination kernel for batches > 128 queries (measured equal)
 static std::atomic<int64_t> g_batch_prefilter{1};           // candidate groups are pre-filtered on the fp16 copy before exact scoring
+static std::atomic<int64_t> g_pdl{1};                       // programmatic dependent launch between the kernels of one call
 static std::atomic<int64_t> g_batch_group{0};               // 0 = automatic rows per nomination group, else 16 / 32 / 64
 static std::atomic<int64_t> g_batch_fp16{1};                // nominate on fp16 operand copies (0: the fp32 rows as tf32)
 static int g_sms = 0;
@@ -57,6 +58,7 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 
 int lanes() { return g_lanes.load(); }
+bool pdl_enabled() { return g_pdl.load() != 0; }
 int sm_count() { return g_sms; }
 
 // ---- per-thread context ------------------------------------------------------------------------------
@@ -659,6 +661,10 @@ int32_t vs_set_option(const char* name, int64_t value) {
   if (!strcmp(name, "scan_reserve_sms")) {
     if (value < 0 || value >= 128) return fail(VS_EINVAL, "scan_reserve_sms must be in 0..127");
     g_scan_reserve_sms.store(value);
+    return VS_OK;
+  }
+  if (!strcmp(name, "pdl")) {
+    g_pdl.store(value != 0);
     return VS_OK;
   }
   if (!strcmp(name, "batch_prefilter")) {

@@ -202,6 +202,7 @@ cudaError_t launch_row_convert(const float* X, int64_t n, int d, int dp, float s
 __global__ void __launch_bounds__(256)
 query_convert_kernel(const float* __restrict__ Q, int nq, int nq_pad, int d, int dp, float sx, __half* __restrict__ Qh,
                      float* __restrict__ qinv) {
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (qi >= nq_pad) return;
@@ -339,6 +340,8 @@ batch_gemm_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(s_tmem);
+  pdl_trigger();  // the selection kernel may be set up while this one runs
+  pdl_wait();     // scaled queries / scratch reset of the launches before
 
   if (warp == 0) {
     if (lane == 0) {  // ===== TMA producer =====
@@ -549,6 +552,8 @@ batch_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   cluster_sync_all();  // both CTAs' barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(s_tmem);
+  pdl_trigger();
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {  // ===== TMA producer (both CTAs) =====
@@ -777,10 +782,12 @@ __device__ __forceinline__ void batch_list_fallback(int32_t* fb, int nq_total, i
 template <int TPR, int U, bool COSINE, class TK>
 __global__ void __launch_bounds__(BQ_SELECT_THREADS)
 batch_select_kernel(const float* __restrict__ X, int64_t n, int d, const float* __restrict__ Q,
-                    const uint8_t* __restrict__ skip, const float* __restrict__ gm, int64_t gm_stride,
+                    const uint8_t* __restrict__ skip, const float* gm /* written by the predecessor: no __restrict__ */, int64_t gm_stride,
                     int64_t ngroups, int gsz, const SegStats* __restrict__ stats, int half, HalfOperands H, int k, int kp,
                     int cap, int32_t* __restrict__ fb, int nq_total, TopkOut out) {
   extern __shared__ __align__(128) ulonglong2 smem[];
+  pdl_trigger();
+  pdl_wait();  // group minima of the nomination kernel
   constexpr int L = TPR * 4;
   constexpr int RPB = (32 / TPR) * U;  // rows per scoring batch
   const int BPG = gsz / RPB;           // scoring batches per group (the host keeps gsz >= RPB)
@@ -790,7 +797,7 @@ batch_select_kernel(const float* __restrict__ X, int64_t n, int d, const float* 
   const int qi = blockIdx.y;
   const int stride1 = kp + TOPK_BUF;
   const float* __restrict__ q = Q + (size_t)qi * d;
-  const float* __restrict__ gmq = gm + (size_t)qi * gm_stride;
+  const float* gmq = gm + (size_t)qi * gm_stride;
 
   // shared memory: [collectors (phase 1 and phase 3 alias)][group list: cap ints][query: d floats]
   size_t coll_bytes = (size_t)nw * topk_warp_smem(kp);
@@ -849,7 +856,7 @@ batch_select_kernel(const float* __restrict__ X, int64_t n, int d, const float* 
 #pragma unroll
         for (int j = 0; j < BQ_SEL_MLP; j++) {
           const int64_t c = cb + (int64_t)j * blockDim.x;
-          v[j] = c < c1 ? __ldg(gm4 + c) : inf4;
+          v[j] = c < c1 ? gm4[c] : inf4;
         }
 #pragma unroll
         for (int j = 0; j < BQ_SEL_MLP; j++) {
@@ -913,7 +920,7 @@ batch_select_kernel(const float* __restrict__ X, int64_t n, int d, const float* 
 #pragma unroll
       for (int j = 0; j < BQ_SEL_MLP; j++) {
         const int64_t c = cb + (int64_t)j * blockDim.x;
-        v[j] = c < c1 ? __ldg(gm4 + c) : inf4;
+        v[j] = c < c1 ? gm4[c] : inf4;
       }
 #pragma unroll
       for (int j = 0; j < BQ_SEL_MLP; j++) {
@@ -989,11 +996,13 @@ batch_select_kernel(const float* __restrict__ X, int64_t n, int d, const float* 
 template <int TPR, int U, bool COSINE>
 __global__ void __launch_bounds__(BQ_SELECT_THREADS)
 batch_select_warp_kernel(const float* __restrict__ X, int64_t n, int d, const float* __restrict__ Q,
-                         const uint8_t* __restrict__ skip, const float* __restrict__ gm, int64_t gm_stride,
+                         const uint8_t* __restrict__ skip, const float* gm /* written by the predecessor: no __restrict__ */, int64_t gm_stride,
                          int64_t ngroups, int gsz, const SegStats* __restrict__ stats, int half, HalfOperands H, int k, int cap,
                          int32_t* __restrict__ fb, int nq, int64_t* __restrict__ ids, double* __restrict__ scores,
                          int32_t* __restrict__ counts, int64_t id_base, int64_t out_stride) {
   extern __shared__ __align__(128) ulonglong2 smem[];
+  pdl_trigger();
+  pdl_wait();  // group minima of the nomination kernel
   constexpr int L = TPR * 4;
   constexpr int RPB = (32 / TPR) * U;
   const int BPG = gsz / RPB;
@@ -1006,7 +1015,7 @@ batch_select_warp_kernel(const float* __restrict__ X, int64_t n, int d, const fl
   float* qs = reinterpret_cast<float*>(list + cap);
   int* plist = reinterpret_cast<int*>(qs + qpad - 64);
   const float* __restrict__ q = Q + (size_t)qi * d;
-  const float* __restrict__ gmq = gm + (size_t)qi * gm_stride;
+  const float* gmq = gm + (size_t)qi * gm_stride;
   const float inf = __int_as_float(0x7f800000);
 
   float ss = 0.0f;
@@ -1372,6 +1381,7 @@ cudaError_t launch_batch(const BatchLaunch& L, cudaStream_t st) {
   const int nqb = (L.nq + BQ_M - 1) / BQ_M;
   const int kbe = L.half ? 64 : 32;
   const int num_kb = (L.d + kbe - 1) / kbe;
+  if ((e = cudaMemsetAsync(L.fb, 0, sizeof(int32_t) * (1 + 2 * (size_t)L.nq), st)) != cudaSuccess) return e;
   if (L.half) {
     count_launch();
     const int nq_pad = (L.nq + 2 * BQ_M - 1) / (2 * BQ_M) * (2 * BQ_M);  // whole pairs of query blocks
@@ -1381,7 +1391,6 @@ cudaError_t launch_batch(const BatchLaunch& L, cudaStream_t st) {
   } else {
     if (!encode_rows_map(&tmQ, L.q, L.nq, L.d, L.d, false, BQ_M)) return cudaErrorInvalidValue;
   }
-  if ((e = cudaMemsetAsync(L.fb, 0, sizeof(int32_t) * (1 + 2 * (size_t)L.nq), st)) != cudaSuccess) return e;
   count_launch();
   if (L.pair_stages > 0 && L.pairs && L.nq > BQ_M && L.tmX128 != nullptr && L.sms >= 2) {
     const CUtensorMap tmX = *reinterpret_cast<const CUtensorMap*>(L.tmX128);
@@ -1389,15 +1398,17 @@ cudaError_t launch_batch(const BatchLaunch& L, cudaStream_t st) {
     int nsplit = (L.sms / 2) / nqp;
     if (nsplit < 1) nsplit = 1;
     if (nsplit > L.tiles) nsplit = (int)L.tiles;
-    pick_gemm_pair(L.half, L.cosine, L.group)<<<2 * nqp * nsplit, BQ_THREADS, L.pair_smem, st>>>(
-        tmQ, tmX, L.coef, L.qinv, L.n, num_kb, L.pair_stages, nqp, L.tiles, L.gm, L.gm_stride);
+    e = launch_pdl(pick_gemm_pair(L.half, L.cosine, L.group), dim3(2 * nqp * nsplit), dim3(BQ_THREADS), L.pair_smem, st,
+                   tmQ, tmX, L.coef, L.qinv, L.n, num_kb, L.pair_stages, nqp, L.tiles, L.gm, L.gm_stride);
+    if (e != cudaSuccess) return e;
   } else {
     const CUtensorMap tmX = *reinterpret_cast<const CUtensorMap*>(L.tmX);
     int nsplit = L.sms / nqb;
     if (nsplit < 1) nsplit = 1;
     if (nsplit > L.tiles) nsplit = (int)L.tiles;
-    pick_gemm(L.gemm_stat, L.half, L.cosine, L.group)<<<nqb * nsplit, BQ_THREADS, L.gemm_smem, st>>>(
-        tmQ, tmX, L.coef, L.qinv, L.n, num_kb, L.gemm_stages, nqb, L.tiles, L.gm, L.gm_stride);
+    e = launch_pdl(pick_gemm(L.gemm_stat, L.half, L.cosine, L.group), dim3(nqb * nsplit), dim3(BQ_THREADS), L.gemm_smem, st,
+                   tmQ, tmX, L.coef, L.qinv, L.n, num_kb, L.gemm_stages, nqb, L.tiles, L.gm, L.gm_stride);
+    if (e != cudaSuccess) return e;
   }
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   if (L.gemm_only) return cudaSuccess;  // diagnostics: group minima only
@@ -1415,19 +1426,22 @@ cudaError_t launch_batch(const BatchLaunch& L, cudaStream_t st) {
   if (L.half && L.prefilter) H = HalfOperands{static_cast<const __half*>(L.xh), static_cast<const __half*>(L.qh), L.qinv, L.coef, L.dp};
   if (L.selw_smem != 0 && (W == 1 || force_warp)) {
     const int wpb = BQ_SELECT_THREADS / 32;
-    pick_select_warp(TPR, L.cosine)<<<(L.nq + wpb - 1) / wpb, BQ_SELECT_THREADS, L.selw_smem, st>>>(
-        L.X, L.n, L.d, L.q, L.skip, L.gm, L.gm_stride, L.ngroups, L.group, L.stats, L.half ? 1 : 0, H, L.k, L.cap, L.fb, L.nq,
-        L.ids_out, L.scores_out, L.counts_out, L.id_base, L.out_stride > 0 ? L.out_stride : L.k);
+    e = launch_pdl(pick_select_warp(TPR, L.cosine), dim3((L.nq + wpb - 1) / wpb), dim3(BQ_SELECT_THREADS), L.selw_smem, st,
+                   L.X, L.n, L.d, L.q, L.skip, L.gm, L.gm_stride, L.ngroups, L.group, L.stats, L.half ? 1 : 0, H, L.k, L.cap, L.fb,
+                   L.nq, L.ids_out, L.scores_out, L.counts_out, L.id_base, L.out_stride > 0 ? L.out_stride : (int64_t)L.k);
+    if (e != cudaSuccess) return e;
   } else {
     if (W < 2) W = 2;
-    pick_select(TPR, L.cosine, L.k)<<<dim3(P, L.nq), 32 * W, batch_select_smem(L, W), st>>>(
-        L.X, L.n, L.d, L.q, L.skip, L.gm, L.gm_stride, L.ngroups, L.group, L.stats, L.half ? 1 : 0, H, L.k, L.kp, L.cap, L.fb, L.nq, o);
+    e = launch_pdl(pick_select(TPR, L.cosine, L.k), dim3(P, L.nq), dim3(32 * W), batch_select_smem(L, W), st,
+                   L.X, L.n, L.d, L.q, L.skip, L.gm, L.gm_stride, L.ngroups, L.group, L.stats, L.half ? 1 : 0, H, L.k, L.kp, L.cap,
+                   L.fb, L.nq, o);
+    if (e != cudaSuccess) return e;
   }
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   count_launch();
   const int gy = L.nq < BQ_FB_SLOTS ? L.nq : BQ_FB_SLOTS;
-  pick_fallback(TPR, L.cosine, L.k)<<<dim3(L.fb_gx, gy), L.fb_threads, L.fb_smem, st>>>(
-      L.X, L.n, L.d, L.q, L.skip, L.k, L.kp, L.fb, o);
+  // (launched normally: this kernel re-reads, through plain loads, what the selection kernel wrote)
+  pick_fallback(TPR, L.cosine, L.k)<<<dim3(L.fb_gx, gy), L.fb_threads, L.fb_smem, st>>>(L.X, L.n, L.d, L.q, L.skip, L.k, L.kp, L.fb, o);
   return cudaGetLastError();
 }
 

@@ -196,6 +196,10 @@ __device__ __forceinline__ uint4 ld_stream_u4(const uint4* p) {
   return r;
 }
 
+// programmatic dependent launch (see launch_pdl in kernels.h)
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- mbarrier + bulk asynchronous copy (TMA without a tensor map: 1-D, 16-byte granular) ----------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {

@@ -11,6 +11,30 @@ constexpr int SCAN_THREADS = 256;
 
 void count_launch();  // bumps the process-wide kernel launch counter (api.cu)
 
+// Launch with programmatic stream serialisation: the kernel may be set up (and its CTAs placed, resources
+// permitting) while its predecessor in the stream is still running.  Every kernel launched this way executes
+// pdl_wait() before it touches anything the predecessor wrote; pdl_trigger() at the top of a kernel lets ITS
+// successor start early.  Both are no-ops without the attribute.
+bool pdl_enabled();  // option "pdl" (api.cu)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl_if(bool want, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (want && pdl_enabled()) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  return launch_pdl_if(true, kern, grid, block, smem, st, args...);
+}
+
 // ---- scan.cu: exact brute-force scan + top-k, one launch --------------------------------------
 struct ScanLaunch {
   const float* X;        // [n][d] resident rows

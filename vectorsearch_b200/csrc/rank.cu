@@ -31,10 +31,11 @@ __device__ __forceinline__ void block_bitonic_sort_keys(ulonglong2* a, int n) {
 
 __global__ void __launch_bounds__(1024)
 rank_kernel(const float* __restrict__ X, int64_t n, int d, const uint8_t* __restrict__ skip, int lanes,
-            const float* __restrict__ Q, const int64_t* __restrict__ cand_ids, int nc, int np, int k,
+            const float* __restrict__ Q, const int64_t* cand_ids /* predecessor's output (launch_pdl): no __restrict__ */, int nc, int np, int k,
             int cosine, int64_t id_base, int64_t* __restrict__ ids_out, double* __restrict__ scores_out,
             int32_t* __restrict__ counts_out) {
   extern __shared__ __align__(16) ulonglong2 skey[];  // [np]
+  pdl_wait();  // the candidate ids come from the kernel before (ADC scan / its fallback check)
   const int qi = blockIdx.x;
   const float* q = Q + (size_t)qi * d;
   const int64_t* cand = cand_ids + (size_t)qi * nc;
@@ -331,11 +332,9 @@ cudaError_t launch_rank(const RankLaunch& L, cudaStream_t st) {
   // candidate rows is one or two latency-bound rounds
   int threads = RANK_THREADS;
   while (threads < 1024 && threads < 16 * L.nc) threads <<= 1;
-  rank_kernel<<<L.nq, threads, smem, st>>>(L.X, L.n, L.d, L.skip, L.lanes, L.q, L.cand_ids, L.nc, np,
-                                               L.k, L.metric == 1, L.id_base, L.ids_out, L.scores_out,
-                                               L.counts_out);
   count_launch();
-  return cudaGetLastError();
+  return launch_pdl(rank_kernel, dim3(L.nq), dim3(threads), smem, st, L.X, L.n, L.d, L.skip, L.lanes, L.q, L.cand_ids, L.nc, np,
+                    L.k, (int)(L.metric == 1), L.id_base, L.ids_out, L.scores_out, L.counts_out);
 }
 
 cudaError_t launch_merge(const int64_t* ids, const double* scores, int64_t total, int k,
