@@ -530,11 +530,12 @@ def test_pq_encode_matches_oracle(vs, oracle, n, d, M, K):
         seg.free()
 
 
-@pytest.mark.parametrize("tensor_cores", [1, 0])
+@pytest.mark.parametrize("tensor_cores", [2, 1, 0])
 @pytest.mark.parametrize("n,d,M,K", [(20001, 128, 16, 256), (5000, 64, 8, 200), (777, 32, 4, 3), (63, 8, 1, 256),
                                      (9000, 40, 5, 33)])
 def test_pq_encode_subdim8_tensor_core_and_ffma_nomination(vs, oracle, tensor_cores, n, d, M, K):
-    """subDim 8 (the production shape) nominates with mma.sync 3xTF32 or with the FFMA kernel; both decide
+    """subDim 8 (the production shape) nominates with tcgen05 (fp16 hi/lo operand pairs, pq_tc.cu), with mma.sync
+    3xTF32 or with the FFMA kernel; all decide
     near-ties in the reference arithmetic, so both are bit-identical to the oracle -- near-duplicate centroids,
     centroids trained on the data (rows AT a centroid) and ragged K / n included."""
     vs.set_option("pq_tensor_cores", tensor_cores)

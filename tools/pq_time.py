@@ -14,7 +14,7 @@ seg = vs.Segment.generate(42, 0, n, 128)
 tr = vs.Segment.generate(42, 0, min(n, 1_000_000), 128)
 cent = vs.PqTrainer.train(None, 128, 16, 256, 5, 42, segment=tr)
 tr.free()
-for tc in (1, 0):
+for tc in (2, 0):
     vs.set_option("pq_tensor_cores", tc)
     seg.attach_pq(cent)
     torch.cuda.synchronize()

@@ -255,7 +255,10 @@ struct PqAssignLaunch {
   int32_t* assign_i32;     // nullable: [M][n]
   int s_begin, s_end;      // subspaces to process
 };
-void pq_set_tensor_cores(int on);  // subDim 8: mma.sync 3xTF32 nomination (default) or the FFMA kernel
+// subDim 8 nomination: 0 = FFMA kernel, 1 = mma.sync 3xTF32, 2 = tcgen05 (pq_tc.cu)
+void pq_set_tensor_cores(int mode);
+bool pq_tc_supported(const PqAssignLaunch& L);
+cudaError_t launch_pq_assign_tc(const PqAssignLaunch& L, int sms, cudaStream_t st);  // synchronises st before returning
 cudaError_t launch_pq_assign(const PqAssignLaunch& L, cudaStream_t st);
 
 }  // namespace vs

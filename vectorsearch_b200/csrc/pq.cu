@@ -26,7 +26,7 @@ constexpr int PQ_THREADS = 512;
 // the legacy tensor path issues one m16n8k8 tf32 mma.sync per ~80 cycles per SM sub-partition, 81.6 ms per pass
 // against 42.9 ms for the FFMA kernel.  Kept (and parity-tested) as the reference point for the tcgen05 version.
 static std::atomic<int> g_pq_tensor_cores{0};
-void pq_set_tensor_cores(int on) { g_pq_tensor_cores.store(on); }
+void pq_set_tensor_cores(int mode) { g_pq_tensor_cores.store(mode); }
 constexpr size_t PQ_SMEM_BUDGET = 200 * 1024;
 
 __device__ __forceinline__ float pq_band(float m1, int SD) {
@@ -433,7 +433,16 @@ cudaError_t launch_pq_assign(const PqAssignLaunch& L, cudaStream_t st) {
   if (aligned && (size_t)L.K * L.subDim * 4 <= PQ_SMEM_BUDGET) {
     switch (L.subDim) {
       case 4: return pq_assign_t<4>(L, st);
-      case 8: return (L.K <= 256 && g_pq_tensor_cores.load() != 0) ? pq_assign8_mma(L, st) : pq_assign_t<8>(L, st);
+      case 8: {
+        const int mode = g_pq_tensor_cores.load();
+        if (mode == 2 && pq_tc_supported(L)) {
+          int dev = 0, sms = 0;
+          cudaGetDevice(&dev);
+          cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+          return launch_pq_assign_tc(L, sms, st);
+        }
+        return (L.K <= 256 && mode == 1) ? pq_assign8_mma(L, st) : pq_assign_t<8>(L, st);
+      }
       case 16: return pq_assign_t<16>(L, st);
       case 32: return pq_assign_t<32>(L, st);
       case 48: return pq_assign_t<48>(L, st);

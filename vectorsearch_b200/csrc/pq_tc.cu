@@ -1,0 +1,428 @@
+// pq_tc.cu -- K3 on the 5th-generation tensor cores: PQ assignment (PqEncoder.encode, J/pq/PqEncoder.java:18-37, and
+// the assignment step of PqTrainer.train, J/pq/PqTrainer.java:56-68) for the production shape: 8-float sub-vectors
+// (d = 8 M), K <= 256 centroids per subspace.
+//
+// Per subspace the assignment is [rows x 8] x [8 x K]: a GEMM with an inner dimension of 8.  The reference decides
+// every argmin in fp64 (the sub-vector is shorter than the SIMD register, J/util/Distances.java:77-94), so the
+// tensor cores only NOMINATE, with enough precision that a second look is rare:
+//   * operands are fp16 pairs: x s = xh + xl, c s = ch + cl (s a power of two that brings both into [-64, 64]), and
+//     32 halfs per (row, subspace) / (centroid, subspace) -- two subspaces share a 128-byte operand row -- carry
+//         A = [ xh | xl | xh | 1 1 0 .. ]      B = [ ch | ch | cl | nh nl 0 .. ],   nh + nl = -|c s|^2 / 2
+//     so two tcgen05.mma.kind::f16 (K = 16 each) leave  D = s^2 (<x,c> - |c|^2 / 2)  in TMEM, good to ~2^-21:
+//     argmax_c D = argmin_c |x - c|^2, no coefficient to apply in the epilogue.
+//   * pq_tc_assign_kernel: persistent, warp-specialised like batch_gemm_kernel.  A CTA keeps the B blocks of 4
+//     subspaces resident (64 KB), TMA streams the A blocks of its row tiles (128 rows x 128 bytes per subspace pair), one
+//     thread issues the MMAs into a double-buffered 128 x 256 accumulator, four epilogue warps (thread = row) read
+//     it back and keep the two largest keys (D with the low 6 mantissa bits replaced by a column slot) in four
+//     independent chains.  If the runner-up is outside the error band the winner IS the reference argmin; otherwise
+//     the warp re-reads the accumulator and the centroids inside the band are decided in the reference's own
+//     arithmetic, strict '<' in ascending index -- bit-identical codes, like pq.cu.
+//   * tq_prep_*: one pass that writes the operand images (64 bytes per row and subspace; the scale and the
+//     norm bounds of the error band stay on the device, nothing synchronises).
+// The kernel is bound by its epilogue (four instructions per (row, centroid)), not by the MMA.
+#include <algorithm>
+
+#include "kernels.h"
+#include "tc05.cuh"
+
+namespace vs {
+
+namespace {
+
+constexpr int TQ_M = 128;          // rows per tile = TMEM lanes
+constexpr int TQ_N = 256;          // centroids per subspace (padded) = accumulator columns
+constexpr int TQ_SD = 8;           // floats per sub-vector
+constexpr int TQ_SPC = 4;          // subspaces whose B blocks a CTA keeps resident
+constexpr int TQ_STAGES = 4;
+constexpr int TQ_THREADS = 256;    // warp 0 TMA, warp 1 MMA, warp 2 TMEM allocator, warps 4..7 epilogue
+constexpr uint32_t TQ_A_BYTES = TQ_M * 128;
+constexpr uint32_t TQ_B_BYTES = TQ_N * 128;
+constexpr int TQ_PPC = TQ_SPC / 2;  // subspace pairs per CTA: a 128-byte operand row carries two subspaces
+constexpr size_t TQ_SMEM = (size_t)TQ_PPC * TQ_B_BYTES + (size_t)TQ_STAGES * TQ_A_BYTES + 256;
+constexpr uint32_t TQ_IDESC = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(TQ_N >> 3) << 17) | ((uint32_t)(TQ_M >> 4) << 24);
+
+struct TqStats {            // device-resident, written by the prep kernels
+  unsigned int amax_bits;   // max |element| over rows and centroids (fixes the scale)
+  unsigned int xxmax_bits;  // max |sub-vector|^2 over the rows
+  unsigned int nmax_bits;   // max |centroid|^2
+  int pad;
+};
+
+__device__ __forceinline__ float tq_scale(const TqStats* st) {
+  const float amax = __uint_as_float(st->amax_bits);
+  if (!(amax > 0.0f) || !(amax < 1e30f)) return 1.0f;
+  int e;
+  frexpf(amax, &e);            // amax <= 2^e
+  return ldexpf(1.0f, 6 - e);  // |x s| <= 64
+}
+
+// max |element| of a float array (finite values only)
+__global__ void __launch_bounds__(256) tq_amax_kernel(const float* __restrict__ v, int64_t count, TqStats* __restrict__ st) {
+  float m = 0.0f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+    const float a = fabsf(v[i]);
+    if (a < 1e30f) m = fmaxf(m, a);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL_MASK, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(&st->amax_bits, __float_as_uint(m));
+}
+
+__device__ __forceinline__ void tq_split(float v, float s, __half& hi, __half& lo) {
+  const float t = v * s;  // exact: s is a power of two
+  hi = __float2half_rn(t);
+  lo = __float2half_rn(t - __half2float(hi));
+}
+
+// operand image of the rows: Xop[r][p] = 128 bytes for the subspace PAIR p = (2p, 2p + 1):
+//   {xh[8], xl[8], xh[8], 1, 1, 0 x 6} of subspace 2p, then the same of subspace 2p + 1.
+// Eight threads share a (row, pair) and write one 16-byte chunk each, so a warp stores 512 contiguous bytes.
+__global__ void __launch_bounds__(256)
+tq_prep_rows_kernel(const float* __restrict__ X, int64_t n, int d, int M, __half* __restrict__ Xop, TqStats* __restrict__ st) {
+  const float s = tq_scale(st);
+  float xxm = 0.0f;
+  const int P = M >> 1;
+  const int64_t total = n * P * 8;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int chunk = (int)(t & 7);
+    const int64_t i = t >> 3;  // (row, pair)
+    const int64_t r = i / P;
+    const int p = (int)(i - r * P);
+    const int sub = 2 * p + (chunk >> 2);
+    const float4* src = reinterpret_cast<const float4*>(X + (size_t)r * d + (size_t)sub * TQ_SD);
+    const float4 a = __ldg(src), b = __ldg(src + 1);
+    const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    __align__(16) __half h[8];
+    const int kind = chunk & 3;  // 0: xh, 1: xl, 2: xh, 3: ones
+    if (kind == 3) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) h[j] = __float2half_rn(j < 2 ? 1.0f : 0.0f);
+      float xx = 0.0f;
+#pragma unroll
+      for (int j = 0; j < 8; j++) xx = fmaf(x[j], x[j], xx);
+      if (xx < 1e30f) xxm = fmaxf(xxm, xx);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        __half hi, lo;
+        tq_split(x[j], s, hi, lo);
+        h[j] = kind == 1 ? lo : hi;
+      }
+    }
+    reinterpret_cast<uint4*>(Xop)[t] = *reinterpret_cast<const uint4*>(h);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) xxm = fmaxf(xxm, __shfl_xor_sync(FULL_MASK, xxm, o));
+  if ((threadIdx.x & 31) == 0 && xxm > 0.0f) atomicMax(&st->xxmax_bits, __float_as_uint(xxm));
+}
+
+// operand image of the centroids: Cop[p][c] = 128 bytes {ch[8], ch[8], cl[8], nh, nl, 0 x 6} of subspace 2p, then
+// the same of subspace 2p + 1; rows c >= K (padding up to 256) get the most negative norm term, so they never win
+__global__ void __launch_bounds__(256)
+tq_prep_centroids_kernel(const float* __restrict__ C, int M, int K, __half* __restrict__ Cop, TqStats* __restrict__ st) {
+  const float s = tq_scale(st);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // (subspace, centroid)
+  if (i >= M * TQ_N) return;
+  const int sub = i / TQ_N, c = i % TQ_N;
+  __align__(16) __half h[32];
+#pragma unroll
+  for (int j = 0; j < 32; j++) h[j] = __float2half_rn(0.0f);
+  if (c < K) {
+    const float* src = C + ((size_t)sub * K + c) * TQ_SD;
+    float nn = 0.0f, ns = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      __half hi, lo;
+      tq_split(src[j], s, hi, lo);
+      h[j] = hi;
+      h[8 + j] = hi;
+      h[16 + j] = lo;
+      const float t = src[j] * s;
+      ns = fmaf(t, t, ns);
+      nn = fmaf(src[j], src[j], nn);
+    }
+    const float nt = -0.5f * ns;
+    const __half nh = __float2half_rn(nt);
+    h[24] = nh;
+    h[25] = __float2half_rn(nt - __half2float(nh));
+    if (nn < 1e30f && nn > 0.0f) atomicMax(&st->nmax_bits, __float_as_uint(nn));
+  } else {
+    h[24] = __float2half_rn(-60000.0f);
+  }
+  uint4* dst = reinterpret_cast<uint4*>(Cop + ((size_t)(sub >> 1) * TQ_N + c) * 64 + (size_t)(sub & 1) * 32);
+#pragma unroll
+  for (int j = 0; j < 4; j++) dst[j] = reinterpret_cast<const uint4*>(h)[j];
+}
+
+// grid.x = (M / TQ_SPC) * nsplit: CTA (sg, split) owns subspaces sg*4 .. sg*4+3 and row tiles split, split + nsplit, ..
+__global__ void __launch_bounds__(TQ_THREADS, 1)
+pq_tc_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const float* __restrict__ X, int64_t n, int d, int M, int K, const float* __restrict__ centroids, int lanes,
+                    const TqStats* stats, int64_t row0 /* first row of this slab */, int64_t nslab, int nsg, int64_t tiles,
+                    uint8_t* __restrict__ codes_u8, int32_t* __restrict__ assign_i32) {
+  extern __shared__ __align__(1024) uint8_t tq_smem[];
+  uint8_t* bq = tq_smem;                                          // [TQ_PPC][32 KB] centroid blocks (two subspaces each)
+  uint8_t* stages = bq + (size_t)TQ_PPC * TQ_B_BYTES;             // [TQ_STAGES][16 KB] row blocks (two subspaces each)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stages + (size_t)TQ_STAGES * TQ_A_BYTES);
+  uint64_t* full = bars;                    // [TQ_STAGES]
+  uint64_t* empty = bars + TQ_STAGES;       // [TQ_STAGES]
+  uint64_t* tfull = bars + 2 * TQ_STAGES;   // [2]
+  uint64_t* tempty = bars + 2 * TQ_STAGES + 2;
+  uint64_t* bfull = bars + 2 * TQ_STAGES + 4;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * TQ_STAGES + 5);
+  if ((smem_u32(tq_smem) & 1023u) != 0) __trap();
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int sg = blockIdx.x % nsg;
+  const int split = blockIdx.x / nsg;
+  const int nsplit = gridDim.x / nsg;
+  const int s_first = sg * TQ_SPC;
+  const int ns = min(TQ_SPC, M - s_first);  // even: M is even
+  const int np = ns >> 1;
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    for (int s = 0; s < TQ_STAGES; s++) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, 1);
+    }
+    for (int a = 0; a < 2; a++) {
+      mbar_init(tfull + a, 1);
+      mbar_init(tempty + a, 4);
+    }
+    mbar_init(bfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(s_tmem);
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer =====
+      mbar_expect_tx(bfull, (uint32_t)np * TQ_B_BYTES);
+      for (int pl = 0; pl < np; pl++) tma_load_2d(bq + (size_t)pl * TQ_B_BYTES, &tmB, 0, ((s_first >> 1) + pl) * TQ_N, bfull);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int64_t tile = split; tile < tiles; tile += nsplit) {
+        for (int pl = 0; pl < np; pl++) {
+          mbar_wait(empty + s, ph ^ 1);
+          mbar_expect_tx(full + s, TQ_A_BYTES);
+          tma_load_2d(stages + (size_t)s * TQ_A_BYTES, &tmA, ((s_first >> 1) + pl) * 64, (int)(tile * TQ_M), full + s);
+          if (++s == TQ_STAGES) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ===== MMA issuer =====
+      int s = 0, it = 0;
+      uint32_t ph = 0;
+      mbar_wait(bfull, 0);
+      for (int64_t tile = split; tile < tiles; tile += nsplit) {
+        for (int pl = 0; pl < np; pl++) {
+          mbar_wait(full + s, ph);
+          const uint64_t adesc = umma_desc_sw128(smem_u32(stages + (size_t)s * TQ_A_BYTES));
+          const uint64_t bdesc = umma_desc_sw128(smem_u32(bq + (size_t)pl * TQ_B_BYTES));
+          for (int e = 0; e < 2; e++, it++) {  // the two subspaces of the pair: halfs 0..31 and 32..63 of the operand rows
+            const int a = it & 1;
+            mbar_wait(tempty + a, ((it >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)a * TQ_N;
+            tc_mma_f16(d_tmem, adesc + 4 * e, bdesc + 4 * e, TQ_IDESC, 0u);          // xh.ch + xl.ch
+            tc_mma_f16(d_tmem, adesc + 4 * e + 2, bdesc + 4 * e + 2, TQ_IDESC, 1u);  // xh.cl + 1.nh + 1.nl
+            tc_commit(tfull + a);
+          }
+          tc_commit(empty + s);
+          if (++s == TQ_STAGES) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {  // ===== epilogue: thread = row =====
+    const int lq = warp - 4;
+    const float ninf = __int_as_float(0xff800000);
+    const float s = tq_scale(stats);
+    // |estimate - reference| <= band (in distance units), see pq.cu; in D units: D = s^2 (|x|^2 - dist) / 2
+    const float band = (__uint_as_float(stats->xxmax_bits) + __uint_as_float(stats->nmax_bits)) * (1.0f / 32768.0f) + 1e-30f;
+    const float bandD = band * s * s * 0.5f;
+    int it = 0;
+    for (int64_t tile = split; tile < tiles; tile += nsplit) {
+      const int64_t lrow = tile * TQ_M + lq * 32 + lane;  // row within the slab
+      const bool live = lrow < nslab;
+      const int64_t row = row0 + lrow;
+      for (int sl = 0; sl < ns; sl++, it++) {
+        const int a = it & 1;
+        const int sub = s_first + sl;
+        mbar_wait(tfull + a, (it >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(a * TQ_N);
+        float m1[4], m2[4];  // four independent chains: column j -> chain j & 3, slot j >> 2
+#pragma unroll
+        for (int c = 0; c < 4; c++) m1[c] = m2[c] = ninf;
+        uint32_t v[2][32];
+        tc_ld32(taddr, v[0]);
+#pragma unroll
+        for (int h = 0; h < 8; h++) {
+          tc_wait_ld();
+          tc_pin32(v[h & 1]);
+          if (h < 7) tc_ld32(taddr + (uint32_t)(h + 1) * 32, v[(h + 1) & 1]);
+#pragma unroll
+          for (int j = 0; j < 32; j++) {
+            const int col = h * 32 + j;
+            const float key = __uint_as_float((v[h & 1][j] & 0xffffffc0u) | (uint32_t)(col >> 2));
+            const float lo = fminf(m1[col & 3], key);
+            m1[col & 3] = fmaxf(m1[col & 3], key);
+            m2[col & 3] = fmaxf(m2[col & 3], lo);
+          }
+        }
+        // the row's two largest keys over the four chains
+        float b1 = m1[0], b2 = m2[0];
+        int bc = 0;
+#pragma unroll
+        for (int c = 1; c < 4; c++) {
+          if (m1[c] > b1) {
+            b2 = fmaxf(b1, m2[c]);
+            b1 = m1[c];
+            bc = c;
+          } else {
+            b2 = fmaxf(b2, m1[c]);
+          }
+        }
+        int best = (int)((__float_as_uint(b1) & 63u) * 4u) + bc;
+        const float v1 = __uint_as_float(__float_as_uint(b1) & 0xffffffc0u), v2 = __uint_as_float(__float_as_uint(b2) & 0xffffffc0u);
+        const bool finite = v1 > ninf && v1 < __int_as_float(0x7f800000);
+        // truncating 6 mantissa bits moves a key by at most 2^-17 |D|: part of the band (|D| <= s^2 (|x|^2 + |c|^2))
+        const bool doubt = live && (!finite || !(v1 - v2 > 2.0f * bandD) || best >= K);
+        const unsigned any = __ballot_sync(FULL_MASK, doubt);
+        if (any) {
+          // near-tie, duplicate centroids, NaN or overflow somewhere in this warp: those rows decide in the
+          // reference's arithmetic among the centroids inside the band (all of them when the estimate is unusable)
+          const float* xr = X + (size_t)(live ? row : 0) * d + (size_t)sub * TQ_SD;
+          const float* cg = centroids + (size_t)sub * K * TQ_SD;
+          const float lim = v1 - 4.0f * bandD;
+          double bestDist = __longlong_as_double(0x7ff0000000000000ll);
+          int ebest = 0;
+#pragma unroll 1
+          for (int h = 0; h < 8; h++) {
+            uint32_t w[32];
+            tc_ld32(taddr + (uint32_t)h * 32, w);  // warp-collective: every lane takes part
+            tc_wait_ld();
+            tc_pin32(w);
+            // columns of this load inside the band, as a bit mask (registers only, no indexed array)
+            uint32_t mask = 0u;
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+              const float Dj = __uint_as_float(w[j]);
+              mask |= (!finite || !(Dj < lim)) ? (1u << j) : 0u;  // NaN estimates are looked at
+            }
+            if (!doubt) mask = 0u;
+            while (mask) {  // ascending centroid index
+              const int j = __ffs(mask) - 1;
+              mask &= mask - 1;
+              const int ci = h * 32 + j;
+              if (ci >= K) break;
+              const double dd = ref_sum_thread<REF_L2SQ>(xr, cg + (size_t)ci * TQ_SD, TQ_SD, lanes);
+              if (dd < bestDist) {  // strict <: lowest ci wins ties, NaN never wins (PqEncoder.java:29)
+                bestDist = dd;
+                ebest = ci;
+              }
+            }
+          }
+          if (doubt) best = ebest;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty + a);
+        if (live) {
+          if (codes_u8) codes_u8[(size_t)row * M + sub] = (uint8_t)(best & 0xFF);
+          if (assign_i32) assign_i32[(size_t)sub * n + row] = best;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+struct DevMem {
+  void* p = nullptr;
+  ~DevMem() {
+    if (p) cudaFree(p);
+  }
+};
+
+}  // namespace
+
+bool pq_tc_supported(const PqAssignLaunch& L) {
+  return L.subDim == TQ_SD && L.K >= 1 && L.K <= TQ_N && L.d == L.M * TQ_SD && (L.M % 2) == 0 && L.s_begin == 0 &&
+         L.s_end == L.M && encode_fn() != nullptr;
+}
+
+// Tensor-core assignment over all subspaces.  The operand image of the rows (128 bytes per row and subspace) is
+// built slab by slab in scratch memory, so any n fits.
+cudaError_t launch_pq_assign_tc(const PqAssignLaunch& L, int sms, cudaStream_t st) {
+  cudaError_t e;
+  const int M = L.M;
+  const int nsg = (M + TQ_SPC - 1) / TQ_SPC;
+  size_t free_b = 0, total_b = 0;
+  if ((e = cudaMemGetInfo(&free_b, &total_b)) != cudaSuccess) return e;
+  const size_t per_row = (size_t)(M / 2) * 128;
+  size_t budget = free_b / 2;
+  if (budget > (size_t(24) << 30)) budget = size_t(24) << 30;
+  int64_t slab = (int64_t)(budget / per_row);
+  slab = (slab / TQ_M) * TQ_M;
+  if (slab < TQ_M) return cudaErrorMemoryAllocation;
+  if (slab > L.n) slab = (L.n + TQ_M - 1) / TQ_M * TQ_M;
+  DevMem xop, cop, stats;
+  if ((e = cudaMalloc(&xop.p, (size_t)slab * per_row)) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&cop.p, (size_t)(M / 2) * TQ_N * 128)) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&stats.p, sizeof(TqStats))) != cudaSuccess) return e;
+  TqStats* d_st = static_cast<TqStats*>(stats.p);
+  if ((e = cudaMemsetAsync(d_st, 0, sizeof(TqStats), st)) != cudaSuccess) return e;
+  // one scale for rows and centroids: max |element| of both
+  count_launch();
+  tq_amax_kernel<<<sms * 8, 256, 0, st>>>(L.X, L.n * L.d, d_st);
+  count_launch();
+  tq_amax_kernel<<<8, 256, 0, st>>>(L.centroids, (int64_t)M * L.K * TQ_SD, d_st);
+  count_launch();
+  tq_prep_centroids_kernel<<<(M * TQ_N + 255) / 256, 256, 0, st>>>(L.centroids, M, L.K, static_cast<__half*>(cop.p), d_st);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  CUtensorMap tmB;
+  if (!encode_rows_map(&tmB, cop.p, (int64_t)(M / 2) * TQ_N, 64, 64, true, TQ_N)) return cudaErrorInvalidValue;
+  if ((e = cudaFuncSetAttribute(pq_tc_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TQ_SMEM)) != cudaSuccess) return e;
+  for (int64_t r0 = 0; r0 < L.n; r0 += slab) {
+    const int64_t cnt = std::min<int64_t>(slab, L.n - r0);
+    count_launch();
+    tq_prep_rows_kernel<<<sms * 16, 256, 0, st>>>(L.X + (size_t)r0 * L.d, cnt, L.d, M, static_cast<__half*>(xop.p), d_st);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    CUtensorMap tmA;  // [cnt rows][M / 2 pairs * 64 halfs], box = 64 halfs x 128 rows
+    if (!encode_rows_map(&tmA, xop.p, cnt, M * 32, (int64_t)M * 32, true, TQ_M)) return cudaErrorInvalidValue;
+    const int64_t tiles = (cnt + TQ_M - 1) / TQ_M;
+    int nsplit = sms / nsg;
+    if (nsplit < 1) nsplit = 1;
+    if (nsplit > tiles) nsplit = (int)tiles;
+    count_launch();
+    pq_tc_assign_kernel<<<nsg * nsplit, TQ_THREADS, TQ_SMEM, st>>>(tmA, tmB, L.X, L.n, L.d, M, L.K, L.centroids, L.lanes, d_st, r0,
+                                                                   cnt, nsg, tiles, L.codes_u8, L.assign_i32);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
+  // the scratch is freed when this returns: wait for the kernels that read it
+  return cudaStreamSynchronize(st);
+}
+
+}  // namespace vs
