@@ -195,8 +195,10 @@ int64_t vs_kernel_launch_count(void);
  * work of another stream (the next query's prologue, a collective's CTAs) runs beside it (default 0).
  * "pdl" (default 1): the kernels of one call are chained with programmatic dependent launch (the next
  * kernel is set up while its predecessor runs and waits, in the kernel, for its results).
- * "pq_tensor_cores" (default 0): subDim-8 PQ assignment nominates with mma.sync 3xTF32 instead of FFMA
- * (slower on B200, kept as a measured reference point).  Results never depend on any of them. */
+ * "pq_tensor_cores": how PQ assignment with 8-float sub-vectors nominates -- 2 (default) tcgen05 on fp16
+ * hi/lo operand pairs (pq_tc.cu; needs n * M * 64 bytes of scratch, built slab by slab), 0 the FFMA kernel,
+ * 1 mma.sync 3xTF32 (slower on B200, kept as a measured reference point).  Results never depend on any of
+ * them. */
 int32_t vs_set_option(const char* name, int64_t value);
 
 /* ---- diagnostics -----------------------------------------------------------------------------------

@@ -557,7 +557,7 @@ def test_pq_encode_subdim8_tensor_core_and_ffma_nomination(vs, oracle, tensor_co
         want = oracle.pq_encode_batch(cent, rows, threads=8)
         assert np.array_equal(vs.PqEncoder.encode_batch(cent, rows), want)
     finally:
-        vs.set_option("pq_tensor_cores", 0)
+        vs.set_option("pq_tensor_cores", 2)
 
 
 def test_pq_encode_duplicate_centroids_and_nan(vs, oracle):

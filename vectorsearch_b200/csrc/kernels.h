@@ -258,7 +258,11 @@ struct PqAssignLaunch {
 // subDim 8 nomination: 0 = FFMA kernel, 1 = mma.sync 3xTF32, 2 = tcgen05 (pq_tc.cu)
 void pq_set_tensor_cores(int mode);
 bool pq_tc_supported(const PqAssignLaunch& L);
-cudaError_t launch_pq_assign_tc(const PqAssignLaunch& L, int sms, cudaStream_t st);  // synchronises st before returning
+cudaError_t launch_pq_assign_tc(const PqAssignLaunch& L, int sms, cudaStream_t st);
+// Between begin and end (same host thread) the rows' operand image is built once and reused by every
+// launch_pq_assign_tc over the same rows (the Lloyd iterations of PqTrainer.train).
+void pq_tc_scope_begin();
+void pq_tc_scope_end();
 cudaError_t launch_pq_assign(const PqAssignLaunch& L, cudaStream_t st);
 
 }  // namespace vs

@@ -22,10 +22,11 @@
 namespace vs {
 
 constexpr int PQ_THREADS = 512;
-// subDim 8: nominate with mma.sync (3xTF32) instead of FFMA.  OFF by default: measured on B200 (10M x 128, M 16, K 256)
-// the legacy tensor path issues one m16n8k8 tf32 mma.sync per ~80 cycles per SM sub-partition, 81.6 ms per pass
-// against 42.9 ms for the FFMA kernel.  Kept (and parity-tested) as the reference point for the tcgen05 version.
-static std::atomic<int> g_pq_tensor_cores{0};
+// subDim 8 nomination: 2 = tcgen05 (pq_tc.cu, the default where the shape allows), 1 = mma.sync 3xTF32 (below),
+// 0 = the FFMA kernel above.  Measured on B200, 10M x 128, M 16, K 256, one pass: tcgen05 16.7 ms (+ 3.4 ms to build
+// the operand image, once per training run), FFMA 38 ms, mma.sync 82 ms (the legacy tensor path issues one
+// m16n8k8 tf32 mma.sync per ~80 cycles per SM sub-partition; kept, parity-tested, as a reference point).
+static std::atomic<int> g_pq_tensor_cores{2};
 void pq_set_tensor_cores(int mode) { g_pq_tensor_cores.store(mode); }
 constexpr size_t PQ_SMEM_BUDGET = 200 * 1024;
 

@@ -373,45 +373,94 @@ bool pq_tc_supported(const PqAssignLaunch& L) {
          L.s_end == L.M && encode_fn() != nullptr;
 }
 
-// Tensor-core assignment over all subspaces.  The operand image of the rows (128 bytes per row and subspace) is
+// Operand image kept between calls: PqTrainer.train assigns the SAME rows once per Lloyd iteration, so the trainer
+// opens a scope (pq_tc_scope_begin / _end) within which the rows' image -- when it fits in one slab -- is built once
+// and only the centroid image is refreshed.  Outside a scope nothing outlives a call.
+namespace {
+struct TcScope {
+  bool open = false, valid = false;
+  const float* X = nullptr;
+  int64_t n = 0;
+  int d = 0, M = 0;
+  void *xop = nullptr, *cop = nullptr, *stats = nullptr;
+  void release() {
+    if (xop) cudaFree(xop);
+    if (cop) cudaFree(cop);
+    if (stats) cudaFree(stats);
+    xop = cop = stats = nullptr;
+    valid = false;
+  }
+};
+thread_local TcScope t_scope;
+}  // namespace
+
+void pq_tc_scope_begin() {
+  t_scope.release();
+  t_scope.open = true;
+}
+void pq_tc_scope_end() {
+  cudaDeviceSynchronize();
+  t_scope.release();
+  t_scope.open = false;
+}
+
+// Tensor-core assignment over all subspaces.  The operand image of the rows (64 bytes per row and subspace) is
 // built slab by slab in scratch memory, so any n fits.
 cudaError_t launch_pq_assign_tc(const PqAssignLaunch& L, int sms, cudaStream_t st) {
   cudaError_t e;
   const int M = L.M;
   const int nsg = (M + TQ_SPC - 1) / TQ_SPC;
-  size_t free_b = 0, total_b = 0;
-  if ((e = cudaMemGetInfo(&free_b, &total_b)) != cudaSuccess) return e;
   const size_t per_row = (size_t)(M / 2) * 128;
-  size_t budget = free_b / 2;
-  if (budget > (size_t(24) << 30)) budget = size_t(24) << 30;
-  int64_t slab = (int64_t)(budget / per_row);
-  slab = (slab / TQ_M) * TQ_M;
-  if (slab < TQ_M) return cudaErrorMemoryAllocation;
-  if (slab > L.n) slab = (L.n + TQ_M - 1) / TQ_M * TQ_M;
-  DevMem xop, cop, stats;
-  if ((e = cudaMalloc(&xop.p, (size_t)slab * per_row)) != cudaSuccess) return e;
-  if ((e = cudaMalloc(&cop.p, (size_t)(M / 2) * TQ_N * 128)) != cudaSuccess) return e;
-  if ((e = cudaMalloc(&stats.p, sizeof(TqStats))) != cudaSuccess) return e;
-  TqStats* d_st = static_cast<TqStats*>(stats.p);
-  if ((e = cudaMemsetAsync(d_st, 0, sizeof(TqStats), st)) != cudaSuccess) return e;
-  // one scale for rows and centroids: max |element| of both
+  TcScope& sc = t_scope;
+  const bool reuse = sc.open && sc.valid && sc.X == L.X && sc.n == L.n && sc.d == L.d && sc.M == M;
+  int64_t slab = 0;
+  DevMem xop, cop, stats;  // owners when nothing is kept
+  void *p_xop, *p_cop, *p_stats;
+  if (reuse) {
+    slab = (L.n + TQ_M - 1) / TQ_M * TQ_M;
+    p_xop = sc.xop; p_cop = sc.cop; p_stats = sc.stats;
+  } else {
+    size_t free_b = 0, total_b = 0;
+    if ((e = cudaMemGetInfo(&free_b, &total_b)) != cudaSuccess) return e;
+    size_t budget = free_b / 2;
+    if (budget > (size_t(24) << 30)) budget = size_t(24) << 30;
+    slab = (int64_t)(budget / per_row);
+    slab = (slab / TQ_M) * TQ_M;
+    if (slab < TQ_M) return cudaErrorMemoryAllocation;
+    if (slab > L.n) slab = (L.n + TQ_M - 1) / TQ_M * TQ_M;
+    if ((e = cudaMalloc(&xop.p, (size_t)slab * per_row)) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&cop.p, (size_t)(M / 2) * TQ_N * 128)) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&stats.p, sizeof(TqStats))) != cudaSuccess) return e;
+    p_xop = xop.p; p_cop = cop.p; p_stats = stats.p;
+  }
+  TqStats* d_st = static_cast<TqStats*>(p_stats);
+  if (reuse) {
+    // same rows, new centroids: the scale stays (centroids of a training run are means of the rows), the
+    // centroid norm bound is refreshed
+    if ((e = cudaMemsetAsync(&d_st->nmax_bits, 0, sizeof(unsigned int), st)) != cudaSuccess) return e;
+  } else {
+    if ((e = cudaMemsetAsync(d_st, 0, sizeof(TqStats), st)) != cudaSuccess) return e;
+    // one scale for rows and centroids: max |element| of both
+    count_launch();
+    tq_amax_kernel<<<sms * 8, 256, 0, st>>>(L.X, L.n * L.d, d_st);
+    count_launch();
+    tq_amax_kernel<<<8, 256, 0, st>>>(L.centroids, (int64_t)M * L.K * TQ_SD, d_st);
+  }
   count_launch();
-  tq_amax_kernel<<<sms * 8, 256, 0, st>>>(L.X, L.n * L.d, d_st);
-  count_launch();
-  tq_amax_kernel<<<8, 256, 0, st>>>(L.centroids, (int64_t)M * L.K * TQ_SD, d_st);
-  count_launch();
-  tq_prep_centroids_kernel<<<(M * TQ_N + 255) / 256, 256, 0, st>>>(L.centroids, M, L.K, static_cast<__half*>(cop.p), d_st);
+  tq_prep_centroids_kernel<<<(M * TQ_N + 255) / 256, 256, 0, st>>>(L.centroids, M, L.K, static_cast<__half*>(p_cop), d_st);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   CUtensorMap tmB;
-  if (!encode_rows_map(&tmB, cop.p, (int64_t)(M / 2) * TQ_N, 64, 64, true, TQ_N)) return cudaErrorInvalidValue;
+  if (!encode_rows_map(&tmB, p_cop, (int64_t)(M / 2) * TQ_N, 64, 64, true, TQ_N)) return cudaErrorInvalidValue;
   if ((e = cudaFuncSetAttribute(pq_tc_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TQ_SMEM)) != cudaSuccess) return e;
   for (int64_t r0 = 0; r0 < L.n; r0 += slab) {
     const int64_t cnt = std::min<int64_t>(slab, L.n - r0);
-    count_launch();
-    tq_prep_rows_kernel<<<sms * 16, 256, 0, st>>>(L.X + (size_t)r0 * L.d, cnt, L.d, M, static_cast<__half*>(xop.p), d_st);
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (!reuse) {
+      count_launch();
+      tq_prep_rows_kernel<<<sms * 16, 256, 0, st>>>(L.X + (size_t)r0 * L.d, cnt, L.d, M, static_cast<__half*>(p_xop), d_st);
+      if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
     CUtensorMap tmA;  // [cnt rows][M / 2 pairs * 64 halfs], box = 64 halfs x 128 rows
-    if (!encode_rows_map(&tmA, xop.p, cnt, M * 32, (int64_t)M * 32, true, TQ_M)) return cudaErrorInvalidValue;
+    if (!encode_rows_map(&tmA, p_xop, cnt, M * 32, (int64_t)M * 32, true, TQ_M)) return cudaErrorInvalidValue;
     const int64_t tiles = (cnt + TQ_M - 1) / TQ_M;
     int nsplit = sms / nsg;
     if (nsplit < 1) nsplit = 1;
@@ -420,6 +469,15 @@ cudaError_t launch_pq_assign_tc(const PqAssignLaunch& L, int sms, cudaStream_t s
     pq_tc_assign_kernel<<<nsg * nsplit, TQ_THREADS, TQ_SMEM, st>>>(tmA, tmB, L.X, L.n, L.d, M, L.K, L.centroids, L.lanes, d_st, r0,
                                                                    cnt, nsg, tiles, L.codes_u8, L.assign_i32);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
+  if (reuse) return cudaSuccess;  // everything this call touched lives until the scope ends
+  if (sc.open && slab >= L.n) {   // first call of a scope and the whole image fits: keep it
+    sc.release();
+    sc.X = L.X; sc.n = L.n; sc.d = L.d; sc.M = M;
+    sc.xop = xop.p; sc.cop = cop.p; sc.stats = stats.p;
+    xop.p = cop.p = stats.p = nullptr;
+    sc.valid = true;
+    return cudaSuccess;
   }
   // the scratch is freed when this returns: wait for the kernels that read it
   return cudaStreamSynchronize(st);

@@ -280,6 +280,10 @@ int pq_train_device(cudaStream_t st, const float* dX, int64_t n, int d, int M, i
     TCK(cudaFuncSetAttribute(scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ksmem), "smem attr");
   }
 
+  struct TcScopeGuard {  // the rows do not change during training: their tensor-core operand image is built once
+    TcScopeGuard() { pq_tc_scope_begin(); }
+    ~TcScopeGuard() { pq_tc_scope_end(); }
+  } tc_scope_guard;
   JRandom rnd(seed);
   std::vector<int64_t> h_rows((size_t)M * K);
   std::vector<int32_t> h_counts((size_t)M * K);
