@@ -34,11 +34,12 @@ constexpr int TQ_N = 256;          // centroids per subspace (padded) = accumula
 constexpr int TQ_SD = 8;           // floats per sub-vector
 constexpr int TQ_SPC = 4;          // subspaces whose B blocks a CTA keeps resident
 constexpr int TQ_STAGES = 4;
-constexpr int TQ_THREADS = 256;    // warp 0 TMA, warp 1 MMA, warp 2 TMEM allocator, warps 4..7 epilogue
+constexpr int TQ_THREADS = 384;    // warp 0 TMA, warp 1 MMA, warp 2 TMEM allocator, warps 4..11 epilogue
 constexpr uint32_t TQ_A_BYTES = TQ_M * 128;
 constexpr uint32_t TQ_B_BYTES = TQ_N * 128;
 constexpr int TQ_PPC = TQ_SPC / 2;  // subspace pairs per CTA: a 128-byte operand row carries two subspaces
-constexpr size_t TQ_SMEM = (size_t)TQ_PPC * TQ_B_BYTES + (size_t)TQ_STAGES * TQ_A_BYTES + 256;
+constexpr size_t TQ_XCH_BYTES = 2 * 4 * 32 * 16;  // hand-over of the second epilogue warp's two best keys, double-buffered
+constexpr size_t TQ_SMEM = (size_t)TQ_PPC * TQ_B_BYTES + (size_t)TQ_STAGES * TQ_A_BYTES + TQ_XCH_BYTES + 256;
 constexpr uint32_t TQ_IDESC = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(TQ_N >> 3) << 17) | ((uint32_t)(TQ_M >> 4) << 24);
 
 struct TqStats {            // device-resident, written by the prep kernels
@@ -163,7 +164,8 @@ pq_tc_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   extern __shared__ __align__(1024) uint8_t tq_smem[];
   uint8_t* bq = tq_smem;                                          // [TQ_PPC][32 KB] centroid blocks (two subspaces each)
   uint8_t* stages = bq + (size_t)TQ_PPC * TQ_B_BYTES;             // [TQ_STAGES][16 KB] row blocks (two subspaces each)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stages + (size_t)TQ_STAGES * TQ_A_BYTES);
+  float4* sm_x = reinterpret_cast<float4*>(stages + (size_t)TQ_STAGES * TQ_A_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sm_x) + TQ_XCH_BYTES);
   uint64_t* full = bars;                    // [TQ_STAGES]
   uint64_t* empty = bars + TQ_STAGES;       // [TQ_STAGES]
   uint64_t* tfull = bars + 2 * TQ_STAGES;   // [2]
@@ -190,7 +192,7 @@ pq_tc_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int a = 0; a < 2; a++) {
       mbar_init(tfull + a, 1);
-      mbar_init(tempty + a, 4);
+      mbar_init(tempty + a, 8);
     }
     mbar_init(bfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -249,8 +251,13 @@ pq_tc_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
     }
-  } else if (warp >= 4) {  // ===== epilogue: thread = row =====
-    const int lq = warp - 4;
+  } else if (warp >= 4) {  // ===== epilogue: thread = row, two warps per TMEM lane quarter =====
+    // Warps 4..7 (ch = 0) and 8..11 (ch = 1) reduce columns 0..127 and 128..255 of the same 32 rows; the second
+    // warp hands its two best keys over through shared memory and the first one decides.  Two warps per SM
+    // sub-partition hide the dependent min / max chains and the TMEM round trips of each other.
+    const int ew = warp - 4;
+    const int lq = ew & 3;
+    const int ch = ew >> 2;
     const float ninf = __int_as_float(0xff800000);
     const float s = tq_scale(stats);
     // |estimate - reference| <= band (in distance units), see pq.cu; in D units: D = s^2 (|x|^2 - dist) / 2
@@ -267,26 +274,26 @@ pq_tc_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         mbar_wait(tfull + a, (it >> 1) & 1);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(a * TQ_N);
-        float m1[4], m2[4];  // four independent chains: column j -> chain j & 3, slot j >> 2
+        float m1[4], m2[4];  // four independent chains: column j -> chain j & 3, slot j >> 2 (6 bits: j < 256)
 #pragma unroll
         for (int c = 0; c < 4; c++) m1[c] = m2[c] = ninf;
         uint32_t v[2][32];
-        tc_ld32(taddr, v[0]);
+        tc_ld32(taddr + (uint32_t)ch * 128, v[0]);
 #pragma unroll
-        for (int h = 0; h < 8; h++) {
+        for (int h = 0; h < 4; h++) {
           tc_wait_ld();
           tc_pin32(v[h & 1]);
-          if (h < 7) tc_ld32(taddr + (uint32_t)(h + 1) * 32, v[(h + 1) & 1]);
+          if (h < 3) tc_ld32(taddr + (uint32_t)(ch * 128 + (h + 1) * 32), v[(h + 1) & 1]);
 #pragma unroll
           for (int j = 0; j < 32; j++) {
-            const int col = h * 32 + j;
-            const float key = __uint_as_float((v[h & 1][j] & 0xffffffc0u) | (uint32_t)(col >> 2));
-            const float lo = fminf(m1[col & 3], key);
-            m1[col & 3] = fmaxf(m1[col & 3], key);
-            m2[col & 3] = fmaxf(m2[col & 3], lo);
+            const int cj = h * 32 + j;  // column within this warp's half: the chain index ignores ch (128 % 4 == 0)
+            const float key = __uint_as_float((v[h & 1][j] & 0xffffffc0u) | (uint32_t)(ch * 32 + (cj >> 2)));
+            const float lo = fminf(m1[cj & 3], key);
+            m1[cj & 3] = fmaxf(m1[cj & 3], key);
+            m2[cj & 3] = fmaxf(m2[cj & 3], lo);
           }
         }
-        // the row's two largest keys over the four chains
+        // this half's two largest keys over the four chains (the winning chain travels beside the key)
         float b1 = m1[0], b2 = m2[0];
         int bc = 0;
 #pragma unroll
@@ -297,6 +304,28 @@ pq_tc_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             bc = c;
           } else {
             b2 = fmaxf(b2, m1[c]);
+          }
+        }
+        float4* xch = sm_x + (size_t)((it & 1) * 4 + lq) * 32 + lane;  // double-buffered by step parity
+        if (ch == 1) {
+          *xch = make_float4(b1, b2, __int_as_float(bc), 0.0f);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty + a);                        // this warp is done with the accumulator
+          // hand-over to the deciding warp; one named barrier per (step parity, quarter): this warp may run one
+          // step ahead (the other accumulator), never two (tempty needs the deciding warp's arrival)
+          asm volatile("bar.arrive %0, 64;" ::"r"(8 + (it & 1) * 4 + lq) : "memory");
+          continue;
+        }
+        asm volatile("bar.sync %0, 64;" ::"r"(8 + (it & 1) * 4 + lq) : "memory");
+        {
+          const float4 o = *xch;
+          if (o.x > b1) {
+            b2 = fmaxf(b1, o.y);
+            b1 = o.x;
+            bc = __float_as_int(o.z);
+          } else {
+            b2 = fmaxf(b2, o.x);
           }
         }
         int best = (int)((__float_as_uint(b1) & 63u) * 4u) + bc;
