@@ -197,8 +197,9 @@ int64_t vs_kernel_launch_count(void);
  * kernel is set up while its predecessor runs and waits, in the kernel, for its results).
  * "pq_tensor_cores": how PQ assignment with 8-float sub-vectors nominates -- 2 (default) tcgen05 on fp16
  * hi/lo operand pairs (pq_tc.cu; needs n * M * 64 bytes of scratch, built slab by slab), 0 the FFMA kernel,
- * 1 mma.sync 3xTF32 (slower on B200, kept as a measured reference point).  Results never depend on any of
- * them. */
+ * 1 mma.sync 3xTF32 (slower on B200, kept as a measured reference point).  "pq_tc_keep_bytes" (default 16 GiB):
+ * how much of that scratch a private stream-ordered pool keeps cached between calls (0 = give everything back at
+ * the next synchronisation).  Results never depend on any of them. */
 int32_t vs_set_option(const char* name, int64_t value);
 
 /* ---- diagnostics -----------------------------------------------------------------------------------

@@ -654,6 +654,11 @@ int32_t vs_debug_adc_stats(uint32_t* out8) { return vs::debug_adc_stats(out8) ==
 
 int32_t vs_set_option(const char* name, int64_t value) {
   if (!name) return fail(VS_EINVAL, "null option name");
+  if (!strcmp(name, "pq_tc_keep_bytes")) {
+    if (value < 0) return fail(VS_EINVAL, "pq_tc_keep_bytes must be >= 0");
+    pq_tc_set_keep_bytes((unsigned long long)value);
+    return VS_OK;
+  }
   if (!strcmp(name, "pq_tensor_cores")) {
     if (value < 0 || value > 2) return fail(VS_EINVAL, "pq_tensor_cores must be 0 (FFMA), 1 (mma.sync) or 2 (tcgen05)");
     pq_set_tensor_cores((int)value);

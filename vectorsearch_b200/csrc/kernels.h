@@ -263,6 +263,7 @@ cudaError_t launch_pq_assign_tc(const PqAssignLaunch& L, int sms, cudaStream_t s
 // launch_pq_assign_tc over the same rows (the Lloyd iterations of PqTrainer.train).
 void pq_tc_scope_begin();
 void pq_tc_scope_end();
+void pq_tc_set_keep_bytes(unsigned long long bytes);  // scratch the pool keeps cached between calls
 cudaError_t launch_pq_assign(const PqAssignLaunch& L, cudaStream_t st);
 
 }  // namespace vs

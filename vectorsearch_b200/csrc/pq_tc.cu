@@ -21,6 +21,8 @@
 //     norm bounds of the error band stay on the device, nothing synchronises).
 // The kernel is bound by its epilogue (four instructions per (row, centroid)), not by the MMA.
 #include <algorithm>
+#include <atomic>
+#include <mutex>
 
 #include "kernels.h"
 #include "tc05.cuh"
@@ -388,10 +390,42 @@ pq_tc_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
-struct DevMem {
+// Scratch of the operand images comes from a private stream-ordered pool (one per device): allocation and release
+// are ordered on the caller's stream -- no device-wide synchronisation -- and up to `pq_tc_keep_bytes` stay cached
+// in the pool between calls, so the many small encode calls of an ingest path never reach the driver's allocator.
+std::mutex g_pool_mu;
+cudaMemPool_t g_pools[64] = {};
+std::atomic<unsigned long long> g_pool_keep{16ull << 30};
+
+cudaError_t tq_pool(cudaMemPool_t* out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  std::lock_guard<std::mutex> g(g_pool_mu);
+  if (!g_pools[dev]) {
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    if ((e = cudaMemPoolCreate(&g_pools[dev], &props)) != cudaSuccess) return e;
+  }
+  unsigned long long keep = g_pool_keep.load();
+  if ((e = cudaMemPoolSetAttribute(g_pools[dev], cudaMemPoolAttrReleaseThreshold, &keep)) != cudaSuccess) return e;
+  *out = g_pools[dev];
+  return cudaSuccess;
+}
+
+struct PoolMem {  // released on the stream it was allocated on unless handed over
   void* p = nullptr;
-  ~DevMem() {
-    if (p) cudaFree(p);
+  cudaStream_t st = nullptr;
+  cudaError_t alloc(size_t bytes, cudaMemPool_t pool, cudaStream_t s) {
+    st = s;
+    return cudaMallocFromPoolAsync(&p, bytes, pool, s);
+  }
+  ~PoolMem() {
+    if (p) cudaFreeAsync(p, st);
   }
 };
 
@@ -404,7 +438,8 @@ bool pq_tc_supported(const PqAssignLaunch& L) {
 
 // Operand image kept between calls: PqTrainer.train assigns the SAME rows once per Lloyd iteration, so the trainer
 // opens a scope (pq_tc_scope_begin / _end) within which the rows' image -- when it fits in one slab -- is built once
-// and only the centroid image is refreshed.  Outside a scope nothing outlives a call.
+// and only the centroid image is refreshed.  Outside a scope the scratch goes back to the pool when the call's kernels
+// have run.
 namespace {
 struct TcScope {
   bool open = false, valid = false;
@@ -412,10 +447,11 @@ struct TcScope {
   int64_t n = 0;
   int d = 0, M = 0;
   void *xop = nullptr, *cop = nullptr, *stats = nullptr;
+  cudaStream_t st = nullptr;
   void release() {
-    if (xop) cudaFree(xop);
-    if (cop) cudaFree(cop);
-    if (stats) cudaFree(stats);
+    if (xop) cudaFreeAsync(xop, st);
+    if (cop) cudaFreeAsync(cop, st);
+    if (stats) cudaFreeAsync(stats, st);
     xop = cop = stats = nullptr;
     valid = false;
   }
@@ -428,7 +464,6 @@ void pq_tc_scope_begin() {
   t_scope.open = true;
 }
 void pq_tc_scope_end() {
-  cudaDeviceSynchronize();
   t_scope.release();
   t_scope.open = false;
 }
@@ -441,25 +476,29 @@ cudaError_t launch_pq_assign_tc(const PqAssignLaunch& L, int sms, cudaStream_t s
   const int nsg = (M + TQ_SPC - 1) / TQ_SPC;
   const size_t per_row = (size_t)(M / 2) * 128;
   TcScope& sc = t_scope;
-  const bool reuse = sc.open && sc.valid && sc.X == L.X && sc.n == L.n && sc.d == L.d && sc.M == M;
+  const bool reuse = sc.open && sc.valid && sc.X == L.X && sc.n == L.n && sc.d == L.d && sc.M == M && sc.st == st;
   int64_t slab = 0;
-  DevMem xop, cop, stats;  // owners when nothing is kept
+  PoolMem xop, cop, stats;  // owners when nothing is kept
   void *p_xop, *p_cop, *p_stats;
   if (reuse) {
     slab = (L.n + TQ_M - 1) / TQ_M * TQ_M;
     p_xop = sc.xop; p_cop = sc.cop; p_stats = sc.stats;
   } else {
-    size_t free_b = 0, total_b = 0;
+    cudaMemPool_t pool;
+    if ((e = tq_pool(&pool)) != cudaSuccess) return e;
+    size_t free_b = 0, total_b = 0, cached = 0, used = 0;
     if ((e = cudaMemGetInfo(&free_b, &total_b)) != cudaSuccess) return e;
-    size_t budget = free_b / 2;
+    cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &cached);
+    cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
+    size_t budget = (free_b + (cached > used ? cached - used : 0)) / 2;  // what the pool holds idle is ours to use
     if (budget > (size_t(24) << 30)) budget = size_t(24) << 30;
     slab = (int64_t)(budget / per_row);
     slab = (slab / TQ_M) * TQ_M;
     if (slab < TQ_M) return cudaErrorMemoryAllocation;
     if (slab > L.n) slab = (L.n + TQ_M - 1) / TQ_M * TQ_M;
-    if ((e = cudaMalloc(&xop.p, (size_t)slab * per_row)) != cudaSuccess) return e;
-    if ((e = cudaMalloc(&cop.p, (size_t)(M / 2) * TQ_N * 128)) != cudaSuccess) return e;
-    if ((e = cudaMalloc(&stats.p, sizeof(TqStats))) != cudaSuccess) return e;
+    if ((e = xop.alloc((size_t)slab * per_row, pool, st)) != cudaSuccess) return e;
+    if ((e = cop.alloc((size_t)(M / 2) * TQ_N * 128, pool, st)) != cudaSuccess) return e;
+    if ((e = stats.alloc(sizeof(TqStats), pool, st)) != cudaSuccess) return e;
     p_xop = xop.p; p_cop = cop.p; p_stats = stats.p;
   }
   TqStats* d_st = static_cast<TqStats*>(p_stats);
@@ -502,14 +541,15 @@ cudaError_t launch_pq_assign_tc(const PqAssignLaunch& L, int sms, cudaStream_t s
   if (reuse) return cudaSuccess;  // everything this call touched lives until the scope ends
   if (sc.open && slab >= L.n) {   // first call of a scope and the whole image fits: keep it
     sc.release();
-    sc.X = L.X; sc.n = L.n; sc.d = L.d; sc.M = M;
+    sc.X = L.X; sc.n = L.n; sc.d = L.d; sc.M = M; sc.st = st;
     sc.xop = xop.p; sc.cop = cop.p; sc.stats = stats.p;
     xop.p = cop.p = stats.p = nullptr;
     sc.valid = true;
     return cudaSuccess;
   }
-  // the scratch is freed when this returns: wait for the kernels that read it
-  return cudaStreamSynchronize(st);
+  return cudaSuccess;  // the scratch is released in stream order behind the kernels that read it
 }
+
+void pq_tc_set_keep_bytes(unsigned long long bytes) { g_pool_keep.store(bytes); }
 
 }  // namespace vs
