@@ -341,8 +341,8 @@ def run_ours(args) -> None:
             "data": "synthetic (java.util.Random(42) nextFloat()*2-1 rows generated on device; seeded uniform queries)",
             "config": {"workload": f"C2: exact L2 brute-force top-{TOPK} over {N_ROWS}x{DIM} fp32 per GPU, query batch 1",
                        "rows_per_gpu": N_ROWS, "dim": DIM, "k": TOPK, "query_batch": 1,
-                       "parallelism": (f"row-range shards x{world}, NCCL all-gather top-k merge per query; independent queries "
-                                       "alternate between two streams") if world > 1 else "1 GPU",
+                       "parallelism": (f"row-range shards x{world}, cross-shard top-k exchange per query = {sh.exchange}; "
+                                       "independent queries alternate between two streams") if world > 1 else "1 GPU",
                        "l2_policy": "input 512 MB per step > 126 MB L2 (no flush needed)",
                        "pipelining": "independent queries alternate between two CUDA streams; the scan leaves "
                                      f"{os.environ.get('VS_SCAN_RESERVE', '16')} SMs free so that the neighbouring query's "

@@ -178,6 +178,31 @@ int32_t vs_adc_rerank_packed_dev(uint64_t h, const float* d_q, int32_t nq, int32
  * stable order -- and of those the scored ones by exact score descending, ties in approximate order; first k. */
 int32_t vs_merge_adc_rerank_packed_dev(const int64_t* d_gath, int32_t world, int32_t nq, int32_t n_cand, int32_t k,
                                        int64_t* d_ids_out, double* d_scores_out, int32_t* d_counts_out, void* stream);
+/* ---- peer exchange: the all-gather and the merge as two kernels over NVLink peer memory -----------------
+ * One process per GPU of one node.  vs_peer_create allocates this rank's communication buffer (`depth` slots of
+ * [world][slot_bytes] plus arrival flags) and returns its 64-byte cudaIpc handle; the host exchanges the handles
+ * of all ranks by any means (the coordinator uses one torch.distributed all-gather) and passes the rank-ordered
+ * [world][64] array to vs_peer_connect.  vs_exchange_merge_* then replace "collective all-gather of d_pack +
+ * vs_merge_*_packed_dev": the rank pushes its packed lists into every peer's buffer with plain stores and raises
+ * a flag there; the merge kernel waits for the `world` flags of its own buffer and reads local memory only.
+ * Results are those of the NCCL path, bit for bit.  Every rank must issue the same exchanges in the same order
+ * (as with any collective); a slot is reused every `depth` exchanges, so depth >= 2 * (streams a rank alternates
+ * its exchanges between) -- the coordinator uses 8 for 2 streams.  A peer that never arrives traps the waiting
+ * kernel after 20 s instead of hanging the GPU. */
+#define VS_PEER_HANDLE_BYTES 64
+int32_t vs_peer_create(int32_t rank, int32_t world, int64_t slot_bytes, int32_t depth, uint64_t* comm_out,
+                       uint8_t* handle_out /* [VS_PEER_HANDLE_BYTES] */);
+int32_t vs_peer_connect(uint64_t comm, const uint8_t* handles /* [world][VS_PEER_HANDLE_BYTES] */);
+/* One process driving several GPUs (a JVM with one context per device; the tests with several communicators on one
+ * GPU): no IPC -- pass the base addresses (vs_peer_base) of all ranks' buffers, peer access already enabled. */
+int32_t vs_peer_base(uint64_t comm, uint64_t* base_out);
+int32_t vs_peer_connect_ptrs(uint64_t comm, const uint64_t* bases /* [world] */);
+int32_t vs_peer_destroy(uint64_t comm);
+int32_t vs_exchange_merge_packed_dev(uint64_t comm, const int64_t* d_pack, int32_t nq, int32_t k, int32_t descending,
+                                     int64_t* d_ids_out, double* d_scores_out, int32_t* d_counts_out, void* stream);
+int32_t vs_exchange_merge_adc_rerank_packed_dev(uint64_t comm, const int64_t* d_pack, int32_t nq, int32_t n_cand,
+                                                int32_t k, int64_t* d_ids_out, double* d_scores_out,
+                                                int32_t* d_counts_out, void* stream);
 int32_t vs_merge_topk_dev(const int64_t* d_ids, const double* d_scores, int64_t total, int32_t k,
                           int64_t* d_ids_out, double* d_scores_out, int32_t* d_count_out, void* stream);
 /* number of kernels this library has launched so far in this process (for gpu_launches) */

@@ -410,6 +410,72 @@ def test_adc_rerank_across_shards(vs, oracle, shards, metric):
             seg.free()
 
 
+@pytest.mark.parametrize("world,nq,k", [(2, 1, 10), (3, 5, 7), (8, 64, 10), (4, 3, 100)])
+def test_peer_exchange_merge_equals_gather_then_merge(vs, world, nq, k):
+    """The peer-memory exchange (push into every rank's buffer + flag wait inside the merge kernel) must give what
+    "all-gather, then vs_merge_packed_dev" gives.  Ranks are emulated by `world` communicators on this GPU, each
+    on its own stream, connected by address; more rounds than the ring is deep, so every slot is reused."""
+    import ctypes as C
+
+    import torch
+
+    from vectorsearch_b200 import _lib as L
+
+    lib = vs.load()
+    depth, rounds = 4, 11
+    comms, bases = [], (C.c_uint64 * world)()
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    rng = np.random.default_rng(world * 1000 + nq)
+    try:
+        for r in range(world):
+            comm, hd = C.c_uint64(0), (C.c_uint8 * 64)()
+            L.check(lib.vs_peer_create(r, world, 1 << 20, depth, C.byref(comm), hd))
+            comms.append(comm.value)
+            b = C.c_uint64(0)
+            L.check(lib.vs_peer_base(comm.value, C.byref(b)))
+            bases[r] = b.value
+        for r in range(world):
+            L.check(lib.vs_peer_connect_ptrs(comms[r], bases))
+        for rnd in range(rounds):
+            # per-rank packed lists: ids (some empty slots = -1), scores with ties across ranks, NaN and -0.0
+            ids = rng.integers(0, 1 << 40, size=(world, nq, k)).astype(np.int64)
+            sc = rng.integers(-3, 4, size=(world, nq, k)).astype(np.float64) / 2
+            sc[rng.random(sc.shape) < 0.05] = np.nan
+            sc[rng.random(sc.shape) < 0.05] = -0.0
+            sc = -np.sort(-sc, axis=2)          # each rank's list is sorted (as a scan's is); NaN placement is free
+            ids[rng.random(ids.shape) < 0.1] = -1
+            pack = np.concatenate([ids, sc.view(np.int64)], axis=2)  # [world][nq][2k]
+            d_pack = torch.from_numpy(pack).cuda()
+            want_i = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+            want_s = torch.empty((nq, k), dtype=torch.float64, device="cuda")
+            want_c = torch.empty((nq,), dtype=torch.int32, device="cuda")
+            st0 = torch.cuda.current_stream().cuda_stream
+            L.check(lib.vs_merge_packed_dev(d_pack.data_ptr(), world, nq, k, 1, want_i.data_ptr(), want_s.data_ptr(),
+                                            want_c.data_ptr(), st0))
+            torch.cuda.synchronize()
+            outs = []
+            for r in range(world):
+                oi = torch.full((nq, k), -7, dtype=torch.int64, device="cuda")
+                os_ = torch.zeros((nq, k), dtype=torch.float64, device="cuda")
+                oc = torch.zeros((nq,), dtype=torch.int32, device="cuda")
+                outs.append((oi, os_, oc))
+            torch.cuda.synchronize()
+            for r in range(world):               # rank r's merge spins until the later-launched ranks have published
+                oi, os_, oc = outs[r]
+                L.check(lib.vs_exchange_merge_packed_dev(comms[r], d_pack[r].data_ptr(), nq, k, 1, oi.data_ptr(),
+                                                         os_.data_ptr(), oc.data_ptr(), streams[r].cuda_stream))
+            torch.cuda.synchronize()
+            for r in range(world):
+                oi, os_, oc = outs[r]
+                assert torch.equal(oc, want_c), (rnd, r)
+                assert torch.equal(oi, want_i), (rnd, r)
+                assert torch.equal(os_.view(torch.int64), want_s.view(torch.int64)), (rnd, r)
+    finally:
+        torch.cuda.synchronize()
+        for c in comms:
+            lib.vs_peer_destroy(c)
+
+
 def _quantisation_error(oracle, cent, rows):
     codes = oracle.pq_encode_batch(cent, rows)
     M, K, sd = cent.shape

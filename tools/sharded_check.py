@@ -29,6 +29,7 @@ qs[0] = rows[17]
 lo, hi = shard_range(n, rank, world)
 seg = vs.Segment.upload(rows[lo:hi], id_base=lo)
 sh = ShardedSegment(seg, rank, world)
+print(f"[rank {rank}] cross-shard exchange: {sh.exchange}", flush=True)
 ok = True
 # --- sharded PQ training (all-reduce of sums and counts per iteration)
 want = orc.pq_train(rows, d, M, K, 5, 42)

@@ -66,6 +66,13 @@ SIGNATURES = {
     "vs_merge_topk_dev": (i32, [vp, vp, i64, i32, vp, vp, vp, vp]),
     "vs_adc_rerank_packed_dev": (i32, [u64, vp, i32, i32, i32, i32, vp, vp]),
     "vs_merge_adc_rerank_packed_dev": (i32, [vp, i32, i32, i32, i32, vp, vp, vp, vp]),
+    "vs_peer_create": (i32, [i32, i32, i64, i32, C.POINTER(u64), vp]),
+    "vs_peer_connect": (i32, [u64, vp]),
+    "vs_peer_base": (i32, [u64, C.POINTER(u64)]),
+    "vs_peer_connect_ptrs": (i32, [u64, C.POINTER(u64)]),
+    "vs_peer_destroy": (i32, [u64]),
+    "vs_exchange_merge_packed_dev": (i32, [u64, vp, i32, i32, i32, vp, vp, vp, vp]),
+    "vs_exchange_merge_adc_rerank_packed_dev": (i32, [u64, vp, i32, i32, i32, vp, vp, vp, vp]),
     "vs_kernel_launch_count": (i64, []),
     "vs_set_option": (i32, [C.c_char_p, i64]),
     "vs_debug_batch_groupmins": (i32, [u64, f32p, i32, i32, f32p, i64, i64p, i32p, f64p]),

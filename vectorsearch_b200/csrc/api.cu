@@ -1521,6 +1521,177 @@ int32_t vs_merge_packed_dev(const int64_t* d_gath, int32_t world, int32_t nq, in
   return VS_OK;
 }
 
+// ---- peer exchange: all-gather + merge over NVLink peer memory (rank.cu) ------------------------------------
+namespace {
+constexpr uint64_t PEER_MAGIC = 0x7673706565723031ull;  // "vspeer01"
+struct PeerComm {
+  uint64_t magic = PEER_MAGIC;
+  int rank = 0, world = 1, depth = 0, device = 0;
+  size_t slot_bytes = 0, flags_off = 0, ticket_off = 0, total = 0;
+  unsigned char* bases[VS_PEER_MAX_WORLD] = {};
+  bool connected = false, by_ptr = false;
+  std::atomic<uint64_t> seq{0};
+};
+PeerComm* peer_lookup(uint64_t comm) {
+  PeerComm* pc = reinterpret_cast<PeerComm*>(static_cast<uintptr_t>(comm));
+  return (pc && pc->magic == PEER_MAGIC) ? pc : nullptr;
+}
+struct PeerSlot {
+  size_t data_off, flag_off;
+  const int64_t* gath;
+  const unsigned long long* flags;
+  unsigned int* ticket;
+  uint64_t seq;
+};
+// Every rank issues the same exchanges in the same order (as with any collective): the sequence number picks the slot.
+PeerSlot peer_next(PeerComm* pc, size_t payload) {
+  PeerSlot ps;
+  ps.seq = pc->seq.fetch_add(1) + 1;
+  const size_t slot = (size_t)((ps.seq - 1) % (uint64_t)pc->depth);
+  unsigned char* own = pc->bases[pc->rank];
+  const size_t slot_base = slot * (size_t)pc->world * pc->slot_bytes;
+  ps.data_off = slot_base + (size_t)pc->rank * payload;
+  ps.flag_off = pc->flags_off + slot * VS_PEER_MAX_WORLD * 8;
+  ps.gath = reinterpret_cast<const int64_t*>(own + slot_base);
+  ps.flags = reinterpret_cast<const unsigned long long*>(own + ps.flag_off);
+  ps.ticket = reinterpret_cast<unsigned int*>(own + pc->ticket_off) + slot;
+  return ps;
+}
+}  // namespace
+
+int32_t vs_peer_create(int32_t rank, int32_t world, int64_t slot_bytes, int32_t depth, uint64_t* comm_out,
+                       uint8_t* handle_out) {
+  if (!comm_out || !handle_out) return fail(VS_EINVAL, "null pointer");
+  if (world < 1 || world > VS_PEER_MAX_WORLD || rank < 0 || rank >= world)
+    return fail(VS_EINVAL, "rank / world out of range (world <= %d)", VS_PEER_MAX_WORLD);
+  if (slot_bytes < 16 || (slot_bytes & 15) != 0 || depth < 2 || depth > 64)
+    return fail(VS_EINVAL, "slot_bytes must be a positive multiple of 16 and depth in 2..64");
+  static_assert(sizeof(cudaIpcMemHandle_t) == VS_PEER_HANDLE_BYTES, "handle size");
+  ThreadCtx* c;
+  RET(ctx_bind(&c));
+  PeerComm* pc = new PeerComm();
+  pc->rank = rank;
+  pc->world = world;
+  pc->depth = depth;
+  pc->slot_bytes = (size_t)slot_bytes;
+  pc->flags_off = (size_t)depth * world * pc->slot_bytes;
+  pc->ticket_off = pc->flags_off + (size_t)depth * VS_PEER_MAX_WORLD * 8;
+  pc->total = pc->ticket_off + (size_t)depth * 4 + 256;
+  cudaGetDevice(&pc->device);
+  cudaError_t e = cudaMalloc(&pc->bases[rank], pc->total);  // plain cudaMalloc: cudaIpc cannot export pool memory
+  if (e == cudaSuccess) e = cudaMemset(pc->bases[rank], 0, pc->total);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  cudaIpcMemHandle_t hd;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&hd, pc->bases[rank]);
+  if (e != cudaSuccess) {
+    if (pc->bases[rank]) cudaFree(pc->bases[rank]);
+    delete pc;
+    return cuda_fail(e, "peer buffer");
+  }
+  memcpy(handle_out, &hd, sizeof(hd));
+  *comm_out = static_cast<uint64_t>(reinterpret_cast<uintptr_t>(pc));
+  return VS_OK;
+}
+
+int32_t vs_peer_connect(uint64_t comm, const uint8_t* handles) {
+  PeerComm* pc = peer_lookup(comm);
+  if (!pc || !handles) return fail(VS_EINVAL, "bad peer communicator");
+  if (pc->connected) return fail(VS_ESTATE, "peer communicator is already connected");
+  ThreadCtx* c;
+  RET(ctx_bind(&c));
+  for (int p = 0; p < pc->world; p++) {
+    if (p == pc->rank) continue;
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, handles + (size_t)p * VS_PEER_HANDLE_BYTES, sizeof(hd));
+    void* ptr = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaIpcOpenMemHandle (peer buffer; needs P2P access between the GPUs)");
+    pc->bases[p] = static_cast<unsigned char*>(ptr);
+  }
+  pc->connected = true;
+  return VS_OK;
+}
+
+// One process driving several GPUs (or several communicators on one GPU, as the tests do): no IPC needed, the
+// caller passes the base addresses (vs_peer_base) of all ranks' buffers.  With different devices the caller has
+// enabled peer access between them (cudaDeviceEnablePeerAccess).
+int32_t vs_peer_base(uint64_t comm, uint64_t* base_out) {
+  PeerComm* pc = peer_lookup(comm);
+  if (!pc || !base_out) return fail(VS_EINVAL, "bad peer communicator");
+  *base_out = static_cast<uint64_t>(reinterpret_cast<uintptr_t>(pc->bases[pc->rank]));
+  return VS_OK;
+}
+
+int32_t vs_peer_connect_ptrs(uint64_t comm, const uint64_t* bases) {
+  PeerComm* pc = peer_lookup(comm);
+  if (!pc || !bases) return fail(VS_EINVAL, "bad peer communicator");
+  if (pc->connected) return fail(VS_ESTATE, "peer communicator is already connected");
+  for (int p = 0; p < pc->world; p++) {
+    if (p == pc->rank) continue;
+    if (!bases[p]) return fail(VS_EINVAL, "null base address for rank %d", p);
+    pc->bases[p] = reinterpret_cast<unsigned char*>(static_cast<uintptr_t>(bases[p]));
+  }
+  pc->connected = true;
+  pc->by_ptr = true;
+  return VS_OK;
+}
+
+int32_t vs_peer_destroy(uint64_t comm) {
+  PeerComm* pc = peer_lookup(comm);
+  if (!pc) return fail(VS_EINVAL, "bad peer communicator");
+  cudaDeviceSynchronize();
+  for (int p = 0; p < pc->world; p++) {
+    if (!pc->bases[p]) continue;
+    if (p == pc->rank) cudaFree(pc->bases[p]);
+    else if (!pc->by_ptr) cudaIpcCloseMemHandle(pc->bases[p]);
+  }
+  pc->magic = 0;
+  delete pc;
+  return VS_OK;
+}
+
+int32_t vs_exchange_merge_packed_dev(uint64_t comm, const int64_t* d_pack, int32_t nq, int32_t k, int32_t descending,
+                                     int64_t* d_ids_out, double* d_scores_out, int32_t* d_counts_out, void* stream) {
+  PeerComm* pc = peer_lookup(comm);
+  if (!pc || !pc->connected) return fail(VS_ESTATE, "peer communicator is not connected");
+  if (!d_pack || !d_ids_out || !d_scores_out || !d_counts_out) return fail(VS_EINVAL, "null pointer");
+  if (nq <= 0) return fail(VS_EINVAL, "nq must be positive");
+  if (k <= 0 || k > TOPK_MAX_K) return fail(VS_EINVAL, "k must be in 1..%d", TOPK_MAX_K);
+  const size_t payload = (size_t)nq * 2 * k * 8;
+  if (payload > pc->slot_bytes) return fail(VS_EINVAL, "packed lists (%zu bytes) exceed the communicator's slot", payload);
+  ThreadCtx* c;
+  RET(ctx_bind(&c));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const PeerSlot ps = peer_next(pc, payload);
+  CK(launch_peer_publish(pc->bases, pc->world, pc->rank, d_pack, payload, ps.data_off, ps.flag_off, ps.seq, ps.ticket, st),
+     "peer publish launch");
+  CK(launch_merge_packed(ps.gath, pc->world, nq, k, descending != 0, d_ids_out, d_scores_out, d_counts_out, st, ps.flags,
+                         ps.seq), "merge launch");
+  return VS_OK;
+}
+
+int32_t vs_exchange_merge_adc_rerank_packed_dev(uint64_t comm, const int64_t* d_pack, int32_t nq, int32_t n_cand, int32_t k,
+                                                int64_t* d_ids_out, double* d_scores_out, int32_t* d_counts_out,
+                                                void* stream) {
+  PeerComm* pc = peer_lookup(comm);
+  if (!pc || !pc->connected) return fail(VS_ESTATE, "peer communicator is not connected");
+  if (!d_pack || !d_ids_out || !d_scores_out || !d_counts_out) return fail(VS_EINVAL, "null pointer");
+  if (nq <= 0 || n_cand <= 0 || k <= 0 || k > n_cand) return fail(VS_EINVAL, "need nq > 0 and 0 < k <= n_cand");
+  if (k > TOPK_MAX_K) return fail(VS_EINVAL, "k must be in 1..%d", TOPK_MAX_K);
+  if ((int64_t)pc->world * n_cand > 8192) return fail(VS_EINVAL, "world * n_cand must be <= 8192");
+  const size_t payload = (size_t)nq * 4 * n_cand * 8;
+  if (payload > pc->slot_bytes) return fail(VS_EINVAL, "packed candidates (%zu bytes) exceed the communicator's slot", payload);
+  ThreadCtx* c;
+  RET(ctx_bind(&c));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const PeerSlot ps = peer_next(pc, payload);
+  CK(launch_peer_publish(pc->bases, pc->world, pc->rank, d_pack, payload, ps.data_off, ps.flag_off, ps.seq, ps.ticket, st),
+     "peer publish launch");
+  CK(launch_merge_adc_rerank(ps.gath, pc->world, nq, n_cand, k, d_ids_out, d_scores_out, d_counts_out, st, ps.flags, ps.seq),
+     "merge launch");
+  return VS_OK;
+}
+
 // ADC top n_cand of this shard with the exact score of every candidate, packed for the cross-shard merge
 int32_t vs_adc_rerank_packed_dev(uint64_t h, const float* d_q, int32_t nq, int32_t n_cand, int32_t metric,
                                  int32_t normalize_on_read, int64_t* d_pack, void* stream) {

@@ -149,15 +149,26 @@ cudaError_t launch_rank(const RankLaunch& L, cudaStream_t st);
 // cross-shard ADC + re-rank: per query int64[4][nc] = ids | approx bits | exact score bits | state
 cudaError_t launch_score_pack(const RankLaunch& L, const double* cand_approx, const int32_t* cand_counts, int64_t* pack,
                               cudaStream_t st);
+// wait_flags != nullptr: the gathered lists arrive through the peer exchange; the kernel first waits until
+// wait_flags[0..w) have reached wait_seq (launch_peer_publish of every rank)
 cudaError_t launch_merge_adc_rerank(const int64_t* gath, int w, int nq, int nc, int k, int64_t* ids_out,
-                                    double* scores_out, int32_t* counts_out, cudaStream_t st);
+                                    double* scores_out, int32_t* counts_out, cudaStream_t st,
+                                    const unsigned long long* wait_flags = nullptr, unsigned long long wait_seq = 0);
+// Peer exchange (rank.cu): copy `bytes` of payload to bases[p] + data_off of every peer p, then set
+// flag word `rank` at bases[p] + flag_off to seq.  ticket: one zeroed word of this rank per concurrent exchange.
+constexpr int VS_PEER_MAX_WORLD = 16;
+constexpr unsigned long long VS_PEER_TIMEOUT_NS = 20ull * 1000 * 1000 * 1000;
+cudaError_t launch_peer_publish(unsigned char* const* bases, int w, int rank, const void* payload, size_t bytes,
+                                size_t data_off, size_t flag_off, unsigned long long seq, unsigned int* ticket,
+                                cudaStream_t st);
 // stable sort by score descending of `total` (id, score) pairs, first k
 cudaError_t launch_merge(const int64_t* ids, const double* scores, int64_t total, int k,
                          int64_t* ids_out, double* scores_out, int32_t* count_out, cudaStream_t st);
 // gathered [w][nq][2k] packed lists (k ids then k score bit patterns; id < 0 = empty slot):
 // per query, concatenate in rank order, stable sort (descending scores or ascending distances), first k
 cudaError_t launch_merge_packed(const int64_t* gath, int w, int nq, int k, bool descending,
-                                int64_t* ids_out, double* scores_out, int32_t* counts_out, cudaStream_t st);
+                                int64_t* ids_out, double* scores_out, int32_t* counts_out, cudaStream_t st,
+                                const unsigned long long* wait_flags = nullptr, unsigned long long wait_seq = 0);
 
 // ---- misc.cu ----------------------------------------------------------------------------------
 // element e of the output = draw (first + e) of new java.util.Random(seed); kind 0: nextFloat()*2f-1f,

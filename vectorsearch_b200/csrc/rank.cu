@@ -120,11 +120,71 @@ merge_kernel(const int64_t* __restrict__ ids, const double* __restrict__ scores,
   if (threadIdx.x == 0) *count_out = s_found;
 }
 
+// ---- cross-shard exchange over NVLink peer memory ----------------------------------------------------
+// Every rank owns a communication buffer that all peers have mapped (cudaIpc): `depth` slots of [world][slot_bytes]
+// payload plus one arrival flag per (slot, source rank).  A rank PUSHES its packed result into slot s of every
+// peer with plain stores (posted writes over NVLink), fences, and raises its flag there to the exchange's sequence
+// number; the merge kernel of each rank waits for the `world` flags of ITS OWN buffer and reads local memory only.
+// No rank ever waits inside the publishing kernel, so nothing depends on how CTAs of different GPUs are scheduled.
+struct PeerBases {
+  unsigned char* base[VS_PEER_MAX_WORLD];
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// Block-wide: returns once flags[0..w) have all reached seq.  A peer that never arrives (a dead process) traps
+// after VS_PEER_TIMEOUT_NS instead of hanging the GPU: the error surfaces at the caller's next synchronisation.
+__device__ __forceinline__ void peer_wait(const unsigned long long* flags, int w, unsigned long long seq) {
+  if (flags == nullptr) return;
+  if ((int)threadIdx.x < w) {
+    const unsigned long long t0 = global_timer_ns();
+    while (ld_acquire_sys(flags + threadIdx.x) < seq) {
+      __nanosleep(64);
+      if (global_timer_ns() - t0 > VS_PEER_TIMEOUT_NS) __trap();
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(1024)
+peer_publish_kernel(PeerBases peers, int w, int rank, const uint4* payload, size_t n16, size_t data_off, size_t flag_off,
+                    unsigned long long seq, unsigned int* ticket) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+    const uint4 v = payload[i];
+    for (int p = 0; p < w; p++) reinterpret_cast<uint4*>(peers.base[p] + data_off)[i] = v;
+  }
+  __threadfence_system();
+  __shared__ int s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (s_last) {  // every CTA's stores are fenced: raise this rank's flag at every peer
+    __threadfence_system();
+    if ((int)threadIdx.x < w)
+      st_release_sys(reinterpret_cast<unsigned long long*>(peers.base[threadIdx.x] + flag_off) + rank, seq);
+    if (threadIdx.x == 0) *ticket = 0u;
+  }
+}
+
 __global__ void __launch_bounds__(RANK_THREADS)
-merge_packed_kernel(const int64_t* __restrict__ gath, int w, int nq, int k, int kp, int descending,
+merge_packed_kernel(const int64_t* gath, int w, int nq, int k, int kp, int descending,
                     int64_t* __restrict__ ids_out, double* __restrict__ scores_out,
-                    int32_t* __restrict__ counts_out) {
+                    int32_t* __restrict__ counts_out, const unsigned long long* wait_flags, unsigned long long wait_seq) {
   extern __shared__ __align__(128) ulonglong2 smem[];
+  peer_wait(wait_flags, w, wait_seq);  // peer exchange: the gathered lists arrive in this rank's own buffer
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int nw = blockDim.x >> 5;
@@ -239,9 +299,11 @@ cudaError_t launch_score_pack(const RankLaunch& L, const double* cand_approx, co
 }
 
 __global__ void __launch_bounds__(1024)
-merge_adc_rerank_kernel(const int64_t* __restrict__ gath, int w, int nq, int nc, int np, int np2, int k,
-                        int64_t* __restrict__ ids_out, double* __restrict__ scores_out, int32_t* __restrict__ counts_out) {
+merge_adc_rerank_kernel(const int64_t* gath, int w, int nq, int nc, int np, int np2, int k,
+                        int64_t* __restrict__ ids_out, double* __restrict__ scores_out, int32_t* __restrict__ counts_out,
+                        const unsigned long long* wait_flags, unsigned long long wait_seq) {
   extern __shared__ __align__(16) ulonglong2 skey[];  // [np] approximate order, then [np2] exact order
+  peer_wait(wait_flags, w, wait_seq);
   ulonglong2* skey2 = skey + np;
   const int qi = blockIdx.x;
   const int total = w * nc;
@@ -287,8 +349,25 @@ merge_adc_rerank_kernel(const int64_t* __restrict__ gath, int w, int nq, int nc,
   if (threadIdx.x == 0) counts_out[qi] = s_found;
 }
 
+cudaError_t launch_peer_publish(unsigned char* const* bases, int w, int rank, const void* payload, size_t bytes,
+                                size_t data_off, size_t flag_off, unsigned long long seq, unsigned int* ticket,
+                                cudaStream_t st) {
+  if (w < 1 || w > VS_PEER_MAX_WORLD || (bytes & 15) != 0 || (data_off & 15) != 0) return cudaErrorInvalidValue;
+  PeerBases pb;
+  for (int p = 0; p < VS_PEER_MAX_WORLD; p++) pb.base[p] = p < w ? bases[p] : nullptr;
+  const size_t n16 = bytes / 16;
+  const int threads = n16 >= 1024 ? 1024 : (n16 > 32 ? (int)((n16 + 31) / 32 * 32) : 32);
+  int ctas = (int)((n16 * (size_t)w + 16383) / 16384);  // about 16 stores per thread
+  ctas = ctas < 1 ? 1 : (ctas > 16 ? 16 : ctas);
+  peer_publish_kernel<<<ctas, threads < w ? 32 : threads, 0, st>>>(pb, w, rank, static_cast<const uint4*>(payload), n16, data_off,
+                                                                   flag_off, seq, ticket);
+  count_launch();
+  return cudaGetLastError();
+}
+
 cudaError_t launch_merge_adc_rerank(const int64_t* gath, int w, int nq, int nc, int k, int64_t* ids_out,
-                                    double* scores_out, int32_t* counts_out, cudaStream_t st) {
+                                    double* scores_out, int32_t* counts_out, cudaStream_t st,
+                                    const unsigned long long* wait_flags, unsigned long long wait_seq) {
   if ((int64_t)w * nc > RANK_MAX_CAND) return cudaErrorInvalidValue;
   int np = 2, np2 = 2;
   while (np < w * nc) np <<= 1;
@@ -301,20 +380,23 @@ cudaError_t launch_merge_adc_rerank(const int64_t* gath, int w, int nq, int nc, 
   if (smem > (size_t)(RANK_MAX_CAND + TOPK_MAX_K) * 16) return cudaErrorInvalidValue;
   int threads = RANK_THREADS;
   while (threads < 1024 && threads < np / 2) threads <<= 1;
-  merge_adc_rerank_kernel<<<nq, threads, smem, st>>>(gath, w, nq, nc, np, np2, k, ids_out, scores_out, counts_out);
+  merge_adc_rerank_kernel<<<nq, threads, smem, st>>>(gath, w, nq, nc, np, np2, k, ids_out, scores_out, counts_out, wait_flags,
+                                                     wait_seq);
   count_launch();
   return cudaGetLastError();
 }
 
 cudaError_t launch_merge_packed(const int64_t* gath, int w, int nq, int k, bool descending,
-                                int64_t* ids_out, double* scores_out, int32_t* counts_out, cudaStream_t st) {
+                                int64_t* ids_out, double* scores_out, int32_t* counts_out, cudaStream_t st,
+                                const unsigned long long* wait_flags, unsigned long long wait_seq) {
   const int kp = topk_pad(k);
   const size_t smem = (size_t)(RANK_THREADS / 32) * topk_warp_smem(kp);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(merge_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  merge_packed_kernel<<<nq, RANK_THREADS, smem, st>>>(gath, w, nq, k, kp, descending ? 1 : 0, ids_out, scores_out, counts_out);
+  merge_packed_kernel<<<nq, RANK_THREADS, smem, st>>>(gath, w, nq, k, kp, descending ? 1 : 0, ids_out, scores_out, counts_out,
+                                                      wait_flags, wait_seq);
   count_launch();
   return cudaGetLastError();
 }

@@ -11,6 +11,10 @@ Everything numeric runs in libvsgpu; torch only carries device buffers, streams 
 """
 from __future__ import annotations
 
+import ctypes as C
+import os
+import warnings
+
 import numpy as np
 
 from . import _lib as L
@@ -98,10 +102,17 @@ def merge_adc_rerank_host(packs: np.ndarray, k: int):
     return (np.array([e[2] for _, e in top], np.int64), np.array([e[3] for _, e in top], np.float64))
 
 
+def PEER_DEPTH_OK(slots: int, depth: int) -> bool:
+    return depth >= 2 * (max(1, slots) + 1)
+
+
 class ShardedSegment:
     """One rank's row range of a corpus + the collective merge (torch.distributed)."""
 
-    def __init__(self, segment, rank: int, world: int, group=None, slots: int = 2):
+    PEER_SLOT_BYTES = 4 << 20  # largest packed result one exchange may carry through the peer buffers
+    PEER_DEPTH = 8             # slots in flight: >= 2 x the streams exchanges alternate between (slots + current)
+
+    def __init__(self, segment, rank: int, world: int, group=None, slots: int = 2, peer: bool | None = None):
         import torch
         import torch.distributed as dist
 
@@ -110,11 +121,61 @@ class ShardedSegment:
         self.lib = L.load()
         self.dev = torch.device("cuda", torch.cuda.current_device())
         self._bufs = {}
+        # Cross-shard exchange: libvsgpu's own two kernels over NVLink peer memory (each rank pushes its packed
+        # lists into every peer's buffer; the merge waits on arrival flags) when the ranks are processes of one
+        # box, else one NCCL all-gather + merge.  Same results either way.
+        self._comm = None
+        self.exchange = "none" if world == 1 else "nccl all-gather"
+        if peer is None:
+            peer = os.environ.get("VS_PEER", "1") != "0"
+        if (world > 1 and peer and world <= 16 and PEER_DEPTH_OK(slots, self.PEER_DEPTH) and dist.is_available()
+                and dist.is_initialized() and dist.get_backend(group) == "nccl"):
+            self._peer_setup()
         # query batches are independent: consecutive ones alternate between `slots` streams (each with its
         # own buffers; libvsgpu keeps one scratch set per stream), so the latency of one batch's all-gather
         # and merge hides behind the next batch's scan
         self._streams = [torch.cuda.Stream(device=self.dev) for _ in range(max(1, slots))]
         self._next = 0
+
+    def _peer_setup(self):
+        """Create this rank's peer buffer, trade the cudaIpc handles with ONE all-gather, map the peers'."""
+        t = self.torch
+        comm = C.c_uint64(0)
+        handle = (C.c_uint8 * 64)()
+        try:
+            check(self.lib.vs_peer_create(self.rank, self.world, self.PEER_SLOT_BYTES, self.PEER_DEPTH, C.byref(comm), handle))
+            ok = 1
+        except Exception as e:  # noqa: BLE001 -- the NCCL path stays available
+            warnings.warn(f"peer exchange unavailable on rank {self.rank} ({e}); using the NCCL all-gather")
+            ok = 0
+        mine = t.tensor([ok] + list(handle), dtype=t.uint8, device=self.dev)
+        allh = t.empty((self.world, 65), dtype=t.uint8, device=self.dev)
+        self.dist.all_gather_into_tensor(allh.view(-1), mine, group=self.group)
+        allh = allh.cpu().numpy()
+        agreed = bool(allh[:, 0].all())
+        if agreed:
+            try:
+                buf = np.ascontiguousarray(allh[:, 1:]).tobytes()
+                check(self.lib.vs_peer_connect(comm.value, buf))
+            except Exception as e:  # noqa: BLE001
+                warnings.warn(f"peer exchange unavailable on rank {self.rank} ({e}); using the NCCL all-gather")
+                agreed = False
+        # every rank must take the same path: agree once more
+        flag = t.tensor([1 if agreed else 0], dtype=t.int32, device=self.dev)
+        self.dist.all_reduce(flag, op=self.dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 1:
+            self._comm = comm.value
+            self.exchange = "peer-memory push + flag wait (libvsgpu kernels over NVLink)"
+        elif ok:
+            self.lib.vs_peer_destroy(comm.value)
+
+    def close(self):
+        """Release the peer buffers (collective: peers may still be writing into this rank's buffer)."""
+        if self._comm is not None:
+            self.torch.cuda.synchronize()
+            self.dist.barrier(group=self.group)
+            self.lib.vs_peer_destroy(self._comm)
+            self._comm = None
 
     def _buffers(self, nq: int, k: int, slot: int = -1):
         key = (nq, k, slot)
@@ -155,6 +216,10 @@ class ShardedSegment:
         st = t.cuda.current_stream().cuda_stream
         check(self.lib.vs_bruteforce_topk_packed_dev(self.seg.handle, d_q.data_ptr(), nq, k, metric,
                                                      b["pack"].data_ptr(), b["cn"].data_ptr(), st))
+        if self._comm is not None and nq * 2 * k * 8 <= self.PEER_SLOT_BYTES:
+            check(self.lib.vs_exchange_merge_packed_dev(self._comm, b["pack"].data_ptr(), nq, k, 1, b["out_i"].data_ptr(),
+                                                        b["out_s"].data_ptr(), b["out_c"].data_ptr(), st))
+            return b["out_i"], b["out_s"], b["out_c"]
         if self.world == 1:
             gath = b["pack"]
         else:
@@ -181,6 +246,11 @@ class ShardedSegment:
         st = t.cuda.current_stream().cuda_stream
         check(self.lib.vs_adc_rerank_packed_dev(self.seg.handle, d_q.data_ptr(), nq, n_cand, metric, 0,
                                                 b["pack"].data_ptr(), st))
+        if self._comm is not None and nq * 4 * n_cand * 8 <= self.PEER_SLOT_BYTES:
+            check(self.lib.vs_exchange_merge_adc_rerank_packed_dev(self._comm, b["pack"].data_ptr(), nq, n_cand, k,
+                                                                   b["out_i"].data_ptr(), b["out_s"].data_ptr(),
+                                                                   b["out_c"].data_ptr(), st))
+            return b["out_i"], b["out_s"], b["out_c"]
         if self.world == 1:
             gath = b["pack"]
         else:
