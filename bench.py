@@ -249,7 +249,11 @@ def run_ours(args) -> None:
     slots = [dict(stream=torch.cuda.Stream(device=dev), ids=torch.empty((1, TOPK), dtype=torch.int64, device=dev),
                   sc=torch.empty((1, TOPK), dtype=torch.float64, device=dev), cn=torch.empty((1,), dtype=torch.int32, device=dev))
              for _ in range(2)]
-    vs.set_option("scan_reserve_sms", int(os.environ.get("VS_SCAN_RESERVE", "16")))
+    # SMs the persistent scan leaves to the neighbouring stream: 4 are enough for the prologue / merge of the other
+    # query and for the peer exchange's two small kernels; an NCCL all-gather needs room for its own CTAs
+    reserve_default = "16" if (world > 1 and "peer" not in sh.exchange) else "4"
+    reserve_sms = int(os.environ.get("VS_SCAN_RESERVE", reserve_default))
+    vs.set_option("scan_reserve_sms", reserve_sms)
 
     def step_dev(i: int):
         if world == 1:
@@ -345,8 +349,8 @@ def run_ours(args) -> None:
                                        "independent queries alternate between two streams") if world > 1 else "1 GPU",
                        "l2_policy": "input 512 MB per step > 126 MB L2 (no flush needed)",
                        "pipelining": "independent queries alternate between two CUDA streams; the scan leaves "
-                                     f"{os.environ.get('VS_SCAN_RESERVE', '16')} SMs free so that the neighbouring query's "
-                                     "prologue / merge (and the all-gather's CTAs at N > 1) run beside it"},
+                                     f"{reserve_sms} SMs free so that the neighbouring query's "
+                                     "prologue / merge (and the cross-shard exchange at N > 1) run beside it"},
             "qps": 1e3 / ms_per_step,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": profiled_traffic("r1_c2_scan_full.txt"),

@@ -301,15 +301,35 @@ class ShardedSegment:
         check(rc)
         return cent
 
+    def _host_buffers(self, nq: int, k: int, d: int):
+        key = ("host", nq, k, d)
+        if key not in self._bufs:
+            t, dev = self.torch, self.dev
+            b = dict(q=t.empty((nq, d), dtype=t.float32).pin_memory(), dq=t.empty((nq, d), dtype=t.float32, device=dev),
+                     ids=t.empty((nq, k), dtype=t.int64).pin_memory(), sc=t.empty((nq, k), dtype=t.float64).pin_memory(),
+                     cn=t.empty((nq,), dtype=t.int32).pin_memory())
+            b["q_np"], b["ids_np"], b["sc_np"], b["cn_np"] = b["q"].numpy(), b["ids"].numpy(), b["sc"].numpy(), b["cn"].numpy()
+            self._bufs[key] = b
+        return self._bufs[key]
+
     def bruteforce_topk(self, q, k: int, metric: int = METRIC_L2):
-        """Host query [d] or [nq][d] (numpy) -> numpy results; H2D and D2H inside (the e2e path)."""
+        """Host query [d] or [nq][d] (numpy) -> numpy results; H2D and D2H inside (the e2e path): the query goes
+        through a pinned staging buffer, the three result arrays come back with asynchronous copies and ONE
+        stream synchronisation."""
         t = self.torch
         q = np.ascontiguousarray(q, dtype=np.float32)
         single = q.ndim == 1
         q2 = q.reshape(1, -1) if single else q
-        d_q = t.from_numpy(q2).to(self.dev, non_blocking=True)
-        ids, sc, cn = self.bruteforce_topk_dev(d_q, q2.shape[0], k, metric)
-        ids, sc, cn = ids.cpu().numpy(), sc.cpu().numpy(), cn.cpu().numpy()
+        nq = q2.shape[0]
+        h = self._host_buffers(nq, k, q2.shape[1])
+        h["q_np"][...] = q2
+        h["dq"].copy_(h["q"], non_blocking=True)
+        ids, sc, cn = self.bruteforce_topk_dev(h["dq"], nq, k, metric)
+        h["ids"].copy_(ids, non_blocking=True)
+        h["sc"].copy_(sc, non_blocking=True)
+        h["cn"].copy_(cn, non_blocking=True)
+        t.cuda.current_stream().synchronize()
+        ids, sc, cn = h["ids_np"].copy(), h["sc_np"].copy(), h["cn_np"].copy()
         if single:
             return ids[0, :cn[0]], sc[0, :cn[0]]
         return ids, sc, cn
