@@ -286,13 +286,21 @@ pq_tc_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tc_wait_ld();
           tc_pin32(v[h & 1]);
           if (h < 3) tc_ld32(taddr + (uint32_t)(ch * 128 + (h + 1) * 32), v[(h + 1) & 1]);
+          // two columns of a chain per step: 5 min / max operations (one of them 3-input) instead of 6 -- the ALU
+          // pipe is what bounds this kernel (profiles/r1_pq_tc_full.txt)
 #pragma unroll
-          for (int j = 0; j < 32; j++) {
-            const int cj = h * 32 + j;  // column within this warp's half: the chain index ignores ch (128 % 4 == 0)
-            const float key = __uint_as_float((v[h & 1][j] & 0xffffffc0u) | (uint32_t)(ch * 32 + (cj >> 2)));
-            const float lo = fminf(m1[cj & 3], key);
-            m1[cj & 3] = fmaxf(m1[cj & 3], key);
-            m2[cj & 3] = fmaxf(m2[cj & 3], lo);
+          for (int p = 0; p < 4; p++) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+              const int ja = 8 * p + c, jb = ja + 4;  // columns of this load; the chain index ignores ch and h
+              const int ca = h * 32 + ja, cb = h * 32 + jb;
+              const float ka = __uint_as_float((v[h & 1][ja] & 0xffffffc0u) | (uint32_t)(ch * 32 + (ca >> 2)));
+              const float kb = __uint_as_float((v[h & 1][jb] & 0xffffffc0u) | (uint32_t)(ch * 32 + (cb >> 2)));
+              const float hi = fmaxf(ka, kb), lo = fminf(ka, kb);
+              const float t = fminf(m1[c], hi);
+              m2[c] = fmaxf(fmaxf(m2[c], lo), t);
+              m1[c] = fmaxf(m1[c], hi);
+            }
           }
         }
         // this half's two largest keys over the four chains (the winning chain travels beside the key)
