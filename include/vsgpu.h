@@ -185,10 +185,11 @@ int32_t vs_merge_adc_rerank_packed_dev(const int64_t* d_gath, int32_t world, int
  * [world][64] array to vs_peer_connect.  vs_exchange_merge_* then replace "collective all-gather of d_pack +
  * vs_merge_*_packed_dev": the rank pushes its packed lists into every peer's buffer with plain stores and raises
  * a flag there; the merge kernel waits for the `world` flags of its own buffer and reads local memory only.
- * Results are those of the NCCL path, bit for bit.  Every rank must issue the same exchanges in the same order
- * (as with any collective); a slot is reused every `depth` exchanges, so depth >= 2 * (streams a rank alternates
- * its exchanges between) -- the coordinator uses 8 for 2 streams.  A peer that never arrives traps the waiting
- * kernel after 20 s instead of hanging the GPU. */
+ * Results are those of the NCCL path, bit for bit.  Every rank must issue the same exchanges in the same order on
+ * corresponding streams (as with any collective).  Each stream a communicator sees gets its own ring of 4 slots,
+ * in order of first use, so exchanges on different streams may interleave freely; depth (a multiple of 4) = 4 x the
+ * number of streams the communicator will serve -- one more stream is refused with VS_ESTATE.  A peer that never
+ * arrives traps the waiting kernel after 20 s instead of hanging the GPU. */
 #define VS_PEER_HANDLE_BYTES 64
 int32_t vs_peer_create(int32_t rank, int32_t world, int64_t slot_bytes, int32_t depth, uint64_t* comm_out,
                        uint8_t* handle_out /* [VS_PEER_HANDLE_BYTES] */);

@@ -414,7 +414,8 @@ def test_adc_rerank_across_shards(vs, oracle, shards, metric):
 def test_peer_exchange_merge_equals_gather_then_merge(vs, world, nq, k):
     """The peer-memory exchange (push into every rank's buffer + flag wait inside the merge kernel) must give what
     "all-gather, then vs_merge_packed_dev" gives.  Ranks are emulated by `world` communicators on this GPU, each
-    on its own stream, connected by address; more rounds than the ring is deep, so every slot is reused."""
+    on its own stream, connected by address; more rounds than a stream's ring is deep, so every slot is reused, and a
+    second stream per rank every third round (its own ring)."""
     import ctypes as C
 
     import torch
@@ -422,9 +423,10 @@ def test_peer_exchange_merge_equals_gather_then_merge(vs, world, nq, k):
     from vectorsearch_b200 import _lib as L
 
     lib = vs.load()
-    depth, rounds = 4, 11
+    depth, rounds = 8, 11
     comms, bases = [], (C.c_uint64 * world)()
     streams = [torch.cuda.Stream() for _ in range(world)]
+    streams2 = [torch.cuda.Stream() for _ in range(world)]
     rng = np.random.default_rng(world * 1000 + nq)
     try:
         for r in range(world):
@@ -462,14 +464,20 @@ def test_peer_exchange_merge_equals_gather_then_merge(vs, world, nq, k):
             torch.cuda.synchronize()
             for r in range(world):               # rank r's merge spins until the later-launched ranks have published
                 oi, os_, oc = outs[r]
+                st = (streams2 if rnd % 3 == 2 else streams)[r].cuda_stream
                 L.check(lib.vs_exchange_merge_packed_dev(comms[r], d_pack[r].data_ptr(), nq, k, 1, oi.data_ptr(),
-                                                         os_.data_ptr(), oc.data_ptr(), streams[r].cuda_stream))
+                                                         os_.data_ptr(), oc.data_ptr(), st))
             torch.cuda.synchronize()
             for r in range(world):
                 oi, os_, oc = outs[r]
                 assert torch.equal(oc, want_c), (rnd, r)
                 assert torch.equal(oi, want_i), (rnd, r)
                 assert torch.equal(os_.view(torch.int64), want_s.view(torch.int64)), (rnd, r)
+        # a third stream does not fit a communicator of depth 8 (two rings): refused, not corrupted
+        oi, os_, oc = outs[0]
+        rc = lib.vs_exchange_merge_packed_dev(comms[0], d_pack[0].data_ptr(), nq, k, 1, oi.data_ptr(), os_.data_ptr(),
+                                              oc.data_ptr(), torch.cuda.Stream().cuda_stream)
+        assert rc != 0
     finally:
         torch.cuda.synchronize()
         for c in comms:

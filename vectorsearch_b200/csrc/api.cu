@@ -1530,7 +1530,9 @@ struct PeerComm {
   size_t slot_bytes = 0, flags_off = 0, ticket_off = 0, total = 0;
   unsigned char* bases[VS_PEER_MAX_WORLD] = {};
   bool connected = false, by_ptr = false;
-  std::atomic<uint64_t> seq{0};
+  std::mutex mu;
+  std::vector<cudaStream_t> streams;  // ring r belongs to streams[r]
+  std::vector<uint64_t> ring_seq;
 };
 PeerComm* peer_lookup(uint64_t comm) {
   PeerComm* pc = reinterpret_cast<PeerComm*>(static_cast<uintptr_t>(comm));
@@ -1543,11 +1545,26 @@ struct PeerSlot {
   unsigned int* ticket;
   uint64_t seq;
 };
-// Every rank issues the same exchanges in the same order (as with any collective): the sequence number picks the slot.
-PeerSlot peer_next(PeerComm* pc, size_t payload) {
-  PeerSlot ps;
-  ps.seq = pc->seq.fetch_add(1) + 1;
-  const size_t slot = (size_t)((ps.seq - 1) % (uint64_t)pc->depth);
+// Slots are handed out per STREAM: each stream a communicator sees gets its own ring of PEER_RING slots, in order
+// of first use (every rank issues the same exchanges on corresponding streams in the same order, as with any
+// collective).  On one stream a rank publishes exchange t only after its own merge of t-1, which needed everybody's
+// publish of t-1 and hence everybody's merge of t-2: the slot of t-PEER_RING is free on every rank, however far
+// other streams have run ahead.
+constexpr int PEER_RING = 4;
+bool peer_next(PeerComm* pc, size_t payload, cudaStream_t st, PeerSlot* out) {
+  std::lock_guard<std::mutex> g(pc->mu);
+  int ring = -1;
+  for (size_t i = 0; i < pc->streams.size(); i++)
+    if (pc->streams[i] == st) ring = (int)i;
+  if (ring < 0) {
+    if ((int)(pc->streams.size() + 1) * PEER_RING > pc->depth) return false;
+    ring = (int)pc->streams.size();
+    pc->streams.push_back(st);
+    pc->ring_seq.push_back(0);
+  }
+  PeerSlot& ps = *out;
+  ps.seq = ++pc->ring_seq[ring];
+  const size_t slot = (size_t)ring * PEER_RING + (size_t)((ps.seq - 1) % PEER_RING);
   unsigned char* own = pc->bases[pc->rank];
   const size_t slot_base = slot * (size_t)pc->world * pc->slot_bytes;
   ps.data_off = slot_base + (size_t)pc->rank * payload;
@@ -1555,7 +1572,7 @@ PeerSlot peer_next(PeerComm* pc, size_t payload) {
   ps.gath = reinterpret_cast<const int64_t*>(own + slot_base);
   ps.flags = reinterpret_cast<const unsigned long long*>(own + ps.flag_off);
   ps.ticket = reinterpret_cast<unsigned int*>(own + pc->ticket_off) + slot;
-  return ps;
+  return true;
 }
 }  // namespace
 
@@ -1564,8 +1581,9 @@ int32_t vs_peer_create(int32_t rank, int32_t world, int64_t slot_bytes, int32_t 
   if (!comm_out || !handle_out) return fail(VS_EINVAL, "null pointer");
   if (world < 1 || world > VS_PEER_MAX_WORLD || rank < 0 || rank >= world)
     return fail(VS_EINVAL, "rank / world out of range (world <= %d)", VS_PEER_MAX_WORLD);
-  if (slot_bytes < 16 || (slot_bytes & 15) != 0 || depth < 2 || depth > 64)
-    return fail(VS_EINVAL, "slot_bytes must be a positive multiple of 16 and depth in 2..64");
+  if (slot_bytes < 16 || (slot_bytes & 15) != 0 || depth < PEER_RING || depth > 64 || depth % PEER_RING != 0)
+    return fail(VS_EINVAL, "slot_bytes must be a positive multiple of 16 and depth a multiple of %d in %d..64", PEER_RING,
+                PEER_RING);
   static_assert(sizeof(cudaIpcMemHandle_t) == VS_PEER_HANDLE_BYTES, "handle size");
   ThreadCtx* c;
   RET(ctx_bind(&c));
@@ -1662,7 +1680,9 @@ int32_t vs_exchange_merge_packed_dev(uint64_t comm, const int64_t* d_pack, int32
   ThreadCtx* c;
   RET(ctx_bind(&c));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const PeerSlot ps = peer_next(pc, payload);
+  PeerSlot ps;
+  if (!peer_next(pc, payload, st, &ps))
+    return fail(VS_ESTATE, "communicator of depth %d serves %d streams; this is one more", pc->depth, pc->depth / PEER_RING);
   CK(launch_peer_publish(pc->bases, pc->world, pc->rank, d_pack, payload, ps.data_off, ps.flag_off, ps.seq, ps.ticket, st),
      "peer publish launch");
   CK(launch_merge_packed(ps.gath, pc->world, nq, k, descending != 0, d_ids_out, d_scores_out, d_counts_out, st, ps.flags,
@@ -1684,7 +1704,9 @@ int32_t vs_exchange_merge_adc_rerank_packed_dev(uint64_t comm, const int64_t* d_
   ThreadCtx* c;
   RET(ctx_bind(&c));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const PeerSlot ps = peer_next(pc, payload);
+  PeerSlot ps;
+  if (!peer_next(pc, payload, st, &ps))
+    return fail(VS_ESTATE, "communicator of depth %d serves %d streams; this is one more", pc->depth, pc->depth / PEER_RING);
   CK(launch_peer_publish(pc->bases, pc->world, pc->rank, d_pack, payload, ps.data_off, ps.flag_off, ps.seq, ps.ticket, st),
      "peer publish launch");
   CK(launch_merge_adc_rerank(ps.gath, pc->world, nq, n_cand, k, d_ids_out, d_scores_out, d_counts_out, st, ps.flags, ps.seq),

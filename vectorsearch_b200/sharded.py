@@ -102,15 +102,11 @@ def merge_adc_rerank_host(packs: np.ndarray, k: int):
     return (np.array([e[2] for _, e in top], np.int64), np.array([e[3] for _, e in top], np.float64))
 
 
-def PEER_DEPTH_OK(slots: int, depth: int) -> bool:
-    return depth >= 2 * (max(1, slots) + 1)
-
-
 class ShardedSegment:
     """One rank's row range of a corpus + the collective merge (torch.distributed)."""
 
-    PEER_SLOT_BYTES = 4 << 20  # largest packed result one exchange may carry through the peer buffers
-    PEER_DEPTH = 8             # slots in flight: >= 2 x the streams exchanges alternate between (slots + current)
+    PEER_SLOT_BYTES = 2 << 20  # largest packed result one exchange may carry through the peer buffers
+    PEER_RING = 4              # slots per stream (libvsgpu hands every stream its own ring)
 
     def __init__(self, segment, rank: int, world: int, group=None, slots: int = 2, peer: bool | None = None):
         import torch
@@ -128,7 +124,8 @@ class ShardedSegment:
         self.exchange = "none" if world == 1 else "nccl all-gather"
         if peer is None:
             peer = os.environ.get("VS_PEER", "1") != "0"
-        if (world > 1 and peer and world <= 16 and PEER_DEPTH_OK(slots, self.PEER_DEPTH) and dist.is_available()
+        self._peer_depth = self.PEER_RING * (max(1, slots) + 2)  # the coordinator's streams, torch's current one, a spare
+        if (world > 1 and peer and world <= 16 and self._peer_depth <= 64 and dist.is_available()
                 and dist.is_initialized() and dist.get_backend(group) == "nccl"):
             self._peer_setup()
         # query batches are independent: consecutive ones alternate between `slots` streams (each with its
@@ -143,7 +140,7 @@ class ShardedSegment:
         comm = C.c_uint64(0)
         handle = (C.c_uint8 * 64)()
         try:
-            check(self.lib.vs_peer_create(self.rank, self.world, self.PEER_SLOT_BYTES, self.PEER_DEPTH, C.byref(comm), handle))
+            check(self.lib.vs_peer_create(self.rank, self.world, self.PEER_SLOT_BYTES, self._peer_depth, C.byref(comm), handle))
             ok = 1
         except Exception as e:  # noqa: BLE001 -- the NCCL path stays available
             warnings.warn(f"peer exchange unavailable on rank {self.rank} ({e}); using the NCCL all-gather")
