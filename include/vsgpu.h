@@ -201,6 +201,12 @@ int32_t vs_peer_connect_ptrs(uint64_t comm, const uint64_t* bases /* [world] */)
 int32_t vs_peer_destroy(uint64_t comm);
 int32_t vs_exchange_merge_packed_dev(uint64_t comm, const int64_t* d_pack, int32_t nq, int32_t k, int32_t descending,
                                      int64_t* d_ids_out, double* d_scores_out, int32_t* d_counts_out, void* stream);
+/* The whole sharded query as one HOST-buffer call (what a rank's request thread makes): H2D of the queries, local
+ * scan, peer exchange, merge, results back (short lists are written by the merge kernel straight into pinned host
+ * memory), one synchronisation.  Collective: every rank calls it with the same queries; results are identical on
+ * every rank and equal to vs_bruteforce_topk over the concatenated shards. */
+int32_t vs_bruteforce_topk_exchange(uint64_t h, uint64_t comm, const float* q, int32_t nq, int32_t k, int32_t metric,
+                                    int64_t* ids_out, double* scores_out, int32_t* counts_out);
 int32_t vs_exchange_merge_adc_rerank_packed_dev(uint64_t comm, const int64_t* d_pack, int32_t nq, int32_t n_cand,
                                                 int32_t k, int64_t* d_ids_out, double* d_scores_out,
                                                 int32_t* d_counts_out, void* stream);

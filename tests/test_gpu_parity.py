@@ -484,6 +484,73 @@ def test_peer_exchange_merge_equals_gather_then_merge(vs, world, nq, k):
             lib.vs_peer_destroy(c)
 
 
+@pytest.mark.parametrize("world,nq", [(2, 1), (3, 4)])
+def test_sharded_host_call_through_peer_exchange(vs, oracle, world, nq):
+    """vs_bruteforce_topk_exchange: the whole sharded query as one host-buffer call per rank (H2D, scan, peer
+    exchange, merge into pinned host memory, one synchronisation).  Ranks are host threads with one shard each on
+    this GPU; every rank must return the reference's result over the concatenated rows, ties included."""
+    import ctypes as C
+    import threading
+
+    from vectorsearch_b200 import _lib as L
+    from vectorsearch_b200.sharded import shard_range
+
+    lib = vs.load()
+    n, d, k = 30011, 48, 10
+    rows = oracle.gen_rows(42, 0, n, d)
+    rows[20000:20006] = rows[5]                       # ties across shards: the lower global row wins
+    qs = oracle.gen_rows(43, 0, nq, d)
+    qs[0] = rows[5]
+    segs, comms, bases = [], [], (C.c_uint64 * world)()
+    try:
+        for r in range(world):
+            lo, hi = shard_range(n, r, world)
+            segs.append(vs.Segment.upload(rows[lo:hi], id_base=lo))
+            comm, hd = C.c_uint64(0), (C.c_uint8 * 64)()
+            L.check(lib.vs_peer_create(r, world, 1 << 16, 4, C.byref(comm), hd))
+            comms.append(comm.value)
+            b = C.c_uint64(0)
+            L.check(lib.vs_peer_base(comm.value, C.byref(b)))
+            bases[r] = b.value
+        for r in range(world):
+            L.check(lib.vs_peer_connect_ptrs(comms[r], bases))
+        out, errs = [None] * world, []
+
+        def run(r):
+            try:
+                res = []
+                for rep in range(6):                  # more calls than the ring is deep
+                    ids = np.zeros((nq, k), np.int64)
+                    sc = np.zeros((nq, k), np.float64)
+                    cn = np.zeros(nq, np.int32)
+                    L.check(lib.vs_bruteforce_topk_exchange(segs[r].handle, comms[r], qs.ctypes.data_as(L.f32p), nq, k, 0,
+                                                            ids.ctypes.data_as(L.i64p), sc.ctypes.data_as(L.f64p),
+                                                            cn.ctypes.data_as(L.i32p)))
+                    res.append((ids, sc, cn))
+                out[r] = res
+            except Exception as e:  # noqa: BLE001
+                errs.append(e)
+
+        threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+        for th in threads:
+            th.start()
+        for th in threads:
+            th.join(timeout=120)
+        assert not errs, errs
+        for i in range(nq):
+            oi, os_, _ = oracle.bruteforce_topk(rows, qs[i], k)
+            for r in range(world):
+                for ids, sc, cn in out[r]:
+                    assert cn[i] == len(oi)
+                    assert np.array_equal(ids[i], oi), (r, i, ids[i], oi)
+                    assert _same(sc[i], os_)
+    finally:
+        for c in comms:
+            lib.vs_peer_destroy(c)
+        for seg in segs:
+            seg.free()
+
+
 def _quantisation_error(oracle, cent, rows):
     codes = oracle.pq_encode_batch(cent, rows)
     M, K, sd = cent.shape

@@ -1533,6 +1533,10 @@ struct PeerComm {
   std::mutex mu;
   std::vector<cudaStream_t> streams;  // ring r belongs to streams[r]
   std::vector<uint64_t> ring_seq;
+  // staging of the host-buffer entry point (vs_bruteforce_topk_exchange): device and pinned host, grown on demand
+  std::mutex xmu;
+  unsigned char *x_dev = nullptr, *x_host = nullptr;
+  size_t x_dev_cap = 0, x_host_cap = 0;
 };
 PeerComm* peer_lookup(uint64_t comm) {
   PeerComm* pc = reinterpret_cast<PeerComm*>(static_cast<uintptr_t>(comm));
@@ -1663,6 +1667,8 @@ int32_t vs_peer_destroy(uint64_t comm) {
     if (p == pc->rank) cudaFree(pc->bases[p]);
     else if (!pc->by_ptr) cudaIpcCloseMemHandle(pc->bases[p]);
   }
+  if (pc->x_dev) cudaFree(pc->x_dev);
+  if (pc->x_host) cudaFreeHost(pc->x_host);
   pc->magic = 0;
   delete pc;
   return VS_OK;
@@ -1687,6 +1693,68 @@ int32_t vs_exchange_merge_packed_dev(uint64_t comm, const int64_t* d_pack, int32
      "peer publish launch");
   CK(launch_merge_packed(ps.gath, pc->world, nq, k, descending != 0, d_ids_out, d_scores_out, d_counts_out, st, ps.flags,
                          ps.seq), "merge launch");
+  return VS_OK;
+}
+
+// The whole sharded query as ONE host call (the e2e path of a rank): pinned staging in, local scan into the packed
+// list, peer exchange, merge -- short result lists are written by the merge kernel straight into pinned host
+// memory -- one synchronisation.  Collective: every rank calls it with the same queries.
+int32_t vs_bruteforce_topk_exchange(uint64_t h, uint64_t comm, const float* q, int32_t nq, int32_t k, int32_t metric,
+                                    int64_t* ids_out, double* scores_out, int32_t* counts_out) {
+  Segment* s = seg_lookup(h);
+  RET(check_query_args(s, q, nq, k, metric));
+  if (!ids_out || !scores_out) return fail(VS_EINVAL, "null output pointer");
+  PeerComm* pc = peer_lookup(comm);
+  if (!pc || !pc->connected) return fail(VS_ESTATE, "peer communicator is not connected");
+  ThreadCtx* c;
+  RET(ctx_bind(&c));
+  auto up = [](size_t b) { return (b + 255) & ~size_t(255); };
+  const size_t qb = up((size_t)nq * s->d * 4), pb = up((size_t)nq * 2 * k * 8), ib = up((size_t)nq * k * 8), cb = up((size_t)nq * 4);
+  if ((size_t)nq * 2 * k * 8 > pc->slot_bytes) return fail(VS_EINVAL, "packed lists exceed the communicator's slot");
+  std::lock_guard<std::mutex> g(pc->xmu);
+  const size_t need_d = qb + pb + cb + 2 * ib + cb, need_h = qb + 2 * ib + cb;
+  if (need_d > pc->x_dev_cap) {
+    CK(cudaStreamSynchronize(c->stream), "sync");
+    if (pc->x_dev) cudaFree(pc->x_dev);
+    pc->x_dev = nullptr;
+    pc->x_dev_cap = 0;
+    CK(cudaMalloc(&pc->x_dev, need_d), "cudaMalloc(exchange staging)");
+    pc->x_dev_cap = need_d;
+  }
+  if (need_h > pc->x_host_cap) {
+    CK(cudaStreamSynchronize(c->stream), "sync");
+    if (pc->x_host) cudaFreeHost(pc->x_host);
+    pc->x_host = nullptr;
+    pc->x_host_cap = 0;
+    CK(cudaMallocHost(&pc->x_host, need_h), "cudaMallocHost(exchange staging)");
+    pc->x_host_cap = need_h;
+  }
+  unsigned char* d = pc->x_dev;
+  float* dq = reinterpret_cast<float*>(d);
+  int64_t* dpack = reinterpret_cast<int64_t*>(d + qb);
+  int32_t* dcn_local = reinterpret_cast<int32_t*>(d + qb + pb);
+  int64_t* dids = reinterpret_cast<int64_t*>(d + qb + pb + cb);
+  double* dsc = reinterpret_cast<double*>(d + qb + pb + cb + ib);
+  int32_t* dcn = reinterpret_cast<int32_t*>(d + qb + pb + cb + 2 * ib);
+  unsigned char* hh = pc->x_host;
+  float* hq = reinterpret_cast<float*>(hh);
+  int64_t* hids = reinterpret_cast<int64_t*>(hh + qb);
+  double* hsc = reinterpret_cast<double*>(hh + qb + ib);
+  int32_t* hcn = reinterpret_cast<int32_t*>(hh + qb + 2 * ib);
+  memcpy(hq, q, (size_t)nq * s->d * 4);
+  CK(cudaMemcpyAsync(dq, hq, (size_t)nq * s->d * 4, cudaMemcpyHostToDevice, c->stream), "H2D q");
+  RET(vs_bruteforce_topk_packed_dev(h, dq, nq, k, metric, dpack, dcn_local, c->stream));
+  const bool direct = (size_t)nq * k <= 4096;  // short lists: the merge writes pinned host memory (UVA) itself
+  RET(vs_exchange_merge_packed_dev(comm, dpack, nq, k, 1, direct ? hids : dids, direct ? hsc : dsc, direct ? hcn : dcn, c->stream));
+  if (!direct) {
+    CK(cudaMemcpyAsync(hids, dids, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, c->stream), "D2H ids");
+    CK(cudaMemcpyAsync(hsc, dsc, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, c->stream), "D2H scores");
+    CK(cudaMemcpyAsync(hcn, dcn, (size_t)nq * 4, cudaMemcpyDeviceToHost, c->stream), "D2H counts");
+  }
+  CK(cudaStreamSynchronize(c->stream), "sync");
+  memcpy(ids_out, hids, (size_t)nq * k * 8);
+  memcpy(scores_out, hsc, (size_t)nq * k * 8);
+  if (counts_out) memcpy(counts_out, hcn, (size_t)nq * 4);
   return VS_OK;
 }
 

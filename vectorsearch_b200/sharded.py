@@ -318,6 +318,17 @@ class ShardedSegment:
         single = q.ndim == 1
         q2 = q.reshape(1, -1) if single else q
         nq = q2.shape[0]
+        if self._comm is not None and nq * 2 * k * 8 <= self.PEER_SLOT_BYTES and self.seg.n > 0:
+            # one C call: pinned staging, scan, peer exchange, merge writing host memory, one synchronisation
+            ids = np.zeros((nq, k), dtype=np.int64)
+            sc = np.zeros((nq, k), dtype=np.float64)
+            cn = np.zeros(nq, dtype=np.int32)
+            check(self.lib.vs_bruteforce_topk_exchange(
+                self.seg.handle, self._comm, q2.ctypes.data_as(L.f32p), nq, k, metric, ids.ctypes.data_as(L.i64p),
+                sc.ctypes.data_as(L.f64p), cn.ctypes.data_as(L.i32p)))
+            if single:
+                return ids[0, :cn[0]], sc[0, :cn[0]]
+            return ids, sc, cn
         h = self._host_buffers(nq, k, q2.shape[1])
         h["q_np"][...] = q2
         h["dq"].copy_(h["q"], non_blocking=True)
