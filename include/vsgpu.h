@@ -207,6 +207,9 @@ int32_t vs_exchange_merge_packed_dev(uint64_t comm, const int64_t* d_pack, int32
  * every rank and equal to vs_bruteforce_topk over the concatenated shards. */
 int32_t vs_bruteforce_topk_exchange(uint64_t h, uint64_t comm, const float* q, int32_t nq, int32_t k, int32_t metric,
                                     int64_t* ids_out, double* scores_out, int32_t* counts_out);
+int32_t vs_adc_rerank_topk_exchange(uint64_t h, uint64_t comm, const float* q, int32_t nq, int32_t n_cand, int32_t k,
+                                    int32_t metric, int32_t normalize_on_read, int64_t* ids_out, double* scores_out,
+                                    int32_t* counts_out);
 int32_t vs_exchange_merge_adc_rerank_packed_dev(uint64_t comm, const int64_t* d_pack, int32_t nq, int32_t n_cand,
                                                 int32_t k, int64_t* d_ids_out, double* d_scores_out,
                                                 int32_t* d_counts_out, void* stream);

@@ -551,6 +551,78 @@ def test_sharded_host_call_through_peer_exchange(vs, oracle, world, nq):
             seg.free()
 
 
+@pytest.mark.parametrize("world,metric", [(2, 0), (3, 1)])
+def test_sharded_adc_rerank_host_call_through_peer_exchange(vs, oracle, world, metric):
+    """vs_adc_rerank_topk_exchange, ranks as host threads: equals the single-segment ADC + re-rank of the reference
+    (global first n_cand by approximate distance, re-ranked exactly)."""
+    import ctypes as C
+    import threading
+
+    from vectorsearch_b200 import _lib as L
+    from vectorsearch_b200.sharded import shard_range
+
+    lib = vs.load()
+    n, d, M, K, n_cand, k, nq = 40000, 64, 8, 64, 100, 10, 3
+    rows = oracle.gen_rows(42, 0, n, d)
+    rows[1000:1040] = rows[17]
+    rows[30000:30030] = rows[17]
+    qs = oracle.gen_rows(43, 0, nq, d)
+    qs[0] = rows[17]
+    cent = oracle.pq_train(rows[:5000], d, M, K, 3, 42)
+    codes = oracle.pq_encode_batch(cent, rows, threads=4)
+    segs, comms, bases = [], [], (C.c_uint64 * world)()
+    try:
+        for r in range(world):
+            lo, hi = shard_range(n, r, world)
+            seg = vs.Segment.upload(rows[lo:hi], id_base=lo)
+            seg.attach_pq(cent, codes[lo:hi])
+            segs.append(seg)
+            comm, hd = C.c_uint64(0), (C.c_uint8 * 64)()
+            L.check(lib.vs_peer_create(r, world, 1 << 16, 4, C.byref(comm), hd))
+            comms.append(comm.value)
+            b = C.c_uint64(0)
+            L.check(lib.vs_peer_base(comm.value, C.byref(b)))
+            bases[r] = b.value
+        for r in range(world):
+            L.check(lib.vs_peer_connect_ptrs(comms[r], bases))
+        out, errs = [None] * world, []
+
+        def run(r):
+            try:
+                res = []
+                for rep in range(5):
+                    ids = np.zeros((nq, k), np.int64)
+                    sc = np.zeros((nq, k), np.float64)
+                    cn = np.zeros(nq, np.int32)
+                    L.check(lib.vs_adc_rerank_topk_exchange(segs[r].handle, comms[r], qs.ctypes.data_as(L.f32p), nq, n_cand, k,
+                                                            metric, 0, ids.ctypes.data_as(L.i64p), sc.ctypes.data_as(L.f64p),
+                                                            cn.ctypes.data_as(L.i32p)))
+                    res.append((ids, sc, cn))
+                out[r] = res
+            except Exception as e:  # noqa: BLE001
+                errs.append(e)
+
+        threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+        for th in threads:
+            th.start()
+        for th in threads:
+            th.join(timeout=120)
+        assert not errs, errs
+        for i in range(nq):
+            ci, _ = oracle.adc_topn(oracle.build_lut(cent, qs[i]), codes, n_cand)
+            ri, rs, _ = oracle.rerank_topk(rows, qs[i], ci, k, metric)
+            for r in range(world):
+                for ids, sc, cn in out[r]:
+                    c = len(ri)
+                    assert cn[i] == c
+                    assert np.array_equal(ids[i, :c], ri) and _same(sc[i, :c], rs), (r, i, ids[i], ri)
+    finally:
+        for c in comms:
+            lib.vs_peer_destroy(c)
+        for seg in segs:
+            seg.free()
+
+
 def _quantisation_error(oracle, cent, rows):
     codes = oracle.pq_encode_batch(cent, rows)
     M, K, sd = cent.shape

@@ -73,6 +73,7 @@ SIGNATURES = {
     "vs_peer_destroy": (i32, [u64]),
     "vs_exchange_merge_packed_dev": (i32, [u64, vp, i32, i32, i32, vp, vp, vp, vp]),
     "vs_bruteforce_topk_exchange": (i32, [u64, u64, f32p, i32, i32, i32, i64p, f64p, i32p]),
+    "vs_adc_rerank_topk_exchange": (i32, [u64, u64, f32p, i32, i32, i32, i32, i32, i64p, f64p, i32p]),
     "vs_exchange_merge_adc_rerank_packed_dev": (i32, [u64, vp, i32, i32, i32, vp, vp, vp, vp]),
     "vs_kernel_launch_count": (i64, []),
     "vs_set_option": (i32, [C.c_char_p, i64]),

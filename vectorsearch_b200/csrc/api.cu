@@ -1523,9 +1523,7 @@ int32_t vs_merge_packed_dev(const int64_t* d_gath, int32_t world, int32_t nq, in
 
 // ---- peer exchange: all-gather + merge over NVLink peer memory (rank.cu) ------------------------------------
 namespace {
-constexpr uint64_t PEER_MAGIC = 0x7673706565723031ull;  // "vspeer01"
 struct PeerComm {
-  uint64_t magic = PEER_MAGIC;
   int rank = 0, world = 1, depth = 0, device = 0;
   size_t slot_bytes = 0, flags_off = 0, ticket_off = 0, total = 0;
   unsigned char* bases[VS_PEER_MAX_WORLD] = {};
@@ -1538,9 +1536,14 @@ struct PeerComm {
   unsigned char *x_dev = nullptr, *x_host = nullptr;
   size_t x_dev_cap = 0, x_host_cap = 0;
 };
+// communicators live in a registry: a stale or foreign handle is an error, never a wild pointer
+std::mutex g_peer_mu;
+std::unordered_map<uint64_t, PeerComm*> g_peers;
+uint64_t g_peer_next_id = 0x7065657200000001ull;  // "peer" + counter
 PeerComm* peer_lookup(uint64_t comm) {
-  PeerComm* pc = reinterpret_cast<PeerComm*>(static_cast<uintptr_t>(comm));
-  return (pc && pc->magic == PEER_MAGIC) ? pc : nullptr;
+  std::lock_guard<std::mutex> g(g_peer_mu);
+  auto it = g_peers.find(comm);
+  return it == g_peers.end() ? nullptr : it->second;
 }
 struct PeerSlot {
   size_t data_off, flag_off;
@@ -1611,7 +1614,11 @@ int32_t vs_peer_create(int32_t rank, int32_t world, int64_t slot_bytes, int32_t 
     return cuda_fail(e, "peer buffer");
   }
   memcpy(handle_out, &hd, sizeof(hd));
-  *comm_out = static_cast<uint64_t>(reinterpret_cast<uintptr_t>(pc));
+  {
+    std::lock_guard<std::mutex> g(g_peer_mu);
+    *comm_out = g_peer_next_id++;
+    g_peers[*comm_out] = pc;
+  }
   return VS_OK;
 }
 
@@ -1659,7 +1666,15 @@ int32_t vs_peer_connect_ptrs(uint64_t comm, const uint64_t* bases) {
 }
 
 int32_t vs_peer_destroy(uint64_t comm) {
-  PeerComm* pc = peer_lookup(comm);
+  PeerComm* pc = nullptr;
+  {
+    std::lock_guard<std::mutex> g(g_peer_mu);
+    auto it = g_peers.find(comm);
+    if (it != g_peers.end()) {
+      pc = it->second;
+      g_peers.erase(it);
+    }
+  }
   if (!pc) return fail(VS_EINVAL, "bad peer communicator");
   cudaDeviceSynchronize();
   for (int p = 0; p < pc->world; p++) {
@@ -1669,7 +1684,6 @@ int32_t vs_peer_destroy(uint64_t comm) {
   }
   if (pc->x_dev) cudaFree(pc->x_dev);
   if (pc->x_host) cudaFreeHost(pc->x_host);
-  pc->magic = 0;
   delete pc;
   return VS_OK;
 }
@@ -1696,23 +1710,8 @@ int32_t vs_exchange_merge_packed_dev(uint64_t comm, const int64_t* d_pack, int32
   return VS_OK;
 }
 
-// The whole sharded query as ONE host call (the e2e path of a rank): pinned staging in, local scan into the packed
-// list, peer exchange, merge -- short result lists are written by the merge kernel straight into pinned host
-// memory -- one synchronisation.  Collective: every rank calls it with the same queries.
-int32_t vs_bruteforce_topk_exchange(uint64_t h, uint64_t comm, const float* q, int32_t nq, int32_t k, int32_t metric,
-                                    int64_t* ids_out, double* scores_out, int32_t* counts_out) {
-  Segment* s = seg_lookup(h);
-  RET(check_query_args(s, q, nq, k, metric));
-  if (!ids_out || !scores_out) return fail(VS_EINVAL, "null output pointer");
-  PeerComm* pc = peer_lookup(comm);
-  if (!pc || !pc->connected) return fail(VS_ESTATE, "peer communicator is not connected");
-  ThreadCtx* c;
-  RET(ctx_bind(&c));
-  auto up = [](size_t b) { return (b + 255) & ~size_t(255); };
-  const size_t qb = up((size_t)nq * s->d * 4), pb = up((size_t)nq * 2 * k * 8), ib = up((size_t)nq * k * 8), cb = up((size_t)nq * 4);
-  if ((size_t)nq * 2 * k * 8 > pc->slot_bytes) return fail(VS_EINVAL, "packed lists exceed the communicator's slot");
-  std::lock_guard<std::mutex> g(pc->xmu);
-  const size_t need_d = qb + pb + cb + 2 * ib + cb, need_h = qb + 2 * ib + cb;
+// staging of the host-buffer exchange calls (caller holds pc->xmu)
+static int peer_staging(PeerComm* pc, ThreadCtx* c, size_t need_d, size_t need_h) {
   if (need_d > pc->x_dev_cap) {
     CK(cudaStreamSynchronize(c->stream), "sync");
     if (pc->x_dev) cudaFree(pc->x_dev);
@@ -1729,6 +1728,26 @@ int32_t vs_bruteforce_topk_exchange(uint64_t h, uint64_t comm, const float* q, i
     CK(cudaMallocHost(&pc->x_host, need_h), "cudaMallocHost(exchange staging)");
     pc->x_host_cap = need_h;
   }
+  return VS_OK;
+}
+
+// The whole sharded query as ONE host call (the e2e path of a rank): pinned staging in, local scan into the packed
+// list, peer exchange, merge -- short result lists are written by the merge kernel straight into pinned host
+// memory -- one synchronisation.  Collective: every rank calls it with the same queries.
+int32_t vs_bruteforce_topk_exchange(uint64_t h, uint64_t comm, const float* q, int32_t nq, int32_t k, int32_t metric,
+                                    int64_t* ids_out, double* scores_out, int32_t* counts_out) {
+  Segment* s = seg_lookup(h);
+  RET(check_query_args(s, q, nq, k, metric));
+  if (!ids_out || !scores_out) return fail(VS_EINVAL, "null output pointer");
+  PeerComm* pc = peer_lookup(comm);
+  if (!pc || !pc->connected) return fail(VS_ESTATE, "peer communicator is not connected");
+  ThreadCtx* c;
+  RET(ctx_bind(&c));
+  auto up = [](size_t b) { return (b + 255) & ~size_t(255); };
+  const size_t qb = up((size_t)nq * s->d * 4), pb = up((size_t)nq * 2 * k * 8), ib = up((size_t)nq * k * 8), cb = up((size_t)nq * 4);
+  if ((size_t)nq * 2 * k * 8 > pc->slot_bytes) return fail(VS_EINVAL, "packed lists exceed the communicator's slot");
+  std::lock_guard<std::mutex> g(pc->xmu);
+  RET(peer_staging(pc, c, qb + pb + cb + 2 * ib + cb, qb + 2 * ib + cb));
   unsigned char* d = pc->x_dev;
   float* dq = reinterpret_cast<float*>(d);
   int64_t* dpack = reinterpret_cast<int64_t*>(d + qb);
@@ -1779,6 +1798,53 @@ int32_t vs_exchange_merge_adc_rerank_packed_dev(uint64_t comm, const int64_t* d_
      "peer publish launch");
   CK(launch_merge_adc_rerank(ps.gath, pc->world, nq, n_cand, k, d_ids_out, d_scores_out, d_counts_out, st, ps.flags, ps.seq),
      "merge launch");
+  return VS_OK;
+}
+
+// Sealed segments across shards as ONE host call: ADC candidates with their exact scores, peer exchange, global
+// re-rank merge (FdbVectorIndex.java:769,820-828,997-1043 with shards in the role of row ranges of one segment).
+int32_t vs_adc_rerank_topk_exchange(uint64_t h, uint64_t comm, const float* q, int32_t nq, int32_t n_cand, int32_t k,
+                                    int32_t metric, int32_t normalize_on_read, int64_t* ids_out, double* scores_out,
+                                    int32_t* counts_out) {
+  Segment* s = seg_lookup(h);
+  RET(check_query_args(s, q, nq, n_cand, metric));
+  if (!ids_out || !scores_out) return fail(VS_EINVAL, "null output pointer");
+  if (k <= 0 || k > n_cand || k > TOPK_MAX_K) return fail(VS_EINVAL, "k must be in 1..min(n_cand, %d)", TOPK_MAX_K);
+  PeerComm* pc = peer_lookup(comm);
+  if (!pc || !pc->connected) return fail(VS_ESTATE, "peer communicator is not connected");
+  ThreadCtx* c;
+  RET(ctx_bind(&c));
+  auto up = [](size_t b) { return (b + 255) & ~size_t(255); };
+  const size_t qb = up((size_t)nq * s->d * 4), pb = up((size_t)nq * 4 * n_cand * 8), ib = up((size_t)nq * k * 8), cb = up((size_t)nq * 4);
+  if ((size_t)nq * 4 * n_cand * 8 > pc->slot_bytes) return fail(VS_EINVAL, "packed candidates exceed the communicator's slot");
+  std::lock_guard<std::mutex> g(pc->xmu);
+  RET(peer_staging(pc, c, qb + pb + 2 * ib + cb, qb + 2 * ib + cb));
+  unsigned char* d = pc->x_dev;
+  float* dq = reinterpret_cast<float*>(d);
+  int64_t* dpack = reinterpret_cast<int64_t*>(d + qb);
+  int64_t* dids = reinterpret_cast<int64_t*>(d + qb + pb);
+  double* dsc = reinterpret_cast<double*>(d + qb + pb + ib);
+  int32_t* dcn = reinterpret_cast<int32_t*>(d + qb + pb + 2 * ib);
+  unsigned char* hh = pc->x_host;
+  float* hq = reinterpret_cast<float*>(hh);
+  int64_t* hids = reinterpret_cast<int64_t*>(hh + qb);
+  double* hsc = reinterpret_cast<double*>(hh + qb + ib);
+  int32_t* hcn = reinterpret_cast<int32_t*>(hh + qb + 2 * ib);
+  memcpy(hq, q, (size_t)nq * s->d * 4);
+  CK(cudaMemcpyAsync(dq, hq, (size_t)nq * s->d * 4, cudaMemcpyHostToDevice, c->stream), "H2D q");
+  RET(vs_adc_rerank_packed_dev(h, dq, nq, n_cand, metric, normalize_on_read, dpack, c->stream));
+  const bool direct = (size_t)nq * k <= 4096;
+  RET(vs_exchange_merge_adc_rerank_packed_dev(comm, dpack, nq, n_cand, k, direct ? hids : dids, direct ? hsc : dsc,
+                                              direct ? hcn : dcn, c->stream));
+  if (!direct) {
+    CK(cudaMemcpyAsync(hids, dids, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, c->stream), "D2H ids");
+    CK(cudaMemcpyAsync(hsc, dsc, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, c->stream), "D2H scores");
+    CK(cudaMemcpyAsync(hcn, dcn, (size_t)nq * 4, cudaMemcpyDeviceToHost, c->stream), "D2H counts");
+  }
+  CK(cudaStreamSynchronize(c->stream), "sync");
+  memcpy(ids_out, hids, (size_t)nq * k * 8);
+  memcpy(scores_out, hsc, (size_t)nq * k * 8);
+  if (counts_out) memcpy(counts_out, hcn, (size_t)nq * 4);
   return VS_OK;
 }
 

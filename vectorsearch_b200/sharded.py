@@ -257,6 +257,29 @@ class ShardedSegment:
                                                       b["out_s"].data_ptr(), b["out_c"].data_ptr(), st))
         return b["out_i"], b["out_s"], b["out_c"]
 
+    def adc_rerank_topk(self, q, n_cand: int, k: int, metric: int = METRIC_L2):
+        """Host query [d] or [nq][d] -> numpy results of the cross-shard ADC + re-rank (H2D and D2H inside): one C
+        call through the peer exchange when it is up, else the device path with torch copies."""
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        single = q.ndim == 1
+        q2 = q.reshape(1, -1) if single else q
+        nq = q2.shape[0]
+        if self._comm is not None and nq * 4 * n_cand * 8 <= self.PEER_SLOT_BYTES and self.seg.n > 0:
+            ids = np.zeros((nq, k), dtype=np.int64)
+            sc = np.zeros((nq, k), dtype=np.float64)
+            cn = np.zeros(nq, dtype=np.int32)
+            check(self.lib.vs_adc_rerank_topk_exchange(
+                self.seg.handle, self._comm, q2.ctypes.data_as(L.f32p), nq, n_cand, k, metric, 0,
+                ids.ctypes.data_as(L.i64p), sc.ctypes.data_as(L.f64p), cn.ctypes.data_as(L.i32p)))
+        else:
+            d_q = self.torch.from_numpy(q2).to(self.dev)
+            ids, sc, cn = self.adc_rerank_topk_dev(d_q, nq, n_cand, k, metric)
+            self.torch.cuda.current_stream().synchronize()
+            ids, sc, cn = ids.cpu().numpy(), sc.cpu().numpy(), cn.cpu().numpy()
+        if single:
+            return ids[0, :cn[0]], sc[0, :cn[0]]
+        return ids, sc, cn
+
     def pq_train(self, n_total: int, row_lo: int, m: int, k: int, iterations: int, seed: int, allreduce=None,
                  exact_order: bool = True):
         """PqTrainer.train over the sharded corpus (config C3): local assignment and per-cluster sums on
