@@ -228,6 +228,8 @@ int64_t vs_kernel_launch_count(void);
  * "batch_warp_min_queries" (0 = automatic); "batch_pairs" (default 0): batches of more than 128 queries
  * nominate on CTA pairs (tcgen05 cta_group::2).  "scan_reserve_sms": SMs the one-query scan leaves free so that
  * work of another stream (the next query's prologue, a collective's CTAs) runs beside it (default 0).
+ * "peer_fused" (default 1): a one-query peer exchange publishes inside the merge kernel (one launch) instead
+ * of a publishing kernel followed by the merge.
  * "pdl" (default 1): the kernels of one call are chained with programmatic dependent launch (the next
  * kernel is set up while its predecessor runs and waits, in the kernel, for its results).
  * "pq_tensor_cores": how PQ assignment with 8-float sub-vectors nominates -- 2 (default) tcgen05 on fp16

@@ -462,6 +462,7 @@ def test_peer_exchange_merge_equals_gather_then_merge(vs, world, nq, k):
                 oc = torch.zeros((nq,), dtype=torch.int32, device="cuda")
                 outs.append((oi, os_, oc))
             torch.cuda.synchronize()
+            vs.set_option("peer_fused", rnd % 2)  # one query: publish inside the merge kernel / as a kernel of its own
             for r in range(world):               # rank r's merge spins until the later-launched ranks have published
                 oi, os_, oc = outs[r]
                 st = (streams2 if rnd % 3 == 2 else streams)[r].cuda_stream
@@ -479,6 +480,7 @@ def test_peer_exchange_merge_equals_gather_then_merge(vs, world, nq, k):
                                               oc.data_ptr(), torch.cuda.Stream().cuda_stream)
         assert rc != 0
     finally:
+        vs.set_option("peer_fused", 1)
         torch.cuda.synchronize()
         for c in comms:
             lib.vs_peer_destroy(c)

@@ -28,6 +28,7 @@ static std::atomic<int64_t> g_batch_min_queries{3};        // query batches at l
 static std::atomic<int64_t> g_batch_min_rows{16384};       // ... on segments at least this long
 static std::atomic<int64_t> g_batch_gm_bytes{int64_t(1) << 30};  // group-minima scratch per query chunk
 static std::atomic<int64_t> g_batch_warp_min_q{0};         // > 0: batches this large always select with one warp per query (tests)
+static std::atomic<int> g_peer_fused{1};                      // one-query exchanges: publish inside the merge kernel
 static std::atomic<int64_t> g_scan_reserve_sms{0};          // SMs the one-query scan leaves free (for a collective's CTAs)
 static std::atomic<int64_t> g_batch_pairs{0};               // 1: cta_group::2 nomination kernel for batches > 128 queries (measured equal)
 static std::atomic<int64_t> g_batch_prefilter{1};           // candidate groups are pre-filtered on the fp16 copy before exact scoring
@@ -654,6 +655,10 @@ int32_t vs_debug_adc_stats(uint32_t* out8) { return vs::debug_adc_stats(out8) ==
 
 int32_t vs_set_option(const char* name, int64_t value) {
   if (!name) return fail(VS_EINVAL, "null option name");
+  if (!strcmp(name, "peer_fused")) {
+    g_peer_fused.store(value != 0 ? 1 : 0);
+    return VS_OK;
+  }
   if (!strcmp(name, "pq_tc_keep_bytes")) {
     if (value < 0) return fail(VS_EINVAL, "pq_tc_keep_bytes must be >= 0");
     pq_tc_set_keep_bytes((unsigned long long)value);
@@ -1703,10 +1708,13 @@ int32_t vs_exchange_merge_packed_dev(uint64_t comm, const int64_t* d_pack, int32
   PeerSlot ps;
   if (!peer_next(pc, payload, st, &ps))
     return fail(VS_ESTATE, "communicator of depth %d serves %d streams; this is one more", pc->depth, pc->depth / PEER_RING);
-  CK(launch_peer_publish(pc->bases, pc->world, pc->rank, d_pack, payload, ps.data_off, ps.flag_off, ps.seq, ps.ticket, st),
-     "peer publish launch");
+  const PeerPublish pub{pc->bases, d_pack, payload, ps.data_off, ps.flag_off, pc->rank};
+  const bool fused = nq == 1 && g_peer_fused.load() != 0;  // one query: the merge kernel publishes, then waits
+  if (!fused)
+    CK(launch_peer_publish(pc->bases, pc->world, pc->rank, d_pack, payload, ps.data_off, ps.flag_off, ps.seq, ps.ticket, st),
+       "peer publish launch");
   CK(launch_merge_packed(ps.gath, pc->world, nq, k, descending != 0, d_ids_out, d_scores_out, d_counts_out, st, ps.flags,
-                         ps.seq), "merge launch");
+                         ps.seq, fused ? &pub : nullptr), "merge launch");
   return VS_OK;
 }
 
@@ -1794,10 +1802,13 @@ int32_t vs_exchange_merge_adc_rerank_packed_dev(uint64_t comm, const int64_t* d_
   PeerSlot ps;
   if (!peer_next(pc, payload, st, &ps))
     return fail(VS_ESTATE, "communicator of depth %d serves %d streams; this is one more", pc->depth, pc->depth / PEER_RING);
-  CK(launch_peer_publish(pc->bases, pc->world, pc->rank, d_pack, payload, ps.data_off, ps.flag_off, ps.seq, ps.ticket, st),
-     "peer publish launch");
-  CK(launch_merge_adc_rerank(ps.gath, pc->world, nq, n_cand, k, d_ids_out, d_scores_out, d_counts_out, st, ps.flags, ps.seq),
-     "merge launch");
+  const PeerPublish pub{pc->bases, d_pack, payload, ps.data_off, ps.flag_off, pc->rank};
+  const bool fused = nq == 1 && g_peer_fused.load() != 0;
+  if (!fused)
+    CK(launch_peer_publish(pc->bases, pc->world, pc->rank, d_pack, payload, ps.data_off, ps.flag_off, ps.seq, ps.ticket, st),
+       "peer publish launch");
+  CK(launch_merge_adc_rerank(ps.gath, pc->world, nq, n_cand, k, d_ids_out, d_scores_out, d_counts_out, st, ps.flags, ps.seq,
+                             fused ? &pub : nullptr), "merge launch");
   return VS_OK;
 }
 

@@ -150,10 +150,18 @@ cudaError_t launch_rank(const RankLaunch& L, cudaStream_t st);
 cudaError_t launch_score_pack(const RankLaunch& L, const double* cand_approx, const int32_t* cand_counts, int64_t* pack,
                               cudaStream_t st);
 // wait_flags != nullptr: the gathered lists arrive through the peer exchange; the kernel first waits until
-// wait_flags[0..w) have reached wait_seq (launch_peer_publish of every rank)
+// wait_flags[0..w) have reached wait_seq (launch_peer_publish of every rank).  pub != nullptr and nq == 1: the
+// kernel publishes this rank's list itself first (no separate launch_peer_publish for that exchange).
+struct PeerPublish {
+  unsigned char* const* bases;
+  const void* payload;
+  size_t bytes, data_off, flag_off;
+  int rank;
+};
 cudaError_t launch_merge_adc_rerank(const int64_t* gath, int w, int nq, int nc, int k, int64_t* ids_out,
                                     double* scores_out, int32_t* counts_out, cudaStream_t st,
-                                    const unsigned long long* wait_flags = nullptr, unsigned long long wait_seq = 0);
+                                    const unsigned long long* wait_flags = nullptr, unsigned long long wait_seq = 0,
+                                    const PeerPublish* pub = nullptr);
 // Peer exchange (rank.cu): copy `bytes` of payload to bases[p] + data_off of every peer p, then set
 // flag word `rank` at bases[p] + flag_off to seq.  ticket: one zeroed word of this rank per concurrent exchange.
 constexpr int VS_PEER_MAX_WORLD = 16;
@@ -168,7 +176,8 @@ cudaError_t launch_merge(const int64_t* ids, const double* scores, int64_t total
 // per query, concatenate in rank order, stable sort (descending scores or ascending distances), first k
 cudaError_t launch_merge_packed(const int64_t* gath, int w, int nq, int k, bool descending,
                                 int64_t* ids_out, double* scores_out, int32_t* counts_out, cudaStream_t st,
-                                const unsigned long long* wait_flags = nullptr, unsigned long long wait_seq = 0);
+                                const unsigned long long* wait_flags = nullptr, unsigned long long wait_seq = 0,
+                                const PeerPublish* pub = nullptr);
 
 // ---- misc.cu ----------------------------------------------------------------------------------
 // element e of the output = draw (first + e) of new java.util.Random(seed); kind 0: nextFloat()*2f-1f,

@@ -158,6 +158,27 @@ __device__ __forceinline__ void peer_wait(const unsigned long long* flags, int w
   __syncthreads();
 }
 
+// One query (a single CTA): the merge kernel publishes this rank's list itself before it waits -- one launch less
+// on the latency path.  With more CTAs the publishing stays a kernel of its own (nobody may wait before every CTA of
+// every rank has published, which only a kernel boundary guarantees without assumptions about CTA scheduling).
+struct PeerPublishDev {
+  PeerBases peers;
+  const uint4* payload;
+  size_t n16, data_off, flag_off;  // n16 == 0: nothing to publish
+  int rank;
+};
+__device__ __forceinline__ void peer_publish_inline(const PeerPublishDev& pp, int w, unsigned long long seq) {
+  if (pp.n16 == 0) return;
+  for (size_t i = threadIdx.x; i < pp.n16; i += blockDim.x) {
+    const uint4 v = pp.payload[i];
+    for (int p = 0; p < w; p++) reinterpret_cast<uint4*>(pp.peers.base[p] + pp.data_off)[i] = v;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if ((int)threadIdx.x < w)
+    st_release_sys(reinterpret_cast<unsigned long long*>(pp.peers.base[threadIdx.x] + pp.flag_off) + pp.rank, seq);
+}
+
 __global__ void __launch_bounds__(1024)
 peer_publish_kernel(PeerBases peers, int w, int rank, const uint4* payload, size_t n16, size_t data_off, size_t flag_off,
                     unsigned long long seq, unsigned int* ticket) {
@@ -182,8 +203,10 @@ peer_publish_kernel(PeerBases peers, int w, int rank, const uint4* payload, size
 __global__ void __launch_bounds__(RANK_THREADS)
 merge_packed_kernel(const int64_t* gath, int w, int nq, int k, int kp, int descending,
                     int64_t* __restrict__ ids_out, double* __restrict__ scores_out,
-                    int32_t* __restrict__ counts_out, const unsigned long long* wait_flags, unsigned long long wait_seq) {
+                    int32_t* __restrict__ counts_out, const unsigned long long* wait_flags, unsigned long long wait_seq,
+                    PeerPublishDev pub) {
   extern __shared__ __align__(128) ulonglong2 smem[];
+  peer_publish_inline(pub, w, wait_seq);
   peer_wait(wait_flags, w, wait_seq);  // peer exchange: the gathered lists arrive in this rank's own buffer
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -301,8 +324,9 @@ cudaError_t launch_score_pack(const RankLaunch& L, const double* cand_approx, co
 __global__ void __launch_bounds__(1024)
 merge_adc_rerank_kernel(const int64_t* gath, int w, int nq, int nc, int np, int np2, int k,
                         int64_t* __restrict__ ids_out, double* __restrict__ scores_out, int32_t* __restrict__ counts_out,
-                        const unsigned long long* wait_flags, unsigned long long wait_seq) {
+                        const unsigned long long* wait_flags, unsigned long long wait_seq, PeerPublishDev pub) {
   extern __shared__ __align__(16) ulonglong2 skey[];  // [np] approximate order, then [np2] exact order
+  peer_publish_inline(pub, w, wait_seq);
   peer_wait(wait_flags, w, wait_seq);
   ulonglong2* skey2 = skey + np;
   const int qi = blockIdx.x;
@@ -349,6 +373,19 @@ merge_adc_rerank_kernel(const int64_t* gath, int w, int nq, int nc, int np, int 
   if (threadIdx.x == 0) counts_out[qi] = s_found;
 }
 
+static PeerPublishDev make_publish(const PeerPublish* pub, int w, int nq) {
+  PeerPublishDev pd{};
+  if (pub != nullptr && nq == 1 && w <= VS_PEER_MAX_WORLD) {
+    for (int p = 0; p < w; p++) pd.peers.base[p] = pub->bases[p];
+    pd.payload = static_cast<const uint4*>(pub->payload);
+    pd.n16 = pub->bytes / 16;
+    pd.data_off = pub->data_off;
+    pd.flag_off = pub->flag_off;
+    pd.rank = pub->rank;
+  }
+  return pd;
+}
+
 cudaError_t launch_peer_publish(unsigned char* const* bases, int w, int rank, const void* payload, size_t bytes,
                                 size_t data_off, size_t flag_off, unsigned long long seq, unsigned int* ticket,
                                 cudaStream_t st) {
@@ -367,7 +404,7 @@ cudaError_t launch_peer_publish(unsigned char* const* bases, int w, int rank, co
 
 cudaError_t launch_merge_adc_rerank(const int64_t* gath, int w, int nq, int nc, int k, int64_t* ids_out,
                                     double* scores_out, int32_t* counts_out, cudaStream_t st,
-                                    const unsigned long long* wait_flags, unsigned long long wait_seq) {
+                                    const unsigned long long* wait_flags, unsigned long long wait_seq, const PeerPublish* pub) {
   if ((int64_t)w * nc > RANK_MAX_CAND) return cudaErrorInvalidValue;
   int np = 2, np2 = 2;
   while (np < w * nc) np <<= 1;
@@ -381,14 +418,14 @@ cudaError_t launch_merge_adc_rerank(const int64_t* gath, int w, int nq, int nc, 
   int threads = RANK_THREADS;
   while (threads < 1024 && threads < np / 2) threads <<= 1;
   merge_adc_rerank_kernel<<<nq, threads, smem, st>>>(gath, w, nq, nc, np, np2, k, ids_out, scores_out, counts_out, wait_flags,
-                                                     wait_seq);
+                                                     wait_seq, make_publish(pub, w, nq));
   count_launch();
   return cudaGetLastError();
 }
 
 cudaError_t launch_merge_packed(const int64_t* gath, int w, int nq, int k, bool descending,
                                 int64_t* ids_out, double* scores_out, int32_t* counts_out, cudaStream_t st,
-                                const unsigned long long* wait_flags, unsigned long long wait_seq) {
+                                const unsigned long long* wait_flags, unsigned long long wait_seq, const PeerPublish* pub) {
   const int kp = topk_pad(k);
   const size_t smem = (size_t)(RANK_THREADS / 32) * topk_warp_smem(kp);
   if (smem > 48 * 1024) {
@@ -396,7 +433,7 @@ cudaError_t launch_merge_packed(const int64_t* gath, int w, int nq, int k, bool 
     if (e != cudaSuccess) return e;
   }
   merge_packed_kernel<<<nq, RANK_THREADS, smem, st>>>(gath, w, nq, k, kp, descending ? 1 : 0, ids_out, scores_out, counts_out,
-                                                      wait_flags, wait_seq);
+                                                      wait_flags, wait_seq, make_publish(pub, w, nq));
   count_launch();
   return cudaGetLastError();
 }
