@@ -22,9 +22,13 @@
  *     concatenated, J/tasks/SegmentBuildService.java:325-338); ids are int64 row indices
  *     (segment id_base + local row); scores are IEEE doubles carrying the reference's
  *     arithmetic (score = -l2 for L2, = similarity for COSINE, J/fdb/FdbVectorIndex.java:687-693).
- *   - one process drives one GPU (vs_init(device)); multi-GPU runs use one process per GPU
- *     and shard rows by range (see vectorsearch_b200/sharded.py).
- *   - thread-safe and re-entrant: each calling thread gets its own stream and scratch.
+ *   - devices: vs_init(device) binds one GPU; vs_init_multi(n, devices) binds several to ONE process (the JVM):
+ *     segments uploaded afterwards are sharded by ascending row range over all of them and every query / build
+ *     entry point fans out inside the library (worker thread per GPU, cross-shard exchange over NVLink peer
+ *     memory) -- same results, bit for bit, as on one GPU.  One process per GPU (torchrun, MPI) is the other
+ *     supported shape: vs_peer_* + the *_exchange entry points (see vectorsearch_b200/sharded.py).
+ *   - thread-safe and re-entrant: each calling thread gets its own stream and scratch per device; a segment stays
+ *     alive until every call that uses it has returned, whatever vs_segment_free does on another thread.
  *   - there is NO CPU fallback: every entry point fails with VS_ECUDA when no device is usable.
  */
 #ifndef VSGPU_H
@@ -52,6 +56,15 @@ int32_t vs_version(void);
 const char* vs_last_error(void);
 /* Binds the calling process to one CUDA device.  Fails with VS_ECUDA if there is none. */
 int32_t vs_init(int32_t device);
+/* One process, several GPUs of one box (the reference's caller is one JVM fanning out with CompletableFuture.allOf,
+ * J/fdb/FdbVectorIndex.java:418-437).  device_ids[0] is the primary device (pair operations, host-row builds).  With
+ * n_gpus > 1 the devices must be identical and peer-accessible; vs_segment_upload / _generate / _upload_strided /
+ * _upload_records then return SHARDED handles (rows split by ascending range), which every segment, query and build
+ * entry point of this header accepts: vs_bruteforce_topk, vs_adc_topk, vs_adc_rerank_topk, vs_rerank_topk,
+ * vs_pq_train (rows == NULL), vs_pq_encode_batch (rows == NULL), vs_segment_*, vs_adc_query_*, vs_adc_gather.
+ * Re-binding (another vs_init / vs_init_multi) frees the previous group's sharded segments. */
+int32_t vs_init_multi(int32_t n_gpus, const int32_t* device_ids);
+int32_t vs_device_count(void); /* devices bound by the last vs_init / vs_init_multi */
 int32_t vs_shutdown(void);
 /* Lane count of the JVM's FloatVector.SPECIES_PREFERRED being reproduced (J/util/Distances.java:15):
  * 16 (AVX-512, default), 8 (AVX2), 4 (NEON/SSE).  Affects only the low-order bits of scores. */
@@ -86,6 +99,17 @@ int32_t vs_pq_approx_distance(const double* lut, int32_t M, int32_t K, const uin
  * missing" (J/fdb/FdbVectorIndex.java:681,696,1000,1022). */
 int32_t vs_segment_upload(const float* rows, int64_t n, int32_t d, const uint8_t* skip_mask,
                           int64_t id_base, uint64_t* handle_out);
+/* The same from the reference's stored bytes: packed little-endian fp32 (FloatPacker.floatsToBytes,
+ * J/util/FloatPacker.java:21-25 = VectorRecord.embedding, vectorsearch.proto:114-117), `stride` bytes from one
+ * record's embedding to the next (>= d * 4).  One strided copy; nothing is decoded on the host. */
+int32_t vs_segment_upload_strided(const uint8_t* bytes, int64_t n, int32_t d, int64_t stride, const uint8_t* skip_mask,
+                                  int64_t id_base, uint64_t* handle_out);
+/* ... and from serialized VectorRecord messages as they come out of the segment's range read
+ * (J/fdb/FdbVectorIndex.java:676-699): record i is buf[offsets[i] .. offsets[i + 1]).  The embedding field goes to the
+ * device through pinned staging, `deleted` becomes the row's skip flag (:681), vec_ids_out (nullable, [n]) receives each
+ * row's vec_id.  VS_EINVAL for a malformed message or an embedding that is not d * 4 bytes long. */
+int32_t vs_segment_upload_records(const uint8_t* buf, const int64_t* offsets, int64_t n, int32_t d, int64_t id_base,
+                                  int32_t* vec_ids_out, uint64_t* handle_out);
 /* Synthetic rows generated on the device: element (r, c) is draw (first_row + r) * d + c of
  * new java.util.Random(seed), mapped as nextFloat()*2f-1f (B/DistanceAndPqBenchmark.java:127-133). */
 int32_t vs_segment_generate(int64_t seed, int64_t first_row, int64_t n, int32_t d, int64_t id_base,
@@ -98,6 +122,30 @@ int32_t vs_segment_attach_pq(uint64_t h, const float* centroids, int32_t M, int3
                              const uint8_t* codes);
 int32_t vs_segment_download_codes(uint64_t h, int64_t first, int64_t count, uint8_t* codes_out);
 int32_t vs_segment_free(uint64_t h);
+
+/* ---- wire formats and residency (the steps either side of the scoring path) ---------------------------------
+ * PQCodebook (vectorsearch.proto:135-142: int32 m = 1; int32 k = 2; repeated bytes centroids = 3, entry s = K * subDim
+ * little-endian fp32) as SegmentBuildService.buildCodebookBytes writes it (J/tasks/SegmentBuildService.java:325-338)
+ * and SegmentCaches.decodeCodebook reads it (J/cache/SegmentCaches.java:141-162).  vs_codebook_encode emits the bytes
+ * protobuf-java's toByteArray() produces; out == NULL only reports the length.  vs_codebook_decode: centroids_out ==
+ * NULL only reports M, K and subDim. */
+int32_t vs_codebook_encode(const float* centroids, int32_t M, int32_t K, int32_t subDim, uint8_t* out, int64_t capacity,
+                           int64_t* len_out);
+int32_t vs_codebook_decode(const uint8_t* bytes, int64_t len, float* centroids_out, int64_t capacity_floats, int32_t* M_out,
+                           int32_t* K_out, int32_t* subDim_out);
+/* vs_segment_attach_pq from the stored PQCodebook message (codes == NULL encodes the resident rows on the device) */
+int32_t vs_segment_attach_pq_codebook(uint64_t h, const uint8_t* codebook, int64_t len, const uint8_t* codes);
+/* Residency table keyed by segment id and SegmentMeta.State (vectorsearch.proto:84: 0 ACTIVE, 1 PENDING, 2 SEALED,
+ * 3 COMPACTING, 4 WRITING): upload on PENDING, attach PQ and put again on SEALED.  The table owns the handles it
+ * holds.  put frees a previous copy of the same segment and, with a budget set, least-recently-used segments;
+ * get returns VS_EHANDLE when the segment is not resident and VS_ESTATE (handle_out still set, for an in-place
+ * upgrade) when it is resident in another state; invalidate drops the copy (compaction rebuild,
+ * J/tasks/MaintenanceService.java:388-390, vacuum, segment deletion). */
+int32_t vs_residency_put(int64_t seg_id, int32_t state, uint64_t handle);
+int32_t vs_residency_get(int64_t seg_id, int32_t state, uint64_t* handle_out);
+int32_t vs_residency_invalidate(int64_t seg_id);
+int32_t vs_residency_set_budget(int64_t bytes /* 0 = unlimited */);
+int32_t vs_residency_stats(int64_t* segments_out, int64_t* bytes_out);
 
 /* ---- query operations --------------------------------------------------------------------
  * Outputs are [nq][k] (or [nq][n_cand]); counts_out[i] entries of row i are valid, the rest
@@ -116,6 +164,15 @@ int32_t vs_rerank_topk(uint64_t h, const float* q, const int64_t* cand_ids, int3
 int32_t vs_adc_rerank_topk(uint64_t h, const float* q, int32_t nq, int32_t n_cand, int32_t k,
                            int32_t metric, int32_t normalize_on_read, int64_t* ids_out,
                            double* scores_out, int32_t* counts_out);
+/* BEST_FIRST expansion scoring (J/fdb/FdbVectorIndex.java:741,746-759,950-963): the LUT is built once per (query,
+ * sealed segment) and kept on the device; every expansion step scores an id list against the RESIDENT codes
+ * (pqApproxDistance, bit-exact) instead of reading all codes of the segment into a HashMap per query.  ids without a
+ * code (outside the segment) get valid 0 and distance NaN (the reference skips them, :957).  valid_out is nullable. */
+int32_t vs_adc_query_begin(uint64_t h, const float* q, uint64_t* query_out);
+int32_t vs_adc_query_gather(uint64_t query, const int64_t* ids, int64_t n_ids, double* out, uint8_t* valid_out);
+int32_t vs_adc_query_end(uint64_t query);
+/* the three in one call */
+int32_t vs_adc_gather(uint64_t h, const float* q, const int64_t* ids, int64_t n_ids, double* out, uint8_t* valid_out);
 /* cross-segment merge: stable sort by score descending of lists concatenated in segment order,
  * first k, J/fdb/FdbVectorIndex.java:432-437 */
 int32_t vs_merge_topk(const int64_t* ids, const double* scores, int64_t total, int32_t k,
@@ -144,6 +201,14 @@ typedef int32_t (*vs_allreduce_fn)(void* user, int32_t kind, int64_t count);
 int32_t vs_pq_train_sharded(uint64_t h, int64_t n_total, int64_t row_lo, int32_t rank, int32_t world, int32_t exact_order,
                             int32_t M, int32_t K, int32_t iterations, int64_t seed, float* d_comm_f32, int32_t* d_comm_i32,
                             vs_allreduce_fn allreduce, void* user, float* centroids_out);
+/* The same with the all-reduce done by libvsgpu itself over the peer buffers of `comm` (vs_peer_*): every rank pushes
+ * its [sums | counts] into all peers' buffers over NVLink and a reduce kernel waits for the arrival flags -- no
+ * callback, no collective library, no host synchronisation per reduction.  exact_order != 0: the running sums pass
+ * from rank to rank inside that one exchange (bit-identical centroids); 0: fp32 sums combined in ascending rank order
+ * (deterministic, identical on every rank, re-associated across shards).  Collective over the communicator; every
+ * rank must own at least one row.  The slots of `comm` must hold M * K * (d / M + 1) * 4 bytes. */
+int32_t vs_pq_train_sharded_peer(uint64_t h, uint64_t comm, int64_t n_total, int64_t row_lo, int32_t exact_order, int32_t M,
+                                 int32_t K, int32_t iterations, int64_t seed, float* centroids_out);
 /* PqEncoder.encode over n rows, J/pq/PqEncoder.java:18-37, J/tasks/SegmentBuildService.java:301 */
 int32_t vs_pq_encode_batch(const float* centroids, int32_t M, int32_t K, int32_t subDim,
                            const float* rows, uint64_t h, int64_t n, uint8_t* codes_out);
@@ -173,6 +238,15 @@ int32_t vs_merge_packed_dev(const int64_t* d_gath, int32_t world, int32_t nq, in
  * bits | state (1 scored, 0 dropped by the re-rank: deleted or gid missing, -1 empty slot). */
 int32_t vs_adc_rerank_packed_dev(uint64_t h, const float* d_q, int32_t nq, int32_t n_cand, int32_t metric,
                                  int32_t normalize_on_read, int64_t* d_pack, void* stream);
+/* ADC lists of this shard for a cross-shard merge by ascending approximate distance: d_pack is [nq][2 n_cand] =
+ * ids | approximate distance bits (merge with vs_merge_packed_dev / vs_exchange_merge_packed_dev, descending = 0). */
+int32_t vs_adc_topk_packed_dev(uint64_t h, const float* d_q, int32_t nq, int32_t n_cand, int64_t* d_pack, int32_t* d_counts,
+                               void* stream);
+/* fetchExactAndScore over caller-supplied candidates when the rows are sharded: each shard scores the candidates it
+ * owns; d_pack is [4][n_cand] in the ADC + re-rank layout with the candidate's POSITION as its approximate key, so the
+ * cross-shard merge keeps ties in candidate order (J/fdb/FdbVectorIndex.java:1031). */
+int32_t vs_rerank_packed_dev(uint64_t h, const float* d_q, const int64_t* d_cand, int32_t n_cand, int32_t metric,
+                             int32_t normalize_on_read, int64_t* d_pack, void* stream);
 /* d_gath is the all-gathered [world][nq][4][n_cand] buffer.  Per query: the global first n_cand by
  * (approximate distance, rank, position) -- shards are ascending row ranges, so that is the reference's
  * stable order -- and of those the scored ones by exact score descending, ties in approximate order; first k. */
@@ -186,10 +260,14 @@ int32_t vs_merge_adc_rerank_packed_dev(const int64_t* d_gath, int32_t world, int
  * vs_merge_*_packed_dev": the rank pushes its packed lists into every peer's buffer with plain stores and raises
  * a flag there; the merge kernel waits for the `world` flags of its own buffer and reads local memory only.
  * Results are those of the NCCL path, bit for bit.  Every rank must issue the same exchanges in the same order on
- * corresponding streams (as with any collective).  Each stream a communicator sees gets its own ring of 4 slots,
- * in order of first use, so exchanges on different streams may interleave freely; depth (a multiple of 4) = 4 x the
- * number of streams the communicator will serve -- one more stream is refused with VS_ESTATE.  A peer that never
- * arrives traps the waiting kernel after 20 s instead of hanging the GPU. */
+ * corresponding streams (as with any collective).  Ring 0 (4 slots) belongs to the communicator's own stream, on which
+ * the host-buffer entry points (vs_*_exchange, vs_pq_train_sharded_peer) run whichever thread calls them; every caller
+ * stream the communicator sees through the *_dev entry points gets a ring of its own, in order of first use
+ * (vs_peer_release_stream hands one back).  depth (a multiple of 4) = 4 x (1 + the number of caller streams) -- one
+ * more stream is refused with VS_ESTATE.  A one-query exchange is ONE kernel that publishes and then waits for its
+ * peers: every rank's kernel must be able to run at the same time (one GPU per rank); communicators whose ranks share
+ * a device (vs_peer_connect_ptrs) use the separate publishing kernel instead.  A rank whose shard is empty takes
+ * part with an all-empty list.  A peer that never arrives traps the waiting kernel after 20 s instead of hanging the GPU. */
 #define VS_PEER_HANDLE_BYTES 64
 int32_t vs_peer_create(int32_t rank, int32_t world, int64_t slot_bytes, int32_t depth, uint64_t* comm_out,
                        uint8_t* handle_out /* [VS_PEER_HANDLE_BYTES] */);
@@ -198,6 +276,7 @@ int32_t vs_peer_connect(uint64_t comm, const uint8_t* handles /* [world][VS_PEER
  * GPU): no IPC -- pass the base addresses (vs_peer_base) of all ranks' buffers, peer access already enabled. */
 int32_t vs_peer_base(uint64_t comm, uint64_t* base_out);
 int32_t vs_peer_connect_ptrs(uint64_t comm, const uint64_t* bases /* [world] */);
+int32_t vs_peer_release_stream(uint64_t comm, void* stream);
 int32_t vs_peer_destroy(uint64_t comm);
 int32_t vs_exchange_merge_packed_dev(uint64_t comm, const int64_t* d_pack, int32_t nq, int32_t k, int32_t descending,
                                      int64_t* d_ids_out, double* d_scores_out, int32_t* d_counts_out, void* stream);
@@ -213,6 +292,19 @@ int32_t vs_adc_rerank_topk_exchange(uint64_t h, uint64_t comm, const float* q, i
 int32_t vs_exchange_merge_adc_rerank_packed_dev(uint64_t comm, const int64_t* d_pack, int32_t nq, int32_t n_cand,
                                                 int32_t k, int64_t* d_ids_out, double* d_scores_out,
                                                 int32_t* d_counts_out, void* stream);
+/* The sharded query as ONE stream call per rank (local scan into the stream's packed send buffer, peer exchange, merge;
+ * device or pinned-host outputs, nothing synchronises): what a pipelined coordinator issues per query. */
+int32_t vs_bruteforce_topk_exchange_dev(uint64_t h, uint64_t comm, const float* d_q, int32_t nq, int32_t k, int32_t metric,
+                                        int64_t* d_ids, double* d_scores, int32_t* d_counts, void* stream);
+int32_t vs_adc_rerank_topk_exchange_dev(uint64_t h, uint64_t comm, const float* d_q, int32_t nq, int32_t n_cand, int32_t k,
+                                        int32_t metric, int32_t normalize_on_read, int64_t* d_ids, double* d_scores,
+                                        int32_t* d_counts, void* stream);
+/* Host-buffer forms of the other two query operations over row shards (collective, identical results on every rank) */
+int32_t vs_adc_topk_exchange(uint64_t h, uint64_t comm, const float* q, int32_t nq, int32_t n_cand, int64_t* ids_out,
+                             double* approx_out, int32_t* counts_out);
+int32_t vs_rerank_topk_exchange(uint64_t h, uint64_t comm, const float* q, const int64_t* cand_ids, int32_t n_cand, int32_t k,
+                                int32_t metric, int32_t normalize_on_read, int64_t* ids_out, double* scores_out,
+                                int32_t* count_out);
 int32_t vs_merge_topk_dev(const int64_t* d_ids, const double* d_scores, int64_t total, int32_t k,
                           int64_t* d_ids_out, double* d_scores_out, int32_t* d_count_out, void* stream);
 /* number of kernels this library has launched so far in this process (for gpu_launches) */
@@ -234,7 +326,9 @@ int64_t vs_kernel_launch_count(void);
  * kernel is set up while its predecessor runs and waits, in the kernel, for its results).
  * "pq_tensor_cores": how PQ assignment with 8-float sub-vectors nominates -- 2 (default) tcgen05 on fp16
  * hi/lo operand pairs (pq_tc.cu; needs n * M * 64 bytes of scratch, built slab by slab), 0 the FFMA kernel,
- * 1 mma.sync 3xTF32 (slower on B200, kept as a measured reference point).  "pq_tc_keep_bytes" (default 16 GiB):
+ * 1 mma.sync 3xTF32 (slower on B200, kept as a measured reference point).  "train_exact_order" (default 1): vs_pq_train
+ * on a SHARDED handle continues the cluster sums rank after rank (bit-identical centroids); 0 = one rank-ordered
+ * all-reduce per iteration.  "pq_tc_keep_bytes" (default 16 GiB):
  * how much of that scratch a private stream-ordered pool keeps cached between calls (0 = give everything back at
  * the next synchronisation).  Results never depend on any of them. */
 int32_t vs_set_option(const char* name, int64_t value);

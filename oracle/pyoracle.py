@@ -143,15 +143,32 @@ class Oracle:
                                      _p(out, _u8p), C.c_int(threads))
         return out
 
-    def pq_train(self, rows, D: int, M: int, K: int, iterations: int, seed: int, return_draws=False):
+    def pq_encode_batch_fast(self, centroids, rows, threads: int = 1) -> np.ndarray:
+        """pq_encode_batch with the centroid-major evaluation (bit-identical; for BASELINE-size checks)."""
+        c = _f32(centroids)
+        M, K, sub = c.shape
+        rows = _f32(rows)
+        n = rows.shape[0]
+        out = np.zeros((n, M), dtype=np.uint8)
+        self.lib.vso_pq_encode_batch_fast(_p(c, _f32p), M, K, sub, _p(rows, _f32p), C.c_int64(n),
+                                          _p(out, _u8p), C.c_int(threads))
+        return out
+
+    def pq_train(self, rows, D: int, M: int, K: int, iterations: int, seed: int, return_draws=False,
+                 threads: int = 0):
+        """threads == 0: the literal single-threaded restatement; > 0: vso_pq_train_mt (bit-identical)."""
         rows = _f32(rows).reshape(-1, D) if D > 0 else _f32(rows)
         n = rows.shape[0]
         if M <= 0 or K <= 0 or D <= 0 or D % M != 0:
             raise ValueError("Invalid PQ params (m,k,dimension)")  # IllegalArgumentException
         out = np.zeros((M, K, D // M), dtype=np.float32)
         draws = C.c_int64(0)
-        rc = self.lib.vso_pq_train(_p(rows, _f32p), C.c_int64(n), D, M, K, iterations,
-                                   C.c_int64(seed), _p(out, _f32p), C.byref(draws))
+        if threads > 0:
+            rc = self.lib.vso_pq_train_mt(_p(rows, _f32p), C.c_int64(n), D, M, K, iterations,
+                                          C.c_int64(seed), _p(out, _f32p), C.byref(draws), C.c_int(threads))
+        else:
+            rc = self.lib.vso_pq_train(_p(rows, _f32p), C.c_int64(n), D, M, K, iterations,
+                                       C.c_int64(seed), _p(out, _f32p), C.byref(draws))
         if rc == -1:
             raise ValueError("Invalid PQ params (m,k,dimension)")
         if rc == -2:

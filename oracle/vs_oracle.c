@@ -266,6 +266,160 @@ int vso_pq_train(const float* rows, int64_t n, int D, int M, int K, int iteratio
   return 0;
 }
 
+/* ---- the same trainer with the order-independent parts spread over host threads ----------
+ * Used by the BASELINE-size parity tests (C3: 10M x 128, 5 iterations = 2e11 sub-distances).
+ * Bit-identical to vso_pq_train by construction, and checked against it in tests/:
+ *   - assignment (:56-68): rows are independent; each (row, centroid) distance is the same
+ *     sequence of operations.  For sub-vectors shorter than the SIMD register the vector loop
+ *     of Distances.l2Squared runs zero times (:79 loopBound == 0) and the whole distance is the
+ *     scalar double tail: d = (double)a - (double)b; sum += d * d (:88-91).  That case is laid
+ *     out centroid-major here so that the compiler can evaluate 8 centroids per instruction --
+ *     per (row, centroid) still mul-then-add in double, ascending component order.
+ *   - update (:70-77): every (cluster, component) sum must add its rows in ascending row order.
+ *     Thread t owns the clusters with ci % T == t and walks ALL rows in order, so each chain
+ *     sees exactly the reference's sequence of fp32 additions. */
+static void assign_rows_mt(const float* data, int64_t n, int subDim, const float* C, int K,
+                           int32_t* assign, int threads) {
+  const int L = g_lanes;
+  if (subDim < L && subDim <= 64) {
+    /* centroid-major copy in double: Ct[j][ci] = (double)C[ci][j] (the widening is exact) */
+    double* Ct = (double*)malloc((size_t)subDim * K * sizeof(double));
+    for (int ci = 0; ci < K; ci++)
+      for (int j = 0; j < subDim; j++) Ct[(size_t)j * K + ci] = (double)C[(size_t)ci * subDim + j];
+#pragma omp parallel num_threads(threads > 0 ? threads : 1)
+    {
+      double* dist = (double*)malloc((size_t)K * sizeof(double));
+#pragma omp for schedule(static)
+      for (int64_t i = 0; i < n; i++) {
+        const float* x = data + (size_t)i * subDim;
+        /* sum = (double)reduceLanes(zero lanes) = 0.0; then sum += d*d for j ascending */
+        for (int ci = 0; ci < K; ci++) dist[ci] = 0.0;
+        for (int j = 0; j < subDim; j++) {
+          const double xj = (double)x[j];
+          const double* cj = Ct + (size_t)j * K;
+#pragma omp simd
+          for (int ci = 0; ci < K; ci++) {
+            const double d = xj - cj[ci];
+            dist[ci] = dist[ci] + d * d;
+          }
+        }
+        int best = 0;
+        double bestDist = INFINITY;
+        for (int ci = 0; ci < K; ci++)
+          if (dist[ci] < bestDist) { /* strict <: lowest ci wins ties, NaN never wins */
+            bestDist = dist[ci];
+            best = ci;
+          }
+        assign[i] = best;
+      }
+      free(dist);
+    }
+    free(Ct);
+    return;
+  }
+#pragma omp parallel for schedule(static) num_threads(threads > 0 ? threads : 1)
+  for (int64_t i = 0; i < n; i++) {
+    const float* x = data + (size_t)i * subDim;
+    int best = 0;
+    double bestDist = INFINITY;
+    for (int ci = 0; ci < K; ci++) {
+      double d = vso_l2_squared(x, C + (size_t)ci * subDim, subDim);
+      if (d < bestDist) {
+        bestDist = d;
+        best = ci;
+      }
+    }
+    assign[i] = best;
+  }
+}
+
+int vso_pq_train_mt(const float* rows, int64_t n, int D, int M, int K, int iterations, int64_t seed,
+                    float* centroids_out, int64_t* draws_out, int threads) {
+  if (M <= 0 || K <= 0 || D <= 0) return -1;
+  if (D % M != 0) return -1;
+  if (n <= 0) return -2;
+  if (n > 0x7fffffffLL) return -2;
+  const int T = threads > 0 ? threads : 1;
+  const int subDim = D / M;
+  vso_jrandom rnd;
+  vso_jr_init(&rnd, seed);
+  int64_t draws = 0;
+  float* data = (float*)malloc((size_t)n * subDim * sizeof(float));
+  int32_t* assign = (int32_t*)malloc((size_t)n * sizeof(int32_t));
+  float* newC = (float*)malloc((size_t)K * subDim * sizeof(float));
+  int32_t* counts = (int32_t*)malloc((size_t)K * sizeof(int32_t));
+  for (int s = 0; s < M; s++) {
+    float* C = centroids_out + (size_t)s * K * subDim;
+#pragma omp parallel for schedule(static) num_threads(T)
+    for (int64_t i = 0; i < n; i++)
+      memcpy(data + (size_t)i * subDim, rows + (size_t)i * D + (size_t)s * subDim,
+             (size_t)subDim * sizeof(float));
+    for (int ci = 0; ci < K; ci++) {
+      int32_t idx = vso_jr_next_int_bound(&rnd, (int32_t)n);
+      draws++;
+      memcpy(C + (size_t)ci * subDim, data + (size_t)idx * subDim, (size_t)subDim * sizeof(float));
+    }
+    for (int it = 0; it < iterations; it++) {
+      assign_rows_mt(data, n, subDim, C, K, assign, T);
+      memset(newC, 0, (size_t)K * subDim * sizeof(float));
+      memset(counts, 0, (size_t)K * sizeof(int32_t));
+#pragma omp parallel num_threads(T)
+      {
+#ifdef _OPENMP
+        const int t = omp_get_thread_num(), nt = omp_get_num_threads();
+#else
+        const int t = 0, nt = 1;
+#endif
+        for (int64_t i = 0; i < n; i++) {
+          const int a = assign[i];
+          if (a % nt != t) continue;
+          const float* x = data + (size_t)i * subDim;
+          float* c = newC + (size_t)a * subDim;
+          for (int d = 0; d < subDim; d++) c[d] += x[d];
+          counts[a]++;
+        }
+      }
+      for (int ci = 0; ci < K; ci++) {
+        float* c = newC + (size_t)ci * subDim;
+        if (counts[ci] == 0) {
+          int32_t idx = vso_jr_next_int_bound(&rnd, (int32_t)n);
+          draws++;
+          memcpy(c, data + (size_t)idx * subDim, (size_t)subDim * sizeof(float));
+        } else {
+          for (int d = 0; d < subDim; d++) c[d] /= (float)counts[ci];
+        }
+      }
+      memcpy(C, newC, (size_t)K * subDim * sizeof(float));
+    }
+  }
+  free(data);
+  free(assign);
+  free(newC);
+  free(counts);
+  if (draws_out) *draws_out = draws;
+  return 0;
+}
+
+/* PqEncoder.encode over n rows with the same centroid-major evaluation (BASELINE-size checks) */
+void vso_pq_encode_batch_fast(const float* centroids, int M, int K, int subDim, const float* rows,
+                              int64_t n, uint8_t* codes_out, int threads) {
+  const int D = M * subDim;
+  const int T = threads > 0 ? threads : 1;
+  float* data = (float*)malloc((size_t)n * subDim * sizeof(float));
+  int32_t* assign = (int32_t*)malloc((size_t)n * sizeof(int32_t));
+  for (int s = 0; s < M; s++) {
+#pragma omp parallel for schedule(static) num_threads(T)
+    for (int64_t i = 0; i < n; i++)
+      memcpy(data + (size_t)i * subDim, rows + (size_t)i * D + (size_t)s * subDim,
+             (size_t)subDim * sizeof(float));
+    assign_rows_mt(data, n, subDim, centroids + (size_t)s * K * subDim, K, assign, T);
+#pragma omp parallel for schedule(static) num_threads(T)
+    for (int64_t i = 0; i < n; i++) codes_out[(size_t)i * M + s] = (uint8_t)(assign[i] & 0xFF);
+  }
+  free(data);
+  free(assign);
+}
+
 /* ========================================================================== */
 /* ADC -- J/fdb/FdbVectorIndex.java:1057-1079, :754-769                        */
 /* ========================================================================== */

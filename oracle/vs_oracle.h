@@ -69,6 +69,15 @@ void vso_pq_encode_batch(const float* centroids, int M, int K, int subDim, const
 int vso_pq_train(const float* rows, int64_t n, int D, int M, int K, int iterations, int64_t seed,
                  float* centroids_out, int64_t* draws_out);
 
+/* The same two functions with the order-independent loops spread over `threads` host threads
+ * (assignment per row; per-cluster sums owned by one thread each, rows still in ascending
+ * order).  Bit-identical to the single-threaded restatements (checked in tests/); they exist so
+ * that the BASELINE-size parity tests (10M x 128) finish in seconds. */
+int vso_pq_train_mt(const float* rows, int64_t n, int D, int M, int K, int iterations, int64_t seed,
+                    float* centroids_out, int64_t* draws_out, int threads);
+void vso_pq_encode_batch_fast(const float* centroids, int M, int K, int subDim, const float* rows,
+                              int64_t n, uint8_t* codes_out, int threads);
+
 /* ---- ADC (J/fdb/FdbVectorIndex.java) ---------------------------------------- */
 /* buildLut :1067-1079 -> double[M][K] */
 void vso_build_lut(const float* centroids, int M, int K, int subDim, const float* q, double* lut);

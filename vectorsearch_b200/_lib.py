@@ -29,6 +29,8 @@ SIGNATURES = {
     "vs_version": (i32, []),
     "vs_last_error": (C.c_char_p, []),
     "vs_init": (i32, [i32]),
+    "vs_init_multi": (i32, [i32, i32p]),
+    "vs_device_count": (i32, []),
     "vs_shutdown": (i32, []),
     "vs_set_simd_lanes": (i32, [i32]),
     "vs_get_simd_lanes": (i32, []),
@@ -43,6 +45,8 @@ SIGNATURES = {
     "vs_build_lut": (i32, [f32p, i32, i32, i32, f32p, f64p]),
     "vs_pq_approx_distance": (i32, [f64p, i32, i32, u8p, i64, f64p]),
     "vs_segment_upload": (i32, [f32p, i64, i32, u8p, i64, u64p]),
+    "vs_segment_upload_strided": (i32, [vp, i64, i32, i64, u8p, i64, u64p]),
+    "vs_segment_upload_records": (i32, [vp, i64p, i64, i32, i64, i32p, u64p]),
     "vs_segment_generate": (i32, [i64, i64, i64, i32, i64, u64p]),
     "vs_segment_set_skip": (i32, [u64, u8p]),
     "vs_segment_info": (i32, [u64, i64p, i32p, i32p, i32p, i64p]),
@@ -50,6 +54,18 @@ SIGNATURES = {
     "vs_segment_attach_pq": (i32, [u64, f32p, i32, i32, u8p]),
     "vs_segment_download_codes": (i32, [u64, i64, i64, u8p]),
     "vs_segment_free": (i32, [u64]),
+    "vs_codebook_encode": (i32, [f32p, i32, i32, i32, vp, i64, i64p]),
+    "vs_codebook_decode": (i32, [vp, i64, f32p, i64, i32p, i32p, i32p]),
+    "vs_segment_attach_pq_codebook": (i32, [u64, vp, i64, u8p]),
+    "vs_residency_put": (i32, [i64, i32, u64]),
+    "vs_residency_get": (i32, [i64, i32, u64p]),
+    "vs_residency_invalidate": (i32, [i64]),
+    "vs_residency_set_budget": (i32, [i64]),
+    "vs_residency_stats": (i32, [i64p, i64p]),
+    "vs_adc_query_begin": (i32, [u64, f32p, u64p]),
+    "vs_adc_query_gather": (i32, [u64, i64p, i64, f64p, u8p]),
+    "vs_adc_query_end": (i32, [u64]),
+    "vs_adc_gather": (i32, [u64, f32p, i64p, i64, f64p, u8p]),
     "vs_bruteforce_topk": (i32, [u64, f32p, i32, i32, i32, i64p, f64p, i32p]),
     "vs_adc_topk": (i32, [u64, f32p, i32, i32, i64p, f64p, i32p]),
     "vs_rerank_topk": (i32, [u64, f32p, i64p, i32, i32, i32, i32, i64p, f64p, i32p]),
@@ -57,6 +73,7 @@ SIGNATURES = {
     "vs_merge_topk": (i32, [i64p, f64p, i64, i32, i64p, f64p, i32p]),
     "vs_pq_train": (i32, [f32p, u64, i64, i32, i32, i32, i32, i64, f32p]),
     "vs_pq_train_sharded": (i32, [u64, i64, i64, i32, i32, i32, i32, i32, i32, i64, vp, vp, vp, vp, f32p]),
+    "vs_pq_train_sharded_peer": (i32, [u64, u64, i64, i64, i32, i32, i32, i32, i64, f32p]),
     "vs_pq_encode_batch": (i32, [f32p, i32, i32, i32, f32p, u64, i64, u8p]),
     "vs_bruteforce_topk_dev": (i32, [u64, vp, i32, i32, i32, vp, vp, vp, vp]),
     "vs_adc_topk_dev": (i32, [u64, vp, i32, i32, vp, vp, vp, vp]),
@@ -66,15 +83,22 @@ SIGNATURES = {
     "vs_merge_topk_dev": (i32, [vp, vp, i64, i32, vp, vp, vp, vp]),
     "vs_adc_rerank_packed_dev": (i32, [u64, vp, i32, i32, i32, i32, vp, vp]),
     "vs_merge_adc_rerank_packed_dev": (i32, [vp, i32, i32, i32, i32, vp, vp, vp, vp]),
+    "vs_adc_topk_packed_dev": (i32, [u64, vp, i32, i32, vp, vp, vp]),
+    "vs_rerank_packed_dev": (i32, [u64, vp, vp, i32, i32, i32, vp, vp]),
     "vs_peer_create": (i32, [i32, i32, i64, i32, C.POINTER(u64), vp]),
     "vs_peer_connect": (i32, [u64, vp]),
     "vs_peer_base": (i32, [u64, C.POINTER(u64)]),
     "vs_peer_connect_ptrs": (i32, [u64, C.POINTER(u64)]),
+    "vs_peer_release_stream": (i32, [u64, vp]),
     "vs_peer_destroy": (i32, [u64]),
     "vs_exchange_merge_packed_dev": (i32, [u64, vp, i32, i32, i32, vp, vp, vp, vp]),
     "vs_bruteforce_topk_exchange": (i32, [u64, u64, f32p, i32, i32, i32, i64p, f64p, i32p]),
     "vs_adc_rerank_topk_exchange": (i32, [u64, u64, f32p, i32, i32, i32, i32, i32, i64p, f64p, i32p]),
     "vs_exchange_merge_adc_rerank_packed_dev": (i32, [u64, vp, i32, i32, i32, vp, vp, vp, vp]),
+    "vs_bruteforce_topk_exchange_dev": (i32, [u64, u64, vp, i32, i32, i32, vp, vp, vp, vp]),
+    "vs_adc_rerank_topk_exchange_dev": (i32, [u64, u64, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp]),
+    "vs_adc_topk_exchange": (i32, [u64, u64, f32p, i32, i32, i64p, f64p, i32p]),
+    "vs_rerank_topk_exchange": (i32, [u64, u64, f32p, i64p, i32, i32, i32, i32, i64p, f64p, i32p]),
     "vs_kernel_launch_count": (i64, []),
     "vs_set_option": (i32, [C.c_char_p, i64]),
     "vs_debug_batch_groupmins": (i32, [u64, f32p, i32, i32, f32p, i64, i64p, i32p, f64p]),

@@ -69,6 +69,27 @@ cudaError_t launch_approx_distance(const double* lut, int M, int K, const uint8_
   return cudaGetLastError();
 }
 
+// BEST_FIRST expansion scoring (J/fdb/FdbVectorIndex.java:950-963): pqApproxDistance of the listed ids against the
+// resident codes.  ids outside [id_base, id_base + n) have no code (codeMap.get(nb) == null): valid 0, distance NaN.
+__global__ void adc_gather_kernel(const double* __restrict__ lut, int M, int K, const uint8_t* __restrict__ codes, int64_t n,
+                                  int64_t id_base, const int64_t* __restrict__ ids, int64_t n_ids,
+                                  double* __restrict__ out, uint8_t* __restrict__ valid) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_ids) return;
+  const int64_t row = ids[i] - id_base;
+  const bool ok = row >= 0 && row < n;
+  out[i] = ok ? adc_exact(lut, codes + (size_t)row * M, M, K) : __longlong_as_double(0x7ff8000000000000ll);
+  valid[i] = ok ? 1 : 0;
+}
+
+cudaError_t launch_adc_gather(const double* lut, int M, int K, const uint8_t* codes, int64_t n, int64_t id_base,
+                              const int64_t* ids, int64_t n_ids, double* out, uint8_t* valid, cudaStream_t st) {
+  if (n_ids <= 0) return cudaSuccess;
+  adc_gather_kernel<<<(unsigned)((n_ids + 127) / 128), 128, 0, st>>>(lut, M, K, codes, n, id_base, ids, n_ids, out, valid);
+  count_launch();
+  return cudaGetLastError();
+}
+
 // fp32 estimate vs exact fp64 sum: each fp32 LUT entry is within 2^-24 relative of the double,
 // M-1 fp32 adds of non-negative terms add 2^-24 each -> (M+1) * 2^-24; doubled for slack.
 __device__ __forceinline__ float adc_filter_threshold(const Key& thr, int M) {

@@ -1,6 +1,7 @@
 // api.cu -- the C ABI of libvsgpu (include/vsgpu.h): handle table, per-thread streams and
 // scratch, host<->device staging, launch configuration.  No torch types, no CPU fallback: every
 // compute entry point fails with VS_ECUDA when no device is bound.
+#include <algorithm>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -20,7 +21,13 @@ namespace vs {
 static std::atomic<int64_t> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+// Devices this process drives: slot i -> CUDA ordinal g_devs[i]; slot 0 is the primary device (vs_init(device) binds
+// exactly one).  A host thread works on its default device (a group worker's own GPU, else the primary) unless the
+// call names a segment, which carries the device its rows live on.
 static std::atomic<int> g_device{-1};
+static std::atomic<int> g_ndev{0};
+static int g_devs[VS_MAX_DEVICES] = {};
+static thread_local int t_default_dev = -1;
 static std::atomic<int> g_lanes{16};
 static std::atomic<int64_t> g_adc_fast_min_rows{16384};   // below this the generic ADC kernel runs
 static std::atomic<int64_t> g_adc_fast_cap{4096};         // candidate-list entries per scan CTA
@@ -37,7 +44,7 @@ static std::atomic<int64_t> g_batch_group{0};               // 0 = automatic row
 static std::atomic<int64_t> g_batch_fp16{1};                // nominate on fp16 operand copies (0: the fp32 rows as tf32)
 static int g_sms = 0;
 static std::mutex g_mu;
-static std::unordered_map<uint64_t, Segment*> g_segments;
+static std::unordered_map<uint64_t, std::shared_ptr<Segment>> g_segments;
 static uint64_t g_next_handle = 1;
 
 static thread_local std::string t_err;
@@ -59,6 +66,15 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 
 int lanes() { return g_lanes.load(); }
+void set_thread_device(int cuda_dev) { t_default_dev = cuda_dev; }
+int primary_device() { return g_device.load(); }
+static bool device_registered(int dev) {
+  const int n = g_ndev.load();
+  for (int i = 0; i < n; i++)
+    if (g_devs[i] == dev) return true;
+  return false;
+}
+void set_error(const char* msg) { t_err = msg ? msg : ""; }
 bool pdl_enabled() { return g_pdl.load() != 0; }
 int sm_count() { return g_sms; }
 
@@ -102,7 +118,8 @@ struct ThreadCtx {
   }
   ~ThreadCtx() {
     // process teardown: the context may already be gone; ignore errors
-    if (device >= 0 && g_device.load() == device) {
+    if (device >= 0 && device_registered(device)) {
+      cudaSetDevice(device);
       park();
       for (DevScratch& a : slots) {
         if (a.d_buf) cudaFree(a.d_buf);
@@ -114,7 +131,7 @@ struct ThreadCtx {
     }
   }
 };
-static thread_local ThreadCtx t_ctx;
+static thread_local ThreadCtx t_ctxs[VS_MAX_DEVICES];  // one per CUDA ordinal this thread has worked on
 
 // Makes the device scratch of `stream` the active one (at most MAX_SLOTS streams per host thread; beyond that
 // the least recently bound caller stream is drained and its set is handed over).
@@ -132,6 +149,11 @@ static int ctx_use_stream(ThreadCtx* c, void* stream) {
   if (free_slot < 0) {  // recycle a caller-stream slot (never slot 0, the thread's own stream)
     free_slot = 1 + (c->active >= 1 ? c->active % (ThreadCtx::MAX_SLOTS - 1) : 0);
     cudaError_t e = cudaStreamSynchronize(static_cast<cudaStream_t>(c->slots[free_slot].key));
+    if (e == cudaErrorInvalidResourceHandle || e == cudaErrorContextIsDestroyed) {
+      // the caller has destroyed that stream since: its work is done or abandoned; drain the device instead
+      cudaGetLastError();
+      e = cudaDeviceSynchronize();
+    }
     if (e != cudaSuccess) return cuda_fail(e, "sync (scratch hand-over)");
   }
   c->slots[free_slot].used = true;
@@ -140,10 +162,10 @@ static int ctx_use_stream(ThreadCtx* c, void* stream) {
   return VS_OK;
 }
 
-int ctx_bind(ThreadCtx** out) {
-  const int dev = g_device.load();
+static int ctx_bind_dev(ThreadCtx** out, int dev) {
   if (dev < 0) return fail(VS_ECUDA, "vs_init has not bound a CUDA device (there is no CPU fallback)");
-  ThreadCtx& c = t_ctx;
+  if (dev >= VS_MAX_DEVICES) return fail(VS_ECUDA, "CUDA device ordinal %d is beyond the %d this build supports", dev, VS_MAX_DEVICES);
+  ThreadCtx& c = t_ctxs[dev];
   cudaError_t e = cudaSetDevice(dev);
   if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
   if (c.device != dev) {
@@ -155,6 +177,10 @@ int ctx_bind(ThreadCtx** out) {
   *out = &c;
   return ctx_use_stream(&c, c.stream);
 }
+// the calling thread's default device: a group worker's own GPU, else the primary
+int ctx_bind(ThreadCtx** out) { return ctx_bind_dev(out, t_default_dev >= 0 ? t_default_dev : g_device.load()); }
+// the device a segment's rows live on
+static int ctx_bind_seg(ThreadCtx** out, const Segment* s) { return ctx_bind_dev(out, s->device); }
 
 static int ctx_reserve_dev(ThreadCtx* c, size_t bytes) {
   if (bytes <= c->d_cap) return VS_OK;
@@ -232,29 +258,38 @@ struct Arena {
 };
 
 // ---- segments -----------------------------------------------------------------------------------------
-Segment* seg_lookup(uint64_t h) {
+std::shared_ptr<Segment> seg_lookup(uint64_t h) {
   std::lock_guard<std::mutex> lk(g_mu);
   auto it = g_segments.find(h);
   return it == g_segments.end() ? nullptr : it->second;
 }
-static uint64_t seg_register(Segment* s) {
-  std::lock_guard<std::mutex> lk(g_mu);
-  uint64_t h = g_next_handle++;
-  g_segments[h] = s;
-  return h;
-}
 static void seg_destroy(Segment* s) {
   if (!s) return;
-  if (s->X) cudaFree(s->X);
-  if (s->skip) cudaFree(s->skip);
-  if (s->centroids) cudaFree(s->centroids);
-  if (s->codes) cudaFree(s->codes);
-  for (int m = 0; m < 2; m++) {
-    if (s->ab[m]) cudaFree(s->ab[m]);
-    if (s->stats[m]) cudaFree(s->stats[m]);
+  // A query on another thread may have enqueued work on these buffers without having synchronised yet (the _dev
+  // entry points): the last reference drains the device before the memory goes back.
+  if (device_registered(s->device)) {
+    cudaSetDevice(s->device);
+    cudaDeviceSynchronize();
+    if (s->X) cudaFree(s->X);
+    if (s->skip) cudaFree(s->skip);
+    if (s->centroids) cudaFree(s->centroids);
+    if (s->codes) cudaFree(s->codes);
+    for (int m = 0; m < 2; m++) {
+      if (s->ab[m]) cudaFree(s->ab[m]);
+      if (s->stats[m]) cudaFree(s->stats[m]);
+    }
+    if (s->Xh) cudaFree(s->Xh);
   }
-  if (s->Xh) cudaFree(s->Xh);
   delete s;
+}
+// Handles own one reference; every entry point holds another for the duration of the call, so vs_segment_free on one
+// thread cannot pull the rows from under a query running on another (the fan-out of J/fdb/FdbVectorIndex.java:418-432).
+static uint64_t seg_register(Segment* s) {
+  std::shared_ptr<Segment> sp(s, seg_destroy);
+  std::lock_guard<std::mutex> lk(g_mu);
+  uint64_t h = g_next_handle++;
+  g_segments[h] = std::move(sp);
+  return h;
 }
 
 #define CK(call, what)                                   \
@@ -289,8 +324,11 @@ static int cached_occ(uint64_t key, F compute) {
   g_occ_cache[key] = occ;
   return occ;
 }
+// (kernel attributes such as the dynamic shared-memory opt-in are per device: the current device is part of every key)
 static uint64_t occ_key(int kind, int a, int b, int c, int threads, size_t smem) {
-  uint64_t h = 1469598103934665603ull;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  uint64_t h = 1469598103934665603ull ^ ((uint64_t)(dev + 1) * 0x9e3779b97f4a7c15ull);
   for (uint64_t v : {(uint64_t)kind, (uint64_t)a, (uint64_t)b, (uint64_t)c, (uint64_t)threads, (uint64_t)smem}) {
     h ^= v;
     h *= 1099511628211ull;
@@ -397,7 +435,8 @@ static int bruteforce_dev(ThreadCtx* c, cudaStream_t st, const Segment* s, const
 
 static int adc_dev(cudaStream_t st, const Segment* s, const float* d_q, int nq, int n_cand, double* d_lut,
                    int64_t* d_ids, double* d_approx, int32_t* d_counts, ulonglong2* d_partial,
-                   unsigned long long* d_ticket, unsigned int* d_fs, unsigned long long* d_cand, const AdcPlan& p) {
+                   unsigned long long* d_ticket, unsigned int* d_fs, unsigned long long* d_cand, const AdcPlan& p,
+                   int64_t out_stride = 0) {
   (void)n_cand;
   if (p.fast) {
     // the candidate scratch also carries the per-subspace LUT extremes: [nq * cand_entries][nq * M * 2]
@@ -406,7 +445,7 @@ static int adc_dev(cudaStream_t st, const Segment* s, const float* d_q, int nq, 
     AdcFastLaunch L = p.fastL;
     L.codes = s->codes; L.lut64 = d_lut; L.mm = d_mm; L.nq = nq; L.fs = d_fs; L.cand = d_cand;
     L.partial = d_partial; L.ctrl = d_ticket; L.ids_out = d_ids; L.approx_out = d_approx;
-    L.counts_out = d_counts; L.id_base = s->id_base;
+    L.counts_out = d_counts; L.id_base = s->id_base; L.out_stride = out_stride;
     CK(launch_adc_fast(L, st), "adc fast-scan launch");
     CK(launch_adc_fallback(L, st), "adc fallback launch");
     return VS_OK;
@@ -415,7 +454,7 @@ static int adc_dev(cudaStream_t st, const Segment* s, const float* d_q, int nq, 
   AdcScanLaunch L = p.slow;
   L.codes = s->codes; L.lut64 = d_lut; L.nq = nq;
   L.partial = d_partial; L.ctrl = d_ticket; L.ids_out = d_ids; L.approx_out = d_approx;
-  L.counts_out = d_counts; L.id_base = s->id_base;
+  L.counts_out = d_counts; L.id_base = s->id_base; L.out_stride = out_stride;
   CK(launch_adc_scan(L, st), "adc scan launch");
   return VS_OK;
 }
@@ -598,7 +637,11 @@ extern "C" {
 int32_t vs_version(void) { return 100; }
 const char* vs_last_error(void) { return t_err.c_str(); }
 
-int32_t vs_init(int32_t device) {
+// Binds the devices this process drives.  One device: everything runs on it.  Several (one JVM, all GPUs of the box):
+// slot 0 is the primary (pair operations, host-row builds), vs_segment_upload shards rows across all of them and the
+// query / build entry points fan out on one worker thread per GPU (group.cu) -- no torch, no second process.
+int32_t vs_init_multi(int32_t n_gpus, const int32_t* device_ids) {
+  if (n_gpus < 1 || n_gpus > VS_MAX_DEVICES || !device_ids) return fail(VS_EINVAL, "n_gpus must be in 1..%d", VS_MAX_DEVICES);
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
   if (e != cudaSuccess || count <= 0) {
@@ -606,28 +649,59 @@ int32_t vs_init(int32_t device) {
     return fail(VS_ECUDA, "no usable CUDA device (%s); libvsgpu has no CPU fallback",
                 e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
   }
-  if (device < 0 || device >= count) return fail(VS_EINVAL, "device %d out of range (0..%d)", device, count - 1);
-  CK(cudaSetDevice(device), "cudaSetDevice");
-  cudaDeviceProp prop;
-  CK(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties");
-  if (prop.major < 10) return fail(VS_ECUDA, "device %d is sm_%d%d; libvsgpu is built for sm_100a only", device, prop.major, prop.minor);
-  g_sms = prop.multiProcessorCount;
-  g_device.store(device);
+  int sms = 0;
+  for (int i = 0; i < n_gpus; i++) {
+    const int device = device_ids[i];
+    if (device < 0 || device >= count) return fail(VS_EINVAL, "device %d out of range (0..%d)", device, count - 1);
+    if (device >= VS_MAX_DEVICES) return fail(VS_EINVAL, "device ordinal %d is beyond the %d this build supports", device, VS_MAX_DEVICES);
+    for (int j = 0; j < i; j++)
+      if (device_ids[j] == device) return fail(VS_EINVAL, "device %d listed twice", device);
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties");
+    if (prop.major < 10) return fail(VS_ECUDA, "device %d is sm_%d%d; libvsgpu is built for sm_100a only", device, prop.major, prop.minor);
+    if (i > 0 && prop.multiProcessorCount != sms) return fail(VS_EINVAL, "the devices of a group must be identical (SM counts differ)");
+    sms = prop.multiProcessorCount;
+  }
+  // re-binding: a previous group (its workers, communicators and sharded segments) goes first
+  if (group_size() > 0) RET(group_stop());
+  // a device that stays bound keeps its resident segments; others must not leave segments behind
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (auto& kv : g_segments) {
+      bool stays = false;
+      for (int i = 0; i < n_gpus; i++) stays = stays || device_ids[i] == kv.second->device;
+      if (!stays) return fail(VS_ESTATE, "device %d still holds resident segments: free them (or vs_shutdown) before re-binding", kv.second->device);
+    }
+  }
+  CK(cudaSetDevice(device_ids[0]), "cudaSetDevice");
+  g_sms = sms;
+  for (int i = 0; i < n_gpus; i++) g_devs[i] = device_ids[i];
+  g_ndev.store(n_gpus);
+  g_device.store(device_ids[0]);
+  if (n_gpus > 1) {
+    int r = group_start(n_gpus, device_ids);
+    if (r != VS_OK) {  // fall back to nothing: the caller sees the failure
+      g_ndev.store(1);
+      return r;
+    }
+  }
   return VS_OK;
 }
 
+int32_t vs_init(int32_t device) { return vs_init_multi(1, &device); }
+
+int32_t vs_device_count(void) { return g_ndev.load(); }
+
 int32_t vs_shutdown(void) {
-  std::vector<Segment*> segs;
+  residency_clear();
+  if (group_size() > 0) group_stop();
+  std::vector<std::shared_ptr<Segment>> segs;
   {
     std::lock_guard<std::mutex> lk(g_mu);
-    for (auto& kv : g_segments) segs.push_back(kv.second);
+    for (auto& kv : g_segments) segs.push_back(std::move(kv.second));
     g_segments.clear();
   }
-  if (g_device.load() >= 0) {
-    cudaSetDevice(g_device.load());
-    cudaDeviceSynchronize();
-    for (Segment* s : segs) seg_destroy(s);
-  }
+  segs.clear();  // seg_destroy drains each segment's device first
   return VS_OK;
 }
 
@@ -651,12 +725,18 @@ int32_t vs_device_info(int32_t* sm_count_, int64_t* free_bytes, int64_t* total_b
 
 int64_t vs_kernel_launch_count(void) { return g_launches.load(); }
 
+#ifdef VS_DEBUG_EXPORTS  // development builds only (make EXTRA=-DVS_DEBUG_EXPORTS): not part of the product ABI
 int32_t vs_debug_adc_stats(uint32_t* out8) { return vs::debug_adc_stats(out8) == 0 ? VS_OK : VS_ECUDA; }
+#endif
 
 int32_t vs_set_option(const char* name, int64_t value) {
   if (!name) return fail(VS_EINVAL, "null option name");
   if (!strcmp(name, "peer_fused")) {
     g_peer_fused.store(value != 0 ? 1 : 0);
+    return VS_OK;
+  }
+  if (!strcmp(name, "train_exact_order")) {
+    group_set_train_exact(value != 0);
     return VS_OK;
   }
   if (!strcmp(name, "pq_tc_keep_bytes")) {
@@ -838,6 +918,7 @@ static int seg_new(int64_t n, int32_t d, int64_t id_base, Segment** out) {
   s->n = n;
   s->d = d;
   s->id_base = id_base;
+  cudaGetDevice(&s->device);  // the calling thread's context is bound (ctx_bind)
   if (n > 0) {
     cudaError_t e = cudaMalloc(&s->X, (size_t)n * d * 4);
     if (e != cudaSuccess) {
@@ -875,6 +956,7 @@ static int seg_set_skip(ThreadCtx* c, Segment* s, const uint8_t* skip_mask) {
 int32_t vs_segment_upload(const float* rows, int64_t n, int32_t d, const uint8_t* skip_mask,
                           int64_t id_base, uint64_t* handle_out) {
   if (!handle_out || (!rows && n > 0)) return fail(VS_EINVAL, "null pointer");
+  if (group_wants_sharding()) return group_segment_upload(rows, n, d, skip_mask, id_base, handle_out);
   ThreadCtx* c;
   RET(ctx_bind(&c));
   Segment* s;
@@ -896,9 +978,156 @@ int32_t vs_segment_upload(const float* rows, int64_t n, int32_t d, const uint8_t
   return VS_OK;
 }
 
+// Rows as they sit in the reference's storage: packed little-endian fp32 (FloatPacker.floatsToBytes,
+// J/util/FloatPacker.java:21-25 -- the bytes of VectorRecord.embedding, vectorsearch.proto:114-117), `stride` bytes
+// from one record's embedding to the next (>= d * 4).  The bytes ARE the device layout: one strided copy, no decode.
+int32_t vs_segment_upload_strided(const uint8_t* bytes, int64_t n, int32_t d, int64_t stride, const uint8_t* skip_mask,
+                                  int64_t id_base, uint64_t* handle_out) {
+  if (!handle_out || (!bytes && n > 0)) return fail(VS_EINVAL, "null pointer");
+  if (d <= 0 || n < 0 || stride < (int64_t)d * 4) return fail(VS_EINVAL, "need d > 0, n >= 0 and stride >= d * 4");
+  if (group_wants_sharding()) return group_segment_upload_strided(bytes, n, d, stride, skip_mask, id_base, handle_out);
+  ThreadCtx* c;
+  RET(ctx_bind(&c));
+  Segment* s;
+  RET(seg_new(n, d, id_base, &s));
+  if (n > 0) {
+    cudaError_t e = cudaMemcpy2DAsync(s->X, (size_t)d * 4, bytes, (size_t)stride, (size_t)d * 4, (size_t)n, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) {
+      seg_destroy(s);
+      return cuda_fail(e, "H2D rows (strided)");
+    }
+  }
+  int r = seg_set_skip(c, s, skip_mask);
+  if (r != VS_OK) {
+    seg_destroy(s);
+    return r;
+  }
+  *handle_out = seg_register(s);
+  return VS_OK;
+}
+
+// ---- serialized VectorRecord messages (vectorsearch.proto:108-127) ---------------------------------------------
+// proto3 wire format: tag = (field << 3) | type; type 0 varint, 1 fixed64, 2 length-delimited, 5 fixed32.
+namespace {
+inline bool pb_varint(const uint8_t*& p, const uint8_t* end, uint64_t* v) {
+  uint64_t r = 0;
+  for (int shift = 0; shift < 64 && p < end; shift += 7) {
+    const uint8_t b = *p++;
+    r |= (uint64_t)(b & 0x7f) << shift;
+    if (!(b & 0x80)) {
+      *v = r;
+      return true;
+    }
+  }
+  return false;
+}
+struct RecordView {
+  const uint8_t* emb = nullptr;
+  uint64_t emb_len = 0;
+  int32_t vec_id = 0;
+  bool deleted = false;
+};
+// walks one VectorRecord: seg_id = 1, vec_id = 2, embedding = 3 (bytes), deleted = 4 (bool), payload = 5; unknown
+// fields are skipped as protobuf requires; the LAST occurrence of a field wins (protobuf merge semantics)
+inline bool pb_vector_record(const uint8_t* p, const uint8_t* end, RecordView* out) {
+  while (p < end) {
+    uint64_t tag;
+    if (!pb_varint(p, end, &tag)) return false;
+    const uint32_t field = (uint32_t)(tag >> 3), type = (uint32_t)(tag & 7);
+    uint64_t v = 0;
+    switch (type) {
+      case 0:
+        if (!pb_varint(p, end, &v)) return false;
+        if (field == 2) out->vec_id = (int32_t)v;
+        if (field == 4) out->deleted = v != 0;
+        break;
+      case 1:
+        if (end - p < 8) return false;
+        p += 8;
+        break;
+      case 2:
+        if (!pb_varint(p, end, &v) || (uint64_t)(end - p) < v) return false;
+        if (field == 3) {
+          out->emb = p;
+          out->emb_len = v;
+        }
+        p += v;
+        break;
+      case 5:
+        if (end - p < 4) return false;
+        p += 4;
+        break;
+      default:
+        return false;  // groups are not used by this schema
+    }
+  }
+  return true;
+}
+}  // namespace
+
+// Consumes the stored VectorRecord values of a segment as they come out of the range read
+// (J/fdb/FdbVectorIndex.java:676-699): record i is buf[offsets[i] .. offsets[i+1]).  Embeddings go to the device through
+// pinned staging in slabs (no float[] is ever materialised), `deleted` becomes the row's skip flag (:681), vec_ids_out
+// (nullable, [n]) receives each row's vec_id so that the caller can map rows back to gids.
+int32_t vs_segment_upload_records(const uint8_t* buf, const int64_t* offsets, int64_t n, int32_t d, int64_t id_base,
+                                  int32_t* vec_ids_out, uint64_t* handle_out) {
+  if (!handle_out || ((!buf || !offsets) && n > 0)) return fail(VS_EINVAL, "null pointer");
+  if (d <= 0 || n < 0) return fail(VS_EINVAL, "need d > 0 and n >= 0");
+  if (group_wants_sharding()) return group_segment_upload_records(buf, offsets, n, d, id_base, vec_ids_out, handle_out);
+  ThreadCtx* c;
+  RET(ctx_bind(&c));
+  Segment* s;
+  RET(seg_new(n, d, id_base, &s));
+  std::vector<uint8_t> skip((size_t)n, 0);
+  bool any_deleted = false;
+  const size_t row_b = (size_t)d * 4;
+  int64_t slab = (int64_t)((size_t(16) << 20) / row_b);
+  if (slab < 1) slab = 1;
+  int r = ctx_reserve_host(c, 2 * (size_t)slab * row_b);
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  cudaError_t e = cudaSuccess;
+  for (int i = 0; i < 2 && r == VS_OK && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
+  for (int64_t r0 = 0, b = 0; r == VS_OK && e == cudaSuccess && r0 < n; r0 += slab, b ^= 1) {
+    const int64_t cnt = std::min<int64_t>(slab, n - r0);
+    uint8_t* stage = static_cast<uint8_t*>(c->h_buf) + (size_t)b * slab * row_b;
+    if (r0 >= 2 * slab) e = cudaEventSynchronize(ev[b]);  // the copy that last used this half has finished
+    for (int64_t i = 0; i < cnt && r == VS_OK; i++) {
+      const int64_t o0 = offsets[r0 + i], o1 = offsets[r0 + i + 1];
+      RecordView rv;
+      if (o1 < o0 || !pb_vector_record(buf + o0, buf + o1, &rv)) {
+        r = fail(VS_EINVAL, "record %lld is not a valid VectorRecord message", (long long)(r0 + i));
+      } else if (rv.emb_len != row_b) {
+        r = fail(VS_EINVAL, "record %lld: embedding holds %llu bytes, dimension %d needs %zu", (long long)(r0 + i),
+                 (unsigned long long)rv.emb_len, d, row_b);
+      } else {
+        memcpy(stage + (size_t)i * row_b, rv.emb, row_b);
+        skip[(size_t)(r0 + i)] = rv.deleted ? 1 : 0;
+        any_deleted = any_deleted || rv.deleted;
+        if (vec_ids_out) vec_ids_out[r0 + i] = rv.vec_id;
+      }
+    }
+    if (r != VS_OK || e != cudaSuccess) break;
+    e = cudaMemcpyAsync(s->X + (size_t)r0 * d, stage, (size_t)cnt * row_b, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaEventRecord(ev[b], c->stream);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  for (int i = 0; i < 2; i++)
+    if (ev[i]) cudaEventDestroy(ev[i]);
+  if (r == VS_OK && e != cudaSuccess) r = cuda_fail(e, "H2D rows (records)");
+  if (r == VS_OK && any_deleted) r = seg_set_skip(c, s, skip.data());
+  if (r != VS_OK) {
+    seg_destroy(s);
+    return r;
+  }
+  *handle_out = seg_register(s);
+  return VS_OK;
+}
+
 int32_t vs_segment_generate(int64_t seed, int64_t first_row, int64_t n, int32_t d, int64_t id_base,
                             uint64_t* handle_out) {
   if (!handle_out || first_row < 0) return fail(VS_EINVAL, "null pointer or negative first_row");
+  if (group_wants_sharding()) return group_segment_generate(seed, first_row, n, d, id_base, handle_out);
   ThreadCtx* c;
   RET(ctx_bind(&c));
   Segment* s;
@@ -914,15 +1143,19 @@ int32_t vs_segment_generate(int64_t seed, int64_t first_row, int64_t n, int32_t 
 }
 
 int32_t vs_segment_set_skip(uint64_t h, const uint8_t* skip_mask) {
-  ThreadCtx* c;
-  RET(ctx_bind(&c));
-  Segment* s = seg_lookup(h);
+  if (group_is_sharded(h)) return group_segment_set_skip(h, skip_mask);
+  std::shared_ptr<Segment> s_ref = seg_lookup(h);
+  Segment* s = s_ref.get();
   if (!s) return fail(VS_EHANDLE, "unknown segment handle");
+  ThreadCtx* c;
+  RET(ctx_bind_seg(&c, s));
   return seg_set_skip(c, s, skip_mask);
 }
 
 int32_t vs_segment_info(uint64_t h, int64_t* n, int32_t* d, int32_t* M, int32_t* K, int64_t* id_base) {
-  Segment* s = seg_lookup(h);
+  if (group_is_sharded(h)) return group_segment_info(h, n, d, M, K, id_base);
+  std::shared_ptr<Segment> s_ref = seg_lookup(h);
+  Segment* s = s_ref.get();
   if (!s) return fail(VS_EHANDLE, "unknown segment handle");
   if (n) *n = s->n;
   if (d) *d = s->d;
@@ -933,10 +1166,12 @@ int32_t vs_segment_info(uint64_t h, int64_t* n, int32_t* d, int32_t* M, int32_t*
 }
 
 int32_t vs_segment_download_rows(uint64_t h, int64_t first, int64_t count, float* rows_out) {
-  ThreadCtx* c;
-  RET(ctx_bind(&c));
-  Segment* s = seg_lookup(h);
+  if (group_is_sharded(h)) return group_segment_download_rows(h, first, count, rows_out);
+  std::shared_ptr<Segment> s_ref = seg_lookup(h);
+  Segment* s = s_ref.get();
   if (!s) return fail(VS_EHANDLE, "unknown segment handle");
+  ThreadCtx* c;
+  RET(ctx_bind_seg(&c, s));
   if (first < 0 || count < 0 || first + count > s->n || (!rows_out && count > 0)) return fail(VS_EINVAL, "row range out of bounds");
   if (count == 0) return VS_OK;
   CK(cudaMemcpyAsync(rows_out, s->X + (size_t)first * s->d, (size_t)count * s->d * 4, cudaMemcpyDeviceToHost, c->stream), "D2H rows");
@@ -945,10 +1180,12 @@ int32_t vs_segment_download_rows(uint64_t h, int64_t first, int64_t count, float
 }
 
 int32_t vs_segment_attach_pq(uint64_t h, const float* centroids, int32_t M, int32_t K, const uint8_t* codes) {
-  ThreadCtx* c;
-  RET(ctx_bind(&c));
-  Segment* s = seg_lookup(h);
+  if (group_is_sharded(h)) return group_segment_attach_pq(h, centroids, M, K, codes);
+  std::shared_ptr<Segment> s_ref = seg_lookup(h);
+  Segment* s = s_ref.get();
   if (!s) return fail(VS_EHANDLE, "unknown segment handle");
+  ThreadCtx* c;
+  RET(ctx_bind_seg(&c, s));
   if (!centroids) return fail(VS_EINVAL, "null centroids");
   if (M <= 0 || K <= 0 || s->d % M != 0) return fail(VS_EINVAL, "Invalid PQ params (m,k,dimension)");
   const int subDim = s->d / M;
@@ -980,10 +1217,12 @@ int32_t vs_segment_attach_pq(uint64_t h, const float* centroids, int32_t M, int3
 }
 
 int32_t vs_segment_download_codes(uint64_t h, int64_t first, int64_t count, uint8_t* codes_out) {
-  ThreadCtx* c;
-  RET(ctx_bind(&c));
-  Segment* s = seg_lookup(h);
+  if (group_is_sharded(h)) return group_segment_download_codes(h, first, count, codes_out);
+  std::shared_ptr<Segment> s_ref = seg_lookup(h);
+  Segment* s = s_ref.get();
   if (!s) return fail(VS_EHANDLE, "unknown segment handle");
+  ThreadCtx* c;
+  RET(ctx_bind_seg(&c, s));
   if (s->M == 0) return fail(VS_ESTATE, "segment has no PQ attached");
   if (first < 0 || count < 0 || first + count > s->n || (!codes_out && count > 0)) return fail(VS_EINVAL, "row range out of bounds");
   if (count == 0) return VS_OK;
@@ -993,19 +1232,18 @@ int32_t vs_segment_download_codes(uint64_t h, int64_t first, int64_t count, uint
 }
 
 int32_t vs_segment_free(uint64_t h) {
-  Segment* s = nullptr;
+  if (group_is_sharded(h)) return group_segment_free(h);
+  std::shared_ptr<Segment> sp;
   {
     std::lock_guard<std::mutex> lk(g_mu);
     auto it = g_segments.find(h);
     if (it == g_segments.end()) return fail(VS_EHANDLE, "unknown segment handle");
-    s = it->second;
+    sp = std::move(it->second);
     g_segments.erase(it);
   }
-  if (g_device.load() >= 0) {
-    cudaSetDevice(g_device.load());
-    cudaDeviceSynchronize();
-  }
-  seg_destroy(s);
+  // the memory goes back when the last holder lets go (seg_destroy): a query still running on another thread
+  // keeps the rows alive until it returns
+  sp.reset();
   return VS_OK;
 }
 
@@ -1017,11 +1255,13 @@ static const size_t PARTIAL_BUDGET = size_t(192) << 20;
 
 int32_t vs_bruteforce_topk(uint64_t h, const float* q, int32_t nq, int32_t k, int32_t metric,
                            int64_t* ids_out, double* scores_out, int32_t* counts_out) {
-  Segment* s = seg_lookup(h);
+  if (group_is_sharded(h)) return group_bruteforce_topk(h, q, nq, k, metric, ids_out, scores_out, counts_out);
+  std::shared_ptr<Segment> s_ref = seg_lookup(h);
+  Segment* s = s_ref.get();
   RET(check_query_args(s, q, nq, k, metric));
   if (!ids_out || !scores_out) return fail(VS_EINVAL, "null output pointer");
   ThreadCtx* c;
-  RET(ctx_bind(&c));
+  RET(ctx_bind_seg(&c, s));
   if (s->n == 0) {
     fill_empty(ids_out, scores_out, counts_out, nq, k);
     return VS_OK;
@@ -1112,13 +1352,14 @@ int32_t vs_bruteforce_topk(uint64_t h, const float* q, int32_t nq, int32_t k, in
 
 static int adc_common(uint64_t h, const float* q, int32_t nq, int32_t n_cand, bool rerank, int32_t k,
                       int32_t metric, int64_t* ids_out, double* scores_out, int32_t* counts_out) {
-  Segment* s = seg_lookup(h);
+  std::shared_ptr<Segment> s_ref = seg_lookup(h);
+  Segment* s = s_ref.get();
   RET(check_query_args(s, q, nq, n_cand, rerank ? metric : VS_METRIC_L2));
   if (rerank && (k <= 0 || k > TOPK_MAX_K)) return fail(VS_EINVAL, "k must be in 1..%d", TOPK_MAX_K);
   if (!ids_out || !scores_out) return fail(VS_EINVAL, "null output pointer");
   if (s->M == 0) return fail(VS_ESTATE, "segment has no PQ attached");
   ThreadCtx* c;
-  RET(ctx_bind(&c));
+  RET(ctx_bind_seg(&c, s));
   const int kout = rerank ? k : n_cand;
   if (s->n == 0) {
     fill_empty(ids_out, scores_out, counts_out, nq, kout);
@@ -1183,12 +1424,15 @@ static int adc_common(uint64_t h, const float* q, int32_t nq, int32_t n_cand, bo
 
 int32_t vs_adc_topk(uint64_t h, const float* q, int32_t nq, int32_t n_cand, int64_t* ids_out,
                     double* approx_out, int32_t* counts_out) {
+  if (group_is_sharded(h)) return group_adc_topk(h, q, nq, n_cand, ids_out, approx_out, counts_out);
   return adc_common(h, q, nq, n_cand, false, 0, VS_METRIC_L2, ids_out, approx_out, counts_out);
 }
 
 int32_t vs_adc_rerank_topk(uint64_t h, const float* q, int32_t nq, int32_t n_cand, int32_t k, int32_t metric,
                            int32_t normalize_on_read, int64_t* ids_out, double* scores_out,
                            int32_t* counts_out) {
+  if (group_is_sharded(h))
+    return group_adc_rerank_topk(h, q, nq, n_cand, k, metric, normalize_on_read, ids_out, scores_out, counts_out);
   (void)normalize_on_read;  // same arithmetic either way (J/fdb/FdbVectorIndex.java:1006-1012)
   return adc_common(h, q, nq, n_cand, true, k, metric, ids_out, scores_out, counts_out);
 }
@@ -1196,15 +1440,18 @@ int32_t vs_adc_rerank_topk(uint64_t h, const float* q, int32_t nq, int32_t n_can
 int32_t vs_rerank_topk(uint64_t h, const float* q, const int64_t* cand_ids, int32_t n_cand, int32_t k,
                        int32_t metric, int32_t normalize_on_read, int64_t* ids_out, double* scores_out,
                        int32_t* count_out) {
+  if (group_is_sharded(h))
+    return group_rerank_topk(h, q, cand_ids, n_cand, k, metric, normalize_on_read, ids_out, scores_out, count_out);
   (void)normalize_on_read;
-  Segment* s = seg_lookup(h);
+  std::shared_ptr<Segment> s_ref = seg_lookup(h);
+  Segment* s = s_ref.get();
   if (!s) return fail(VS_EHANDLE, "unknown segment handle");
   if (!q || !ids_out || !scores_out || (!cand_ids && n_cand > 0)) return fail(VS_EINVAL, "null pointer");
   if (n_cand < 0 || n_cand > 8192) return fail(VS_EINVAL, "n_cand must be in 0..8192");
   if (k <= 0 || k > TOPK_MAX_K) return fail(VS_EINVAL, "k must be in 1..%d", TOPK_MAX_K);
   if (metric != VS_METRIC_L2 && metric != VS_METRIC_COSINE) return fail(VS_EINVAL, "unknown metric %d", metric);
   ThreadCtx* c;
-  RET(ctx_bind(&c));
+  RET(ctx_bind_seg(&c, s));
   if (n_cand == 0 || s->n == 0) {
     fill_empty(ids_out, scores_out, count_out, 1, k);
     return VS_OK;
@@ -1274,6 +1521,124 @@ int32_t vs_merge_topk(const int64_t* ids, const double* scores, int64_t total, i
   return VS_OK;
 }
 
+// ---- BEST_FIRST expansion scoring: approximate distances of listed ids against the resident codes -------------
+// The reference builds the LUT once per (query, sealed segment) (J/fdb/FdbVectorIndex.java:741), reads ALL codes of
+// the segment into a HashMap (:746-759) and then scores frontier neighbours one at a time (:950-963).  Here the codes
+// are already resident: vs_adc_query_begin builds the LUT on the device and keeps it, vs_adc_query_gather scores an
+// id list per expansion step, vs_adc_query_end releases the LUT.
+namespace {
+struct AdcQuery {
+  std::shared_ptr<Segment> seg;      // plain handle: the LUT lives on the segment's device
+  double* d_lut = nullptr;           // [M][K]
+  std::vector<uint64_t> shard_q;     // sharded handle: one context per shard
+  uint64_t sharded = 0;
+};
+std::mutex g_aq_mu;
+std::unordered_map<uint64_t, std::shared_ptr<AdcQuery>> g_aq;
+uint64_t g_aq_next = 0x4151000000000001ull;  // "AQ"
+std::shared_ptr<AdcQuery> aq_lookup(uint64_t qh) {
+  std::lock_guard<std::mutex> g(g_aq_mu);
+  auto it = g_aq.find(qh);
+  return it == g_aq.end() ? nullptr : it->second;
+}
+}  // namespace
+
+int32_t vs_adc_query_begin(uint64_t h, const float* q, uint64_t* query_out) {
+  if (!q || !query_out) return fail(VS_EINVAL, "null pointer");
+  auto aq = std::make_shared<AdcQuery>();
+  if (group_is_sharded(h)) {
+    RET(group_adc_query_begin(h, q, &aq->shard_q));
+    aq->sharded = h;
+  } else {
+    aq->seg = seg_lookup(h);
+    Segment* s = aq->seg.get();
+    if (!s) return fail(VS_EHANDLE, "unknown segment handle");
+    if (s->M == 0) return fail(VS_ESTATE, "segment has no PQ attached");
+    ThreadCtx* c;
+    RET(ctx_bind_seg(&c, s));
+    const size_t qb = (size_t)s->d * 4;
+    RET(ctx_reserve_dev(c, Arena::need({qb})));
+    RET(ctx_reserve_host(c, qb));
+    CK(cudaMalloc(&aq->d_lut, (size_t)s->M * s->K * 8), "cudaMalloc(lut)");
+    float* dq = static_cast<float*>(c->d_buf);
+    memcpy(c->h_buf, q, qb);
+    cudaError_t e = cudaMemcpyAsync(dq, c->h_buf, qb, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = launch_build_lut(s->centroids, s->M, s->K, s->subDim, dq, 1, lanes(), aq->d_lut, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) {
+      cudaFree(aq->d_lut);
+      return cuda_fail(e, "build_lut");
+    }
+  }
+  std::lock_guard<std::mutex> g(g_aq_mu);
+  *query_out = g_aq_next++;
+  g_aq[*query_out] = aq;
+  return VS_OK;
+}
+
+int32_t vs_adc_query_gather(uint64_t query, const int64_t* ids, int64_t n_ids, double* out, uint8_t* valid_out) {
+  std::shared_ptr<AdcQuery> aq = aq_lookup(query);
+  if (!aq) return fail(VS_EHANDLE, "unknown ADC query context");
+  if (n_ids < 0 || ((!ids || !out) && n_ids > 0)) return fail(VS_EINVAL, "null pointer or negative count");
+  if (n_ids == 0) return VS_OK;
+  if (aq->sharded) return group_adc_query_gather(aq->sharded, aq->shard_q, ids, n_ids, out, valid_out);
+  Segment* s = aq->seg.get();
+  ThreadCtx* c;
+  RET(ctx_bind_seg(&c, s));
+  const size_t ib = (size_t)n_ids * 8, ob = (size_t)n_ids * 8, vb = (size_t)n_ids;
+  RET(ctx_reserve_dev(c, Arena::need({ib, ob, vb})));
+  RET(ctx_reserve_host(c, Arena::need({ib, ob, vb})));
+  Arena A(c->d_buf), H(c->h_buf);
+  int64_t* dids = A.take<int64_t>(n_ids);
+  double* dout = A.take<double>(n_ids);
+  uint8_t* dval = A.take<uint8_t>(n_ids);
+  int64_t* hids = H.take<int64_t>(n_ids);
+  double* hout = H.take<double>(n_ids);
+  uint8_t* hval = H.take<uint8_t>(n_ids);
+  memcpy(hids, ids, ib);
+  CK(cudaMemcpyAsync(dids, hids, ib, cudaMemcpyHostToDevice, c->stream), "H2D ids");
+  // short lists: the kernel writes the pinned staging buffer itself (device-visible under UVA)
+  const bool direct = n_ids <= 4096;
+  CK(launch_adc_gather(aq->d_lut, s->M, s->K, s->codes, s->n, s->id_base, dids, n_ids, direct ? hout : dout,
+                       direct ? hval : dval, c->stream), "adc gather launch");
+  if (!direct) {
+    CK(cudaMemcpyAsync(hout, dout, ob, cudaMemcpyDeviceToHost, c->stream), "D2H distances");
+    CK(cudaMemcpyAsync(hval, dval, vb, cudaMemcpyDeviceToHost, c->stream), "D2H valid");
+  }
+  CK(cudaStreamSynchronize(c->stream), "sync");
+  memcpy(out, hout, ob);
+  if (valid_out) memcpy(valid_out, hval, vb);
+  return VS_OK;
+}
+
+int32_t vs_adc_query_end(uint64_t query) {
+  std::shared_ptr<AdcQuery> aq;
+  {
+    std::lock_guard<std::mutex> g(g_aq_mu);
+    auto it = g_aq.find(query);
+    if (it == g_aq.end()) return fail(VS_EHANDLE, "unknown ADC query context");
+    aq = it->second;
+    g_aq.erase(it);
+  }
+  if (aq->sharded) return group_adc_query_end(aq->shard_q);
+  if (aq->d_lut && device_registered(aq->seg->device)) {
+    cudaSetDevice(aq->seg->device);
+    cudaFree(aq->d_lut);  // (implicitly waits for the device)
+  }
+  return VS_OK;
+}
+
+// one-shot form: LUT, gather, release
+int32_t vs_adc_gather(uint64_t h, const float* q, const int64_t* ids, int64_t n_ids, double* out, uint8_t* valid_out) {
+  uint64_t qh = 0;
+  RET(vs_adc_query_begin(h, q, &qh));
+  const int r = vs_adc_query_gather(qh, ids, n_ids, out, valid_out);
+  std::string msg = r != VS_OK ? t_err : std::string();
+  vs_adc_query_end(qh);
+  if (r != VS_OK) t_err = msg;
+  return r;
+}
+
 // =================================================================================================
 // build operations
 // =================================================================================================
@@ -1282,7 +1647,8 @@ int32_t vs_merge_topk(const int64_t* ids, const double* scores, int64_t total, i
 int32_t vs_pq_train_sharded(uint64_t h, int64_t n_total, int64_t row_lo, int32_t rank, int32_t world, int32_t exact_order,
                             int32_t M, int32_t K, int32_t iterations, int64_t seed, float* d_comm_f32, int32_t* d_comm_i32,
                             vs_allreduce_fn allreduce, void* user, float* centroids_out) {
-  Segment* s = seg_lookup(h);
+  std::shared_ptr<Segment> s_ref = seg_lookup(h);
+  Segment* s = s_ref.get();
   if (!s) return fail(VS_EHANDLE, "unknown segment handle");
   const int d = s->d;
   if (M <= 0 || K <= 0) return fail(VS_EINVAL, "Invalid PQ params (m,k,dimension)");
@@ -1294,7 +1660,7 @@ int32_t vs_pq_train_sharded(uint64_t h, int64_t n_total, int64_t row_lo, int32_t
   if (s->n == 0) return fail(VS_EINVAL, "a rank must own at least one row");
   if (world <= 0 || rank < 0 || rank >= world) return fail(VS_EINVAL, "rank must be in [0, world)");
   ThreadCtx* c;
-  RET(ctx_bind(&c));
+  RET(ctx_bind_seg(&c, s));
   TrainComm comm{row_lo, n_total, rank, world, exact_order != 0 ? 1 : 0, user, allreduce, d_comm_f32, d_comm_i32};
   return pq_train_device(c->stream, s->X, s->n, d, M, K, iterations, seed, lanes(), centroids_out, &comm);
 }
@@ -1303,19 +1669,23 @@ int32_t vs_pq_encode_batch(const float* centroids, int32_t M, int32_t K, int32_t
                            uint64_t h, int64_t n, uint8_t* codes_out) {
   if (!centroids || (!codes_out && n > 0) || n < 0) return fail(VS_EINVAL, "null pointer or negative n");
   RET(check_pq_shape(M, K, subDim));
-  ThreadCtx* c;
-  RET(ctx_bind(&c));
-  if (n == 0) return VS_OK;
+  if (!rows && group_is_sharded(h)) return group_pq_encode(h, centroids, M, K, subDim, n, codes_out);
   const int d = M * subDim;
   const float* dX = nullptr;
+  std::shared_ptr<Segment> s_ref;
   Segment* s = nullptr;
-  if (!rows) {
-    s = seg_lookup(h);
+  if (!rows && n > 0) {
+    s_ref = seg_lookup(h);
+    s = s_ref.get();
     if (!s) return fail(VS_EHANDLE, "rows == NULL needs a valid segment handle");
     if (s->d != d) return fail(VS_EINVAL, "segment dimension %d != M*subDim %d", s->d, d);
     if (n > s->n) return fail(VS_EINVAL, "n exceeds the segment's row count");
     dX = s->X;
   }
+  ThreadCtx* c;
+  if (s) RET(ctx_bind_seg(&c, s));
+  else RET(ctx_bind(&c));
+  if (n == 0) return VS_OK;
   const size_t cb = (size_t)M * K * subDim * 4;
   // host rows are streamed through the scratch in slabs
   const int64_t slab = rows ? std::min<int64_t>(n, (int64_t)((size_t(256) << 20) / ((size_t)d * 4)) + 1) : n;
@@ -1348,8 +1718,15 @@ int32_t vs_pq_train(const float* rows, uint64_t h, int64_t n, int32_t d, int32_t
   if (!centroids_out) return fail(VS_EINVAL, "null output pointer");
   if (n <= 0) return fail(VS_EEMPTY, "empty training set (the reference throws IndexOutOfBoundsException)");
   if (n > 0x7fffffffLL) return fail(VS_EINVAL, "a Java List cannot hold more than 2^31-1 vectors");
+  std::shared_ptr<Segment> s_ref;
+  if (!rows) {
+    if (group_is_sharded(h)) return group_pq_train(h, n, d, M, K, iterations, seed, centroids_out);
+    s_ref = seg_lookup(h);
+    if (!s_ref) return fail(VS_EHANDLE, "rows == NULL needs a valid segment handle");
+  }
   ThreadCtx* c;
-  RET(ctx_bind(&c));
+  if (s_ref) RET(ctx_bind_seg(&c, s_ref.get()));
+  else RET(ctx_bind(&c));
   const float* dX = nullptr;
   float* owned = nullptr;
   if (rows) {
@@ -1361,8 +1738,7 @@ int32_t vs_pq_train(const float* rows, uint64_t h, int64_t n, int32_t d, int32_t
     }
     dX = owned;
   } else {
-    Segment* s = seg_lookup(h);
-    if (!s) return fail(VS_EHANDLE, "rows == NULL needs a valid segment handle");
+    Segment* s = s_ref.get();
     if (s->d != d) return fail(VS_EINVAL, "segment dimension %d != d %d", s->d, d);
     if (n > s->n) return fail(VS_EINVAL, "n exceeds the segment's row count");
     dX = s->X;
@@ -1408,11 +1784,12 @@ static int batch_try_dev(ThreadCtx* c, cudaStream_t st, Segment* s, const float*
 // the group minima of a(q, x) (L2: |x|^2 - 2<q,x>; COSINE: -<q,x>/|x|) and the slack the selection adds.
 int32_t vs_debug_batch_groupmins(uint64_t h, const float* q, int32_t nq, int32_t metric, float* gm_out,
                                  int64_t gm_capacity, int64_t* ngroups_out, int32_t* group_out, double* slack_out) {
-  Segment* s = seg_lookup(h);
+  std::shared_ptr<Segment> s_ref = seg_lookup(h);
+  Segment* s = s_ref.get();
   RET(check_query_args(s, q, nq, 1, metric));
   if (!ngroups_out || !group_out) return fail(VS_EINVAL, "null output pointer");
   ThreadCtx* c;
-  RET(ctx_bind(&c));
+  RET(ctx_bind_seg(&c, s));
   const bool cosine = metric == VS_METRIC_COSINE;
   if (s->n == 0 || !batch_supported(s->d, lanes(), cosine, s->n)) return fail(VS_ESTATE, "segment shape not eligible for the batched path");
   bool ok = false, half = false;
@@ -1462,11 +1839,12 @@ int32_t vs_debug_batch_groupmins(uint64_t h, const float* q, int32_t nq, int32_t
 
 int32_t vs_bruteforce_topk_dev(uint64_t h, const float* d_q, int32_t nq, int32_t k, int32_t metric,
                                int64_t* d_ids, double* d_scores, int32_t* d_counts, void* stream) {
-  Segment* s = seg_lookup(h);
+  std::shared_ptr<Segment> s_ref = seg_lookup(h);
+  Segment* s = s_ref.get();
   RET(check_query_args(s, d_q, nq, k, metric));
   if (!d_ids || !d_scores || !d_counts) return fail(VS_EINVAL, "null output pointer");
   ThreadCtx* c;
-  RET(ctx_bind(&c));
+  RET(ctx_bind_seg(&c, s));
   RET(ctx_use_stream(c, stream));
   if (s->n == 0) return fail(VS_EINVAL, "empty segment: use the host variant");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1489,13 +1867,17 @@ int32_t vs_bruteforce_topk_dev(uint64_t h, const float* d_q, int32_t nq, int32_t
 
 int32_t vs_bruteforce_topk_packed_dev(uint64_t h, const float* d_q, int32_t nq, int32_t k, int32_t metric,
                                       int64_t* d_pack, int32_t* d_counts, void* stream) {
-  Segment* s = seg_lookup(h);
+  std::shared_ptr<Segment> s_ref = seg_lookup(h);
+  Segment* s = s_ref.get();
   RET(check_query_args(s, d_q, nq, k, metric));
   if (!d_pack || !d_counts) return fail(VS_EINVAL, "null output pointer");
   ThreadCtx* c;
-  RET(ctx_bind(&c));
+  RET(ctx_bind_seg(&c, s));
   RET(ctx_use_stream(c, stream));
-  if (s->n == 0) return fail(VS_EINVAL, "empty segment: use the host variant");
+  if (s->n == 0) {  // an empty shard contributes an all-empty list to the exchange (same collective path as its peers)
+    CK(launch_fill_pack(d_pack, nq, k, 0, d_counts, static_cast<cudaStream_t>(stream)), "fill launch");
+    return VS_OK;
+  }
   bool done = false;
   RET(batch_try_dev(c, static_cast<cudaStream_t>(stream), s, d_q, nq, k, metric, d_pack, reinterpret_cast<double*>(d_pack + k),
                     d_counts, 2 * (int64_t)k, &done));
@@ -1536,10 +1918,20 @@ struct PeerComm {
   std::mutex mu;
   std::vector<cudaStream_t> streams;  // ring r belongs to streams[r]
   std::vector<uint64_t> ring_seq;
-  // staging of the host-buffer entry point (vs_bruteforce_topk_exchange): device and pinned host, grown on demand
+  // The host-buffer entry points (vs_*_exchange) run on a stream the COMMUNICATOR owns, serialised by xmu: whichever
+  // request thread makes the call, every rank's host-path exchanges use the same ring in the same order (a ring keyed
+  // on the calling thread's stream would burn a ring per thread and could differ between ranks).
   std::mutex xmu;
+  cudaStream_t xstream = nullptr;
   unsigned char *x_dev = nullptr, *x_host = nullptr;
   size_t x_dev_cap = 0, x_host_cap = 0;
+  bool shared_device = false;  // several ranks on one GPU: the fused publish-then-wait kernel could stall (rank.cu)
+  struct RingPack {
+    cudaStream_t stream;
+    int64_t* p;
+    size_t cap;
+  };
+  std::vector<RingPack> ring_packs;  // send buffers of the one-call stream entry points
 };
 // communicators live in a registry: a stale or foreign handle is an error, never a wild pointer
 std::mutex g_peer_mu;
@@ -1556,6 +1948,7 @@ struct PeerSlot {
   const unsigned long long* flags;
   unsigned int* ticket;
   uint64_t seq;
+  int ring = -1;
 };
 // Slots are handed out per STREAM: each stream a communicator sees gets its own ring of PEER_RING slots, in order
 // of first use (every rank issues the same exchanges on corresponding streams in the same order, as with any
@@ -1569,13 +1962,21 @@ bool peer_next(PeerComm* pc, size_t payload, cudaStream_t st, PeerSlot* out) {
   for (size_t i = 0; i < pc->streams.size(); i++)
     if (pc->streams[i] == st) ring = (int)i;
   if (ring < 0) {
-    if ((int)(pc->streams.size() + 1) * PEER_RING > pc->depth) return false;
-    ring = (int)pc->streams.size();
-    pc->streams.push_back(st);
-    pc->ring_seq.push_back(0);
+    // a ring whose stream was released (vs_peer_release_stream) is free for the next newcomer
+    for (size_t i = 0; i < pc->streams.size() && ring < 0; i++)
+      if (pc->streams[i] == nullptr && i != 0) ring = (int)i;
+    if (ring >= 0) {
+      pc->streams[ring] = st;
+    } else {
+      if ((int)(pc->streams.size() + 1) * PEER_RING > pc->depth) return false;
+      ring = (int)pc->streams.size();
+      pc->streams.push_back(st);
+      pc->ring_seq.push_back(0);
+    }
   }
   PeerSlot& ps = *out;
   ps.seq = ++pc->ring_seq[ring];
+  ps.ring = ring;
   const size_t slot = (size_t)ring * PEER_RING + (size_t)((ps.seq - 1) % PEER_RING);
   unsigned char* own = pc->bases[pc->rank];
   const size_t slot_base = slot * (size_t)pc->world * pc->slot_bytes;
@@ -1585,6 +1986,23 @@ bool peer_next(PeerComm* pc, size_t payload, cudaStream_t st, PeerSlot* out) {
   ps.flags = reinterpret_cast<const unsigned long long*>(own + ps.flag_off);
   ps.ticket = reinterpret_cast<unsigned int*>(own + pc->ticket_off) + slot;
   return true;
+}
+// a launch failed after peer_next on this rank: hand the sequence number back so the ring stays in step with the
+// peers (they time out on this exchange, but the communicator is not left off by one for good)
+void peer_rollback(PeerComm* pc, const PeerSlot& ps) {
+  std::lock_guard<std::mutex> g(pc->mu);
+  if (ps.ring >= 0 && ps.ring < (int)pc->ring_seq.size() && pc->ring_seq[ps.ring] == ps.seq) pc->ring_seq[ps.ring]--;
+}
+// the communicator's own stream (host entry points); caller holds pc->xmu
+int peer_xstream(PeerComm* pc, cudaStream_t* out) {
+  if (!pc->xstream) {
+    cudaError_t e = cudaStreamCreateWithFlags(&pc->xstream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaStreamCreate (communicator stream)");
+    std::lock_guard<std::mutex> g(pc->mu);
+    pc->streams[0] = pc->xstream;  // ring 0 on every rank, whatever the order in which other streams show up
+  }
+  *out = pc->xstream;
+  return VS_OK;
 }
 }  // namespace
 
@@ -1608,6 +2026,9 @@ int32_t vs_peer_create(int32_t rank, int32_t world, int64_t slot_bytes, int32_t 
   pc->ticket_off = pc->flags_off + (size_t)depth * VS_PEER_MAX_WORLD * 8;
   pc->total = pc->ticket_off + (size_t)depth * 4 + 256;
   cudaGetDevice(&pc->device);
+  // ring 0 belongs to the communicator's own stream (the host entry points)
+  pc->streams.push_back(nullptr);
+  pc->ring_seq.push_back(0);
   cudaError_t e = cudaMalloc(&pc->bases[rank], pc->total);  // plain cudaMalloc: cudaIpc cannot export pool memory
   if (e == cudaSuccess) e = cudaMemset(pc->bases[rank], 0, pc->total);
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -1632,7 +2053,7 @@ int32_t vs_peer_connect(uint64_t comm, const uint8_t* handles) {
   if (!pc || !handles) return fail(VS_EINVAL, "bad peer communicator");
   if (pc->connected) return fail(VS_ESTATE, "peer communicator is already connected");
   ThreadCtx* c;
-  RET(ctx_bind(&c));
+  RET(ctx_bind_dev(&c, pc->device));
   for (int p = 0; p < pc->world; p++) {
     if (p == pc->rank) continue;
     cudaIpcMemHandle_t hd;
@@ -1648,7 +2069,7 @@ int32_t vs_peer_connect(uint64_t comm, const uint8_t* handles) {
 
 // One process driving several GPUs (or several communicators on one GPU, as the tests do): no IPC needed, the
 // caller passes the base addresses (vs_peer_base) of all ranks' buffers.  With different devices the caller has
-// enabled peer access between them (cudaDeviceEnablePeerAccess).
+// enabled peer access between them (cudaDeviceEnablePeerAccess; vs_init_multi does).
 int32_t vs_peer_base(uint64_t comm, uint64_t* base_out) {
   PeerComm* pc = peer_lookup(comm);
   if (!pc || !base_out) return fail(VS_EINVAL, "bad peer communicator");
@@ -1660,14 +2081,38 @@ int32_t vs_peer_connect_ptrs(uint64_t comm, const uint64_t* bases) {
   PeerComm* pc = peer_lookup(comm);
   if (!pc || !bases) return fail(VS_EINVAL, "bad peer communicator");
   if (pc->connected) return fail(VS_ESTATE, "peer communicator is already connected");
+  int devs[VS_PEER_MAX_WORLD];
   for (int p = 0; p < pc->world; p++) {
-    if (p == pc->rank) continue;
-    if (!bases[p]) return fail(VS_EINVAL, "null base address for rank %d", p);
-    pc->bases[p] = reinterpret_cast<unsigned char*>(static_cast<uintptr_t>(bases[p]));
+    if (p != pc->rank) {
+      if (!bases[p]) return fail(VS_EINVAL, "null base address for rank %d", p);
+      pc->bases[p] = reinterpret_cast<unsigned char*>(static_cast<uintptr_t>(bases[p]));
+    }
+    cudaPointerAttributes at{};
+    devs[p] = -1 - p;
+    if (cudaPointerGetAttributes(&at, pc->bases[p]) == cudaSuccess && at.type == cudaMemoryTypeDevice) devs[p] = at.device;
+    else cudaGetLastError();
+    // two ranks on one GPU: the fused one-query kernel (publish, then spin on the peers) needs every rank's kernel
+    // resident at once, which one device does not guarantee -> separate publish kernel for this communicator
+    for (int o = 0; o < p; o++)
+      if (devs[o] == devs[p]) pc->shared_device = true;
   }
   pc->connected = true;
   pc->by_ptr = true;
   return VS_OK;
+}
+
+// A caller stream that will not be used with this communicator again gives its ring back (every rank releases the
+// corresponding stream at the same point of its exchange sequence, as with any collective).
+int32_t vs_peer_release_stream(uint64_t comm, void* stream) {
+  PeerComm* pc = peer_lookup(comm);
+  if (!pc) return fail(VS_EINVAL, "bad peer communicator");
+  std::lock_guard<std::mutex> g(pc->mu);
+  for (size_t i = 1; i < pc->streams.size(); i++)
+    if (pc->streams[i] == static_cast<cudaStream_t>(stream)) {
+      pc->streams[i] = nullptr;  // ring_seq stays: the slot numbering continues where every rank left it
+      return VS_OK;
+    }
+  return fail(VS_EINVAL, "the communicator has no ring for this stream");
 }
 
 int32_t vs_peer_destroy(uint64_t comm) {
@@ -1681,6 +2126,7 @@ int32_t vs_peer_destroy(uint64_t comm) {
     }
   }
   if (!pc) return fail(VS_EINVAL, "bad peer communicator");
+  cudaSetDevice(pc->device);
   cudaDeviceSynchronize();
   for (int p = 0; p < pc->world; p++) {
     if (!pc->bases[p]) continue;
@@ -1689,39 +2135,70 @@ int32_t vs_peer_destroy(uint64_t comm) {
   }
   if (pc->x_dev) cudaFree(pc->x_dev);
   if (pc->x_host) cudaFreeHost(pc->x_host);
+  if (pc->xstream) cudaStreamDestroy(pc->xstream);
+  for (auto& rp : pc->ring_packs) cudaFree(rp.p);
   delete pc;
+  return VS_OK;
+}
+
+// kind 0: [nq][2k] lists merged by score (descending != 0) or distance; kind 1: ADC + re-rank packs [nq][4][nc] -> k.
+// Everything that can fail for one rank alone is checked BEFORE the slot is taken; a launch failure hands it back.
+static int exchange_merge(PeerComm* pc, cudaStream_t st, int kind, const int64_t* d_pack, int nq, int nc, int k, int descending,
+                          int64_t* d_ids_out, double* d_scores_out, int32_t* d_counts_out) {
+  if (!pc || !pc->connected) return fail(VS_ESTATE, "peer communicator is not connected");
+  if (!d_pack || !d_ids_out || !d_scores_out || !d_counts_out) return fail(VS_EINVAL, "null pointer");
+  if (nq <= 0) return fail(VS_EINVAL, "nq must be positive");
+  if (k <= 0 || k > TOPK_MAX_K) return fail(VS_EINVAL, "k must be in 1..%d", TOPK_MAX_K);
+  if (kind == 1) {
+    if (nc <= 0 || k > nc) return fail(VS_EINVAL, "need 0 < k <= n_cand");
+    if ((int64_t)pc->world * nc > 8192) return fail(VS_EINVAL, "world * n_cand must be <= 8192");
+  }
+  const size_t payload = kind == 0 ? (size_t)nq * 2 * k * 8 : (size_t)nq * 4 * nc * 8;
+  if (payload > pc->slot_bytes) return fail(VS_EINVAL, "packed lists (%zu bytes) exceed the communicator's slot", payload);
+  PeerSlot ps;
+  if (!peer_next(pc, payload, st, &ps))
+    return fail(VS_ESTATE, "communicator of depth %d serves %d streams; this is one more", pc->depth, pc->depth / PEER_RING);
+  const PeerPublish pub{pc->bases, d_pack, payload, ps.data_off, ps.flag_off, pc->rank};
+  const bool fused = nq == 1 && g_peer_fused.load() != 0 && !pc->shared_device;  // one query: the merge kernel publishes, then waits
+  cudaError_t e = cudaSuccess;
+  if (!fused) e = launch_peer_publish(pc->bases, pc->world, pc->rank, d_pack, payload, ps.data_off, ps.flag_off, ps.seq, ps.ticket, st);
+  if (e == cudaSuccess) {
+    e = kind == 0 ? launch_merge_packed(ps.gath, pc->world, nq, k, descending != 0, d_ids_out, d_scores_out, d_counts_out, st,
+                                        ps.flags, ps.seq, fused ? &pub : nullptr)
+                  : launch_merge_adc_rerank(ps.gath, pc->world, nq, nc, k, d_ids_out, d_scores_out, d_counts_out, st, ps.flags,
+                                            ps.seq, fused ? &pub : nullptr);
+    // (a separate publish that went out has used the slot: only the fused form can still hand it back)
+    if (e != cudaSuccess && fused) peer_rollback(pc, ps);
+  } else {
+    peer_rollback(pc, ps);
+  }
+  if (e != cudaSuccess) return cuda_fail(e, "exchange launch");
   return VS_OK;
 }
 
 int32_t vs_exchange_merge_packed_dev(uint64_t comm, const int64_t* d_pack, int32_t nq, int32_t k, int32_t descending,
                                      int64_t* d_ids_out, double* d_scores_out, int32_t* d_counts_out, void* stream) {
   PeerComm* pc = peer_lookup(comm);
-  if (!pc || !pc->connected) return fail(VS_ESTATE, "peer communicator is not connected");
-  if (!d_pack || !d_ids_out || !d_scores_out || !d_counts_out) return fail(VS_EINVAL, "null pointer");
-  if (nq <= 0) return fail(VS_EINVAL, "nq must be positive");
-  if (k <= 0 || k > TOPK_MAX_K) return fail(VS_EINVAL, "k must be in 1..%d", TOPK_MAX_K);
-  const size_t payload = (size_t)nq * 2 * k * 8;
-  if (payload > pc->slot_bytes) return fail(VS_EINVAL, "packed lists (%zu bytes) exceed the communicator's slot", payload);
+  if (!pc) return fail(VS_ESTATE, "peer communicator is not connected");
   ThreadCtx* c;
-  RET(ctx_bind(&c));
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  PeerSlot ps;
-  if (!peer_next(pc, payload, st, &ps))
-    return fail(VS_ESTATE, "communicator of depth %d serves %d streams; this is one more", pc->depth, pc->depth / PEER_RING);
-  const PeerPublish pub{pc->bases, d_pack, payload, ps.data_off, ps.flag_off, pc->rank};
-  const bool fused = nq == 1 && g_peer_fused.load() != 0;  // one query: the merge kernel publishes, then waits
-  if (!fused)
-    CK(launch_peer_publish(pc->bases, pc->world, pc->rank, d_pack, payload, ps.data_off, ps.flag_off, ps.seq, ps.ticket, st),
-       "peer publish launch");
-  CK(launch_merge_packed(ps.gath, pc->world, nq, k, descending != 0, d_ids_out, d_scores_out, d_counts_out, st, ps.flags,
-                         ps.seq, fused ? &pub : nullptr), "merge launch");
-  return VS_OK;
+  RET(ctx_bind_dev(&c, pc->device));
+  return exchange_merge(pc, static_cast<cudaStream_t>(stream), 0, d_pack, nq, 0, k, descending, d_ids_out, d_scores_out, d_counts_out);
+}
+
+int32_t vs_exchange_merge_adc_rerank_packed_dev(uint64_t comm, const int64_t* d_pack, int32_t nq, int32_t n_cand, int32_t k,
+                                                int64_t* d_ids_out, double* d_scores_out, int32_t* d_counts_out,
+                                                void* stream) {
+  PeerComm* pc = peer_lookup(comm);
+  if (!pc) return fail(VS_ESTATE, "peer communicator is not connected");
+  ThreadCtx* c;
+  RET(ctx_bind_dev(&c, pc->device));
+  return exchange_merge(pc, static_cast<cudaStream_t>(stream), 1, d_pack, nq, n_cand, k, 1, d_ids_out, d_scores_out, d_counts_out);
 }
 
 // staging of the host-buffer exchange calls (caller holds pc->xmu)
-static int peer_staging(PeerComm* pc, ThreadCtx* c, size_t need_d, size_t need_h) {
+static int peer_staging(PeerComm* pc, cudaStream_t st, size_t need_d, size_t need_h) {
   if (need_d > pc->x_dev_cap) {
-    CK(cudaStreamSynchronize(c->stream), "sync");
+    CK(cudaStreamSynchronize(st), "sync");
     if (pc->x_dev) cudaFree(pc->x_dev);
     pc->x_dev = nullptr;
     pc->x_dev_cap = 0;
@@ -1729,7 +2206,7 @@ static int peer_staging(PeerComm* pc, ThreadCtx* c, size_t need_d, size_t need_h
     pc->x_dev_cap = need_d;
   }
   if (need_h > pc->x_host_cap) {
-    CK(cudaStreamSynchronize(c->stream), "sync");
+    CK(cudaStreamSynchronize(st), "sync");
     if (pc->x_host) cudaFreeHost(pc->x_host);
     pc->x_host = nullptr;
     pc->x_host_cap = 0;
@@ -1739,23 +2216,90 @@ static int peer_staging(PeerComm* pc, ThreadCtx* c, size_t need_d, size_t need_h
   return VS_OK;
 }
 
-// The whole sharded query as ONE host call (the e2e path of a rank): pinned staging in, local scan into the packed
-// list, peer exchange, merge -- short result lists are written by the merge kernel straight into pinned host
-// memory -- one synchronisation.  Collective: every rank calls it with the same queries.
-int32_t vs_bruteforce_topk_exchange(uint64_t h, uint64_t comm, const float* q, int32_t nq, int32_t k, int32_t metric,
-                                    int64_t* ids_out, double* scores_out, int32_t* counts_out) {
-  Segment* s = seg_lookup(h);
-  RET(check_query_args(s, q, nq, k, metric));
-  if (!ids_out || !scores_out) return fail(VS_EINVAL, "null output pointer");
+// per-stream packed send buffers of the one-call stream entry points (vs_*_exchange_dev): one per ring, since on one
+// stream the publish of exchange t has read the buffer before the scan of exchange t+1 writes it
+static int peer_ring_pack(PeerComm* pc, cudaStream_t st, size_t bytes, int64_t** pack_out) {
+  std::lock_guard<std::mutex> g(pc->mu);
+  for (auto& rp : pc->ring_packs)
+    if (rp.stream == st && rp.cap >= bytes) {
+      *pack_out = rp.p;
+      return VS_OK;
+    }
+  PeerComm::RingPack rp{};
+  rp.stream = st;
+  rp.cap = bytes < (size_t(64) << 10) ? (size_t(64) << 10) : bytes;
+  CK(cudaMalloc(&rp.p, rp.cap), "cudaMalloc(exchange send buffer)");
+  pc->ring_packs.push_back(rp);  // an outgrown buffer of the same stream stays until the communicator goes (work may be in flight)
+  *pack_out = rp.p;
+  return VS_OK;
+}
+
+// The sharded query as ONE stream call: local scan into this stream's packed send buffer, peer exchange, merge.  Outputs
+// are device pointers (or pinned host memory, which the merge kernel writes directly); nothing synchronises.
+int32_t vs_bruteforce_topk_exchange_dev(uint64_t h, uint64_t comm, const float* d_q, int32_t nq, int32_t k, int32_t metric,
+                                        int64_t* d_ids, double* d_scores, int32_t* d_counts, void* stream) {
   PeerComm* pc = peer_lookup(comm);
   if (!pc || !pc->connected) return fail(VS_ESTATE, "peer communicator is not connected");
+  if (k <= 0 || k > TOPK_MAX_K || nq <= 0) return fail(VS_EINVAL, "nq must be positive and k in 1..%d", TOPK_MAX_K);
+  const size_t payload = (size_t)nq * 2 * k * 8;
+  if (payload > pc->slot_bytes) return fail(VS_EINVAL, "packed lists (%zu bytes) exceed the communicator's slot", payload);
   ThreadCtx* c;
-  RET(ctx_bind(&c));
+  RET(ctx_bind_dev(&c, pc->device));
+  int64_t* d_pack = nullptr;
+  RET(peer_ring_pack(pc, static_cast<cudaStream_t>(stream), payload + (size_t)nq * 4 + 256, &d_pack));
+  int32_t* d_cn_local = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(d_pack) + ((payload + 255) & ~size_t(255)));
+  RET(vs_bruteforce_topk_packed_dev(h, d_q, nq, k, metric, d_pack, d_cn_local, stream));
+  return exchange_merge(pc, static_cast<cudaStream_t>(stream), 0, d_pack, nq, 0, k, 1, d_ids, d_scores, d_counts);
+}
+
+int32_t vs_adc_rerank_topk_exchange_dev(uint64_t h, uint64_t comm, const float* d_q, int32_t nq, int32_t n_cand, int32_t k,
+                                        int32_t metric, int32_t normalize_on_read, int64_t* d_ids, double* d_scores,
+                                        int32_t* d_counts, void* stream) {
+  PeerComm* pc = peer_lookup(comm);
+  if (!pc || !pc->connected) return fail(VS_ESTATE, "peer communicator is not connected");
+  if (nq <= 0 || n_cand <= 0 || k <= 0 || k > n_cand || k > TOPK_MAX_K) return fail(VS_EINVAL, "need nq > 0 and 0 < k <= n_cand");
+  if ((int64_t)pc->world * n_cand > 8192) return fail(VS_EINVAL, "world * n_cand must be <= 8192");
+  const size_t payload = (size_t)nq * 4 * n_cand * 8;
+  if (payload > pc->slot_bytes) return fail(VS_EINVAL, "packed candidates (%zu bytes) exceed the communicator's slot", payload);
+  ThreadCtx* c;
+  RET(ctx_bind_dev(&c, pc->device));
+  int64_t* d_pack = nullptr;
+  RET(peer_ring_pack(pc, static_cast<cudaStream_t>(stream), payload, &d_pack));
+  RET(vs_adc_rerank_packed_dev(h, d_q, nq, n_cand, metric, normalize_on_read, d_pack, stream));
+  return exchange_merge(pc, static_cast<cudaStream_t>(stream), 1, d_pack, nq, n_cand, k, 1, d_ids, d_scores, d_counts);
+}
+
+// The host-buffer forms (what a rank's request thread calls): pinned staging in, the stream call above on the
+// communicator's own stream, results back (short lists are written by the merge kernel straight into pinned host
+// memory), one synchronisation.  Collective: every rank calls with the same queries.
+//   kind 0: brute force; 1: ADC + re-rank; 2: ADC lists (ascending approximate distance); 3: re-rank of caller candidates
+static int exchange_host(int kind, uint64_t h, uint64_t comm, const float* q, int nq, const int64_t* cand, int n_cand, int k,
+                         int metric, int nor, int64_t* ids_out, double* scores_out, int32_t* counts_out) {
+  std::shared_ptr<Segment> s_ref = seg_lookup(h);
+  Segment* s = s_ref.get();
+  const int kout = kind == 2 ? n_cand : k;
+  RET(check_query_args(s, q, nq, kout, kind == 2 ? VS_METRIC_L2 : metric));
+  if (!ids_out || !scores_out) return fail(VS_EINVAL, "null output pointer");
+  if (kind != 0 && (n_cand <= 0 || n_cand > 8192)) return fail(VS_EINVAL, "n_cand must be in 1..8192");
+  if ((kind == 1 || kind == 3) && k > n_cand) return fail(VS_EINVAL, "k must be in 1..n_cand");
+  if (kind == 2 && n_cand > TOPK_MAX_K) return fail(VS_EINVAL, "n_cand must be in 1..%d", TOPK_MAX_K);
+  if (kind == 3 && (!cand || nq != 1)) return fail(VS_EINVAL, "re-rank takes one query and a candidate list");
+  if ((kind == 1 || kind == 2) && s->M == 0 && s->n > 0) return fail(VS_ESTATE, "segment has no PQ attached");
+  PeerComm* pc = peer_lookup(comm);
+  if (!pc || !pc->connected) return fail(VS_ESTATE, "peer communicator is not connected");
+  if (pc->device != s->device) return fail(VS_EINVAL, "segment and communicator live on different devices");
+  const size_t payload = (kind == 0 || kind == 2) ? (size_t)nq * 2 * kout * 8 : (size_t)nq * 4 * n_cand * 8;
+  if (payload > pc->slot_bytes) return fail(VS_EINVAL, "packed lists exceed the communicator's slot");
+  if ((kind == 1 || kind == 3) && (int64_t)pc->world * n_cand > 8192) return fail(VS_EINVAL, "world * n_cand must be <= 8192");
+  ThreadCtx* c;
+  RET(ctx_bind_seg(&c, s));
   auto up = [](size_t b) { return (b + 255) & ~size_t(255); };
-  const size_t qb = up((size_t)nq * s->d * 4), pb = up((size_t)nq * 2 * k * 8), ib = up((size_t)nq * k * 8), cb = up((size_t)nq * 4);
-  if ((size_t)nq * 2 * k * 8 > pc->slot_bytes) return fail(VS_EINVAL, "packed lists exceed the communicator's slot");
+  const size_t qb = up((size_t)nq * s->d * 4), pb = up(payload), ib = up((size_t)nq * kout * 8), cb = up((size_t)nq * 4);
+  const size_t cdb = kind == 3 ? up((size_t)n_cand * 8) : 0;
   std::lock_guard<std::mutex> g(pc->xmu);
-  RET(peer_staging(pc, c, qb + pb + cb + 2 * ib + cb, qb + 2 * ib + cb));
+  cudaStream_t st;
+  RET(peer_xstream(pc, &st));
+  RET(peer_staging(pc, st, qb + pb + cb + 2 * ib + cb + cdb, qb + 2 * ib + cb + cdb));
   unsigned char* d = pc->x_dev;
   float* dq = reinterpret_cast<float*>(d);
   int64_t* dpack = reinterpret_cast<int64_t*>(d + qb);
@@ -1763,114 +2307,75 @@ int32_t vs_bruteforce_topk_exchange(uint64_t h, uint64_t comm, const float* q, i
   int64_t* dids = reinterpret_cast<int64_t*>(d + qb + pb + cb);
   double* dsc = reinterpret_cast<double*>(d + qb + pb + cb + ib);
   int32_t* dcn = reinterpret_cast<int32_t*>(d + qb + pb + cb + 2 * ib);
+  int64_t* dcand = reinterpret_cast<int64_t*>(d + qb + pb + cb + 2 * ib + cb);
   unsigned char* hh = pc->x_host;
   float* hq = reinterpret_cast<float*>(hh);
   int64_t* hids = reinterpret_cast<int64_t*>(hh + qb);
   double* hsc = reinterpret_cast<double*>(hh + qb + ib);
   int32_t* hcn = reinterpret_cast<int32_t*>(hh + qb + 2 * ib);
+  int64_t* hcand = reinterpret_cast<int64_t*>(hh + qb + 2 * ib + cb);
   memcpy(hq, q, (size_t)nq * s->d * 4);
-  CK(cudaMemcpyAsync(dq, hq, (size_t)nq * s->d * 4, cudaMemcpyHostToDevice, c->stream), "H2D q");
-  RET(vs_bruteforce_topk_packed_dev(h, dq, nq, k, metric, dpack, dcn_local, c->stream));
-  const bool direct = (size_t)nq * k <= 4096;  // short lists: the merge writes pinned host memory (UVA) itself
-  RET(vs_exchange_merge_packed_dev(comm, dpack, nq, k, 1, direct ? hids : dids, direct ? hsc : dsc, direct ? hcn : dcn, c->stream));
-  if (!direct) {
-    CK(cudaMemcpyAsync(hids, dids, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, c->stream), "D2H ids");
-    CK(cudaMemcpyAsync(hsc, dsc, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, c->stream), "D2H scores");
-    CK(cudaMemcpyAsync(hcn, dcn, (size_t)nq * 4, cudaMemcpyDeviceToHost, c->stream), "D2H counts");
+  CK(cudaMemcpyAsync(dq, hq, (size_t)nq * s->d * 4, cudaMemcpyHostToDevice, st), "H2D q");
+  if (kind == 3) {
+    memcpy(hcand, cand, (size_t)n_cand * 8);
+    CK(cudaMemcpyAsync(dcand, hcand, (size_t)n_cand * 8, cudaMemcpyHostToDevice, st), "H2D candidates");
   }
-  CK(cudaStreamSynchronize(c->stream), "sync");
-  memcpy(ids_out, hids, (size_t)nq * k * 8);
-  memcpy(scores_out, hsc, (size_t)nq * k * 8);
+  if (kind == 0) RET(vs_bruteforce_topk_packed_dev(h, dq, nq, k, metric, dpack, dcn_local, st));
+  else if (kind == 1) RET(vs_adc_rerank_packed_dev(h, dq, nq, n_cand, metric, nor, dpack, st));
+  else if (kind == 2) RET(vs_adc_topk_packed_dev(h, dq, nq, n_cand, dpack, dcn_local, st));
+  else RET(vs_rerank_packed_dev(h, dq, dcand, n_cand, metric, nor, dpack, st));
+  const bool direct = (size_t)nq * kout <= 4096;  // short lists: the merge writes pinned host memory (UVA) itself
+  RET(exchange_merge(pc, st, (kind == 0 || kind == 2) ? 0 : 1, dpack, nq, n_cand, kout, kind == 2 ? 0 : 1, direct ? hids : dids,
+                     direct ? hsc : dsc, direct ? hcn : dcn));
+  if (!direct) {
+    CK(cudaMemcpyAsync(hids, dids, (size_t)nq * kout * 8, cudaMemcpyDeviceToHost, st), "D2H ids");
+    CK(cudaMemcpyAsync(hsc, dsc, (size_t)nq * kout * 8, cudaMemcpyDeviceToHost, st), "D2H scores");
+    CK(cudaMemcpyAsync(hcn, dcn, (size_t)nq * 4, cudaMemcpyDeviceToHost, st), "D2H counts");
+  }
+  CK(cudaStreamSynchronize(st), "sync");
+  memcpy(ids_out, hids, (size_t)nq * kout * 8);
+  memcpy(scores_out, hsc, (size_t)nq * kout * 8);
   if (counts_out) memcpy(counts_out, hcn, (size_t)nq * 4);
   return VS_OK;
 }
 
-int32_t vs_exchange_merge_adc_rerank_packed_dev(uint64_t comm, const int64_t* d_pack, int32_t nq, int32_t n_cand, int32_t k,
-                                                int64_t* d_ids_out, double* d_scores_out, int32_t* d_counts_out,
-                                                void* stream) {
-  PeerComm* pc = peer_lookup(comm);
-  if (!pc || !pc->connected) return fail(VS_ESTATE, "peer communicator is not connected");
-  if (!d_pack || !d_ids_out || !d_scores_out || !d_counts_out) return fail(VS_EINVAL, "null pointer");
-  if (nq <= 0 || n_cand <= 0 || k <= 0 || k > n_cand) return fail(VS_EINVAL, "need nq > 0 and 0 < k <= n_cand");
-  if (k > TOPK_MAX_K) return fail(VS_EINVAL, "k must be in 1..%d", TOPK_MAX_K);
-  if ((int64_t)pc->world * n_cand > 8192) return fail(VS_EINVAL, "world * n_cand must be <= 8192");
-  const size_t payload = (size_t)nq * 4 * n_cand * 8;
-  if (payload > pc->slot_bytes) return fail(VS_EINVAL, "packed candidates (%zu bytes) exceed the communicator's slot", payload);
-  ThreadCtx* c;
-  RET(ctx_bind(&c));
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  PeerSlot ps;
-  if (!peer_next(pc, payload, st, &ps))
-    return fail(VS_ESTATE, "communicator of depth %d serves %d streams; this is one more", pc->depth, pc->depth / PEER_RING);
-  const PeerPublish pub{pc->bases, d_pack, payload, ps.data_off, ps.flag_off, pc->rank};
-  const bool fused = nq == 1 && g_peer_fused.load() != 0;
-  if (!fused)
-    CK(launch_peer_publish(pc->bases, pc->world, pc->rank, d_pack, payload, ps.data_off, ps.flag_off, ps.seq, ps.ticket, st),
-       "peer publish launch");
-  CK(launch_merge_adc_rerank(ps.gath, pc->world, nq, n_cand, k, d_ids_out, d_scores_out, d_counts_out, st, ps.flags, ps.seq,
-                             fused ? &pub : nullptr), "merge launch");
-  return VS_OK;
+int32_t vs_bruteforce_topk_exchange(uint64_t h, uint64_t comm, const float* q, int32_t nq, int32_t k, int32_t metric,
+                                    int64_t* ids_out, double* scores_out, int32_t* counts_out) {
+  return exchange_host(0, h, comm, q, nq, nullptr, 0, k, metric, 0, ids_out, scores_out, counts_out);
 }
-
-// Sealed segments across shards as ONE host call: ADC candidates with their exact scores, peer exchange, global
-// re-rank merge (FdbVectorIndex.java:769,820-828,997-1043 with shards in the role of row ranges of one segment).
+// Sealed segments across shards: ADC candidates with their exact scores, peer exchange, global re-rank merge
+// (FdbVectorIndex.java:769,820-828,997-1043 with shards in the role of row ranges of one segment).
 int32_t vs_adc_rerank_topk_exchange(uint64_t h, uint64_t comm, const float* q, int32_t nq, int32_t n_cand, int32_t k,
                                     int32_t metric, int32_t normalize_on_read, int64_t* ids_out, double* scores_out,
                                     int32_t* counts_out) {
-  Segment* s = seg_lookup(h);
-  RET(check_query_args(s, q, nq, n_cand, metric));
-  if (!ids_out || !scores_out) return fail(VS_EINVAL, "null output pointer");
-  if (k <= 0 || k > n_cand || k > TOPK_MAX_K) return fail(VS_EINVAL, "k must be in 1..min(n_cand, %d)", TOPK_MAX_K);
-  PeerComm* pc = peer_lookup(comm);
-  if (!pc || !pc->connected) return fail(VS_ESTATE, "peer communicator is not connected");
-  ThreadCtx* c;
-  RET(ctx_bind(&c));
-  auto up = [](size_t b) { return (b + 255) & ~size_t(255); };
-  const size_t qb = up((size_t)nq * s->d * 4), pb = up((size_t)nq * 4 * n_cand * 8), ib = up((size_t)nq * k * 8), cb = up((size_t)nq * 4);
-  if ((size_t)nq * 4 * n_cand * 8 > pc->slot_bytes) return fail(VS_EINVAL, "packed candidates exceed the communicator's slot");
-  std::lock_guard<std::mutex> g(pc->xmu);
-  RET(peer_staging(pc, c, qb + pb + 2 * ib + cb, qb + 2 * ib + cb));
-  unsigned char* d = pc->x_dev;
-  float* dq = reinterpret_cast<float*>(d);
-  int64_t* dpack = reinterpret_cast<int64_t*>(d + qb);
-  int64_t* dids = reinterpret_cast<int64_t*>(d + qb + pb);
-  double* dsc = reinterpret_cast<double*>(d + qb + pb + ib);
-  int32_t* dcn = reinterpret_cast<int32_t*>(d + qb + pb + 2 * ib);
-  unsigned char* hh = pc->x_host;
-  float* hq = reinterpret_cast<float*>(hh);
-  int64_t* hids = reinterpret_cast<int64_t*>(hh + qb);
-  double* hsc = reinterpret_cast<double*>(hh + qb + ib);
-  int32_t* hcn = reinterpret_cast<int32_t*>(hh + qb + 2 * ib);
-  memcpy(hq, q, (size_t)nq * s->d * 4);
-  CK(cudaMemcpyAsync(dq, hq, (size_t)nq * s->d * 4, cudaMemcpyHostToDevice, c->stream), "H2D q");
-  RET(vs_adc_rerank_packed_dev(h, dq, nq, n_cand, metric, normalize_on_read, dpack, c->stream));
-  const bool direct = (size_t)nq * k <= 4096;
-  RET(vs_exchange_merge_adc_rerank_packed_dev(comm, dpack, nq, n_cand, k, direct ? hids : dids, direct ? hsc : dsc,
-                                              direct ? hcn : dcn, c->stream));
-  if (!direct) {
-    CK(cudaMemcpyAsync(hids, dids, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, c->stream), "D2H ids");
-    CK(cudaMemcpyAsync(hsc, dsc, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, c->stream), "D2H scores");
-    CK(cudaMemcpyAsync(hcn, dcn, (size_t)nq * 4, cudaMemcpyDeviceToHost, c->stream), "D2H counts");
-  }
-  CK(cudaStreamSynchronize(c->stream), "sync");
-  memcpy(ids_out, hids, (size_t)nq * k * 8);
-  memcpy(scores_out, hsc, (size_t)nq * k * 8);
-  if (counts_out) memcpy(counts_out, hcn, (size_t)nq * 4);
-  return VS_OK;
+  return exchange_host(1, h, comm, q, nq, nullptr, n_cand, k, metric, normalize_on_read, ids_out, scores_out, counts_out);
+}
+int32_t vs_adc_topk_exchange(uint64_t h, uint64_t comm, const float* q, int32_t nq, int32_t n_cand, int64_t* ids_out,
+                             double* approx_out, int32_t* counts_out) {
+  return exchange_host(2, h, comm, q, nq, nullptr, n_cand, n_cand, VS_METRIC_L2, 0, ids_out, approx_out, counts_out);
+}
+int32_t vs_rerank_topk_exchange(uint64_t h, uint64_t comm, const float* q, const int64_t* cand_ids, int32_t n_cand, int32_t k,
+                                int32_t metric, int32_t normalize_on_read, int64_t* ids_out, double* scores_out,
+                                int32_t* count_out) {
+  return exchange_host(3, h, comm, q, 1, cand_ids, n_cand, k, metric, normalize_on_read, ids_out, scores_out, count_out);
 }
 
 // ADC top n_cand of this shard with the exact score of every candidate, packed for the cross-shard merge
 int32_t vs_adc_rerank_packed_dev(uint64_t h, const float* d_q, int32_t nq, int32_t n_cand, int32_t metric,
                                  int32_t normalize_on_read, int64_t* d_pack, void* stream) {
   (void)normalize_on_read;  // same expression with norm(q) hoisted (J/fdb/FdbVectorIndex.java:1006-1010)
-  Segment* s = seg_lookup(h);
+  std::shared_ptr<Segment> s_ref = seg_lookup(h);
+  Segment* s = s_ref.get();
   RET(check_query_args(s, d_q, nq, n_cand, metric));
   if (!d_pack) return fail(VS_EINVAL, "null output pointer");
-  if (s->M == 0) return fail(VS_ESTATE, "segment has no PQ attached");
+  if (s->M == 0 && s->n > 0) return fail(VS_ESTATE, "segment has no PQ attached");
   ThreadCtx* c;
-  RET(ctx_bind(&c));
+  RET(ctx_bind_seg(&c, s));
   RET(ctx_use_stream(c, stream));
-  if (s->n == 0) return fail(VS_EINVAL, "empty segment: use the host variant");
+  if (s->n == 0) {  // an empty shard: every slot empty (state -1)
+    CK(launch_fill_pack(d_pack, nq, n_cand, 1, nullptr, static_cast<cudaStream_t>(stream)), "fill launch");
+    return VS_OK;
+  }
   AdcPlan p;
   RET(plan_adc(s, nq, n_cand, &p));
   const size_t pb = (size_t)nq * p.partial_keys * 16, lb = (size_t)nq * s->M * s->K * 8;
@@ -1898,6 +2403,116 @@ int32_t vs_adc_rerank_packed_dev(uint64_t h, const float* d_q, int32_t nq, int32
   return VS_OK;
 }
 
+// ADC lists of this shard packed for the cross-shard merge by ascending approximate distance: [nq][2 n_cand] =
+// ids | approximate distance bits (the layout of vs_bruteforce_topk_packed_dev)
+int32_t vs_adc_topk_packed_dev(uint64_t h, const float* d_q, int32_t nq, int32_t n_cand, int64_t* d_pack, int32_t* d_counts,
+                               void* stream) {
+  std::shared_ptr<Segment> s_ref = seg_lookup(h);
+  Segment* s = s_ref.get();
+  RET(check_query_args(s, d_q, nq, n_cand, VS_METRIC_L2));
+  if (!d_pack || !d_counts) return fail(VS_EINVAL, "null output pointer");
+  if (s->M == 0 && s->n > 0) return fail(VS_ESTATE, "segment has no PQ attached");
+  ThreadCtx* c;
+  RET(ctx_bind_seg(&c, s));
+  RET(ctx_use_stream(c, stream));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (s->n == 0) {
+    CK(launch_fill_pack(d_pack, nq, n_cand, 0, d_counts, st), "fill launch");
+    return VS_OK;
+  }
+  AdcPlan p;
+  RET(plan_adc(s, nq, n_cand, &p));
+  const size_t pb = (size_t)nq * p.partial_keys * 16, lb = (size_t)nq * s->M * s->K * 8;
+  const size_t cdb = (size_t)nq * (p.cand_entries + p.extra_words) * 8;
+  if (pb + cdb > (size_t(1) << 31)) return fail(VS_EINVAL, "query batch too large for the stream variant");
+  const bool grow = Arena::need({pb, lb, cdb}) > c->d_cap || (size_t)nq > c->ticket_cap || (p.fast && (size_t)nq > c->fs_cap);
+  RET(ctx_reserve_dev(c, Arena::need({pb, lb, cdb})));
+  RET(ctx_reserve_ticket(c, nq));
+  if (p.fast) RET(ctx_reserve_fs(c, nq));
+  if (grow) CK(cudaStreamSynchronize(c->stream), "sync");
+  Arena A(c->d_buf);
+  ulonglong2* dpart = A.take<ulonglong2>((size_t)nq * p.partial_keys);
+  double* dlut = A.take<double>((size_t)nq * s->M * s->K);
+  unsigned long long* dcand = A.take<unsigned long long>((size_t)nq * (p.cand_entries + p.extra_words));
+  return adc_dev(st, s, d_q, nq, n_cand, dlut, d_pack, reinterpret_cast<double*>(d_pack + n_cand), d_counts, dpart, c->d_ticket,
+                 c->d_fs, dcand, p, 2 * (int64_t)n_cand);
+}
+
+// fetchExactAndScore over caller-supplied candidates when the rows are sharded: every shard scores the candidates it
+// owns; the pack is the ADC + re-rank layout with the candidate's POSITION as its approximate key, so the cross-shard
+// merge (vs_exchange_merge_adc_rerank_packed_dev with k results) keeps ties in candidate order (:1031).
+int32_t vs_rerank_packed_dev(uint64_t h, const float* d_q, const int64_t* d_cand, int32_t n_cand, int32_t metric,
+                             int32_t normalize_on_read, int64_t* d_pack, void* stream) {
+  (void)normalize_on_read;
+  std::shared_ptr<Segment> s_ref = seg_lookup(h);
+  Segment* s = s_ref.get();
+  RET(check_query_args(s, d_q, 1, 1, metric));
+  if (!d_cand || !d_pack || n_cand <= 0 || n_cand > 8192) return fail(VS_EINVAL, "need candidates, an output and n_cand in 1..8192");
+  ThreadCtx* c;
+  RET(ctx_bind_seg(&c, s));
+  RankLaunch L{};
+  L.X = s->X; L.n = s->n; L.d = s->d; L.skip = s->skip; L.lanes = lanes(); L.q = d_q; L.nq = 1;
+  L.cand_ids = d_cand; L.nc = n_cand; L.k = n_cand; L.metric = metric; L.id_base = s->id_base;
+  CK(launch_score_pack(L, nullptr, nullptr, d_pack, static_cast<cudaStream_t>(stream), true), "score_pack launch");
+  return VS_OK;
+}
+
+// ---- sharded PqTrainer.train over the library's own exchange ---------------------------------------------------
+static int train_peer_begin(void* pcv, cudaStream_t st, size_t bytes, PeerXchg* x) {
+  PeerComm* pc = static_cast<PeerComm*>(pcv);
+  if (bytes > pc->slot_bytes)
+    return fail(VS_EINVAL, "the training exchange needs %zu bytes per rank; the communicator's slots hold %zu", bytes, pc->slot_bytes);
+  PeerSlot ps;
+  if (!peer_next(pc, bytes, st, &ps))
+    return fail(VS_ESTATE, "communicator of depth %d serves %d streams; this is one more", pc->depth, pc->depth / PEER_RING);
+  x->gath = reinterpret_cast<const unsigned char*>(ps.gath);
+  x->stride = bytes;
+  x->flags = ps.flags;
+  x->seq = ps.seq;
+  x->data_off = ps.data_off;
+  x->flag_off = ps.flag_off;
+  x->ticket = ps.ticket;
+  return VS_OK;
+}
+static int train_peer_publish(void* pcv, cudaStream_t st, const void* payload, const PeerXchg* x) {
+  PeerComm* pc = static_cast<PeerComm*>(pcv);
+  CK(launch_peer_publish(pc->bases, pc->world, pc->rank, payload, x->stride, x->data_off, x->flag_off, x->seq, x->ticket, st),
+     "peer publish launch");
+  return VS_OK;
+}
+
+// PqTrainer.train over row shards with the per-iteration all-reduce of cluster sums and counts done by libvsgpu over
+// the peer buffers (K10): no callback, no collective library, no host synchronisation per reduction.  Collective:
+// every rank of `comm` calls it with its own shard.  exact_order as in vs_pq_train_sharded.
+int32_t vs_pq_train_sharded_peer(uint64_t h, uint64_t comm, int64_t n_total, int64_t row_lo, int32_t exact_order, int32_t M,
+                                 int32_t K, int32_t iterations, int64_t seed, float* centroids_out) {
+  std::shared_ptr<Segment> s_ref = seg_lookup(h);
+  Segment* s = s_ref.get();
+  if (!s) return fail(VS_EHANDLE, "unknown segment handle");
+  PeerComm* pc = peer_lookup(comm);
+  if (!pc || !pc->connected) return fail(VS_ESTATE, "peer communicator is not connected");
+  const int d = s->d;
+  if (M <= 0 || K <= 0) return fail(VS_EINVAL, "Invalid PQ params (m,k,dimension)");
+  if (d % M != 0) return fail(VS_EINVAL, "dimension must be divisible by m");
+  if (!centroids_out) return fail(VS_EINVAL, "null pointer");
+  if (n_total <= 0) return fail(VS_EEMPTY, "empty training set (the reference throws IndexOutOfBoundsException)");
+  if (n_total > 0x7fffffffLL) return fail(VS_EINVAL, "a Java List cannot hold more than 2^31-1 vectors");
+  if (row_lo < 0 || row_lo + s->n > n_total) return fail(VS_EINVAL, "row range outside the corpus");
+  if (pc->device != s->device) return fail(VS_EINVAL, "segment and communicator live on different devices");
+  const size_t need = ((size_t)K * d + 3) / 4 * 16 + (size_t)M * K * 4 + 16;
+  if (need > pc->slot_bytes) return fail(VS_EINVAL, "the training exchange needs %zu bytes per rank; the communicator's slots hold %zu", need, pc->slot_bytes);
+  ThreadCtx* c;
+  RET(ctx_bind_seg(&c, s));
+  std::lock_guard<std::mutex> g(pc->xmu);  // the communicator's own stream: one collective at a time, same ring on every rank
+  cudaStream_t st;
+  RET(peer_xstream(pc, &st));
+  TrainComm tc{row_lo, n_total, pc->rank, pc->world, exact_order != 0 ? 1 : 0, nullptr, nullptr, nullptr, nullptr};
+  tc.peer = pc;
+  tc.peer_begin = train_peer_begin;
+  tc.peer_publish = train_peer_publish;
+  return pq_train_device(st, s->X, s->n, d, M, K, iterations, seed, lanes(), centroids_out, &tc);
+}
+
 int32_t vs_merge_adc_rerank_packed_dev(const int64_t* d_gath, int32_t world, int32_t nq, int32_t n_cand, int32_t k,
                                        int64_t* d_ids_out, double* d_scores_out, int32_t* d_counts_out, void* stream) {
   if (!d_gath || !d_ids_out || !d_scores_out || !d_counts_out) return fail(VS_EINVAL, "null pointer");
@@ -1923,12 +2538,13 @@ int32_t vs_merge_topk_dev(const int64_t* d_ids, const double* d_scores, int64_t 
 
 int32_t vs_adc_topk_dev(uint64_t h, const float* d_q, int32_t nq, int32_t n_cand, int64_t* d_ids,
                         double* d_approx, int32_t* d_counts, void* stream) {
-  Segment* s = seg_lookup(h);
+  std::shared_ptr<Segment> s_ref = seg_lookup(h);
+  Segment* s = s_ref.get();
   RET(check_query_args(s, d_q, nq, n_cand, VS_METRIC_L2));
   if (!d_ids || !d_approx || !d_counts) return fail(VS_EINVAL, "null output pointer");
   if (s->M == 0) return fail(VS_ESTATE, "segment has no PQ attached");
   ThreadCtx* c;
-  RET(ctx_bind(&c));
+  RET(ctx_bind_seg(&c, s));
   RET(ctx_use_stream(c, stream));
   if (s->n == 0) return fail(VS_EINVAL, "empty segment: use the host variant");
   AdcPlan p;
@@ -1953,13 +2569,14 @@ int32_t vs_adc_rerank_topk_dev(uint64_t h, const float* d_q, int32_t nq, int32_t
                                int32_t metric, int32_t normalize_on_read, int64_t* d_ids, double* d_scores,
                                int32_t* d_counts, void* stream) {
   (void)normalize_on_read;
-  Segment* s = seg_lookup(h);
+  std::shared_ptr<Segment> s_ref = seg_lookup(h);
+  Segment* s = s_ref.get();
   RET(check_query_args(s, d_q, nq, n_cand, metric));
   if (k <= 0 || k > TOPK_MAX_K) return fail(VS_EINVAL, "k must be in 1..%d", TOPK_MAX_K);
   if (!d_ids || !d_scores || !d_counts) return fail(VS_EINVAL, "null output pointer");
   if (s->M == 0) return fail(VS_ESTATE, "segment has no PQ attached");
   ThreadCtx* c;
-  RET(ctx_bind(&c));
+  RET(ctx_bind_seg(&c, s));
   RET(ctx_use_stream(c, stream));
   if (s->n == 0) return fail(VS_EINVAL, "empty segment: use the host variant");
   AdcPlan p;

@@ -147,8 +147,13 @@ struct RankLaunch {
 };
 cudaError_t launch_rank(const RankLaunch& L, cudaStream_t st);
 // cross-shard ADC + re-rank: per query int64[4][nc] = ids | approx bits | exact score bits | state
+// cand_approx == nullptr: the candidate's position is its approximate key (caller-supplied candidates re-ranked across
+// shards); cand_counts == nullptr: all nc are valid; foreign_empty: ids outside [id_base, id_base + n) are another
+// shard's (state -1) instead of missing records (state 0)
 cudaError_t launch_score_pack(const RankLaunch& L, const double* cand_approx, const int32_t* cand_counts, int64_t* pack,
-                              cudaStream_t st);
+                              cudaStream_t st, bool foreign_empty = false);
+// an empty shard's contribution: kind 0 = [nq][2k] lists (ids -1, NaN), kind 1 = [nq][4][k] ADC + re-rank packs (state -1)
+cudaError_t launch_fill_pack(int64_t* pack, int nq, int k, int kind, int32_t* counts, cudaStream_t st);
 // wait_flags != nullptr: the gathered lists arrive through the peer exchange; the kernel first waits until
 // wait_flags[0..w) have reached wait_seq (launch_peer_publish of every rank).  pub != nullptr and nq == 1: the
 // kernel publishes this rank's list itself first (no separate launch_peer_publish for that exchange).
@@ -169,6 +174,13 @@ constexpr unsigned long long VS_PEER_TIMEOUT_NS = 20ull * 1000 * 1000 * 1000;
 cudaError_t launch_peer_publish(unsigned char* const* bases, int w, int rank, const void* payload, size_t bytes,
                                 size_t data_off, size_t flag_off, unsigned long long seq, unsigned int* ticket,
                                 cudaStream_t st);
+// All-reduce over the peer buffers (K10): the `w` published copies of [nf floats | ni ints] (each `stride` bytes apart,
+// ints at the 16-byte-rounded end of the floats) are combined after the arrival flags reach seq.  mode 0: fp32 sum in
+// ascending rank order, 1: bitwise OR (exact broadcast of rows owned by one rank), 2: rank w-1's copy; ints: sum.
+cudaError_t launch_peer_reduce(const void* gath, int w, size_t stride, int64_t nf, int64_t ni, int mode, float* out_f,
+                               int32_t* out_i, const unsigned long long* flags, unsigned long long seq, cudaStream_t st);
+// orders the stream behind the publish of ONE source rank
+cudaError_t launch_peer_wait_one(const unsigned long long* flags, int src, unsigned long long seq, cudaStream_t st);
 // stable sort by score descending of `total` (id, score) pairs, first k
 cudaError_t launch_merge(const int64_t* ids, const double* scores, int64_t total, int k,
                          int64_t* ids_out, double* scores_out, int32_t* count_out, cudaStream_t st);
@@ -196,6 +208,9 @@ cudaError_t launch_build_lut(const float* centroids, int M, int K, int subDim, c
                              int lanes, double* lut64, cudaStream_t st);
 cudaError_t launch_approx_distance(const double* lut, int M, int K, const uint8_t* codes, int64_t n,
                                    double* out, cudaStream_t st);
+// pqApproxDistance of listed ids (global: id_base + row) against resident codes; ids without a code: valid 0, NaN
+cudaError_t launch_adc_gather(const double* lut, int M, int K, const uint8_t* codes, int64_t n, int64_t id_base,
+                              const int64_t* ids, int64_t n_ids, double* out, uint8_t* valid, cudaStream_t st);
 struct AdcScanLaunch {
   const uint8_t* codes;  // [n][M]
   int64_t n;

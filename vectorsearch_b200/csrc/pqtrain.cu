@@ -254,6 +254,37 @@ int pq_train_device(cudaStream_t st, const float* dX, int64_t n, int d, int M, i
     if (comm->allreduce(comm->user, kind, count) != 0) return fail(VS_ESTATE, "all-reduce callback failed");
     return VS_OK;
   };
+  // Peer transport (comm->peer != nullptr): the exchange is the library's own -- every rank pushes
+  // [floats | ints] into all peers' buffers over NVLink and a reduce kernel waits for the arrival flags.  Nothing
+  // leaves the stream: no callback, no host synchronisation per reduction.
+  const bool peer = comm != nullptr && comm->peer != nullptr;
+  const size_t max_f = (size_t)M * K * sd, max_i = (size_t)M * K;
+  auto ioff_of = [](size_t nf) { return ((nf + 3) / 4 * 4) * 4; };
+  auto bytes_of = [&](size_t nf, size_t ni) { return (ioff_of(nf) + ni * 4 + 15) / 16 * 16; };
+  DevBuf b_send, b_reinit;
+  if (peer) {
+    if (cudaMalloc(&b_send.p, bytes_of(max_f, max_i)) != cudaSuccess || cudaMalloc(&b_reinit.p, max_f * 4) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(VS_ENOMEM, "cudaMalloc(exchange buffers)");
+    }
+  }
+  float* d_send_f = b_send.as<float>();
+  // rows owned by exactly one rank (initial centroids, re-initialised clusters) -> the same values on every rank
+  auto peer_bcast_rows = [&](const int64_t* d_rows_, int s_begin, int ns_, float* out) -> int {
+    const int64_t total = (int64_t)ns_ * K * sd;
+    PeerXchg x;
+    int r_ = comm->peer_begin(comm->peer, st, bytes_of((size_t)total, 0), &x);
+    if (r_ != VS_OK) return r_;
+    cudaError_t e = cudaMemsetAsync(d_send_f, 0, bytes_of((size_t)total, 0), st);
+    if (e != cudaSuccess) return cuda_fail(e, "memset");
+    gather_owned_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dX, n, d, K, sd, comm->row_lo, d_rows_, d_send_f, s_begin, ns_);
+    count_launch();
+    if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "gather launch");
+    if ((r_ = comm->peer_publish(comm->peer, st, d_send_f, &x)) != VS_OK) return r_;
+    if ((e = launch_peer_reduce(x.gath, comm->world, x.stride, total, 0, 1, out, nullptr, x.flags, x.seq, st)) != cudaSuccess)
+      return cuda_fail(e, "peer reduce launch");
+    return VS_OK;
+  };
   if ((size_t)K * 4 > 96 * 1024) return fail(VS_EINVAL, "K too large for the device trainer (max 24576)");
   const int nb = (int)((n + RB - 1) / RB);
   DevBuf b_cent, b_assign, b_order, b_hist, b_counts, b_offsets, b_sums, b_rows;
@@ -312,7 +343,10 @@ int pq_train_device(cudaStream_t st, const float* dX, int64_t n, int d, int M, i
     TCK(cudaMemcpyAsync(d_rows, h_rows.data(), (size_t)ns * K * 8, cudaMemcpyHostToDevice, st), "H2D init rows");
     {
       const int64_t total = (int64_t)ns * K * sd;
-      if (comm) {
+      if (peer) {
+        int r_ = peer_bcast_rows(d_rows, s0, ns, d_cent + (size_t)s0 * K * sd);
+        if (r_ != VS_OK) return r_;
+      } else if (comm) {
         TCK(cudaMemsetAsync(comm->d_f32, 0, (size_t)total * 4, st), "memset");
         gather_owned_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dX, n, d, K, sd, comm->row_lo, d_rows, comm->d_f32, s0, ns);
         count_launch();
@@ -343,7 +377,26 @@ int pq_train_device(cudaStream_t st, const float* dX, int64_t n, int d, int M, i
       count_launch();
       TCK(cudaGetLastError(), "scatter launch");
       const int64_t total = (int64_t)ns * K * sd;
-      if (comm && comm->exact_order) {
+      if (peer) {
+        // ONE exchange per iteration carries sums and counts.  exact_order: the running sums pass from rank to rank
+        // in ascending row order inside that exchange -- rank r waits (on the device) for rank r-1's copy, continues
+        // its chains from there and publishes; the copy of the last rank is the reference's sum, bit for bit.
+        const size_t ioff = ioff_of((size_t)total);
+        PeerXchg x;
+        { int r_ = comm->peer_begin(comm->peer, st, bytes_of((size_t)total, (size_t)ns * K), &x); if (r_ != VS_OK) return r_; }
+        const float* carry = nullptr;
+        if (comm->exact_order && comm->rank > 0) {
+          TCK(launch_peer_wait_one(x.flags, comm->rank - 1, x.seq, st), "peer wait launch");
+          carry = reinterpret_cast<const float*>(x.gath + (size_t)(comm->rank - 1) * x.stride);
+        }
+        chain_sum_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dX, n, d, K, sd, s0, ns, d_order, d_offsets, carry, d_send_f);
+        count_launch();
+        TCK(cudaGetLastError(), "chain launch");
+        TCK(cudaMemcpyAsync(reinterpret_cast<char*>(d_send_f) + ioff, d_counts, (size_t)ns * K * 4, cudaMemcpyDeviceToDevice, st), "D2D counts");
+        { int r_ = comm->peer_publish(comm->peer, st, d_send_f, &x); if (r_ != VS_OK) return r_; }
+        TCK(launch_peer_reduce(x.gath, comm->world, x.stride, total, (int64_t)ns * K, comm->exact_order ? 2 : 0, d_sums, d_counts,
+                               x.flags, x.seq, st), "peer reduce launch");
+      } else if (comm && comm->exact_order) {
         // The reference adds the rows of a cluster in ascending row order.  Shards are ascending row ranges, so
         // rank r continues the running sums of ranks 0..r-1: world rounds, in each of which exactly one rank
         // contributes (the others add zeros, x + 0.0f == x) -- the sums, hence the centroids, are the reference's bit for bit.
@@ -393,7 +446,13 @@ int pq_train_device(cudaStream_t st, const float* dX, int64_t n, int d, int M, i
       }
       TCK(cudaMemcpyAsync(d_rows, h_rows.data(), (size_t)ns * K * 8, cudaMemcpyHostToDevice, st), "H2D reinit rows");
       const float* reinit_vals = nullptr;
-      if (comm && any_empty) {  // the re-init rows may live on other ranks (every rank sees the same empties)
+      if (peer) {
+        if (any_empty) {
+          int r_ = peer_bcast_rows(d_rows, s0, ns, b_reinit.as<float>());
+          if (r_ != VS_OK) return r_;
+        }
+        reinit_vals = b_reinit.as<float>();
+      } else if (comm && any_empty) {  // the re-init rows may live on other ranks (every rank sees the same empties)
         TCK(cudaMemsetAsync(comm->d_f32, 0, (size_t)total * 4, st), "memset");
         gather_owned_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dX, n, d, K, sd, comm->row_lo, d_rows, comm->d_f32, s0, ns);
         count_launch();

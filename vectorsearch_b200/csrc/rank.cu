@@ -125,7 +125,12 @@ merge_kernel(const int64_t* __restrict__ ids, const double* __restrict__ scores,
 // payload plus one arrival flag per (slot, source rank).  A rank PUSHES its packed result into slot s of every
 // peer with plain stores (posted writes over NVLink), fences, and raises its flag there to the exchange's sequence
 // number; the merge kernel of each rank waits for the `world` flags of ITS OWN buffer and reads local memory only.
-// No rank ever waits inside the publishing kernel, so nothing depends on how CTAs of different GPUs are scheduled.
+// peer_publish_kernel never waits, so a multi-query exchange depends on nothing but stream order.  The fused
+// one-query path (peer_publish_inline below) is different: that kernel publishes and THEN spins on its peers, so
+// every rank's merge kernel must be able to run at the same time.  That holds with one GPU per rank; ranks that share
+// a device (vs_peer_connect_ptrs with buffers on one GPU) or serialised launches (CUDA_LAUNCH_BLOCKING, a profiler's
+// kernel replay) would stall until the time-out trap, so api.cu turns the fused path off for communicators whose
+// ranks share a device.
 struct PeerBases {
   unsigned char* base[VS_PEER_MAX_WORLD];
 };
@@ -269,13 +274,14 @@ merge_packed_kernel(const int64_t* gath, int w, int nq, int k, int kp, int desce
 __global__ void __launch_bounds__(1024)
 score_pack_kernel(const float* __restrict__ X, int64_t n, int d, const uint8_t* __restrict__ skip, int lanes,
                   const float* __restrict__ Q, const int64_t* __restrict__ cand_ids, const double* __restrict__ cand_approx,
-                  const int32_t* __restrict__ cand_counts, int nc, int cosine, int64_t id_base, int64_t* __restrict__ pack) {
+                  const int32_t* __restrict__ cand_counts, int nc, int cosine, int64_t id_base, int foreign_empty,
+                  int64_t* __restrict__ pack) {
   const int qi = blockIdx.x;
   const float* q = Q + (size_t)qi * d;
   const int64_t* cand = cand_ids + (size_t)qi * nc;
-  const double* appr = cand_approx + (size_t)qi * nc;
+  const double* appr = cand_approx != nullptr ? cand_approx + (size_t)qi * nc : nullptr;  // null: the position is the key
   int64_t* out = pack + (size_t)qi * 4 * nc;
-  const int cnt = cand_counts[qi];
+  const int cnt = cand_counts != nullptr ? cand_counts[qi] : nc;
   const int lane = threadIdx.x & 31;
   const int hl = lane & 15;
   const int hw = threadIdx.x >> 4;
@@ -285,8 +291,10 @@ score_pack_kernel(const float* __restrict__ X, int64_t n, int d, const uint8_t* 
   double qq = 0.0;
   if (cosine) qq = ref_sum_halfwarp<REF_DOT>(q, q, d, lanes, hl, hmask, base_lane);
   for (int c = hw; c < nc; c += nhw) {
-    const int64_t g = c < cnt ? cand[c] : -1;
+    int64_t g = c < cnt ? cand[c] : -1;
     const int64_t row = g - id_base;
+    // caller-supplied candidates re-ranked across shards: an id another shard owns is not this shard's entry
+    if (foreign_empty && (row < 0 || row >= n)) g = -1;
     int64_t state = g < 0 ? -1 : 0;
     double score = 0.0;
     bool ok = g >= 0 && row >= 0 && row < n;
@@ -304,7 +312,7 @@ score_pack_kernel(const float* __restrict__ X, int64_t n, int d, const uint8_t* 
     }
     if (hl == 0) {
       out[c] = g;
-      out[nc + c] = g >= 0 ? __double_as_longlong(appr[c]) : 0;
+      out[nc + c] = g >= 0 ? __double_as_longlong(appr != nullptr ? appr[c] : (double)c) : 0;
       out[2 * nc + c] = __double_as_longlong(score);
       out[3 * nc + c] = state;
     }
@@ -312,11 +320,11 @@ score_pack_kernel(const float* __restrict__ X, int64_t n, int d, const uint8_t* 
 }
 
 cudaError_t launch_score_pack(const RankLaunch& L, const double* cand_approx, const int32_t* cand_counts, int64_t* pack,
-                              cudaStream_t st) {
+                              cudaStream_t st, bool foreign_empty) {
   int threads = RANK_THREADS;
   while (threads < 1024 && threads < 16 * L.nc) threads <<= 1;
   score_pack_kernel<<<L.nq, threads, 0, st>>>(L.X, L.n, L.d, L.skip, L.lanes, L.q, L.cand_ids, cand_approx, cand_counts,
-                                               L.nc, L.metric == 1, L.id_base, pack);
+                                               L.nc, L.metric == 1, L.id_base, foreign_empty ? 1 : 0, pack);
   count_launch();
   return cudaGetLastError();
 }
@@ -371,6 +379,89 @@ merge_adc_rerank_kernel(const int64_t* gath, int w, int nq, int nc, int np, int 
   if (found) atomicAdd(&s_found, found);
   __syncthreads();
   if (threadIdx.x == 0) counts_out[qi] = s_found;
+}
+
+// ---- an empty shard's contribution to an exchange --------------------------------------------------------
+// kind 0: brute-force / ADC lists [nq][2k] (ids -1, score bits NaN); kind 1: ADC + re-rank packs [nq][4][k] (state -1)
+__global__ void fill_pack_kernel(int64_t* __restrict__ pack, int nq, int k, int kind, int32_t* __restrict__ counts) {
+  const int64_t per = kind == 0 ? 2 * (int64_t)k : 4 * (int64_t)k;
+  const int64_t total = (int64_t)nq * per;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t j = i % per;
+    int64_t v;
+    if (kind == 0) v = j < k ? -1 : 0x7ff8000000000000ll;
+    else v = (j < k || j >= 3 * (int64_t)k) ? -1 : 0;
+    pack[i] = v;
+  }
+  if (counts != nullptr)
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += (int64_t)gridDim.x * blockDim.x) counts[i] = 0;
+}
+cudaError_t launch_fill_pack(int64_t* pack, int nq, int k, int kind, int32_t* counts, cudaStream_t st) {
+  const int64_t total = (int64_t)nq * (kind == 0 ? 2 : 4) * k;
+  int ctas = (int)((total + 255) / 256);
+  ctas = ctas < 1 ? 1 : (ctas > 1024 ? 1024 : ctas);
+  fill_pack_kernel<<<ctas, 256, 0, st>>>(pack, nq, k, kind, counts);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// ---- all-reduce over the peer buffers (K10): PqTrainer's per-cluster sums and counts across row shards -------
+// Every rank has pushed [nf floats | ni ints] into slot `rank` of every peer (launch_peer_publish).  These kernels
+// wait for the arrival flags in this rank's own buffer and combine the `w` copies from local memory:
+//   floats  mode 0: fp32 sum in ASCENDING RANK ORDER ((c0 + c1) + c2 ...): deterministic and identical on every rank
+//           mode 1: bitwise OR (rows owned by exactly one rank, zero elsewhere: an exact broadcast, -0.0f included)
+//           mode 2: the copy of rank w-1 (the exact-order chain has passed through every rank)
+//   ints    integer sum.
+__global__ void __launch_bounds__(256)
+peer_reduce_kernel(const unsigned char* gath, int w, size_t stride, int64_t nf, int64_t ni, int mode,
+                   float* __restrict__ out_f, int32_t* __restrict__ out_i, const unsigned long long* flags,
+                   unsigned long long seq) {
+  peer_wait(flags, w, seq);
+  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, step = (int64_t)gridDim.x * blockDim.x;
+  const size_t ioff = (size_t)((nf + 3) / 4 * 4) * 4;
+  for (int64_t i = i0; i < nf; i += step) {
+    if (mode == 0) {
+      float acc = reinterpret_cast<const float*>(gath)[i];
+      for (int r = 1; r < w; r++) acc = __fadd_rn(acc, reinterpret_cast<const float*>(gath + (size_t)r * stride)[i]);
+      out_f[i] = acc;
+    } else if (mode == 1) {
+      unsigned int acc = 0u;
+      for (int r = 0; r < w; r++) acc |= reinterpret_cast<const unsigned int*>(gath + (size_t)r * stride)[i];
+      out_f[i] = __uint_as_float(acc);
+    } else {
+      out_f[i] = reinterpret_cast<const float*>(gath + (size_t)(w - 1) * stride)[i];
+    }
+  }
+  for (int64_t i = i0; i < ni; i += step) {
+    int32_t acc = 0;
+    for (int r = 0; r < w; r++) acc += reinterpret_cast<const int32_t*>(gath + (size_t)r * stride + ioff)[i];
+    out_i[i] = acc;
+  }
+}
+cudaError_t launch_peer_reduce(const void* gath, int w, size_t stride, int64_t nf, int64_t ni, int mode, float* out_f,
+                               int32_t* out_i, const unsigned long long* flags, unsigned long long seq, cudaStream_t st) {
+  if (w < 1 || w > VS_PEER_MAX_WORLD) return cudaErrorInvalidValue;
+  const int64_t m = nf > ni ? nf : ni;
+  int ctas = (int)((m + 255) / 256);
+  ctas = ctas < 1 ? 1 : (ctas > 296 ? 296 : ctas);
+  peer_reduce_kernel<<<ctas, 256, 0, st>>>(static_cast<const unsigned char*>(gath), w, stride, nf, ni, mode, out_f, out_i, flags, seq);
+  count_launch();
+  return cudaGetLastError();
+}
+// waits (one warp) until the flag of source rank `src` has reached seq: orders the stream behind ONE peer's publish
+__global__ void peer_wait_one_kernel(const unsigned long long* flags, int src, unsigned long long seq) {
+  if (threadIdx.x == 0) {
+    const unsigned long long t0 = global_timer_ns();
+    while (ld_acquire_sys(flags + src) < seq) {
+      __nanosleep(64);
+      if (global_timer_ns() - t0 > VS_PEER_TIMEOUT_NS) __trap();
+    }
+  }
+}
+cudaError_t launch_peer_wait_one(const unsigned long long* flags, int src, unsigned long long seq, cudaStream_t st) {
+  peer_wait_one_kernel<<<1, 32, 0, st>>>(flags, src, seq);
+  count_launch();
+  return cudaGetLastError();
 }
 
 static PeerPublishDev make_publish(const PeerPublish* pub, int w, int nq) {

@@ -26,6 +26,19 @@ def init(device: int = 0) -> None:
     _initialised = True
 
 
+def init_multi(devices) -> None:
+    """One process, several GPUs (vs_init_multi): segments created afterwards are sharded over `devices` and
+    every Segment / PqTrainer / PqEncoder call fans out inside libvsgpu."""
+    global _initialised
+    devs = (C.c_int32 * len(devices))(*[int(d) for d in devices])
+    check(L.load().vs_init_multi(len(devices), devs))
+    _initialised = True
+
+
+def device_count() -> int:
+    return int(L.load().vs_device_count())
+
+
 def _ensure() -> C.CDLL:
     if not _initialised:
         init(0)
@@ -204,6 +217,7 @@ class Segment:
         n, d, M, K, base = C.c_int64(), C.c_int32(), C.c_int32(), C.c_int32(), C.c_int64()
         check(L.load().vs_segment_info(handle, C.byref(n), C.byref(d), C.byref(M), C.byref(K), C.byref(base)))
         self.n, self.d, self.id_base = n.value, d.value, base.value
+        self.M, self.K = M.value, K.value  # 0 until a codebook is attached
 
     # -- residency -----------------------------------------------------------------------------
     @classmethod
@@ -222,6 +236,38 @@ class Segment:
         h = C.c_uint64()
         check(lib.vs_segment_upload(_p(rows, L.f32p), n, d, sp, id_base, C.byref(h)))
         return cls(h.value)
+
+    @classmethod
+    def upload_bytes(cls, data: bytes, n: int, d: int, stride: int | None = None, skip=None, id_base: int = 0) -> "Segment":
+        """Rows from the reference's stored bytes: FloatPacker little-endian fp32, `stride` bytes between the
+        embeddings of consecutive records (vs_segment_upload_strided)."""
+        lib = _ensure()
+        stride = d * 4 if stride is None else stride
+        buf = np.frombuffer(data, dtype=np.uint8)
+        if n > 0 and buf.size < (n - 1) * stride + d * 4:
+            raise ValueError("byte string too short for n records")
+        sp = None
+        if skip is not None:
+            skip = np.ascontiguousarray(skip, dtype=np.uint8)
+            sp = _p(skip, L.u8p)
+        h = C.c_uint64()
+        check(lib.vs_segment_upload_strided(buf.ctypes.data_as(C.c_void_p), n, d, stride, sp, id_base, C.byref(h)))
+        return cls(h.value)
+
+    @classmethod
+    def upload_records(cls, records, d: int, id_base: int = 0):
+        """Rows from serialized VectorRecord messages (vectorsearch.proto:108-127), as a segment's range read returns
+        them.  Returns (segment, vec_ids): `deleted` records become skipped rows (vs_segment_upload_records)."""
+        lib = _ensure()
+        offs = np.zeros(len(records) + 1, dtype=np.int64)
+        for i, r in enumerate(records):
+            offs[i + 1] = offs[i] + len(r)
+        buf = np.frombuffer(b"".join(records), dtype=np.uint8) if records else np.zeros(1, np.uint8)
+        vec_ids = np.zeros(len(records), dtype=np.int32)
+        h = C.c_uint64()
+        check(lib.vs_segment_upload_records(buf.ctypes.data_as(C.c_void_p), _p(offs, L.i64p), len(records), d, id_base,
+                                            _p(vec_ids, L.i32p), C.byref(h)))
+        return cls(h.value), vec_ids
 
     @classmethod
     def generate(cls, seed: int, first_row: int, n: int, d: int, id_base: int = 0) -> "Segment":
@@ -257,6 +303,18 @@ class Segment:
             cp = _p(codes, L.u8p)
         check(L.load().vs_segment_attach_pq(self.handle, _p(c, L.f32p), M, K, cp))
         self.M, self.K = M, K
+
+    def attach_pq_codebook(self, codebook: bytes, codes=None) -> None:
+        """attach_pq from the stored PQCodebook message (SegmentBuildService.buildCodebookBytes)."""
+        buf = np.frombuffer(codebook, dtype=np.uint8)
+        cp = None
+        if codes is not None:
+            codes = np.ascontiguousarray(codes, dtype=np.uint8)
+            cp = _p(codes, L.u8p)
+        check(L.load().vs_segment_attach_pq_codebook(self.handle, buf.ctypes.data_as(C.c_void_p), buf.size, cp))
+        M, K = C.c_int32(), C.c_int32()
+        check(L.load().vs_segment_info(self.handle, None, None, C.byref(M), C.byref(K), None))
+        self.M, self.K = M.value, K.value
 
     def codes(self, first: int = 0, count: int | None = None) -> np.ndarray:
         count = self.n - first if count is None else count
@@ -334,3 +392,118 @@ class Segment:
                                           int(bool(normalize_on_read)), _p(ids, L.i64p), _p(sc, L.f64p),
                                           _p(cn, L.i32p)))
         return self._trim(ids, sc, cn, single)
+
+
+    # -- BEST_FIRST expansion scoring -------------------------------------------------------------------
+    def adc_query(self, q) -> "AdcQuery":
+        """LUT of `q` against this sealed segment, kept on the device (buildLut once per query and segment,
+        FdbVectorIndex.java:741); score id lists with .gather() per expansion step (:950-963)."""
+        return AdcQuery(self, q)
+
+    def adc_gather(self, q, ids):
+        """One-shot: pqApproxDistance of the listed ids -> (distances, valid)."""
+        q = _f32(q).ravel()
+        ids = np.ascontiguousarray(ids, dtype=np.int64).ravel()
+        out = np.zeros(ids.size, dtype=np.float64)
+        valid = np.zeros(ids.size, dtype=np.uint8)
+        check(L.load().vs_adc_gather(self.handle, _p(q, L.f32p), _p(ids, L.i64p), ids.size, _p(out, L.f64p), _p(valid, L.u8p)))
+        return out, valid.astype(bool)
+
+
+class AdcQuery:
+    """vs_adc_query_begin / _gather / _end as a context manager."""
+
+    def __init__(self, segment: Segment, q):
+        q = _f32(q).ravel()
+        if q.size != segment.d:
+            raise ValueError("query dimension does not match the segment")
+        h = C.c_uint64()
+        check(L.load().vs_adc_query_begin(segment.handle, _p(q, L.f32p), C.byref(h)))
+        self.handle = h.value
+
+    def gather(self, ids):
+        ids = np.ascontiguousarray(ids, dtype=np.int64).ravel()
+        out = np.zeros(ids.size, dtype=np.float64)
+        valid = np.zeros(ids.size, dtype=np.uint8)
+        check(L.load().vs_adc_query_gather(self.handle, _p(ids, L.i64p), ids.size, _p(out, L.f64p), _p(valid, L.u8p)))
+        return out, valid.astype(bool)
+
+    def close(self) -> None:
+        if self.handle:
+            check(L.load().vs_adc_query_end(self.handle))
+            self.handle = 0
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+# ---- wire formats (vectorsearch.proto) and residency -------------------------------------------------------------
+def codebook_encode(centroids) -> bytes:
+    """float[M][K][subDim] -> serialized PQCodebook, the bytes SegmentBuildService.buildCodebookBytes stores."""
+    c = _f32(centroids)
+    M, K, sub = c.shape
+    n = C.c_int64()
+    check(L.load().vs_codebook_encode(_p(c, L.f32p), M, K, sub, None, 0, C.byref(n)))
+    out = np.zeros(n.value, dtype=np.uint8)
+    check(L.load().vs_codebook_encode(_p(c, L.f32p), M, K, sub, out.ctypes.data_as(C.c_void_p), out.size, C.byref(n)))
+    return out.tobytes()
+
+
+def codebook_decode(data: bytes) -> np.ndarray:
+    """Serialized PQCodebook -> float[M][K][subDim] (SegmentCaches.decodeCodebook)."""
+    buf = np.frombuffer(data, dtype=np.uint8) if len(data) else np.zeros(1, np.uint8)
+    M, K, sub = C.c_int32(), C.c_int32(), C.c_int32()
+    check(L.load().vs_codebook_decode(buf.ctypes.data_as(C.c_void_p), len(data), None, 0, C.byref(M), C.byref(K), C.byref(sub)))
+    out = np.zeros((M.value, K.value, sub.value), dtype=np.float32)
+    check(L.load().vs_codebook_decode(buf.ctypes.data_as(C.c_void_p), len(data), _p(out, L.f32p), out.size, None, None, None))
+    return out
+
+
+STATE_ACTIVE, STATE_PENDING, STATE_SEALED, STATE_COMPACTING, STATE_WRITING = 0, 1, 2, 3, 4
+
+
+class Residency:
+    """The residency table of libvsgpu keyed by (segment id, SegmentMeta.State); it owns the handles it holds."""
+
+    @staticmethod
+    def put(seg_id: int, state: int, segment: Segment) -> None:
+        check(L.load().vs_residency_put(seg_id, state, segment.handle))
+
+    @staticmethod
+    def get(seg_id: int, state: int):
+        """-> Segment if resident in `state`; None if not resident; raises VsError(VS_ESTATE) if resident in another state."""
+        h = C.c_uint64()
+        rc = L.load().vs_residency_get(seg_id, state, C.byref(h))
+        if rc == L.VS_EHANDLE:
+            return None
+        check(rc)
+        return Segment(h.value)
+
+    @staticmethod
+    def peek(seg_id: int, state: int):
+        """-> (Segment or None, in_requested_state)."""
+        h = C.c_uint64()
+        rc = L.load().vs_residency_get(seg_id, state, C.byref(h))
+        if rc == L.VS_EHANDLE:
+            return None, False
+        if rc == L.VS_ESTATE:
+            return Segment(h.value), False
+        check(rc)
+        return Segment(h.value), True
+
+    @staticmethod
+    def invalidate(seg_id: int) -> None:
+        check(L.load().vs_residency_invalidate(seg_id))
+
+    @staticmethod
+    def set_budget(nbytes: int) -> None:
+        check(L.load().vs_residency_set_budget(nbytes))
+
+    @staticmethod
+    def stats() -> dict:
+        n, b = C.c_int64(), C.c_int64()
+        check(L.load().vs_residency_stats(C.byref(n), C.byref(b)))
+        return {"segments": n.value, "bytes": b.value}
