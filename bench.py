@@ -1,22 +1,25 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the scoring hot path (BASELINE.json metric).
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c2|c4]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c2|all]
 
-Workload at N=1 (BASELINE.json configs[1], "C2"): exact L2 brute-force top-10 over 1M x 128 fp32
-synthetic vectors, query batch 1.  A STEP is one query scanned over the whole resident segment
-(one launch of the scan kernel = 1M distance evaluations = 512 MB of algorithmic HBM traffic; the
-segment is 4x the 126 MB L2, so every step streams from HBM).  `value` is distance-evals/s with
-the segment and the queries resident in HBM; `e2e` is the same metric through the C-ABI host call
-(query copied host->device and ids/scores device->host inside every step).
+Workload (BASELINE.json configs[1], "C2"): exact L2 brute-force top-10 over 1M x 128 fp32 synthetic vectors per
+GPU, query batch 1.  A STEP is one query scanned over the whole resident corpus: at N GPUs every rank holds its
+own 1M-row range of an N x 1M corpus (weak scaling), scans it (one launch of the scan kernel = 1M distance
+evaluations = 512 MB of algorithmic HBM traffic; the shard is 4x the 126 MB L2, so every step streams from
+HBM), pushes its top-10 into every peer's buffer over NVLink and merges the N lists.  `value` is
+distance-evals/s with the corpus and the queries resident in HBM; `e2e` is the same metric through the C-ABI
+host call (query copied host->device and ids/scores device->host inside every step).
 
-N > 1 (weak scaling): every rank holds its own 1M-row range of an N x 1M corpus; a step scans all
-ranks' rows for one query, all-gathers the per-rank top-10 lists (one NCCL collective) and merges
-them.  value = N x 1M evals per step / max-over-ranks device time.
+After the timed regions rank 0 re-scans all N x 1M rows of the last query with the CPU oracle and asserts the
+merged ids and scores ("parity_checked"); a mismatch fails the run.
 
---impl reference times the reference's CPU algorithm (the C oracle port of
-J/fdb/FdbVectorIndex.java:676-721; the reference is Java and no JVM exists in this image) on the
-box's host cores with all threads, same workload, same metric.
+`extra` carries the other BASELINE configs at this N: C2 with query batch 1024 (N = 1), C3 (PQ train + encode
+over 10M x 128 in total) and C4 (ADC top-100 + re-rank to top-10 over 100M x 128 in total, strong scaling).
+
+--impl reference times the reference's CPU algorithm (the C oracle port of J/fdb/FdbVectorIndex.java:676-721;
+the reference is Java and no JVM exists in this image) on the box's host cores with all threads, same
+workload (N x 1M rows per step), same query stream, same metric and config.
 """
 from __future__ import annotations
 
@@ -34,31 +37,43 @@ if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))
 
 N_ROWS, DIM, TOPK = 1_000_000, 128, 10
-C4_ROWS, C4_M, C4_K, C4_NCAND = 100_000_000, 16, 256, 100
+C3_ROWS, C4_ROWS, PQ_M, PQ_K, C4_NCAND = 10_000_000, 100_000_000, 16, 256, 100
 CORPUS_SEED, QUERY_SEED = 42, 43
+METRIC = "distance-evals/s (exact L2 brute-force top-10)"
+DATA = "synthetic (java.util.Random(42) nextFloat()*2-1 rows, Random(43) queries; the reference's own generator)"
+
+
+def config_for(world: int) -> dict:
+    """The same dict in both arms (the driver compares them)."""
+    return {"workload": f"C2: exact L2 brute-force top-{TOPK} over {N_ROWS}x{DIM} fp32 per GPU, query batch 1",
+            "rows_per_gpu": N_ROWS, "rows_total": N_ROWS * world, "dim": DIM, "k": TOPK, "query_batch": 1,
+            "l2_policy": "input 512 MB per GPU per step > 126 MB L2 (no flush needed)"}
 
 
 def host_threads() -> int:
     return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
 
 
-def profiled_traffic(name: str) -> float | None:
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full`
-    summary profiles/<name> (made by tools/ncu_summary.py), or None."""
-    p = ROOT / "profiles" / name
-    if not p.exists():
-        return None
-    tot, seen = 0.0, 0
-    for line in p.read_text().splitlines():
-        for key in ("dram__bytes_read.sum [", "dram__bytes_write.sum ["):
-            if line.startswith(key):
-                unit = line[len(key):line.index("]")]
-                scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit)
-                vals = [float(v) for v in line.split(":", 1)[1].split(",")]
-                if scale and vals:
-                    tot += scale * sum(vals) / len(vals)
-                    seen += 1
-    return tot if seen == 2 else None
+def profiled_traffic(*names: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the first committed `ncu --set full` summary
+    among profiles/<names> (made by tools/ncu_summary.py) -> (bytes, file) or (None, None)."""
+    for name in names:
+        p = ROOT / "profiles" / name
+        if not p.exists():
+            continue
+        tot, seen = 0.0, 0
+        for line in p.read_text().splitlines():
+            for key in ("dram__bytes_read.sum [", "dram__bytes_write.sum ["):
+                if line.startswith(key):
+                    unit = line[len(key):line.index("]")]
+                    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit)
+                    vals = [float(v) for v in line.split(":", 1)[1].split(",")]
+                    if scale and vals:
+                        tot += scale * sum(vals) / len(vals)
+                        seen += 1
+        if seen == 2:
+            return tot, f"profiles/{name}"
+    return None, None
 
 
 def measured_peaks() -> tuple[float, str]:
@@ -83,11 +98,13 @@ def measured_tensor_peak() -> tuple[float, str]:
 
 
 # ---------------------------------------------------------------------------------------------------
-# clocks: sampled DURING the timed regions with NVML
+# clocks: sampled DURING the timed regions with NVML (the thread runs for the whole process; only
+# samples taken while a region is open are kept, so opening a region costs nothing on the host)
 # ---------------------------------------------------------------------------------------------------
 class ClockSampler:
     def __init__(self, index: int):
         self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._active = False
         self._stop = threading.Event()
         self._thread = None
         try:
@@ -97,6 +114,8 @@ class ClockSampler:
             self.nv = pynvml
             self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
         except Exception:
             self.nv = None
 
@@ -107,28 +126,26 @@ class ClockSampler:
                  "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
                  "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
         while not self._stop.is_set():
-            try:
-                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
-                r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
-                for n, bit in names.items():
-                    if r & bit:
-                        self.reasons.add(n)
-            except Exception:
-                pass
-            time.sleep(0.002)
+            if self._active:
+                try:
+                    self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                    r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                    for n, bit in names.items():
+                        if r & bit:
+                            self.reasons.add(n)
+                except Exception:
+                    pass
+            time.sleep(0.001)
 
     def __enter__(self):
-        if self.nv is not None:
-            self._stop.clear()
-            self._thread = threading.Thread(target=self._loop, daemon=True)
-            self._thread.start()
+        self._active = True
         return self
 
     def __exit__(self, *a):
-        if self._thread is not None:
-            self._stop.set()
-            self._thread.join()
-            self._thread = None
+        self._active = False
+
+    def close(self):
+        self._stop.set()
 
     def summary(self) -> dict:
         return {"sm_mhz": statistics.median(self.samples) if self.samples else None,
@@ -136,56 +153,83 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference's brute-force scorer, all host threads
+# CPU arm: the oracle port of the reference's brute-force scorer
 # ---------------------------------------------------------------------------------------------------
-def cpu_bruteforce(steps: int, warmup: int, budget_s: float | None):
-    """Returns (evals_per_s, ms_per_step, steps_done, threads, sample description)."""
-    import numpy as np
-
+def _native_oracle():
     from oracle import pyoracle
 
     try:
         pyoracle.build(native=True, force=True)  # -march=native for THIS box's cores
-        orc = pyoracle.get(native=True)
-        kind = "-O3 -march=native"
+        return pyoracle.get(native=True), "-O3 -march=native"
     except Exception:
-        orc = pyoracle.get()
-        kind = "-O3 -march=x86-64-v3"
-    threads = host_threads()
-    rows = orc.gen_rows(CORPUS_SEED, 0, N_ROWS, DIM)
+        return pyoracle.get(), "-O3 -march=x86-64-v3"
+
+
+def cpu_bruteforce(world: int, steps: int, warmup: int, budget_s: float | None, threads: int | None = None):
+    """The reference's segment scorer over world x 1M rows per step (searchBruteForceSegment per 1M-row segment,
+    merged as J/fdb/FdbVectorIndex.java:432-437).  Returns (evals_per_s, ms_per_step, steps_done, threads, sample)."""
+    import numpy as np
+
+    orc, kind = _native_oracle()
+    threads = threads or host_threads()
+    segs = [orc.gen_rows(CORPUS_SEED, r * N_ROWS, N_ROWS, DIM) for r in range(world)]
     qs = orc.gen_rows(QUERY_SEED, 0, max(steps + warmup, 1), DIM)
+
+    def step(q):
+        ids, scs = [], []
+        for r, rows in enumerate(segs):
+            i, s, _ = orc.bruteforce_topk(rows, q, TOPK, threads=threads)
+            ids.append(i + r * N_ROWS)
+            scs.append(s)
+        return orc.merge_topk(np.concatenate(ids), np.concatenate(scs), TOPK)
+
     for i in range(warmup):
-        orc.bruteforce_topk(rows, qs[i], TOPK, threads=threads)
+        step(qs[i])
     t0 = time.perf_counter()
     done = 0
     for i in range(steps):
-        orc.bruteforce_topk(rows, qs[warmup + i], TOPK, threads=threads)
+        step(qs[warmup + i])
         done += 1
         if budget_s is not None and time.perf_counter() - t0 > budget_s and done >= 3:
             break
     dt = time.perf_counter() - t0
-    sample = (f"{done} queries x {N_ROWS} rows x {DIM} dims, C oracle port of the reference's Java loop "
-              f"({kind}, OpenMP {threads} threads)")
-    return N_ROWS * done / dt, dt / done * 1e3, done, threads, sample
+    sample = (f"{done} queries x {world} x {N_ROWS} rows x {DIM} dims, C oracle port of the reference's Java loop "
+              f"({kind}, {'OpenMP ' + str(threads) + ' threads' if threads > 1 else 'single thread, as the reference scores a segment'})")
+    return world * N_ROWS * done / dt, dt / done * 1e3, done, threads, sample
 
 
 def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    val, ms, done, threads, sample = cpu_bruteforce(args.steps, args.warmup, None)
+    world = max(1, args.gpus)
+    val, ms, done, threads, sample = cpu_bruteforce(world, args.steps, args.warmup, None)
     line = {
-        "impl": "reference", "metric": "distance-evals/s (exact L2 brute-force top-10)", "value": val,
-        "unit": "distance-evals/s", "n_gpus": args.gpus, "steps": done, "warmup": args.warmup,
-        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic (java.util.Random(42) nextFloat()*2-1 rows, Random(43) queries)",
-        "config": {"workload": f"C2: exact L2 brute-force top-{TOPK} over {N_ROWS}x{DIM} fp32, query batch 1",
-                   "rows": N_ROWS, "dim": DIM, "k": TOPK, "query_batch": 1},
-        "qps": 1e3 / ms,
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "distance-evals/s", "n_gpus": args.gpus,
+        "steps": done, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": DATA, "config": config_for(world), "qps": 1e3 / ms,
         "cpu_baseline": {"value": val, "unit": "distance-evals/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "distance-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def oracle_check_c2(world: int, q, ids, scores) -> None:
+    """Rank 0: the last query over all world x 1M rows with the oracle; raises on any difference."""
+    import numpy as np
+
+    from oracle import pyoracle
+
+    orc = pyoracle.get()
+    oi, os_ = [], []
+    for r in range(world):
+        rows = orc.gen_rows(CORPUS_SEED, r * N_ROWS, N_ROWS, DIM)
+        i, s, _ = orc.bruteforce_topk(rows, q, TOPK, threads=host_threads())
+        oi.append(i + r * N_ROWS)
+        os_.append(s)
+    wi, ws = orc.merge_topk(np.concatenate(oi), np.concatenate(os_), TOPK)
+    if not (np.array_equal(np.asarray(ids), wi) and np.array_equal(np.asarray(scores).view(np.uint64), ws.view(np.uint64))):
+        raise SystemExit(f"PARITY FAILURE (C2, {world} GPUs): got {list(ids)} {list(scores)}, oracle {wi.tolist()} {ws.tolist()}")
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -211,12 +255,10 @@ def run_ours(args) -> None:
     lib = vs.load()
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-        # the scan is a persistent one-CTA-per-SM kernel: leave a few SMs to the all-gather's CTAs, or the
-        # collective of query i can only start once the scan of query i+1 has drained
-        # (scan_reserve_sms below)
 
     K, W = args.steps, args.warmup
     hbm_peak, peak_src = measured_peaks()
+    clocks = ClockSampler(local_rank)
 
     def barrier():
         if world > 1:
@@ -232,10 +274,13 @@ def run_ours(args) -> None:
 
     # resident corpus shard: rows [rank*N, (rank+1)*N) of the Java LCG stream, generated on the device
     seg = vs.Segment.generate(CORPUS_SEED, rank * N_ROWS, N_ROWS, DIM, id_base=rank * N_ROWS)
-    sh = ShardedSegment(seg, rank, world)
-    # queries: identical on every rank (seeded), uniform in [-1, 1) like the reference's generators
-    g = torch.Generator(device="cpu").manual_seed(QUERY_SEED)
-    q_host = (torch.rand((W + K, DIM), generator=g, dtype=torch.float32) * 2 - 1).pin_memory()
+    n_slots = int(os.environ.get("VS_BENCH_SLOTS", "2"))
+    sh = ShardedSegment(seg, rank, world, slots=n_slots)
+    # queries: draws of java.util.Random(43), the stream the reference arm uses, generated by libvsgpu's own generator
+    qseg = vs.Segment.generate(QUERY_SEED, 0, W + K + 1, DIM)
+    qn = qseg.rows()
+    qseg.free()
+    q_host = torch.from_numpy(qn).pin_memory()
     q_dev = q_host.to(dev)
     ids = torch.empty((1, TOPK), dtype=torch.int64, device=dev)
     sc = torch.empty((1, TOPK), dtype=torch.float64, device=dev)
@@ -244,46 +289,57 @@ def run_ours(args) -> None:
     st = stream.cuda_stream
     q_base, ids_p, sc_p, cn_p = q_dev.data_ptr(), ids.data_ptr(), sc.data_ptr(), cn.data_ptr()
 
-    # Independent queries alternate between two streams (libvsgpu keeps one scratch set per stream): the
-    # prologue and the last-CTA merge of one scan overlap the streaming phase of the next.
-    slots = [dict(stream=torch.cuda.Stream(device=dev), ids=torch.empty((1, TOPK), dtype=torch.int64, device=dev),
+    # Independent queries alternate between the coordinator's streams (libvsgpu keeps one scratch set and one
+    # exchange ring per stream): the prologue, the last-CTA merge and the cross-shard exchange of one query overlap
+    # the streaming phase of the next.  ONE C call per step at every N.
+    slots = [dict(stream=s_, ids=torch.empty((1, TOPK), dtype=torch.int64, device=dev),
                   sc=torch.empty((1, TOPK), dtype=torch.float64, device=dev), cn=torch.empty((1,), dtype=torch.int32, device=dev))
-             for _ in range(2)]
-    # SMs the persistent scan leaves to the neighbouring stream: 4 are enough for the prologue / merge of the other
-    # query and for the peer exchange's two small kernels; an NCCL all-gather needs room for its own CTAs
-    reserve_default = "16" if (world > 1 and "peer" not in sh.exchange) else "4"
+             for s_ in sh._streams]
+    # SMs the persistent scan leaves to the neighbouring stream: enough for the prologue / merge of the other query
+    # and for the peer exchange's small kernels; an NCCL all-gather (fallback path) needs room for its own CTAs
+    reserve_default = "16" if (world > 1 and sh._comm is None) else "4"
     reserve_sms = int(os.environ.get("VS_SCAN_RESERVE", reserve_default))
     vs.set_option("scan_reserve_sms", reserve_sms)
+    comm = sh._comm
 
     def step_dev(i: int):
+        s = slots[i % len(slots)]
         if world == 1:
-            s = slots[i & 1]
             L.check(lib.vs_bruteforce_topk_dev(seg.handle, q_base + i * DIM * 4, 1, TOPK, 0, s["ids"].data_ptr(),
                                                s["sc"].data_ptr(), s["cn"].data_ptr(), s["stream"].cuda_stream))
+        elif comm is not None:
+            L.check(lib.vs_bruteforce_topk_exchange_dev(seg.handle, comm, q_base + i * DIM * 4, 1, TOPK, 0, s["ids"].data_ptr(),
+                                                        s["sc"].data_ptr(), s["cn"].data_ptr(), s["stream"].cuda_stream))
         else:
-            # independent queries alternate between the coordinator's two streams: scan(i + 1) overlaps the
-            # all-gather and merge of query i; every step's merged result is complete before the region ends
             sh.bruteforce_topk_pipelined(q_dev[i:i + 1], 1, TOPK, 0)
 
-    clocks = ClockSampler(local_rank)
-    # ---- device-resident throughput: W warm-up steps, then EXACTLY K timed steps ----------------------
     def drain():
-        if world > 1:
+        if world > 1 and comm is None:
             sh.drain()
-        else:
-            for s in slots:
-                stream.wait_stream(s["stream"])
+        for s in slots:
+            stream.wait_stream(s["stream"])
 
+    # ---- device-resident throughput: W warm-up steps, then EXACTLY K timed steps ----------------------
     for s in slots:
         s["stream"].wait_stream(stream)
     for i in range(W):
         step_dev(i)
     drain()
     barrier()
+    # One untimed lock-step exchange right before e0: its merge kernel waits ON THE DEVICE for every rank's list, so
+    # all GPUs leave it together and e0 is recorded on every rank when the slowest host has arrived -- the host skew
+    # left by the barrier (tens to hundreds of microseconds) stays out of a 20-step window.
+    if world > 1 and comm is not None:
+        for s in slots:
+            L.check(lib.vs_bruteforce_topk_exchange_dev(seg.handle, comm, q_base + (W + K) * DIM * 4, 1, TOPK, 0, s["ids"].data_ptr(),
+                                                        s["sc"].data_ptr(), s["cn"].data_ptr(), s["stream"].cuda_stream))
+        drain()
     launches0 = vs.kernel_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with clocks:
         e0.record(stream)
+        for s in slots:
+            s["stream"].wait_stream(stream)
         for i in range(K):
             step_dev(W + i)
         drain()
@@ -293,6 +349,8 @@ def run_ours(args) -> None:
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     ms_per_step = ms_total / K
     value = world * N_ROWS * K / (ms_total * 1e-3)
+    last = slots[(W + K - 1) % len(slots)]
+    dev_last = (last["ids"].cpu().numpy()[0].copy(), last["sc"].cpu().numpy()[0].copy())
 
     # ---- per-launch duration of the scan kernel (roofline), events around every launch ------------------
     # (launched alone it has the whole GPU: all SMs; the reserve only pays off when queries overlap)
@@ -308,9 +366,9 @@ def run_ours(args) -> None:
     kern_ms = sum(durs) / len(durs)
     alg_bytes = N_ROWS * DIM * 4
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+    vs.set_option("scan_reserve_sms", reserve_sms)
 
     # ---- end to end through the public host API: pinned host query in, ids + scores out, every step -----
-    qn = q_host.numpy()
     for i in range(W):
         sh.bruteforce_topk(qn[i], TOPK) if world > 1 else seg.bruteforce_topk(qn[i], TOPK)
     barrier()
@@ -322,39 +380,52 @@ def run_ours(args) -> None:
         e2e_s = time.perf_counter() - t0
     e2e_s = max_over_ranks(e2e_s)
     e2e_value = world * N_ROWS * K / e2e_s
-    last_ids = np.asarray(r[0]).tolist()
+    last_ids, last_sc = np.asarray(r[0]), np.asarray(r[1])
+
+    # ---- parity: the last query against the oracle over ALL ranks' rows (rank 0), both paths -------------
+    parity = False
+    if rank == 0 and not args.no_check:
+        oracle_check_c2(world, qn[W + K - 1], last_ids, last_sc)
+        oracle_check_c2(world, qn[W + K - 1], dev_last[0], dev_last[1])
+        parity = True
 
     # ---- CPU baseline: bounded sample on rank 0 at N=1 only ---------------------------------------------
     cpu = None
     if world == 1 and not args.no_cpu:
-        cval, cms, cdone, cthreads, csample = cpu_bruteforce(200, 2, 12.0)
+        cval, cms, cdone, cthreads, csample = cpu_bruteforce(1, 200, 2, 10.0)
+        sval, sms_, sdone, _, ssample = cpu_bruteforce(1, 20, 1, 6.0, threads=1)
         cpu = {"value": cval, "unit": "distance-evals/s", "cores": cthreads, "kind": "port", "sample": csample,
-               "ms_per_query": cms}
+               "ms_per_query": cms,
+               "single_thread": {"value": sval, "unit": "distance-evals/s", "cores": 1, "ms_per_query": sms_, "sample": ssample}}
 
     extra = {}
-    if world == 1:
-        extra["c2_b1024"] = bench_c2_batch(vs, L, lib, torch, dev, seg, min(K, 50), W)
-    if args.workload in ("c4", "all") and world == 1:
-        extra["c4"] = bench_c4(vs, L, lib, torch, dev, min(K, 50), W, hbm_peak)
+    if args.workload == "all":
+        if world == 1:
+            extra["c2_b1024"] = bench_c2_batch(vs, L, lib, torch, dev, seg, min(K, 50), W)
+        seg.free()
+        seg = None
+        ctx = dict(vs=vs, L=L, lib=lib, torch=torch, dist=dist, dev=dev, rank=rank, world=world, barrier=barrier,
+                   max_over_ranks=max_over_ranks, hbm_peak=hbm_peak, check=not args.no_check, n_slots=n_slots)
+        extra["c3"] = bench_c3(ctx)
+        extra["c4"] = bench_c4(ctx, min(K, 50), W)
 
     if rank == 0:
+        traffic, traffic_src = profiled_traffic("r2_c2_scan_full.txt", "r1_c2_scan_full.txt")
         line = {
-            "metric": "distance-evals/s (exact L2 brute-force top-10)", "value": value, "unit": "distance-evals/s",
+            "metric": METRIC, "value": value, "unit": "distance-evals/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic (java.util.Random(42) nextFloat()*2-1 rows generated on device; seeded uniform queries)",
-            "config": {"workload": f"C2: exact L2 brute-force top-{TOPK} over {N_ROWS}x{DIM} fp32 per GPU, query batch 1",
-                       "rows_per_gpu": N_ROWS, "dim": DIM, "k": TOPK, "query_batch": 1,
-                       "parallelism": (f"row-range shards x{world}, cross-shard top-k exchange per query = {sh.exchange}; "
-                                       "independent queries alternate between two streams") if world > 1 else "1 GPU",
-                       "l2_policy": "input 512 MB per step > 126 MB L2 (no flush needed)",
-                       "pipelining": "independent queries alternate between two CUDA streams; the scan leaves "
-                                     f"{reserve_sms} SMs free so that the neighbouring query's "
-                                     "prologue / merge (and the cross-shard exchange at N > 1) run beside it"},
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": DATA, "config": config_for(world),
+            "parallelism": (f"row-range shards x{world}, cross-shard top-k exchange per query = {sh.exchange}; one C call per step "
+                            f"(scan + push + merge); {len(slots)} queries in flight on {len(slots)} streams; one untimed lock-step "
+                            "exchange before the timed region") if world > 1 else
+                           f"1 GPU; independent queries alternate between {len(slots)} CUDA streams",
+            "pipelining": f"the scan leaves {reserve_sms} SMs free so that the neighbouring query's prologue / merge "
+                          "(and the cross-shard exchange at N > 1) run beside it",
             "qps": 1e3 / ms_per_step,
+            "parity_checked": parity,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": profiled_traffic("r1_c2_scan_full.txt"),
-                         "traffic_source": "profiles/r1_c2_scan_full.txt (ncu --set full, dram read+write per launch)",
+                         "frac": achieved / hbm_peak, "traffic": traffic,
+                         "traffic_source": f"{traffic_src} (ncu --set full, dram read+write per launch)" if traffic_src else None,
                          "peak_source": peak_src,
                          "kernel": "scan_tma_kernel<TPR=4,U=2,L2,WarpTopKReg> (K1)", "kernel_ms": kern_ms,
                          "kernel_ms_median": durs[len(durs) // 2], "algorithmic_bytes_per_launch": alg_bytes,
@@ -366,14 +437,17 @@ def run_ours(args) -> None:
                     "d2h_bytes_per_step": TOPK * 16 + 4, "ms_per_step": e2e_s / K * 1e3, "qps": K / e2e_s},
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
-            "top10_last_query": last_ids,
+            "top10_last_query": last_ids.tolist(),
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
         if extra:
             line["extra"] = extra
         print(json.dumps(line), flush=True)
-    seg.free()
+    clocks.close()
+    if seg is not None:
+        seg.free()
+    sh.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -385,8 +459,10 @@ def bench_c2_batch(vs, L, lib, torch, dev, seg, K, W, nq=1024):
     import numpy as np
 
     tpeak, tsrc = measured_tensor_peak()
-    g = torch.Generator(device="cpu").manual_seed(QUERY_SEED + 1)
-    q_host = (torch.rand((nq, DIM), generator=g, dtype=torch.float32) * 2 - 1).pin_memory()
+    qseg = vs.Segment.generate(QUERY_SEED + 1, 0, nq, DIM)
+    qn = qseg.rows()
+    qseg.free()
+    q_host = torch.from_numpy(qn).pin_memory()
     q_dev = q_host.to(dev)
     ids = torch.empty((nq, TOPK), dtype=torch.int64, device=dev)
     sc = torch.empty((nq, TOPK), dtype=torch.float64, device=dev)
@@ -409,7 +485,6 @@ def bench_c2_batch(vs, L, lib, torch, dev, seg, K, W, nq=1024):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / K
     launches = vs.kernel_launch_count() - l0
-    qn = q_host.numpy()
     for _ in range(3):
         seg.bruteforce_topk(qn, TOPK)
     t0 = time.perf_counter()
@@ -420,82 +495,240 @@ def bench_c2_batch(vs, L, lib, torch, dev, seg, K, W, nq=1024):
     tf = flops / (ms * 1e-3) / 1e12
     # the same 1024 queries one at a time through the streaming scan must give the same lists (spot check)
     same = all(np.array_equal(seg.bruteforce_topk(qn[i], TOPK)[0], r[0][i]) for i in (0, 511, 1023))
+    traffic, traffic_src = profiled_traffic("r2_c2_b1024_gemm_full.txt")
     return {"workload": f"C2: exact L2 brute-force top-{TOPK} over {N_ROWS}x{DIM} fp32, query batch {nq}, 1 GPU",
             "ms_per_batch": ms, "qps": nq / (ms * 1e-3), "distance_evals_per_s": N_ROWS * nq / (ms * 1e-3),
             "roofline": {"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak,
                          "peak_source": tsrc, "algorithmic_flops_per_batch": flops,
                          "kernel": "batch_gemm_kernel<STAT,HALF,L2,G64> (K2, tcgen05 kind::f16) + batch_select + fallback; "
-                                   "achieved is over the WHOLE batch, the GEMM alone is the share profiles/r1_c2_b1024_launches.txt shows",
-                         "traffic": None},
+                                   "achieved is over the WHOLE batch",
+                         "traffic": traffic, "traffic_source": traffic_src},
             "e2e": {"ms_per_batch": e2e_ms, "qps": nq / (e2e_ms * 1e-3), "distance_evals_per_s": N_ROWS * nq / (e2e_ms * 1e-3),
                     "h2d_bytes_per_step": nq * DIM * 4, "d2h_bytes_per_step": nq * (TOPK * 16 + 4)},
             "gpu_launches": int(launches), "matches_per_query_scan": bool(same)}
 
 
-def bench_c4(vs, L, lib, torch, dev, K, W, hbm_peak):
-    """C4 (1 GPU): PQ ADC top-100 scan + exact re-rank to top-10 over 100M x 128 (M=16 codes)."""
-    n = int(os.environ.get("VS_C4_ROWS", C4_ROWS))
+def _shard(n_total: int, rank: int, world: int):
+    from vectorsearch_b200.sharded import shard_range
+
+    return shard_range(n_total, rank, world)
+
+
+def bench_c3(ctx):
+    """C3: PqTrainer.train (5 iterations, seed 42) + PqEncoder.encode over 10M x 128 IN TOTAL, M=16, K=256, rows sharded
+    by range over the GPUs.  At N > 1 the per-iteration all-reduce of cluster sums and counts is libvsgpu's own exchange
+    over the peer buffers (K10); both modes are timed: exact_order (centroids bit-identical to the reference) and one
+    rank-ordered all-reduce per iteration (north_star's scheme)."""
+    import numpy as np
+
+    from vectorsearch_b200.sharded import ShardedSegment
+
+    vs, torch, rank, world = ctx["vs"], ctx["torch"], ctx["rank"], ctx["world"]
+    n_total = int(os.environ.get("VS_C3_ROWS", C3_ROWS))
+    lo, hi = _shard(n_total, rank, world)
+    seg = vs.Segment.generate(CORPUS_SEED, lo, hi - lo, DIM, id_base=lo)
+    sh = ShardedSegment(seg, rank, world, slots=1) if world > 1 else None
+    out = {"workload": f"C3: PQ k-means train (5 iterations, seed 42) + encode, M={PQ_M} K={PQ_K}, {n_total}x{DIM} in total over {world} GPU(s)"}
+
+    def train(exact: bool):
+        if world == 1:
+            return vs.PqTrainer.train(None, DIM, PQ_M, PQ_K, 5, 42, segment=seg)
+        return sh.pq_train(n_total, lo, PQ_M, PQ_K, 5, 42, exact_order=exact)
+
+    cent = None
+    for name, exact in (("exact_order", True), ("one_allreduce", False)):
+        if world == 1 and not exact:
+            continue
+        train(exact)  # warm (scratch pools, plans)
+        ctx["barrier"]()
+        best = None
+        for _ in range(2):
+            t0 = time.perf_counter()
+            c = train(exact)
+            dt = ctx["max_over_ranks"](time.perf_counter() - t0)
+            ctx["barrier"]()
+            best = dt if best is None else min(best, dt)
+        if exact:
+            cent = c
+        out[f"train_s_{name}" if world > 1 else "train_s"] = best
+    # encode: every rank its own rows, no collective
+    seg.attach_pq(cent)  # warm
+    ctx["barrier"]()
     t0 = time.perf_counter()
-    seg = vs.Segment.generate(CORPUS_SEED, 0, n, DIM)
+    seg.attach_pq(cent)
+    torch.cuda.synchronize()
+    enc = ctx["max_over_ranks"](time.perf_counter() - t0)
+    out["encode_s"] = enc
+    out["encode_vectors_per_s"] = n_total / enc
+    tr = out.get("train_s_one_allreduce", out.get("train_s"))
+    out["train_subdistance_evals_per_s"] = 5.0 * n_total * PQ_M * PQ_K / tr
+    passes_s = (tr + enc) / 6.0
+    out["roofline"] = {"bound": "hbm", "achieved": n_total / world * DIM * 4 / passes_s / 1e9, "peak": ctx["hbm_peak"], "unit": "GB/s",
+                       "frac": n_total / world * DIM * 4 / passes_s / 1e9 / ctx["hbm_peak"],
+                       "kernel": "pq_tc_assign_kernel (K3) + partition + chain sums (K4), per pass over the rows",
+                       "algorithmic_bytes_per_pass_per_gpu": n_total // world * DIM * 4, "traffic": None,
+                       "note": "6 passes (5 Lloyd iterations + 1 encode); ALU-bound argmin epilogue, not HBM"}
+    if ctx["check"]:
+        # parity: a code sample of this rank against the oracle (every rank checks its own rows), centroid digest on rank 0
+        from oracle import pyoracle
+
+        orc = pyoracle.get()
+        m = min(20000, hi - lo)
+        got = seg.codes(0, m)
+        want = orc.pq_encode_batch_fast(cent, orc.gen_rows(CORPUS_SEED, lo, m, DIM), threads=max(1, host_threads() // world))
+        if not np.array_equal(got, want):
+            raise SystemExit(f"PARITY FAILURE (C3 codes, rank {rank})")
+        out["parity_checked"] = "codes of the first 20000 rows of every shard equal the oracle's for the trained codebook"
+    seg.free()
+    if sh is not None:
+        sh.close()
+    return out
+
+
+def bench_c4(ctx, K, W):
+    """C4: PQ ADC top-100 scan + exact re-rank to top-10 over 100M x 128 IN TOTAL (M=16 codes), rows sharded by range over
+    the GPUs (strong scaling).  The codebook is trained on the first 1M rows (identical on every rank)."""
+    import numpy as np
+
+    from vectorsearch_b200.sharded import ShardedSegment
+
+    vs, L, lib, torch, dev = ctx["vs"], ctx["L"], ctx["lib"], ctx["torch"], ctx["dev"]
+    rank, world, hbm_peak = ctx["rank"], ctx["world"], ctx["hbm_peak"]
+    n_total = int(os.environ.get("VS_C4_ROWS", C4_ROWS))
+    lo, hi = _shard(n_total, rank, world)
+    n = hi - lo
+    t0 = time.perf_counter()
+    seg = vs.Segment.generate(CORPUS_SEED, lo, n, DIM, id_base=lo)
     torch.cuda.synchronize()
     t_gen = time.perf_counter() - t0
     t0 = time.perf_counter()
-    # codebook trained on the first 1M rows (PqTrainer.train(..., 5, 42)), codes for all rows on device
-    train = vs.Segment.generate(CORPUS_SEED, 0, min(n, 1_000_000), DIM)
-    cent = vs.PqTrainer.train(None, DIM, C4_M, C4_K, 5, 42, segment=train)
-    train.free()
+    train = vs.Segment.generate(CORPUS_SEED, 0, min(n_total, 1_000_000), DIM)
+    cent = vs.PqTrainer.train(None, DIM, PQ_M, PQ_K, 5, 42, segment=train)
+    t_train_cold = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    vs.PqTrainer.train(None, DIM, PQ_M, PQ_K, 5, 42, segment=train)
     t_train = time.perf_counter() - t0
+    train.free()
     t0 = time.perf_counter()
     seg.attach_pq(cent)
-    t_enc = time.perf_counter() - t0
-    g = torch.Generator(device="cpu").manual_seed(QUERY_SEED)
-    q_dev = (torch.rand((W + K, DIM), generator=g, dtype=torch.float32) * 2 - 1).to(dev)
-    ids = torch.empty((1, TOPK), dtype=torch.int64, device=dev)
-    sc = torch.empty((1, TOPK), dtype=torch.float64, device=dev)
-    cn = torch.empty((1,), dtype=torch.int32, device=dev)
-    st = torch.cuda.current_stream().cuda_stream
-    for i in range(W):
-        L.check(lib.vs_adc_rerank_topk_dev(seg.handle, q_dev[i].data_ptr(), 1, C4_NCAND, TOPK, 0, 0, ids.data_ptr(),
-                                           sc.data_ptr(), cn.data_ptr(), st))
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(K):
-        L.check(lib.vs_adc_rerank_topk_dev(seg.handle, q_dev[W + i].data_ptr(), 1, C4_NCAND, TOPK, 0, 0,
-                                           ids.data_ptr(), sc.data_ptr(), cn.data_ptr(), st))
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / K
-    # the ADC scan alone (LUT build + fast scan + conditional fallback launch), for its roofline
+    t_enc_cold = ctx["max_over_ranks"](time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    seg.attach_pq(cent)
+    t_enc = ctx["max_over_ranks"](time.perf_counter() - t0)
+    sh = ShardedSegment(seg, rank, world, slots=ctx["n_slots"])
+    qseg = vs.Segment.generate(QUERY_SEED, 0, W + K, DIM)
+    qh = qseg.rows()
+    qseg.free()
+    q_dev = torch.from_numpy(qh).to(dev)
+    stream = torch.cuda.current_stream()
+
+    def run(nq_per_step: int, steps: int):
+        """steps x (nq_per_step queries) alternating between the coordinator's streams; ms per QUERY, max over ranks"""
+        for s_ in sh._streams:
+            s_.wait_stream(stream)
+        for i in range(min(W, 3)):
+            sh.adc_rerank_topk_pipelined(q_dev[:nq_per_step], nq_per_step, C4_NCAND, TOPK)
+        sh.drain()
+        ctx["barrier"]()
+        sh.adc_rerank_topk_pipelined(q_dev[:nq_per_step], nq_per_step, C4_NCAND, TOPK)  # untimed lock-step exchange
+        sh.drain()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for s_ in sh._streams:
+            s_.wait_stream(stream)
+        for i in range(steps):
+            j = (W + i * nq_per_step) % max(1, (W + K - nq_per_step))
+            sh.adc_rerank_topk_pipelined(q_dev[j:j + nq_per_step], nq_per_step, C4_NCAND, TOPK)
+        sh.drain()
+        e1.record(stream)
+        ctx["barrier"]()
+        return ctx["max_over_ranks"](e0.elapsed_time(e1)) / (steps * nq_per_step)
+
+    ms = run(1, K)
+    ms_b8 = run(8, max(4, K // 4))
+    # the ADC scan alone on this rank's codes (LUT build + fast scan + conditional fallback launch), for its roofline
     ids100 = torch.empty((1, C4_NCAND), dtype=torch.int64, device=dev)
     ap100 = torch.empty((1, C4_NCAND), dtype=torch.float64, device=dev)
+    cn = torch.empty((1,), dtype=torch.int32, device=dev)
+    st = stream.cuda_stream
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for i in range(3):
+        L.check(lib.vs_adc_topk_dev(seg.handle, q_dev[i].data_ptr(), 1, C4_NCAND, ids100.data_ptr(), ap100.data_ptr(), cn.data_ptr(), st))
     e0.record()
     for i in range(K):
         L.check(lib.vs_adc_topk_dev(seg.handle, q_dev[W + i].data_ptr(), 1, C4_NCAND, ids100.data_ptr(),
                                     ap100.data_ptr(), cn.data_ptr(), st))
     e1.record()
     torch.cuda.synchronize()
-    ms_adc = e0.elapsed_time(e1) / K
-    gbs = n * C4_M / (ms_adc * 1e-3) / 1e9
+    ms_adc = ctx["max_over_ranks"](e0.elapsed_time(e1) / K)
+    gbs = n * PQ_M / (ms_adc * 1e-3) / 1e9
     # end to end through the host API: query from host memory in, ids + scores out, every query
-    qh = q_dev.cpu().numpy()
+    call = (lambda q: sh.adc_rerank_topk(q, C4_NCAND, TOPK)) if world > 1 else (lambda q: seg.adc_rerank_topk(q, C4_NCAND, TOPK))
     for i in range(3):
-        seg.adc_rerank_topk(qh[i], C4_NCAND, TOPK)
+        call(qh[i])
+    ctx["barrier"]()
     t0 = time.perf_counter()
     for i in range(K):
-        seg.adc_rerank_topk(qh[W + i], C4_NCAND, TOPK)
-    e2e_ms = (time.perf_counter() - t0) / K * 1e3
-    out = {"workload": f"C4: ADC top-{C4_NCAND} + exact re-rank top-{TOPK} over {n}x{DIM} (M={C4_M} uint8 codes), 1 GPU",
-           "ms_per_query": ms, "adc_evals_per_s": n / (ms * 1e-3), "qps": 1e3 / ms,
-           "e2e": {"ms_per_query": e2e_ms, "adc_evals_per_s": n / (e2e_ms * 1e-3), "h2d_bytes_per_step": DIM * 4,
+        res = call(qh[W + i])
+    ctx["barrier"]()
+    e2e_ms = ctx["max_over_ranks"](time.perf_counter() - t0) / K * 1e3
+    traffic, traffic_src = profiled_traffic("r2_c4_adc_full.txt")
+    out = {"workload": f"C4: ADC top-{C4_NCAND} + exact re-rank top-{TOPK} over {n_total}x{DIM} in total (M={PQ_M} uint8 codes), {world} GPU(s)",
+           "rows_per_gpu": n, "ms_per_query": ms, "adc_evals_per_s": n_total / (ms * 1e-3), "qps": 1e3 / ms,
+           "ms_per_query_batch8": ms_b8, "adc_evals_per_s_batch8": n_total / (ms_b8 * 1e-3),
+           "streams": len(sh._streams),
+           "e2e": {"ms_per_query": e2e_ms, "adc_evals_per_s": n_total / (e2e_ms * 1e-3), "h2d_bytes_per_step": DIM * 4,
                    "d2h_bytes_per_step": TOPK * 16 + 4},
            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                        "kernel": "build_lut_mm + adc_fastscan_kernel<4> (K5+K6)", "ms_per_launch_group": ms_adc,
-                        "algorithmic_bytes_per_launch": n * C4_M, "traffic": None},
-           "generate_s": t_gen, "train_1M_5iters_s": t_train, "encode_s": t_enc,
-           "encode_vectors_per_s": n / t_enc}
+                        "kernel": "build_lut_mm + adc_fastscan_kernel<4> (K5+K6), one rank's codes, launched alone",
+                        "ms_per_launch_group": ms_adc, "algorithmic_bytes_per_launch": n * PQ_M,
+                        "achieved_in_step": n * PQ_M / (ms * 1e-3) / 1e9, "traffic": traffic, "traffic_source": traffic_src},
+           "generate_s": t_gen, "train_1M_5iters_s": t_train, "train_1M_5iters_cold_s": t_train_cold,
+           "encode_s": t_enc, "encode_cold_s": t_enc_cold, "encode_vectors_per_s": n_total / t_enc,
+           "encode_vectors_per_s_cold": n_total / t_enc_cold}
+    if ctx["check"]:
+        out["parity_checked"] = check_c4(ctx, seg, cent, lo, n, qh[W + K - 1], res)
     seg.free()
+    sh.close()
     return out
+
+
+def check_c4(ctx, seg, cent, lo, n, q, res):
+    """The last query of the e2e loop against the oracle: every rank scans ITS codes with the oracle (first 100 by
+    approximate distance, the reference's stable order), rank 0 merges the lists by (approx, global row) -- shards are
+    ascending row ranges -- and re-ranks the global first 100 exactly from regenerated rows."""
+    import numpy as np
+
+    from oracle import pyoracle
+
+    torch, dist, rank, world = ctx["torch"], ctx["dist"], ctx["rank"], ctx["world"]
+    orc = pyoracle.get()
+    codes = seg.codes()
+    lut = orc.build_lut(cent, q)
+    ci, ca = orc.adc_topn(lut, codes, C4_NCAND, threads=max(1, host_threads() // world))
+    pack = np.full((2, C4_NCAND), -1, np.int64)
+    pack[0, :len(ci)] = ci + lo
+    pack[1, :len(ci)] = ca.view(np.int64)
+    if world > 1:
+        t = torch.from_numpy(pack).to(ctx["dev"])
+        g = torch.empty((world,) + pack.shape, dtype=torch.int64, device=ctx["dev"])
+        dist.all_gather_into_tensor(g.view(-1), t.view(-1))
+        g = g.cpu().numpy()
+    else:
+        g = pack[None]
+    if rank != 0:
+        return None
+    ids = np.concatenate([g[r, 0][g[r, 0] >= 0] for r in range(world)])
+    ap = np.concatenate([g[r, 1][g[r, 0] >= 0] for r in range(world)]).view(np.float64)
+    order = np.lexsort((ids, ap))[:C4_NCAND]   # ascending approximate distance, ties to the lower global row
+    first = ids[order]
+    cand_rows = np.concatenate([orc.gen_rows(CORPUS_SEED, int(i), 1, DIM) for i in first])
+    pos, sc, _ = orc.rerank_topk(cand_rows, q, np.arange(len(first)), TOPK)
+    want_i, want_s = first[pos], sc
+    got_i, got_s = np.asarray(res[0]), np.asarray(res[1])
+    if not (np.array_equal(got_i, want_i) and np.array_equal(got_s.view(np.uint64), want_s.view(np.uint64))):
+        raise SystemExit(f"PARITY FAILURE (C4, {world} GPUs): got {got_i.tolist()}, oracle {want_i.tolist()}")
+    return "ADC top-100 + re-rank top-10 of the last query equal the oracle's over all shards' codes"
 
 
 def main() -> None:
@@ -504,9 +737,10 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="all", choices=["c2", "c4", "all"],
-                    help="c2 = the headline line only; c4/all also time C4 (ADC + re-rank, 100M rows) into `extra`")
+    ap.add_argument("--workload", default="all", choices=["c2", "all"],
+                    help="c2 = the headline line only; all = also C2 batch 1024 (N = 1), C3 and C4 into `extra`")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-check", action="store_true", help="skip the oracle parity checks after the timed regions")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

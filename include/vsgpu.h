@@ -62,7 +62,8 @@ int32_t vs_init(int32_t device);
  * _upload_records then return SHARDED handles (rows split by ascending range), which every segment, query and build
  * entry point of this header accepts: vs_bruteforce_topk, vs_adc_topk, vs_adc_rerank_topk, vs_rerank_topk,
  * vs_pq_train (rows == NULL), vs_pq_encode_batch (rows == NULL), vs_segment_*, vs_adc_query_*, vs_adc_gather.
- * Re-binding (another vs_init / vs_init_multi) frees the previous group's sharded segments. */
+ * A device may be listed more than once (several ranks share it; this is how a one-GPU box exercises the
+ * coordinator).  Re-binding (another vs_init / vs_init_multi) frees the previous group's sharded segments. */
 int32_t vs_init_multi(int32_t n_gpus, const int32_t* device_ids);
 int32_t vs_device_count(void); /* devices bound by the last vs_init / vs_init_multi */
 int32_t vs_shutdown(void);
@@ -173,6 +174,13 @@ int32_t vs_adc_query_gather(uint64_t query, const int64_t* ids, int64_t n_ids, d
 int32_t vs_adc_query_end(uint64_t query);
 /* the three in one call */
 int32_t vs_adc_gather(uint64_t h, const float* q, const int64_t* ids, int64_t n_ids, double* out, uint8_t* valid_out);
+/* Graph-construction distances: GraphBuilder.buildL2Neighbors(vectors, degree) (J/graph/GraphBuilder.java:41-56)
+ * when l_build <= 0, buildPrunedNeighbors(vectors, degree, l_build, alpha) (:73-109) otherwise, over the rows of a
+ * resident segment (no skip mask: the builder takes every vector).  The O(n^2) distance work is the batched brute
+ * force of this library with the segment as its own query set; lists are in the reference's order: l2Squared
+ * ascending, ties to the lower row, the node itself excluded.  neighbors_out is int32[n][degree] (row indices, -1
+ * padded), counts_out (nullable) int32[n].  degree <= 512, candidate lists (degree resp. l_build) <= 1023. */
+int32_t vs_knn_graph(uint64_t h, int32_t degree, int32_t l_build, double alpha, int32_t* neighbors_out, int32_t* counts_out);
 /* cross-segment merge: stable sort by score descending of lists concatenated in segment order,
  * first k, J/fdb/FdbVectorIndex.java:432-437 */
 int32_t vs_merge_topk(const int64_t* ids, const double* scores, int64_t total, int32_t k,
@@ -266,7 +274,9 @@ int32_t vs_merge_adc_rerank_packed_dev(const int64_t* d_gath, int32_t world, int
  * (vs_peer_release_stream hands one back).  depth (a multiple of 4) = 4 x (1 + the number of caller streams) -- one
  * more stream is refused with VS_ESTATE.  A one-query exchange is ONE kernel that publishes and then waits for its
  * peers: every rank's kernel must be able to run at the same time (one GPU per rank); communicators whose ranks share
- * a device (vs_peer_connect_ptrs) use the separate publishing kernel instead.  A rank whose shard is empty takes
+ * a device (vs_peer_connect_ptrs) publish with a kernel of their own and let the calling HOST thread wait for the
+ * arrival flags before the merge is launched (no wait on the device can be deadlock-free there; the exchange is then
+ * blocking for that thread).  A rank whose shard is empty takes
  * part with an all-empty list.  A peer that never arrives traps the waiting kernel after 20 s instead of hanging the GPU. */
 #define VS_PEER_HANDLE_BYTES 64
 int32_t vs_peer_create(int32_t rank, int32_t world, int64_t slot_bytes, int32_t depth, uint64_t* comm_out,
@@ -321,7 +331,9 @@ int64_t vs_kernel_launch_count(void);
  * nominate on CTA pairs (tcgen05 cta_group::2).  "scan_reserve_sms": SMs the one-query scan leaves free so that
  * work of another stream (the next query's prologue, a collective's CTAs) runs beside it (default 0).
  * "peer_fused" (default 1): a one-query peer exchange publishes inside the merge kernel (one launch) instead
- * of a publishing kernel followed by the merge.
+ * of a publishing kernel followed by the merge.  "peer_spin_shared" (default 0, for tests of the polling kernels on a
+ * one-GPU box): communicators whose ranks share a device poll inside the kernels like any other instead of letting
+ * the host wait -- only safe when no large kernel of a peer has to run beside the polling one.
  * "pdl" (default 1): the kernels of one call are chained with programmatic dependent launch (the next
  * kernel is set up while its predecessor runs and waits, in the kernel, for its results).
  * "pq_tensor_cores": how PQ assignment with 8-float sub-vectors nominates -- 2 (default) tcgen05 on fp16

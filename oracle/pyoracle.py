@@ -251,6 +251,17 @@ class Oracle:
                                     C.c_int64(cap), _p(oi, _i64p), _p(os_, _f64p))
         return oi[:c].copy(), os_[:c].copy()
 
+    # -- GraphBuilder ------------------------------------------------------------------
+    def knn_graph(self, rows, degree: int, l_build: int = 0, alpha: float = 1.0, threads: int = 1):
+        """buildL2Neighbors (l_build == 0) / buildPrunedNeighbors -> list of int32 arrays."""
+        rows = _f32(rows)
+        n, d = rows.shape
+        out = np.full((n, max(degree, 1)), -1, dtype=np.int32)
+        cn = np.zeros(n, dtype=np.int32)
+        self.lib.vso_knn_graph(_p(rows, _f32p), C.c_int64(n), d, degree, l_build, C.c_double(alpha),
+                               out.ctypes.data_as(C.POINTER(C.c_int32)), cn.ctypes.data_as(C.POINTER(C.c_int32)), C.c_int(threads))
+        return [out[i, :cn[i]] for i in range(n)]
+
     # -- FloatPacker -------------------------------------------------------------------
     def floats_to_bytes(self, arr) -> bytes:
         a = _f32(arr)

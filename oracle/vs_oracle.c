@@ -637,6 +637,80 @@ int64_t vso_merge_topk(const int64_t* ids, const double* scores, int64_t total, 
 }
 
 /* ========================================================================== */
+/* GraphBuilder -- J/graph/GraphBuilder.java:41-56 (buildL2Neighbors) and      */
+/* :73-109 (buildPrunedNeighbors).  Arrays.sort on Integer[] is a stable merge */
+/* sort, so equal l2Squared keeps ascending j; comparingDouble = Double.compare */
+/* ========================================================================== */
+typedef struct {
+  double d;
+  int32_t j;
+} vso_dj;
+static int dj_cmp(const void* a, const void* b) {
+  const vso_dj* x = (const vso_dj*)a;
+  const vso_dj* y = (const vso_dj*)b;
+  int c = jcmp(x->d, y->d);
+  if (c) return c;
+  return x->j < y->j ? -1 : (x->j > y->j ? 1 : 0);
+}
+
+/* l_build <= 0: buildL2Neighbors(vectors, degree); else buildPrunedNeighbors(vectors, degree, l_build, alpha).
+ * out: int32[n][degree], -1 padded; counts: int32[n]. */
+void vso_knn_graph(const float* rows, int64_t n, int d, int degree, int l_build, double alpha,
+                   int32_t* out, int32_t* counts, int threads) {
+  const int T = resolve_threads(threads);
+  const int prune_mode = l_build > 0;
+  const int prune = alpha > 1.0; /* :79 */
+#pragma omp parallel num_threads(T)
+  {
+    vso_dj* dj = (vso_dj*)malloc((size_t)(n > 1 ? n - 1 : 1) * sizeof(vso_dj));
+    int32_t* selected = (int32_t*)malloc((size_t)(degree > 0 ? degree : 1) * sizeof(int32_t));
+#pragma omp for schedule(dynamic, 16)
+    for (int64_t i = 0; i < n; i++) {
+      int64_t p = 0;
+      for (int64_t j = 0; j < n; j++)
+        if (j != i) {
+          dj[p].d = vso_l2_squared(rows + (size_t)i * d, rows + (size_t)j * d, d); /* :50 / :84 */
+          dj[p].j = (int32_t)j;
+          p++;
+        }
+      qsort(dj, (size_t)p, sizeof(vso_dj), dj_cmp);
+      int32_t* o = out + (size_t)i * degree;
+      for (int c = 0; c < degree; c++) o[c] = -1;
+      if (!prune_mode) {
+        int64_t take = degree < n - 1 ? degree : n - 1; /* :51 */
+        if (take < 0) take = 0;
+        for (int64_t k = 0; k < take; k++) o[k] = dj[k].j;
+        counts[i] = (int32_t)take;
+      } else {
+        int64_t limit = l_build < n - 1 ? l_build : n - 1; /* :88 */
+        if (limit < 0) limit = 0;
+        const int64_t cap = degree < limit ? degree : limit; /* :89 */
+        int64_t sN = 0;
+        for (int64_t k = 0; k < limit && sN < cap; k++) {
+          const int32_t u = dj[k].j;
+          int keep = 1;
+          if (prune) {
+            const double diu = dj[k].d;
+            for (int64_t t = 0; t < sN; t++) {
+              const double dup = vso_l2_squared(rows + (size_t)u * d, rows + (size_t)selected[t] * d, d);
+              if (dup <= alpha * diu) { /* :101 */
+                keep = 0;
+                break;
+              }
+            }
+          }
+          if (keep) selected[sN++] = u;
+        }
+        for (int64_t k = 0; k < sN; k++) o[k] = selected[k];
+        counts[i] = (int32_t)sN;
+      }
+    }
+    free(dj);
+    free(selected);
+  }
+}
+
+/* ========================================================================== */
 /* FloatPacker -- J/util/FloatPacker.java:21-39 (little-endian fp32)           */
 /* ========================================================================== */
 void vso_floats_to_bytes(const float* arr, int n, uint8_t* out) {

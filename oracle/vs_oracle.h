@@ -104,6 +104,12 @@ int64_t vso_rerank_topk(const float* rows, int64_t n, int d, const uint8_t* skip
 int64_t vso_merge_topk(const int64_t* ids, const double* scores, int64_t total, int64_t k,
                        int64_t* ids_out, double* scores_out);
 
+/* ---- GraphBuilder (J/graph/GraphBuilder.java:41-56, :73-109) ------------------ */
+/* l_build <= 0: buildL2Neighbors(vectors, degree); else buildPrunedNeighbors(vectors, degree, l_build, alpha).
+ * out: int32[n][degree] (-1 padded), counts: int32[n]. */
+void vso_knn_graph(const float* rows, int64_t n, int d, int degree, int l_build, double alpha,
+                   int32_t* out, int32_t* counts, int threads);
+
 /* ---- FloatPacker (J/util/FloatPacker.java:21-39) ----------------------------- */
 void vso_floats_to_bytes(const float* arr, int n, uint8_t* out);
 void vso_bytes_to_floats(const uint8_t* bytes, int nbytes, float* out);

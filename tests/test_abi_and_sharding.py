@@ -4,6 +4,7 @@ right under a real 2-process gloo group."""
 import os
 import re
 import socket
+import subprocess
 from pathlib import Path
 
 import numpy as np
@@ -217,3 +218,90 @@ def test_two_rank_gloo_adc_rerank_equals_single_segment(oracle):
     ri, rs, _ = oracle.rerank_topk(full, qv, ci, k, 0)
     for rank, gi, gs in got:
         assert gi == ri.tolist() and gs == rs.view(np.uint64).tolist(), f"rank {rank}"
+
+
+# ---- round 2: a plain-C caller, host-only wire-format functions, the order-preserving threaded oracle --------------
+def _build_c_smoke(tmp_path):
+    exe = tmp_path / "c_abi_smoke"
+    libdir = ROOT / "vectorsearch_b200"
+    cc = "/usr/bin/gcc" if Path("/usr/bin/gcc").exists() else "gcc"
+    subprocess.run([cc, "-O1", "-Wall", "-o", str(exe), str(ROOT / "tests" / "c_abi_smoke.c"), f"-L{libdir}", "-lvsgpu",
+                    f"-Wl,-rpath,{libdir}", "-lm"], check=True, capture_output=True)
+    return exe
+
+
+def test_plain_c_caller_links_and_fails_loudly_without_a_device(tmp_path):
+    """tests/c_abi_smoke.c includes only include/vsgpu.h and links -lvsgpu: the boundary needs neither Python nor
+    torch.  Without a GPU it must stop at vs_init with VS_ECUDA and the no-CPU-fallback message (exit 77)."""
+    import torch
+
+    exe = _build_c_smoke(tmp_path)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    if torch.cuda.is_available():
+        assert r.returncode == 0, r.stdout + r.stderr
+    else:
+        assert r.returncode == 77, r.stdout + r.stderr
+        assert "no CPU fallback" in r.stdout
+
+
+@pytest.mark.gpu
+def test_plain_c_caller_on_the_device(tmp_path):
+    exe = _build_c_smoke(tmp_path)
+    for ngpu in ("1", "2"):  # "2": vs_init_multi with two ranks on device 0 -- the in-library coordinator from plain C
+        r = subprocess.run([str(exe), ngpu], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert "c_abi_smoke ok" in r.stdout
+
+
+def test_codebook_wire_format_on_the_host(oracle):
+    """vs_codebook_encode / _decode are host-side byte handling (no device needed): the bytes equal what the real
+    protobuf runtime serializes for the reference's PQCodebook message (vectorsearch.proto:135-142)."""
+    from google.protobuf import descriptor_pb2, descriptor_pool, message_factory
+
+    import vectorsearch_b200 as vs
+
+    fdp = descriptor_pb2.FileDescriptorProto()
+    fdp.name, fdp.package, fdp.syntax = "vs_cpu_wire_test.proto", "vscpu", "proto3"
+    T = descriptor_pb2.FieldDescriptorProto
+    cb = fdp.message_type.add()
+    cb.name = "PQCodebook"
+    for name, num, typ, lab in (("m", 1, T.TYPE_INT32, T.LABEL_OPTIONAL), ("k", 2, T.TYPE_INT32, T.LABEL_OPTIONAL),
+                                ("centroids", 3, T.TYPE_BYTES, T.LABEL_REPEATED)):
+        f = cb.field.add()
+        f.name, f.number, f.type, f.label = name, num, typ, lab
+    pool = descriptor_pool.DescriptorPool()
+    pool.Add(fdp)
+    PQCodebook = message_factory.GetMessageClass(pool.FindMessageTypeByName("vscpu.PQCodebook"))
+    for M, K, sub in ((16, 256, 8), (2, 2, 2), (1, 300, 3), (4, 16, 48)):
+        cent = oracle.gen_floats(5, 0, M * K * sub).reshape(M, K, sub)
+        msg = PQCodebook(m=M, k=K)
+        for s in range(M):  # SegmentBuildService.java:330-336: putFloat in (ci, di) order, little-endian
+            msg.centroids.append(b"".join(oracle.floats_to_bytes(cent[s, ci]) for ci in range(K)))
+        want = msg.SerializeToString()
+        assert vs.codebook_encode(cent) == want
+        back = vs.codebook_decode(want)
+        assert back.shape == (M, K, sub) and np.array_equal(back.view(np.uint32), cent.view(np.uint32))
+        again = PQCodebook()
+        again.ParseFromString(vs.codebook_encode(cent))  # and the real runtime parses ours
+        assert again.m == M and again.k == K and len(again.centroids) == M
+    for bad in (b"\x08", b"\x08\x02\x10\x02\x1a\x05abcd", b"\x08\x02\x10\x02\x1a\x10" + b"x" * 16):
+        with pytest.raises(ValueError):
+            vs.codebook_decode(bad)
+
+
+@pytest.mark.parametrize("lanes", [16, 8])
+def test_threaded_oracle_trainer_is_bit_identical(oracle, lanes):
+    """vso_pq_train_mt / vso_pq_encode_batch_fast (used by the BASELINE-size GPU tests) against the literal
+    single-threaded restatements: same centroids, same draws, same codes, for every thread count."""
+    oracle.set_lanes(lanes)
+    try:
+        for n, d, M, K, it in ((6000, 64, 8, 32, 3), (500, 16, 2, 64, 4), (3000, 96, 4, 16, 2)):
+            rows = oracle.gen_rows(21, 0, n, d)
+            rows[100:160] = rows[7]  # duplicates: empty clusters and re-initialisation draws
+            want, draws = oracle.pq_train(rows, d, M, K, it, 42, return_draws=True)
+            for t in (1, 3, 8):
+                got, gd = oracle.pq_train(rows, d, M, K, it, 42, return_draws=True, threads=t)
+                assert gd == draws and np.array_equal(got.view(np.uint32), want.view(np.uint32)), (n, d, t)
+            assert np.array_equal(oracle.pq_encode_batch_fast(want, rows, threads=5), oracle.pq_encode_batch(want, rows, threads=2))
+    finally:
+        oracle.set_lanes(16)

@@ -423,7 +423,7 @@ def test_peer_exchange_merge_equals_gather_then_merge(vs, world, nq, k):
     from vectorsearch_b200 import _lib as L
 
     lib = vs.load()
-    depth, rounds = 8, 11
+    depth, rounds = 12, 11  # ring 0 is the communicator's own stream; two caller streams per rank
     comms, bases = [], (C.c_uint64 * world)()
     streams = [torch.cuda.Stream() for _ in range(world)]
     streams2 = [torch.cuda.Stream() for _ in range(world)]
@@ -463,6 +463,10 @@ def test_peer_exchange_merge_equals_gather_then_merge(vs, world, nq, k):
                 outs.append((oi, os_, oc))
             torch.cuda.synchronize()
             vs.set_option("peer_fused", rnd % 2)  # one query: publish inside the merge kernel / as a kernel of its own
+            # ONE host thread issues every rank's exchange here, so the calls must not block: poll inside the kernels (what
+            # ranks on separate GPUs do) instead of the host-side wait that communicators sharing a device default to --
+            # safe in this test, nothing large runs beside the polling kernels
+            vs.set_option("peer_spin_shared", 1)
             for r in range(world):               # rank r's merge spins until the later-launched ranks have published
                 oi, os_, oc = outs[r]
                 st = (streams2 if rnd % 3 == 2 else streams)[r].cuda_stream
@@ -474,13 +478,14 @@ def test_peer_exchange_merge_equals_gather_then_merge(vs, world, nq, k):
                 assert torch.equal(oc, want_c), (rnd, r)
                 assert torch.equal(oi, want_i), (rnd, r)
                 assert torch.equal(os_.view(torch.int64), want_s.view(torch.int64)), (rnd, r)
-        # a third stream does not fit a communicator of depth 8 (two rings): refused, not corrupted
+        # a third caller stream does not fit a communicator of depth 12 (its own ring + two): refused, not corrupted
         oi, os_, oc = outs[0]
         rc = lib.vs_exchange_merge_packed_dev(comms[0], d_pack[0].data_ptr(), nq, k, 1, oi.data_ptr(), os_.data_ptr(),
                                               oc.data_ptr(), torch.cuda.Stream().cuda_stream)
         assert rc != 0
     finally:
         vs.set_option("peer_fused", 1)
+        vs.set_option("peer_spin_shared", 0)
         torch.cuda.synchronize()
         for c in comms:
             lib.vs_peer_destroy(c)

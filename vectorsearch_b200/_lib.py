@@ -71,6 +71,7 @@ SIGNATURES = {
     "vs_rerank_topk": (i32, [u64, f32p, i64p, i32, i32, i32, i32, i64p, f64p, i32p]),
     "vs_adc_rerank_topk": (i32, [u64, f32p, i32, i32, i32, i32, i32, i64p, f64p, i32p]),
     "vs_merge_topk": (i32, [i64p, f64p, i64, i32, i64p, f64p, i32p]),
+    "vs_knn_graph": (i32, [u64, i32, i32, C.c_double, i32p, i32p]),
     "vs_pq_train": (i32, [f32p, u64, i64, i32, i32, i32, i32, i64, f32p]),
     "vs_pq_train_sharded": (i32, [u64, i64, i64, i32, i32, i32, i32, i32, i32, i64, vp, vp, vp, vp, f32p]),
     "vs_pq_train_sharded_peer": (i32, [u64, u64, i64, i64, i32, i32, i32, i32, i64, f32p]),

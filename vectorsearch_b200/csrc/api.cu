@@ -3,13 +3,17 @@
 // compute entry point fails with VS_ECUDA when no device is bound.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
+
+#include <cuda.h>
 
 #include "../../include/vsgpu.h"
 #include "host.h"
@@ -36,6 +40,7 @@ static std::atomic<int64_t> g_batch_min_rows{16384};       // ... on segments at
 static std::atomic<int64_t> g_batch_gm_bytes{int64_t(1) << 30};  // group-minima scratch per query chunk
 static std::atomic<int64_t> g_batch_warp_min_q{0};         // > 0: batches this large always select with one warp per query (tests)
 static std::atomic<int> g_peer_fused{1};                      // one-query exchanges: publish inside the merge kernel
+static std::atomic<int> g_peer_spin_shared{0};                // tests: poll inside the kernels even when ranks share a device
 static std::atomic<int64_t> g_scan_reserve_sms{0};          // SMs the one-query scan leaves free (for a collective's CTAs)
 static std::atomic<int64_t> g_batch_pairs{0};               // 1: cta_group::2 nomination kernel for batches > 128 queries (measured equal)
 static std::atomic<int64_t> g_batch_prefilter{1};           // candidate groups are pre-filtered on the fp16 copy before exact scoring
@@ -106,6 +111,7 @@ struct ThreadCtx {
   static constexpr int MAX_SLOTS = 4;
   DevScratch slots[MAX_SLOTS];
   int active = -1;
+  std::vector<void*> parked_host;  // outgrown pinned buffers, released with the context
   void park() {
     if (active < 0) return;
     DevScratch& a = slots[active];
@@ -127,11 +133,13 @@ struct ThreadCtx {
         if (a.d_fs) cudaFree(a.d_fs);
       }
       if (h_buf) cudaFreeHost(h_buf);
+      for (void* p : parked_host) cudaFreeHost(p);
       if (stream) cudaStreamDestroy(stream);
     }
   }
 };
 static thread_local ThreadCtx t_ctxs[VS_MAX_DEVICES];  // one per CUDA ordinal this thread has worked on
+static void park_host(ThreadCtx* c, void* p) { c->parked_host.push_back(p); }
 
 // Makes the device scratch of `stream` the active one (at most MAX_SLOTS streams per host thread; beyond that
 // the least recently bound caller stream is drained and its set is handed over).
@@ -182,22 +190,44 @@ int ctx_bind(ThreadCtx** out) { return ctx_bind_dev(out, t_default_dev >= 0 ? t_
 // the device a segment's rows live on
 static int ctx_bind_seg(ThreadCtx** out, const Segment* s) { return ctx_bind_dev(out, s->device); }
 
+// Scratch grows inside calls that may be collective: a rank of a peer exchange must never synchronise the whole DEVICE
+// on its way to publishing, because a peer that shares the GPU (several ranks on one device: the one-GPU test shape of
+// vs_init_multi / vs_peer_connect_ptrs) may be spinning in its merge kernel for exactly that publish.  cudaFree does
+// synchronise the device; stream-ordered allocation and release (and waiting for ONE stream) do not.
+static cudaError_t scratch_alloc(void** p, size_t bytes, cudaStream_t st) {
+  cudaError_t e = cudaMallocAsync(p, bytes, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // usable from any stream from here on
+  return e;
+}
+static void scratch_free(void* p, cudaStream_t st) {
+  if (p) cudaFreeAsync(p, st);
+}
+// pinned host buffers that were outgrown are parked (cudaFreeHost may synchronise too) and released with the context
 static int ctx_reserve_dev(ThreadCtx* c, size_t bytes) {
   if (bytes <= c->d_cap) return VS_OK;
-  cudaStreamSynchronize(c->stream);
-  if (c->d_buf) cudaFree(c->d_buf);
+  // work enqueued on the stream that owns this scratch set may still use the old buffer: order the release behind it
+  cudaStream_t owner = (c->active >= 0 && c->slots[c->active].key) ? static_cast<cudaStream_t>(c->slots[c->active].key) : c->stream;
+  if (owner != c->stream) {
+    cudaEvent_t ev;
+    if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess) {
+      cudaEventRecord(ev, owner);
+      cudaStreamWaitEvent(c->stream, ev, 0);
+      cudaEventDestroy(ev);
+    }
+  }
+  scratch_free(c->d_buf, c->stream);
   c->d_buf = nullptr;
   c->d_cap = 0;
   size_t cap = bytes + bytes / 4 + 4096;
-  cudaError_t e = cudaMalloc(&c->d_buf, cap);
-  if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(scratch)");
+  cudaError_t e = scratch_alloc(&c->d_buf, cap, c->stream);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMallocAsync(scratch)");
   c->d_cap = cap;
   return VS_OK;
 }
 static int ctx_reserve_host(ThreadCtx* c, size_t bytes) {
   if (bytes <= c->h_cap) return VS_OK;
   cudaStreamSynchronize(c->stream);
-  if (c->h_buf) cudaFreeHost(c->h_buf);
+  if (c->h_buf) park_host(c, c->h_buf);
   c->h_buf = nullptr;
   c->h_cap = 0;
   size_t cap = bytes + bytes / 4 + 4096;
@@ -209,12 +239,14 @@ static int ctx_reserve_host(ThreadCtx* c, size_t bytes) {
 static int ctx_reserve_ticket(ThreadCtx* c, size_t n) {
   if (n <= c->ticket_cap) return VS_OK;
   cudaStreamSynchronize(c->stream);
-  if (c->d_ticket) cudaFree(c->d_ticket);
+  scratch_free(c->d_ticket, c->stream);
   c->d_ticket = nullptr;
   c->ticket_cap = 0;
   size_t cap = n < 1024 ? 1024 : n * 2;
-  cudaError_t e = cudaMalloc(&c->d_ticket, cap * 4 * sizeof(unsigned long long));
-  if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(ticket)");
+  void* tp = nullptr;
+  cudaError_t e = scratch_alloc(&tp, cap * 4 * sizeof(unsigned long long), c->stream);
+  c->d_ticket = static_cast<unsigned long long*>(tp);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMallocAsync(ticket)");
   e = cudaMemsetAsync(c->d_ticket, 0, cap * 4 * sizeof(unsigned long long), c->stream);
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemset(ticket)");
   c->ticket_cap = cap;
@@ -224,12 +256,14 @@ static int ctx_reserve_ticket(ThreadCtx* c, size_t n) {
 static int ctx_reserve_fs(ThreadCtx* c, size_t n) {
   if (n <= c->fs_cap) return VS_OK;
   cudaStreamSynchronize(c->stream);
-  if (c->d_fs) cudaFree(c->d_fs);
+  scratch_free(c->d_fs, c->stream);
   c->d_fs = nullptr;
   c->fs_cap = 0;
   size_t cap = n < 4 ? 4 : n * 2;
-  cudaError_t e = cudaMalloc(&c->d_fs, cap * FS_WORDS * sizeof(unsigned int));
-  if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(fast-scan scratch)");
+  void* fp = nullptr;
+  cudaError_t e = scratch_alloc(&fp, cap * FS_WORDS * sizeof(unsigned int), c->stream);
+  c->d_fs = static_cast<unsigned int*>(fp);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMallocAsync(fast-scan scratch)");
   e = cudaMemsetAsync(c->d_fs, 0, cap * FS_WORDS * sizeof(unsigned int), c->stream);
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemset(fast-scan scratch)");
   e = cudaStreamSynchronize(c->stream);
@@ -654,8 +688,8 @@ int32_t vs_init_multi(int32_t n_gpus, const int32_t* device_ids) {
     const int device = device_ids[i];
     if (device < 0 || device >= count) return fail(VS_EINVAL, "device %d out of range (0..%d)", device, count - 1);
     if (device >= VS_MAX_DEVICES) return fail(VS_EINVAL, "device ordinal %d is beyond the %d this build supports", device, VS_MAX_DEVICES);
-    for (int j = 0; j < i; j++)
-      if (device_ids[j] == device) return fail(VS_EINVAL, "device %d listed twice", device);
+    // (a device may be listed more than once: several ranks then share it -- slower, but the whole coordinator runs
+    //  on a one-GPU box, which is how the tests cover it)
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties");
     if (prop.major < 10) return fail(VS_ECUDA, "device %d is sm_%d%d; libvsgpu is built for sm_100a only", device, prop.major, prop.minor);
@@ -733,6 +767,10 @@ int32_t vs_set_option(const char* name, int64_t value) {
   if (!name) return fail(VS_EINVAL, "null option name");
   if (!strcmp(name, "peer_fused")) {
     g_peer_fused.store(value != 0 ? 1 : 0);
+    return VS_OK;
+  }
+  if (!strcmp(name, "peer_spin_shared")) {
+    g_peer_spin_shared.store(value != 0 ? 1 : 0);
     return VS_OK;
   }
   if (!strcmp(name, "train_exact_order")) {
@@ -1639,6 +1677,93 @@ int32_t vs_adc_gather(uint64_t h, const float* q, const int64_t* ids, int64_t n_
   return r;
 }
 
+// ---- graph construction distances (GraphBuilder.buildL2Neighbors / buildPrunedNeighbors) ------------------------
+// The O(n^2) all-pairs part of sealing: every row of the segment queries the segment (the batched tensor-core
+// nomination + exact re-score of vs_bruteforce_topk, device to device, rows never leave HBM), then knn_finalize
+// re-orders each node's candidates by (l2Squared, j) -- the reference's Comparator.comparingDouble(l2Squared) over a
+// stable sort (J/graph/GraphBuilder.java:50, :83-87) -- drops the node itself and, for the pruned variant, applies
+// the greedy alpha rule (:92-106).  l_build <= 0: buildL2Neighbors(vectors, degree); else buildPrunedNeighbors(vectors,
+// degree, l_build, alpha).  neighbors_out is int[n][degree] (row indices, -1 padded), counts_out[n] the list lengths.
+int32_t vs_knn_graph(uint64_t h, int32_t degree, int32_t l_build, double alpha, int32_t* neighbors_out, int32_t* counts_out) {
+  if (group_is_sharded(h)) return fail(VS_ESTATE, "graph construction runs on one device: upload the segment with vs_init(device)");
+  std::shared_ptr<Segment> s_ref = seg_lookup(h);
+  Segment* s = s_ref.get();
+  if (!s) return fail(VS_EHANDLE, "unknown segment handle");
+  if (!neighbors_out || degree <= 0 || degree > 512) return fail(VS_EINVAL, "need an output and degree in 1..512");
+  if (s->skip) return fail(VS_ESTATE, "the segment has a skip mask: GraphBuilder takes every vector of the segment");
+  if (s->n > 0x7fffffffLL) return fail(VS_EINVAL, "a Java array cannot hold more than 2^31-1 vectors");
+  ThreadCtx* c;
+  RET(ctx_bind_seg(&c, s));
+  const int64_t n = s->n;
+  if (n == 0) return VS_OK;
+  const bool prune_mode = l_build > 0;
+  const bool prune = prune_mode && alpha > 1.0;                       // :79 boolean prune = alpha > 1.0
+  int64_t limit = prune_mode ? std::min<int64_t>(std::max(0, l_build), n - 1) : std::min<int64_t>(degree, n - 1);   // :88 / :51
+  const int out_deg = prune_mode ? (int)std::min<int64_t>(degree, limit) : degree;  // :89 selected.length
+  if (limit + 1 > TOPK_MAX_K) return fail(VS_EINVAL, "candidate lists of more than %d rows are not supported", TOPK_MAX_K - 1);
+  if (n == 1 || limit == 0) {
+    for (int64_t i = 0; i < n * degree; i++) neighbors_out[i] = -1;
+    if (counts_out) for (int64_t i = 0; i < n; i++) counts_out[i] = 0;
+    return VS_OK;
+  }
+  // the node itself is (usually) its own nearest row: one extra slot for it, a few more to close groups of equal distance
+  const int kq = (int)std::min<int64_t>(std::min<int64_t>(limit + 1 + 8, TOPK_MAX_K), n);
+  // rows per pass: the per-query partial lists of the scan path (one list per CTA) stay within half a gigabyte
+  int64_t chunk64 = (int64_t(1) << 29) / ((int64_t)g_sms * kq * 16);
+  chunk64 = std::max<int64_t>(16, std::min<int64_t>(2048, chunk64));
+  const int chunk = (int)std::min<int64_t>(n, chunk64);
+  const int keep = prune_mode ? out_deg : (int)std::min<int64_t>(degree, limit);
+  cudaStream_t st = c->stream;
+  struct Tmp {
+    void* p = nullptr;
+    ~Tmp() { if (p) cudaFree(p); }
+  } t_ids, t_sc, t_cn, t_nb, t_ct, t_fl, t_nodes;
+  CK(cudaMalloc(&t_ids.p, (size_t)chunk * kq * 8), "cudaMalloc(knn ids)");
+  CK(cudaMalloc(&t_sc.p, (size_t)chunk * kq * 8), "cudaMalloc(knn scores)");
+  CK(cudaMalloc(&t_cn.p, (size_t)chunk * 4), "cudaMalloc(knn counts)");
+  CK(cudaMalloc(&t_nb.p, (size_t)n * degree * 4), "cudaMalloc(neighbors)");
+  CK(cudaMalloc(&t_ct.p, (size_t)n * 4), "cudaMalloc(neighbor counts)");
+  CK(cudaMalloc(&t_fl.p, (size_t)chunk * 4), "cudaMalloc(flags)");
+  CK(cudaMalloc(&t_nodes.p, (size_t)chunk * 4), "cudaMalloc(nodes)");
+  int64_t* d_ids = static_cast<int64_t*>(t_ids.p);
+  double* d_sc = static_cast<double*>(t_sc.p);
+  int32_t* d_cn = static_cast<int32_t*>(t_cn.p);
+  int32_t* d_nb = static_cast<int32_t*>(t_nb.p);
+  int32_t* d_ct = static_cast<int32_t*>(t_ct.p);
+  int32_t* d_fl = static_cast<int32_t*>(t_fl.p);
+  int32_t* d_nodes = static_cast<int32_t*>(t_nodes.p);
+  std::vector<int32_t> h_fl(chunk), h_nodes;
+  for (int64_t r0 = 0; r0 < n; r0 += chunk) {
+    const int cnt = (int)std::min<int64_t>(chunk, n - r0);
+    // queries = the segment's own rows, already on the device
+    RET(vs_bruteforce_topk_dev(h, s->X + (size_t)r0 * s->d, cnt, kq, VS_METRIC_L2, d_ids, d_sc, d_cn, st));
+    CK(launch_knn_finalize(s->X, n, s->d, lanes(), r0, cnt, d_ids, d_sc, d_cn, kq, (int)limit, degree, keep, true,
+                           alpha, prune, s->id_base, d_nb, d_ct, d_fl, st), "knn finalize launch");
+    CK(cudaMemcpyAsync(h_fl.data(), d_fl, (size_t)cnt * 4, cudaMemcpyDeviceToHost, st), "D2H flags");
+    CK(cudaStreamSynchronize(st), "sync");
+    h_nodes.clear();
+    for (int q = 0; q < cnt; q++)
+      if (h_fl[q]) h_nodes.push_back((int32_t)(r0 + q));
+    // nodes whose list may have cut a run of equal distances short: exact candidates, same finalisation (no closure check)
+    for (size_t f0 = 0; f0 < h_nodes.size(); f0 += chunk) {
+      const int fc = (int)std::min<size_t>(chunk, h_nodes.size() - f0);
+      const int kx = (int)std::min<int64_t>(limit, n - 1);
+      CK(cudaMemcpyAsync(d_nodes, h_nodes.data() + f0, (size_t)fc * 4, cudaMemcpyHostToDevice, st), "H2D nodes");
+      CK(launch_knn_exact(s->X, n, s->d, lanes(), d_nodes, fc, kx, s->id_base, d_ids, d_sc, d_cn, st), "knn exact launch");
+      // the exact lists are per listed node, not per consecutive row: finalise them one node at a time
+      for (int q = 0; q < fc; q++)
+        CK(launch_knn_finalize(s->X, n, s->d, lanes(), h_nodes[f0 + q], 1, d_ids + (size_t)q * kx, d_sc + (size_t)q * kx, d_cn + q, kx,
+                               (int)limit, degree, keep, false, alpha, prune, s->id_base, d_nb, d_ct, nullptr, st),
+           "knn finalize launch");
+      CK(cudaStreamSynchronize(st), "sync");
+    }
+  }
+  CK(cudaMemcpyAsync(neighbors_out, d_nb, (size_t)n * degree * 4, cudaMemcpyDeviceToHost, st), "D2H neighbors");
+  if (counts_out) CK(cudaMemcpyAsync(counts_out, d_ct, (size_t)n * 4, cudaMemcpyDeviceToHost, st), "D2H counts");
+  CK(cudaStreamSynchronize(st), "sync");
+  return VS_OK;
+}
+
 // =================================================================================================
 // build operations
 // =================================================================================================
@@ -1925,6 +2050,9 @@ struct PeerComm {
   cudaStream_t xstream = nullptr;
   unsigned char *x_dev = nullptr, *x_host = nullptr;
   size_t x_dev_cap = 0, x_host_cap = 0;
+  std::vector<unsigned char*> x_host_parked;
+  cudaStream_t pstream = nullptr;            // flag polling by the host (ranks sharing a device)
+  unsigned long long* h_flags = nullptr;     // pinned [VS_PEER_MAX_WORLD]
   bool shared_device = false;  // several ranks on one GPU: the fused publish-then-wait kernel could stall (rank.cu)
   struct RingPack {
     cudaStream_t stream;
@@ -1986,6 +2114,34 @@ bool peer_next(PeerComm* pc, size_t payload, cudaStream_t st, PeerSlot* out) {
   ps.flags = reinterpret_cast<const unsigned long long*>(own + ps.flag_off);
   ps.ticket = reinterpret_cast<unsigned int*>(own + pc->ticket_off) + slot;
   return true;
+}
+// Ranks that share a GPU (several communicators on one device: the one-GPU shape of vs_init_multi and of the tests)
+// cannot wait ON THE DEVICE at all.  A CTA polling inside a kernel holds its SM's resources, and a persistent
+// one-CTA-per-SM kernel of the very peer it waits for (the scan, the nomination GEMM: all of an SM's shared memory)
+// may then never become fully resident.  A stream memory operation (cuStreamWaitValue64) occupies no SM but blocks
+// its hardware channel, which the peer's stream may be multiplexed onto.  Either way: deadlock until a time-out.
+// So for such communicators the HOST waits: it drains its own stream (its publish is out), polls the arrival flags
+// with small copies on a stream of their own, and only then launches the consuming kernel, which has nothing left to
+// poll.  The exchange is then blocking for the calling thread -- a property of this test shape only; ranks on
+// separate GPUs keep the fully asynchronous in-kernel wait.  src < 0: the flags of every rank.
+int peer_host_wait(PeerComm* pc, cudaStream_t st, const unsigned long long* flags, unsigned long long seq, int src) {
+  CK(cudaStreamSynchronize(st), "sync (exchange, shared device)");
+  if (!pc->pstream) {
+    CK(cudaStreamCreateWithFlags(&pc->pstream, cudaStreamNonBlocking), "cudaStreamCreate (flag polling)");
+    CK(cudaMallocHost(reinterpret_cast<void**>(&pc->h_flags), VS_PEER_MAX_WORLD * 8), "cudaMallocHost (flag polling)");
+  }
+  const auto t0 = std::chrono::steady_clock::now();
+  for (int spins = 0;; spins++) {
+    CK(cudaMemcpyAsync(pc->h_flags, flags, (size_t)pc->world * 8, cudaMemcpyDeviceToHost, pc->pstream), "D2H flags");
+    CK(cudaStreamSynchronize(pc->pstream), "sync (flag polling)");
+    bool all = true;
+    for (int r = 0; r < pc->world; r++)
+      if ((src < 0 || r == src) && pc->h_flags[r] < seq) all = false;
+    if (all) return VS_OK;
+    if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(20))
+      return fail(VS_ESTATE, "peer exchange %llu: a rank of this communicator did not arrive within 20 s", seq);
+    if (spins > 50) std::this_thread::sleep_for(std::chrono::microseconds(50));
+  }
 }
 // a launch failed after peer_next on this rank: hand the sequence number back so the ring stays in step with the
 // peers (they time out on this exchange, but the communicator is not left off by one for good)
@@ -2135,7 +2291,10 @@ int32_t vs_peer_destroy(uint64_t comm) {
   }
   if (pc->x_dev) cudaFree(pc->x_dev);
   if (pc->x_host) cudaFreeHost(pc->x_host);
+  for (unsigned char* hp : pc->x_host_parked) cudaFreeHost(hp);
   if (pc->xstream) cudaStreamDestroy(pc->xstream);
+  if (pc->pstream) cudaStreamDestroy(pc->pstream);
+  if (pc->h_flags) cudaFreeHost(pc->h_flags);
   for (auto& rp : pc->ring_packs) cudaFree(rp.p);
   delete pc;
   return VS_OK;
@@ -2159,13 +2318,20 @@ static int exchange_merge(PeerComm* pc, cudaStream_t st, int kind, const int64_t
   if (!peer_next(pc, payload, st, &ps))
     return fail(VS_ESTATE, "communicator of depth %d serves %d streams; this is one more", pc->depth, pc->depth / PEER_RING);
   const PeerPublish pub{pc->bases, d_pack, payload, ps.data_off, ps.flag_off, pc->rank};
-  const bool fused = nq == 1 && g_peer_fused.load() != 0 && !pc->shared_device;  // one query: the merge kernel publishes, then waits
+  const bool on_stream = pc->shared_device && g_peer_spin_shared.load() == 0;  // the host waits, not a kernel (peer_host_wait)
+  const bool fused = nq == 1 && g_peer_fused.load() != 0 && !on_stream;  // one query: the merge kernel publishes, then waits
   cudaError_t e = cudaSuccess;
   if (!fused) e = launch_peer_publish(pc->bases, pc->world, pc->rank, d_pack, payload, ps.data_off, ps.flag_off, ps.seq, ps.ticket, st);
+  const unsigned long long* poll = ps.flags;
+  if (e == cudaSuccess && on_stream) {  // the host waits for the flags; the merge kernel has nothing to poll
+    const int wr = peer_host_wait(pc, st, ps.flags, ps.seq, -1);
+    if (wr != VS_OK) return wr;
+    poll = nullptr;
+  }
   if (e == cudaSuccess) {
     e = kind == 0 ? launch_merge_packed(ps.gath, pc->world, nq, k, descending != 0, d_ids_out, d_scores_out, d_counts_out, st,
-                                        ps.flags, ps.seq, fused ? &pub : nullptr)
-                  : launch_merge_adc_rerank(ps.gath, pc->world, nq, nc, k, d_ids_out, d_scores_out, d_counts_out, st, ps.flags,
+                                        poll, ps.seq, fused ? &pub : nullptr)
+                  : launch_merge_adc_rerank(ps.gath, pc->world, nq, nc, k, d_ids_out, d_scores_out, d_counts_out, st, poll,
                                             ps.seq, fused ? &pub : nullptr);
     // (a separate publish that went out has used the slot: only the fused form can still hand it back)
     if (e != cudaSuccess && fused) peer_rollback(pc, ps);
@@ -2197,17 +2363,19 @@ int32_t vs_exchange_merge_adc_rerank_packed_dev(uint64_t comm, const int64_t* d_
 
 // staging of the host-buffer exchange calls (caller holds pc->xmu)
 static int peer_staging(PeerComm* pc, cudaStream_t st, size_t need_d, size_t need_h) {
-  if (need_d > pc->x_dev_cap) {
+  if (need_d > pc->x_dev_cap) {  // (no device-wide synchronisation here: see scratch_alloc)
     CK(cudaStreamSynchronize(st), "sync");
-    if (pc->x_dev) cudaFree(pc->x_dev);
+    scratch_free(pc->x_dev, st);
     pc->x_dev = nullptr;
     pc->x_dev_cap = 0;
-    CK(cudaMalloc(&pc->x_dev, need_d), "cudaMalloc(exchange staging)");
-    pc->x_dev_cap = need_d;
+    void* xp = nullptr;
+    CK(scratch_alloc(&xp, need_d + need_d / 2, st), "cudaMallocAsync(exchange staging)");
+    pc->x_dev = static_cast<unsigned char*>(xp);
+    pc->x_dev_cap = need_d + need_d / 2;
   }
   if (need_h > pc->x_host_cap) {
     CK(cudaStreamSynchronize(st), "sync");
-    if (pc->x_host) cudaFreeHost(pc->x_host);
+    if (pc->x_host) pc->x_host_parked.push_back(pc->x_host);
     pc->x_host = nullptr;
     pc->x_host_cap = 0;
     CK(cudaMallocHost(&pc->x_host, need_h), "cudaMallocHost(exchange staging)");
@@ -2474,6 +2642,16 @@ static int train_peer_begin(void* pcv, cudaStream_t st, size_t bytes, PeerXchg* 
   x->ticket = ps.ticket;
   return VS_OK;
 }
+// orders the consumer behind the publish of rank src (src < 0: of every rank).  *enqueued = 1 when the wait has already
+// happened (ranks share a device: the host waited, the consuming kernel must not poll), 0 when the kernel polls the flags.
+static int train_peer_wait(void* pcv, cudaStream_t st, const PeerXchg* x, int src, int* enqueued) {
+  PeerComm* pc = static_cast<PeerComm*>(pcv);
+  *enqueued = 0;
+  if (!pc->shared_device || g_peer_spin_shared.load() != 0) return VS_OK;
+  RET(peer_host_wait(pc, st, x->flags, x->seq, src));
+  *enqueued = 1;
+  return VS_OK;
+}
 static int train_peer_publish(void* pcv, cudaStream_t st, const void* payload, const PeerXchg* x) {
   PeerComm* pc = static_cast<PeerComm*>(pcv);
   CK(launch_peer_publish(pc->bases, pc->world, pc->rank, payload, x->stride, x->data_off, x->flag_off, x->seq, x->ticket, st),
@@ -2510,6 +2688,7 @@ int32_t vs_pq_train_sharded_peer(uint64_t h, uint64_t comm, int64_t n_total, int
   tc.peer = pc;
   tc.peer_begin = train_peer_begin;
   tc.peer_publish = train_peer_publish;
+  tc.peer_wait = train_peer_wait;
   return pq_train_device(st, s->X, s->n, d, M, K, iterations, seed, lanes(), centroids_out, &tc);
 }
 

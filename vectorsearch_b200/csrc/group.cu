@@ -206,7 +206,7 @@ int group_start(int n, const int* cuda_devs) {
   // peer access both ways between every pair, one communicator rank per GPU
   int rc = fan_out(G, [&](int r) {
     for (int p = 0; p < n; p++) {
-      if (p == r) continue;
+      if (p == r || devs[p] == devs[r]) continue;
       int can = 0;
       cudaError_t e = cudaDeviceCanAccessPeer(&can, devs[r], devs[p]);
       if (e != cudaSuccess || !can) {

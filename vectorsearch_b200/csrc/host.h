@@ -108,6 +108,8 @@ struct TrainComm {
   void* peer = nullptr;
   int (*peer_begin)(void* peer, cudaStream_t st, size_t bytes, PeerXchg* x) = nullptr;    // reserves the next slot
   int (*peer_publish)(void* peer, cudaStream_t st, const void* payload, const PeerXchg* x) = nullptr;
+  // orders st behind rank src's publish (src < 0: all); *enqueued = 1: done on the stream, the kernel must not poll
+  int (*peer_wait)(void* peer, cudaStream_t st, const PeerXchg* x, int src, int* enqueued) = nullptr;
 };
 // PqTrainer.train on device-resident rows; centroids_out is HOST memory [M][K][d/M]  (pqtrain.cu)
 int pq_train_device(cudaStream_t st, const float* dX, int64_t n, int d, int M, int K, int iterations,

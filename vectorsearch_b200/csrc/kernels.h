@@ -181,6 +181,16 @@ cudaError_t launch_peer_reduce(const void* gath, int w, size_t stride, int64_t n
                                int32_t* out_i, const unsigned long long* flags, unsigned long long seq, cudaStream_t st);
 // orders the stream behind the publish of ONE source rank
 cudaError_t launch_peer_wait_one(const unsigned long long* flags, int src, unsigned long long seq, cudaStream_t st);
+// Graph construction (GraphBuilder.buildL2Neighbors / buildPrunedNeighbors): node row0 + q's nominated candidates
+// (brute-force order, the node itself possibly among them) -> the reference's neighbour list in (l2Squared, j) order,
+// optionally pruned.  flags[q] = 1: the candidate list may have cut a group of equal-distance rows: redo exactly.
+cudaError_t launch_knn_finalize(const float* X, int64_t n, int d, int lanes, int64_t row0, int nrows, const int64_t* cand_ids,
+                                const double* cand_scores, const int32_t* cand_counts, int kq, int take, int degree, int keep,
+                                bool check_closure, double alpha, bool prune, int64_t id_base, int32_t* neighbors,
+                                int32_t* counts, int32_t* flags, cudaStream_t st);
+// exact candidates of listed nodes: the kq smallest (l2Squared, j), j != node, written like a brute-force result
+cudaError_t launch_knn_exact(const float* X, int64_t n, int d, int lanes, const int32_t* nodes, int nnodes, int kq, int64_t id_base,
+                             int64_t* cand_ids, double* cand_scores, int32_t* cand_counts, cudaStream_t st);
 // stable sort by score descending of `total` (id, score) pairs, first k
 cudaError_t launch_merge(const int64_t* ids, const double* scores, int64_t total, int k,
                          int64_t* ids_out, double* scores_out, int32_t* count_out, cudaStream_t st);

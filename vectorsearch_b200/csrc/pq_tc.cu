@@ -12,14 +12,16 @@
 //     argmax_c D = argmin_c |x - c|^2, no coefficient to apply in the epilogue.
 //   * pq_tc_assign_kernel: persistent, warp-specialised like batch_gemm_kernel.  A CTA keeps the B blocks of 4
 //     subspaces resident (64 KB), TMA streams the A blocks of its row tiles (128 rows x 128 bytes per subspace pair), one
-//     thread issues the MMAs into a double-buffered 128 x 256 accumulator, four epilogue warps (thread = row) read
-//     it back and keep the two largest keys (D with the low 6 mantissa bits replaced by a column slot) in four
-//     independent chains.  If the runner-up is outside the error band the winner IS the reference argmin; otherwise
+//     thread issues the MMAs into a double-buffered 128 x 256 accumulator, eight epilogue warps (thread = row, two
+//     warps share a row's 256 columns) read it back twice: once for the largest key (D with the low 6 mantissa bits
+//     replaced by a column slot; ALU pipe), once to count the columns inside the error band of that maximum with
+//     saturating multiply-adds (FMA pipe).  If nothing else is inside the band the winner IS the reference argmin; otherwise
 //     the warp re-reads the accumulator and the centroids inside the band are decided in the reference's own
 //     arithmetic, strict '<' in ascending index -- bit-identical codes, like pq.cu.
 //   * tq_prep_*: one pass that writes the operand images (64 bytes per row and subspace; the scale and the
 //     norm bounds of the error band stay on the device, nothing synchronises).
-// The kernel is bound by its epilogue (four instructions per (row, centroid)), not by the MMA.
+// The kernel is bound by its epilogue (3.5 instructions per (row, centroid): 1.5 on the half-rate ALU pipe, 2 on the FMA
+// pipe), not by the MMA.
 #include <algorithm>
 #include <atomic>
 #include <mutex>
@@ -276,9 +278,12 @@ pq_tc_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         mbar_wait(tfull + a, (it >> 1) & 1);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(a * TQ_N);
-        float m1[4], m2[4];  // four independent chains: column j -> chain j & 3, slot j >> 2 (6 bits: j < 256)
+        // Pass 1 (ALU pipe, 1.5 operations per column): the LARGEST key of this warp's 128 columns -- D with its low 6
+        // mantissa bits replaced by a column slot -- in four independent chains, two columns per 3-input maximum
+        // (column j -> chain j & 3, slot j >> 2).
+        float m1[4];
 #pragma unroll
-        for (int c = 0; c < 4; c++) m1[c] = m2[c] = ninf;
+        for (int c = 0; c < 4; c++) m1[c] = ninf;
         uint32_t v[2][32];
         tc_ld32(taddr + (uint32_t)ch * 128, v[0]);
 #pragma unroll
@@ -286,8 +291,6 @@ pq_tc_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tc_wait_ld();
           tc_pin32(v[h & 1]);
           if (h < 3) tc_ld32(taddr + (uint32_t)(ch * 128 + (h + 1) * 32), v[(h + 1) & 1]);
-          // two columns of a chain per step: 5 min / max operations (one of them 3-input) instead of 6 -- the ALU
-          // pipe is what bounds this kernel (profiles/r1_pq_tc_full.txt)
 #pragma unroll
           for (int p = 0; p < 4; p++) {
 #pragma unroll
@@ -296,29 +299,45 @@ pq_tc_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               const int ca = h * 32 + ja, cb = h * 32 + jb;
               const float ka = __uint_as_float((v[h & 1][ja] & 0xffffffc0u) | (uint32_t)(ch * 32 + (ca >> 2)));
               const float kb = __uint_as_float((v[h & 1][jb] & 0xffffffc0u) | (uint32_t)(ch * 32 + (cb >> 2)));
-              const float hi = fmaxf(ka, kb), lo = fminf(ka, kb);
-              const float t = fminf(m1[c], hi);
-              m2[c] = fmaxf(fmaxf(m2[c], lo), t);
-              m1[c] = fmaxf(m1[c], hi);
+              m1[c] = fmaxf(fmaxf(m1[c], ka), kb);
             }
           }
         }
-        // this half's two largest keys over the four chains (the winning chain travels beside the key)
-        float b1 = m1[0], b2 = m2[0];
+        float b1 = m1[0];
         int bc = 0;
 #pragma unroll
         for (int c = 1; c < 4; c++) {
           if (m1[c] > b1) {
-            b2 = fmaxf(b1, m2[c]);
             b1 = m1[c];
             bc = c;
-          } else {
-            b2 = fmaxf(b2, m1[c]);
           }
+        }
+        // Pass 2 (FMA pipe, which pass 1 leaves idle): is any OTHER column of this half within the error band of that
+        // maximum?  The accumulator is read once more and every column adds sat((D - (v - 4 band)) / (2 band)): 1 for
+        // the maximum itself and for every column within 2 band of it (the band the decision needs), a fraction for
+        // columns between 2 and 4 band, 0 below and for NaN -- so a sum above 1.5 means "doubt" and can only err on
+        // the safe side.  The runner-up VALUE is no longer tracked: 3.5 -> 1.5 half-rate operations per column.
+        float cnt;
+        {
+          const float vl = __uint_as_float(__float_as_uint(b1) & 0xffffffc0u);
+          const float big = fminf(1.0f / (2.0f * bandD), 1.152921504606846976e18f);  // 2^60: D * big stays finite
+          const float off = -(vl - 4.0f * bandD) * big;
+          float c4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+          tc_ld32(taddr + (uint32_t)ch * 128, v[0]);
+#pragma unroll
+          for (int h = 0; h < 4; h++) {
+            tc_wait_ld();
+            tc_pin32(v[h & 1]);
+            if (h < 3) tc_ld32(taddr + (uint32_t)(ch * 128 + (h + 1) * 32), v[(h + 1) & 1]);
+#pragma unroll
+            for (int j = 0; j < 32; j++) c4[j & 3] += __saturatef(fmaf(__uint_as_float(v[h & 1][j]), big, off));
+          }
+          cnt = (c4[0] + c4[1]) + (c4[2] + c4[3]);
+          if (!(vl > ninf)) cnt = 2.0f;  // no finite maximum (NaN row, overflow): doubt
         }
         float4* xch = sm_x + (size_t)((it & 1) * 4 + lq) * 32 + lane;  // double-buffered by step parity
         if (ch == 1) {
-          *xch = make_float4(b1, b2, __int_as_float(bc), 0.0f);
+          *xch = make_float4(b1, cnt, __int_as_float(bc), 0.0f);
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty + a);                        // this warp is done with the accumulator
@@ -328,21 +347,24 @@ pq_tc_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           continue;
         }
         asm volatile("bar.sync %0, 64;" ::"r"(8 + (it & 1) * 4 + lq) : "memory");
+        float b2;  // the best key of the half that lost: the only column of that half that can matter
         {
           const float4 o = *xch;
           if (o.x > b1) {
-            b2 = fmaxf(b1, o.y);
+            b2 = b1;
             b1 = o.x;
+            cnt = o.y;
             bc = __float_as_int(o.z);
           } else {
-            b2 = fmaxf(b2, o.x);
+            b2 = o.x;
           }
         }
         int best = (int)((__float_as_uint(b1) & 63u) * 4u) + bc;
         const float v1 = __uint_as_float(__float_as_uint(b1) & 0xffffffc0u), v2 = __uint_as_float(__float_as_uint(b2) & 0xffffffc0u);
         const bool finite = v1 > ninf && v1 < __int_as_float(0x7f800000);
         // truncating 6 mantissa bits moves a key by at most 2^-17 |D|: part of the band (|D| <= s^2 (|x|^2 + |c|^2))
-        const bool doubt = live && (!finite || !(v1 - v2 > 2.0f * bandD) || best >= K);
+        // doubt: a second column of the winning half inside the band (cnt), or the other half's best inside it (v2)
+        const bool doubt = live && (!finite || cnt > 1.5f || !(v1 - v2 > 2.0f * bandD) || best >= K);
         const unsigned any = __ballot_sync(FULL_MASK, doubt);
         if (any) {
           // near-tie, duplicate centroids, NaN or overflow somewhere in this warp: those rows decide in the

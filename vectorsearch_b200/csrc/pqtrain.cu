@@ -169,7 +169,7 @@ scatter_kernel(const int32_t* __restrict__ assign, int64_t n, int K, int nb, int
 }
 
 // thread per (subspace, cluster, component): sequential fp32 sum over the cluster's rows in row order
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(64)
 chain_sum_kernel(const float* __restrict__ X, int64_t n, int d, int K, int sd, int s_begin, int ns,
                  const int32_t* __restrict__ order, const int32_t* __restrict__ offsets,
                  const float* __restrict__ carry /* nullable: running sums of the lower row ranges */,
@@ -186,6 +186,26 @@ chain_sum_kernel(const float* __restrict__ X, int64_t n, int d, int K, int sd, i
   const float* col = X + (size_t)(s_begin + sl) * sd + comp;
   float acc = carry != nullptr ? carry[t] : 0.0f;
   int32_t j = j0;
+  // The additions are a dependent chain (that IS the reference's order); the loads are not.  The kernel is bound by how
+  // many row fetches are in flight (32 768 threads over 148 SMs is seven warps per SM), so every thread keeps CH_U gathers
+  // outstanding and fetches the NEXT batch's row indices before it adds the current one.
+  constexpr int CH_U = 32;
+  int32_t idx[CH_U];
+  if (j + CH_U <= j1) {
+#pragma unroll
+    for (int u = 0; u < CH_U; u++) idx[u] = ord[j + u];
+  }
+  for (; j + CH_U <= j1; j += CH_U) {
+    float v[CH_U];
+#pragma unroll
+    for (int u = 0; u < CH_U; u++) v[u] = __ldg(col + (size_t)idx[u] * d);
+    if (j + 2 * CH_U <= j1) {
+#pragma unroll
+      for (int u = 0; u < CH_U; u++) idx[u] = ord[j + CH_U + u];
+    }
+#pragma unroll
+    for (int u = 0; u < CH_U; u++) acc = __fadd_rn(acc, v[u]);
+  }
   for (; j + 8 <= j1; j += 8) {
     float v[8];
 #pragma unroll
@@ -281,7 +301,9 @@ int pq_train_device(cudaStream_t st, const float* dX, int64_t n, int d, int M, i
     count_launch();
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "gather launch");
     if ((r_ = comm->peer_publish(comm->peer, st, d_send_f, &x)) != VS_OK) return r_;
-    if ((e = launch_peer_reduce(x.gath, comm->world, x.stride, total, 0, 1, out, nullptr, x.flags, x.seq, st)) != cudaSuccess)
+    int enq = 0;
+    if ((r_ = comm->peer_wait(comm->peer, st, &x, -1, &enq)) != VS_OK) return r_;
+    if ((e = launch_peer_reduce(x.gath, comm->world, x.stride, total, 0, 1, out, nullptr, enq ? nullptr : x.flags, x.seq, st)) != cudaSuccess)
       return cuda_fail(e, "peer reduce launch");
     return VS_OK;
   };
@@ -386,23 +408,27 @@ int pq_train_device(cudaStream_t st, const float* dX, int64_t n, int d, int M, i
         { int r_ = comm->peer_begin(comm->peer, st, bytes_of((size_t)total, (size_t)ns * K), &x); if (r_ != VS_OK) return r_; }
         const float* carry = nullptr;
         if (comm->exact_order && comm->rank > 0) {
-          TCK(launch_peer_wait_one(x.flags, comm->rank - 1, x.seq, st), "peer wait launch");
+          int enq1 = 0;
+          { int r_ = comm->peer_wait(comm->peer, st, &x, comm->rank - 1, &enq1); if (r_ != VS_OK) return r_; }
+          if (!enq1) TCK(launch_peer_wait_one(x.flags, comm->rank - 1, x.seq, st), "peer wait launch");
           carry = reinterpret_cast<const float*>(x.gath + (size_t)(comm->rank - 1) * x.stride);
         }
-        chain_sum_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dX, n, d, K, sd, s0, ns, d_order, d_offsets, carry, d_send_f);
+        chain_sum_kernel<<<(unsigned)((total + 63) / 64), 64, 0, st>>>(dX, n, d, K, sd, s0, ns, d_order, d_offsets, carry, d_send_f);
         count_launch();
         TCK(cudaGetLastError(), "chain launch");
         TCK(cudaMemcpyAsync(reinterpret_cast<char*>(d_send_f) + ioff, d_counts, (size_t)ns * K * 4, cudaMemcpyDeviceToDevice, st), "D2D counts");
         { int r_ = comm->peer_publish(comm->peer, st, d_send_f, &x); if (r_ != VS_OK) return r_; }
+        int enq = 0;
+        { int r_ = comm->peer_wait(comm->peer, st, &x, -1, &enq); if (r_ != VS_OK) return r_; }
         TCK(launch_peer_reduce(x.gath, comm->world, x.stride, total, (int64_t)ns * K, comm->exact_order ? 2 : 0, d_sums, d_counts,
-                               x.flags, x.seq, st), "peer reduce launch");
+                               enq ? nullptr : x.flags, x.seq, st), "peer reduce launch");
       } else if (comm && comm->exact_order) {
         // The reference adds the rows of a cluster in ascending row order.  Shards are ascending row ranges, so
         // rank r continues the running sums of ranks 0..r-1: world rounds, in each of which exactly one rank
         // contributes (the others add zeros, x + 0.0f == x) -- the sums, hence the centroids, are the reference's bit for bit.
         for (int r = 0; r < comm->world; r++) {
           if (r == comm->rank) {
-            chain_sum_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dX, n, d, K, sd, s0, ns, d_order, d_offsets,
+            chain_sum_kernel<<<(unsigned)((total + 63) / 64), 64, 0, st>>>(dX, n, d, K, sd, s0, ns, d_order, d_offsets,
                                                                               r == 0 ? nullptr : comm->d_f32, d_sums);
             count_launch();
             TCK(cudaGetLastError(), "chain launch");
@@ -417,7 +443,7 @@ int pq_train_device(cudaStream_t st, const float* dX, int64_t n, int d, int M, i
         { int r_ = reduce(1, (int64_t)ns * K); if (r_ != VS_OK) return r_; }
         TCK(cudaMemcpyAsync(d_counts, comm->d_i32, (size_t)ns * K * 4, cudaMemcpyDeviceToDevice, st), "D2D counts");
       } else {
-      chain_sum_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dX, n, d, K, sd, s0, ns, d_order, d_offsets, nullptr, d_sums);
+      chain_sum_kernel<<<(unsigned)((total + 63) / 64), 64, 0, st>>>(dX, n, d, K, sd, s0, ns, d_order, d_offsets, nullptr, d_sums);
       count_launch();
       TCK(cudaGetLastError(), "chain launch");
       if (comm) {  // per-cluster sums and counts of all shards, one all-reduce each (sums re-associated across shards)

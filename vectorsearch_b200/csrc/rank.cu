@@ -381,6 +381,192 @@ merge_adc_rerank_kernel(const int64_t* gath, int w, int nq, int nc, int np, int 
   if (threadIdx.x == 0) counts_out[qi] = s_found;
 }
 
+// ---- graph construction: GraphBuilder.buildL2Neighbors / buildPrunedNeighbors (J/graph/GraphBuilder.java:41-109) ----
+// For node i the reference sorts ALL j != i by l2Squared(v_i, v_j) ascending with a stable sort (ties keep the lower j) and
+// takes the first L; the pruned variant then walks that list and drops a candidate u when a kept neighbour p has
+// l2Squared(v_u, v_p) <= alpha * l2Squared(v_i, v_u).  The O(n^2) part is the brute-force scan (K1 / K2: every row of the
+// segment is a query against the segment itself); this kernel turns each row's nominated candidates into the reference's
+// list.  The scan orders by sqrt(l2Squared) ("B order"), the reference by l2Squared itself ("A order"): sqrt is monotone
+// but not injective in double, so A is recovered by re-scoring the candidates here, and a row whose candidate list may
+// have cut a group of equal-sqrt rows short is FLAGGED and redone exactly (knn_exact_kernel).
+constexpr int KNN_THREADS = 256;
+constexpr int KNN_MAX_DEGREE = 512;
+
+__global__ void __launch_bounds__(KNN_THREADS)
+knn_finalize_kernel(const float* __restrict__ X, int64_t n, int d, int lanes, int64_t row0,
+                    const int64_t* __restrict__ cand_ids, const double* __restrict__ cand_scores,
+                    const int32_t* __restrict__ cand_counts, int kq, int np, int take, int degree, int keep, int check_closure,
+                    double alpha, int prune, int64_t id_base, int32_t* __restrict__ neighbors, int32_t* __restrict__ counts,
+                    int32_t* __restrict__ flags) {
+  // take: candidates considered (min(degree or lBuild, n-1)); keep: most neighbours kept (<= degree); degree: row pitch of the output
+  extern __shared__ __align__(16) ulonglong2 skey[];  // [np]
+  __shared__ int s_sel[KNN_MAX_DEGREE];
+  __shared__ int s_nsel, s_drop, s_flag;
+  const int qi = blockIdx.x;
+  const int64_t i = row0 + qi;
+  const float* xi = X + (size_t)i * d;
+  const int64_t* cand = cand_ids + (size_t)qi * kq;
+  const int cnt = cand_counts[qi] < kq ? cand_counts[qi] : kq;
+  const int lane = threadIdx.x & 31, hl = lane & 15, hw = threadIdx.x >> 4, nhw = blockDim.x >> 4;
+  const unsigned hmask = (lane < 16) ? 0x0000ffffu : 0xffff0000u;
+  const int base_lane = lane & 16;
+  if (threadIdx.x == 0) s_flag = 0;
+  for (int c = threadIdx.x; c < np; c += blockDim.x) st_key(skey + c, key_empty());
+  __syncthreads();
+  for (int c = hw; c < cnt; c += nhw) {
+    const int64_t j = cand[c] - id_base;
+    if (j < 0 || j >= n || j == i) continue;  // uniform across the half-warp
+    const double dd = ref_sum_halfwarp<REF_L2SQ>(xi, X + (size_t)j * d, d, lanes, hl, hmask, base_lane);
+    if (hl == 0) st_key(skey + c, Key{rank_hi_from_dist(dd), (uint64_t)j});
+  }
+  if (check_closure && threadIdx.x == 0) {
+    // B order = list order.  t = the score of the take-th entry that is a real neighbour (not the node itself, not a
+    // NaN distance); the list is closed when it is exhausted or its last entry is strictly farther than t.
+    bool closed = cnt < kq;
+    if (!closed) {
+      int seen = 0, pt = -1;
+      for (int c = 0; c < cnt && pt < 0; c++) {
+        const int64_t j = cand[c] - id_base;
+        const double sc = cand_scores[(size_t)qi * kq + c];
+        if (j == i || sc != sc) continue;
+        if (++seen == take) pt = c;
+      }
+      if (pt >= 0) {
+        const double t = cand_scores[(size_t)qi * kq + pt], last = cand_scores[(size_t)qi * kq + cnt - 1];
+        closed = last == last && last < t;  // scores are -distance: strictly smaller = strictly farther
+      }
+    }
+    s_flag = closed ? 0 : 1;
+  }
+  __syncthreads();
+  block_bitonic_sort_keys(skey, np);  // (l2Squared, j) ascending, NaN distances last, empty slots at the end
+  int total = 0;  // real candidates, capped at `take`
+  if (!prune) {
+    for (int c = threadIdx.x; c < degree; c += blockDim.x) {
+      const Key e = c < np ? ld_key(skey + c) : key_empty();
+      neighbors[(size_t)i * degree + c] = (c < keep && !key_is_empty(e)) ? (int32_t)e.lo : -1;
+    }
+    if (threadIdx.x == 0) {
+      while (total < keep && total < np && !key_is_empty(ld_key(skey + total))) total++;
+      counts[i] = total;
+      if (flags != nullptr) flags[qi] = s_flag;
+    }
+    return;
+  }
+  // pruned: greedy in A order over the first `take` (= min(lBuild, n-1)) candidates, at most `degree` kept
+  if (threadIdx.x == 0) s_nsel = 0;
+  __syncthreads();
+  for (int c = 0; c < take && c < np; c++) {
+    const Key e = ld_key(skey + c);
+    if (key_is_empty(e)) break;                 // uniform: shared memory
+    if (s_nsel >= keep) break;
+    const int u = (int)e.lo;
+    const double diu = dist_from_rank_hi(e.hi);
+    if (threadIdx.x == 0) s_drop = 0;
+    __syncthreads();
+    const int ns = s_nsel;
+    const float* xu = X + (size_t)u * d;
+    for (int t = hw; t < ns; t += nhw) {
+      const double dup = ref_sum_halfwarp<REF_L2SQ>(xu, X + (size_t)s_sel[t] * d, d, lanes, hl, hmask, base_lane);
+      if (hl == 0 && dup <= __dmul_rn(alpha, diu)) s_drop = 1;  // :101 (NaN compares false: kept, as in Java)
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && !s_drop) s_sel[s_nsel++] = u;
+    __syncthreads();
+  }
+  for (int c = threadIdx.x; c < degree; c += blockDim.x) neighbors[(size_t)i * degree + c] = c < s_nsel ? s_sel[c] : -1;
+  if (threadIdx.x == 0) {
+    counts[i] = s_nsel;
+    if (flags != nullptr) flags[qi] = s_flag;
+  }
+}
+
+// exact A-order candidates of ONE node: every row scored with the reference arithmetic (a half-warp per row), the kq
+// smallest (l2Squared, j) kept.  Slow (the whole segment per node) and exact; only flagged nodes come here.
+__global__ void __launch_bounds__(KNN_THREADS)
+knn_exact_kernel(const float* __restrict__ X, int64_t n, int d, int lanes, const int32_t* __restrict__ nodes, int kq, int kp,
+                 int64_t id_base, int64_t* __restrict__ cand_ids, double* __restrict__ cand_scores, int32_t* __restrict__ cand_counts) {
+  extern __shared__ __align__(128) ulonglong2 smem[];
+  const int qi = blockIdx.x;
+  const int64_t i = nodes[qi];
+  const float* xi = X + (size_t)i * d;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5, hl = lane & 15;
+  const unsigned hmask = (lane < 16) ? 0x0000ffffu : 0xffff0000u;
+  const int base_lane = lane & 16;
+  const int stride_keys = kp + TOPK_BUF;
+  WarpTopK tk;
+  tk.init(smem + (size_t)warp * stride_keys, kp, kq, lane);
+  for (int64_t j0 = (int64_t)warp * 32; j0 < n; j0 += (int64_t)nw * 32) {
+    // 16 rounds x 2 half-warps score 32 consecutive rows; lane l ends up holding the key of row j0 + l
+    Key mine = key_empty();
+    bool have = false;
+    for (int r = 0; r < 16; r++) {
+      const int64_t j = j0 + 2 * r + (lane >> 4);  // uniform within a half-warp
+      double dd = 0.0;
+      if (j < n) dd = ref_sum_halfwarp<REF_L2SQ>(xi, X + (size_t)j * d, d, lanes, hl, hmask, base_lane);
+      const double v0 = __shfl_sync(FULL_MASK, dd, 0), v1 = __shfl_sync(FULL_MASK, dd, 16);
+      if (lane == 2 * r) {
+        mine = Key{rank_hi_from_dist(v0), (uint64_t)(j0 + 2 * r)};
+        have = j0 + 2 * r < n && j0 + 2 * r != i;
+      }
+      if (lane == 2 * r + 1) {
+        mine = Key{rank_hi_from_dist(v1), (uint64_t)(j0 + 2 * r + 1)};
+        have = j0 + 2 * r + 1 < n && j0 + 2 * r + 1 != i;
+      }
+    }
+    tk.push(mine, have, lane);
+  }
+  tk.flush(lane);
+  block_combine_lists(smem, stride_keys, nw, kp, warp, lane);
+  __shared__ int s_found;
+  if (threadIdx.x == 0) s_found = 0;
+  __syncthreads();
+  int found = 0;
+  for (int c = threadIdx.x; c < kq; c += blockDim.x) {
+    const Key e = ld_key(smem + c);
+    const bool ok = !key_is_empty(e);
+    cand_ids[(size_t)qi * kq + c] = ok ? id_base + (int64_t)e.lo : -1;
+    cand_scores[(size_t)qi * kq + c] = ok ? dist_from_rank_hi(e.hi) : __longlong_as_double(0x7ff8000000000000ll);
+    found += ok ? 1 : 0;
+  }
+  if (found) atomicAdd(&s_found, found);
+  __syncthreads();
+  if (threadIdx.x == 0) cand_counts[qi] = s_found;
+}
+
+cudaError_t launch_knn_finalize(const float* X, int64_t n, int d, int lanes, int64_t row0, int nrows, const int64_t* cand_ids,
+                                const double* cand_scores, const int32_t* cand_counts, int kq, int take, int degree, int keep,
+                                bool check_closure, double alpha, bool prune, int64_t id_base, int32_t* neighbors,
+                                int32_t* counts, int32_t* flags, cudaStream_t st) {
+  if (degree > KNN_MAX_DEGREE || keep > degree || kq > RANK_MAX_CAND) return cudaErrorInvalidValue;
+  int np = 2;
+  while (np < kq) np <<= 1;
+  const size_t smem = (size_t)np * 16;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(knn_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  knn_finalize_kernel<<<nrows, KNN_THREADS, smem, st>>>(X, n, d, lanes, row0, cand_ids, cand_scores, cand_counts, kq, np, take,
+                                                        degree, keep, check_closure ? 1 : 0, alpha, prune ? 1 : 0, id_base,
+                                                        neighbors, counts, flags);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_knn_exact(const float* X, int64_t n, int d, int lanes, const int32_t* nodes, int nnodes, int kq, int64_t id_base,
+                             int64_t* cand_ids, double* cand_scores, int32_t* cand_counts, cudaStream_t st) {
+  const int kp = topk_pad(kq);
+  const size_t smem = (size_t)(KNN_THREADS / 32) * topk_warp_smem(kp);
+  if (smem > 200 * 1024) return cudaErrorInvalidValue;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(knn_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  knn_exact_kernel<<<nnodes, KNN_THREADS, smem, st>>>(X, n, d, lanes, nodes, kq, kp, id_base, cand_ids, cand_scores, cand_counts);
+  count_launch();
+  return cudaGetLastError();
+}
+
 // ---- an empty shard's contribution to an exchange --------------------------------------------------------
 // kind 0: brute-force / ADC lists [nq][2k] (ids -1, score bits NaN); kind 1: ADC + re-rank packs [nq][4][k] (state -1)
 __global__ void fill_pack_kernel(int64_t* __restrict__ pack, int nq, int k, int kind, int32_t* __restrict__ counts) {

@@ -394,6 +394,15 @@ class Segment:
         return self._trim(ids, sc, cn, single)
 
 
+    # -- graph construction ----------------------------------------------------------------------------
+    def knn_graph(self, degree: int, l_build: int = 0, alpha: float = 1.0):
+        """GraphBuilder.buildL2Neighbors(vectors, degree) (l_build == 0) or buildPrunedNeighbors(vectors, degree,
+        l_build, alpha) over this segment's rows -> list of int32 arrays (neighbour rows per node)."""
+        nb = np.full((self.n, degree), -1, dtype=np.int32)
+        cn = np.zeros(self.n, dtype=np.int32)
+        check(L.load().vs_knn_graph(self.handle, degree, l_build, float(alpha), _p(nb, L.i32p), _p(cn, L.i32p)))
+        return [nb[i, :cn[i]] for i in range(self.n)]
+
     # -- BEST_FIRST expansion scoring -------------------------------------------------------------------
     def adc_query(self, q) -> "AdcQuery":
         """LUT of `q` against this sealed segment, kept on the device (buildLut once per query and segment,

@@ -124,7 +124,8 @@ class ShardedSegment:
         self.exchange = "none" if world == 1 else "nccl all-gather"
         if peer is None:
             peer = os.environ.get("VS_PEER", "1") != "0"
-        self._peer_depth = self.PEER_RING * (max(1, slots) + 2)  # the coordinator's streams, torch's current one, a spare
+        # rings: the communicator's own (host entry points), the coordinator's streams, torch's current one, a spare
+        self._peer_depth = self.PEER_RING * (max(1, slots) + 3)
         if (world > 1 and peer and world <= 16 and self._peer_depth <= 64 and dist.is_available()
                 and dist.is_initialized() and dist.get_backend(group) == "nccl"):
             self._peer_setup()
@@ -211,12 +212,15 @@ class ShardedSegment:
         t = self.torch
         b = self._buffers(nq, k, slot)
         st = t.cuda.current_stream().cuda_stream
+        # the path depends only on what every rank has agreed on (communicator up, payload size) -- never on this
+        # rank's own row count: an empty shard takes part with an all-empty list
+        if self._comm is not None and nq * 2 * k * 8 <= self.PEER_SLOT_BYTES:
+            # ONE C call per query batch: scan into the stream's send buffer, push to the peers, merge
+            check(self.lib.vs_bruteforce_topk_exchange_dev(self.seg.handle, self._comm, d_q.data_ptr(), nq, k, metric,
+                                                           b["out_i"].data_ptr(), b["out_s"].data_ptr(), b["out_c"].data_ptr(), st))
+            return b["out_i"], b["out_s"], b["out_c"]
         check(self.lib.vs_bruteforce_topk_packed_dev(self.seg.handle, d_q.data_ptr(), nq, k, metric,
                                                      b["pack"].data_ptr(), b["cn"].data_ptr(), st))
-        if self._comm is not None and nq * 2 * k * 8 <= self.PEER_SLOT_BYTES:
-            check(self.lib.vs_exchange_merge_packed_dev(self._comm, b["pack"].data_ptr(), nq, k, 1, b["out_i"].data_ptr(),
-                                                        b["out_s"].data_ptr(), b["out_c"].data_ptr(), st))
-            return b["out_i"], b["out_s"], b["out_c"]
         if self.world == 1:
             gath = b["pack"]
         else:
@@ -226,12 +230,12 @@ class ShardedSegment:
                                            b["out_s"].data_ptr(), b["out_c"].data_ptr(), st))
         return b["out_i"], b["out_s"], b["out_c"]
 
-    def adc_rerank_topk_dev(self, d_q, nq: int, n_cand: int, k: int, metric: int = METRIC_L2):
+    def adc_rerank_topk_dev(self, d_q, nq: int, n_cand: int, k: int, metric: int = METRIC_L2, slot: int = -1):
         """Config C4 across shards: local ADC top n_cand + their exact scores (packed), ONE all-gather,
         one merge that re-ranks the GLOBAL first n_cand by approximate distance -- the reference's
         candidate set (J/fdb/FdbVectorIndex.java:820-828), not the union of per-shard winners."""
         t = self.torch
-        key = ("adc", nq, n_cand, k)
+        key = ("adc", nq, n_cand, k, slot)
         if key not in self._bufs:
             dev, w = self.dev, self.world
             self._bufs[key] = dict(
@@ -241,13 +245,12 @@ class ShardedSegment:
                 out_c=t.empty((nq,), dtype=t.int32, device=dev))
         b = self._bufs[key]
         st = t.cuda.current_stream().cuda_stream
+        if self._comm is not None and nq * 4 * n_cand * 8 <= self.PEER_SLOT_BYTES:
+            check(self.lib.vs_adc_rerank_topk_exchange_dev(self.seg.handle, self._comm, d_q.data_ptr(), nq, n_cand, k, metric, 0,
+                                                           b["out_i"].data_ptr(), b["out_s"].data_ptr(), b["out_c"].data_ptr(), st))
+            return b["out_i"], b["out_s"], b["out_c"]
         check(self.lib.vs_adc_rerank_packed_dev(self.seg.handle, d_q.data_ptr(), nq, n_cand, metric, 0,
                                                 b["pack"].data_ptr(), st))
-        if self._comm is not None and nq * 4 * n_cand * 8 <= self.PEER_SLOT_BYTES:
-            check(self.lib.vs_exchange_merge_adc_rerank_packed_dev(self._comm, b["pack"].data_ptr(), nq, n_cand, k,
-                                                                   b["out_i"].data_ptr(), b["out_s"].data_ptr(),
-                                                                   b["out_c"].data_ptr(), st))
-            return b["out_i"], b["out_s"], b["out_c"]
         if self.world == 1:
             gath = b["pack"]
         else:
@@ -257,6 +260,15 @@ class ShardedSegment:
                                                       b["out_s"].data_ptr(), b["out_c"].data_ptr(), st))
         return b["out_i"], b["out_s"], b["out_c"]
 
+    def adc_rerank_topk_pipelined(self, d_q, nq: int, n_cand: int, k: int, metric: int = METRIC_L2):
+        """adc_rerank_topk_dev on the next of the coordinator's streams (see bruteforce_topk_pipelined)."""
+        t = self.torch
+        slot = self._next
+        self._next = (self._next + 1) % len(self._streams)
+        with t.cuda.stream(self._streams[slot]):
+            ids, sc, cn = self.adc_rerank_topk_dev(d_q, nq, n_cand, k, metric, slot)
+        return ids, sc, cn, self._streams[slot]
+
     def adc_rerank_topk(self, q, n_cand: int, k: int, metric: int = METRIC_L2):
         """Host query [d] or [nq][d] -> numpy results of the cross-shard ADC + re-rank (H2D and D2H inside): one C
         call through the peer exchange when it is up, else the device path with torch copies."""
@@ -264,7 +276,7 @@ class ShardedSegment:
         single = q.ndim == 1
         q2 = q.reshape(1, -1) if single else q
         nq = q2.shape[0]
-        if self._comm is not None and nq * 4 * n_cand * 8 <= self.PEER_SLOT_BYTES and self.seg.n > 0:
+        if self._comm is not None and nq * 4 * n_cand * 8 <= self.PEER_SLOT_BYTES:
             ids = np.zeros((nq, k), dtype=np.int64)
             sc = np.zeros((nq, k), dtype=np.float64)
             cn = np.zeros(nq, dtype=np.int32)
@@ -293,6 +305,12 @@ class ShardedSegment:
 
         t = self.torch
         d = self.seg.d
+        if allreduce is None and self._comm is not None and (k * d + m * k) * 4 + 64 <= self.PEER_SLOT_BYTES:
+            # the all-reduce of sums and counts runs inside libvsgpu over the peer buffers (no upcall, no host sync per reduction)
+            cent = np.empty((m, k, d // m), dtype=np.float32)
+            check(self.lib.vs_pq_train_sharded_peer(self.seg.handle, self._comm, n_total, row_lo, 1 if exact_order else 0,
+                                                    m, k, iterations, seed, cent.ctypes.data_as(L.f32p)))
+            return cent
         f32 = t.zeros(m * k * (d // m), dtype=t.float32, device=self.dev)
         i32 = t.zeros(m * k, dtype=t.int32, device=self.dev)
         t.cuda.synchronize()
@@ -341,7 +359,7 @@ class ShardedSegment:
         single = q.ndim == 1
         q2 = q.reshape(1, -1) if single else q
         nq = q2.shape[0]
-        if self._comm is not None and nq * 2 * k * 8 <= self.PEER_SLOT_BYTES and self.seg.n > 0:
+        if self._comm is not None and nq * 2 * k * 8 <= self.PEER_SLOT_BYTES:
             # one C call: pinned staging, scan, peer exchange, merge writing host memory, one synchronisation
             ids = np.zeros((nq, k), dtype=np.int64)
             sc = np.zeros((nq, k), dtype=np.float64)
