@@ -320,7 +320,11 @@ pq_tc_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         float cnt;
         {
           const float vl = __uint_as_float(__float_as_uint(b1) & 0xffffffc0u);
-          const float big = fminf(1.0f / (2.0f * bandD), 1.152921504606846976e18f);  // 2^60: D * big stays finite
+          // (a band so narrow that 1 / band would overflow the product -- rows scaled into the denormals by one huge
+          //  element -- cannot be counted this way: every row of such a call is decided exactly)
+          const float big_raw = 1.0f / (2.0f * bandD);
+          const bool countable = big_raw <= 1.152921504606846976e18f;  // 2^60: D * big stays finite
+          const float big = countable ? big_raw : 0.0f;
           const float off = -(vl - 4.0f * bandD) * big;
           float c4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
           tc_ld32(taddr + (uint32_t)ch * 128, v[0]);
@@ -333,7 +337,7 @@ pq_tc_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int j = 0; j < 32; j++) c4[j & 3] += __saturatef(fmaf(__uint_as_float(v[h & 1][j]), big, off));
           }
           cnt = (c4[0] + c4[1]) + (c4[2] + c4[3]);
-          if (!(vl > ninf)) cnt = 2.0f;  // no finite maximum (NaN row, overflow): doubt
+          if (!(vl > ninf) || !countable) cnt = 2.0f;  // no finite maximum (NaN row, overflow) or no usable band: doubt
         }
         float4* xch = sm_x + (size_t)((it & 1) * 4 + lq) * 32 + lane;  // double-buffered by step parity
         if (ch == 1) {
