@@ -1228,16 +1228,21 @@ int32_t vs_segment_attach_pq(uint64_t h, const float* centroids, int32_t M, int3
   if (M <= 0 || K <= 0 || s->d % M != 0) return fail(VS_EINVAL, "Invalid PQ params (m,k,dimension)");
   const int subDim = s->d / M;
   CK(cudaStreamSynchronize(c->stream), "sync");
-  if (s->centroids) cudaFree(s->centroids);
-  if (s->codes) cudaFree(s->codes);
-  s->centroids = nullptr;
-  s->codes = nullptr;
+  // re-sealing with the same shape (a rebuilt codebook) keeps the buffers: freeing and re-allocating gigabytes of codes
+  // costs more than encoding them
+  const bool same_shape = s->centroids && s->M == M && s->K == K && (s->codes || s->n == 0);
+  if (!same_shape) {
+    if (s->centroids) cudaFree(s->centroids);
+    if (s->codes) cudaFree(s->codes);
+    s->centroids = nullptr;
+    s->codes = nullptr;
+  }
   s->M = s->K = s->subDim = 0;
   const size_t cb = (size_t)M * K * subDim * 4;
-  CK(cudaMalloc(&s->centroids, cb), "cudaMalloc(centroids)");
+  if (!s->centroids) CK(cudaMalloc(&s->centroids, cb), "cudaMalloc(centroids)");
   CK(cudaMemcpyAsync(s->centroids, centroids, cb, cudaMemcpyHostToDevice, c->stream), "H2D centroids");
   if (s->n > 0) {
-    CK(cudaMalloc(&s->codes, (size_t)s->n * M), "cudaMalloc(codes)");
+    if (!s->codes) CK(cudaMalloc(&s->codes, (size_t)s->n * M), "cudaMalloc(codes)");
     if (codes) {
       CK(cudaMemcpyAsync(s->codes, codes, (size_t)s->n * M, cudaMemcpyHostToDevice, c->stream), "H2D codes");
     } else {

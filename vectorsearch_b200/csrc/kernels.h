@@ -309,6 +309,8 @@ cudaError_t launch_pq_assign_tc(const PqAssignLaunch& L, int sms, cudaStream_t s
 void pq_tc_scope_begin();
 void pq_tc_scope_end();
 void pq_tc_set_keep_bytes(unsigned long long bytes);  // scratch the pool keeps cached between calls
+// stream-ordered scratch from that pool (released with cudaFreeAsync on the same stream)
+cudaError_t pq_pool_alloc(void** p, size_t bytes, cudaStream_t st);
 cudaError_t launch_pq_assign(const PqAssignLaunch& L, cudaStream_t st);
 
 }  // namespace vs

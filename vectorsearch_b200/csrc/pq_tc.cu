@@ -502,8 +502,39 @@ void pq_tc_scope_end() {
   t_scope.open = false;
 }
 
-// Tensor-core assignment over all subspaces.  The operand image of the rows (64 bytes per row and subspace) is
-// built slab by slab in scratch memory, so any n fits.
+// Tensor-core assignment over all subspaces.  The operand image of the rows (64 bytes per row and subspace) is built in
+// scratch memory:
+//   * inside a training scope, when the whole image fits the budget, it is built ONCE and kept for the Lloyd iterations;
+//   * otherwise (every encode call) in two small slabs (TQ_SLAB_BYTES each) that alternate: the image of slab i+1 is
+//     written on a helper stream while the tensor-core kernel of slab i runs, so the conversion pass hides behind the
+//     assignment, and the 2 x 2 GB stay cached in the pool between calls -- an encode never reaches the driver's
+//     allocator after the first one (a 24 GB slab per call, as round 1 had it, cost 0.1 s of mapping per 4 GB above the
+//     pool's keep threshold: 100M rows encoded cold in 4.5 s instead of 0.6 s).
+namespace {
+constexpr size_t TQ_SLAB_BYTES = size_t(2) << 30;
+struct HelperStream {
+  cudaStream_t st[64] = {};
+  ~HelperStream() {}  // process teardown: the context may be gone
+};
+thread_local HelperStream t_helper;
+cudaError_t helper_stream(cudaStream_t* out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  if (!t_helper.st[dev] && (e = cudaStreamCreateWithFlags(&t_helper.st[dev], cudaStreamNonBlocking)) != cudaSuccess) return e;
+  *out = t_helper.st[dev];
+  return cudaSuccess;
+}
+struct Ev {
+  cudaEvent_t e = nullptr;
+  cudaError_t make() { return cudaEventCreateWithFlags(&e, cudaEventDisableTiming); }
+  ~Ev() {
+    if (e) cudaEventDestroy(e);
+  }
+};
+}  // namespace
+
 cudaError_t launch_pq_assign_tc(const PqAssignLaunch& L, int sms, cudaStream_t st) {
   cudaError_t e;
   const int M = L.M;
@@ -511,29 +542,40 @@ cudaError_t launch_pq_assign_tc(const PqAssignLaunch& L, int sms, cudaStream_t s
   const size_t per_row = (size_t)(M / 2) * 128;
   TcScope& sc = t_scope;
   const bool reuse = sc.open && sc.valid && sc.X == L.X && sc.n == L.n && sc.d == L.d && sc.M == M && sc.st == st;
+  const int64_t n_pad = (L.n + TQ_M - 1) / TQ_M * TQ_M;
   int64_t slab = 0;
-  PoolMem xop, cop, stats;  // owners when nothing is kept
-  void *p_xop, *p_cop, *p_stats;
+  bool whole = false;         // one image of all rows (kept by an open scope)
+  PoolMem xop, xop2, cop, stats;  // owners when nothing is kept
+  void *p_xop[2] = {nullptr, nullptr}, *p_cop, *p_stats;
   if (reuse) {
-    slab = (L.n + TQ_M - 1) / TQ_M * TQ_M;
-    p_xop = sc.xop; p_cop = sc.cop; p_stats = sc.stats;
+    slab = n_pad;
+    whole = true;
+    p_xop[0] = sc.xop; p_cop = sc.cop; p_stats = sc.stats;
   } else {
     cudaMemPool_t pool;
     if ((e = tq_pool(&pool)) != cudaSuccess) return e;
-    size_t free_b = 0, total_b = 0, cached = 0, used = 0;
-    if ((e = cudaMemGetInfo(&free_b, &total_b)) != cudaSuccess) return e;
-    cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &cached);
-    cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
-    size_t budget = (free_b + (cached > used ? cached - used : 0)) / 2;  // what the pool holds idle is ours to use
-    if (budget > (size_t(24) << 30)) budget = size_t(24) << 30;
-    slab = (int64_t)(budget / per_row);
-    slab = (slab / TQ_M) * TQ_M;
-    if (slab < TQ_M) return cudaErrorMemoryAllocation;
-    if (slab > L.n) slab = (L.n + TQ_M - 1) / TQ_M * TQ_M;
-    if ((e = xop.alloc((size_t)slab * per_row, pool, st)) != cudaSuccess) return e;
+    if (sc.open) {  // a training run: keep the whole image if the device has room for it
+      size_t free_b = 0, total_b = 0, cached = 0, used = 0;
+      if ((e = cudaMemGetInfo(&free_b, &total_b)) != cudaSuccess) return e;
+      cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &cached);
+      cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
+      size_t budget = (free_b + (cached > used ? cached - used : 0)) / 2;  // what the pool holds idle is ours to use
+      if (budget > (size_t(24) << 30)) budget = size_t(24) << 30;
+      whole = (size_t)n_pad * per_row <= budget;
+    }
+    if (whole) {
+      slab = n_pad;
+      if ((e = xop.alloc((size_t)slab * per_row, pool, st)) != cudaSuccess) return e;
+    } else {
+      slab = (int64_t)(TQ_SLAB_BYTES / per_row) / TQ_M * TQ_M;
+      if (slab < TQ_M) slab = TQ_M;
+      if (slab > n_pad) slab = n_pad;
+      if ((e = xop.alloc((size_t)slab * per_row, pool, st)) != cudaSuccess) return e;
+      if (slab < n_pad && (e = xop2.alloc((size_t)slab * per_row, pool, st)) != cudaSuccess) return e;
+    }
     if ((e = cop.alloc((size_t)(M / 2) * TQ_N * 128, pool, st)) != cudaSuccess) return e;
     if ((e = stats.alloc(sizeof(TqStats), pool, st)) != cudaSuccess) return e;
-    p_xop = xop.p; p_cop = cop.p; p_stats = stats.p;
+    p_xop[0] = xop.p; p_xop[1] = xop2.p ? xop2.p : xop.p; p_cop = cop.p; p_stats = stats.p;
   }
   TqStats* d_st = static_cast<TqStats*>(p_stats);
   if (reuse) {
@@ -554,15 +596,38 @@ cudaError_t launch_pq_assign_tc(const PqAssignLaunch& L, int sms, cudaStream_t s
   CUtensorMap tmB;
   if (!encode_rows_map(&tmB, p_cop, (int64_t)(M / 2) * TQ_N, 64, 64, true, TQ_N)) return cudaErrorInvalidValue;
   if ((e = cudaFuncSetAttribute(pq_tc_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TQ_SMEM)) != cudaSuccess) return e;
-  for (int64_t r0 = 0; r0 < L.n; r0 += slab) {
+  // Two slabs alternate: the helper stream writes the image of slab i (after the assignment that last read that buffer)
+  // while `st` runs the assignment of slab i-1.  NOTE the row-norm bound (xxmax) grows as slabs are converted: the
+  // assignment of slab i reads it after the images of slabs 0..i, all of which it covers (a bound over MORE rows only
+  // widens the band).
+  const bool piped = !reuse && !whole && slab < n_pad;
+  cudaStream_t hs = st;
+  Ev ready[2], done[2], start;
+  if (piped) {
+    if ((e = helper_stream(&hs)) != cudaSuccess) return e;
+    for (int i = 0; i < 2; i++)
+      if ((e = ready[i].make()) != cudaSuccess || (e = done[i].make()) != cudaSuccess) return e;
+    if ((e = start.make()) != cudaSuccess) return e;
+    if ((e = cudaEventRecord(start.e, st)) != cudaSuccess) return e;       // scale, centroid image, fresh buffers
+    if ((e = cudaStreamWaitEvent(hs, start.e, 0)) != cudaSuccess) return e;
+  }
+  int64_t si = 0;
+  for (int64_t r0 = 0; r0 < L.n; r0 += slab, si++) {
     const int64_t cnt = std::min<int64_t>(slab, L.n - r0);
+    const int b = (int)(si & 1);
+    void* xb = p_xop[piped ? b : 0];
     if (!reuse) {
+      if (piped && si >= 2 && (e = cudaStreamWaitEvent(hs, done[b].e, 0)) != cudaSuccess) return e;
       count_launch();
-      tq_prep_rows_kernel<<<sms * 16, 256, 0, st>>>(L.X + (size_t)r0 * L.d, cnt, L.d, M, static_cast<__half*>(p_xop), d_st);
+      tq_prep_rows_kernel<<<sms * 16, 256, 0, hs>>>(L.X + (size_t)r0 * L.d, cnt, L.d, M, static_cast<__half*>(xb), d_st);
       if ((e = cudaGetLastError()) != cudaSuccess) return e;
+      if (piped) {
+        if ((e = cudaEventRecord(ready[b].e, hs)) != cudaSuccess) return e;
+        if ((e = cudaStreamWaitEvent(st, ready[b].e, 0)) != cudaSuccess) return e;
+      }
     }
     CUtensorMap tmA;  // [cnt rows][M / 2 pairs * 64 halfs], box = 64 halfs x 128 rows
-    if (!encode_rows_map(&tmA, p_xop, cnt, M * 32, (int64_t)M * 32, true, TQ_M)) return cudaErrorInvalidValue;
+    if (!encode_rows_map(&tmA, xb, cnt, M * 32, (int64_t)M * 32, true, TQ_M)) return cudaErrorInvalidValue;
     const int64_t tiles = (cnt + TQ_M - 1) / TQ_M;
     int nsplit = sms / nsg;
     if (nsplit < 1) nsplit = 1;
@@ -571,9 +636,10 @@ cudaError_t launch_pq_assign_tc(const PqAssignLaunch& L, int sms, cudaStream_t s
     pq_tc_assign_kernel<<<nsg * nsplit, TQ_THREADS, TQ_SMEM, st>>>(tmA, tmB, L.X, L.n, L.d, M, L.K, L.centroids, L.lanes, d_st, r0,
                                                                    cnt, nsg, tiles, L.codes_u8, L.assign_i32);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (piped && (e = cudaEventRecord(done[b].e, st)) != cudaSuccess) return e;
   }
   if (reuse) return cudaSuccess;  // everything this call touched lives until the scope ends
-  if (sc.open && slab >= L.n) {   // first call of a scope and the whole image fits: keep it
+  if (sc.open && whole) {         // first call of a scope and the whole image fits: keep it
     sc.release();
     sc.X = L.X; sc.n = L.n; sc.d = L.d; sc.M = M; sc.st = st;
     sc.xop = xop.p; sc.cop = cop.p; sc.stats = stats.p;
@@ -585,5 +651,12 @@ cudaError_t launch_pq_assign_tc(const PqAssignLaunch& L, int sms, cudaStream_t s
 }
 
 void pq_tc_set_keep_bytes(unsigned long long bytes) { g_pool_keep.store(bytes); }
+
+cudaError_t pq_pool_alloc(void** p, size_t bytes, cudaStream_t st) {
+  cudaMemPool_t pool;
+  cudaError_t e = tq_pool(&pool);
+  if (e != cudaSuccess) return e;
+  return cudaMallocFromPoolAsync(p, bytes, pool, st);
+}
 
 }  // namespace vs
