@@ -164,7 +164,9 @@ __global__ void __launch_bounds__(TQ_THREADS, 1)
 pq_tc_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const float* __restrict__ X, int64_t n, int d, int M, int K, const float* __restrict__ centroids, int lanes,
                     const TqStats* stats, int64_t row0 /* first row of this slab */, int64_t nslab, int nsg, int64_t tiles,
-                    uint8_t* __restrict__ codes_u8, int32_t* __restrict__ assign_i32) {
+                    uint8_t* __restrict__ codes_u8, int32_t* __restrict__ assign_i32,
+                    unsigned long long* __restrict__ dlist /* [nsg][dcap]: (row << 8 | subspace) of undecided entries */,
+                    unsigned int* __restrict__ dcount /* [nsg] */, unsigned int dcap) {
   extern __shared__ __align__(1024) uint8_t tq_smem[];
   uint8_t* bq = tq_smem;                                          // [TQ_PPC][32 KB] centroid blocks (two subspaces each)
   uint8_t* stages = bq + (size_t)TQ_PPC * TQ_B_BYTES;             // [TQ_STAGES][16 KB] row blocks (two subspaces each)
@@ -218,7 +220,7 @@ pq_tc_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       uint32_t ph = 0;
       for (int64_t tile = split; tile < tiles; tile += nsplit) {
         for (int pl = 0; pl < np; pl++) {
-          mbar_wait(empty + s, ph ^ 1);
+          mbar_wait_suspend(empty + s, ph ^ 1);
           mbar_expect_tx(full + s, TQ_A_BYTES);
           tma_load_2d(stages + (size_t)s * TQ_A_BYTES, &tmA, ((s_first >> 1) + pl) * 64, (int)(tile * TQ_M), full + s);
           if (++s == TQ_STAGES) {
@@ -232,15 +234,15 @@ pq_tc_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {  // ===== MMA issuer =====
       int s = 0, it = 0;
       uint32_t ph = 0;
-      mbar_wait(bfull, 0);
+      mbar_wait_suspend(bfull, 0);
       for (int64_t tile = split; tile < tiles; tile += nsplit) {
         for (int pl = 0; pl < np; pl++) {
-          mbar_wait(full + s, ph);
+          mbar_wait_suspend(full + s, ph);
           const uint64_t adesc = umma_desc_sw128(smem_u32(stages + (size_t)s * TQ_A_BYTES));
           const uint64_t bdesc = umma_desc_sw128(smem_u32(bq + (size_t)pl * TQ_B_BYTES));
           for (int e = 0; e < 2; e++, it++) {  // the two subspaces of the pair: halfs 0..31 and 32..63 of the operand rows
             const int a = it & 1;
-            mbar_wait(tempty + a, ((it >> 1) & 1) ^ 1);
+            mbar_wait_suspend(tempty + a, ((it >> 1) & 1) ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)a * TQ_N;
             tc_mma_f16(d_tmem, adesc + 4 * e, bdesc + 4 * e, TQ_IDESC, 0u);          // xh.ch + xl.ch
@@ -275,7 +277,7 @@ pq_tc_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int sl = 0; sl < ns; sl++, it++) {
         const int a = it & 1;
         const int sub = s_first + sl;
-        mbar_wait(tfull + a, (it >> 1) & 1);
+        mbar_wait_suspend(tfull + a, (it >> 1) & 1);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(a * TQ_N);
         // Pass 1 (ALU pipe, 1.5 operations per column): the LARGEST key of this warp's 128 columns -- D with its low 6
@@ -369,43 +371,24 @@ pq_tc_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // truncating 6 mantissa bits moves a key by at most 2^-17 |D|: part of the band (|D| <= s^2 (|x|^2 + |c|^2))
         // doubt: a second column of the winning half inside the band (cnt), or the other half's best inside it (v2)
         const bool doubt = live && (!finite || cnt > 1.5f || !(v1 - v2 > 2.0f * bandD) || best >= K);
-        const unsigned any = __ballot_sync(FULL_MASK, doubt);
-        if (any) {
-          // near-tie, duplicate centroids, NaN or overflow somewhere in this warp: those rows decide in the
-          // reference's arithmetic among the centroids inside the band (all of them when the estimate is unusable)
-          const float* xr = X + (size_t)(live ? row : 0) * d + (size_t)sub * TQ_SD;
-          const float* cg = centroids + (size_t)sub * K * TQ_SD;
-          const float lim = v1 - 4.0f * bandD;
-          double bestDist = __longlong_as_double(0x7ff0000000000000ll);
-          int ebest = 0;
-#pragma unroll 1
-          for (int h = 0; h < 8; h++) {
-            uint32_t w[32];
-            tc_ld32(taddr + (uint32_t)h * 32, w);  // warp-collective: every lane takes part
-            tc_wait_ld();
-            tc_pin32(w);
-            // columns of this load inside the band, as a bit mask (registers only, no indexed array)
-            uint32_t mask = 0u;
-#pragma unroll
-            for (int j = 0; j < 32; j++) {
-              const float Dj = __uint_as_float(w[j]);
-              mask |= (!finite || !(Dj < lim)) ? (1u << j) : 0u;  // NaN estimates are looked at
-            }
-            if (!doubt) mask = 0u;
-            while (mask) {  // ascending centroid index
-              const int j = __ffs(mask) - 1;
-              mask &= mask - 1;
-              const int ci = h * 32 + j;
-              if (ci >= K) break;
-              const double dd = ref_sum_thread<REF_L2SQ>(xr, cg + (size_t)ci * TQ_SD, TQ_SD, lanes);
-              if (dd < bestDist) {  // strict <: lowest ci wins ties, NaN never wins (PqEncoder.java:29)
-                bestDist = dd;
-                ebest = ci;
-              }
-            }
+        // Rows in doubt are NOT decided here.  Deciding them inline (re-reading the accumulator, gathering the row and the
+        // in-band centroids from global memory) made such a step ~8x as long as a normal one, and because the accumulator
+        // is released only when all four lane quarters are done, one doubtful quarter (29 % of the steps on uniform data)
+        // stalled the whole CTA pipeline: 37 % of the epilogue's stall samples sat on the wait for the next accumulator
+        // (profiles/r2_pq_tc_full.txt).  They are appended to a per-subspace-group list instead and decided by
+        // pq_tc_resolve_kernel right after this kernel; the code written below is provisional for them.
+        const unsigned dm = __ballot_sync(FULL_MASK, doubt);
+        if (dm) {
+          unsigned int base = 0;
+          if (lane == 0) base = atomicAdd(dcount + sg, (unsigned int)__popc(dm));
+          base = __shfl_sync(FULL_MASK, base, 0);
+          if (doubt) {
+            const unsigned int pos = base + (unsigned int)__popc(dm & ((1u << lane) - 1u));
+            if (pos < dcap) dlist[(size_t)sg * dcap + pos] = ((unsigned long long)row << 8) | (unsigned long long)sub;
+            // (beyond the capacity the count alone tells the resolver to decide every entry of this group)
           }
-          if (doubt) best = ebest;
         }
+        if (best >= K) best = 0;
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty + a);
@@ -421,6 +404,81 @@ pq_tc_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// Decides the entries pq_tc_assign_kernel left undecided, in the reference's arithmetic: fp32 distances to all K
+// centroids nominate, everything inside the rounding band of the best is evaluated like Distances.l2Squared and compared
+// with strict '<' in ascending index (the logic of pq_assign_kernel, pq.cu) -- independent of the tensor-core estimate.
+// grid.y = subspace group; the group's centroids sit in shared memory.  A list that overflowed its capacity (degenerate
+// data: everything in doubt) makes the group decide EVERY (row, subspace) of the slab.
+constexpr int TQ_RESOLVE_THREADS = 256;
+__global__ void __launch_bounds__(TQ_RESOLVE_THREADS)
+pq_tc_resolve_kernel(const float* __restrict__ X, int64_t n, int d, int M, int K, const float* __restrict__ centroids, int lanes,
+                     int64_t row0, int64_t nslab, const unsigned long long* __restrict__ dlist, const unsigned int* __restrict__ dcount,
+                     unsigned int dcap, uint8_t* __restrict__ codes_u8, int32_t* __restrict__ assign_i32) {
+  extern __shared__ __align__(16) float rcs[];  // [ns][K][8]
+  const int sg = blockIdx.y;
+  const unsigned int cnt = dcount[sg];
+  if (cnt == 0) return;
+  const int s_first = sg * TQ_SPC;
+  const int ns = min(TQ_SPC, M - s_first);
+  {
+    const float4* src = reinterpret_cast<const float4*>(centroids + (size_t)s_first * K * TQ_SD);
+    float4* dst = reinterpret_cast<float4*>(rcs);
+    for (int i = threadIdx.x; i < ns * K * TQ_SD / 4; i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  const bool all = cnt > dcap;
+  const int64_t items = all ? nslab * ns : (int64_t)cnt;
+  for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < items; it += (int64_t)gridDim.x * blockDim.x) {
+    int64_t row;
+    int sub;
+    if (all) {
+      row = row0 + it / ns;
+      sub = s_first + (int)(it % ns);
+    } else {
+      const unsigned long long e = dlist[(size_t)sg * dcap + it];
+      row = (int64_t)(e >> 8);
+      sub = (int)(e & 255u);
+    }
+    const float* xr = X + (size_t)row * d + (size_t)sub * TQ_SD;
+    float x[TQ_SD];
+    {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(xr)), b = __ldg(reinterpret_cast<const float4*>(xr) + 1);
+      x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+    }
+    const float* c0 = rcs + (size_t)(sub - s_first) * K * TQ_SD;
+    auto est = [&](int ci) {
+      const float4* c = reinterpret_cast<const float4*>(c0 + (size_t)ci * TQ_SD);
+      const float4 u = c[0], w = c[1];
+      float e0 = 0.0f, e1 = 0.0f;
+      const float t0 = x[0] - u.x, t1 = x[1] - u.y, t2 = x[2] - u.z, t3 = x[3] - u.w;
+      const float t4 = x[4] - w.x, t5 = x[5] - w.y, t6 = x[6] - w.z, t7 = x[7] - w.w;
+      e0 = fmaf(t0, t0, e0); e1 = fmaf(t1, t1, e1); e0 = fmaf(t2, t2, e0); e1 = fmaf(t3, t3, e1);
+      e0 = fmaf(t4, t4, e0); e1 = fmaf(t5, t5, e1); e0 = fmaf(t6, t6, e0); e1 = fmaf(t7, t7, e1);
+      return e0 + e1;
+    };
+    float m1 = __int_as_float(0x7f800000);
+    for (int ci = 0; ci < K; ci++) m1 = fminf(m1, est(ci));  // NaN estimates are ignored by fminf
+    const bool finite = m1 < __int_as_float(0x7f800000);
+    // |estimate - reference| <= (2 SD + 24) 2^-24 relative on both sides; 3x slack (pq_band in pq.cu)
+    const float lim = finite ? m1 * (1.0f + 3.0f * (float)(2 * TQ_SD + 24) * (1.0f / 16777216.0f)) + 1e-30f : __int_as_float(0x7f800000);
+    const float* cg = centroids + (size_t)sub * K * TQ_SD;
+    double bestDist = __longlong_as_double(0x7ff0000000000000ll);
+    int best = 0;
+    for (int ci = 0; ci < K; ci++) {
+      const float e = est(ci);
+      if (finite && !(e <= lim)) continue;  // outside the band (a NaN estimate with a finite best cannot be the argmin:
+                                            //  its exact distance is NaN as well, and NaN never wins)
+      const double dd = ref_sum_thread<REF_L2SQ>(xr, cg + (size_t)ci * TQ_SD, TQ_SD, lanes);
+      if (dd < bestDist) {  // strict <: lowest ci wins ties, NaN never wins (PqEncoder.java:29)
+        bestDist = dd;
+        best = ci;
+      }
+    }
+    if (codes_u8) codes_u8[(size_t)row * M + sub] = (uint8_t)(best & 0xFF);
+    if (assign_i32) assign_i32[(size_t)sub * n + row] = best;
   }
 }
 
@@ -577,6 +635,21 @@ cudaError_t launch_pq_assign_tc(const PqAssignLaunch& L, int sms, cudaStream_t s
     if ((e = stats.alloc(sizeof(TqStats), pool, st)) != cudaSuccess) return e;
     p_xop[0] = xop.p; p_xop[1] = xop2.p ? xop2.p : xop.p; p_cop = cop.p; p_stats = stats.p;
   }
+  // undecided entries of one slab: per subspace group a list of (row, subspace); room for one entry in eight
+  PoolMem dl, dc;
+  const unsigned int dcap = (unsigned int)std::max<int64_t>(4096, std::min<int64_t>(slab, L.n) * TQ_SPC / 8);
+  {
+    cudaMemPool_t pool;
+    if ((e = tq_pool(&pool)) != cudaSuccess) return e;
+    if ((e = dl.alloc((size_t)nsg * dcap * 8, pool, st)) != cudaSuccess) return e;
+    if ((e = dc.alloc((size_t)nsg * 4, pool, st)) != cudaSuccess) return e;
+  }
+  unsigned long long* d_list = static_cast<unsigned long long*>(dl.p);
+  unsigned int* d_cnt = static_cast<unsigned int*>(dc.p);
+  const size_t resolve_smem = (size_t)TQ_SPC * L.K * TQ_SD * 4;
+  if (resolve_smem > 48 * 1024 &&
+      (e = cudaFuncSetAttribute(pq_tc_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)resolve_smem)) != cudaSuccess)
+    return e;
   TqStats* d_st = static_cast<TqStats*>(p_stats);
   if (reuse) {
     // same rows, new centroids: the scale stays (centroids of a training run are means of the rows), the
@@ -632,11 +705,16 @@ cudaError_t launch_pq_assign_tc(const PqAssignLaunch& L, int sms, cudaStream_t s
     int nsplit = sms / nsg;
     if (nsplit < 1) nsplit = 1;
     if (nsplit > tiles) nsplit = (int)tiles;
+    if ((e = cudaMemsetAsync(d_cnt, 0, (size_t)nsg * 4, st)) != cudaSuccess) return e;
     count_launch();
     pq_tc_assign_kernel<<<nsg * nsplit, TQ_THREADS, TQ_SMEM, st>>>(tmA, tmB, L.X, L.n, L.d, M, L.K, L.centroids, L.lanes, d_st, r0,
-                                                                   cnt, nsg, tiles, L.codes_u8, L.assign_i32);
+                                                                   cnt, nsg, tiles, L.codes_u8, L.assign_i32, d_list, d_cnt, dcap);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    if (piped && (e = cudaEventRecord(done[b].e, st)) != cudaSuccess) return e;
+    if (piped && (e = cudaEventRecord(done[b].e, st)) != cudaSuccess) return e;  // (the resolver does not read the image)
+    count_launch();
+    pq_tc_resolve_kernel<<<dim3((unsigned)std::max(1, sms / nsg) * 2, nsg), TQ_RESOLVE_THREADS, resolve_smem, st>>>(
+        L.X, L.n, L.d, M, L.K, L.centroids, L.lanes, r0, cnt, d_list, d_cnt, dcap, L.codes_u8, L.assign_i32);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
   if (reuse) return cudaSuccess;  // everything this call touched lives until the scope ends
   if (sc.open && whole) {         // first call of a scope and the whole image fits: keep it
