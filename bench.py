@@ -410,7 +410,7 @@ def run_ours(args) -> None:
         extra["c4"] = bench_c4(ctx, min(K, 50), W)
 
     if rank == 0:
-        traffic, traffic_src = profiled_traffic("r2_c2_scan_full.txt", "r1_c2_scan_full.txt")
+        traffic, traffic_src = profiled_traffic("r2_c2_scan_full.txt", "r1/r1_c2_scan_full.txt")
         line = {
             "metric": METRIC, "value": value, "unit": "distance-evals/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True,

@@ -133,6 +133,34 @@ def test_bruteforce_ties_nan_skip(vs, oracle, metric):
     _check_bruteforce(vs, oracle, rows, np.zeros(32, np.float32), 5, metric)  # zero query
 
 
+@pytest.mark.parametrize("d,lanes", [(100, 16), (20, 8), (70, 16), (6, 4)])
+def test_bruteforce_nan_only_in_the_fp64_tail(vs, oracle, d, lanes):
+    """with d % lanes != 0 the L2 pre-filter sees the fp32 lane part over [0, ub) only; a row whose ONLY NaN
+    sits in the fp64 tail [ub, d) must still surface (its score is NaN, which Double.compare sorts first)."""
+    vs.set_simd_lanes(lanes)
+    oracle.set_lanes(lanes)
+    try:
+        n = 30_000
+        rows = oracle.gen_rows(42, 0, n, d)
+        ub = d - d % lanes
+        rows[17_000, ub:] = np.nan               # the whole tail
+        rows[25_001, d - 1] = np.nan             # its last element only
+        rows[29_999, ub] = np.inf                # an infinite distance is NOT NaN: it sorts last, not first
+        q = oracle.gen_floats(43, 0, d)
+        seg = vs.Segment.upload(rows)
+        try:
+            for k in (1, 10, 40):
+                ids, sc = seg.bruteforce_topk(q, k)
+                oi, os_, _ = oracle.bruteforce_topk(rows, q, k)
+                assert np.array_equal(ids, oi) and _same(sc, os_), (k, ids[:4], oi[:4])
+            assert set(seg.bruteforce_topk(q, 2)[0].tolist()) == {17_000, 25_001}
+        finally:
+            seg.free()
+    finally:
+        vs.set_simd_lanes(16)
+        oracle.set_lanes(16)
+
+
 def test_bruteforce_query_batch(vs, oracle):
     rows = oracle.gen_rows(42, 0, 8000, 128)
     qs = oracle.gen_rows(43, 0, 5, 128)

@@ -218,6 +218,8 @@ scan_tma_kernel(const float* __restrict__ X, int64_t n, int d, const float* __re
           est = s[u];
         }
         bool cand = (t == TPR - 1) && row < n && !(est > fthr);
+        if (!COSINE && ub < d && (t == TPR - 1) && row < n && !cand)  // a NaN in the fp64 tail only (scan_rows.cuh)
+          cand = scan_tail_has_nan(reinterpret_cast<const float*>(sp + (size_t)(r0 + u * G + g) * row_bytes), ub, d);
         Key key = key_empty();
         if (cand) {
           if (skip != nullptr && skip[row]) {

@@ -44,6 +44,19 @@ static __device__ __noinline__ Key scan_exact_key(const float* __restrict__ q, c
 }
 
 
+// L2 with d % lanes != 0: the pre-filter compares the fp32 lane part over [0, ub) only.  A row whose ONLY NaN sits in the
+// fp64 tail [ub, d) has a finite lane sum and would be dropped once a threshold exists, while the reference scores it
+// NaN -- which Double.compare sorts FIRST in descending score order (J/fdb/FdbVectorIndex.java:708).  Rows the filter
+// rejects therefore get their (at most lanes - 1) tail elements checked for NaN before they are discarded.
+static __device__ __forceinline__ bool scan_tail_has_nan(const float* __restrict__ xr, int ub, int d) {
+  bool nan = false;
+  for (int i = ub; i < d; i++) {
+    const float v = xr[i];
+    nan |= v != v;
+  }
+  return nan;
+}
+
 // One batch = (32/TPR) * U consecutive rows starting at row_base, register-staged 128-bit streaming
 // loads.  All 32 lanes must call.  qs = the query in shared memory, q = the same query in global memory.
 template <int TPR, int U, bool COSINE, class TK>
@@ -147,6 +160,7 @@ __device__ __forceinline__ void scan_batch_ldg(const float* __restrict__ X, int6
         est = s[u];
       }
       bool cand = (t == TPR - 1) && row < n && !(est > fthr);
+      if (!COSINE && ub < d && (t == TPR - 1) && row < n && !cand) cand = scan_tail_has_nan(X + (size_t)row * d, ub, d);
       Key key = key_empty();
       if (cand) {
         if (skip != nullptr && skip[row]) {
