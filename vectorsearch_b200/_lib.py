@@ -66,10 +66,10 @@ SIGNATURES = {
     "vs_adc_query_gather": (i32, [u64, i64p, i64, f64p, u8p]),
     "vs_adc_query_end": (i32, [u64]),
     "vs_adc_gather": (i32, [u64, f32p, i64p, i64, f64p, u8p]),
-    "vs_bruteforce_topk": (i32, [u64, f32p, i32, i32, i32, i64p, f64p, i32p]),
+    "vs_bruteforce_topk": (i32, [u64, vp, i32, i32, i32, vp, vp, vp]),  # (addresses: the hot calls pass plain integers)
     "vs_adc_topk": (i32, [u64, f32p, i32, i32, i64p, f64p, i32p]),
     "vs_rerank_topk": (i32, [u64, f32p, i64p, i32, i32, i32, i32, i64p, f64p, i32p]),
-    "vs_adc_rerank_topk": (i32, [u64, f32p, i32, i32, i32, i32, i32, i64p, f64p, i32p]),
+    "vs_adc_rerank_topk": (i32, [u64, vp, i32, i32, i32, i32, i32, vp, vp, vp]),
     "vs_merge_topk": (i32, [i64p, f64p, i64, i32, i64p, f64p, i32p]),
     "vs_knn_graph": (i32, [u64, i32, i32, C.c_double, i32p, i32p]),
     "vs_pq_train": (i32, [f32p, u64, i64, i32, i32, i32, i32, i64, f32p]),
@@ -93,8 +93,8 @@ SIGNATURES = {
     "vs_peer_release_stream": (i32, [u64, vp]),
     "vs_peer_destroy": (i32, [u64]),
     "vs_exchange_merge_packed_dev": (i32, [u64, vp, i32, i32, i32, vp, vp, vp, vp]),
-    "vs_bruteforce_topk_exchange": (i32, [u64, u64, f32p, i32, i32, i32, i64p, f64p, i32p]),
-    "vs_adc_rerank_topk_exchange": (i32, [u64, u64, f32p, i32, i32, i32, i32, i32, i64p, f64p, i32p]),
+    "vs_bruteforce_topk_exchange": (i32, [u64, u64, vp, i32, i32, i32, vp, vp, vp]),
+    "vs_adc_rerank_topk_exchange": (i32, [u64, u64, vp, i32, i32, i32, i32, i32, vp, vp, vp]),
     "vs_exchange_merge_adc_rerank_packed_dev": (i32, [u64, vp, i32, i32, i32, vp, vp, vp, vp]),
     "vs_bruteforce_topk_exchange_dev": (i32, [u64, u64, vp, i32, i32, i32, vp, vp, vp, vp]),
     "vs_adc_rerank_topk_exchange_dev": (i32, [u64, u64, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp]),

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <climits>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -1379,13 +1380,14 @@ int32_t vs_bruteforce_topk(uint64_t h, const float* q, int32_t nq, int32_t k, in
       // short result lists: the last CTA writes ids / scores / counts straight into the pinned staging buffer
       // (device-visible under UVA) -- three device-to-host copies less on the latency path of a query
       RET(bruteforce_dev(c, c->stream, s, dq, g, k, metric, hids, hsc, hcn, dpart, c->d_ticket, p));
+      CK(cudaStreamSynchronize(c->stream), "sync");
     } else {
       RET(bruteforce_dev(c, c->stream, s, dq, g, k, metric, dids, dsc, dcn, dpart, c->d_ticket, p));
       CK(cudaMemcpyAsync(hids, dids, (size_t)g * k * 8, cudaMemcpyDeviceToHost, c->stream), "D2H ids");
       CK(cudaMemcpyAsync(hsc, dsc, (size_t)g * k * 8, cudaMemcpyDeviceToHost, c->stream), "D2H scores");
       CK(cudaMemcpyAsync(hcn, dcn, (size_t)g * 4, cudaMemcpyDeviceToHost, c->stream), "D2H counts");
+      CK(cudaStreamSynchronize(c->stream), "sync");
     }
-    CK(cudaStreamSynchronize(c->stream), "sync");
     memcpy(ids_out + (size_t)q0 * k, hids, (size_t)g * k * 8);
     memcpy(scores_out + (size_t)q0 * k, hsc, (size_t)g * k * 8);
     if (counts_out) memcpy(counts_out + q0, hcn, (size_t)g * 4);

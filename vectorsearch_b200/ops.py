@@ -2,6 +2,7 @@
 from __future__ import annotations
 
 import ctypes as C
+import threading
 
 import numpy as np
 
@@ -13,6 +14,45 @@ _initialised = False
 
 def _f32(a) -> np.ndarray:
     return np.ascontiguousarray(a, dtype=np.float32)
+
+
+# Result buffers of the query calls, one set per (thread, shape): numpy's ctypes accessors cost several microseconds per
+# array and per call -- 21 us of wrapper around an 80 us query -- so the hot calls keep their output arrays and the raw
+# addresses, pass plain integers through ctypes, and hand COPIES of the filled part back.
+_tls = threading.local()
+
+
+def _out_buffers(nq: int, k: int):
+    cache = getattr(_tls, "out", None)
+    if cache is None:
+        cache = _tls.out = {}
+    b = cache.get((nq, k))
+    if b is None:
+        if len(cache) > 64:
+            cache.clear()
+        ids = np.zeros((nq, k), dtype=np.int64)
+        sc = np.zeros((nq, k), dtype=np.float64)
+        cn = np.zeros(nq, dtype=np.int32)
+        b = cache[(nq, k)] = (ids, sc, cn, ids.ctypes.data, sc.ctypes.data, cn.ctypes.data)
+    return b
+
+
+def _query_ptr(q, d: int):
+    """-> (array kept alive, address, nq, single) for a query [d] or a batch [nq][d]."""
+    if type(q) is not np.ndarray or q.dtype != np.float32 or not q.flags.c_contiguous:
+        q = np.ascontiguousarray(q, dtype=np.float32)
+    single = q.ndim == 1
+    if (q.shape[0] if single else q.shape[-1]) != d or q.ndim > 2:
+        raise ValueError("query dimension does not match the segment")
+    return q, q.__array_interface__["data"][0], (1 if single else q.shape[0]), single
+
+
+def _results(b, nq: int, single: bool):
+    ids, sc, cn = b[0], b[1], b[2]
+    if single:
+        c = int(cn[0])
+        return ids[0, :c].copy(), sc[0, :c].copy()
+    return ids.copy(), sc.copy(), cn.copy()
 
 
 def _p(a: np.ndarray, t):
@@ -346,15 +386,10 @@ class Segment:
     def bruteforce_topk(self, q, k: int, metric: int = METRIC_L2):
         """searchBruteForceSegment scoring + sort + subList (:676-721).  q [d] -> (ids, scores);
         q [nq][d] -> (ids [nq][k], scores [nq][k], counts [nq]); score = -l2 or cosine similarity."""
-        single = np.ndim(q) == 1
-        q = self._queries(q, self.d)
-        nq = q.shape[0]
-        ids = np.zeros((nq, k), dtype=np.int64)
-        sc = np.zeros((nq, k), dtype=np.float64)
-        cn = np.zeros(nq, dtype=np.int32)
-        check(L.load().vs_bruteforce_topk(self.handle, _p(q, L.f32p), nq, k, metric, _p(ids, L.i64p),
-                                          _p(sc, L.f64p), _p(cn, L.i32p)))
-        return self._trim(ids, sc, cn, single)
+        q, qp, nq, single = _query_ptr(q, self.d)
+        b = _out_buffers(nq, k)
+        check(L.load().vs_bruteforce_topk(self.handle, qp, nq, k, metric, b[3], b[4], b[5]))
+        return _results(b, nq, single)
 
     def adc_topk(self, q, n_cand: int):
         """buildLut + ADC scan + ascending stable sort + first n_cand (:741,:754-769,:820-822)."""
@@ -382,17 +417,10 @@ class Segment:
 
     def adc_rerank_topk(self, q, n_cand: int, k: int, metric: int = METRIC_L2, normalize_on_read: bool = False):
         """ADC top n_cand followed by exact re-rank to k in one call (config C4)."""
-        single = np.ndim(q) == 1
-        q = self._queries(q, self.d)
-        nq = q.shape[0]
-        ids = np.zeros((nq, k), dtype=np.int64)
-        sc = np.zeros((nq, k), dtype=np.float64)
-        cn = np.zeros(nq, dtype=np.int32)
-        check(L.load().vs_adc_rerank_topk(self.handle, _p(q, L.f32p), nq, n_cand, k, metric,
-                                          int(bool(normalize_on_read)), _p(ids, L.i64p), _p(sc, L.f64p),
-                                          _p(cn, L.i32p)))
-        return self._trim(ids, sc, cn, single)
-
+        q, qp, nq, single = _query_ptr(q, self.d)
+        b = _out_buffers(nq, k)
+        check(L.load().vs_adc_rerank_topk(self.handle, qp, nq, n_cand, k, metric, 1 if normalize_on_read else 0, b[3], b[4], b[5]))
+        return _results(b, nq, single)
 
     # -- graph construction ----------------------------------------------------------------------------
     def knn_graph(self, degree: int, l_build: int = 0, alpha: float = 1.0):

@@ -277,12 +277,12 @@ class ShardedSegment:
         q2 = q.reshape(1, -1) if single else q
         nq = q2.shape[0]
         if self._comm is not None and nq * 4 * n_cand * 8 <= self.PEER_SLOT_BYTES:
-            ids = np.zeros((nq, k), dtype=np.int64)
-            sc = np.zeros((nq, k), dtype=np.float64)
-            cn = np.zeros(nq, dtype=np.int32)
-            check(self.lib.vs_adc_rerank_topk_exchange(
-                self.seg.handle, self._comm, q2.ctypes.data_as(L.f32p), nq, n_cand, k, metric, 0,
-                ids.ctypes.data_as(L.i64p), sc.ctypes.data_as(L.f64p), cn.ctypes.data_as(L.i32p)))
+            from .ops import _out_buffers, _results
+
+            b = _out_buffers(nq, k)
+            check(self.lib.vs_adc_rerank_topk_exchange(self.seg.handle, self._comm, q2.__array_interface__["data"][0], nq, n_cand, k,
+                                                       metric, 0, b[3], b[4], b[5]))
+            return _results(b, nq, single)
         else:
             d_q = self.torch.from_numpy(q2).to(self.dev)
             ids, sc, cn = self.adc_rerank_topk_dev(d_q, nq, n_cand, k, metric)
@@ -361,15 +361,12 @@ class ShardedSegment:
         nq = q2.shape[0]
         if self._comm is not None and nq * 2 * k * 8 <= self.PEER_SLOT_BYTES:
             # one C call: pinned staging, scan, peer exchange, merge writing host memory, one synchronisation
-            ids = np.zeros((nq, k), dtype=np.int64)
-            sc = np.zeros((nq, k), dtype=np.float64)
-            cn = np.zeros(nq, dtype=np.int32)
-            check(self.lib.vs_bruteforce_topk_exchange(
-                self.seg.handle, self._comm, q2.ctypes.data_as(L.f32p), nq, k, metric, ids.ctypes.data_as(L.i64p),
-                sc.ctypes.data_as(L.f64p), cn.ctypes.data_as(L.i32p)))
-            if single:
-                return ids[0, :cn[0]], sc[0, :cn[0]]
-            return ids, sc, cn
+            from .ops import _out_buffers, _results
+
+            b = _out_buffers(nq, k)
+            check(self.lib.vs_bruteforce_topk_exchange(self.seg.handle, self._comm, q2.__array_interface__["data"][0], nq, k, metric,
+                                                       b[3], b[4], b[5]))
+            return _results(b, nq, single)
         h = self._host_buffers(nq, k, q2.shape[1])
         h["q_np"][...] = q2
         h["dq"].copy_(h["q"], non_blocking=True)
