@@ -15,6 +15,8 @@ if os.environ.get("VS_TF32"):
     vs.set_option("batch_fp16", 0)
 if os.environ.get("VS_PAIRS"):
     vs.set_option("batch_pairs", int(os.environ["VS_PAIRS"]))
+if os.environ.get("VS_WARPQ"):
+    vs.set_option("batch_warp_min_queries", int(os.environ["VS_WARPQ"]))
 if os.environ.get("VS_GROUP"):
     vs.set_option("batch_group", int(os.environ["VS_GROUP"]))
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
