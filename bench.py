@@ -437,6 +437,9 @@ def run_ours(args) -> None:
                    max_over_ranks=max_over_ranks, hbm_peak=hbm_peak, check=not args.no_check, n_slots=n_slots)
         extra["c3"] = bench_c3(ctx)
         extra["c4"] = bench_c4(ctx, min(K, 50), W)
+        extra["c5"] = bench_c5(ctx, min(K, 10), W)
+        if world == 1 and not args.no_cpu:
+            extra["c1"] = bench_c1(ctx)
 
     if rank == 0:
         traffic, traffic_src = profiled_traffic("r2_c2_scan_full.txt", "r1/r1_c2_scan_full.txt")
@@ -728,6 +731,126 @@ def bench_c4(ctx, K, W):
         out["parity_checked"] = check_c4(ctx, seg, cent, lo, n, qh[W + K - 1], res)
     seg.free()
     sh.close()
+    return out
+
+
+def bench_c5(ctx, K, W):
+    """C5: cosine brute-force top-50, query batch 256, 768-d rows sharded by range.  BASELINE's shape is 50M x 768 over 8
+    GPUs = 6.25M rows (19.2 GB) per GPU; every N runs THAT per-GPU shape (N x 6.25M rows in total: the 153.6 GB corpus does
+    not fit fewer than 8 GPUs next to its fp16 operand copy), so the 8-GPU line is C5 itself."""
+    import numpy as np
+
+    from vectorsearch_b200.sharded import ShardedSegment
+
+    vs, torch, dev, rank, world = ctx["vs"], ctx["torch"], ctx["dev"], ctx["rank"], ctx["world"]
+    n, d, nq, k = int(os.environ.get("VS_C5_ROWS", 6_250_000)), 768, 256, 50
+    seg = vs.Segment.generate(CORPUS_SEED, rank * n, n, d, id_base=rank * n)
+    sh = ShardedSegment(seg, rank, world, slots=1)
+    qseg = vs.Segment.generate(QUERY_SEED, 0, nq, d)
+    qn = qseg.rows()
+    qseg.free()
+    q_dev = torch.from_numpy(qn).to(dev)
+    stream = torch.cuda.current_stream()
+    for _ in range(max(3, min(W, 3))):  # the first call also builds the nomination state (row norms, fp16 copy)
+        ids, sc, cn = sh.bruteforce_topk_dev(q_dev, nq, k, 1)
+    torch.cuda.synchronize()
+    ctx["barrier"]()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(K):
+        ids, sc, cn = sh.bruteforce_topk_dev(q_dev, nq, k, 1)
+    e1.record(stream)
+    ctx["barrier"]()
+    ms = ctx["max_over_ranks"](e0.elapsed_time(e1)) / K
+    for _ in range(2):
+        res = sh.bruteforce_topk(qn, k, 1) if world > 1 else seg.bruteforce_topk(qn, k, 1)
+    ctx["barrier"]()
+    t0 = time.perf_counter()
+    for _ in range(max(2, K // 2)):
+        res = sh.bruteforce_topk(qn, k, 1) if world > 1 else seg.bruteforce_topk(qn, k, 1)
+    ctx["barrier"]()
+    e2e_ms = ctx["max_over_ranks"](time.perf_counter() - t0) / max(2, K // 2) * 1e3
+    tpeak, tsrc = measured_tensor_peak()
+    flops = 2.0 * n * d * nq  # per GPU
+    tf = flops / (ms * 1e-3) / 1e12
+    out = {"workload": f"C5: cosine brute-force top-{k}, query batch {nq}, {world} x {n}x{d} fp32 rows ({world} GPU(s), rows sharded by range)",
+           "rows_per_gpu": n, "rows_total": n * world, "ms_per_batch": ms, "qps": nq / (ms * 1e-3),
+           "distance_evals_per_s": float(n) * world * nq / (ms * 1e-3),
+           "e2e": {"ms_per_batch": e2e_ms, "qps": nq / (e2e_ms * 1e-3), "h2d_bytes_per_step": nq * d * 4, "d2h_bytes_per_step": nq * (k * 16 + 4)},
+           "roofline": {"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak, "peak_source": tsrc,
+                        "algorithmic_flops_per_batch_per_gpu": flops,
+                        "hbm_view": {"algorithmic_bytes_per_batch_per_gpu": n * d * 4, "achieved_GBs": n * d * 4 / (ms * 1e-3) / 1e9,
+                                     "frac_of_measured_peak": n * d * 4 / (ms * 1e-3) / 1e9 / ctx["hbm_peak"]},
+                        "kernel": "batch_gemm_kernel<streaming operands, HALF, COSINE> (K2) + batch_select + exchange; per GPU", "traffic": None}}
+    if ctx["check"]:
+        # parity: query 0 of the batch against the oracle over ALL shards' rows -- every rank scans its own rows (regenerated
+        # slab by slab), rank 0 merges the per-rank lists like the reference merges segments
+        from oracle import pyoracle
+
+        orc = pyoracle.get()
+        thr = max(1, host_threads() // world)
+        oi, os_ = [], []
+        for r0 in range(0, n, 500_000):
+            cnt = min(500_000, n - r0)
+            rows = orc.gen_rows(CORPUS_SEED, rank * n + r0, cnt, d)
+            i_, s_, _ = orc.bruteforce_topk(rows, qn[0], k, 1, threads=thr)
+            oi.append(i_ + rank * n + r0)
+            os_.append(s_)
+        li, ls = orc.merge_topk(np.concatenate(oi), np.concatenate(os_), k)
+        pack = np.zeros((2, k), np.int64)
+        pack[0], pack[1] = li, ls.view(np.int64)
+        if world > 1:
+            t = torch.from_numpy(pack).to(dev)
+            g = torch.empty((world, 2, k), dtype=torch.int64, device=dev)
+            ctx["dist"].all_gather_into_tensor(g.view(-1), t.view(-1))
+            g = g.cpu().numpy()
+        else:
+            g = pack[None]
+        if rank == 0:
+            wi, ws = orc.merge_topk(g[:, 0].ravel(), g[:, 1].ravel().view(np.float64), k)
+            gi, gs = np.asarray(res[0])[0], np.asarray(res[1])[0]
+            if not (np.array_equal(gi, wi) and np.array_equal(gs.view(np.uint64), ws.view(np.uint64))):
+                raise SystemExit(f"PARITY FAILURE (C5, {world} GPUs): got {gi.tolist()}, oracle {wi.tolist()}")
+            out["parity_checked"] = "cosine top-50 of query 0 equals the oracle's over all shards' rows"
+    seg.free()
+    sh.close()
+    return out
+
+
+def bench_c1(ctx):
+    """C1: the DistanceAndPqBenchmark shapes (JMH, single thread, Random(42) inputs).  The CPU column is the oracle port in a
+    C loop (ns per call, the unit JMH reports); the GPU column is one C-ABI call per operation -- a kernel launch each,
+    which is why the throughput path is the segment API and not these pair operations."""
+    import numpy as np
+
+    from oracle import pyoracle
+
+    vs = ctx["vs"]
+    orc, kind = _native_oracle()
+    out = {"workload": "C1: DistanceAndPqBenchmark shapes: l2 / cosine dim 128 and 768, pqEncode M=16 K=256 dim=128, pqLutDistance M=16",
+           "cpu": {"kind": f"oracle port, C loop, one thread ({kind})", "unit": "ns/op"}, "gpu": {"unit": "us/call through the C ABI (one launch each)"}}
+    for dim in (128, 768):
+        a, b = orc.gen_floats(42, 0, dim), orc.gen_floats(42, dim, dim)  # DistanceState: a then b from Random(42)
+        out["cpu"][f"l2_{dim}"] = orc.bench_ns_per_op(0, a, b, iters=300_000)
+        out["cpu"][f"cosine_{dim}"] = orc.bench_ns_per_op(1, a, b, iters=300_000)
+        for name, fn in (("l2", vs.Distances.l2), ("cosine", vs.Distances.cosine)):
+            fn(a, b)
+            t0 = time.perf_counter()
+            for _ in range(200):
+                fn(a, b)
+            out["gpu"][f"{name}_{dim}"] = (time.perf_counter() - t0) / 200 * 1e6
+    cent = orc.gen_floats(42, 0, PQ_M * PQ_K * 8, 1).reshape(PQ_M, PQ_K, 8)   # PqState: centroids nextFloat()
+    v = orc.gen_floats(42, PQ_M * PQ_K * 8, DIM)
+    lut = orc.gen_floats(42, PQ_M * PQ_K * 8 + DIM, PQ_M * PQ_K, 2).reshape(PQ_M, PQ_K)
+    codes = orc.gen_codes(42, PQ_M * PQ_K * 8 + DIM + PQ_M * PQ_K, PQ_M)
+    out["cpu"]["pqEncode"] = orc.bench_ns_per_op(2, v, centroids=cent, iters=20_000)
+    out["cpu"]["pqLutDistance"] = orc.bench_ns_per_op(3, centroids=cent, lut=lut, codes=codes, iters=2_000_000)
+    vs.PqEncoder.encode(cent, v)
+    t0 = time.perf_counter()
+    for _ in range(100):
+        vs.PqEncoder.encode(cent, v)
+    out["gpu"]["pqEncode"] = (time.perf_counter() - t0) / 100 * 1e6
+    assert np.array_equal(vs.PqEncoder.encode(cent, v), orc.pq_encode(cent, v))
     return out
 
 

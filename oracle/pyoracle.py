@@ -47,6 +47,7 @@ def _load(native: bool) -> C.CDLL:
     lib.vso_cosine.restype = C.c_double
     lib.vso_pq_approx_distance.restype = C.c_double
     lib.vso_jr_next_float.restype = C.c_float
+    lib.vso_bench_ns_per_op.restype = C.c_double
     for fn in ("vso_adc_topn", "vso_bruteforce_topk", "vso_rerank_topk", "vso_merge_topk"):
         getattr(lib, fn).restype = C.c_int64
     return lib
@@ -261,6 +262,17 @@ class Oracle:
         self.lib.vso_knn_graph(_p(rows, _f32p), C.c_int64(n), d, degree, l_build, C.c_double(alpha),
                                out.ctypes.data_as(C.POINTER(C.c_int32)), cn.ctypes.data_as(C.POINTER(C.c_int32)), C.c_int(threads))
         return [out[i, :cn[i]] for i in range(n)]
+
+    # -- JMH-like timing (config C1) ------------------------------------------------------
+    def bench_ns_per_op(self, kind: int, a=None, b=None, centroids=None, lut=None, codes=None, iters: int = 100000) -> float:
+        a = _f32(a) if a is not None else np.zeros(1, np.float32)
+        b = _f32(b) if b is not None else a
+        c = _f32(centroids) if centroids is not None else np.zeros((1, 1, 1), np.float32)
+        M, K, sub = c.shape
+        lt = _f32(lut) if lut is not None else np.zeros((M, K), np.float32)
+        cd = np.ascontiguousarray(codes, dtype=np.uint8) if codes is not None else np.zeros(M, np.uint8)
+        return float(self.lib.vso_bench_ns_per_op(kind, _p(a, _f32p), _p(b, _f32p), C.c_int(a.size), _p(c, _f32p), M, K, sub,
+                                                  _p(lt, _f32p), _p(cd, _u8p), C.c_int64(iters)))
 
     # -- FloatPacker -------------------------------------------------------------------
     def floats_to_bytes(self, arr) -> bytes:

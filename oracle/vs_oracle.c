@@ -761,3 +761,37 @@ void vso_gen_codes(int64_t seed, int64_t first, int64_t count, uint8_t* out) {
   vso_jr_skip(&r, (uint64_t)first);
   for (int64_t i = 0; i < count; i++) out[i] = (uint8_t)vso_jr_next_int_bound(&r, 256);
 }
+
+
+/* ========================================================================== */
+/* JMH-like timing of the DistanceAndPqBenchmark bodies (config C1): the        */
+/* benchmark method is called `iters` times in a C loop (B/DistanceAndPqBenchmark.java:95-123); */
+/* returns nanoseconds per call.  kind 0: l2, 1: cosine, 2: pqEncode, 3: pqLutDistance (float LUT). */
+/* ========================================================================== */
+#include <time.h>
+double vso_bench_ns_per_op(int kind, const float* a, const float* b, int len, const float* centroids,
+                           int M, int K, int subDim, const float* lut, const uint8_t* codes, int64_t iters) {
+  volatile double sink = 0.0;
+  uint8_t out[256];
+  struct timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  for (int64_t i = 0; i < iters; i++) {
+    switch (kind) {
+      case 0: sink += vso_l2(a, b, len); break;
+      case 1: sink += vso_cosine(a, b, len); break;
+      case 2:
+        vso_pq_encode(centroids, M, K, subDim, a, out);
+        sink += out[0];
+        break;
+      default: {
+        float dist = 0.0f; /* :117-122 */
+        for (int m = 0; m < M; m++) dist += lut[(size_t)m * K + (codes[m] & 0xFF)];
+        sink += dist;
+      }
+    }
+    __asm__ volatile("" ::: "memory");
+  }
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  (void)sink;
+  return ((double)(t1.tv_sec - t0.tv_sec) * 1e9 + (double)(t1.tv_nsec - t0.tv_nsec)) / (double)(iters > 0 ? iters : 1);
+}

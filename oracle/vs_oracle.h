@@ -124,6 +124,10 @@ void vso_gen_floats(int64_t seed, int64_t first, int64_t count, int kind, float*
 /* code byte e = (byte) nextInt(256) of draw e  (:86-89) */
 void vso_gen_codes(int64_t seed, int64_t first, int64_t count, uint8_t* out);
 
+/* JMH-like ns/op of the DistanceAndPqBenchmark bodies (config C1), kind 0 l2, 1 cosine, 2 pqEncode, 3 pqLutDistance */
+double vso_bench_ns_per_op(int kind, const float* a, const float* b, int len, const float* centroids,
+                           int M, int K, int subDim, const float* lut, const uint8_t* codes, int64_t iters);
+
 #ifdef __cplusplus
 }
 #endif
