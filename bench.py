@@ -771,6 +771,7 @@ def bench_c5(ctx, K, W):
     ctx["barrier"]()
     e2e_ms = ctx["max_over_ranks"](time.perf_counter() - t0) / max(2, K // 2) * 1e3
     tpeak, tsrc = measured_tensor_peak()
+    traffic, traffic_src = profiled_traffic("r2_c5_gemm_pair_full.txt")
     flops = 2.0 * n * d * nq  # per GPU
     tf = flops / (ms * 1e-3) / 1e12
     out = {"workload": f"C5: cosine brute-force top-{k}, query batch {nq}, {world} x {n}x{d} fp32 rows ({world} GPU(s), rows sharded by range)",
@@ -781,7 +782,11 @@ def bench_c5(ctx, K, W):
                         "algorithmic_flops_per_batch_per_gpu": flops,
                         "hbm_view": {"algorithmic_bytes_per_batch_per_gpu": n * d * 4, "achieved_GBs": n * d * 4 / (ms * 1e-3) / 1e9,
                                      "frac_of_measured_peak": n * d * 4 / (ms * 1e-3) / 1e9 / ctx["hbm_peak"]},
-                        "kernel": "batch_gemm_kernel<streaming operands, HALF, COSINE> (K2) + batch_select + exchange; per GPU", "traffic": None}}
+                        "kernel": "batch_gemm_pair_kernel<streaming operands, HALF, COSINE> (K2 on CTA pairs, tcgen05 cta_group::2) + batch_select "
+                                  "+ exchange; per GPU; achieved is over the WHOLE batch",
+                        "traffic": traffic, "traffic_source": traffic_src,
+                        "note": "profiles/r2_c5_gemm_pair_full.txt: the nomination kernel alone keeps the tensor pipe 97 % active "
+                                "(sm__pipe_tensor_cycles_active) at the clock the board sustains under this load"}}
     if ctx["check"]:
         # parity: query 0 of the batch against the oracle over ALL shards' rows -- every rank scans its own rows (regenerated
         # slab by slab), rank 0 merges the per-rank lists like the reference merges segments

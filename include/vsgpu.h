@@ -327,8 +327,10 @@ int64_t vs_kernel_launch_count(void);
  * the per-query scan; "batch_fp16" (default 1): nominate on an fp16 operand copy of the rows (n * d * 2
  * bytes of HBM, made at the first batched query) instead of the fp32 rows read as tf32; "batch_group"
  * (0 = automatic, 16 / 32 / 64): rows per nomination group; "batch_gm_bytes": scratch per query chunk;
- * "batch_warp_min_queries" (0 = automatic); "batch_pairs" (default 0): batches of more than 128 queries
- * nominate on CTA pairs (tcgen05 cta_group::2).  "scan_reserve_sms": SMs the one-query scan leaves free so that
+ * "batch_warp_min_queries" (0 = automatic); "batch_pairs": whether batches of more than 128 queries nominate on
+ * CTA pairs (tcgen05 cta_group::2) -- 0 never, 1 wherever it fits, 2 (default) for long vectors only, where both
+ * operands stream through shared memory; "batch_select_ctas" (0 = automatic) and "batch_prefetch_rounds"
+ * (default 1, this device only): diagnostics of the selection kernel.  "scan_reserve_sms": SMs the one-query scan leaves free so that
  * work of another stream (the next query's prologue, a collective's CTAs) runs beside it (default 0).
  * "peer_fused" (default 1): a one-query peer exchange publishes inside the merge kernel (one launch) instead
  * of a publishing kernel followed by the merge.  "peer_spin_shared" (default 0, for tests of the polling kernels on a

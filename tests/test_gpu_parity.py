@@ -196,7 +196,7 @@ def force_batch(vs, request):
     vs.set_option("batch_pairs", 1 if "pairs" in request.param else 0)  # cta_group::2 nomination kernel
     yield
     vs.set_option("batch_group", 0)
-    vs.set_option("batch_pairs", 0)
+    vs.set_option("batch_pairs", 2)  # automatic: long vectors only
     vs.set_option("batch_min_queries", 3)
     vs.set_option("batch_min_rows", 16384)
     vs.set_option("batch_fp16", 1)

@@ -17,6 +17,10 @@ if os.environ.get("VS_PAIRS"):
     vs.set_option("batch_pairs", int(os.environ["VS_PAIRS"]))
 if os.environ.get("VS_WARPQ"):
     vs.set_option("batch_warp_min_queries", int(os.environ["VS_WARPQ"]))
+if os.environ.get("VS_PFR"):
+    vs.set_option("batch_prefetch_rounds", int(os.environ["VS_PFR"]))
+if os.environ.get("VS_SELP"):
+    vs.set_option("batch_select_ctas", int(os.environ["VS_SELP"]))
 if os.environ.get("VS_GROUP"):
     vs.set_option("batch_group", int(os.environ["VS_GROUP"]))
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000

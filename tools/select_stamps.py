@@ -5,14 +5,21 @@ import numpy as np, torch
 import vectorsearch_b200 as vs
 from vectorsearch_b200 import _lib as L
 vs.init(0); lib = vs.load()
-n, d, nq, k = 1_000_000, 128, int(sys.argv[1]) if len(sys.argv) > 1 else 1024, 10
+nq = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+n, d, k, metric = (int(os.environ.get(e, v)) for e, v in (("VS_N", 1_000_000), ("VS_D", 128), ("VS_K", 10), ("VS_METRIC", 0)))
+if os.environ.get("VS_PAIRS"):
+    vs.set_option("batch_pairs", int(os.environ["VS_PAIRS"]))
+if os.environ.get("VS_SELP"):
+    vs.set_option("batch_select_ctas", int(os.environ["VS_SELP"]))
+if os.environ.get("VS_GROUP"):
+    vs.set_option("batch_group", int(os.environ["VS_GROUP"]))
 seg = vs.Segment.generate(42, 0, n, d)
 dev = torch.device("cuda:0")
 q = torch.rand(nq, d, device=dev) * 2 - 1
 ids = torch.zeros(nq, k, dtype=torch.int64, device=dev); sc = torch.zeros(nq, k, dtype=torch.float64, device=dev); cn = torch.zeros(nq, dtype=torch.int32, device=dev)
 st = torch.cuda.current_stream().cuda_stream
 for it in range(4):
-    L.check(lib.vs_bruteforce_topk_dev(seg.handle, q.data_ptr(), nq, k, 0, ids.data_ptr(), sc.data_ptr(), cn.data_ptr(), st))
+    L.check(lib.vs_bruteforce_topk_dev(seg.handle, q.data_ptr(), nq, k, metric, ids.data_ptr(), sc.data_ptr(), cn.data_ptr(), st))
 torch.cuda.synchronize()
 buf = np.zeros(8 * 1024, dtype=np.uint64)
 lib.vs_debug_read_stamps_batch.argtypes = [C.c_void_p, C.c_int64]

@@ -43,9 +43,13 @@ static std::atomic<int64_t> g_batch_warp_min_q{0};         // > 0: batches this 
 static std::atomic<int> g_peer_fused{1};                      // one-query exchanges: publish inside the merge kernel
 static std::atomic<int> g_peer_spin_shared{0};                // tests: poll inside the kernels even when ranks share a device
 static std::atomic<int64_t> g_scan_reserve_sms{0};          // SMs the one-query scan leaves free (for a collective's CTAs)
-static std::atomic<int64_t> g_batch_pairs{0};               // 1: cta_group::2 nomination kernel for batches > 128 queries (measured equal)
+// cta_group::2 nomination kernel for batches > 128 queries: 0 never, 1 wherever it fits, 2 (default) long vectors only --
+// where both operands stream it moves a third less through L2 and the tensor pipe runs at 97 %; with the query
+// block resident (d = 128) it measured equal to the single-CTA kernel
+static std::atomic<int64_t> g_batch_pairs{2};
 static std::atomic<int64_t> g_batch_prefilter{1};           // candidate groups are pre-filtered on the fp16 copy before exact scoring
 static std::atomic<int64_t> g_pdl{1};                       // programmatic dependent launch between the kernels of one call
+static std::atomic<int64_t> g_batch_select_ctas{0};         // 0 = automatic selection CTAs per query, else 1..64 (diagnostics)
 static std::atomic<int64_t> g_batch_group{0};               // 0 = automatic rows per nomination group, else 16 / 32 / 64
 static std::atomic<int64_t> g_batch_fp16{1};                // nominate on fp16 operand copies (0: the fp32 rows as tf32)
 static int g_sms = 0;
@@ -514,8 +518,8 @@ static bool batch_wanted(const Segment* s, int nq, bool cosine) {
 
 static int plan_batch(const Segment* s, int k, bool cosine, bool half, BatchLaunch* out) {
   const int ln = lanes();
-  const int go = (int)g_batch_group.load();
-  const uint64_t key = occ_key(cosine ? 31 : 30, s->d, ln, k, (half ? 1 : 0) + 2 * go, (size_t)s->n);
+  const int go = (int)g_batch_group.load(), sp = (int)g_batch_select_ctas.load();
+  const uint64_t key = occ_key(cosine ? 31 : 30, s->d, ln, k, (half ? 1 : 0) + 2 * go + 256 * sp, (size_t)s->n);
   {
     std::lock_guard<std::mutex> lk(g_scan_mu);
     auto it = g_batch_cache.find(key);
@@ -526,6 +530,7 @@ static int plan_batch(const Segment* s, int k, bool cosine, bool half, BatchLaun
   }
   BatchLaunch L{};
   L.n = s->n; L.d = s->d; L.lanes = ln; L.cosine = cosine; L.k = k; L.half = half; L.dp = (s->d + 7) & ~7; L.group_override = go;
+  L.select_ctas_override = sp;
   if (!batch_configure(L, g_sms)) return fail(VS_ECUDA, "batched scan cannot be resident for d=%d k=%d", s->d, k);
   std::lock_guard<std::mutex> lk(g_scan_mu);
   g_batch_cache[key] = L;
@@ -635,7 +640,7 @@ static int batch_run_dev(cudaStream_t st, const Segment* s, const BatchLaunch& p
     BatchLaunch L = p;
     L.X = s->X; L.skip = s->skip; L.q = d_q + (size_t)q0 * s->d; L.nq = c;
     L.tmX = p.half ? s->tmXh : s->tmX; L.tmX128 = p.half ? s->tmXh_b128 : s->tmX_b128; L.x_scale = s->x_scale;
-    L.pairs = g_batch_pairs.load() != 0;
+    L.pairs = g_batch_pairs.load() == 1 || (g_batch_pairs.load() == 2 && !p.pair_stat);
     L.xh = s->Xh; L.prefilter = g_batch_prefilter.load() != 0;
     L.coef = static_cast<const float*>(s->ab[m]); L.stats = static_cast<const SegStats*>(s->stats[m]);
     L.gm = A.take<float>((size_t)((chunk + 255) / 256 * 256) * p.gm_stride);
@@ -802,7 +807,18 @@ int32_t vs_set_option(const char* name, int64_t value) {
     return VS_OK;
   }
   if (!strcmp(name, "batch_pairs")) {
-    g_batch_pairs.store(value != 0);
+    if (value < 0 || value > 2) return fail(VS_EINVAL, "batch_pairs must be 0 (never), 1 (always) or 2 (long vectors only)");
+    g_batch_pairs.store(value);
+    return VS_OK;
+  }
+  if (!strcmp(name, "batch_prefetch_rounds")) {  // this device only (diagnostics)
+    if (value < -1 || value > 64) return fail(VS_EINVAL, "batch_prefetch_rounds must be -1 .. 64");
+    CK(cudaError_t(batch_set_prefetch_rounds((int)value)), "batch_prefetch_rounds");
+    return VS_OK;
+  }
+  if (!strcmp(name, "batch_select_ctas")) {
+    if (value < 0 || value > 64) return fail(VS_EINVAL, "batch_select_ctas must be 0 (automatic) .. 64");
+    g_batch_select_ctas.store(value);
     return VS_OK;
   }
   if (!strcmp(name, "batch_group")) {
@@ -1944,7 +1960,7 @@ int32_t vs_debug_batch_groupmins(uint64_t h, const float* q, int32_t nq, int32_t
   BatchLaunch L = bp;
   const int m = cosine ? 1 : 0;
   L.X = s->X; L.skip = s->skip; L.q = dq; L.nq = nq; L.tmX = half ? s->tmXh : s->tmX; L.x_scale = s->x_scale;
-  L.tmX128 = half ? s->tmXh_b128 : s->tmX_b128; L.pairs = g_batch_pairs.load() != 0;
+  L.tmX128 = half ? s->tmXh_b128 : s->tmX_b128; L.pairs = g_batch_pairs.load() == 1 || (g_batch_pairs.load() == 2 && !bp.pair_stat);
   L.coef = static_cast<const float*>(s->ab[m]); L.stats = static_cast<const SegStats*>(s->stats[m]);
   const int chunk = batch_chunk(bp, nq);
   L.gm = B.take<float>((size_t)((chunk + 255) / 256 * 256) * bp.gm_stride);

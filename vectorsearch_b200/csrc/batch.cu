@@ -440,7 +440,10 @@ __device__ __forceinline__ void tc_mma_pair(bool half, uint32_t d_tmem, uint64_t
                  ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
 
-template <bool HALF, bool COSINE, int GROUP>
+// STAT as above; otherwise (long vectors: the query block does not fit beside the stages) every stage carries one
+// k-block of the CTA's query block AND of its half of the row tile -- 32 KB per CTA for the flops the single-CTA
+// kernel moves 48 KB for, which is what matters at d = 768 where that kernel runs into the L2 -> SM rate.
+template <bool STAT, bool HALF, bool COSINE, int GROUP>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BQ_THREADS, 1)
 batch_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmX /* 128-row box */,
                        const float* __restrict__ coef, const float* __restrict__ qinv, int64_t n, int num_kb, int nstages,
@@ -449,9 +452,11 @@ batch_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   uint8_t* base = bq_smem;
   if ((smem_u32(base) & 1023u) != 0) __trap();
   constexpr int KB_ELEMS = HALF ? 64 : 32;
-  uint8_t* aq = base;                                   // [num_kb][16 KB] this CTA's query block
-  uint8_t* stages = base + (size_t)num_kb * BQ_A_BYTES;  // [nstages][16 KB] this CTA's half of the row tile
-  float* sm_coef = reinterpret_cast<float*>(stages + (size_t)nstages * BQ_BH_BYTES);
+  constexpr uint32_t STAGE_BYTES = STAT ? BQ_BH_BYTES : BQ_A_BYTES + BQ_BH_BYTES;
+  uint8_t* aq = base;                                   // STAT: [num_kb][16 KB] this CTA's query block
+  // [nstages] this CTA's half of the row tile (16 KB), preceded by the query block's k-block when both stream
+  uint8_t* stages = base + (STAT ? (size_t)num_kb * BQ_A_BYTES : 0);
+  float* sm_coef = reinterpret_cast<float*>(stages + (size_t)nstages * STAGE_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sm_coef) + BQ_AB_BYTES);
   uint64_t* full = bars;                                  // leader's copy is the live one
   uint64_t* empty = bars + BQ_PAIR_MAX_STAGES;            // one per CTA
@@ -496,15 +501,19 @@ batch_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 
   if (warp == 0) {
     if (lane == 0) {  // ===== TMA producer (both CTAs) =====
-      if (rank == 0) mbar_expect_tx(afull, 2u * (uint32_t)num_kb * BQ_A_BYTES);
-      for (int kb = 0; kb < num_kb; kb++) tma_load_2d_pair(aq + (size_t)kb * BQ_A_BYTES, &tmQ, kb * KB_ELEMS, qb * BQ_M, afull);
+      if (STAT) {
+        if (rank == 0) mbar_expect_tx(afull, 2u * (uint32_t)num_kb * BQ_A_BYTES);
+        for (int kb = 0; kb < num_kb; kb++) tma_load_2d_pair(aq + (size_t)kb * BQ_A_BYTES, &tmQ, kb * KB_ELEMS, qb * BQ_M, afull);
+      }
       int s = 0;
       uint32_t ph = 0;
       for (int64_t tile = split; tile < tiles; tile += nsplit) {
         for (int kb = 0; kb < num_kb; kb++) {
           mbar_wait(empty + s, ph ^ 1);
-          if (rank == 0) mbar_expect_tx(full + s, 2u * BQ_BH_BYTES);
-          tma_load_2d_pair(stages + (size_t)s * BQ_BH_BYTES, &tmX, kb * KB_ELEMS, (int)(tile * BQ_N + rank * (BQ_N / 2)), full + s);
+          if (rank == 0) mbar_expect_tx(full + s, 2u * STAGE_BYTES);
+          uint8_t* st = stages + (size_t)s * STAGE_BYTES;
+          if (!STAT) tma_load_2d_pair(st, &tmQ, kb * KB_ELEMS, qb * BQ_M, full + s);
+          tma_load_2d_pair(st + (STAT ? 0 : BQ_A_BYTES), &tmX, kb * KB_ELEMS, (int)(tile * BQ_N + rank * (BQ_N / 2)), full + s);
           if (++s == nstages) {
             s = 0;
             ph ^= 1;
@@ -516,7 +525,7 @@ batch_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     if (lane == 0 && rank == 0) {  // ===== MMA issuer (leader CTA only) =====
       int s = 0, it = 0;
       uint32_t ph = 0;
-      mbar_wait(afull, 0);
+      if (STAT) mbar_wait(afull, 0);
       for (int64_t tile = split; tile < tiles; tile += nsplit, it++) {
         const int a = it & 1;
         mbar_wait(tempty + a, ((it >> 1) & 1) ^ 1);  // both CTAs' epilogues have drained this accumulator
@@ -525,8 +534,9 @@ batch_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         for (int kb = 0; kb < num_kb; kb++) {
           mbar_wait(full + s, ph);
           tc_fence_after();
-          const uint64_t adesc = umma_desc_sw128(smem_u32(aq + (size_t)kb * BQ_A_BYTES));
-          const uint64_t bdesc = umma_desc_sw128(smem_u32(stages + (size_t)s * BQ_BH_BYTES));
+          const uint32_t sst = smem_u32(stages + (size_t)s * STAGE_BYTES);
+          const uint64_t adesc = umma_desc_sw128(STAT ? smem_u32(aq + (size_t)kb * BQ_A_BYTES) : sst);
+          const uint64_t bdesc = umma_desc_sw128(sst + (STAT ? 0u : BQ_A_BYTES));
 #pragma unroll
           for (int kk = 0; kk < 4; kk++)
             tc_mma_pair(HALF, d_tmem, adesc + 2 * kk, bdesc + 2 * kk, HALF ? BQ_IDESC_F16_M256 : BQ_IDESC_TF32_M256, (kb | kk) != 0 ? 1u : 0u);
@@ -624,35 +634,81 @@ struct HalfOperands {
   int dp;
 };
 
-template <bool COSINE, class TK>
-__device__ __forceinline__ void bq_group_prefilter_exact(const HalfOperands& H, const float* __restrict__ X, int64_t n, int d,
-                                                         const float* __restrict__ q, const float* __restrict__ qf /* smem [dp] */,
-                                                         float qi_scale, const uint8_t* __restrict__ skip, int lanes, double qq,
-                                                         float tau, int64_t row0, int gsz, int* __restrict__ plist /* warp smem [gsz] */,
-                                                         TK& tk, int lane) {
+constexpr int BQ_PLIST = 128;  // survivors a warp collects before it scores them (ints of warp-private shared memory)
+
+// Rolling L2 prefetch of a warp's candidate rows, eight rows (one pre-filter round) at a time and c_bq_pf_ahead rounds
+// ahead of the loads.  (Asking for every candidate group of every query up front, as this kernel once did, is
+// fine at d = 128 but pushes ~1 GB through a 126 MB L2 at d = 768, k = 50: most lines were evicted before use
+// and fetched from HBM twice.)
+__constant__ int c_bq_pf_ahead = 1;
+int batch_set_prefetch_rounds(int rounds) { return (int)cudaMemcpyToSymbol(c_bq_pf_ahead, &rounds, sizeof(int)); }
+struct PrefetchCursor {
+  const int* list;
+  const char* xb;   // fp16 rows
+  int64_t rbytes;   // bytes per row
+  int64_t n;
+  int gi, step, cnt, gsz, r0;
+  __device__ __forceinline__ void advance(int lane) {  // request the cursor's round, move on
+    if (gi >= cnt) return;
+    if (lane == 0) {
+      const int64_t row = (int64_t)list[gi] * gsz + r0;
+      int64_t rows = n - row;
+      if (rows > 8) rows = 8;
+      if (rows > gsz - r0) rows = gsz - r0;
+      if (rows > 0)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(xb + row * rbytes), "r"((uint32_t)(rows * rbytes)) : "memory");
+    }
+    r0 += 8;
+    if (r0 >= gsz) {
+      r0 = 0;
+      gi += step;
+    }
+  }
+};
+
+// Pre-filter of candidate group `gi` (rows row0 .. row0 + gsz): appends (gi << 6 | row in group) of every row with
+// a <= tau to plist and asks L2 for the fp32 row, so that the exact scores (bq_score_survivors, after several
+// groups) do not wait on HBM row by row.  Four lanes per row, eight rows per round, up to eight 16-byte loads in
+// flight per lane: the rows come from L2 (bulk prefetch of the whole group) and the loop is pure latency.
+template <bool COSINE>
+__device__ __forceinline__ int bq_group_prefilter(const HalfOperands& H, const float* __restrict__ X, int64_t n, int d,
+                                                  const float* __restrict__ qf /* smem [dp] */, float qi_scale, float tau,
+                                                  int64_t row0, int gsz, int gi, int* __restrict__ plist, int pcnt,
+                                                  PrefetchCursor& pf, int lane) {
   const int t = lane & 3, g = lane >> 2;
   const int chunks = H.dp >> 3;  // 16-byte chunks (8 halfs) per row
-  int pcnt = 0;
   for (int r0 = 0; r0 < gsz; r0 += 8) {
+    pf.advance(lane);
     const int64_t row = row0 + r0 + g;
     const bool live = row < n && r0 + g < gsz;
     float dot = 0.0f;
     if (live) {
       const uint4* xr = reinterpret_cast<const uint4*>(H.Xh + (size_t)row * H.dp);
       float d0 = 0.0f, d1 = 0.0f;
-      for (int c = t; c < chunks; c += 4) {
-        const uint4 v = __ldg(xr + c);
-        const float4 qa = *reinterpret_cast<const float4*>(qf + c * 8), qb = *reinterpret_cast<const float4*>(qf + c * 8 + 4);
-        const float2 x0 = __half22float2(*reinterpret_cast<const __half2*>(&v.x)), x1 = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
-        const float2 x2 = __half22float2(*reinterpret_cast<const __half2*>(&v.z)), x3 = __half22float2(*reinterpret_cast<const __half2*>(&v.w));
-        d0 = fmaf(x0.x, qa.x, d0);
-        d1 = fmaf(x0.y, qa.y, d1);
-        d0 = fmaf(x1.x, qa.z, d0);
-        d1 = fmaf(x1.y, qa.w, d1);
-        d0 = fmaf(x2.x, qb.x, d0);
-        d1 = fmaf(x2.y, qb.y, d1);
-        d0 = fmaf(x3.x, qb.z, d0);
-        d1 = fmaf(x3.y, qb.w, d1);
+      for (int c0 = t; c0 < chunks; c0 += 32) {
+        uint4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const int c = c0 + 4 * j;
+          v[j] = c < chunks ? __ldg(xr + c) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const int c = c0 + 4 * j;
+          if (c < chunks) {
+            const float4 qa = *reinterpret_cast<const float4*>(qf + c * 8), qb = *reinterpret_cast<const float4*>(qf + c * 8 + 4);
+            const float2 x0 = __half22float2(*reinterpret_cast<const __half2*>(&v[j].x)), x1 = __half22float2(*reinterpret_cast<const __half2*>(&v[j].y));
+            const float2 x2 = __half22float2(*reinterpret_cast<const __half2*>(&v[j].z)), x3 = __half22float2(*reinterpret_cast<const __half2*>(&v[j].w));
+            d0 = fmaf(x0.x, qa.x, d0);
+            d1 = fmaf(x0.y, qa.y, d1);
+            d0 = fmaf(x1.x, qa.z, d0);
+            d1 = fmaf(x1.y, qa.w, d1);
+            d0 = fmaf(x2.x, qb.x, d0);
+            d1 = fmaf(x2.y, qb.y, d1);
+            d0 = fmaf(x3.x, qb.z, d0);
+            d1 = fmaf(x3.y, qb.w, d1);
+          }
+        }
       }
       dot = d0 + d1;
     }
@@ -665,11 +721,23 @@ __device__ __forceinline__ void bq_group_prefilter_exact(const HalfOperands& H, 
       pass = a <= tau;  // dead rows carry +inf / NaN coefficients and never pass
     }
     const unsigned m = __ballot_sync(FULL_MASK, pass);
-    if (pass) plist[pcnt + __popc(m & ((1u << lane) - 1u))] = r0 + g;
+    if (pass) {
+      plist[pcnt + __popc(m & ((1u << lane) - 1u))] = (gi << 6) | (r0 + g);
+      if ((d & 3) == 0)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(X + (size_t)row * d), "r"((uint32_t)d * 4u) : "memory");
+    }
     pcnt += __popc(m);
   }
+  return pcnt;
+}
+
+// exact scores of the survivors: one row per half-warp, lane hl is SIMD lane hl of the modelled JVM
+template <bool COSINE, class TK>
+__device__ __forceinline__ void bq_score_survivors(const float* __restrict__ X, int d, const float* __restrict__ q,
+                                                   const uint8_t* __restrict__ skip, int lanes, double qq,
+                                                   const int* __restrict__ list, int gsz, const int* __restrict__ plist, int pcnt,
+                                                   TK& tk, int lane) {
   __syncwarp();
-  // exact scores of the survivors: one row per half-warp, lane hl is SIMD lane hl of the modelled JVM
   const int hl = lane & 15, hw = lane >> 4;
   const unsigned hmask = (lane < 16) ? 0x0000ffffu : 0xffff0000u;
   const int base_lane = lane & 16;
@@ -678,7 +746,8 @@ __device__ __forceinline__ void bq_group_prefilter_exact(const HalfOperands& H, 
     Key key = key_empty();
     bool ok = false;
     if (have) {  // uniform across the half-warp
-      const int64_t row = row0 + plist[i + hw];
+      const int e = plist[i + hw];
+      const int64_t row = (int64_t)list[e >> 6] * gsz + (e & 63);
       ok = !(skip != nullptr && skip[row]);
       if (ok) {
         const float* x = X + (size_t)row * d;
@@ -696,6 +765,28 @@ __device__ __forceinline__ void bq_group_prefilter_exact(const HalfOperands& H, 
     tk.push(key, ok && hl == 0, lane);
   }
   __syncwarp();
+}
+
+// all of a warp's candidate groups list[first], list[first + step], ...: pre-filter, then exact scores in batches
+template <bool COSINE, class TK>
+__device__ __forceinline__ void bq_groups_prefilter_exact(const HalfOperands& H, const float* __restrict__ X, int64_t n, int d,
+                                                          const float* __restrict__ q, const float* __restrict__ qf, float qi_scale,
+                                                          const uint8_t* __restrict__ skip, int lanes, double qq, float tau,
+                                                          const int* __restrict__ list, int first, int step, int cnt, int gsz,
+                                                          int* __restrict__ plist /* warp smem [BQ_PLIST] */, TK& tk, int lane) {
+  int pcnt = 0;
+  PrefetchCursor pf{list, reinterpret_cast<const char*>(H.Xh), (int64_t)H.dp * 2, n, first, step, cnt, gsz, 0};
+  const int ahead = c_bq_pf_ahead;
+  if (ahead < 0) pf.gi = cnt;  // no prefetch
+  for (int i = 0; i < ahead; i++) pf.advance(lane);
+  for (int gi = first; gi < cnt; gi += step) {
+    if (pcnt + gsz > BQ_PLIST) {
+      bq_score_survivors<COSINE, TK>(X, d, q, skip, lanes, qq, list, gsz, plist, pcnt, tk, lane);
+      pcnt = 0;
+    }
+    pcnt = bq_group_prefilter<COSINE>(H, X, n, d, qf, qi_scale, tau, (int64_t)list[gi] * gsz, gsz, gi, plist, pcnt, pf, lane);
+  }
+  bq_score_survivors<COSINE, TK>(X, d, q, skip, lanes, qq, list, gsz, plist, pcnt, tk, lane);
 }
 
 // ---- (3) threshold, candidate groups, exact ranking --------------------------------------------------------------
@@ -889,11 +980,12 @@ batch_select_kernel(const float* __restrict__ X, int64_t n, int d, const float* 
   {
     // one bulk L2 prefetch per candidate group (its rows are contiguous): the fp16 rows the pre-filter reads, or
     // the fp32 rows when whole groups are scored exactly
+    // (the fp16 pre-filter prefetches its rows itself, a few rounds ahead of its loads)
     const bool hp = H.Xh != nullptr;
-    const char* xb = hp ? reinterpret_cast<const char*>(H.Xh) : reinterpret_cast<const char*>(X);
-    const int64_t rbytes = hp ? (int64_t)H.dp * 2 : (int64_t)d * 4;
+    const char* xb = reinterpret_cast<const char*>(X);
+    const int64_t rbytes = (int64_t)d * 4;
     const int64_t xbytes = n * rbytes, gbytes = (int64_t)gsz * rbytes;
-    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+    for (int i = threadIdx.x; i < (hp ? 0 : cnt); i += blockDim.x) {
       const int64_t off = (int64_t)list[i] * gbytes;
       const int64_t len = off + gbytes <= xbytes ? gbytes : xbytes - off;
       if (len > 0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(xb + off), "r"((uint32_t)len) : "memory");
@@ -908,9 +1000,8 @@ batch_select_kernel(const float* __restrict__ X, int64_t n, int d, const float* 
   uint64_t seen_hi = KEY_EMPTY64, seen_lo = KEY_EMPTY64;
   if (H.Xh != nullptr) {
     // fp16 pre-filter per group, exact scores for the rows that pass (qs holds the scaled fp16 query as floats)
-    int* plist = reinterpret_cast<int*>(qs + ((H.dp + 3) & ~3)) + warp * 64;
-    for (int gi = warp; gi < cnt; gi += nw)
-      bq_group_prefilter_exact<COSINE, TK>(H, X, n, d, q, qs, H.qinv[qi], skip, L, qq, tau, (int64_t)list[gi] * gsz, gsz, plist, tk, lane);
+    int* plist = reinterpret_cast<int*>(qs + ((H.dp + 3) & ~3)) + warp * BQ_PLIST;
+    bq_groups_prefilter_exact<COSINE, TK>(H, X, n, d, q, qs, H.qinv[qi], skip, L, qq, tau, list, warp, nw, cnt, gsz, plist, tk, lane);
   } else {
   const int total = cnt * BPG;
   for (int b = warp; b < total; b += nw) {
@@ -949,10 +1040,10 @@ batch_select_warp_kernel(const float* __restrict__ X, int64_t n, int d, const fl
   const int warp = threadIdx.x >> 5;
   const int qi = blockIdx.x * (blockDim.x >> 5) + warp;
   if (qi >= nq) return;
-  const int qpad = (((H.Xh != nullptr ? H.dp : d) + 3) & ~3) + 64;  // query floats + the pre-filter's survivor list
+  const int qpad = (((H.Xh != nullptr ? H.dp : d) + 3) & ~3) + BQ_PLIST;  // query floats + the pre-filter's survivor list
   int* list = reinterpret_cast<int*>(smem) + (size_t)warp * (cap + qpad);
   float* qs = reinterpret_cast<float*>(list + cap);
-  int* plist = reinterpret_cast<int*>(qs + qpad - 64);
+  int* plist = reinterpret_cast<int*>(qs + qpad - BQ_PLIST);
   const float* __restrict__ q = Q + (size_t)qi * d;
   const float* gmq = gm + (size_t)qi * gm_stride;
   const float inf = __int_as_float(0x7f800000);
@@ -1028,10 +1119,10 @@ batch_select_warp_kernel(const float* __restrict__ X, int64_t n, int d, const fl
   __syncwarp();
   {
     const bool hp = H.Xh != nullptr;
-    const char* xb = hp ? reinterpret_cast<const char*>(H.Xh) : reinterpret_cast<const char*>(X);
-    const int64_t rbytes = hp ? (int64_t)H.dp * 2 : (int64_t)d * 4;
+    const char* xb = reinterpret_cast<const char*>(X);
+    const int64_t rbytes = (int64_t)d * 4;
     const int64_t xbytes = n * rbytes, gbytes = (int64_t)gsz * rbytes;
-    for (int i = lane; i < cnt; i += 32) {
+    for (int i = lane; i < (hp ? 0 : cnt); i += 32) {
       const int64_t off = (int64_t)list[i] * gbytes;
       const int64_t len = off + gbytes <= xbytes ? gbytes : xbytes - off;
       if (len > 0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(xb + off), "r"((uint32_t)len) : "memory");
@@ -1044,8 +1135,7 @@ batch_select_warp_kernel(const float* __restrict__ X, int64_t n, int d, const fl
   float fthr = inf;
   uint64_t seen_hi = KEY_EMPTY64, seen_lo = KEY_EMPTY64;
   if (H.Xh != nullptr) {
-    for (int gi = 0; gi < cnt; gi++)
-      bq_group_prefilter_exact<COSINE, WarpTopKReg>(H, X, n, d, q, qs, H.qinv[qi], skip, L, qq, tau, (int64_t)list[gi] * gsz, gsz, plist, tk, lane);
+    bq_groups_prefilter_exact<COSINE, WarpTopKReg>(H, X, n, d, q, qs, H.qinv[qi], skip, L, qq, tau, list, 0, 1, cnt, gsz, plist, tk, lane);
   } else {
   const int total = cnt * BPG;
   for (int b = 0; b < total; b++) {
@@ -1183,12 +1273,17 @@ static GemmKern pick_gemm(bool stat, bool half, bool cosine, int group) {
 }
 
 template <int GROUP>
-static GemmKern pick_gemm_pair_g(bool half, bool cosine) {
-  if (half) return cosine ? batch_gemm_pair_kernel<true, true, GROUP> : batch_gemm_pair_kernel<true, false, GROUP>;
-  return cosine ? batch_gemm_pair_kernel<false, true, GROUP> : batch_gemm_pair_kernel<false, false, GROUP>;
+static GemmKern pick_gemm_pair_g(bool stat, bool half, bool cosine) {
+  if (stat) {
+    if (half) return cosine ? batch_gemm_pair_kernel<true, true, true, GROUP> : batch_gemm_pair_kernel<true, true, false, GROUP>;
+    return cosine ? batch_gemm_pair_kernel<true, false, true, GROUP> : batch_gemm_pair_kernel<true, false, false, GROUP>;
+  }
+  if (half) return cosine ? batch_gemm_pair_kernel<false, true, true, GROUP> : batch_gemm_pair_kernel<false, true, false, GROUP>;
+  return cosine ? batch_gemm_pair_kernel<false, false, true, GROUP> : batch_gemm_pair_kernel<false, false, false, GROUP>;
 }
-static GemmKern pick_gemm_pair(bool half, bool cosine, int group) {
-  return group == 16 ? pick_gemm_pair_g<16>(half, cosine) : (group == 32 ? pick_gemm_pair_g<32>(half, cosine) : pick_gemm_pair_g<64>(half, cosine));
+static GemmKern pick_gemm_pair(bool stat, bool half, bool cosine, int group) {
+  return group == 16 ? pick_gemm_pair_g<16>(stat, half, cosine)
+                     : (group == 32 ? pick_gemm_pair_g<32>(stat, half, cosine) : pick_gemm_pair_g<64>(stat, half, cosine));
 }
 
 // dynamic shared memory of batch_select_kernel with nw warps: collectors, group list, query
@@ -1198,7 +1293,7 @@ static size_t batch_select_smem(const BatchLaunch& L, int nw) {
   if (b3 > coll) coll = b3;
   coll = (coll + 15) & ~size_t(15);
   // collectors, group list, query (d floats, or the dp floats of the scaled fp16 query), survivor lists of the pre-filter
-  return coll + (size_t)((L.cap + 3) & ~3) * 4 + (size_t)((L.dp + 3) & ~3) * 4 + (size_t)nw * 64 * 4;
+  return coll + (size_t)((L.cap + 3) & ~3) * 4 + (size_t)((L.dp + 3) & ~3) * 4 + (size_t)nw * BQ_PLIST * 4;
 }
 
 bool batch_configure(BatchLaunch& L, int sms) {
@@ -1230,13 +1325,14 @@ bool batch_configure(BatchLaunch& L, int sms) {
     if (ns > BQ_MAX_STAGES) ns = BQ_MAX_STAGES;
     L.gemm_stages = ns;
     L.gemm_smem = fixed + (L.gemm_stat ? a_res : 0) + (size_t)ns * per;
-    // CTA pairs (batches > 128 queries): resident query block + at least 4 stages of half a row tile
-    L.pair_stages = 0;
-    if (fixed + a_res + 4 * (size_t)BQ_BH_BYTES + 128 <= BQ_GEMM_SMEM_BUDGET) {
-      int ns2 = (int)((BQ_GEMM_SMEM_BUDGET - fixed - a_res - 128) / BQ_BH_BYTES);
+    // CTA pairs (batches > 128 queries): resident query block + at least 4 stages of half a row tile, else both stream
+    L.pair_stat = fixed + a_res + 4 * (size_t)BQ_BH_BYTES + 128 <= BQ_GEMM_SMEM_BUDGET;
+    {
+      const size_t per2 = L.pair_stat ? BQ_BH_BYTES : BQ_A_BYTES + BQ_BH_BYTES;
+      int ns2 = (int)((BQ_GEMM_SMEM_BUDGET - fixed - (L.pair_stat ? a_res : 0) - 128) / per2);
       if (ns2 > BQ_PAIR_MAX_STAGES) ns2 = BQ_PAIR_MAX_STAGES;
       L.pair_stages = ns2;
-      L.pair_smem = fixed + a_res + 128 + (size_t)ns2 * BQ_BH_BYTES;
+      L.pair_smem = fixed + (L.pair_stat ? a_res : 0) + 128 + (size_t)ns2 * per2;
     }
   }
   // candidate groups per select CTA: the k-th smallest group minimum admits about k groups, the slack a few more
@@ -1247,7 +1343,7 @@ bool batch_configure(BatchLaunch& L, int sms) {
     L.cap = L.cap / 2 > L.k + 64 ? L.cap / 2 : L.k + 64;
   }
   if (L.select_smem > BQ_SELECT_SMEM_MAX) return false;
-  L.selw_smem = (size_t)(BQ_SELECT_THREADS / 32) * (size_t)(L.cap + ((L.dp + 3) & ~3) + 64) * 4;
+  L.selw_smem = (size_t)(BQ_SELECT_THREADS / 32) * (size_t)(L.cap + ((L.dp + 3) & ~3) + BQ_PLIST) * 4;
   if (L.k <= TOPK_REG_MAX_K && L.selw_smem <= BQ_SELW_SMEM_MAX) {
     if (set_smem_attr(pick_select_warp(L.lanes / 4, L.cosine), BQ_SELW_SMEM_MAX) != cudaSuccess) return false;
   } else {
@@ -1263,7 +1359,7 @@ bool batch_configure(BatchLaunch& L, int sms) {
     cudaError_t e;
     e = set_smem_attr(pick_gemm(L.gemm_stat, L.half, L.cosine, L.group), BQ_GEMM_SMEM_BUDGET);
     if (e != cudaSuccess) return false;
-    if (L.pair_stages > 0 && set_smem_attr(pick_gemm_pair(L.half, L.cosine, L.group), BQ_GEMM_SMEM_BUDGET) != cudaSuccess) return false;
+    if (L.pair_stages > 0 && set_smem_attr(pick_gemm_pair(L.pair_stat, L.half, L.cosine, L.group), BQ_GEMM_SMEM_BUDGET) != cudaSuccess) return false;
   }
   if (set_smem_attr(pick_select(TPR, L.cosine, L.k), BQ_SELECT_SMEM_MAX) != cudaSuccess) return false;
   if (set_smem_attr(pick_fallback(TPR, L.cosine, L.k), BQ_SELECT_SMEM_MAX) != cudaSuccess) return false;
@@ -1272,7 +1368,10 @@ bool batch_configure(BatchLaunch& L, int sms) {
 
 int batch_select_ctas(const BatchLaunch& L, int nq) {
   // enough select CTAs to fill the GPU when the batch is small; slices no shorter than 2048 groups
-  int64_t P = (2 * (int64_t)L.sms + nq - 1) / nq;
+  // (every CTA nominates about k groups of its slice whatever the slice's length, so the re-score work grows with
+  // P: rounded down -- 256 queries get one CTA each on 148 SMs, not two)
+  int64_t P = 2 * (int64_t)L.sms / nq;
+  if (L.select_ctas_override > 0) P = L.select_ctas_override;
   const int64_t by_len = (L.ngroups + 2047) / 2048;
   if (P > by_len) P = by_len;
   if (P > 64) P = 64;
@@ -1308,7 +1407,7 @@ cudaError_t launch_batch(const BatchLaunch& L, cudaStream_t st) {
     int nsplit = (L.sms / 2) / nqp;
     if (nsplit < 1) nsplit = 1;
     if (nsplit > L.tiles) nsplit = (int)L.tiles;
-    e = launch_pdl(pick_gemm_pair(L.half, L.cosine, L.group), dim3(2 * nqp * nsplit), dim3(BQ_THREADS), L.pair_smem, st,
+    e = launch_pdl(pick_gemm_pair(L.pair_stat, L.half, L.cosine, L.group), dim3(2 * nqp * nsplit), dim3(BQ_THREADS), L.pair_smem, st,
                    tmQ, tmX, L.coef, L.qinv, L.n, num_kb, L.pair_stages, nqp, L.tiles, L.gm, L.gm_stride);
     if (e != cudaSuccess) return e;
   } else {

@@ -106,6 +106,7 @@ struct BatchLaunch {
   int32_t* counts_out;
   int64_t id_base;
   int64_t out_stride;
+  int select_ctas_override;  // 0 = choose the selection CTAs per query from the batch size
   int group_override;    // 0 = choose the rows per nomination group (16 / 32 / 64) from the shape
   bool gemm_only;        // diagnostics: stop after the group minima
   int warp_min_q;        // chunks of at least this many queries select with one warp per query (k <= 32)
@@ -116,14 +117,16 @@ struct BatchLaunch {
   size_t gemm_smem, select_smem, selw_smem, fb_smem;
   bool gemm_stat;        // query block resident in shared memory (short vectors)
   int gemm_stages;
-  int pair_stages;       // > 0: the cta_group::2 kernel fits (resident query block per CTA)
+  int pair_stages;       // stages of the cta_group::2 kernel
+  bool pair_stat;        // ... with the query block resident per CTA (else both operands stream)
   size_t pair_smem;
 };
 bool batch_supported(int d, int lanes, bool cosine, int64_t n);
 double batch_slack_host(bool cosine, bool half, int d, double xmax, double qn);
 bool batch_encode_segment_map(void* tm128, const void* rows, int64_t n, int d, int64_t pitch, bool half, int box_rows);
 cudaError_t launch_row_convert(const float* X, int64_t n, int d, int dp, float sx, void* Xh, int sms, cudaStream_t st);
-bool batch_configure(BatchLaunch& L, int sms);          // from (n, d, lanes, cosine, k, half)
+bool batch_configure(BatchLaunch& L, int sms);
+int batch_set_prefetch_rounds(int rounds);  // diagnostics: rounds of 8 rows the pre-filter prefetches ahead (-1: none)          // from (n, d, lanes, cosine, k, half)
 int64_t batch_partial_keys(const BatchLaunch& L, int nq);  // keys of `partial` per query for a chunk of nq
 cudaError_t launch_batch(const BatchLaunch& L, cudaStream_t st);  // one chunk of L.nq queries
 
