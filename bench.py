@@ -97,6 +97,14 @@ def measured_tensor_peak() -> tuple[float, str]:
     return 1670.0, "fallback (B200_PROFILING.md dense bf16)"
 
 
+def sustained_tensor_peak():
+    """The same GEMM back to back for seconds (MEASURED_PEAKS.json bf16_tflops_sustained) or None."""
+    try:
+        return float(json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["bf16_tflops_sustained"])
+    except Exception:
+        return None
+
+
 # ---------------------------------------------------------------------------------------------------
 # clocks: sampled DURING the timed regions with NVML (the thread runs for the whole process; only
 # samples taken while a region is open are kept, so opening a region costs nothing on the host)
@@ -682,24 +690,32 @@ def bench_c4(ctx, K, W):
         ctx["barrier"]()
         return ctx["max_over_ranks"](e0.elapsed_time(e1)) / (steps * nq_per_step)
 
-    ms = run(1, K)
-    ms_b8 = run(8, max(4, K // 4))
-    ms_b32 = run(32, max(4, K // 8))
-    # the ADC scan alone on this rank's codes (LUT build + fast scan + conditional fallback launch), for its roofline
+    # the ADC scan alone on this rank's codes (LUT build + fast scan + conditional fallback launch), for its roofline:
+    # once before the sustained runs (after a short idle: the board's state for a kernel timed alone) and once after
     ids100 = torch.empty((1, C4_NCAND), dtype=torch.int64, device=dev)
     ap100 = torch.empty((1, C4_NCAND), dtype=torch.float64, device=dev)
     cn = torch.empty((1,), dtype=torch.int32, device=dev)
     st = stream.cuda_stream
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for i in range(3):
-        L.check(lib.vs_adc_topk_dev(seg.handle, q_dev[i].data_ptr(), 1, C4_NCAND, ids100.data_ptr(), ap100.data_ptr(), cn.data_ptr(), st))
-    e0.record()
-    for i in range(K):
-        L.check(lib.vs_adc_topk_dev(seg.handle, q_dev[W + i].data_ptr(), 1, C4_NCAND, ids100.data_ptr(),
-                                    ap100.data_ptr(), cn.data_ptr(), st))
-    e1.record()
+
+    def adc_alone():
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for i in range(3):
+            L.check(lib.vs_adc_topk_dev(seg.handle, q_dev[i].data_ptr(), 1, C4_NCAND, ids100.data_ptr(), ap100.data_ptr(), cn.data_ptr(), st))
+        e0.record()
+        for i in range(K):
+            L.check(lib.vs_adc_topk_dev(seg.handle, q_dev[W + i].data_ptr(), 1, C4_NCAND, ids100.data_ptr(),
+                                        ap100.data_ptr(), cn.data_ptr(), st))
+        e1.record()
+        torch.cuda.synchronize()
+        return ctx["max_over_ranks"](e0.elapsed_time(e1) / K)
+
     torch.cuda.synchronize()
-    ms_adc = ctx["max_over_ranks"](e0.elapsed_time(e1) / K)
+    time.sleep(2.0)
+    ms_adc = adc_alone()
+    ms = run(1, K)
+    ms_b8 = run(8, max(4, K // 4))
+    ms_b32 = run(32, max(4, K // 8))
+    ms_adc_loaded = adc_alone()
     gbs = n * PQ_M / (ms_adc * 1e-3) / 1e9
     # end to end through the host API: query from host memory in, ids + scores out, every query
     call = (lambda q: sh.adc_rerank_topk(q, C4_NCAND, TOPK)) if world > 1 else (lambda q: seg.adc_rerank_topk(q, C4_NCAND, TOPK))
@@ -722,7 +738,10 @@ def bench_c4(ctx, K, W):
                    "d2h_bytes_per_step": TOPK * 16 + 4},
            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
                         "kernel": "build_lut_mm + adc_fastscan_kernel<4> (K5+K6), one rank's codes, launched alone",
-                        "ms_per_launch_group": ms_adc, "algorithmic_bytes_per_launch": n * PQ_M,
+                        "ms_per_launch_group": ms_adc, "ms_per_launch_group_after_sustained_load": ms_adc_loaded,
+                        "algorithmic_bytes_per_launch": n * PQ_M,
+                        "note": "timed alone after 2 s of idle; the same loop right after the sustained runs is slower "
+                                "(the board stays in a lower clock state for seconds after ~50 ms of full load)",
                         "achieved_in_step": n * PQ_M / (ms * 1e-3) / 1e9, "traffic": traffic, "traffic_source": traffic_src},
            "generate_s": t_gen, "train_1M_5iters_s": t_train, "train_1M_5iters_cold_s": t_train_cold,
            "encode_s": t_enc, "encode_cold_s": t_enc_cold, "encode_vectors_per_s": n_total / t_enc,
@@ -780,6 +799,8 @@ def bench_c5(ctx, K, W):
            "e2e": {"ms_per_batch": e2e_ms, "qps": nq / (e2e_ms * 1e-3), "h2d_bytes_per_step": nq * d * 4, "d2h_bytes_per_step": nq * (k * 16 + 4)},
            "roofline": {"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak, "peak_source": tsrc,
                         "algorithmic_flops_per_batch_per_gpu": flops,
+                        "peak_sustained": sustained_tensor_peak(),
+                        "frac_of_sustained": (tf / sustained_tensor_peak()) if sustained_tensor_peak() else None,
                         "hbm_view": {"algorithmic_bytes_per_batch_per_gpu": n * d * 4, "achieved_GBs": n * d * 4 / (ms * 1e-3) / 1e9,
                                      "frac_of_measured_peak": n * d * 4 / (ms * 1e-3) / 1e9 / ctx["hbm_peak"]},
                         "kernel": "batch_gemm_pair_kernel<streaming operands, HALF, COSINE> (K2 on CTA pairs, tcgen05 cta_group::2) + batch_select "
