@@ -327,7 +327,8 @@ int64_t vs_kernel_launch_count(void);
  * the per-query scan; "batch_fp16" (default 1): nominate on an fp16 operand copy of the rows (n * d * 2
  * bytes of HBM, made at the first batched query) instead of the fp32 rows read as tf32; "batch_group"
  * (0 = automatic, 16 / 32 / 64): rows per nomination group; "batch_gm_bytes": scratch per query chunk;
- * "batch_warp_min_queries" (0 = automatic); "batch_pairs": whether batches of more than 128 queries nominate on
+ * "batch_warp_min_queries" (default 0 = never): batches of at least that many queries select with one warp
+ * per query instead of a CTA per query; "batch_pairs": whether batches of more than 128 queries nominate on
  * CTA pairs (tcgen05 cta_group::2) -- 0 never, 1 wherever it fits, 2 (default) for long vectors only, where both
  * operands stream through shared memory; "batch_select_ctas" (0 = automatic) and "batch_prefetch_rounds"
  * (default 1, this device only): diagnostics of the selection kernel.  "scan_reserve_sms": SMs the one-query scan leaves free so that
