@@ -1006,3 +1006,45 @@ def test_c2_full_size_l2_top10(vs, oracle):
         assert ids2[0] == 123456 and sc2[0] == 0.0 and np.all(np.diff(sc2) <= 0)
     finally:
         seg.free()
+
+
+@pytest.mark.gpu
+def test_scratch_slots_survive_destroyed_communicator_streams(vs, oracle):
+    """A host thread keeps one scratch set per stream it has worked on (four at most).  Communicators own a stream
+    each; creating, using and destroying more of them than there are slots must not leave a slot keyed by a dead
+    stream behind (the recycling path synchronises the slot's stream)."""
+    import ctypes as C
+
+    from vectorsearch_b200 import _lib as L
+
+    lib = vs.load()
+    n, d, k, nq = 20011, 32, 5, 3
+    rows = oracle.gen_rows(42, 0, n, d)
+    qs = oracle.gen_rows(43, 0, nq, d)
+    seg = vs.Segment.upload(rows)
+    try:
+        want = [oracle.bruteforce_topk(rows, qs[i], k)[0] for i in range(nq)]
+        for rep in range(7):
+            comm, hd = C.c_uint64(0), (C.c_uint8 * 64)()
+            L.check(lib.vs_peer_create(0, 1, 1 << 16, 4, C.byref(comm), hd))
+            try:
+                bases = (C.c_uint64 * 1)()
+                b = C.c_uint64(0)
+                L.check(lib.vs_peer_base(comm.value, C.byref(b)))
+                bases[0] = b.value
+                L.check(lib.vs_peer_connect_ptrs(comm.value, bases))
+                ids = np.zeros((nq, k), np.int64)
+                sc = np.zeros((nq, k), np.float64)
+                cn = np.zeros(nq, np.int32)
+                L.check(lib.vs_bruteforce_topk_exchange(seg.handle, comm.value, qs.ctypes.data_as(L.f32p), nq, k, 0,
+                                                        ids.ctypes.data_as(L.i64p), sc.ctypes.data_as(L.f64p),
+                                                        cn.ctypes.data_as(L.i32p)))
+                for i in range(nq):
+                    assert np.array_equal(ids[i], want[i])
+            finally:
+                lib.vs_peer_destroy(comm.value)
+            got = seg.bruteforce_topk(qs, k, 0)   # the thread's own stream in between
+            for i in range(nq):
+                assert np.array_equal(np.asarray(got[0])[i], want[i])
+    finally:
+        seg.free()

@@ -162,7 +162,7 @@ static int ctx_use_stream(ThreadCtx* c, void* stream) {
   if (free_slot < 0) {  // recycle a caller-stream slot (never slot 0, the thread's own stream)
     free_slot = 1 + (c->active >= 1 ? c->active % (ThreadCtx::MAX_SLOTS - 1) : 0);
     cudaError_t e = cudaStreamSynchronize(static_cast<cudaStream_t>(c->slots[free_slot].key));
-    if (e == cudaErrorInvalidResourceHandle || e == cudaErrorContextIsDestroyed) {
+    if (e == cudaErrorInvalidResourceHandle || e == cudaErrorContextIsDestroyed || e == cudaErrorDeviceUninitialized) {
       // the caller has destroyed that stream since: its work is done or abandoned; drain the device instead
       cudaGetLastError();
       e = cudaDeviceSynchronize();
@@ -173,6 +173,24 @@ static int ctx_use_stream(ThreadCtx* c, void* stream) {
   c->slots[free_slot].key = stream;
   c->activate(free_slot);
   return VS_OK;
+}
+
+// A stream the library owns is about to be destroyed: the calling thread's scratch sets must not keep it as a key
+// (a recycled slot would otherwise synchronise a dead handle).  The device has been drained by the caller.
+static void ctx_forget_stream(int dev, void* stream) {
+  if (dev < 0 || dev >= VS_MAX_DEVICES) return;
+  ThreadCtx& c = t_ctxs[dev];
+  if (c.device != dev) return;
+  for (int i = 1; i < ThreadCtx::MAX_SLOTS; i++) {
+    if (c.slots[i].used && c.slots[i].key == stream) {
+      if (c.active == i) {
+        c.park();
+        c.activate(0);
+      }
+      c.slots[i].key = nullptr;  // keeps its buffers; the next new stream takes the slot over
+      c.slots[i].used = false;
+    }
+  }
 }
 
 static int ctx_bind_dev(ThreadCtx** out, int dev) {
@@ -2315,8 +2333,14 @@ int32_t vs_peer_destroy(uint64_t comm) {
   if (pc->x_dev) cudaFree(pc->x_dev);
   if (pc->x_host) cudaFreeHost(pc->x_host);
   for (unsigned char* hp : pc->x_host_parked) cudaFreeHost(hp);
-  if (pc->xstream) cudaStreamDestroy(pc->xstream);
-  if (pc->pstream) cudaStreamDestroy(pc->pstream);
+  if (pc->xstream) {
+    ctx_forget_stream(pc->device, pc->xstream);
+    cudaStreamDestroy(pc->xstream);
+  }
+  if (pc->pstream) {
+    ctx_forget_stream(pc->device, pc->pstream);
+    cudaStreamDestroy(pc->pstream);
+  }
   if (pc->h_flags) cudaFreeHost(pc->h_flags);
   for (auto& rp : pc->ring_packs) cudaFree(rp.p);
   delete pc;
