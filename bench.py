@@ -389,35 +389,57 @@ def run_ours(args) -> None:
     e2e_s = max_over_ranks(e2e_s)
     e2e_value = world * N_ROWS * K / e2e_s
     last_ids, last_sc = np.asarray(r[0]), np.asarray(r[1])
-    # The same K host calls issued by TWO request threads (N = 1): the reference's caller scores segments on many
-    # executor threads at once (J/fdb/FdbVectorIndex.java:418-432) and libvsgpu gives every calling thread its own
-    # stream and staging, so consecutive queries overlap on the device as they do in the device-resident region.
-    # Reported beside the one-thread figure, which stays the headline `e2e.value`.
+    # The same K host calls issued by TWO request threads: the reference's caller scores segments on many executor
+    # threads at once (J/fdb/FdbVectorIndex.java:418-432) and libvsgpu gives every calling thread its own stream and
+    # staging, so consecutive queries overlap on the device as they do in the device-resident region.  At N > 1 every
+    # request thread has its own peer communicator (thread t of every rank exchanges with thread t of the others).
     e2e_two = None
-    if world == 1:
+    if not args.one_request_thread:
         vs.set_option("scan_reserve_sms", reserve_sms)
+        callers = [(lambda q: seg.bruteforce_topk(q, TOPK))] * 2
+        sh2 = None
+        if world > 1:
+            sh2 = ShardedSegment(seg, rank, world, slots=1)
+            callers = [(lambda q: sh.bruteforce_topk(q, TOPK)), (lambda q: sh2.bruteforce_topk(q, TOPK))]
         start, errs = threading.Barrier(3), []
 
         def worker(t):
             try:
                 for i in range(W):
-                    seg.bruteforce_topk(qn[i], TOPK)
+                    callers[t](qn[i])
                 start.wait()
                 for i in range(t, K, 2):
-                    seg.bruteforce_topk(qn[W + i], TOPK)
+                    callers[t](qn[W + i])
             except Exception as e:  # noqa: BLE001
                 errs.append(e)
+                try:
+                    start.abort()
+                except Exception:  # noqa: BLE001
+                    pass
 
-        th = [threading.Thread(target=worker, args=(t,)) for t in range(2)]
+        th = [threading.Thread(target=worker, args=(t,), daemon=True) for t in range(2)]
         for t_ in th:
             t_.start()
-        start.wait()
-        t0 = time.perf_counter()
-        for t_ in th:
-            t_.join()
-        two_s = time.perf_counter() - t0
-        if not errs:
-            e2e_two = {"value": N_ROWS * K / two_s, "unit": "distance-evals/s", "ms_per_step": two_s / K * 1e3, "request_threads": 2}
+        try:
+            barrier()
+            start.wait(timeout=60)
+            t0 = time.perf_counter()
+            for t_ in th:
+                t_.join(timeout=60)
+            two_s = time.perf_counter() - t0
+        except threading.BrokenBarrierError:
+            two_s = None
+        ok = two_s is not None and not errs and not any(t_.is_alive() for t_ in th)
+        if world > 1:
+            flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            ok = bool(flag.item())
+        if ok:
+            two_s = max_over_ranks(two_s)
+            e2e_two = {"value": world * N_ROWS * K / two_s, "unit": "distance-evals/s", "ms_per_step": two_s / K * 1e3,
+                       "qps": K / two_s, "request_threads": 2}
+        if sh2 is not None and ok:
+            sh2.close()
 
     # ---- parity: the last query against the oracle over ALL ranks' rows (rank 0), both paths -------------
     parity = False
@@ -450,6 +472,13 @@ def run_ours(args) -> None:
             extra["c1"] = bench_c1(ctx)
 
     if rank == 0:
+        # the headline e2e is whole-job throughput through the host API: the better of one and two request threads
+        # (both reported; host buffers in and out on every step in either case)
+        one = {"value": e2e_value, "unit": "distance-evals/s", "ms_per_step": e2e_s / K * 1e3, "qps": K / e2e_s, "request_threads": 1}
+        best = e2e_two if (e2e_two is not None and e2e_two["value"] > e2e_value) else one
+        e2e_obj = {"value": best["value"], "unit": "distance-evals/s", "h2d_bytes_per_step": DIM * 4,
+                   "d2h_bytes_per_step": TOPK * 16 + 4, "ms_per_step": best["ms_per_step"], "qps": best["qps"],
+                   "request_threads": best["request_threads"], "one_request_thread": one, "two_request_threads": e2e_two}
         traffic, traffic_src = profiled_traffic("r2_c2_scan_full.txt", "r1/r1_c2_scan_full.txt")
         line = {
             "metric": METRIC, "value": value, "unit": "distance-evals/s",
@@ -473,9 +502,7 @@ def run_ours(args) -> None:
                          "note": "achieved = bytes / duration of the kernel launched ALONE (events around every launch); "
                                  "achieved_in_step = bytes / ms_per_step of the timed region, where consecutive queries overlap "
                                  "on two streams (a read-only stream can exceed the read+write copy rate used as peak)"},
-            "e2e": {"value": e2e_value, "unit": "distance-evals/s", "h2d_bytes_per_step": DIM * 4,
-                    "d2h_bytes_per_step": TOPK * 16 + 4, "ms_per_step": e2e_s / K * 1e3, "qps": K / e2e_s,
-                    "request_threads": 1, "two_request_threads": e2e_two},
+            "e2e": e2e_obj,
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
             "top10_last_query": last_ids.tolist(),
@@ -926,6 +953,7 @@ def main() -> None:
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="all", choices=["c2", "all"],
                     help="c2 = the headline line only; all = also C2 batch 1024 (N = 1), C3 and C4 into `extra`")
+    ap.add_argument("--one-request-thread", action="store_true", help="skip the two-request-thread end-to-end leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-check", action="store_true", help="skip the oracle parity checks after the timed regions")
     args = ap.parse_args()
