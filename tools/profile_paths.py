@@ -1,6 +1,6 @@
 """One hot path per invocation, a handful of launches: what `ncu` captures for the profiles/ summaries.
 
-    python tools/profile_paths.py scan|adc|batch|pq|rerank|knn|exchange
+    python tools/profile_paths.py scan|adc|batch|batch768|pq|rerank|knn|exchange
 
 scan: C2 (1M x 128, one query); adc: C4 ADC top-100 over VS_ROWS rows (default 100M) + re-rank; batch: C2 query batch
 1024; pq: encode of 10M x 128; knn: graph lists of a 20k x 128 segment; exchange: three ranks on this GPU
@@ -51,6 +51,14 @@ elif which == "batch":
     cn = torch.empty((1024,), dtype=torch.int32, device=dev)
     for i in range(4):
         L.check(lib.vs_bruteforce_topk_dev(seg.handle, q.data_ptr(), 1024, 10, 0, ids.data_ptr(), sc.data_ptr(), cn.data_ptr(), st))
+    torch.cuda.synchronize()
+elif which == "batch768":   # C5's per-GPU shape: 6.25M x 768, cosine top-50, 256 queries
+    seg = vs.Segment.generate(42, 0, 6_250_000, 768)
+    q = torch.from_numpy(rng.random((256, 768), dtype=np.float32) * 2 - 1).to(dev)
+    ids = torch.empty((256, 50), dtype=torch.int64, device=dev); sc = torch.empty((256, 50), dtype=torch.float64, device=dev)
+    cn = torch.empty((256,), dtype=torch.int32, device=dev)
+    for i in range(4):
+        L.check(lib.vs_bruteforce_topk_dev(seg.handle, q.data_ptr(), 256, 50, 1, ids.data_ptr(), sc.data_ptr(), cn.data_ptr(), st))
     torch.cuda.synchronize()
 elif which == "pq":
     seg = vs.Segment.generate(42, 0, 10_000_000, 128)
