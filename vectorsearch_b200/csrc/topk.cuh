@@ -359,6 +359,19 @@ static __device__ __noinline__ bool topk_epilogue(WarpTopKReg& tk, ulonglong2* s
   __threadfence();
   phase_stamp(6);
   const int nl = gridDim.x;  // <= TOPK_MAX_LISTS (host guarantees)
+  const int total = nl * k;
+  // every published key is requested now (up to PRE per thread, in registers) so that the filter below does not
+  // start a second round trip to L2 after the bound is known
+  constexpr int PRE = 8;
+  ulonglong2 pre[PRE];
+  const bool cached = total <= PRE * (int)blockDim.x;
+  if (cached) {
+#pragma unroll
+    for (int i = 0; i < PRE; i++) {
+      const int idx = threadIdx.x + i * blockDim.x;
+      pre[i] = idx < total ? __ldcg(all + idx) : make_ulonglong2(KEY_EMPTY64, KEY_EMPTY64);
+    }
+  }
   for (int i = threadIdx.x; i < nl; i += blockDim.x) surv[i] = __ldcg(all + (size_t)i * k);
   if (threadIdx.x < k) st_key(outk + threadIdx.x, key_empty());
   __syncthreads();
@@ -375,13 +388,23 @@ static __device__ __noinline__ bool topk_epilogue(WarpTopKReg& tk, ulonglong2* s
   const Key B = ld_key(&s_bound);
   phase_stamp(2);
   __syncthreads();  // heads are dead from here on: surv is reused for the survivors
-  const int total = nl * k;
-  for (int i = threadIdx.x; i < total; i += blockDim.x) {
-    const ulonglong2 v = __ldcg(all + i);
-    const Key x{v.x, v.y};
-    if (!key_is_empty(x) && !key_lt(B, x)) {
-      const int slot = atomicAdd(&s_cnt, 1);
-      st_key(surv + slot, x);  // at most k lists reach below the bound: slot < k*k
+  if (cached) {
+#pragma unroll
+    for (int i = 0; i < PRE; i++) {
+      const Key x{pre[i].x, pre[i].y};
+      if (!key_is_empty(x) && !key_lt(B, x)) {
+        const int slot = atomicAdd(&s_cnt, 1);
+        st_key(surv + slot, x);  // at most k lists reach below the bound: slot < k*k
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+      const ulonglong2 v = __ldcg(all + i);
+      const Key x{v.x, v.y};
+      if (!key_is_empty(x) && !key_lt(B, x)) {
+        const int slot = atomicAdd(&s_cnt, 1);
+        st_key(surv + slot, x);
+      }
     }
   }
   __syncthreads();
