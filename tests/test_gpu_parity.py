@@ -1048,3 +1048,87 @@ def test_scratch_slots_survive_destroyed_communicator_streams(vs, oracle):
                 assert np.array_equal(np.asarray(got[0])[i], want[i])
     finally:
         seg.free()
+
+
+# ---- one or two queries: nomination on the fp16 copy (scan_half_kernel, batch.cu) ----------------------------------------
+@pytest.fixture
+def force_half_scan(vs):
+    """Route single queries (and pairs) of every segment size through the fp16-copy scan."""
+    vs.set_option("batch_min_rows", 1)
+    vs.set_option("scan_fp16", 1)
+    yield
+    vs.set_option("batch_min_rows", 16384)
+
+
+def _launches(vs):
+    return vs.kernel_launch_count()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("metric", [0, 1])
+@pytest.mark.parametrize("n,d,k,nq", [(40000, 128, 10, 1), (20000, 768, 32, 2), (9000, 72, 10, 1), (6000, 100, 16, 2),
+                                      (300, 32, 1, 1), (7, 128, 10, 2), (70001, 64, 17, 1), (33003, 128, 5, 2),
+                                      (50000, 256, 10, 1), (2500, 128, 50, 1)])
+def test_half_scan_matches_oracle(vs, oracle, force_half_scan, n, d, k, nq, metric):
+    rows = oracle.gen_rows(42, 0, n, d)
+    qs = oracle.gen_rows(43, 0, nq, d)
+    _check_batch(vs, oracle, rows, qs, k, metric)
+    _check_batch(vs, oracle, rows, qs[:1].ravel().reshape(1, d), k, metric, id_base=123_456_789_012)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("metric", [0, 1])
+def test_half_scan_ties_clusters_skip_and_fallbacks(vs, oracle, force_half_scan, metric):
+    n, d = 60000, 64
+    rows = oracle.gen_rows(11, 0, n, d)
+    rows[100:400] = rows[7]           # 300 exact duplicates side by side: full lists inside the band -> exact fallback
+    rows[20000] = rows[7]
+    rows[9] = 0.0                     # zero norm: cosine 0.0
+    rows[5000:5004] *= 3.0
+    qs = oracle.gen_rows(12, 0, 6, d)
+    qs[0] = rows[7]
+    qs[1] = 0.0                       # zero query
+    skip = np.zeros(n, np.uint8)
+    skip[[7, 101, 102, n - 1]] = 1
+    for i in range(0, 6, 2):          # two queries per call, then one
+        _check_batch(vs, oracle, rows, qs[i:i + 2], 10, metric)
+        _check_batch(vs, oracle, rows, qs[i:i + 1], 30, metric, skip=skip, id_base=1_000_000_007)
+    # a cluster of near neighbours stored contiguously (the rows closest to the query sit in ONE tile)
+    rows2 = rows.copy()
+    rows2[30000:30040] = qs[2] + 1e-3 * oracle.gen_rows(13, 0, 40, d)
+    _check_batch(vs, oracle, rows2, qs[2:3], 10, metric)
+    _check_batch(vs, oracle, rows2, qs[2:3], 32, metric)
+    # non-finite query -> exact scan; NaN / inf row -> the whole segment stays on the fp32 scan
+    qs2 = qs.copy()
+    qs2[3, 5] = np.nan
+    qs2[4, 0] = np.inf
+    _check_batch(vs, oracle, rows, qs2[3:5], 10, metric)
+    rows3 = rows.copy()
+    rows3[50, 3] = np.nan
+    rows3[3000, 0] = np.inf
+    _check_batch(vs, oracle, rows3, qs[:2], 10, metric)
+
+
+@pytest.mark.gpu
+def test_half_scan_is_the_path_taken_and_can_be_switched_off(vs, oracle):
+    """1M x 128, one query: by default the fp16-copy scan answers (query conversion + scan + fallback check = 3
+    launches); with scan_fp16 = 0 the fp32 streaming scan does (1 launch).  Same bits either way."""
+    seg = vs.Segment.generate(42, 0, 200_000, 128)
+    try:
+        q = oracle.gen_rows(43, 0, 3, 128)
+        seg.bruteforce_topk(q[0], 10)          # builds the copy
+        a0 = _launches(vs)
+        r_half = seg.bruteforce_topk(q[1], 10)
+        a1 = _launches(vs)
+        vs.set_option("scan_fp16", 0)
+        r_full = seg.bruteforce_topk(q[1], 10)
+        a2 = _launches(vs)
+        assert a1 - a0 == 2 and a2 - a1 == 1
+        assert np.array_equal(np.asarray(r_half[0]), np.asarray(r_full[0]))
+        assert np.array_equal(np.asarray(r_half[1]).view(np.uint64), np.asarray(r_full[1]).view(np.uint64))
+        rows = oracle.gen_rows(42, 0, 200_000, 128)
+        oi, os_, _ = oracle.bruteforce_topk(rows, q[1], 10, 0, threads=8)
+        assert np.array_equal(np.asarray(r_half[0]).ravel(), oi) and _same(np.asarray(r_half[1]).ravel(), os_)
+    finally:
+        vs.set_option("scan_fp16", 1)
+        seg.free()

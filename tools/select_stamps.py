@@ -27,6 +27,12 @@ lib.vs_debug_read_stamps_batch(buf.ctypes.data_as(C.c_void_p), buf.nbytes)
 s = buf.reshape(1024, 8)[:min(nq, 1024), :7].astype(np.int64)
 t0 = s[:, 0].min()
 names = ["start", "setup(q, slack)", "phase1 (T)", "phase2 (list)", "prefetch issued", "phase3 (exact)", "epilogue"]
+if nq <= 2:  # scan_half_kernel: CTA 0 records 0-3, the last CTA 4-7
+    s8 = buf.reshape(1024, 8)[:nq].astype(np.int64)
+    for qi in range(nq):
+        r = s8[qi] - s8[qi, 0]
+        print("query", qi, " ".join(f"{nm} {x/1e3:.2f}" for nm, x in zip(["start", "query staged", "loop done (CTA 0)", "published (CTA 0)", "last CTA begins", "candidates", "scored", "end"], r)))
+    sys.exit(0)
 print("kernel span: %.1f us; CTA start spread: %.1f us" % ((s[:, 6].max() - t0) / 1e3, (s[:, 0].max() - t0) / 1e3))
 for i in range(1, 7):
     dt = (s[:, i] - s[:, i - 1]) / 1e3

@@ -49,6 +49,7 @@ static std::atomic<int64_t> g_scan_reserve_sms{0};          // SMs the one-query
 static std::atomic<int64_t> g_batch_pairs{2};
 static std::atomic<int64_t> g_batch_prefilter{1};           // candidate groups are pre-filtered on the fp16 copy before exact scoring
 static std::atomic<int64_t> g_pdl{1};                       // programmatic dependent launch between the kernels of one call
+static std::atomic<int64_t> g_scan_fp16{1};                 // 1: single queries nominate on the fp16 copy (half the bytes), 0: fp32 scan
 static std::atomic<int64_t> g_batch_select_ctas{0};         // 0 = automatic selection CTAs per query, else 1..64 (diagnostics)
 static std::atomic<int64_t> g_batch_group{0};               // 0 = automatic rows per nomination group, else 16 / 32 / 64
 static std::atomic<int64_t> g_batch_fp16{1};                // nominate on fp16 operand copies (0: the fp32 rows as tf32)
@@ -529,9 +530,12 @@ static int rerank_dev(cudaStream_t st, const Segment* s, const float* d_q, int n
 // ---- batched-query brute force (batch.cu) ---------------------------------------------------------------
 static std::unordered_map<uint64_t, BatchLaunch> g_batch_cache;
 
-static bool batch_wanted(const Segment* s, int nq, bool cosine) {
-  return nq >= g_batch_min_queries.load() && s->n >= g_batch_min_rows.load() &&
-         batch_supported(s->d, lanes(), cosine, s->n);
+// 0: per-query fp32 scan (scan.cu); 1: tensor-core nomination (query batches); 2: the CUDA-core scan of the fp16 copy
+// for the one or two queries below the batch threshold (option "scan_fp16")
+static int batch_wanted(const Segment* s, int nq, bool cosine) {
+  if (s->n < g_batch_min_rows.load() || !batch_supported(s->d, lanes(), cosine, s->n)) return 0;
+  if (nq >= g_batch_min_queries.load()) return 1;
+  return g_scan_fp16.load() != 0 && g_batch_fp16.load() != 0 ? 2 : 0;
 }
 
 static int plan_batch(const Segment* s, int k, bool cosine, bool half, BatchLaunch* out) {
@@ -648,7 +652,7 @@ static size_t batch_scratch_need(const BatchLaunch& p, int nq) {
 // everything on `st`, no synchronisation; scratch = batch_scratch_need bytes, tickets for one chunk reserved
 static int batch_run_dev(cudaStream_t st, const Segment* s, const BatchLaunch& p, bool cosine, const float* d_q, int nq,
                          int64_t* d_ids, double* d_scores, int32_t* d_counts, int64_t out_stride, void* scratch,
-                         unsigned long long* d_ticket) {
+                         unsigned long long* d_ticket, bool direct = false) {
   const int m = cosine ? 1 : 0;
   const int chunk = batch_chunk(p, nq);
   const int64_t os = out_stride > 0 ? out_stride : p.k;
@@ -660,6 +664,7 @@ static int batch_run_dev(cudaStream_t st, const Segment* s, const BatchLaunch& p
     L.tmX = p.half ? s->tmXh : s->tmX; L.tmX128 = p.half ? s->tmXh_b128 : s->tmX_b128; L.x_scale = s->x_scale;
     L.pairs = g_batch_pairs.load() == 1 || (g_batch_pairs.load() == 2 && !p.pair_stat);
     L.xh = s->Xh; L.prefilter = g_batch_prefilter.load() != 0;
+    L.direct = direct; L.reserve_sms = (int)g_scan_reserve_sms.load();
     L.coef = static_cast<const float*>(s->ab[m]); L.stats = static_cast<const SegStats*>(s->stats[m]);
     L.gm = A.take<float>((size_t)((chunk + 255) / 256 * 256) * p.gm_stride);
     L.fb = A.take<int32_t>(1 + 2 * (size_t)chunk);
@@ -832,6 +837,10 @@ int32_t vs_set_option(const char* name, int64_t value) {
   if (!strcmp(name, "batch_prefetch_rounds")) {  // this device only (diagnostics)
     if (value < -1 || value > 64) return fail(VS_EINVAL, "batch_prefetch_rounds must be -1 .. 64");
     CK(cudaError_t(batch_set_prefetch_rounds((int)value)), "batch_prefetch_rounds");
+    return VS_OK;
+  }
+  if (!strcmp(name, "scan_fp16")) {
+    g_scan_fp16.store(value != 0);
     return VS_OK;
   }
   if (!strcmp(name, "batch_select_ctas")) {
@@ -1345,12 +1354,14 @@ int32_t vs_bruteforce_topk(uint64_t h, const float* q, int32_t nq, int32_t k, in
     return VS_OK;
   }
   const bool cosine = metric == VS_METRIC_COSINE;
-  if (batch_wanted(s, nq, cosine)) {  // tensor-core nomination + exact re-score (batch.cu)
+  const int bmode = batch_wanted(s, nq, cosine);
+  if (bmode != 0) {  // nomination on tensor cores (batches) or on the fp16 copy (one or two queries) + exact re-score (batch.cu)
     bool ok = false, half = false;
     RET(batch_prepare(c->stream, s, cosine, &ok, &half));
+    BatchLaunch bp;
+    if (ok) RET(plan_batch(s, k, cosine, half, &bp));
+    if (ok && bmode == 2 && !(half && bp.sh_ok)) ok = false;
     if (ok) {
-      BatchLaunch bp;
-      RET(plan_batch(s, k, cosine, half, &bp));
       int64_t hg = (int64_t(32) << 20) / ((int64_t)s->d * 4);  // queries per host staging group
       if (hg < 128) hg = 128;
       if (hg > nq) hg = nq;
@@ -1374,10 +1385,15 @@ int32_t vs_bruteforce_topk(uint64_t h, const float* q, int32_t nq, int32_t k, in
         int32_t* hcn = H.take<int32_t>(group);
         memcpy(hq, q + (size_t)q0 * s->d, (size_t)g * s->d * 4);
         CK(cudaMemcpyAsync(dq, hq, (size_t)g * s->d * 4, cudaMemcpyHostToDevice, c->stream), "H2D q");
-        RET(batch_run_dev(c->stream, s, bp, cosine, dq, g, dids, dsc, dcn, 0, scratch, c->d_ticket));
-        CK(cudaMemcpyAsync(hids, dids, (size_t)g * k * 8, cudaMemcpyDeviceToHost, c->stream), "D2H ids");
-        CK(cudaMemcpyAsync(hsc, dsc, (size_t)g * k * 8, cudaMemcpyDeviceToHost, c->stream), "D2H scores");
-        CK(cudaMemcpyAsync(hcn, dcn, (size_t)g * 4, cudaMemcpyDeviceToHost, c->stream), "D2H counts");
+        if ((size_t)g * k <= 4096) {
+          // short result lists: written straight into the pinned staging buffer (device-visible under UVA)
+          RET(batch_run_dev(c->stream, s, bp, cosine, dq, g, hids, hsc, hcn, 0, scratch, c->d_ticket, bmode == 2));
+        } else {
+          RET(batch_run_dev(c->stream, s, bp, cosine, dq, g, dids, dsc, dcn, 0, scratch, c->d_ticket, bmode == 2));
+          CK(cudaMemcpyAsync(hids, dids, (size_t)g * k * 8, cudaMemcpyDeviceToHost, c->stream), "D2H ids");
+          CK(cudaMemcpyAsync(hsc, dsc, (size_t)g * k * 8, cudaMemcpyDeviceToHost, c->stream), "D2H scores");
+          CK(cudaMemcpyAsync(hcn, dcn, (size_t)g * 4, cudaMemcpyDeviceToHost, c->stream), "D2H counts");
+        }
         CK(cudaStreamSynchronize(c->stream), "sync");
         memcpy(ids_out + (size_t)q0 * k, hids, (size_t)g * k * 8);
         memcpy(scores_out + (size_t)q0 * k, hsc, (size_t)g * k * 8);
@@ -1928,12 +1944,14 @@ static int batch_try_dev(ThreadCtx* c, cudaStream_t st, Segment* s, const float*
                          int64_t* d_ids, double* d_scores, int32_t* d_counts, int64_t out_stride, bool* done) {
   *done = false;
   const bool cosine = metric == VS_METRIC_COSINE;
-  if (!batch_wanted(s, nq, cosine)) return VS_OK;
+  const int mode = batch_wanted(s, nq, cosine);
+  if (mode == 0) return VS_OK;
   bool ok = false, half = false;
   RET(batch_prepare(st, s, cosine, &ok, &half));
   if (!ok) return VS_OK;
   BatchLaunch bp;
   RET(plan_batch(s, k, cosine, half, &bp));
+  if (mode == 2 && !(half && bp.sh_ok)) return VS_OK;
   const size_t sb = batch_scratch_need(bp, nq);
   const int chunk = batch_chunk(bp, nq);
   const bool grow = Arena::need({sb}) > c->d_cap || (size_t)chunk > c->ticket_cap;
@@ -1941,7 +1959,7 @@ static int batch_try_dev(ThreadCtx* c, cudaStream_t st, Segment* s, const float*
   RET(ctx_reserve_ticket(c, chunk));
   if (grow) CK(cudaStreamSynchronize(c->stream), "sync");  // ticket memset ran on c->stream
   Arena A(c->d_buf);
-  RET(batch_run_dev(st, s, bp, cosine, d_q, nq, d_ids, d_scores, d_counts, out_stride, A.take<char>(sb), c->d_ticket));
+  RET(batch_run_dev(st, s, bp, cosine, d_q, nq, d_ids, d_scores, d_counts, out_stride, A.take<char>(sb), c->d_ticket, mode == 2));
   *done = true;
   return VS_OK;
 }

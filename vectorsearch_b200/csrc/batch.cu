@@ -603,24 +603,6 @@ batch_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   }
 }
 
-// development-only phase timestamps of the selection kernel (build with -DVS_BQ_STAMPS; tools/select_stamps.py)
-#ifdef VS_BQ_STAMPS
-static __device__ unsigned long long g_bq_stamps[8 * 1024];
-__device__ __forceinline__ void bq_stamp(int ph) {
-  if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y < 1024) {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    g_bq_stamps[blockIdx.y * 8 + ph] = t;
-  }
-}
-int debug_read_stamps_batch(void* dst, size_t bytes) {
-  cudaDeviceSynchronize();
-  return (int)cudaMemcpyFromSymbol(dst, g_bq_stamps, bytes);
-}
-#else
-__device__ __forceinline__ void bq_stamp(int) {}
-#endif
-
 // ---- candidate groups: fp16 pre-filter, then exact scores ------------------------------------------------------------
 // A candidate group holds gsz rows of which one or two matter.  With the fp16 operand copy at hand the warp first
 // recomputes a(q, x) for the group's rows from that copy (half the bytes of the fp32 rows; exact products, fp32
@@ -806,6 +788,441 @@ __host__ __device__ __forceinline__ double batch_slack(bool cosine, bool half, i
 // fb = [count][nq query indices][nq flags]: list query qi once, whichever CTA asks first
 __device__ __forceinline__ void batch_list_fallback(int32_t* fb, int nq_total, int qi) {
   if (atomicExch(fb + 1 + nq_total + qi, 1) == 0) fb[1 + atomicAdd(fb, 1)] = qi;
+}
+
+// development-only phase timestamps of the selection kernel (build with -DVS_BQ_STAMPS; tools/select_stamps.py)
+#ifdef VS_BQ_STAMPS
+static __device__ unsigned long long g_bq_stamps[8 * 1024];
+__device__ __forceinline__ void bq_stamp(int ph) {
+  if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y < 1024) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    g_bq_stamps[blockIdx.y * 8 + ph] = t;
+  }
+}
+int debug_read_stamps_batch(void* dst, size_t bytes) {
+  cudaDeviceSynchronize();
+  return (int)cudaMemcpyFromSymbol(dst, g_bq_stamps, bytes);
+}
+__device__ __forceinline__ void bq_stamp_any(int ph) {  // whichever CTA runs this phase (the last CTA of a query)
+  if (threadIdx.x == 0 && blockIdx.y < 1024) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    g_bq_stamps[blockIdx.y * 8 + ph] = t;
+  }
+}
+#else
+__device__ __forceinline__ void bq_stamp(int) {}
+__device__ __forceinline__ void bq_stamp_any(int) {}
+#endif
+
+// ---- (2c) one or two queries: nomination by a CUDA-core scan of the fp16 copy -----------------------------------------
+// A single query cannot amortise the tensor-core tile, but it does not have to read the fp32 rows either: the same
+// a(q, x) the nomination GEMM produces is computed here from the fp16 operand copy (exact fp16 products, fp32 sums --
+// the slack of the batched path covers any summation order), i.e. from HALF the bytes scan.cu streams, and only the
+// rows that can be in the top-k are scored from the fp32 rows in the reference's arithmetic.
+//   * per warp: a private TMA ring over [TR rows of Xh | their TR coefficients], eight lanes per row (a quarter-warp
+//     reads 128 contiguous bytes of one row: no bank conflicts), four rows per step, the warp's KK smallest (a, row) in
+//     registers (one 64-bit key per lane, insertion by ballot + shuffle);
+//   * per CTA: the KK smallest of its warps' keys are published;
+//   * last CTA: B = k-th smallest list head (k distinct rows at or below it), tau = B + 2 * slack; every published key
+//     with a <= tau is a candidate and is scored exactly (one row per half-warp) into the register top-k of scan.cu.
+//     A row that a warp or a CTA dropped has a >= that CTA's KK-th key, so the result is complete iff every FULL list
+//     ends above tau; otherwise (rows of one cluster stored side by side, thousands of duplicates) the query goes to
+//     the exact fallback scan, like a candidate overflow of the batched selection.
+constexpr int SH_THREADS = 512;   // 16 warps when their rings fit (short vectors), else 8: the scan is latency-bound per warp
+constexpr int SH_MIN_THREADS = 256;
+constexpr int SH_CAND = 1024;  // candidate rows the last CTA can hold
+constexpr int SH_MAX_LISTS = 160;  // CTAs per query (published lists the last CTA takes)
+__device__ __forceinline__ uint32_t sh_ord(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float sh_unord(uint32_t o) { return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o); }
+// d0 += x.lo * q.lo, d1 += x.hi * q.hi for the two fp16 values packed in each word: fma.rn.f32.f16 (SASS FHFMA, with
+// .H0 / .H1 operand selectors) multiplies two fp16 values exactly and adds in fp32 with one rounding -- no conversion
+// instructions, one issue slot per element
+__device__ __forceinline__ void sh_fh2(float& d0, float& d1, uint32_t x, uint32_t q) {
+  asm("{\n.reg .b16 xl, xh, ql, qh;\nmov.b32 {xl, xh}, %2;\nmov.b32 {ql, qh}, %3;\n"
+      "fma.rn.f32.f16 %0, xl, ql, %0;\nfma.rn.f32.f16 %1, xh, qh, %1;\n}"
+      : "+f"(d0), "+f"(d1) : "r"(x), "r"(q));
+}
+__device__ __forceinline__ void sh_fh8(const uint4 v, const uint4 q, float& d0, float& d1) {
+  sh_fh2(d0, d1, v.x, q.x);
+  sh_fh2(d0, d1, v.y, q.y);
+  sh_fh2(d0, d1, v.z, q.z);
+  sh_fh2(d0, d1, v.w, q.w);
+}
+
+// CPL > 0: the lane's CPL 16-byte chunks of the scaled query live in registers (dp <= 64 * CPL); 0: in shared memory.
+template <bool COSINE, int KK, int CPL>
+__global__ void __launch_bounds__(SH_THREADS, 1)
+scan_half_kernel(const __half* __restrict__ Xh, int64_t n, int dp, const float* __restrict__ coef, float x_scale,
+                 const SegStats* __restrict__ stats, const float* __restrict__ X, int d, const float* __restrict__ Q,
+                 const uint8_t* __restrict__ skip, int lanes, int k, int TR, int NS, int32_t* __restrict__ fb, int nq_total,
+                 unsigned long long* __restrict__ pub, TopkOut out) {
+  extern __shared__ __align__(128) unsigned char shm[];
+  pdl_trigger();
+  bq_stamp(0);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int t = lane & 7, g = lane >> 3;
+  const int qi = blockIdx.y;
+  const uint32_t row_bytes = (uint32_t)dp * 2u;
+  const uint32_t rows_bytes = (uint32_t)TR * row_bytes;
+  const uint32_t stage_bytes = (rows_bytes + (uint32_t)TR * 4u + 127u) & ~127u;
+  unsigned char* ring = shm + (size_t)warp * NS * stage_bytes;
+  float* qf = reinterpret_cast<float*>(shm + (size_t)nw * NS * stage_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(qf + ((dp + 3) & ~3)) + warp * NS;
+  const float* __restrict__ q = Q + (size_t)qi * d;
+
+  if (lane == 0) {
+    for (int s = 0; s < NS; s++) mbar_init(bars + s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  const int64_t ntiles = (n + TR - 1) / TR;
+  const int64_t first = (int64_t)blockIdx.x * nw + warp, step = (int64_t)gridDim.x * nw;
+  const int64_t whole_tiles = n / TR;  // tiles below this index have all TR rows
+  // lane 0: rows (and, for a whole tile, coefficients) of `tile` into stage s.  Whole tiles -- all but the segment's last --
+  // take the short path: constant sizes, source addresses advanced by constants (the general form costs ~75
+  // instructions of 64-bit arithmetic per tile, a quarter of what scoring the tile's sixteen rows takes)
+  const uint32_t ring_u32 = smem_u32(ring), bars_u32 = smem_u32(bars);
+  const size_t x_step = (size_t)step * TR * row_bytes, c_step = (size_t)step * TR * 4;
+  const unsigned char* x_next = reinterpret_cast<const unsigned char*>(Xh) + (size_t)first * TR * row_bytes;  // of the next tile to request
+  const unsigned char* c_next = reinterpret_cast<const unsigned char*>(coef) + (size_t)first * TR * 4;
+  auto request = [&](int64_t tile, int s) {
+    const uint32_t dst = ring_u32 + (uint32_t)s * stage_bytes, bar = bars_u32 + (uint32_t)s * 8u;
+    if (tile < whole_tiles) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(rows_bytes + (uint32_t)TR * 4u) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(dst), "l"(x_next), "r"(rows_bytes), "r"(bar) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(dst + rows_bytes), "l"(c_next), "r"((uint32_t)TR * 4u), "r"(bar) : "memory");
+    } else {
+      const uint32_t rb = (uint32_t)(n - tile * TR) * row_bytes;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(rb) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(dst), "l"(x_next), "r"(rb), "r"(bar) : "memory");
+    }
+    x_next += x_step;
+    c_next += c_step;
+  };
+  // (nothing read up to the epilogue depends on the predecessor in the stream: the ring fills at once)
+  if (lane == 0)
+    for (int s = 0; s < NS; s++)
+      if (first + (int64_t)s * step < ntiles) request(first + (int64_t)s * step, s);
+  __shared__ float s_q2;
+  __shared__ double s_qq;
+  if (warp == 0) {
+    float ss = 0.0f;
+    for (int i = lane; i < d; i += 32) ss = fmaf(q[i], q[i], ss);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(FULL_MASK, ss, o);
+    if (lane == 0) s_q2 = ss;
+  }
+  __syncthreads();
+  // the query scaled by a power of two and rounded to fp16, like the rows (query_convert_kernel's arithmetic, done
+  // by every CTA for itself: one launch and one dependency less on the latency path of a query)
+  const float q2 = s_q2;
+  float sq = 1.0f;
+  if (q2 > 0.0f && q2 < 1e30f) {
+    int e;
+    frexpf(sqrtf(q2) * 1.0001f, &e);  // |q| < 2^e
+    sq = ldexpf(1.0f, 14 - e);
+  }
+  const float qis = 1.0f / (x_scale * sq);
+  uint4 qr[CPL > 0 ? CPL : 1];   // the lane's chunks t, t + 8, ... of the scaled fp16 query (zero beyond d)
+  int xoff[CPL > 0 ? CPL : 1];   // byte offsets of those chunks inside a row (clamped: the query chunk is zero there)
+  const int chunks = dp >> 3;
+  uint4* qh_s = reinterpret_cast<uint4*>(qf);  // CPL == 0: the whole scaled fp16 query in shared memory
+  auto q_chunk = [&](int c) -> uint4 {  // elements 8c .. 8c + 7
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) f[i] = (c * 8 + i < d) ? q[c * 8 + i] * sq : 0.0f;
+    const __half2 h0 = __floats2half2_rn(f[0], f[1]), h1 = __floats2half2_rn(f[2], f[3]);
+    const __half2 h2 = __floats2half2_rn(f[4], f[5]), h3 = __floats2half2_rn(f[6], f[7]);
+    uint4 o;
+    o.x = *reinterpret_cast<const unsigned int*>(&h0);
+    o.y = *reinterpret_cast<const unsigned int*>(&h1);
+    o.z = *reinterpret_cast<const unsigned int*>(&h2);
+    o.w = *reinterpret_cast<const unsigned int*>(&h3);
+    return o;
+  };
+  if (CPL > 0) {
+#pragma unroll
+    for (int j = 0; j < (CPL > 0 ? CPL : 1); j++) {
+      const int c = t + 8 * j;
+      qr[j] = c < chunks ? q_chunk(c) : make_uint4(0u, 0u, 0u, 0u);
+      xoff[j] = (c < chunks ? c : chunks - 1) * 16;
+    }
+  } else {
+    for (int i = threadIdx.x; i < chunks; i += blockDim.x) qh_s[i] = q_chunk(i);
+  }
+
+  __syncthreads();
+  bq_stamp(1);
+  const bool bad_query = !(q2 < 1e30f);  // non-finite (or absurdly large): exact scan instead (uniform over the grid)
+
+  const float inf = __int_as_float(0x7f800000);
+  // lane i: the warp's i-th smallest a (order-preserving bits) and its row; 0xffffffff = empty
+  uint32_t my_a = 0xffffffffu, my_r = 0xffffffffu, thr_ord = 0xffffffffu;
+  float thr = inf;
+  // What the CTA publishes is the KK smallest keys of ALL its warps, so a row at or above ANY warp's KK-th value is of
+  // no use to any of them: the warps share the smallest such value (s_cta_thr) and filter with it even before their own
+  // list is full -- a tenth of the insertions sixteen private thresholds cost.
+  __shared__ unsigned int s_cta_thr;
+  if (threadIdx.x == 0) s_cta_thr = 0xff800000u;  // +inf
+  __syncthreads();
+  const float m2q = -2.0f * qis;
+  // <q, x> of the row whose first byte is at rowp, summed over the row's eight lanes (every one of them gets the sum)
+  auto row_dot = [&](const unsigned char* rowp) -> float {
+    float d0 = 0.0f, d1 = 0.0f;
+    if (CPL > 0) {
+      uint4 v[CPL > 0 ? CPL : 1];
+#pragma unroll
+      for (int j = 0; j < (CPL > 0 ? CPL : 1); j++) v[j] = *reinterpret_cast<const uint4*>(rowp + xoff[j]);
+#pragma unroll
+      for (int j = 0; j < (CPL > 0 ? CPL : 1); j++) sh_fh8(v[j], qr[j], d0, d1);
+    } else {
+#pragma unroll 4
+      for (int c = t; c < chunks; c += 8) sh_fh8(*reinterpret_cast<const uint4*>(rowp + c * 16), qh_s[c], d0, d1);
+    }
+    return d0 + d1;
+  };
+  auto insert = [&](unsigned m, float a, uint32_t row) {  // lanes of mask m offer (a, row)
+    const uint32_t before = thr_ord;
+    while (m) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      const uint32_t ca = __shfl_sync(FULL_MASK, sh_ord(a), src), cr = __shfl_sync(FULL_MASK, row, src);
+      if (!(ca < thr_ord)) continue;  // the threshold may have tightened since the ballot
+      const int pos = __popc(__ballot_sync(FULL_MASK, my_a <= ca));  // sorted: the smaller keys are a prefix
+      const uint32_t ua = __shfl_up_sync(FULL_MASK, my_a, 1), ur = __shfl_up_sync(FULL_MASK, my_r, 1);
+      if (lane > pos) {
+        my_a = ua;
+        my_r = ur;
+      } else if (lane == pos) {
+        my_a = ca;
+        my_r = cr;
+      }
+      thr_ord = __shfl_sync(FULL_MASK, my_a, KK - 1);
+    }
+    if (thr_ord != before) {
+      thr = sh_unord(thr_ord);
+      if (lane == 0) atomicMin(&s_cta_thr, thr_ord);
+    }
+  };
+  int stage = 0;
+  uint32_t parity = 0;
+  for (int64_t tile = first; tile < ntiles; tile += step) {
+    mbar_wait_suspend(bars + stage, parity);
+    const unsigned char* sp = ring + (size_t)stage * stage_bytes;
+    const float* cf = reinterpret_cast<const float*>(sp + rows_bytes);
+    const uint32_t row0 = (uint32_t)(tile * TR);
+    if (!bad_query) {
+      if ((tile + 1) * TR <= n) {  // whole tile: coefficients came with the rows, no row is out of range
+        const unsigned char* lp = sp + (size_t)g * row_bytes;
+        for (int r0 = 0; r0 < TR; r0 += 8, lp += 8 * row_bytes) {  // two sub-steps of four rows: independent chains
+          const float thr_eff = fminf(thr, sh_unord(*reinterpret_cast<volatile unsigned int*>(&s_cta_thr)));
+          float da = row_dot(lp), db = row_dot(lp + 4 * row_bytes);
+          da += __shfl_xor_sync(FULL_MASK, da, 1);
+          db += __shfl_xor_sync(FULL_MASK, db, 1);
+          da += __shfl_xor_sync(FULL_MASK, da, 2);
+          db += __shfl_xor_sync(FULL_MASK, db, 2);
+          da += __shfl_xor_sync(FULL_MASK, da, 4);
+          db += __shfl_xor_sync(FULL_MASK, db, 4);
+          const float ca = cf[r0 + g], cb = cf[r0 + 4 + g];
+          const float aa = COSINE ? (ca * da) * qis : fmaf(da, m2q, ca);
+          const float ab = COSINE ? (cb * db) * qis : fmaf(db, m2q, cb);
+          // (dead rows carry +inf / NaN coefficients and never pass)
+          const unsigned ma = __ballot_sync(FULL_MASK, t == 0 && aa < thr_eff), mb = __ballot_sync(FULL_MASK, t == 0 && ab < thr_eff);
+          if (ma | mb) {
+            insert(ma, aa, row0 + r0 + g);
+            insert(mb, ab, row0 + r0 + 4 + g);
+          }
+        }
+      } else {  // the segment's last, partial tile
+        for (int r0 = 0; r0 < TR; r0 += 4) {
+          const int ri = r0 + g;
+          const int64_t row = tile * TR + ri;
+          float da = row_dot(sp + (size_t)ri * row_bytes);
+          da += __shfl_xor_sync(FULL_MASK, da, 1);
+          da += __shfl_xor_sync(FULL_MASK, da, 2);
+          da += __shfl_xor_sync(FULL_MASK, da, 4);
+          float aa = inf;
+          if (row < n) {
+            const float ca = __ldg(coef + row);
+            aa = COSINE ? (ca * da) * qis : fmaf(da, m2q, ca);
+          }
+          insert(__ballot_sync(FULL_MASK, t == 0 && row < n && aa < thr), aa, row0 + ri);  // (dead rows: +inf / NaN)
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) {
+      const int64_t nt = tile + (int64_t)NS * step;
+      if (nt < ntiles) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        request(nt, stage);
+      }
+    }
+    if (++stage == NS) {
+      stage = 0;
+      parity ^= 1;
+    }
+  }
+  pdl_wait();  // nothing above wrote global memory; the scratch and the outputs may be in use by earlier kernels until here
+  if (bad_query) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) batch_list_fallback(fb, nq_total, qi);
+    return;
+  }
+
+  bq_stamp(2);
+  // ---- epilogue (the rings are dead: their shared memory is reused) ---------------------------------------------------
+  __shared__ int s_m;
+  if (threadIdx.x == 0) s_m = 0;
+  __syncthreads();
+  uint64_t* keys = reinterpret_cast<uint64_t*>(shm);       // [nw * KK]
+  uint64_t* outk = keys + nw * KK;                          // [KK]
+  uint64_t* heads = outk + KK;                              // [SH_MAX_LISTS]
+  uint32_t* cand = reinterpret_cast<uint32_t*>(heads + SH_MAX_LISTS);     // [SH_CAND]
+  ulonglong2* ekeys = reinterpret_cast<ulonglong2*>(cand + SH_CAND);      // [nw * k], then [k]
+  // The CTA's KK smallest keys all lie at or below the smallest KK-th value any of its warps holds (that warp alone has
+  // KK keys there): only those -- a few dozen of the nw * KK -- are compacted and ranked.
+  if (lane < KK && my_a != 0xffffffffu && my_a <= s_cta_thr) keys[atomicAdd(&s_m, 1)] = ((uint64_t)my_a << 32) | (uint64_t)my_r;
+  if (threadIdx.x < KK) outk[threadIdx.x] = KEY_EMPTY64;
+  __syncthreads();
+  {
+    const int m = s_m;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+      const uint64_t me = keys[i];
+      int rank = 0;
+#pragma unroll 4
+      for (int j = 0; j < m; j++) rank += keys[j] < me ? 1 : 0;  // keys are distinct (row ids)
+      if (rank < KK) outk[rank] = me;
+    }
+  }
+  __syncthreads();
+  const int nl = gridDim.x;
+  unsigned long long* all = pub + (size_t)qi * nl * KK;
+  if (threadIdx.x < KK) __stcg(all + (size_t)blockIdx.x * KK + threadIdx.x, (unsigned long long)outk[threadIdx.x]);
+  __threadfence();
+  __syncthreads();
+  __shared__ unsigned int s_last;
+  __shared__ int s_cnt, s_over;
+  __shared__ uint64_t s_B;
+  unsigned long long* ctrl = out.ctrl + 4 * (size_t)qi;
+  if (threadIdx.x == 0) {
+    const unsigned long long tk = atomicAdd(ctrl, 1ull);
+    s_last = (tk == gridDim.x - 1) ? 1u : 0u;
+    s_cnt = 0;
+    s_over = 0;
+    s_B = KEY_EMPTY64;
+  }
+  __syncthreads();
+  bq_stamp(3);
+  if (!s_last) return;
+  __threadfence();
+  bq_stamp_any(4);
+  // every published key is requested now; the bound is found meanwhile
+  constexpr int PRE = (SH_MAX_LISTS * KK + SH_MIN_THREADS - 1) / SH_MIN_THREADS;
+  uint64_t pre[PRE];
+  const int total = nl * KK;
+#pragma unroll
+  for (int i = 0; i < PRE; i++) {
+    const int idx = threadIdx.x + i * blockDim.x;
+    pre[i] = idx < total ? (uint64_t)__ldcg(all + idx) : KEY_EMPTY64;
+  }
+  for (int i = threadIdx.x; i < nl; i += blockDim.x) heads[i] = (uint64_t)__ldcg(all + (size_t)i * KK);
+  if (COSINE && threadIdx.x == 32) s_qq = ref_sum_thread<REF_DOT>(q, q, d, lanes);
+  __syncthreads();
+  if ((int)blockDim.x >= 2 * nl) {  // two threads per head, half of the comparisons each
+    const int hi = threadIdx.x >> 1, part = threadIdx.x & 1;
+    const uint64_t h = hi < nl ? heads[hi] : KEY_EMPTY64;
+    const int half_n = (nl + 1) >> 1, j0 = part * half_n, j1 = min(nl, j0 + half_n);
+    int rank = 0;
+    if (h != KEY_EMPTY64) {
+#pragma unroll 4
+      for (int j = j0; j < j1; j++) rank += heads[j] < h ? 1 : 0;
+    }
+    rank += __shfl_xor_sync(FULL_MASK, rank, 1);
+    if (h != KEY_EMPTY64 && part == 0 && rank == k - 1) s_B = h;
+  } else {
+    for (int i = threadIdx.x; i < nl; i += blockDim.x) {
+      const uint64_t h = heads[i];
+      if (h == KEY_EMPTY64) continue;
+      int rank = 0;
+#pragma unroll 4
+      for (int j = 0; j < nl; j++) rank += heads[j] < h ? 1 : 0;
+      if (rank == k - 1) s_B = h;
+    }
+  }
+  __syncthreads();
+  float tau = inf;
+  if (s_B != KEY_EMPTY64) {
+    const double slack = batch_slack(COSINE, true, d, sqrt((double)__uint_as_float(stats->xmax2_bits)), sqrt((double)q2));
+    tau = f32_next_up(__double2float_ru((double)sh_unord((uint32_t)(s_B >> 32)) + 2.0 * slack + 1e-37));
+    if (!(tau == tau)) tau = inf;
+  }
+#pragma unroll
+  for (int i = 0; i < PRE; i++) {
+    const uint64_t key = pre[i];
+    if (key == KEY_EMPTY64) continue;
+    if (sh_unord((uint32_t)(key >> 32)) <= tau) {
+      const int slot = atomicAdd(&s_cnt, 1);
+      if (slot < SH_CAND) cand[slot] = (uint32_t)key;
+      if ((threadIdx.x + i * blockDim.x) % KK == KK - 1) s_over = 1;  // a full list ends inside the band
+    }
+  }
+  __syncthreads();
+  bq_stamp_any(5);
+  int cnt = s_cnt;
+  if (s_over || cnt > SH_CAND) {
+    if (threadIdx.x == 0) batch_list_fallback(fb, nq_total, qi);  // the fallback scan overwrites what follows
+    if (cnt > SH_CAND) cnt = SH_CAND;
+  }
+  // exact scores of the candidates: one row per half-warp, lane hl is SIMD lane hl of the modelled JVM
+  WarpTopKReg tk;
+  tk.init(nullptr, 32, k, lane);
+  {
+    const double qq = COSINE ? s_qq : 0.0;
+    const int hl = lane & 15, hw = lane >> 4;
+    const unsigned hmask = (lane < 16) ? 0x0000ffffu : 0xffff0000u;
+    const int base_lane = lane & 16;
+    for (int i = warp * 2; i < cnt; i += nw * 2) {
+      const bool have = i + hw < cnt;
+      Key key = key_empty();
+      bool ok = false;
+      if (have) {  // uniform across the half-warp
+        const int64_t row = (int64_t)cand[i + hw];
+        ok = !(skip != nullptr && skip[row]);
+        if (ok) {
+          const float* x = X + (size_t)row * d;
+          double score;
+          if (COSINE) {
+            const double dotx = ref_sum_halfwarp<REF_DOT>(q, x, d, lanes, hl, hmask, base_lane);
+            const double xx = ref_sum_halfwarp<REF_DOT>(x, x, d, lanes, hl, hmask, base_lane);
+            score = ref_cosine_from_sums(dotx, qq, xx);
+          } else {
+            score = -__dsqrt_rn(ref_sum_halfwarp<REF_L2SQ>(q, x, d, lanes, hl, hmask, base_lane));
+          }
+          key = Key{rank_hi_from_score(score), (uint64_t)row};
+        }
+      }
+      tk.push(key, ok && hl == 0, lane);
+    }
+  }
+  bq_stamp_any(6);
+  ulonglong2* eout = ekeys + nw * k;
+  if (threadIdx.x == 0) s_m = 0;
+  if (threadIdx.x < k) st_key(eout + threadIdx.x, key_empty());
+  __syncthreads();
+  if (lane < k && tk.my_lo != KEY_EMPTY64) st_key(ekeys + atomicAdd(&s_m, 1), Key{tk.my_hi, tk.my_lo});
+  __syncthreads();
+  block_rank_select(ekeys, s_m, k, eout);
+  __syncthreads();
+  topk_write_out(eout, k, out, qi);
+  bq_stamp_any(7);
 }
 
 // grid (P, nq): CTA (p, qi) owns the p-th slice of the row groups (gsz rows each) of query qi.
@@ -1257,6 +1674,15 @@ static FallbackKern pick_fallback(int TPR, bool cosine, int k) {
   return k <= TOPK_REG_MAX_K ? fallback_kernel<WarpTopKReg>(TPR, cosine) : fallback_kernel<WarpTopK>(TPR, cosine);
 }
 
+typedef void (*ScanHalfKern)(const __half*, int64_t, int, const float*, float, const SegStats*, const float*, int,
+                             const float*, const uint8_t*, int, int, int, int, int32_t*, int, unsigned long long*, TopkOut);
+static ScanHalfKern pick_scan_half(bool cosine, int kk, int cpl) {
+#define VS_SH(C, K) (cpl == 2 ? scan_half_kernel<C, K, 2> : (cpl == 4 ? scan_half_kernel<C, K, 4> : scan_half_kernel<C, K, 0>))
+  if (cosine) return kk == 16 ? VS_SH(true, 16) : VS_SH(true, 32);
+  return kk == 16 ? VS_SH(false, 16) : VS_SH(false, 32);
+#undef VS_SH
+}
+
 typedef void (*GemmKern)(const CUtensorMap, const CUtensorMap, const float*, const float*, int64_t, int, int, int, int64_t,
                          float*, int64_t);
 template <int GROUP>
@@ -1335,6 +1761,36 @@ bool batch_configure(BatchLaunch& L, int sms) {
       L.pair_smem = fixed + (L.pair_stat ? a_res : 0) + 128 + (size_t)ns2 * per2;
     }
   }
+  // one or two queries: the CUDA-core scan of the fp16 copy (scan_half_kernel)
+  L.sh_ok = false;
+  if (L.half && L.k <= TOPK_REG_MAX_K && L.n < (int64_t(1) << 32)) {
+    const int kk = L.k <= 16 ? 16 : 32;
+    for (int threads = SH_THREADS; threads >= SH_MIN_THREADS && !L.sh_ok; threads /= 2) {
+      const int nw = threads / 32;
+      int TR = (int)((threads == SH_THREADS ? 4096 : 8192) / ((size_t)L.dp * 2)) & ~7;
+      if (TR < 8) TR = 8;
+      const size_t stage = ((size_t)TR * L.dp * 2 + (size_t)TR * 4 + 127) & ~size_t(127);
+      const size_t fixed = (size_t)((L.dp + 3) & ~3) * 4 + (size_t)nw * 4 * 8 + 256;
+      if (fixed + 2 * (size_t)nw * stage > 216 * 1024) continue;
+      int NS = (int)((216 * 1024 - fixed) / ((size_t)nw * stage));  // bytes in flight per SM are what the stream rate hangs on
+      if (NS > 4) NS = 4;
+      if (NS < 2) NS = 2;
+      const size_t epi = (size_t)(nw * kk + kk + SH_MAX_LISTS) * 8 + (size_t)SH_CAND * 4 + (size_t)(nw * L.k + L.k) * 16 + 64;
+      if ((size_t)nw * NS * stage < epi) continue;
+      L.sh_ok = true;
+      L.sh_threads = threads;
+      L.sh_TR = TR;
+      L.sh_NS = NS;
+      L.sh_kk = kk;
+      L.sh_cpl = L.dp <= 128 ? 2 : (L.dp <= 256 ? 4 : 0);
+      L.sh_smem = (size_t)nw * NS * stage + fixed;
+      const int64_t ntiles = (L.n + TR - 1) / TR;
+      int64_t grid = sms < SH_MAX_LISTS ? sms : SH_MAX_LISTS;
+      if (grid > (ntiles + nw - 1) / nw) grid = (ntiles + nw - 1) / nw;
+      L.sh_grid = (int)(grid < 1 ? 1 : grid);
+      if (set_smem_attr(pick_scan_half(L.cosine, kk, L.sh_cpl), 224 * 1024) != cudaSuccess) return false;
+    }
+  }
   // candidate groups per select CTA: the k-th smallest group minimum admits about k groups, the slack a few more
   L.cap = 4 * L.k + 256;
   for (;;) {
@@ -1391,6 +1847,21 @@ cudaError_t launch_batch(const BatchLaunch& L, cudaStream_t st) {
   const int kbe = L.half ? 64 : 32;
   const int num_kb = (L.d + kbe - 1) / kbe;
   if ((e = cudaMemsetAsync(L.fb, 0, sizeof(int32_t) * (1 + 2 * (size_t)L.nq), st)) != cudaSuccess) return e;
+  if (L.direct) {  // one or two queries: no tensor-core tile to amortise -- CUDA-core scan of the fp16 copy
+    count_launch();
+    TopkOut o{L.partial, L.ctrl, L.partial_keys, L.ids_out, L.scores_out, L.counts_out, L.id_base, 0,
+              L.out_stride > 0 ? L.out_stride : L.k};
+    int grid = L.sh_grid - (L.reserve_sms > 0 ? L.reserve_sms : 0);
+    if (grid < 1) grid = 1;
+    e = launch_pdl(pick_scan_half(L.cosine, L.sh_kk, L.sh_cpl), dim3(grid, L.nq), dim3(L.sh_threads), L.sh_smem, st,
+                   static_cast<const __half*>(L.xh), L.n, L.dp, L.coef, L.x_scale, L.stats, L.X, L.d,
+                   L.q, L.skip, L.lanes, L.k, L.sh_TR, L.sh_NS, L.fb, L.nq, reinterpret_cast<unsigned long long*>(L.gm), o);
+    if (e != cudaSuccess) return e;
+    count_launch();
+    const int gy = L.nq < BQ_FB_SLOTS ? L.nq : BQ_FB_SLOTS;
+    pick_fallback(L.lanes / 4, L.cosine, L.k)<<<dim3(L.fb_gx, gy), L.fb_threads, L.fb_smem, st>>>(L.X, L.n, L.d, L.q, L.skip, L.k, L.kp, L.fb, o);
+    return cudaGetLastError();
+  }
   if (L.half) {
     count_launch();
     const int nq_pad = (L.nq + 2 * BQ_M - 1) / (2 * BQ_M) * (2 * BQ_M);  // whole pairs of query blocks

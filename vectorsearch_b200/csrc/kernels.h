@@ -108,6 +108,8 @@ struct BatchLaunch {
   int64_t out_stride;
   int select_ctas_override;  // 0 = choose the selection CTAs per query from the batch size
   int group_override;    // 0 = choose the rows per nomination group (16 / 32 / 64) from the shape
+  bool direct;           // one or two queries: scan_half_kernel instead of the tensor-core nomination (needs sh_ok)
+  int reserve_sms;       // ... on this many SMs fewer (room for a neighbouring stream's small kernels)
   bool gemm_only;        // diagnostics: stop after the group minima
   int warp_min_q;        // chunks of at least this many queries select with one warp per query (k <= 32)
   // filled by batch_configure:
@@ -120,6 +122,9 @@ struct BatchLaunch {
   int pair_stages;       // stages of the cta_group::2 kernel
   bool pair_stat;        // ... with the query block resident per CTA (else both operands stream)
   size_t pair_smem;
+  bool sh_ok;            // scan_half_kernel fits this shape (fp16 copy, k <= 32)
+  int sh_TR, sh_NS, sh_kk, sh_cpl, sh_grid, sh_threads;
+  size_t sh_smem;
 };
 bool batch_supported(int d, int lanes, bool cosine, int64_t n);
 double batch_slack_host(bool cosine, bool half, int d, double xmax, double qn);
