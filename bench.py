@@ -282,7 +282,7 @@ def run_ours(args) -> None:
 
     # resident corpus shard: rows [rank*N, (rank+1)*N) of the Java LCG stream, generated on the device
     seg = vs.Segment.generate(CORPUS_SEED, rank * N_ROWS, N_ROWS, DIM, id_base=rank * N_ROWS)
-    n_slots = int(os.environ.get("VS_BENCH_SLOTS", "2"))
+    n_slots = int(os.environ.get("VS_BENCH_SLOTS", "3"))
     sh = ShardedSegment(seg, rank, world, slots=n_slots)
     # queries: draws of java.util.Random(43), the stream the reference arm uses, generated by libvsgpu's own generator
     qseg = vs.Segment.generate(QUERY_SEED, 0, W + K + 1, DIM)
@@ -362,19 +362,57 @@ def run_ours(args) -> None:
 
     # ---- per-launch duration of the scan kernel (roofline), events around every launch ------------------
     # (launched alone it has the whole GPU: all SMs; the reserve only pays off when queries overlap)
-    vs.set_option("scan_reserve_sms", 0)
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    with clocks:
-        for i in range(K):
-            evs[i][0].record(stream)
-            L.check(lib.vs_bruteforce_topk_dev(seg.handle, q_base + (W + i) * DIM * 4, 1, TOPK, 0, ids_p, sc_p, cn_p, st))
-            evs[i][1].record(stream)
+    def alone_ms():
+        vs.set_option("scan_reserve_sms", 0)
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        for i in range(3):  # (a changed option makes the first call plan its launch anew)
+            L.check(lib.vs_bruteforce_topk_dev(seg.handle, q_base + i * DIM * 4, 1, TOPK, 0, ids_p, sc_p, cn_p, st))
         torch.cuda.synchronize()
-    durs = sorted(a.elapsed_time(b) for a, b in evs)
-    kern_ms = sum(durs) / len(durs)
-    alg_bytes = N_ROWS * DIM * 4
+        l0 = vs.kernel_launch_count()
+        with clocks:
+            for i in range(K):
+                evs[i][0].record(stream)
+                L.check(lib.vs_bruteforce_topk_dev(seg.handle, q_base + (W + i) * DIM * 4, 1, TOPK, 0, ids_p, sc_p, cn_p, st))
+                evs[i][1].record(stream)
+            torch.cuda.synchronize()
+        vs.set_option("scan_reserve_sms", reserve_sms)
+        d_ = sorted(a.elapsed_time(b) for a, b in evs)
+        return sum(d_) / len(d_), d_[len(d_) // 2], (vs.kernel_launch_count() - l0) / K
+
+    kern_ms, kern_med, launches_per_call = alone_ms()
+    # Which kernel answers a single query: by default the scan of the fp16 operand copy (scan_half_kernel, 2 launches per
+    # call: the scan and the conditional exact fallback); the fp32 streaming scan (scan_tma_kernel, 1 launch) when the copy
+    # is switched off or does not exist.  The roofline uses the bytes THAT kernel has to read.
+    half_path = launches_per_call > 1.5
+    dp = (DIM + 7) // 8 * 8
+    alg_bytes = N_ROWS * (dp * 2 + 4) if half_path else N_ROWS * DIM * 4
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
-    vs.set_option("scan_reserve_sms", reserve_sms)
+    fp32_leg = None
+    if half_path and world == 1:
+        # the same query stream through the fp32 scan (option scan_fp16 = 0): SURVEY 8(d)'s 512 B per evaluation
+        vs.set_option("scan_fp16", 0)
+        f_ms, f_med, _ = alone_ms()
+        for i in range(W):
+            step_dev(i)
+        drain()
+        torch.cuda.synchronize()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(stream)
+        for s in slots:
+            s["stream"].wait_stream(stream)
+        for i in range(K):
+            step_dev(W + i)
+        drain()
+        f1.record(stream)
+        torch.cuda.synchronize()
+        f_step = f0.elapsed_time(f1) / K
+        vs.set_option("scan_fp16", 1)
+        f_bytes = N_ROWS * DIM * 4
+        f_traffic, f_src = profiled_traffic("r2_c2_scan_full.txt", "r1/r1_c2_scan_full.txt")
+        fp32_leg = {"kernel": "scan_tma_kernel<TPR=4,U=2,L2,WarpTopKReg> (K1, option scan_fp16 = 0)", "algorithmic_bytes_per_launch": f_bytes,
+                    "kernel_ms": f_ms, "kernel_ms_median": f_med, "achieved": f_bytes / (f_ms * 1e-3) / 1e9,
+                    "frac": f_bytes / (f_ms * 1e-3) / 1e9 / hbm_peak, "ms_per_step": f_step,
+                    "achieved_in_step": f_bytes / (f_step * 1e-3) / 1e9, "traffic": f_traffic, "traffic_source": f_src}
 
     # ---- end to end through the public host API: pinned host query in, ids + scores out, every step -----
     for i in range(W):
@@ -393,22 +431,24 @@ def run_ours(args) -> None:
     # threads at once (J/fdb/FdbVectorIndex.java:418-432) and libvsgpu gives every calling thread its own stream and
     # staging, so consecutive queries overlap on the device as they do in the device-resident region.  At N > 1 every
     # request thread has its own peer communicator (thread t of every rank exchanges with thread t of the others).
-    e2e_two = None
-    if not args.one_request_thread:
-        vs.set_option("scan_reserve_sms", reserve_sms)
-        callers = [(lambda q: seg.bruteforce_topk(q, TOPK))] * 2
-        sh2 = None
+    e2e_multi = {}
+    extra_sh = []
+
+    def run_request_threads(nt):
+        """The same K host calls issued by nt request threads (thread t of every rank exchanges with thread t of the others)."""
+        callers = [(lambda q: seg.bruteforce_topk(q, TOPK))] * nt
         if world > 1:
-            sh2 = ShardedSegment(seg, rank, world, slots=1)
-            callers = [(lambda q: sh.bruteforce_topk(q, TOPK)), (lambda q: sh2.bruteforce_topk(q, TOPK))]
-        start, errs = threading.Barrier(3), []
+            while len(extra_sh) < nt - 1:
+                extra_sh.append(ShardedSegment(seg, rank, world, slots=1))
+            callers = [(lambda q: sh.bruteforce_topk(q, TOPK))] + [(lambda q, s_=s_: s_.bruteforce_topk(q, TOPK)) for s_ in extra_sh[:nt - 1]]
+        start, errs = threading.Barrier(nt + 1), []
 
         def worker(t):
             try:
                 for i in range(W):
                     callers[t](qn[i])
                 start.wait()
-                for i in range(t, K, 2):
+                for i in range(t, K, nt):
                     callers[t](qn[W + i])
             except Exception as e:  # noqa: BLE001
                 errs.append(e)
@@ -417,7 +457,7 @@ def run_ours(args) -> None:
                 except Exception:  # noqa: BLE001
                     pass
 
-        th = [threading.Thread(target=worker, args=(t,), daemon=True) for t in range(2)]
+        th = [threading.Thread(target=worker, args=(t,), daemon=True) for t in range(nt)]
         for t_ in th:
             t_.start()
         try:
@@ -427,20 +467,29 @@ def run_ours(args) -> None:
                 t0 = time.perf_counter()
                 for t_ in th:
                     t_.join(timeout=60)
-                two_s = time.perf_counter() - t0
+                dt = time.perf_counter() - t0
         except threading.BrokenBarrierError:
-            two_s = None
-        ok = two_s is not None and not errs and not any(t_.is_alive() for t_ in th)
+            dt = None
+        ok = dt is not None and not errs and not any(t_.is_alive() for t_ in th)
         if world > 1:
             flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
             ok = bool(flag.item())
-        if ok:
-            two_s = max_over_ranks(two_s)
-            e2e_two = {"value": world * N_ROWS * K / two_s, "unit": "distance-evals/s", "ms_per_step": two_s / K * 1e3,
-                       "qps": K / two_s, "request_threads": 2}
-        if sh2 is not None and ok:
-            sh2.close()
+        if not ok:
+            return None
+        dt = max_over_ranks(dt)
+        return {"value": world * N_ROWS * K / dt, "unit": "distance-evals/s", "ms_per_step": dt / K * 1e3,
+                "qps": K / dt, "request_threads": nt}
+
+    if not args.one_request_thread:
+        vs.set_option("scan_reserve_sms", reserve_sms)
+        for nt in (2,):  # (three Python request threads measured slower than two: 71 vs 55 us per query at N = 1)
+            r_ = run_request_threads(nt)
+            if r_ is None:
+                break
+            e2e_multi[nt] = r_
+        for s_ in extra_sh:
+            s_.close()
 
     # ---- parity: the last query against the oracle over ALL ranks' rows (rank 0), both paths -------------
     parity = False
@@ -465,7 +514,8 @@ def run_ours(args) -> None:
         seg.free()
         seg = None
         ctx = dict(vs=vs, L=L, lib=lib, torch=torch, dist=dist, dev=dev, rank=rank, world=world, barrier=barrier,
-                   max_over_ranks=max_over_ranks, hbm_peak=hbm_peak, check=not args.no_check, n_slots=n_slots)
+                   max_over_ranks=max_over_ranks, hbm_peak=hbm_peak, check=not args.no_check,
+                   n_slots=int(os.environ.get("VS_BENCH_C4_SLOTS", "2")))
         extra["c3"] = bench_c3(ctx)
         extra["c4"] = bench_c4(ctx, min(K, 50), W)
         extra["c5"] = bench_c5(ctx, min(K, 10), W)
@@ -476,15 +526,47 @@ def run_ours(args) -> None:
         # the headline e2e is whole-job throughput through the host API: the better of one and two request threads
         # (both reported; host buffers in and out on every step in either case)
         one = {"value": e2e_value, "unit": "distance-evals/s", "ms_per_step": e2e_s / K * 1e3, "qps": K / e2e_s, "request_threads": 1}
-        best = e2e_two if (e2e_two is not None and e2e_two["value"] > e2e_value) else one
+        best = max([one] + list(e2e_multi.values()), key=lambda x: x["value"])
         e2e_obj = {"value": best["value"], "unit": "distance-evals/s", "h2d_bytes_per_step": DIM * 4,
                    "d2h_bytes_per_step": TOPK * 16 + 4, "ms_per_step": best["ms_per_step"], "qps": best["qps"],
-                   "request_threads": best["request_threads"], "one_request_thread": one, "two_request_threads": e2e_two}
-        traffic, traffic_src = profiled_traffic("r2_c2_scan_full.txt", "r1/r1_c2_scan_full.txt")
+                   "request_threads": best["request_threads"], "one_request_thread": one,
+                   "two_request_threads": e2e_multi.get(2)}
+        if half_path:
+            traffic, traffic_src = profiled_traffic("r2_c2_scan_half_full.txt")
+            kname = "scan_half_kernel<L2,KK=16,CPL=2> (K1h: streams the fp16 operand copy, exact scores of the candidates from the fp32 rows)"
+            unit_note = (f"{dp * 2 + 4} B per distance evaluation = the row of the fp16 operand copy ({dp * 2} B) + its fp32 coefficient (4 B); "
+                         f"SURVEY 8(d)'s figure for an fp32 scan is {DIM * 4} B")
+        else:
+            traffic, traffic_src = profiled_traffic("r2_c2_scan_full.txt", "r1/r1_c2_scan_full.txt")
+            kname = "scan_tma_kernel<TPR=4,U=2,L2,WarpTopKReg> (K1)"
+            unit_note = f"{DIM * 4} B per distance evaluation (SURVEY 8(d))"
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": achieved / hbm_peak, "traffic": traffic,
+                    "traffic_source": f"{traffic_src} (ncu --set full, dram read+write per launch)" if traffic_src else None,
+                    "peak_source": peak_src, "kernel": kname, "kernel_ms": kern_ms, "kernel_ms_median": kern_med,
+                    "launches_per_call": launches_per_call,
+                    "algorithmic_bytes_per_launch": alg_bytes, "algorithmic_bytes_per_unit": unit_note,
+                    "achieved_in_step": alg_bytes / (ms_per_step * 1e-3) / 1e9,
+                    "frac_in_step": alg_bytes / (ms_per_step * 1e-3) / 1e9 / hbm_peak,
+                    "note": "achieved = the kernel's bytes / duration of one call launched ALONE (events around every call: the scan "
+                            "and, on the fp16 path, the launch of the conditional fallback); achieved_in_step = bytes / ms_per_step "
+                            "of the timed region, where consecutive queries overlap on two streams (a read-only stream can exceed "
+                            "the read+write copy rate used as peak)"}
+        if half_path:
+            roofline["fp32_scan_equivalent"] = {
+                "bytes_per_launch": N_ROWS * DIM * 4, "GBps_alone": N_ROWS * DIM * 4 / (kern_ms * 1e-3) / 1e9,
+                "GBps_in_step": N_ROWS * DIM * 4 / (ms_per_step * 1e-3) / 1e9,
+                "note": "rate an fp32 scan would need for the same time: above the HBM peak, i.e. below the fp32 scan's floor of "
+                        f"{N_ROWS * DIM * 4 / hbm_peak / 1e3:.1f} us per query -- possible only because half the bytes are read"}
+        if fp32_leg is not None:
+            roofline["fp32_scan"] = fp32_leg
         line = {
             "metric": METRIC, "value": value, "unit": "distance-evals/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": DATA, "config": config_for(world),
+            "arithmetic": ("returned ids and scores come from the reference's fp32 / fp64 arithmetic on the fp32 rows (bit-identical to the "
+                           "oracle, parity_checked); the fp16 operand copy only nominates candidates within a proven error bound"
+                           if half_path else "the reference's fp32 / fp64 arithmetic on the fp32 rows"),
             "parallelism": (f"row-range shards x{world}, cross-shard top-k exchange per query = {sh.exchange}; one C call per step "
                             f"(scan + push + merge); {len(slots)} queries in flight on {len(slots)} streams; one untimed lock-step "
                             "exchange before the timed region") if world > 1 else
@@ -493,16 +575,7 @@ def run_ours(args) -> None:
                           "(and the cross-shard exchange at N > 1) run beside it",
             "qps": 1e3 / ms_per_step,
             "parity_checked": parity,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": traffic,
-                         "traffic_source": f"{traffic_src} (ncu --set full, dram read+write per launch)" if traffic_src else None,
-                         "peak_source": peak_src,
-                         "kernel": "scan_tma_kernel<TPR=4,U=2,L2,WarpTopKReg> (K1)", "kernel_ms": kern_ms,
-                         "kernel_ms_median": durs[len(durs) // 2], "algorithmic_bytes_per_launch": alg_bytes,
-                         "achieved_in_step": alg_bytes / (ms_per_step * 1e-3) / 1e9,
-                         "note": "achieved = bytes / duration of the kernel launched ALONE (events around every launch); "
-                                 "achieved_in_step = bytes / ms_per_step of the timed region, where consecutive queries overlap "
-                                 "on two streams (a read-only stream can exceed the read+write copy rate used as peak)"},
+            "roofline": roofline,
             "e2e": e2e_obj,
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),

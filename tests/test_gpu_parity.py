@@ -1051,12 +1051,15 @@ def test_scratch_slots_survive_destroyed_communicator_streams(vs, oracle):
 
 
 # ---- one or two queries: nomination on the fp16 copy (scan_half_kernel, batch.cu) ----------------------------------------
-@pytest.fixture
-def force_half_scan(vs):
-    """Route single queries (and pairs) of every segment size through the fp16-copy scan."""
+@pytest.fixture(params=[0, 1], ids=["ctas-auto", "one-cta-per-sm"])
+def force_half_scan(vs, request):
+    """Route single queries (and pairs) of every segment size through the fp16-copy scan, with the automatic CTA shape
+    (two 256-thread CTAs per SM where k <= 16 and the rings fit) and with one CTA per SM."""
     vs.set_option("batch_min_rows", 1)
     vs.set_option("scan_fp16", 1)
+    vs.set_option("scan_half_ctas", request.param)
     yield
+    vs.set_option("scan_half_ctas", 0)
     vs.set_option("batch_min_rows", 16384)
 
 

@@ -4,6 +4,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import vectorsearch_b200 as vs
 from vectorsearch_b200 import _lib as L
+if os.environ.get("VS_DEV_LIB"):  # the -DVS_BQ_STAMPS build (make BUILD=build_dev OUT=../libvsgpu_dev.so EXTRA=-DVS_BQ_STAMPS)
+    from pathlib import Path
+    L.LIB_PATH = Path(os.environ["VS_DEV_LIB"]).resolve()
 vs.init(0); lib = vs.load()
 nq = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 n, d, k, metric = (int(os.environ.get(e, v)) for e, v in (("VS_N", 1_000_000), ("VS_D", 128), ("VS_K", 10), ("VS_METRIC", 0)))
@@ -11,6 +14,8 @@ if os.environ.get("VS_PAIRS"):
     vs.set_option("batch_pairs", int(os.environ["VS_PAIRS"]))
 if os.environ.get("VS_SELP"):
     vs.set_option("batch_select_ctas", int(os.environ["VS_SELP"]))
+if os.environ.get("VS_SH_CTAS"):
+    vs.set_option("scan_half_ctas", int(os.environ["VS_SH_CTAS"]))
 if os.environ.get("VS_GROUP"):
     vs.set_option("batch_group", int(os.environ["VS_GROUP"]))
 seg = vs.Segment.generate(42, 0, n, d)
@@ -27,11 +32,25 @@ lib.vs_debug_read_stamps_batch(buf.ctypes.data_as(C.c_void_p), buf.nbytes)
 s = buf.reshape(1024, 8)[:min(nq, 1024), :7].astype(np.int64)
 t0 = s[:, 0].min()
 names = ["start", "setup(q, slack)", "phase1 (T)", "phase2 (list)", "prefetch issued", "phase3 (exact)", "epilogue"]
-if nq <= 2:  # scan_half_kernel: CTA 0 records 0-3, the last CTA 4-7
-    s8 = buf.reshape(1024, 8)[:nq].astype(np.int64)
+if nq <= 2:  # scan_half_kernel: phases 0-9 from CTA 0, 10-15 from the last CTA
+    names = ["start", "ring requested", "q2 known", "query staged", "loop done (warp 0)", "after pdl wait", "all warps done",
+             "compacted + ranked", "published + fenced", "ticket drawn", "LAST CTA begins", "keys loaded", "bound found",
+             "candidates listed", "scored", "end"]
+    s16 = buf[4096:4096 + 32 * nq].reshape(nq, 32)[:, :16].astype(np.int64)
     for qi in range(nq):
-        r = s8[qi] - s8[qi, 0]
-        print("query", qi, " ".join(f"{nm} {x/1e3:.2f}" for nm, x in zip(["start", "query staged", "loop done (CTA 0)", "published (CTA 0)", "last CTA begins", "candidates", "scored", "end"], r)))
+        r = (s16[qi] - s16[qi, 0]) / 1e3
+        print("query", qi)
+        for i, nm in enumerate(names):
+            print(f"  {nm:22s} {r[i]:7.2f}  (+{r[i] - r[i - 1] if i else 0.0:5.2f})")
+    c = buf[1024:1024 + 2 * 320].reshape(320, 2).astype(np.int64)
+    c = c[c[:, 0] > 0]
+    t00 = c[:, 0].min()
+    st_, en_ = (c[:, 0] - t00) / 1e3, (c[:, 1] - t00) / 1e3
+    print(f"per CTA ({len(c)} CTAs of query 0): start min {st_.min():.2f} median {np.median(st_):.2f} max {st_.max():.2f} us | loop done min {en_.min():.2f}"
+          f" p10 {np.percentile(en_, 10):.2f} median {np.median(en_):.2f} p90 {np.percentile(en_, 90):.2f} max {en_.max():.2f} us")
+    order = np.argsort(en_)
+    print("  slowest CTAs (index: start, done):", ", ".join(f"{i}: {st_[i]:.1f}, {en_[i]:.1f}" for i in order[-6:]))
+    print("  fastest CTAs (index: start, done):", ", ".join(f"{i}: {st_[i]:.1f}, {en_[i]:.1f}" for i in order[:6]))
     sys.exit(0)
 print("kernel span: %.1f us; CTA start spread: %.1f us" % ((s[:, 6].max() - t0) / 1e3, (s[:, 0].max() - t0) / 1e3))
 for i in range(1, 7):

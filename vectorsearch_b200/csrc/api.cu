@@ -50,6 +50,7 @@ static std::atomic<int64_t> g_batch_pairs{2};
 static std::atomic<int64_t> g_batch_prefilter{1};           // candidate groups are pre-filtered on the fp16 copy before exact scoring
 static std::atomic<int64_t> g_pdl{1};                       // programmatic dependent launch between the kernels of one call
 static std::atomic<int64_t> g_scan_fp16{1};                 // 1: single queries nominate on the fp16 copy (half the bytes), 0: fp32 scan
+static std::atomic<int64_t> g_scan_half_ctas{0};            // scan_half_kernel CTAs per SM: 0 = automatic (two where they fit), 1, 2 (diagnostics)
 static std::atomic<int64_t> g_batch_select_ctas{0};         // 0 = automatic selection CTAs per query, else 1..64 (diagnostics)
 static std::atomic<int64_t> g_batch_group{0};               // 0 = automatic rows per nomination group, else 16 / 32 / 64
 static std::atomic<int64_t> g_batch_fp16{1};                // nominate on fp16 operand copies (0: the fp32 rows as tf32)
@@ -540,8 +541,8 @@ static int batch_wanted(const Segment* s, int nq, bool cosine) {
 
 static int plan_batch(const Segment* s, int k, bool cosine, bool half, BatchLaunch* out) {
   const int ln = lanes();
-  const int go = (int)g_batch_group.load(), sp = (int)g_batch_select_ctas.load();
-  const uint64_t key = occ_key(cosine ? 31 : 30, s->d, ln, k, (half ? 1 : 0) + 2 * go + 256 * sp, (size_t)s->n);
+  const int go = (int)g_batch_group.load(), sp = (int)g_batch_select_ctas.load(), so = (int)g_scan_half_ctas.load();
+  const uint64_t key = occ_key(cosine ? 31 : 30, s->d, ln, k, (half ? 1 : 0) + 2 * go + 256 * sp + 256 * 128 * so, (size_t)s->n);
   {
     std::lock_guard<std::mutex> lk(g_scan_mu);
     auto it = g_batch_cache.find(key);
@@ -553,6 +554,7 @@ static int plan_batch(const Segment* s, int k, bool cosine, bool half, BatchLaun
   BatchLaunch L{};
   L.n = s->n; L.d = s->d; L.lanes = ln; L.cosine = cosine; L.k = k; L.half = half; L.dp = (s->d + 7) & ~7; L.group_override = go;
   L.select_ctas_override = sp;
+  L.sh_override = so;
   if (!batch_configure(L, g_sms)) return fail(VS_ECUDA, "batched scan cannot be resident for d=%d k=%d", s->d, k);
   std::lock_guard<std::mutex> lk(g_scan_mu);
   g_batch_cache[key] = L;
@@ -841,6 +843,11 @@ int32_t vs_set_option(const char* name, int64_t value) {
   }
   if (!strcmp(name, "scan_fp16")) {
     g_scan_fp16.store(value != 0);
+    return VS_OK;
+  }
+  if (!strcmp(name, "scan_half_ctas")) {
+    if (value < 0 || value > 2) return fail(VS_EINVAL, "scan_half_ctas must be 0 (automatic), 1 or 2");
+    g_scan_half_ctas.store(value);
     return VS_OK;
   }
   if (!strcmp(name, "batch_select_ctas")) {

@@ -811,9 +811,28 @@ __device__ __forceinline__ void bq_stamp_any(int ph) {  // whichever CTA runs th
     g_bq_stamps[blockIdx.y * 8 + ph] = t;
   }
 }
+// scan_half_kernel: up to 32 phases per query at g_bq_stamps[4096 + 32 * query + phase]; CTA 0's thread 0, or (any = true)
+// thread 0 of whichever CTA runs the phase
+__device__ __forceinline__ void sh_stamp(int ph, bool any = false) {
+  if (threadIdx.x == 0 && (any || blockIdx.x == 0) && blockIdx.y < 2) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    g_bq_stamps[4096 + blockIdx.y * 32 + ph] = t;
+  }
+}
+// ... and per CTA of query 0: g_bq_stamps[1024 + 2 * CTA + phase] (0 = start, 1 = warp 0 left the loop)
+__device__ __forceinline__ void sh_stamp_cta(int ph) {
+  if (threadIdx.x == 0 && blockIdx.y == 0 && blockIdx.x < 1024) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    g_bq_stamps[1024 + blockIdx.x * 2 + ph] = t;
+  }
+}
 #else
 __device__ __forceinline__ void bq_stamp(int) {}
 __device__ __forceinline__ void bq_stamp_any(int) {}
+__device__ __forceinline__ void sh_stamp(int, bool = false) {}
+__device__ __forceinline__ void sh_stamp_cta(int) {}
 #endif
 
 // ---- (2c) one or two queries: nomination by a CUDA-core scan of the fp16 copy -----------------------------------------
@@ -833,7 +852,9 @@ __device__ __forceinline__ void bq_stamp_any(int) {}
 constexpr int SH_THREADS = 512;   // 16 warps when their rings fit (short vectors), else 8: the scan is latency-bound per warp
 constexpr int SH_MIN_THREADS = 256;
 constexpr int SH_CAND = 1024;  // candidate rows the last CTA can hold
-constexpr int SH_MAX_LISTS = 160;  // CTAs per query (published lists the last CTA takes)
+// CTAs per query (published lists the last CTA takes): two 256-thread CTAs per SM for short lists (k <= 16), see
+// batch_configure; the last CTA holds every published key in registers, so long lists keep one CTA per SM
+__host__ __device__ constexpr int sh_max_lists(int kk) { return kk == 16 ? 320 : 160; }
 __device__ __forceinline__ uint32_t sh_ord(float f) {
   const uint32_t u = __float_as_uint(f);
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
@@ -863,7 +884,8 @@ scan_half_kernel(const __half* __restrict__ Xh, int64_t n, int dp, const float* 
                  unsigned long long* __restrict__ pub, TopkOut out) {
   extern __shared__ __align__(128) unsigned char shm[];
   pdl_trigger();
-  bq_stamp(0);
+  sh_stamp(0);
+  sh_stamp_cta(0);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int t = lane & 7, g = lane >> 3;
   const int qi = blockIdx.y;
@@ -911,8 +933,9 @@ scan_half_kernel(const __half* __restrict__ Xh, int64_t n, int dp, const float* 
   if (lane == 0)
     for (int s = 0; s < NS; s++)
       if (first + (int64_t)s * step < ntiles) request(first + (int64_t)s * step, s);
+  sh_stamp(1);
   __shared__ float s_q2;
-  __shared__ double s_qq;
+  __shared__ double s_qq, s_slack2;
   if (warp == 0) {
     float ss = 0.0f;
     for (int i = lane; i < d; i += 32) ss = fmaf(q[i], q[i], ss);
@@ -923,7 +946,11 @@ scan_half_kernel(const __half* __restrict__ Xh, int64_t n, int dp, const float* 
   __syncthreads();
   // the query scaled by a power of two and rounded to fp16, like the rows (query_convert_kernel's arithmetic, done
   // by every CTA for itself: one launch and one dependency less on the latency path of a query)
+  sh_stamp(2);
   const float q2 = s_q2;
+  // twice the nomination slack of this query (the last CTA's candidate band): off the epilogue's critical path
+  if (threadIdx.x == blockDim.x - 1)
+    s_slack2 = 2.0 * batch_slack(COSINE, true, d, sqrt((double)__uint_as_float(stats->xmax2_bits)), sqrt((double)q2));
   float sq = 1.0f;
   if (q2 > 0.0f && q2 < 1e30f) {
     int e;
@@ -960,7 +987,7 @@ scan_half_kernel(const __half* __restrict__ Xh, int64_t n, int dp, const float* 
   }
 
   __syncthreads();
-  bq_stamp(1);
+  sh_stamp(3);
   const bool bad_query = !(q2 < 1e30f);  // non-finite (or absurdly large): exact scan instead (uniform over the grid)
 
   const float inf = __int_as_float(0x7f800000);
@@ -1071,25 +1098,49 @@ scan_half_kernel(const __half* __restrict__ Xh, int64_t n, int dp, const float* 
       parity ^= 1;
     }
   }
+  sh_stamp(4);
+  sh_stamp_cta(1);
   pdl_wait();  // nothing above wrote global memory; the scratch and the outputs may be in use by earlier kernels until here
   if (bad_query) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) batch_list_fallback(fb, nq_total, qi);
+    if (blockIdx.x == 0 && threadIdx.x == 0) fb[qi] = 1;  // (every launch writes the flag of every query: nothing to zero)
     return;
   }
 
-  bq_stamp(2);
+  sh_stamp(5);
   // ---- epilogue (the rings are dead: their shared memory is reused) ---------------------------------------------------
   __shared__ int s_m;
+  __shared__ unsigned int s_pos[SH_THREADS / 32];
+  // The CTA publishes the KK smallest keys of its warps' (sorted) lists.  All of them lie at or below T = min(V, the
+  // smallest KK-th key of any warp): with c = nw / 2 and p = KK / c - 1, V = the c-th smallest of the warps' (p + 1)-th
+  // keys has c warps with p + 1 keys each at or below it, i.e. KK keys (rows are distinct).  Only the keys at or below T
+  // -- two or three dozen of the nw * KK -- are compacted (one shared-memory atomic per warp) and ranked.
+  const int cw = nw >= 2 ? nw / 2 : 1, pp = KK / cw - 1;
   if (threadIdx.x == 0) s_m = 0;
+  if (lane == pp) s_pos[warp] = my_a;
   __syncthreads();
+  sh_stamp(6);
   uint64_t* keys = reinterpret_cast<uint64_t*>(shm);       // [nw * KK]
   uint64_t* outk = keys + nw * KK;                          // [KK]
-  uint64_t* heads = outk + KK;                              // [SH_MAX_LISTS]
-  uint32_t* cand = reinterpret_cast<uint32_t*>(heads + SH_MAX_LISTS);     // [SH_CAND]
+  uint32_t* heads = reinterpret_cast<uint32_t*>(outk + KK);  // [sh_max_lists(KK)]: the a of every list's smallest key
+  uint32_t* cand = heads + sh_max_lists(KK);                 // [SH_CAND]
   ulonglong2* ekeys = reinterpret_cast<ulonglong2*>(cand + SH_CAND);      // [nw * k], then [k]
-  // The CTA's KK smallest keys all lie at or below the smallest KK-th value any of its warps holds (that warp alone has
-  // KK keys there): only those -- a few dozen of the nw * KK -- are compacted and ranked.
-  if (lane < KK && my_a != 0xffffffffu && my_a <= s_cta_thr) keys[atomicAdd(&s_m, 1)] = ((uint64_t)my_a << 32) | (uint64_t)my_r;
+  {
+    const uint32_t pv = lane < nw ? s_pos[lane] : 0xffffffffu;
+    int rank = 0;
+    for (int j = 0; j < nw; j++) {
+      const uint32_t o = __shfl_sync(FULL_MASK, pv, j);
+      rank += (o < pv || (o == pv && j < lane)) ? 1 : 0;
+    }
+    const unsigned bsel = __ballot_sync(FULL_MASK, lane < nw && rank == cw - 1);
+    const uint32_t V = __shfl_sync(FULL_MASK, pv, __ffs(bsel) - 1);
+    const uint32_t T = min(V, s_cta_thr);
+    const bool ok = lane < KK && my_a != 0xffffffffu && my_a <= T;
+    const unsigned bm = __ballot_sync(FULL_MASK, ok);
+    int base = 0;
+    if (lane == 0 && bm != 0u) base = atomicAdd(&s_m, __popc(bm));
+    base = __shfl_sync(FULL_MASK, base, 0);
+    if (ok) keys[base + __popc(bm & ((1u << lane) - 1u))] = ((uint64_t)my_a << 32) | (uint64_t)my_r;
+  }
   if (threadIdx.x < KK) outk[threadIdx.x] = KEY_EMPTY64;
   __syncthreads();
   {
@@ -1103,29 +1154,31 @@ scan_half_kernel(const __half* __restrict__ Xh, int64_t n, int dp, const float* 
     }
   }
   __syncthreads();
+  sh_stamp(7);
   const int nl = gridDim.x;
   unsigned long long* all = pub + (size_t)qi * nl * KK;
   if (threadIdx.x < KK) __stcg(all + (size_t)blockIdx.x * KK + threadIdx.x, (unsigned long long)outk[threadIdx.x]);
   __threadfence();
   __syncthreads();
+  sh_stamp(8);
   __shared__ unsigned int s_last;
   __shared__ int s_cnt, s_over;
-  __shared__ uint64_t s_B;
+  __shared__ unsigned int s_B;  // order-preserving bits of the k-th smallest list head's a (atomicMax from 0); 0xffffffff = fewer than k lists
   unsigned long long* ctrl = out.ctrl + 4 * (size_t)qi;
   if (threadIdx.x == 0) {
     const unsigned long long tk = atomicAdd(ctrl, 1ull);
     s_last = (tk == gridDim.x - 1) ? 1u : 0u;
     s_cnt = 0;
     s_over = 0;
-    s_B = KEY_EMPTY64;
+    s_B = 0u;
   }
   __syncthreads();
-  bq_stamp(3);
+  sh_stamp(9);
   if (!s_last) return;
   __threadfence();
-  bq_stamp_any(4);
+  sh_stamp(10, true);
   // every published key is requested now; the bound is found meanwhile
-  constexpr int PRE = (SH_MAX_LISTS * KK + SH_MIN_THREADS - 1) / SH_MIN_THREADS;
+  constexpr int PRE = (sh_max_lists(KK) * KK + SH_MIN_THREADS - 1) / SH_MIN_THREADS;
   uint64_t pre[PRE];
   const int total = nl * KK;
 #pragma unroll
@@ -1133,35 +1186,66 @@ scan_half_kernel(const __half* __restrict__ Xh, int64_t n, int dp, const float* 
     const int idx = threadIdx.x + i * blockDim.x;
     pre[i] = idx < total ? (uint64_t)__ldcg(all + idx) : KEY_EMPTY64;
   }
-  for (int i = threadIdx.x; i < nl; i += blockDim.x) heads[i] = (uint64_t)__ldcg(all + (size_t)i * KK);
+  const int nl4 = (nl + 3) & ~3;
+  for (int i = threadIdx.x; i < nl4; i += blockDim.x) heads[i] = i < nl ? (uint32_t)((uint64_t)__ldcg(all + (size_t)i * KK) >> 32) : 0xffffffffu;
   if (COSINE && threadIdx.x == 32) s_qq = ref_sum_thread<REF_DOT>(q, q, d, lanes);
   __syncthreads();
-  if ((int)blockDim.x >= 2 * nl) {  // two threads per head, half of the comparisons each
-    const int hi = threadIdx.x >> 1, part = threadIdx.x & 1;
-    const uint64_t h = hi < nl ? heads[hi] : KEY_EMPTY64;
-    const int half_n = (nl + 1) >> 1, j0 = part * half_n, j1 = min(nl, j0 + half_n);
-    int rank = 0;
-    if (h != KEY_EMPTY64) {
-#pragma unroll 4
-      for (int j = j0; j < j1; j++) rank += heads[j] < h ? 1 : 0;
+  sh_stamp(11, true);
+  // B = the k-th smallest head (with multiplicity): k distinct rows lie at or below it; only its a matters, and it is
+  // the largest head with fewer than k heads below it (none when there are fewer than k lists).  Heads are ranked on
+  // their 32 order-preserving bits.  Many lists per warp (two CTAs per SM: 296 lists, 8 warps): every warp first keeps
+  // the k smallest of its share (ranks by shuffles, ties by index) -- whatever is among the k smallest of all is among
+  // the k smallest of its warp.  Then all-pairs counts, four heads per shared-memory load, S adjacent lanes sharing a
+  // head's comparisons so that every thread of the CTA has work.
+  {
+    const uint32_t* hv = heads;
+    int nh = nl;
+    const int per = (nl + nw - 1) / nw;  // <= 64: nl <= 320 lists, nw >= 8 warps
+    if (per > 2 * k) {
+      uint32_t* lvl = cand;  // [nw * k] (the candidate list is written after the bound is known)
+      const int h0 = warp * per, i1 = lane + 32;
+      const uint32_t v0 = (lane < per && h0 + lane < nl) ? heads[h0 + lane] : 0xffffffffu;
+      const uint32_t v1 = (i1 < per && h0 + i1 < nl) ? heads[h0 + i1] : 0xffffffffu;
+      int r0 = 0, r1 = 0;
+      for (int j = 0; j < per; j++) {
+        const uint32_t o = __shfl_sync(FULL_MASK, j < 32 ? v0 : v1, j & 31);
+        r0 += (o < v0 || (o == v0 && j < lane)) ? 1 : 0;
+        r1 += (o < v1 || (o == v1 && j < i1)) ? 1 : 0;
+      }
+      if (lane < per && r0 < k) lvl[warp * k + r0] = v0;
+      if (i1 < per && r1 < k) lvl[warp * k + r1] = v1;
+      nh = nw * k;
+      if (threadIdx.x < 4) lvl[nh + threadIdx.x] = 0xffffffffu;  // padding of the last quad
+      hv = lvl;
+      __syncthreads();
     }
-    rank += __shfl_xor_sync(FULL_MASK, rank, 1);
-    if (h != KEY_EMPTY64 && part == 0 && rank == k - 1) s_B = h;
-  } else {
-    for (int i = threadIdx.x; i < nl; i += blockDim.x) {
-      const uint64_t h = heads[i];
-      if (h == KEY_EMPTY64) continue;
-      int rank = 0;
+    if (nh < k) {
+      if (threadIdx.x == 0) s_B = 0xffffffffu;
+    } else {
+      const int S = nh > 64 ? 4 : 1;
+      const int quads = (nh + 3) >> 2, qper = (quads + S - 1) / S;
+      const uint4* h4 = reinterpret_cast<const uint4*>(hv);
+      const int items = ((nh * S + 31) & ~31);  // whole warps (the reduction below shuffles)
+      for (int it = threadIdx.x; it < items; it += blockDim.x) {
+        const int i = it / S, part = it - i * S;
+        const uint32_t h = i < nh ? hv[i] : 0u;
+        int lt = 0;
+        const int j1 = min(quads, (part + 1) * qper);
 #pragma unroll 4
-      for (int j = 0; j < nl; j++) rank += heads[j] < h ? 1 : 0;
-      if (rank == k - 1) s_B = h;
+        for (int j = part * qper; j < j1; j++) {
+          const uint4 v = h4[j];
+          lt += (v.x < h ? 1 : 0) + (v.y < h ? 1 : 0) + (v.z < h ? 1 : 0) + (v.w < h ? 1 : 0);
+        }
+        for (int o = 1; o < S; o <<= 1) lt += __shfl_xor_sync(FULL_MASK, lt, o);
+        if (i < nh && part == 0 && lt <= k - 1) atomicMax(&s_B, h);  // (an empty head, 0xffffffff, when fewer than k lists hold a key)
+      }
     }
   }
   __syncthreads();
+  sh_stamp(12, true);
   float tau = inf;
-  if (s_B != KEY_EMPTY64) {
-    const double slack = batch_slack(COSINE, true, d, sqrt((double)__uint_as_float(stats->xmax2_bits)), sqrt((double)q2));
-    tau = f32_next_up(__double2float_ru((double)sh_unord((uint32_t)(s_B >> 32)) + 2.0 * slack + 1e-37));
+  if (s_B != 0xffffffffu) {
+    tau = f32_next_up(__double2float_ru((double)sh_unord(s_B) + s_slack2 + 1e-37));
     if (!(tau == tau)) tau = inf;
   }
 #pragma unroll
@@ -1175,12 +1259,10 @@ scan_half_kernel(const __half* __restrict__ Xh, int64_t n, int dp, const float* 
     }
   }
   __syncthreads();
-  bq_stamp_any(5);
+  sh_stamp(13, true);
   int cnt = s_cnt;
-  if (s_over || cnt > SH_CAND) {
-    if (threadIdx.x == 0) batch_list_fallback(fb, nq_total, qi);  // the fallback scan overwrites what follows
-    if (cnt > SH_CAND) cnt = SH_CAND;
-  }
+  if (threadIdx.x == 0) fb[qi] = (s_over || cnt > SH_CAND) ? 1 : 0;  // 1: the fallback scan overwrites what follows
+  if (cnt > SH_CAND) cnt = SH_CAND;
   // exact scores of the candidates: one row per half-warp, lane hl is SIMD lane hl of the modelled JVM
   WarpTopKReg tk;
   tk.init(nullptr, 32, k, lane);
@@ -1212,7 +1294,7 @@ scan_half_kernel(const __half* __restrict__ Xh, int64_t n, int dp, const float* 
       tk.push(key, ok && hl == 0, lane);
     }
   }
-  bq_stamp_any(6);
+  sh_stamp(14, true);
   ulonglong2* eout = ekeys + nw * k;
   if (threadIdx.x == 0) s_m = 0;
   if (threadIdx.x < k) st_key(eout + threadIdx.x, key_empty());
@@ -1222,7 +1304,7 @@ scan_half_kernel(const __half* __restrict__ Xh, int64_t n, int dp, const float* 
   block_rank_select(ekeys, s_m, k, eout);
   __syncthreads();
   topk_write_out(eout, k, out, qi);
-  bq_stamp_any(7);
+  sh_stamp(15, true);
 }
 
 // grid (P, nq): CTA (p, qi) owns the p-th slice of the row groups (gsz rows each) of query qi.
@@ -1580,11 +1662,13 @@ batch_select_warp_kernel(const float* __restrict__ X, int64_t n, int d, const fl
 template <int TPR, int U, bool COSINE, class TK>
 __global__ void __launch_bounds__(SCAN_THREADS)
 batch_fallback_kernel(const float* __restrict__ X, int64_t n, int d, const float* __restrict__ Q,
-                      const uint8_t* __restrict__ skip, int k, int kp, const int32_t* __restrict__ fb, TopkOut out) {
+                      const uint8_t* __restrict__ skip, int k, int kp, const int32_t* __restrict__ fb, int direct, TopkOut out) {
   extern __shared__ __align__(128) ulonglong2 smem[];
   constexpr int L = TPR * 4;
   constexpr int G = 32 / TPR;
-  const int count = fb[0];
+  // direct (after scan_half_kernel): fb[y] says whether query y needs the scan, grid.y = queries; else fb holds a
+  // count and a list of queries, walked by grid.y slots
+  const int count = direct ? (fb[blockIdx.y] != 0 ? (int)blockIdx.y + 1 : 0) : fb[0];
   if ((int)blockIdx.y >= count) return;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -1598,7 +1682,7 @@ batch_fallback_kernel(const float* __restrict__ X, int64_t n, int d, const float
   const int64_t nbatches = (n + rows_per_batch - 1) / rows_per_batch;
   const int64_t total_warps = (int64_t)gridDim.x * nw;
   for (int slot = blockIdx.y; slot < count; slot += gridDim.y) {
-    const int qi = fb[1 + slot];
+    const int qi = direct ? slot : fb[1 + slot];
     const float* __restrict__ q = Q + (size_t)qi * d;
     __syncthreads();  // previous query's epilogue is done with shared memory
     TK tk;
@@ -1655,7 +1739,7 @@ static SelectWarpKern pick_select_warp(int TPR, bool cosine) {
   if (cosine) return TPR == 4 ? batch_select_warp_kernel<4, 1, true> : (TPR == 2 ? batch_select_warp_kernel<2, 1, true> : batch_select_warp_kernel<1, 1, true>);
   return TPR == 4 ? batch_select_warp_kernel<4, 2, false> : (TPR == 2 ? batch_select_warp_kernel<2, 2, false> : batch_select_warp_kernel<1, 2, false>);
 }
-typedef void (*FallbackKern)(const float*, int64_t, int, const float*, const uint8_t*, int, int, const int32_t*, TopkOut);
+typedef void (*FallbackKern)(const float*, int64_t, int, const float*, const uint8_t*, int, int, const int32_t*, int, TopkOut);
 
 template <class TK>
 static SelectKern select_kernel(int TPR, bool cosine) {
@@ -1765,27 +1849,38 @@ bool batch_configure(BatchLaunch& L, int sms) {
   L.sh_ok = false;
   if (L.half && L.k <= TOPK_REG_MAX_K && L.n < (int64_t(1) << 32)) {
     const int kk = L.k <= 16 ? 16 : 32;
-    for (int threads = SH_THREADS; threads >= SH_MIN_THREADS && !L.sh_ok; threads /= 2) {
-      const int nw = threads / 32;
-      int TR = (int)((threads == SH_THREADS ? 4096 : 8192) / ((size_t)L.dp * 2)) & ~7;
+    // Shapes tried in order.  (1) TWO 256-thread CTAs per SM (short lists only: the last CTA takes twice the lists): a
+    // CTA's set-up (query scaling, ~2.5 us) and epilogue (compaction, publish, ticket, ~3 us) stream nothing, and with
+    // one CTA per SM that is dead time of the SM in a stream of queries -- with two resident CTAs the neighbour (of this
+    // query or, on another stream, of the next) keeps the SM's loads in flight meanwhile.  (2) one 512-thread CTA.
+    // (3) one 256-thread CTA with larger tiles (long vectors: sixteen rings do not fit).
+    struct Shape { int threads, per_sm; size_t tile_bytes, budget; };
+    const Shape shapes[3] = {{256, 2, 4096, 112 * 1024}, {512, 1, 4096, 216 * 1024}, {256, 1, 8192, 216 * 1024}};
+    for (int si = 0; si < 3 && !L.sh_ok; si++) {
+      const Shape& S = shapes[si];
+      if (S.per_sm == 2 && (kk != 16 || L.sh_override == 1)) continue;
+      const int threads = S.threads, nw = threads / 32;
+      int TR = (int)(S.tile_bytes / ((size_t)L.dp * 2)) & ~7;
       if (TR < 8) TR = 8;
       const size_t stage = ((size_t)TR * L.dp * 2 + (size_t)TR * 4 + 127) & ~size_t(127);
       const size_t fixed = (size_t)((L.dp + 3) & ~3) * 4 + (size_t)nw * 4 * 8 + 256;
-      if (fixed + 2 * (size_t)nw * stage > 216 * 1024) continue;
-      int NS = (int)((216 * 1024 - fixed) / ((size_t)nw * stage));  // bytes in flight per SM are what the stream rate hangs on
+      if (fixed + (S.per_sm == 2 ? 3 : 2) * (size_t)nw * stage > S.budget) continue;
+      int NS = (int)((S.budget - fixed) / ((size_t)nw * stage));  // bytes in flight per SM are what the stream rate hangs on
       if (NS > 4) NS = 4;
       if (NS < 2) NS = 2;
-      const size_t epi = (size_t)(nw * kk + kk + SH_MAX_LISTS) * 8 + (size_t)SH_CAND * 4 + (size_t)(nw * L.k + L.k) * 16 + 64;
+      const size_t epi = (size_t)(nw * kk + kk) * 8 + (size_t)sh_max_lists(kk) * 4 + (size_t)SH_CAND * 4 + (size_t)(nw * L.k + L.k) * 16 + 64;
       if ((size_t)nw * NS * stage < epi) continue;
       L.sh_ok = true;
       L.sh_threads = threads;
+      L.sh_per_sm = S.per_sm;
       L.sh_TR = TR;
       L.sh_NS = NS;
       L.sh_kk = kk;
       L.sh_cpl = L.dp <= 128 ? 2 : (L.dp <= 256 ? 4 : 0);
       L.sh_smem = (size_t)nw * NS * stage + fixed;
       const int64_t ntiles = (L.n + TR - 1) / TR;
-      int64_t grid = sms < SH_MAX_LISTS ? sms : SH_MAX_LISTS;
+      int64_t grid = (int64_t)sms * S.per_sm;
+      if (grid > sh_max_lists(kk)) grid = sh_max_lists(kk);
       if (grid > (ntiles + nw - 1) / nw) grid = (ntiles + nw - 1) / nw;
       L.sh_grid = (int)(grid < 1 ? 1 : grid);
       if (set_smem_attr(pick_scan_half(L.cosine, kk, L.sh_cpl), 224 * 1024) != cudaSuccess) return false;
@@ -1809,6 +1904,13 @@ bool batch_configure(BatchLaunch& L, int sms) {
   L.fb_smem = ((topk_block_smem(L.k, L.kp, L.fb_threads / 32) + 15) & ~size_t(15)) + (((size_t)L.d * 4 + 15) & ~size_t(15));
   if (L.fb_smem > BQ_SELECT_SMEM_MAX) return false;
   L.fb_gx = sms > TOPK_MAX_LISTS ? TOPK_MAX_LISTS : sms;
+  // After scan_half_kernel the fallback check runs on every query and almost never has work: 64-thread CTAs (160
+  // registers a thread: 10 K registers a CTA) fit beside the two resident scan CTAs of a neighbouring stream's query.
+  // 256-thread CTAs (41 K registers) had to wait for an SM with at most one scan CTA, and the queries of a stream
+  // queued up behind their own fallback checks (47 instead of 42 us per query with three queries in flight).
+  L.fbd_threads = 64;
+  L.fbd_gx = 2 * sms > TOPK_MAX_LISTS ? TOPK_MAX_LISTS : 2 * sms;
+  L.fbd_smem = ((topk_block_smem(L.k, L.kp, L.fbd_threads / 32) + 15) & ~size_t(15)) + (((size_t)L.d * 4 + 15) & ~size_t(15));
   L.sms = sms;
   const int TPR = L.lanes / 4;
   {
@@ -1836,7 +1938,8 @@ int batch_select_ctas(const BatchLaunch& L, int nq) {
 
 int64_t batch_partial_keys(const BatchLaunch& L, int nq) {
   const int P = batch_select_ctas(L, nq);
-  return (int64_t)(P > L.fb_gx ? P : L.fb_gx) * L.k;
+  const int lists = L.fb_gx > L.fbd_gx ? L.fb_gx : L.fbd_gx;
+  return (int64_t)(P > lists ? P : lists) * L.k;
 }
 
 // One chunk of nq queries (q, outputs and scratch already offset to the chunk).
@@ -1846,12 +1949,12 @@ cudaError_t launch_batch(const BatchLaunch& L, cudaStream_t st) {
   const int nqb = (L.nq + BQ_M - 1) / BQ_M;
   const int kbe = L.half ? 64 : 32;
   const int num_kb = (L.d + kbe - 1) / kbe;
-  if ((e = cudaMemsetAsync(L.fb, 0, sizeof(int32_t) * (1 + 2 * (size_t)L.nq), st)) != cudaSuccess) return e;
   if (L.direct) {  // one or two queries: no tensor-core tile to amortise -- CUDA-core scan of the fp16 copy
+    // (no memset of fb here: the scan writes the fallback flag of every query of the launch)
     count_launch();
     TopkOut o{L.partial, L.ctrl, L.partial_keys, L.ids_out, L.scores_out, L.counts_out, L.id_base, 0,
               L.out_stride > 0 ? L.out_stride : L.k};
-    int grid = L.sh_grid - (L.reserve_sms > 0 ? L.reserve_sms : 0);
+    int grid = L.sh_grid - (L.reserve_sms > 0 ? L.reserve_sms * L.sh_per_sm : 0);
     if (grid < 1) grid = 1;
     e = launch_pdl(pick_scan_half(L.cosine, L.sh_kk, L.sh_cpl), dim3(grid, L.nq), dim3(L.sh_threads), L.sh_smem, st,
                    static_cast<const __half*>(L.xh), L.n, L.dp, L.coef, L.x_scale, L.stats, L.X, L.d,
@@ -1859,9 +1962,10 @@ cudaError_t launch_batch(const BatchLaunch& L, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     count_launch();
     const int gy = L.nq < BQ_FB_SLOTS ? L.nq : BQ_FB_SLOTS;
-    pick_fallback(L.lanes / 4, L.cosine, L.k)<<<dim3(L.fb_gx, gy), L.fb_threads, L.fb_smem, st>>>(L.X, L.n, L.d, L.q, L.skip, L.k, L.kp, L.fb, o);
+    pick_fallback(L.lanes / 4, L.cosine, L.k)<<<dim3(L.fbd_gx, gy), L.fbd_threads, L.fbd_smem, st>>>(L.X, L.n, L.d, L.q, L.skip, L.k, L.kp, L.fb, 1, o);
     return cudaGetLastError();
   }
+  if ((e = cudaMemsetAsync(L.fb, 0, sizeof(int32_t) * (1 + 2 * (size_t)L.nq), st)) != cudaSuccess) return e;
   if (L.half) {
     count_launch();
     const int nq_pad = (L.nq + 2 * BQ_M - 1) / (2 * BQ_M) * (2 * BQ_M);  // whole pairs of query blocks
@@ -1923,7 +2027,7 @@ cudaError_t launch_batch(const BatchLaunch& L, cudaStream_t st) {
   count_launch();
   const int gy = L.nq < BQ_FB_SLOTS ? L.nq : BQ_FB_SLOTS;
   // (launched normally: this kernel re-reads, through plain loads, what the selection kernel wrote)
-  pick_fallback(TPR, L.cosine, L.k)<<<dim3(L.fb_gx, gy), L.fb_threads, L.fb_smem, st>>>(L.X, L.n, L.d, L.q, L.skip, L.k, L.kp, L.fb, o);
+  pick_fallback(TPR, L.cosine, L.k)<<<dim3(L.fb_gx, gy), L.fb_threads, L.fb_smem, st>>>(L.X, L.n, L.d, L.q, L.skip, L.k, L.kp, L.fb, 0, o);
   return cudaGetLastError();
 }
 

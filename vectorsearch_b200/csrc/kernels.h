@@ -107,6 +107,7 @@ struct BatchLaunch {
   int64_t id_base;
   int64_t out_stride;
   int select_ctas_override;  // 0 = choose the selection CTAs per query from the batch size
+  int sh_override;           // scan_half_kernel CTAs per SM: 0 = automatic, 1 = one, 2 = two where they fit (diagnostics)
   int group_override;    // 0 = choose the rows per nomination group (16 / 32 / 64) from the shape
   bool direct;           // one or two queries: scan_half_kernel instead of the tensor-core nomination (needs sh_ok)
   int reserve_sms;       // ... on this many SMs fewer (room for a neighbouring stream's small kernels)
@@ -115,15 +116,15 @@ struct BatchLaunch {
   // filled by batch_configure:
   int64_t tiles, ngroups, gm_stride;
   int group;             // rows per nomination group
-  int cap, sms, fb_gx, fb_threads;
-  size_t gemm_smem, select_smem, selw_smem, fb_smem;
+  int cap, sms, fb_gx, fb_threads, fbd_gx, fbd_threads;  // (fbd_*: the fallback check behind scan_half_kernel)
+  size_t gemm_smem, select_smem, selw_smem, fb_smem, fbd_smem;
   bool gemm_stat;        // query block resident in shared memory (short vectors)
   int gemm_stages;
   int pair_stages;       // stages of the cta_group::2 kernel
   bool pair_stat;        // ... with the query block resident per CTA (else both operands stream)
   size_t pair_smem;
   bool sh_ok;            // scan_half_kernel fits this shape (fp16 copy, k <= 32)
-  int sh_TR, sh_NS, sh_kk, sh_cpl, sh_grid, sh_threads;
+  int sh_TR, sh_NS, sh_kk, sh_cpl, sh_grid, sh_threads, sh_per_sm;
   size_t sh_smem;
 };
 bool batch_supported(int d, int lanes, bool cosine, int64_t n);
