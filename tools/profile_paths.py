@@ -1,6 +1,6 @@
 """One hot path per invocation, a handful of launches: what `ncu` captures for the profiles/ summaries.
 
-    python tools/profile_paths.py scan|adc|batch|batch768|pq|rerank|knn|exchange
+    python tools/profile_paths.py scan|scan32|adc|batch|batch768|pq|rerank|knn|exchange
 
 scan: C2 (1M x 128, one query); adc: C4 ADC top-100 over VS_ROWS rows (default 100M) + re-rank; batch: C2 query batch
 1024; pq: encode of 10M x 128; knn: graph lists of a 20k x 128 segment; exchange: three ranks on this GPU
@@ -24,7 +24,8 @@ dev = torch.device("cuda:0")
 st = torch.cuda.current_stream().cuda_stream
 rng = np.random.default_rng(0)
 
-if which == "scan":
+if which in ("scan", "scan32"):  # scan: the default single-query path (fp16-copy scan); scan32: the fp32 streaming scan
+    vs.set_option("scan_fp16", 0 if which == "scan32" else 1)
     seg = vs.Segment.generate(42, 0, 1_000_000, 128)
     q = torch.from_numpy(rng.random((8, 128), dtype=np.float32) * 2 - 1).to(dev)
     ids = torch.empty((1, 10), dtype=torch.int64, device=dev); sc = torch.empty((1, 10), dtype=torch.float64, device=dev)

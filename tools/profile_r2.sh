@@ -10,7 +10,8 @@ cap() {  # name, kernel regex, skip, script arg
   # the reports themselves only travel back when small (gpurun_out is capped at 64 MiB)
   if [ "$(stat -c %s gpurun_out/r2_$1.ncu-rep 2>/dev/null || echo 0)" -gt 9000000 ] && [ "$1" != "pq_tc" ]; then rm -f gpurun_out/r2_$1.ncu-rep; fi
 }
-cap c2_scan scan_tma_kernel 4 scan
+cap c2_scan_half scan_half_kernel 4 scan
+cap c2_scan scan_tma_kernel 4 scan32
 cap c4_adc adc_fastscan_kernel 3 adc
 cap c4_rank '^.*rank_kernel' 3 rerank
 cap c2_b1024_gemm batch_gemm_kernel 2 batch

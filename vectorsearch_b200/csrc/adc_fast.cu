@@ -122,6 +122,13 @@ __device__ __forceinline__ unsigned int fs_word_sum(unsigned int w, unsigned int
   acc += table[(4 * J + 3) * 8192 + fs_addr<3>(lo, hi)];
   return acc;
 }
+// the same for word J split in two: codes 0-1 of the word (HALF = 0) or codes 2-3 (HALF = 1)
+template <int J, int HALF>
+__device__ __forceinline__ unsigned int fs_half_word_sum(unsigned int lo, unsigned int hi, const unsigned char* table) {
+  unsigned int acc = table[(4 * J + 2 * HALF + 0) * 8192 + fs_addr<2 * HALF + 0>(lo, hi)];
+  acc += table[(4 * J + 2 * HALF + 1) * 8192 + fs_addr<2 * HALF + 1>(lo, hi)];
+  return acc;
+}
 // byte offset of entry c inside one lane's copy of one subspace table (add s*8192 + lane*4):
 // high address byte = bits 2..6 of c, low address byte = bit 7 and bits 0..1 of c
 __host__ __device__ inline unsigned int fs_entry_offset(unsigned int c) { return ((c >> 2) & 31u) * 256u + (c & 0x83u); }
@@ -373,12 +380,37 @@ adc_fastscan_kernel(const uint8_t* __restrict__ codes, int64_t n, int K,
     const uint8_t* p0 = codes + (size_t)row0 * M;
     uint32_t w[U][MW];
     unsigned int S[U];
+    bool skip_section = false;
     if (row0 + (U - 1) * FS_THREADS < n) {  // all of this thread's rows exist (every batch but the last)
 #pragma unroll
       for (int u = 0; u < U; u++) load_row(p0 + (size_t)u * FS_THREADS * M, w[u]);
       drain();
+      if (MW == 4) {
+        // Table bytes are >= 0, so the sum over the first fourteen subspaces is a lower bound of S: when none of the
+        // warp's 256 rows has it at or below the threshold (the threshold sits near the 1e-6 quantile of S at C4; twelve
+        // subspaces were measured too weak a bound: four warp-batches in five had a row below it), the last two lookups
+        // of every row and the candidate section are skipped.
+        unsigned int pmin = 0xffffffffu;
+        unsigned int lo3[U], hi3[U];
 #pragma unroll
-      for (int u = 0; u < U; u++) S[u] = row_sum(w[u]);
+        for (int u = 0; u < U; u++) {
+          hi3[u] = (w[u][3] >> 2) & 0x1f1f1f1fu;
+          lo3[u] = (w[u][3] & 0x83838383u) | lane4x4;
+          S[u] = fs_word_sum<0>(w[u][0], lane4x4, table) + fs_word_sum<1>(w[u][1], lane4x4, table) +
+                 fs_word_sum<2>(w[u][2], lane4x4, table) + fs_half_word_sum<3, 0>(lo3[u], hi3[u], table);
+          pmin = min(pmin, S[u]);
+        }
+        Tloc = min(Tloc, ~tinv);
+        if (!__any_sync(FULL_MASK, pmin <= Tloc)) {
+          skip_section = true;
+        } else {
+#pragma unroll
+          for (int u = 0; u < U; u++) S[u] += fs_half_word_sum<3, 1>(lo3[u], hi3[u], table);
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < U; u++) S[u] = row_sum(w[u]);
+      }
     } else {
       drain();
 #pragma unroll
@@ -393,6 +425,7 @@ adc_fastscan_kernel(const uint8_t* __restrict__ codes, int64_t n, int K,
     Tloc = min(Tloc, ~tinv);
 #pragma unroll
     for (int u = 0; u < U; u++) {
+      if (skip_section) break;  // (warp-uniform)
       const bool pred = S[u] <= Tloc;
       const unsigned m = __ballot_sync(FULL_MASK, pred);
       if (m) {
