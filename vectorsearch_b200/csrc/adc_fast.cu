@@ -12,8 +12,11 @@
 //        sum_s min_s + delta * S  <=  pqApproxDistance  <=  sum_s min_s + delta * (S + M),
 //    S = sum_s q[s][code_s] an integer <= 255*M;
 //  * keeps 32 copies of the M x 256 byte table in shared memory, copy l entirely inside bank l
-//    (byte (s, c) of lane l at  s*8192 + ((c>>2)&31)*256 + (c&0x80) + l*4 + (c&3)):  lane l only ever
-//    touches bank l, so every LDS.U8 of a warp is conflict-free for ANY combination of codes;
+//    (the table sits at the FIXED shared-memory window address 0x4000; byte (s, c) of lane l at
+//    0x4000 + (s>>2)*32768 + ((c&0x7c) + (s&3))*256 + (c&0x80) + l*4 + (c&3): four subspaces interleave their
+//    256-byte lines, so bits 2..6 of a code are the high address byte where they stand, without a shift; the table
+//    address and the subspace's offset are the immediate of the load, and ONE byte permute per code assembles the rest):
+//    lane l only ever touches bank l, so every LDS.U8 of a warp is conflict-free for ANY combination of codes;
 //  * filters rows on the integer S against a device-wide threshold T that is maintained from a
 //    global histogram of S: if b* is the k-th smallest S seen so far, every row of the final
 //    top-k has S <= b* + M + 2 (the bound above plus rounding slack), so T = b* + M + 2 never
@@ -109,29 +112,48 @@ __device__ __forceinline__ unsigned int fs_addr(unsigned int lo, unsigned int hi
   asm("prmt.b32 %0, %1, %2, %3;" : "=r"(off) : "r"(lo), "r"(hi), "n"(((0xc + B) << 12) | ((0xc + B) << 8) | ((4 + B) << 4) | B));
   return off;
 }
+// One table byte: LDS.U8 [R + imm] with R the ABSOLUTE shared-memory address PRMT assembled.  (Through a C++ pointer
+// the compiler kept the table base in a register and spent an IMAD per lookup adding it -- a quarter of the loop's
+// instructions, in a loop bound by instruction issue.)
+constexpr unsigned int FS_TABLE_ADDR = 0x4000u;  // of the table inside the CTA's shared-memory window (a constant, so that
+                                                 // it can ride in the immediate of every lookup)
+template <int IMM>
+__device__ __forceinline__ unsigned int fs_lds(unsigned int addr) {
+  unsigned int v;
+  asm("ld.shared.u8 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(IMM));
+  return v;
+}
+// immediate part of the address of subspace S's entries: the table's address + the subspace's place in it
+template <int S>
+struct FsImm {
+  static constexpr int value = (int)FS_TABLE_ADDR + (S >> 2) * 32768 + (S & 3) * 256;
+};
+// high / low address bytes of the four codes of a word: TWO word-wide operations, then ONE byte permute per code
+// (both bytes of {hi, lo} are offsets from the immediate; hi <= 124 keeps the sign bit the permute replicates clear)
+__device__ __forceinline__ unsigned int fs_hi(unsigned int w) { return w & 0x7c7c7c7cu; }
+__device__ __forceinline__ unsigned int fs_lo(unsigned int w, unsigned int lane4x4) { return (w & 0x83838383u) | lane4x4; }
 // sum of the four table bytes selected by the codes of word J of a row (subspaces 4J .. 4J+3);
-// lane4x4 = lane*4 in every byte: the lane's bank enters through the low address byte, the table base
-// is uniform, so each lookup is PRMT + LDS [R + UR + imm]
+// lane4x4 = lane*4 in every byte: the lane's bank enters through the low address byte
 template <int J>
-__device__ __forceinline__ unsigned int fs_word_sum(unsigned int w, unsigned int lane4x4, const unsigned char* table) {
-  const unsigned int hi = (w >> 2) & 0x1f1f1f1fu;
-  const unsigned int lo = (w & 0x83838383u) | lane4x4;
-  unsigned int acc = table[(4 * J + 0) * 8192 + fs_addr<0>(lo, hi)];
-  acc += table[(4 * J + 1) * 8192 + fs_addr<1>(lo, hi)];
-  acc += table[(4 * J + 2) * 8192 + fs_addr<2>(lo, hi)];
-  acc += table[(4 * J + 3) * 8192 + fs_addr<3>(lo, hi)];
+__device__ __forceinline__ unsigned int fs_word_sum(unsigned int w, unsigned int lane4x4) {
+  const unsigned int hi = fs_hi(w), lo = fs_lo(w, lane4x4);
+  unsigned int acc = fs_lds<FsImm<4 * J + 0>::value>(fs_addr<0>(lo, hi));
+  acc += fs_lds<FsImm<4 * J + 1>::value>(fs_addr<1>(lo, hi));
+  acc += fs_lds<FsImm<4 * J + 2>::value>(fs_addr<2>(lo, hi));
+  acc += fs_lds<FsImm<4 * J + 3>::value>(fs_addr<3>(lo, hi));
   return acc;
 }
 // the same for word J split in two: codes 0-1 of the word (HALF = 0) or codes 2-3 (HALF = 1)
 template <int J, int HALF>
-__device__ __forceinline__ unsigned int fs_half_word_sum(unsigned int lo, unsigned int hi, const unsigned char* table) {
-  unsigned int acc = table[(4 * J + 2 * HALF + 0) * 8192 + fs_addr<2 * HALF + 0>(lo, hi)];
-  acc += table[(4 * J + 2 * HALF + 1) * 8192 + fs_addr<2 * HALF + 1>(lo, hi)];
+__device__ __forceinline__ unsigned int fs_half_word_sum(unsigned int lo, unsigned int hi) {
+  unsigned int acc = fs_lds<FsImm<4 * J + 2 * HALF + 0>::value>(fs_addr<2 * HALF + 0>(lo, hi));
+  acc += fs_lds<FsImm<4 * J + 2 * HALF + 1>::value>(fs_addr<2 * HALF + 1>(lo, hi));
   return acc;
 }
-// byte offset of entry c inside one lane's copy of one subspace table (add s*8192 + lane*4):
-// high address byte = bits 2..6 of c, low address byte = bit 7 and bits 0..1 of c
-__host__ __device__ inline unsigned int fs_entry_offset(unsigned int c) { return ((c >> 2) & 31u) * 256u + (c & 0x83u); }
+// byte offset of entry c of subspace s inside lane 0's copy, from the table's start (add lane*4)
+__host__ __device__ inline unsigned int fs_entry_offset(unsigned int s, unsigned int c) {
+  return (s >> 2) * 32768u + ((c & 0x7cu) + (s & 3u)) * 256u + (c & 0x83u);
+}
 
 // ---- LUT build: one CTA per (subspace, query) ----------------------------------------------------------
 // lut64[q][s][c] = Distances.l2Squared(query, s*subDim, centroids[s][c], 0, subDim) (buildLut,
@@ -201,8 +223,10 @@ adc_fastscan_kernel(const uint8_t* __restrict__ codes, int64_t n, int K,
   unsigned long long* cand_q = cand_all + (size_t)qi * gridDim.x * cap;
   unsigned long long* cand = cand_q + (size_t)blockIdx.x * cap;
 
-  unsigned char* table = fsm;                                                      // [M][32 lines][256 B]
-  unsigned int* s_hist = reinterpret_cast<unsigned int*>(fsm + (size_t)M * 8192);  // [FS_BINS]
+  // the table starts at window address FS_TABLE_ADDR (what lies below it, ~14 KB, is not used)
+  const unsigned int fsm_addr = smem_u32(fsm);
+  unsigned char* table = fsm + (FS_TABLE_ADDR - fsm_addr);                           // [M/4][128 lines][256 B]
+  unsigned int* s_hist = reinterpret_cast<unsigned int*>(table + (size_t)M * 8192);  // [FS_BINS]
   __shared__ unsigned int s_wsum[32];
   __shared__ unsigned int s_T, s_cnt, s_cnt2, s_last, s_nsurv;
   __shared__ long long s_next[2];
@@ -231,15 +255,16 @@ adc_fastscan_kernel(const uint8_t* __restrict__ codes, int64_t n, int K,
     s_delta = (bad || !(delta > 0.0) || !(delta > amax * 1e-9)) ? 0.0 : delta;
   }
   __syncthreads();
-  if (!(s_delta > 0.0)) {
-    // no usable byte image of this table: adc_fallback_kernel evaluates every row exactly
+  if (!(s_delta > 0.0) || fsm_addr > FS_TABLE_ADDR) {
+    // no usable byte image of this table (or, never seen, static shared memory reaching beyond the table's fixed address):
+    // adc_fallback_kernel evaluates every row exactly
     if (blockIdx.x == 0 && tid == 0) atomicExch(ctrl + FS_FLAG, 1u);
     return;
   }
   // ---- replicate the byte table: lane l's copy lives entirely in bank l ------------------------------
   {
-    // word (s, hbit, line) of the byte table holds the four codes c = hbit*128 + line*4 + {0..3}; it goes
-    // to s*8192 + line*256 + hbit*128 + l*4 for every lane l (fs_entry_offset)
+    // word (s, hbit, line) of the byte table holds the four codes c = hbit*128 + line*4 + {0..3}; it goes to
+    // fs_entry_offset(s, c) + l*4 = (s>>2)*32768 + (line*4 + (s&3))*256 + hbit*128 + l*4 for every lane l
     unsigned char* qtab = reinterpret_cast<unsigned char*>(s_hist);  // staging; the histogram is zeroed below
     const double inv_delta = 1.0 / s_delta;
     double v[(M * 256 + FS_THREADS - 1) / FS_THREADS];
@@ -261,7 +286,7 @@ adc_fastscan_kernel(const uint8_t* __restrict__ codes, int64_t n, int K,
     unsigned int* t32 = reinterpret_cast<unsigned int*>(table);
     for (int wi = tid; wi < M * 2048; wi += FS_THREADS) {
       const int l = wi & 31, rest = wi >> 5, s = rest >> 6, hbit = (rest >> 5) & 1, line = rest & 31;
-      t32[s * 2048 + line * 64 + hbit * 32 + l] = q32[rest];
+      t32[(s >> 2) * 8192 + (line * 4 + (s & 3)) * 64 + hbit * 32 + l] = q32[rest];
     }
     __syncthreads();
   }
@@ -280,8 +305,8 @@ adc_fastscan_kernel(const uint8_t* __restrict__ codes, int64_t n, int K,
   // code assembles the offset.
   const unsigned int lane4x4 = (unsigned int)(lane * 4) * 0x01010101u;
   auto row_sum = [&](const uint32_t* w) -> unsigned int {
-    unsigned int acc = fs_word_sum<0>(w[0], lane4x4, table) + fs_word_sum<1>(w[1], lane4x4, table);
-    if (MW == 4) acc += fs_word_sum<2>(w[MW - 2], lane4x4, table) + fs_word_sum<3>(w[MW - 1], lane4x4, table);
+    unsigned int acc = fs_word_sum<0>(w[0], lane4x4) + fs_word_sum<1>(w[1], lane4x4);
+    if (MW == 4) acc += fs_word_sum<2>(w[MW - 2], lane4x4) + fs_word_sum<3>(w[MW - 1], lane4x4);
     return acc;
   };
   auto load_row = [&](const uint8_t* p, uint32_t* w) {
@@ -394,10 +419,10 @@ adc_fastscan_kernel(const uint8_t* __restrict__ codes, int64_t n, int K,
         unsigned int lo3[U], hi3[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
-          hi3[u] = (w[u][3] >> 2) & 0x1f1f1f1fu;
-          lo3[u] = (w[u][3] & 0x83838383u) | lane4x4;
-          S[u] = fs_word_sum<0>(w[u][0], lane4x4, table) + fs_word_sum<1>(w[u][1], lane4x4, table) +
-                 fs_word_sum<2>(w[u][2], lane4x4, table) + fs_half_word_sum<3, 0>(lo3[u], hi3[u], table);
+          hi3[u] = fs_hi(w[u][3]);
+          lo3[u] = fs_lo(w[u][3], lane4x4);
+          S[u] = fs_word_sum<0>(w[u][0], lane4x4) + fs_word_sum<1>(w[u][1], lane4x4) +
+                 fs_word_sum<2>(w[u][2], lane4x4) + fs_half_word_sum<3, 0>(lo3[u], hi3[u]);
           pmin = min(pmin, S[u]);
         }
         Tloc = min(Tloc, ~tinv);
@@ -405,7 +430,7 @@ adc_fastscan_kernel(const uint8_t* __restrict__ codes, int64_t n, int K,
           skip_section = true;
         } else {
 #pragma unroll
-          for (int u = 0; u < U; u++) S[u] += fs_half_word_sum<3, 1>(lo3[u], hi3[u], table);
+          for (int u = 0; u < U; u++) S[u] += fs_half_word_sum<3, 1>(lo3[u], hi3[u]);
         }
       } else {
 #pragma unroll
@@ -509,7 +534,7 @@ adc_fastscan_kernel(const uint8_t* __restrict__ codes, int64_t n, int K,
   __threadfence();
 
   const bool flagged = ld_cg_u32(ctrl + FS_FLAG) != 0u;
-  ulonglong2* keys = reinterpret_cast<ulonglong2*>(fsm);  // the table is dead: M*512 sortable keys
+  ulonglong2* keys = reinterpret_cast<ulonglong2*>(table);  // the table is dead: M*512 sortable keys
   unsigned int* s_off = s_hist;                            // [gridDim.x + 1] list offsets
   const unsigned int sort_cap = M * 512;
   if (!flagged) {
@@ -668,7 +693,8 @@ int debug_adc_stats(unsigned int* out) {
 // ---- host -------------------------------------------------------------------------------------------
 bool adc_fast_supported(int M, int K) { return (M == 8 || M == 16) && K >= 1 && K <= 256; }
 
-static size_t fastscan_smem(int M) { return (size_t)M * 8192 + FS_BINS * 4; }
+// (the table sits at window address FS_TABLE_ADDR whatever lies before the dynamic region: this bound holds for any)
+static size_t fastscan_smem(int M) { return (size_t)FS_TABLE_ADDR + (size_t)M * 8192 + FS_BINS * 4; }
 
 typedef void (*FallbackKern)(const uint8_t*, int64_t, int, int, const double*, unsigned int*, int, int, TopkOut);
 
