@@ -331,7 +331,11 @@ int64_t vs_kernel_launch_count(void);
  * per query instead of a CTA per query; "batch_pairs": whether batches of more than 128 queries nominate on
  * CTA pairs (tcgen05 cta_group::2) -- 0 never, 1 wherever it fits, 2 (default) for long vectors only, where both
  * operands stream through shared memory; "batch_select_ctas" (0 = automatic) and "batch_prefetch_rounds"
- * (default 1, this device only): diagnostics of the selection kernel.  "scan_reserve_sms": SMs the one-query scan leaves free so that
+ * (default 1, this device only): diagnostics of the selection kernel.  "scan_fp16" (default 1): one or two queries
+ * against a segment that has the fp16 operand copy are nominated by a CUDA-core scan of that copy (half the bytes
+ * of the fp32 rows; ids and scores still come from the fp32 rows, bit-identical) -- 0: the fp32 streaming scan;
+ * "scan_half_ctas" (0 = automatic, 1, 2): CTAs per SM of that scan (diagnostics).
+ * "scan_reserve_sms": SMs the one-query scan leaves free so that
  * work of another stream (the next query's prologue, a collective's CTAs) runs beside it (default 0).
  * "peer_fused" (default 1): a one-query peer exchange publishes inside the merge kernel (one launch) instead
  * of a publishing kernel followed by the merge.  "peer_spin_shared" (default 0, for tests of the polling kernels on a
