@@ -4,6 +4,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import vectorsearch_b200 as vs
 from vectorsearch_b200 import _lib as L
+if os.environ.get("VS_DEV_LIB"):  # an experimental build (make BUILD=build_dev OUT=../libvsgpu_dev.so EXTRA=-D...)
+    from pathlib import Path
+    L.LIB_PATH = Path(os.environ["VS_DEV_LIB"]).resolve()
 vs.init(0); lib = vs.load()
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 100_000_000
 seg = vs.Segment.generate(42, 0, n, 128)

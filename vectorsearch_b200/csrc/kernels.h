@@ -256,7 +256,10 @@ cudaError_t launch_adc_scan(const AdcScanLaunch& L, cudaStream_t st);
 constexpr int FS_THREADS = 1024;
 constexpr int FS_U = 8;                     // rows in flight per thread (128 KB per SM: the HBM latency x bandwidth product)
 constexpr int FS_WU = 4;                    // rows per thread of the warm-up sample
-constexpr int FS_PF = 3;                     // batches requested into L2 ahead of the loads
+#ifndef VS_FS_PF
+#define VS_FS_PF 3
+#endif
+constexpr int FS_PF = VS_FS_PF;              // batches requested into L2 ahead of the loads (-DVS_FS_PF=.. for experiments)
 constexpr int FS_BINS = 4096;               // histogram bins of the integer row sum (<= 255 * 16)
 constexpr int FS_CTRL = 8;                  // control words: ticket, ~T, fallback flag
 constexpr int FS_TICKET = 0, FS_TINV = 1, FS_FLAG = 2, FS_NEXT = 3;  // FS_NEXT: dynamic batch counter
