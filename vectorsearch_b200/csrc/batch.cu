@@ -848,8 +848,11 @@ __device__ __forceinline__ void sh_stamp_cta(int) {}
 //     with a <= tau is a candidate and is scored exactly (one row per half-warp) into the register top-k of scan.cu.
 //     A row that a warp or a CTA dropped has a >= that CTA's KK-th key, so the result is complete iff every FULL list
 //     ends above tau; otherwise (rows of one cluster stored side by side, thousands of duplicates) the query goes to
-//     the exact fallback scan, like a candidate overflow of the batched selection.
-constexpr int SH_THREADS = 512;   // 16 warps when their rings fit (short vectors), else 8: the scan is latency-bound per warp
+//     the exact fallback scan, like a candidate overflow of the batched selection (the scan writes a flag per query,
+//     batch_fallback_kernel is launched behind every scan and exits at once when no flag is set).
+//   * sixteen warps per SM wherever their rings fit: as two 256-thread CTAs (k <= 16: a CTA's set-up and epilogue
+//     then overlap the neighbour's streaming) or one 512-thread CTA, else eight (long vectors); see batch_configure.
+constexpr int SH_THREADS = 512;   // the largest CTA: 16 warps (the scan is latency-bound per warp)
 constexpr int SH_MIN_THREADS = 256;
 constexpr int SH_CAND = 1024;  // candidate rows the last CTA can hold
 // CTAs per query (published lists the last CTA takes): two 256-thread CTAs per SM for short lists (k <= 16), see
