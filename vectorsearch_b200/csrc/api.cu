@@ -539,6 +539,14 @@ static int batch_wanted(const Segment* s, int nq, bool cosine) {
   return g_scan_fp16.load() != 0 && g_batch_fp16.load() != 0 ? 2 : 0;
 }
 
+// HBM a resident segment of n x d rows may grow by at its first queries (wire.cu's residency budget counts it up
+// front): the nomination coefficients of both metrics and, unless switched off, the fp16 operand copy.
+int64_t nomination_aux_bytes(int64_t n, int d) {
+  if (n < g_batch_min_rows.load() || !batch_supported(d, lanes(), false, n)) return 0;
+  const int64_t dp = (d + 7) & ~7;
+  return 2 * n * 4 + (g_batch_fp16.load() != 0 ? n * dp * 2 : 0);
+}
+
 static int plan_batch(const Segment* s, int k, bool cosine, bool half, BatchLaunch* out) {
   const int ln = lanes();
   const int go = (int)g_batch_group.load(), sp = (int)g_batch_select_ctas.load(), so = (int)g_scan_half_ctas.load();

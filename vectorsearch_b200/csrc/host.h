@@ -50,6 +50,7 @@ void set_thread_device(int cuda_dev);
 int primary_device();
 void set_error(const char* msg);  // thread-local message of vs_last_error()
 void residency_clear();            // wire.cu: forget the residency table (vs_shutdown frees the handles wholesale)
+int64_t nomination_aux_bytes(int64_t n, int d);  // api.cu: what a resident n x d segment may grow by at its first queries
 
 // ---- group.cu: one process, several GPUs (vs_init_multi) -----------------------------------------------------
 // A sharded segment is a row range split over the group's devices by ascending row range; its handle lives in a

@@ -166,7 +166,8 @@ int64_t handle_bytes(uint64_t h) {
   int64_t n = 0;
   int32_t d = 0, M = 0, K = 0;
   if (vs_segment_info(h, &n, &d, &M, &K, nullptr) != VS_OK) return -1;
-  return n * d * 4 + n * M + (int64_t)K * d * 4;
+  // rows, codes, codebook, and what the first queries add (coefficients, the fp16 operand copy: api.cu)
+  return n * d * 4 + n * M + (int64_t)K * d * 4 + nomination_aux_bytes(n, d);
 }
 }  // namespace
 
