@@ -829,9 +829,14 @@ def bench_c4(ctx, K, W):
     torch.cuda.synchronize()
     time.sleep(2.0)
     ms_adc = adc_alone()
+    # (option adc_reserve_sms: the scan leaves a few SMs to the other stream's LUT build / re-rank / exchange.  Measured at
+    # N = 1 with 4 SMs: 341 / 284 / 303 us per query at 1 / 8 / 32 per launch against 336 / 285 / 298 without -- off by default)
+    adc_reserve = int(os.environ.get("VS_ADC_RESERVE", "0"))
+    vs.set_option("adc_reserve_sms", adc_reserve)
     ms = run(1, K)
     ms_b8 = run(8, max(4, K // 4))
     ms_b32 = run(32, max(4, K // 8))
+    vs.set_option("adc_reserve_sms", 0)
     ms_adc_loaded = adc_alone()
     gbs = n * PQ_M / (ms_adc * 1e-3) / 1e9
     # end to end through the host API: query from host memory in, ids + scores out, every query
@@ -849,7 +854,7 @@ def bench_c4(ctx, K, W):
            "rows_per_gpu": n, "ms_per_query": ms, "adc_evals_per_s": n_total / (ms * 1e-3), "qps": 1e3 / ms,
            "ms_per_query_batch8": ms_b8, "adc_evals_per_s_batch8": n_total / (ms_b8 * 1e-3),
            "ms_per_query_batch32": ms_b32, "adc_evals_per_s_batch32": n_total / (ms_b32 * 1e-3),
-           "floor_ms_per_query": n * PQ_M / (hbm_peak * 1e9) * 1e3,
+           "adc_reserve_sms": adc_reserve, "floor_ms_per_query": n * PQ_M / (hbm_peak * 1e9) * 1e3,
            "streams": len(sh._streams),
            "e2e": {"ms_per_query": e2e_ms, "adc_evals_per_s": n_total / (e2e_ms * 1e-3), "h2d_bytes_per_step": DIM * 4,
                    "d2h_bytes_per_step": TOPK * 16 + 4},

@@ -335,6 +335,8 @@ int64_t vs_kernel_launch_count(void);
  * against a segment that has the fp16 operand copy are nominated by a CUDA-core scan of that copy (half the bytes
  * of the fp32 rows; ids and scores still come from the fp32 rows, bit-identical) -- 0: the fp32 streaming scan;
  * "scan_half_ctas" (0 = automatic, 1, 2): CTAs per SM of that scan (diagnostics).
+ * "adc_reserve_sms" (default 0): the same for the fast ADC scan (queries alternating between streams: the LUT build,
+ * re-rank and merge of one query run beside the scan of the next).
  * "scan_reserve_sms": SMs the one-query scan leaves free so that
  * work of another stream (the next query's prologue, a collective's CTAs) runs beside it (default 0).
  * "peer_fused" (default 1): a one-query peer exchange publishes inside the merge kernel (one launch) instead

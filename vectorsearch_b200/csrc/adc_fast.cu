@@ -731,7 +731,8 @@ cudaError_t launch_build_lut_mm(const float* centroids, int M, int K, int subDim
 }
 
 cudaError_t launch_adc_fast(const AdcFastLaunch& L, cudaStream_t st) {
-  const dim3 grid(L.grid, L.nq);
+  // (the kernel sizes everything from gridDim.x; the lists and counters were sized for L.grid CTAs)
+  const dim3 grid(L.reserve_sms > 0 && L.grid - L.reserve_sms >= 1 ? L.grid - L.reserve_sms : L.grid, L.nq);
   const int64_t stride = L.out_stride > 0 ? L.out_stride : L.k;
   count_launch();
   if (L.M == 16)

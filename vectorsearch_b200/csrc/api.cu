@@ -50,6 +50,7 @@ static std::atomic<int64_t> g_batch_pairs{2};
 static std::atomic<int64_t> g_batch_prefilter{1};           // candidate groups are pre-filtered on the fp16 copy before exact scoring
 static std::atomic<int64_t> g_pdl{1};                       // programmatic dependent launch between the kernels of one call
 static std::atomic<int64_t> g_scan_fp16{1};                 // 1: single queries nominate on the fp16 copy (half the bytes), 0: fp32 scan
+static std::atomic<int64_t> g_adc_reserve_sms{0};           // SMs the fast ADC scan leaves free (queries alternating between streams)
 static std::atomic<int64_t> g_scan_half_ctas{0};            // scan_half_kernel CTAs per SM: 0 = automatic (two where they fit), 1, 2 (diagnostics)
 static std::atomic<int64_t> g_batch_select_ctas{0};         // 0 = automatic selection CTAs per query, else 1..64 (diagnostics)
 static std::atomic<int64_t> g_batch_group{0};               // 0 = automatic rows per nomination group, else 16 / 32 / 64
@@ -505,6 +506,7 @@ static int adc_dev(cudaStream_t st, const Segment* s, const float* d_q, int nq, 
     L.codes = s->codes; L.lut64 = d_lut; L.mm = d_mm; L.nq = nq; L.fs = d_fs; L.cand = d_cand;
     L.partial = d_partial; L.ctrl = d_ticket; L.ids_out = d_ids; L.approx_out = d_approx;
     L.counts_out = d_counts; L.id_base = s->id_base; L.out_stride = out_stride;
+    L.reserve_sms = (int)g_adc_reserve_sms.load();
     CK(launch_adc_fast(L, st), "adc fast-scan launch");
     CK(launch_adc_fallback(L, st), "adc fallback launch");
     return VS_OK;
@@ -851,6 +853,11 @@ int32_t vs_set_option(const char* name, int64_t value) {
   }
   if (!strcmp(name, "scan_fp16")) {
     g_scan_fp16.store(value != 0);
+    return VS_OK;
+  }
+  if (!strcmp(name, "adc_reserve_sms")) {
+    if (value < 0 || value >= 128) return fail(VS_EINVAL, "adc_reserve_sms must be in 0..127");
+    g_adc_reserve_sms.store(value);
     return VS_OK;
   }
   if (!strcmp(name, "scan_half_ctas")) {

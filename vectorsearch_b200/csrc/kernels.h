@@ -286,6 +286,7 @@ struct AdcFastLaunch {
   int64_t id_base;
   int64_t out_stride;
   int grid;                  // scan CTAs per query
+  int reserve_sms;           // ... of which this many are not launched (room for a neighbouring stream's small kernels)
   size_t smem_bytes;
   int final_grid, final_threads;
   size_t final_smem;
